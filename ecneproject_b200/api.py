@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Same names, argument meaning and error behaviour as the Julia it stands in for (Julia is not in
+this image, so the host side above the C ABI is Python; INTEGRATION.md shows the ccall shim a Julia
+maintainer would use instead):
+
+  readR1CS(path)                      ParseR1CS.jl:50-124                  -> R1CS
+  abstraction(name, cons, sub)        R1CSConstraintSolver.jl:237-395      -> (Specials, R1CS)
+  SolveConstraintsSymbolic(...)       R1CSConstraintSolver.jl:583-1646     -> bool   (THE hot path: one
+                                                                           ecne_solve call)
+  solveWithTrustedFunctions(...)      R1CSConstraintSolver.jl:502-581      -> bool
+
+Everything that computes runs in native code: libecne_host.so (parser, abstraction) and
+libecne_b200.so (sm_100a CUDA engine).  There is no Python or CPU fallback for the solver.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _abi
+from ._abi import Problem, Result
+
+# Julia exception class -> Python exception raised by the mirror
+_STATUS_EXC = {
+    _abi.ECNE_E_BADARG: AssertionError,
+    _abi.ECNE_E_DIVZERO: ZeroDivisionError,   # DivideError
+    _abi.ECNE_E_BOUNDS: IndexError,           # BoundsError
+    _abi.ECNE_E_NODSU: NameError,             # UndefVarError(:dsu)
+    _abi.ECNE_E_CUDA: RuntimeError,
+    _abi.ECNE_E_NCCL: RuntimeError,
+    _abi.ECNE_E_UNSUPPORTED: NotImplementedError,
+    _abi.ECNE_E_NOCONVERGE: RuntimeError,
+    _abi.ECNE_E_INTERNAL: RuntimeError,
+    _abi.ECNE_E_KEYERROR: KeyError,
+    _abi.ECNE_E_IO: OSError,
+    _abi.ECNE_E_ASSERT: AssertionError,
+}
+
+_KIND_OF_NAME = {"BigMultModP": _abi.SPECIAL_BIGMULTMODP, "BigLessThan": _abi.SPECIAL_BIGLESSTHAN}
+
+
+def _raise(status, msg):
+    raise _STATUS_EXC.get(status, RuntimeError)(f"[ecne status {status}] {msg}")
+
+
+def _as_np(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype)
+
+
+class R1CS:
+    """A flattened constraint system (include/ecne_abi.h layout).  Owns its native struct."""
+
+    def __init__(self, native):
+        self._native = native  # POINTER(R1CSStruct)
+        s = native.contents
+        self.n_rows = int(s.n_rows)
+        self.n_vars = int(s.n_vars)
+        self.nnz = int(s.nnz)
+        self.seg_ptr = _as_np(s.seg_ptr, 3 * self.n_rows + 1, np.uint64)
+        self.col = _as_np(s.col, self.nnz, np.uint32)
+        self.coef = _as_np(s.coef, 4 * self.nnz, np.uint64).reshape(-1, 4)
+        self.known = _as_np(s.known, int(s.n_known), np.uint32)
+        self.targets = _as_np(s.targets, int(s.n_targets), np.uint32)
+        self.n_pub_out = int(s.n_pub_out)
+        self.n_pub_in = int(s.n_pub_in)
+        self.n_prv_in = int(s.n_prv_in)
+
+    def __len__(self):
+        return self.n_rows
+
+    def __del__(self):
+        try:
+            if self._native:
+                _abi.host_lib().ecne_r1cs_free(self._native)
+                self._native = None
+        except Exception:
+            pass
+
+
+class Specials:
+    """special_constraints (:585): a list of (name, inputs, outputs)."""
+
+    def __init__(self):
+        self._native = _abi.host_lib().ecne_specials_new()
+        self.names = []
+
+    def __len__(self):
+        return int(self._native.contents.n)
+
+    def as_list(self):
+        s = self._native.contents
+        n = int(s.n)
+        ip = _as_np(s.in_ptr, n + 1, np.uint64)
+        op = _as_np(s.out_ptr, n + 1, np.uint64)
+        iv = _as_np(s.in_, int(ip[-1]) if n else 0, np.uint32)
+        ov = _as_np(s.out, int(op[-1]) if n else 0, np.uint32)
+        return [(self.names[i], iv[int(ip[i]):int(ip[i + 1])].tolist(),
+                 ov[int(op[i]):int(op[i + 1])].tolist()) for i in range(n)]
+
+    def __del__(self):
+        try:
+            if self._native:
+                _abi.host_lib().ecne_specials_free(self._native)
+                self._native = None
+        except Exception:
+            pass
+
+
+class SolveResult:
+    """Final VariableState arrays + counters of one SolveConstraintsSymbolic call."""
+
+    def __init__(self, n_vars, full_state=False):
+        words = (n_vars + 63) // 64
+        self.n_vars = n_vars
+        self.unique_bits = np.zeros(words, dtype=np.uint64)
+        self.known_bits = np.zeros(words, dtype=np.uint64)
+        self.lb = self.ub = self.nvalues = self.values = self.abz = None
+        if full_state:
+            self.lb = np.zeros((n_vars, 4), dtype=np.uint64)
+            self.ub = np.zeros((n_vars, 4), dtype=np.uint64)
+            self.nvalues = np.zeros(n_vars, dtype=np.uint8)
+            self.values = np.zeros((n_vars, 2, 4), dtype=np.uint64)
+            self.abz = np.zeros(n_vars, dtype=np.int32)
+        self.c = Result()
+        self.c.unique_bits = self.unique_bits.ctypes.data_as(_abi.u64p)
+        self.c.known_bits = self.known_bits.ctypes.data_as(_abi.u64p)
+        if full_state:
+            self.c.lb = self.lb.ctypes.data_as(_abi.u64p)
+            self.c.ub = self.ub.ctypes.data_as(_abi.u64p)
+            self.c.nvalues = self.nvalues.ctypes.data_as(_abi.u8p)
+            self.c.values = self.values.ctypes.data_as(_abi.u64p)
+            self.c.abz = self.abz.ctypes.data_as(_abi.i32p)
+
+    @property
+    def verdict(self):
+        return bool(self.c.verdict)
+
+    def unique_bytes(self):
+        """Packed bitmap as SURVEY.md Appendix B.1 hashes it: bit (w-1)&7 of byte (w-1)>>3."""
+        return self.unique_bits.view(np.uint8)[: (self.n_vars + 7) // 8].tobytes()
+
+    def known_bytes(self):
+        return self.known_bits.view(np.uint8)[: (self.n_vars + 7) // 8].tobytes()
+
+    def counters(self):
+        c = self.c
+        return {k: getattr(c, k) for k in (
+            "n_unique_nontrivial", "n_nontrivial", "n_targets_unique", "n_unique", "outer_rounds",
+            "inner_rounds", "constraint_evals", "sweep_launches", "ms_h2d", "ms_classify",
+            "ms_solve", "ms_d2h", "ms_exchange", "ms_total", "ms_sweep")}
+
+
+class ProblemHandle:
+    """Keeps the numpy buffers an ecne_problem_t points into alive."""
+
+    def __init__(self, constraints, specials, known_variables, target_variables, num_variables,
+                 secp_solve=False, debug=False):
+        self.keep = []
+        p = Problem()
+        p.n_rows = constraints.n_rows
+        p.n_vars = num_variables
+        p.seg_ptr = self._buf(constraints.seg_ptr, np.uint64, _abi.u64p)
+        p.col = self._buf(constraints.col, np.uint32, _abi.u32p)
+        p.coef = self._buf(constraints.coef.reshape(-1), np.uint64, _abi.u64p)
+        kn = np.asarray(known_variables, dtype=np.uint32)
+        tg = np.asarray(target_variables, dtype=np.uint32)
+        p.known = self._buf(kn, np.uint32, _abi.u32p)
+        p.n_known = len(kn)
+        p.targets = self._buf(tg, np.uint32, _abi.u32p)
+        p.n_targets = len(tg)
+        sl = specials.as_list() if isinstance(specials, Specials) else list(specials or [])
+        kinds, ip, iv, op, ov = [], [0], [], [0], []
+        for name, ins, outs in sl:
+            kinds.append(_KIND_OF_NAME.get(name, _abi.SPECIAL_GENERIC))
+            iv += list(ins)
+            ov += list(outs)
+            ip.append(len(iv))
+            op.append(len(ov))
+        p.n_specials = len(sl)
+        p.sp_kind = self._buf(np.asarray(kinds, dtype=np.int32), np.int32, _abi.i32p)
+        p.sp_in_ptr = self._buf(np.asarray(ip, dtype=np.uint64), np.uint64, _abi.u64p)
+        p.sp_in = self._buf(np.asarray(iv, dtype=np.uint32), np.uint32, _abi.u32p)
+        p.sp_out_ptr = self._buf(np.asarray(op, dtype=np.uint64), np.uint64, _abi.u64p)
+        p.sp_out = self._buf(np.asarray(ov, dtype=np.uint32), np.uint32, _abi.u32p)
+        p.secp_solve = int(bool(secp_solve))
+        p.debug = int(bool(debug))
+        self.c = p
+        self.n_vars = int(num_variables)
+        self.n_rows = int(constraints.n_rows)
+        self.nnz = int(constraints.nnz)
+
+    def _buf(self, arr, dtype, ptype):
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        if a.size == 0:
+            a = np.zeros(1, dtype=dtype)
+        self.keep.append(a)
+        return a.ctypes.data_as(ptype)
+
+
+# ---------------------------------------------------------------------------------------------
+# the mirrored reference functions
+# ---------------------------------------------------------------------------------------------
+def readR1CS(filename):
+    """ParseR1CS.readR1CS (ParseR1CS.jl:50).  The reference returns (equations, knowns, outs,
+    num_wires+1); here those four live on the returned R1CS (.known, .targets, .n_vars)."""
+    lib = _abi.host_lib()
+    out = C.POINTER(_abi.R1CSStruct)()
+    st = lib.ecne_read_r1cs(str(filename).encode(), C.byref(out))
+    if st != 0:
+        _raise(st, lib.ecne_host_last_error().decode())
+    return R1CS(out)
+
+
+def abstraction(function_name, constraints, sub_equation, specials=None):
+    """abstraction() (R1CSConstraintSolver.jl:237).  known_inputs / known_outputs of the trusted
+    circuit travel inside `sub_equation`.  Returns (specials, reduced)."""
+    lib = _abi.host_lib()
+    sp = specials if specials is not None else Specials()
+    red = C.POINTER(_abi.R1CSStruct)()
+    n = C.c_uint64(0)
+    kind = _KIND_OF_NAME.get(function_name, _abi.SPECIAL_GENERIC)
+    st = lib.ecne_abstraction(kind, constraints._native, sub_equation._native, C.byref(red),
+                              sp._native, C.byref(n))
+    if st != 0:
+        _raise(st, lib.ecne_host_last_error().decode())
+    sp.names += [function_name] * int(n.value)
+    return sp, R1CS(red)
+
+
+_initialised = False
+
+
+def _engine():
+    global _initialised
+    lib = _abi.engine_lib()
+    if not _initialised:
+        import os
+        dev = int(os.environ.get("LOCAL_RANK", os.environ.get("ECNE_DEVICE", "0")))
+        st = lib.ecne_init(dev)
+        if st != 0:
+            _raise(st, lib.ecne_last_error().decode())
+        _initialised = True
+    return lib
+
+
+last_result = None
+
+
+def SolveConstraintsSymbolic(constraints, special_constraints, known_variables, debug=False,
+                             target_variables=(), num_variables=-1, input_sym="default.sym",
+                             secp_solve=False, full_state=False):
+    """R1CSConstraintSolver.jl:583-1646, executed by the CUDA engine through ecne_solve.
+
+    Returns function_good (:1645).  The full per-wire state of the call is kept in
+    `ecneproject_b200.api.last_result` (a SolveResult) for the report path (:1599-1644)."""
+    global last_result
+    lib = _engine()
+    ph = ProblemHandle(constraints, special_constraints, known_variables, target_variables,
+                       num_variables, secp_solve, debug)
+    res = SolveResult(int(num_variables), full_state=full_state)
+    st = lib.ecne_solve(C.byref(ph.c), C.byref(res.c))
+    if st != 0:
+        _raise(st, lib.ecne_last_error().decode())
+    last_result = res
+    print(f"Solved for {res.c.n_unique_nontrivial} variables out of {res.c.n_nontrivial} total variables")
+    print(f"Solved for {res.c.n_targets_unique} target variables out of {len(target_variables)} total target variables")
+    return res.verdict
+
+
+def prepare(input_r1cs, trusted_r1cs=(), trusted_r1cs_names=(), printRes=False):
+    """Lines :513-544 of solveWithTrustedFunctions: parse, sort trusted longest-first, abstract.
+    Returns (reduced R1CS, Specials, main R1CS)."""
+    assert len(trusted_r1cs) == len(trusted_r1cs_names)
+    main = readR1CS(input_r1cs)
+    function_list = [(trusted_r1cs_names[i], readR1CS(trusted_r1cs[i])) for i in range(len(trusted_r1cs))]
+    function_list.sort(key=lambda x: -len(x[1]))  # stable, longest first (:527)
+    specials = Specials()
+    reduced = main
+    for name, sub in function_list:
+        if printRes:
+            print("called abstraction")
+        specials, reduced = abstraction(name, reduced, sub, specials)
+    return reduced, specials, main
+
+
+def solveWithTrustedFunctions(input_r1cs, input_r1cs_name, trusted_r1cs=(), trusted_r1cs_names=(),
+                              debug=False, printRes=True, abstractionOnly=False, input_sym="",
+                              secp_solve=False):
+    """solveWithTrustedFunctions (R1CSConstraintSolver.jl:502-581)."""
+    a = time.time()
+    reduced, specials, main = prepare(input_r1cs, list(trusted_r1cs), list(trusted_r1cs_names), printRes)
+    if abstractionOnly:
+        print(specials.as_list())
+        return True
+    print("time to prep inputs", round(time.time() - a, 3), "seconds")
+    result = SolveConstraintsSymbolic(reduced, specials, main.known, debug, main.targets,
+                                      main.n_vars, input_sym, secp_solve)
+    if result:
+        if len(trusted_r1cs) != 0:
+            if printRes:
+                print("R1CS function " + input_r1cs_name +
+                      " has sound constraints assuming trusted functions " + ", ".join(trusted_r1cs_names))
+        elif printRes:
+            print("R1CS function " + input_r1cs_name + " has sound constraints (No trusted functions needed!)")
+        return True
+    if printRes:
+        print("R1CS function " + input_r1cs_name + " has potentially unsound constraints")
+    return False

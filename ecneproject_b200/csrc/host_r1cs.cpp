@@ -1,0 +1,479 @@
+// host_r1cs.cpp — .r1cs -> flattened CSR loader and the trusted-function abstraction pass.
+//
+// Host-side callers of the hot path; behaviour follows
+//   /root/reference/src/ParseR1CS.jl:50-124          (readR1CS)
+//   /root/reference/src/R1CSConstraintSolver.jl:205-395  (checkNonZeroValues, hash_r1cs_equation,
+//                                                        abstraction)
+// but the data structure is the engine's CSR (include/ecne_abi.h), not per-row hash maps.
+#include "ecne_host.h"
+#include "ecne_abi.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+// BN254 scalar prime, little-endian limbs (R1CSConstraintSolver.jl:21-22).
+const uint64_t P[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL,
+                       0x30644e72e131a029ULL};
+
+struct Fe {
+  uint64_t l[4];
+  bool operator==(const Fe& o) const { return memcmp(l, o.l, 32) == 0; }
+  bool operator!=(const Fe& o) const { return !(*this == o); }
+  bool is_zero() const { return (l[0] | l[1] | l[2] | l[3]) == 0; }
+};
+inline int cmp(const Fe& a, const Fe& b) {
+  for (int i = 3; i >= 0; --i) {
+    if (a.l[i] != b.l[i]) return a.l[i] < b.l[i] ? -1 : 1;
+  }
+  return 0;
+}
+inline bool geq_p(const uint64_t* a) {
+  for (int i = 3; i >= 0; --i) {
+    if (a[i] != P[i]) return a[i] > P[i];
+  }
+  return true;
+}
+inline void sub_p(uint64_t* a) {
+  unsigned __int128 borrow = 0;
+  for (int i = 0; i < 4; ++i) {
+    unsigned __int128 d = (unsigned __int128)a[i] - P[i] - (uint64_t)borrow;
+    a[i] = (uint64_t)d;
+    borrow = (d >> 64) & 1;
+  }
+}
+
+inline uint32_t rd32(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+inline uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+template <class T>
+T* dup_vec(const std::vector<T>& v) {
+  T* p = (T*)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
+  if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+  return p;
+}
+
+ecne_r1cs_t* make_r1cs(const std::vector<uint64_t>& seg, const std::vector<uint32_t>& col,
+                       const std::vector<uint64_t>& coef, const std::vector<uint32_t>& known,
+                       const std::vector<uint32_t>& targets, uint64_t n_vars) {
+  ecne_r1cs_t* r = (ecne_r1cs_t*)calloc(1, sizeof(ecne_r1cs_t));
+  r->n_rows = (seg.size() - 1) / 3;
+  r->n_vars = n_vars;
+  r->nnz = col.size();
+  r->seg_ptr = dup_vec(seg);
+  r->col = dup_vec(col);
+  r->coef = dup_vec(coef);
+  r->known = dup_vec(known);
+  r->n_known = known.size();
+  r->targets = dup_vec(targets);
+  r->n_targets = targets.size();
+  return r;
+}
+
+}  // namespace
+
+extern "C" const char* ecne_host_last_error(void) { return g_err.c_str(); }
+
+extern "C" void ecne_r1cs_free(ecne_r1cs_t* r) {
+  if (!r) return;
+  free(r->seg_ptr);
+  free(r->col);
+  free(r->coef);
+  free(r->known);
+  free(r->targets);
+  free(r);
+}
+
+// ParseR1CS.jl:50-124.  Offsets below are 0-based; the Julia is 1-based.
+extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t** out) {
+  if (!arr || !out) return fail(ECNE_E_BADARG, "null argument");
+  *out = nullptr;
+  auto need = [&](uint64_t off, uint64_t n) { return off + n <= len; };
+  if (!need(0, 12)) return fail(ECNE_E_BOUNDS, "file shorter than the 12-byte header");
+  if (rd32(arr + 4) != 1) return fail(ECNE_E_ASSERT, "version != 1 (ParseR1CS.jl:58)");
+  uint32_t sections = rd32(arr + 8);
+  if (sections != 3) return fail(ECNE_E_ASSERT, "nSections != 3 (ParseR1CS.jl:62)");
+  uint64_t cur = 12;
+  uint64_t starts[4] = {0, 0, 0, 0};
+  bool have[4] = {false, false, false, false};
+  for (uint32_t i = 0; i < sections; ++i) {
+    if (!need(cur, 12)) return fail(ECNE_E_BOUNDS, "truncated section table");
+    uint32_t ty = rd32(arr + cur);
+    if (ty < 1 || ty > 3) return fail(ECNE_E_ASSERT, "section type outside 1..3 (ParseR1CS.jl:69)");
+    starts[ty] = cur;
+    have[ty] = true;
+    uint64_t sz = rd64(arr + cur + 4);
+    cur += 12 + sz;
+  }
+  if (!have[1] || !have[2]) return fail(ECNE_E_BOUNDS, "header or constraint section missing");
+  uint64_t s1 = starts[1] + 12;
+  if (!need(s1, 4)) return fail(ECNE_E_BOUNDS, "truncated header section");
+  uint32_t field_size = rd32(arr + s1);
+  s1 += 4;
+  s1 += field_size;  // the prime is read but never checked (ParseR1CS.jl:84)
+  if (!need(s1, 28)) return fail(ECNE_E_BOUNDS, "truncated header section");
+  uint32_t n_wires = rd32(arr + s1);
+  uint32_t pub_out = rd32(arr + s1 + 4);
+  uint32_t pub_in = rd32(arr + s1 + 8);
+  uint32_t prv_in = rd32(arr + s1 + 12);
+  uint64_t n_labels = rd64(arr + s1 + 16);
+  uint32_t n_cons = rd32(arr + s1 + 24);
+
+  uint64_t s2 = starts[2] + 12;
+  std::vector<uint64_t> seg;
+  seg.reserve(3 * (size_t)n_cons + 1);
+  std::vector<uint32_t> col;
+  std::vector<uint64_t> coef;
+  uint64_t guess = (len - std::min<uint64_t>(len, s2)) / 36 + 3 * (uint64_t)n_cons;
+  col.reserve(guess);
+  coef.reserve(guess * 4);
+  seg.push_back(0);
+  std::vector<std::pair<uint32_t, uint32_t>> order;  // (wire, position) for duplicate handling
+  for (uint32_t r = 0; r < n_cons; ++r) {
+    for (int form = 0; form < 3; ++form) {
+      if (!need(s2, 4)) return fail(ECNE_E_BOUNDS, "truncated constraint section");
+      uint32_t n = rd32(arr + s2);
+      s2 += 4;
+      if (!need(s2, (uint64_t)n * 36)) return fail(ECNE_E_BOUNDS, "truncated constraint section");
+      size_t base = col.size();
+      for (uint32_t t = 0; t < n; ++t) {
+        uint32_t idx = rd32(arr + s2);
+        uint64_t c[4];
+        memcpy(c, arr + s2 + 4, 32);  // 32 bytes hard-coded (ParseR1CS.jl:109)
+        s2 += 36;
+        while (geq_p(c)) sub_p(c);  // F(coeff) reduces (ParseR1CS.jl:111)
+        col.push_back(idx + 1);
+        coef.insert(coef.end(), c, c + 4);
+      }
+      if (n == 0) {  // explicit zero on key 1 (ParseR1CS.jl:113-115)
+        col.push_back(1);
+        coef.insert(coef.end(), 4, 0ULL);
+      } else if (n > 1) {
+        // cur_eq[idx+1] = ... : a repeated wire overwrites the earlier value (Dict assignment).
+        bool dup = false;
+        if (n <= 8) {
+          for (uint32_t i = 0; i < n && !dup; ++i)
+            for (uint32_t j = i + 1; j < n; ++j)
+              if (col[base + i] == col[base + j]) { dup = true; break; }
+        } else {
+          order.clear();
+          for (uint32_t i = 0; i < n; ++i) order.push_back({col[base + i], i});
+          std::sort(order.begin(), order.end());
+          for (uint32_t i = 1; i < n; ++i)
+            if (order[i].first == order[i - 1].first) { dup = true; break; }
+        }
+        if (dup) {
+          std::map<uint32_t, uint32_t> last;  // wire -> last position
+          for (uint32_t i = 0; i < n; ++i) last[col[base + i]] = i;
+          std::vector<uint32_t> ncol;
+          std::vector<uint64_t> ncoef;
+          for (auto& kv : last) {
+            ncol.push_back(kv.first);
+            ncoef.insert(ncoef.end(), coef.begin() + 4 * (base + kv.second),
+                         coef.begin() + 4 * (base + kv.second) + 4);
+          }
+          col.resize(base);
+          coef.resize(4 * base);
+          col.insert(col.end(), ncol.begin(), ncol.end());
+          coef.insert(coef.end(), ncoef.begin(), ncoef.end());
+        }
+      }
+      seg.push_back(col.size());
+    }
+  }
+  std::vector<uint32_t> known, targets;
+  known.push_back(1);
+  for (uint64_t i = 2 + (uint64_t)pub_out; i <= 1 + (uint64_t)pub_out + pub_in + prv_in; ++i)
+    known.push_back((uint32_t)i);
+  for (uint64_t i = 2; i <= 1 + (uint64_t)pub_out; ++i) targets.push_back((uint32_t)i);
+  ecne_r1cs_t* r = make_r1cs(seg, col, coef, known, targets, (uint64_t)n_wires + 1);
+  r->n_pub_out = pub_out;
+  r->n_pub_in = pub_in;
+  r->n_prv_in = prv_in;
+  r->field_size = field_size;
+  r->n_labels = n_labels;
+  *out = r;
+  return ECNE_OK;
+}
+
+extern "C" int ecne_read_r1cs(const char* path, ecne_r1cs_t** out) {
+  if (!path || !out) return fail(ECNE_E_BADARG, "null argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(ECNE_E_IO, std::string("cannot open ") + path);
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<uint8_t> buf((size_t)sz);
+  size_t got = sz ? fread(buf.data(), 1, (size_t)sz, f) : 0;
+  fclose(f);
+  if (got != (size_t)sz) return fail(ECNE_E_IO, std::string("short read on ") + path);
+  return ecne_read_r1cs_mem(buf.data(), buf.size(), out);
+}
+
+// ------------------------------------------------------------------------------------------
+// specials container
+// ------------------------------------------------------------------------------------------
+extern "C" ecne_specials_t* ecne_specials_new(void) {
+  ecne_specials_t* s = (ecne_specials_t*)calloc(1, sizeof(ecne_specials_t));
+  s->cap_n = 16;
+  s->cap_in = s->cap_out = 64;
+  s->kind = (int32_t*)malloc(s->cap_n * sizeof(int32_t));
+  s->in_ptr = (uint64_t*)malloc((s->cap_n + 1) * sizeof(uint64_t));
+  s->out_ptr = (uint64_t*)malloc((s->cap_n + 1) * sizeof(uint64_t));
+  s->in = (uint32_t*)malloc(s->cap_in * sizeof(uint32_t));
+  s->out = (uint32_t*)malloc(s->cap_out * sizeof(uint32_t));
+  s->in_ptr[0] = s->out_ptr[0] = 0;
+  return s;
+}
+extern "C" void ecne_specials_free(ecne_specials_t* s) {
+  if (!s) return;
+  free(s->kind);
+  free(s->in_ptr);
+  free(s->out_ptr);
+  free(s->in);
+  free(s->out);
+  free(s);
+}
+namespace {
+void specials_push(ecne_specials_t* s, int32_t kind, const std::vector<uint32_t>& in,
+                   const std::vector<uint32_t>& out) {
+  if (s->n + 1 > s->cap_n) {
+    s->cap_n *= 2;
+    s->kind = (int32_t*)realloc(s->kind, s->cap_n * sizeof(int32_t));
+    s->in_ptr = (uint64_t*)realloc(s->in_ptr, (s->cap_n + 1) * sizeof(uint64_t));
+    s->out_ptr = (uint64_t*)realloc(s->out_ptr, (s->cap_n + 1) * sizeof(uint64_t));
+  }
+  uint64_t ni = s->in_ptr[s->n], no = s->out_ptr[s->n];
+  while (ni + in.size() > s->cap_in) {
+    s->cap_in *= 2;
+    s->in = (uint32_t*)realloc(s->in, s->cap_in * sizeof(uint32_t));
+  }
+  while (no + out.size() > s->cap_out) {
+    s->cap_out *= 2;
+    s->out = (uint32_t*)realloc(s->out, s->cap_out * sizeof(uint32_t));
+  }
+  if (!in.empty()) memcpy(s->in + ni, in.data(), in.size() * sizeof(uint32_t));
+  if (!out.empty()) memcpy(s->out + no, out.data(), out.size() * sizeof(uint32_t));
+  s->kind[s->n] = kind;
+  s->n += 1;
+  s->in_ptr[s->n] = ni + in.size();
+  s->out_ptr[s->n] = no + out.size();
+}
+
+// hash_r1cs_equation (:228-235): the row's three sorted coefficient multisets, zeros dropped,
+// concatenated WITHOUT separators.  Only equality of hashes is ever used (:262), so any hash of
+// that list works; rows are verified form-by-form afterwards (:301-329).
+struct RowSig {
+  std::vector<Fe> list;  // sortedA ++ sortedB ++ sortedC, non-zero
+  uint64_t h;
+};
+uint64_t mix(uint64_t h, uint64_t v) {
+  h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+  h *= 0xff51afd7ed558ccdULL;
+  return h ^ (h >> 33);
+}
+void nonzero_sorted(const ecne_r1cs_t* r, uint64_t seg, std::vector<Fe>& out) {
+  size_t b = out.size();
+  for (uint64_t t = r->seg_ptr[seg]; t < r->seg_ptr[seg + 1]; ++t) {
+    Fe f;
+    memcpy(f.l, r->coef + 4 * t, 32);
+    if (!f.is_zero()) out.push_back(f);
+  }
+  std::sort(out.begin() + b, out.end(), [](const Fe& x, const Fe& y) { return cmp(x, y) < 0; });
+}
+uint64_t row_hash(const ecne_r1cs_t* r, uint64_t row, std::vector<Fe>& tmp) {
+  tmp.clear();
+  for (int f = 0; f < 3; ++f) nonzero_sorted(r, 3 * row + f, tmp);
+  uint64_t h = 0x1234567ULL + tmp.size();
+  for (auto& x : tmp)
+    for (int i = 0; i < 4; ++i) h = mix(h, x.l[i]);
+  return h;
+}
+// checkNonZeroValues (:205-226): same multiset of non-zero values.
+bool same_nonzero_multiset(const ecne_r1cs_t* a, uint64_t sa, const ecne_r1cs_t* b, uint64_t sb,
+                           std::vector<Fe>& t1, std::vector<Fe>& t2) {
+  t1.clear();
+  t2.clear();
+  nonzero_sorted(a, sa, t1);
+  nonzero_sorted(b, sb, t2);
+  if (t1.size() != t2.size()) return false;
+  for (size_t i = 0; i < t1.size(); ++i)
+    if (t1[i] != t2[i]) return false;
+  return true;
+}
+
+// appearance signature of one variable: [(slot, coeff)...] in slot order (:282-292, :305-310).
+typedef std::vector<std::pair<uint32_t, Fe>> Sig;
+int cmp_sig(const Sig& a, const Sig& b) {
+  size_t n = std::min(a.size(), b.size());
+  for (size_t i = 0; i < n; ++i) {
+    if (a[i].first != b[i].first) return a[i].first < b[i].first ? -1 : 1;
+    int c = cmp(a[i].second, b[i].second);
+    if (c) return c;
+  }
+  if (a.size() != b.size()) return a.size() < b.size() ? -1 : 1;
+  return 0;
+}
+struct VarSig {
+  uint32_t var;
+  Sig sig;
+};
+// Build the sorted (by signature; ties by wire id — Julia's Dict order is unpinned, SURVEY.md §7
+// hard part 7) appearance list of rows [row0, row0+n) of r.
+void appearance(const ecne_r1cs_t* r, uint64_t row0, uint64_t n, std::vector<VarSig>& out) {
+  std::unordered_map<uint32_t, uint32_t> idx;
+  out.clear();
+  uint32_t slot = 0;
+  for (uint64_t j = 0; j < n; ++j) {
+    for (int f = 0; f < 3; ++f) {
+      ++slot;
+      uint64_t s = 3 * (row0 + j) + f;
+      for (uint64_t t = r->seg_ptr[s]; t < r->seg_ptr[s + 1]; ++t) {
+        Fe c;
+        memcpy(c.l, r->coef + 4 * t, 32);
+        if (c.is_zero()) continue;
+        uint32_t v = r->col[t];
+        auto it = idx.find(v);
+        uint32_t k;
+        if (it == idx.end()) {
+          k = (uint32_t)out.size();
+          idx.emplace(v, k);
+          out.push_back(VarSig{v, {}});
+        } else {
+          k = it->second;
+        }
+        out[k].sig.push_back({slot, c});
+      }
+    }
+  }
+  std::sort(out.begin(), out.end(), [](const VarSig& a, const VarSig& b) {
+    int c = cmp_sig(a.sig, b.sig);
+    if (c) return c < 0;
+    return a.var < b.var;
+  });
+}
+}  // namespace
+
+// abstraction (:237-395).
+extern "C" int ecne_abstraction(int32_t kind, const ecne_r1cs_t* cons, const ecne_r1cs_t* sub,
+                                ecne_r1cs_t** reduced, ecne_specials_t* specials,
+                                uint64_t* n_matches) {
+  if (!cons || !sub || !reduced || !specials) return fail(ECNE_E_BADARG, "null argument");
+  *reduced = nullptr;
+  const uint64_t N = cons->n_rows, n = sub->n_rows;
+  std::vector<Fe> t1, t2;
+  std::vector<uint64_t> hc(N), hs(n);
+  for (uint64_t i = 0; i < N; ++i) hc[i] = row_hash(cons, i, t1);
+  for (uint64_t i = 0; i < n; ++i) hs[i] = row_hash(sub, i, t1);
+
+  // candidates: the first n-1 row hashes line up (:259-270)
+  std::vector<uint64_t> candidates;
+  if (N + 1 >= n + 1 && N >= n) {
+    for (uint64_t i = 0; i + n <= N; ++i) {
+      bool ok = true;
+      for (uint64_t j = 0; j + 1 < n; ++j) {
+        if (hc[i + j] != hs[j]) {
+          ok = false;
+          break;
+        }
+      }
+      if (ok) candidates.push_back(i);
+    }
+  }
+  std::vector<VarSig> orig, curv;
+  appearance(sub, 0, n, orig);
+  struct Match {
+    uint64_t start;
+    std::unordered_map<uint32_t, uint32_t> map;  // sub wire -> main wire
+  };
+  std::vector<Match> matches;
+  for (uint64_t i : candidates) {
+    bool works = true;
+    for (uint64_t j = 0; j < n && works; ++j)
+      for (int f = 0; f < 3; ++f)
+        if (!same_nonzero_multiset(cons, 3 * (i + j) + f, sub, 3 * j + f, t1, t2)) {
+          works = false;
+          break;
+        }
+    if (!works) continue;
+    appearance(cons, i, n, curv);
+    if (curv.size() != orig.size()) continue;
+    for (size_t k = 0; k < curv.size(); ++k)
+      if (cmp_sig(curv[k].sig, orig[k].sig) != 0) {
+        works = false;
+        break;
+      }
+    if (!works) continue;
+    Match m;
+    m.start = i;
+    for (size_t k = 0; k < curv.size(); ++k) m.map.emplace(orig[k].var, curv[k].var);
+    matches.push_back(std::move(m));
+  }
+
+  // the walk (:357-388), including the stall after an overlapping match (:370)
+  std::vector<uint64_t> seg;
+  std::vector<uint32_t> col;
+  std::vector<uint64_t> coef;
+  seg.push_back(0);
+  size_t cur = 0;
+  uint64_t i = 0, added = 0;
+  while (i < N) {
+    if (cur >= matches.size() || i != matches[cur].start) {
+      for (int f = 0; f < 3; ++f) {
+        uint64_t s = 3 * i + f;
+        col.insert(col.end(), cons->col + cons->seg_ptr[s], cons->col + cons->seg_ptr[s + 1]);
+        coef.insert(coef.end(), cons->coef + 4 * cons->seg_ptr[s],
+                    cons->coef + 4 * cons->seg_ptr[s + 1]);
+        seg.push_back(col.size());
+      }
+      i += 1;
+    } else {
+      std::vector<uint32_t> in, outv;
+      for (uint64_t k = 0; k < sub->n_known; ++k) {
+        uint32_t x = sub->known[k];
+        if (x == 1) continue;
+        auto it = matches[cur].map.find(x);
+        if (it == matches[cur].map.end())
+          return fail(ECNE_E_KEYERROR, "KeyError: trusted input wire never appears (:381)");
+        in.push_back(it->second);
+      }
+      for (uint64_t k = 0; k < sub->n_targets; ++k) {
+        auto it = matches[cur].map.find(sub->targets[k]);
+        if (it == matches[cur].map.end())
+          return fail(ECNE_E_KEYERROR, "KeyError: trusted output wire never appears (:382)");
+        outv.push_back(it->second);
+      }
+      specials_push(specials, kind, in, outv);
+      ++added;
+      i += n;
+      cur += 1;
+    }
+  }
+  std::vector<uint32_t> known(cons->known, cons->known + cons->n_known);
+  std::vector<uint32_t> targets(cons->targets, cons->targets + cons->n_targets);
+  ecne_r1cs_t* r = make_r1cs(seg, col, coef, known, targets, cons->n_vars);
+  r->n_pub_out = cons->n_pub_out;
+  r->n_pub_in = cons->n_pub_in;
+  r->n_prv_in = cons->n_prv_in;
+  r->field_size = cons->field_size;
+  r->n_labels = cons->n_labels;
+  *reduced = r;
+  if (n_matches) *n_matches = added;
+  return ECNE_OK;
+}

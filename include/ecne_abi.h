@@ -1,0 +1,142 @@
+/*
+ * ecne_abi.h — C ABI of libecne_b200.so, the B200-native R1CS soundness-propagation engine.
+ *
+ * Drop-in boundary: the ONE call
+ *     result = SolveConstraintsSymbolic(reduced, specials, knowns_main, debug, outs_main,
+ *                                       num_variables, input_sym, secp_solve)
+ * at /root/reference/src/R1CSConstraintSolver.jl:552 (signature :583-592, returns Bool :1645).
+ * The reference has no FFI of its own; a Julia maintainer keeps readR1CS (ParseR1CS.jl:50-124),
+ * abstraction (:237-395) and solveWithTrustedFunctions (:502-581) untouched and replaces the body
+ * of that one call with `ccall((:ecne_solve, "libecne_b200"), ...)` — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, caller owns every buffer, the library never keeps a host pointer after return;
+ *   - wire ids are the reference's 1-based keys (ParseR1CS.jl:111 stores `wire+1`), wire 1 is the
+ *     constant one;  n_vars == num_variables == nWires+1 (ParseR1CS.jl:123);
+ *   - field elements are 4 little-endian uint64 limbs of the canonical integer in [0, p), p = the
+ *     BN254 scalar prime (R1CSConstraintSolver.jl:21-24) — exactly GFElem.d;
+ *   - a constraint row is three sparse linear forms A, B, C (ParseR1CS.jl:13-25).  They are passed
+ *     as ONE term array in the .r1cs on-disk order (ParseR1CS.jl:100-117): segment 3*i+0/1/2 is
+ *     A/B/C of row i and covers terms seg_ptr[3*i+s] .. seg_ptr[3*i+s+1]-1.  EVERY stored key of
+ *     the Julia DefaultDict is passed, explicit zeros included (the parser stores `[1]=F(0)` for an
+ *     empty form, ParseR1CS.jl:113-115; :641, :1001, :1083, :1512 look at stored zeros);
+ *   - all entry points return 0 on success or a negative ecne_status; ecne_last_error() gives text.
+ *     There is no CPU fallback: without a usable CUDA device every compute entry fails with
+ *     ECNE_E_CUDA.
+ */
+#ifndef ECNE_ABI_H
+#define ECNE_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECNE_ABI_VERSION 1
+
+/* Status codes.  The negative ones mirror the exception classes the reference can raise on this
+ * path (SURVEY.md §5 / §8b "Errors"); the Julia shim rethrows them. */
+typedef enum ecne_status {
+  ECNE_OK = 0,
+  ECNE_E_BADARG = -1,      /* AssertionError-class: malformed problem                       */
+  ECNE_E_DIVZERO = -2,     /* DivideError: divexact(_, 0) at :919-920 or :1467                */
+  ECNE_E_BOUNDS = -3,      /* BoundsError: variable_states[-1] at :916, short lists at :762   */
+  ECNE_E_NODSU = -4,       /* UndefVarError(:dsu) at :762 when secp_solve == false            */
+  ECNE_E_CUDA = -5,        /* CUDA runtime failure / no device / extension not built          */
+  ECNE_E_NCCL = -6,        /* multi-GPU exchange failure                                      */
+  ECNE_E_UNSUPPORTED = -7, /* a linear-system group larger than ECNE_P2_KMAX triggered        */
+  ECNE_E_NOCONVERGE = -8,  /* round guard hit (the reference would loop forever)              */
+  ECNE_E_INTERNAL = -9
+} ecne_status;
+
+/* Special-constraint kinds: only these two names are looked at by the solver (:751, :755). */
+#define ECNE_SPECIAL_GENERIC 0
+#define ECNE_SPECIAL_BIGMULTMODP 1
+#define ECNE_SPECIAL_BIGLESSTHAN 2
+
+/* Largest k for which the k x k "slow_det" of the linear-system sweep (:1389-1400) is evaluated. */
+#define ECNE_P2_KMAX 8
+
+typedef struct ecne_problem {
+  uint64_t n_rows;         /* length(constraints)                                   (:584) */
+  uint64_t n_vars;         /* num_variables                                         (:589) */
+  const uint64_t* seg_ptr; /* [3*n_rows + 1] offsets into col/coef                         */
+  const uint32_t* col;     /* [nnz] 1-based wire id of each stored term                    */
+  const uint64_t* coef;    /* [nnz*4] canonical limbs, zeros allowed                       */
+  const uint32_t* known;   /* known_variables (:586), contains wire 1   (ParseR1CS.jl:123) */
+  uint64_t n_known;
+  const uint32_t* targets; /* target_variables (:588)                                      */
+  uint64_t n_targets;
+  uint64_t n_specials;        /* special_constraints (:585): (name, inputs, outputs)       */
+  const int32_t* sp_kind;     /* [n_specials] ECNE_SPECIAL_*                               */
+  const uint64_t* sp_in_ptr;  /* [n_specials + 1]                                          */
+  const uint32_t* sp_in;      /* inputs, 1-based wires                                     */
+  const uint64_t* sp_out_ptr; /* [n_specials + 1]                                          */
+  const uint32_t* sp_out;     /* outputs                                                   */
+  int32_t secp_solve;         /* :591                                                      */
+  int32_t debug;              /* :587 — accepted, ignored (printing stays in the host)     */
+} ecne_problem_t;
+
+typedef struct ecne_result {
+  int32_t verdict;       /* function_good (:1594-1597, :1645): 1 sound, 0 potentially unsound */
+  int32_t status;        /* copy of the return code                                         */
+  /* Per-wire final VariableState (:135-160).  unique_bits/known_bits are required; the rest may
+   * be NULL.  Bit (w-1)&63 of word (w-1)>>6 belongs to wire w. */
+  uint64_t* unique_bits; /* [(n_vars+63)/64]  .unique                                       */
+  uint64_t* known_bits;  /* [(n_vars+63)/64]  .is_known                                     */
+  uint64_t* lb;          /* [n_vars*4]        .lb.d                                          */
+  uint64_t* ub;          /* [n_vars*4]        .ub.d                                          */
+  uint8_t* nvalues;      /* [n_vars]          length(.values)                                */
+  uint64_t* values;      /* [n_vars*8]        .values[1..2].d                                */
+  int32_t* abz;          /* [n_vars]          .abz (1-based wire or -1)                      */
+  /* counters (:1558-1597 prints the first four) */
+  uint64_t n_unique_nontrivial; /* "Solved for X variables ..."                              */
+  uint64_t n_nontrivial;        /* "... out of Y total variables"                            */
+  uint64_t n_targets_unique;
+  uint64_t n_unique;            /* popcount(unique_bits)                                     */
+  uint64_t outer_rounds;        /* iterations of the `while true` at :706                    */
+  uint64_t inner_rounds;        /* Jacobi rounds of the single-row rule sweep                */
+  uint64_t constraint_evals;    /* rows visited by sweep/phase kernels        */
+  uint64_t sweep_launches;      /* kernels launched by this solve                            */
+  double ms_h2d, ms_classify, ms_solve, ms_d2h, ms_exchange, ms_total;
+  double ms_sweep;              /* device time inside the single-row sweep kernel only       */
+} ecne_result_t;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int ecne_version(void);
+/* Bind this process to CUDA device `device` (one process per GPU).  Idempotent. */
+int ecne_init(int device);
+void ecne_shutdown(void);
+const char* ecne_last_error(void);
+
+/* ---- the drop-in call: host buffers in, host buffers out (H2D + all rounds + D2H) -------- */
+int ecne_solve(const ecne_problem_t* problem, ecne_result_t* result);
+
+/* ---- resident variant: upload + classify once, solve many times (bench `value` leg) ------ */
+typedef struct ecne_resident ecne_resident_t;
+int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out);
+int ecne_solve_resident(ecne_resident_t* r, ecne_result_t* result);
+void ecne_free_resident(ecne_resident_t* r);
+
+/* ---- row-range sharding across the GPUs of one box ------------------------
+ * Every rank is given the WHOLE problem by its host and keeps rows [lo, hi) chosen by nnz
+ * balance; wire state is replicated and the per-round update records are exchanged with one
+ * ncclAllGather.  unique_id is the 128-byte ncclUniqueId made by rank 0 (ecne_dist_unique_id)
+ * and broadcast by the host (torch.distributed / MPI / Julia Distributed). */
+int ecne_dist_unique_id(uint8_t out[128]);
+int ecne_dist_init(int rank, int world, const uint8_t unique_id[128]);
+int ecne_dist_rank(void);
+int ecne_dist_world(void);
+
+/* ---- engine knobs (testing / benchmarking) ---------------------------------------------- */
+int ecne_set_option(const char* key, int64_t value);
+
+/* ---- field-arithmetic known-answer hooks: run the device Montgomery code on n elements ----
+ * op: 0 add, 1 sub, 2 mul, 3 inv (b ignored), 4 neg (b ignored).  a, b, out: [n*4] canonical. */
+int ecne_fr_batch(int op, uint64_t n, const uint64_t* a, const uint64_t* b, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECNE_ABI_H */

@@ -1,0 +1,70 @@
+/*
+ * ecne_host.h — C ABI of libecne_host.so: the host-side callers either side of the hot path
+ * (SURVEY.md §8f "next" rows 1 and 2).  Pure C++ inside, no CUDA.
+ *
+ *   ecne_read_r1cs      replaces ParseR1CS.readR1CS          (/root/reference/src/ParseR1CS.jl:50-124)
+ *   ecne_abstraction    replaces abstraction()               (src/R1CSConstraintSolver.jl:237-395)
+ *
+ * Both produce the flattened layout ecne_abi.h consumes, so that a host (Julia via ccall, Python
+ * via ctypes) can go file -> ecne_problem_t without materialising per-row hash maps.
+ */
+#ifndef ECNE_HOST_H
+#define ECNE_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECNE_E_KEYERROR (-10) /* KeyError at R1CSConstraintSolver.jl:381-382 */
+#define ECNE_E_IO (-11)       /* SystemError opening the file (ParseR1CS.jl:52-53) */
+#define ECNE_E_ASSERT (-12)   /* AssertionError at ParseR1CS.jl:58,62,69 */
+
+/* A parsed constraint system; every array is owned by the library (ecne_r1cs_free). */
+typedef struct ecne_r1cs {
+  uint64_t n_rows;    /* nConstraints                         (ParseR1CS.jl:96)  */
+  uint64_t n_vars;    /* num_wires + 1                        (ParseR1CS.jl:123) */
+  uint64_t nnz;       /* stored terms, explicit zeros included                   */
+  uint64_t* seg_ptr;  /* [3*n_rows+1]                                            */
+  uint32_t* col;      /* [nnz] wire+1                         (ParseR1CS.jl:111) */
+  uint64_t* coef;     /* [nnz*4] canonical limbs, reduced mod p (F(coeff))       */
+  uint32_t* known;    /* [1; 2+nOut .. 1+nOut+nPubIn+nPrvIn]  (ParseR1CS.jl:123) */
+  uint64_t n_known;
+  uint32_t* targets;  /* [2 .. 1+nOut]                                           */
+  uint64_t n_targets;
+  uint32_t n_pub_out, n_pub_in, n_prv_in, field_size;
+  uint64_t n_labels;
+} ecne_r1cs_t;
+
+int ecne_read_r1cs(const char* path, ecne_r1cs_t** out);
+int ecne_read_r1cs_mem(const uint8_t* buf, uint64_t len, ecne_r1cs_t** out);
+void ecne_r1cs_free(ecne_r1cs_t* r);
+
+/* The list of (name, inputs, outputs) "special constraints" (:357-384), CSR over specials. */
+typedef struct ecne_specials {
+  uint64_t n;
+  int32_t* kind;     /* ECNE_SPECIAL_* from the trusted function's name */
+  uint64_t* in_ptr;  /* [n+1] */
+  uint32_t* in;
+  uint64_t* out_ptr; /* [n+1] */
+  uint32_t* out;
+  uint64_t cap_n, cap_in, cap_out; /* private */
+} ecne_specials_t;
+
+ecne_specials_t* ecne_specials_new(void);
+void ecne_specials_free(ecne_specials_t* s);
+
+/* One abstraction() call: find every window of `constraints` isomorphic to `sub`, replace it by a
+ * special constraint of kind `kind` (appended to `specials`), return the reduced system in
+ * *reduced (its known/targets/n_vars are copied from `constraints`).  `n_matches` receives the
+ * number of specials added by this call. */
+int ecne_abstraction(int32_t kind, const ecne_r1cs_t* constraints, const ecne_r1cs_t* sub,
+                     ecne_r1cs_t** reduced, ecne_specials_t* specials, uint64_t* n_matches);
+
+const char* ecne_host_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECNE_HOST_H */
