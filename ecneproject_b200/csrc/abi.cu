@@ -1,0 +1,370 @@
+// abi.cu — the C ABI of include/ecne_abi.h and the outer fixpoint loop
+// (/root/reference/src/R1CSConstraintSolver.jl:706-1556) that drives the kernels.
+#include <nccl.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "engine_host.h"
+
+using namespace ecne;
+
+namespace {
+
+struct Global {
+  bool inited = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // options
+  long long max_rounds = 1000000;     // per P1 launch
+  long long max_outer = 100000;
+  // dist
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+} G;
+
+int fail(int status, const std::string& msg) {
+  G.err = msg;
+  return status;
+}
+
+#define CKA(x)                                                                              \
+  do {                                                                                      \
+    cudaError_t e_ = (x);                                                                   \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(ECNE_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_));            \
+  } while (0)
+
+const char* status_text(int st) {
+  switch (st) {
+    case ECNE_E_DIVZERO: return "DivideError: divexact by zero (R1CSConstraintSolver.jl:919-920 / :1467)";
+    case ECNE_E_BOUNDS: return "BoundsError (R1CSConstraintSolver.jl:916 variable_states[-1] / :762)";
+    case ECNE_E_NODSU: return "UndefVarError: dsu not defined (R1CSConstraintSolver.jl:762; secp_solve=false)";
+    case ECNE_E_UNSUPPORTED: return "a linear-system group with k > ECNE_P2_KMAX unknowns triggered";
+    case ECNE_E_NOCONVERGE: return "round guard hit: the propagation did not reach a fixpoint";
+    case ECNE_E_INTERNAL: return "internal error (record overflow or set-hash collision)";
+    default: return "error";
+  }
+}
+
+}  // namespace
+
+struct ecne_resident {
+  Resident r;
+};
+
+extern "C" int ecne_version(void) { return ECNE_ABI_VERSION; }
+
+extern "C" const char* ecne_last_error(void) { return G.err.c_str(); }
+
+extern "C" int ecne_init(int device) {
+  if (G.inited && G.device == device) return ECNE_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(ECNE_E_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                 cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(ECNE_E_BADARG, "device index out of range");
+  CKA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CKA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(ECNE_E_CUDA, std::string("libecne_b200 is built for sm_100a only; device is ") + prop.name);
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  if (!coop) return fail(ECNE_E_CUDA, "device lacks cooperative launch");
+  if (G.stream) cudaStreamDestroy(G.stream);
+  CKA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  G.device = device;
+  G.inited = true;
+  return ECNE_OK;
+}
+
+extern "C" void ecne_shutdown(void) {
+  if (G.comm) {
+    ncclCommDestroy(G.comm);
+    G.comm = nullptr;
+  }
+  if (G.stream) {
+    cudaStreamDestroy(G.stream);
+    G.stream = nullptr;
+  }
+  G.inited = false;
+  G.device = -1;
+  G.rank = 0;
+  G.world = 1;
+}
+
+extern "C" int ecne_set_option(const char* key, int64_t value) {
+  if (!key) return fail(ECNE_E_BADARG, "null key");
+  std::string k(key);
+  if (k == "max_rounds")
+    G.max_rounds = value;
+  else if (k == "max_outer")
+    G.max_outer = value;
+  else
+    return fail(ECNE_E_BADARG, "unknown option " + k);
+  return ECNE_OK;
+}
+
+extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out) {
+  if (!out) return fail(ECNE_E_BADARG, "null out pointer");
+  *out = nullptr;
+  if (!G.inited) {
+    int st = ecne_init(0);
+    if (st) return st;
+  }
+  ecne_resident* h = new ecne_resident();
+  h->r.stream = G.stream;
+  std::string err;
+  int st = build_resident(problem, &h->r, err);
+  if (st != ECNE_OK) {
+    h->r.arena.release();
+    if (h->r.h_status) cudaFreeHost(h->r.h_status);
+    if (h->r.h_counts) cudaFreeHost(h->r.h_counts);
+    delete h;
+    return fail(st, err);
+  }
+  *out = h;
+  return ECNE_OK;
+}
+
+extern "C" void ecne_free_resident(ecne_resident_t* h) {
+  if (!h) return;
+  h->r.arena.release();
+  if (h->r.h_status) cudaFreeHost(h->r.h_status);
+  if (h->r.h_counts) cudaFreeHost(h->r.h_counts);
+  delete h;
+}
+
+extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
+  if (!h || !res || !res->unique_bits || !res->known_bits) return fail(ECNE_E_BADARG, "null argument");
+  Resident& R = h->r;
+  Dev& d = R.d;
+  cudaStream_t s = R.stream;
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventCreate(&e2);
+  cudaEventRecord(e0, s);
+  CKA(launch_reset(d, s));
+  const int grid = p1_grid_size(G.device);
+  uint64_t outer = 0, launches = 0, phase_evals = 0;
+  unsigned long long rounds_total = 0, evals_total = 0;
+  int status = ECNE_OK;
+  std::string err;
+  float ms_sweep = 0;
+  cudaEvent_t s0, s1;
+  cudaEventCreate(&s0);
+  cudaEventCreate(&s1);
+  while (true) {
+    ++outer;
+    // P0 / P0'
+    launch_p0(d, s);
+    // P1: single-row rules to a fixpoint
+    cudaEventRecord(s0, s);
+    CKA(launch_p1(d, 0, (unsigned int)G.max_rounds, grid, s));
+    cudaEventRecord(s1, s);
+    // P2: linear systems
+    launch_p2_scan(d, 0, s);
+    CKA(cudaMemcpyAsync(R.h_status, d.st, sizeof(Status), cudaMemcpyDeviceToHost, s));
+    CKA(cudaStreamSynchronize(s));
+    {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, s0, s1);
+      ms_sweep += ms;
+    }
+    launches += 4;
+    if (R.h_status->err) {
+      status = -(int)R.h_status->err;
+      break;
+    }
+    if (R.h_status->rec_overflow) {
+      status = ECNE_E_INTERNAL;
+      break;
+    }
+    uint32_t n_cand = R.h_status->p2_cand;
+    if (n_cand) {
+      int st = p2_sort(&R, n_cand, err);
+      if (st) {
+        status = st;
+        break;
+      }
+      launch_p2_groups(d, 0, n_cand, d.p2_key, d.p2_row, s);
+      CKA(cudaMemsetAsync(&d.st->p2_cand, 0, sizeof(unsigned int), s));
+      launches += 4;
+    }
+    launch_replay(d, 0, s);
+    // P3: ABZ tags, P4: IsZero pairs
+    launch_p3(d, 0, s);
+    launch_p4(d, 0, s);
+    launch_replay(d, 0, s);
+    launches += 7;
+    phase_evals += 3ull * d.N;
+    CKA(cudaMemcpyAsync(R.h_status, d.st, sizeof(Status), cudaMemcpyDeviceToHost, s));
+    CKA(cudaMemsetAsync(&d.st->changed, 0, sizeof(unsigned long long), s));
+    CKA(cudaStreamSynchronize(s));
+    if (R.h_status->err) {
+      status = -(int)R.h_status->err;
+      break;
+    }
+    if (R.h_status->rec_overflow) {
+      status = ECNE_E_INTERNAL;
+      break;
+    }
+    rounds_total = R.h_status->rounds;
+    evals_total = R.h_status->evals;
+    if (R.h_status->changed == 0) break;  // successful_steps did not move (:708-711)
+    if ((long long)outer >= G.max_outer) {
+      status = ECNE_E_NOCONVERGE;
+      break;
+    }
+  }
+  cudaEventRecord(e1, s);
+  res->status = status;
+  if (status != ECNE_OK) {
+    cudaStreamSynchronize(s);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    cudaEventDestroy(s0);
+    cudaEventDestroy(s1);
+    return fail(status, err.empty() ? status_text(status) : err);
+  }
+  // verdict + D2H
+  launch_finalize(d, 0, R.d_ubits, R.d_kbits, R.d_counts, s);
+  const size_t words = (R.n_vars + 63) / 64;
+  CKA(cudaMemcpyAsync(res->unique_bits, R.d_ubits, words * 8, cudaMemcpyDeviceToHost, s));
+  CKA(cudaMemcpyAsync(res->known_bits, R.d_kbits, words * 8, cudaMemcpyDeviceToHost, s));
+  CKA(cudaMemcpyAsync(R.h_counts, R.d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  if (res->lb || res->ub || res->nvalues || res->values) {
+    Arena t;
+    fr::u256 *dl = nullptr, *du = nullptr, *dv = nullptr;
+    uint8_t* dn = nullptr;
+    const size_t V = R.n_vars;
+    if (res->lb) CKA(t.alloc(&dl, V));
+    if (res->ub) CKA(t.alloc(&du, V));
+    if (res->values) CKA(t.alloc(&dv, 2 * V));
+    if (res->nvalues) CKA(t.alloc(&dn, V));
+    launch_export(d, 0, dl, du, dn, dv, s);
+    if (dl) CKA(cudaMemcpyAsync(res->lb, dl, V * 32, cudaMemcpyDeviceToHost, s));
+    if (du) CKA(cudaMemcpyAsync(res->ub, du, V * 32, cudaMemcpyDeviceToHost, s));
+    if (dv) CKA(cudaMemcpyAsync(res->values, dv, V * 64, cudaMemcpyDeviceToHost, s));
+    if (dn) CKA(cudaMemcpyAsync(res->nvalues, dn, V, cudaMemcpyDeviceToHost, s));
+    CKA(cudaStreamSynchronize(s));
+    t.release();
+  }
+  if (res->abz) CKA(cudaMemcpyAsync(res->abz, d.abz + 1, R.n_vars * 4, cudaMemcpyDeviceToHost, s));
+  cudaEventRecord(e2, s);
+  CKA(cudaStreamSynchronize(s));
+  CKA(cudaGetLastError());
+  float ms_solve = 0, ms_d2h = 0;
+  cudaEventElapsedTime(&ms_solve, e0, e1);
+  cudaEventElapsedTime(&ms_d2h, e1, e2);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  cudaEventDestroy(s0);
+  cudaEventDestroy(s1);
+  res->n_unique = R.h_counts[0];
+  res->n_nontrivial = R.h_counts[1];
+  res->n_unique_nontrivial = R.h_counts[2];
+  res->n_targets_unique = R.h_counts[3];
+  res->verdict = (R.h_counts[3] == R.n_targets) ? 1 : 0;
+  res->outer_rounds = outer;
+  res->inner_rounds = rounds_total;
+  res->constraint_evals = evals_total + phase_evals;
+  res->sweep_launches = launches;
+  res->ms_h2d = R.ms_h2d;
+  res->ms_classify = R.ms_classify;
+  res->ms_solve = ms_solve;
+  res->ms_d2h = ms_d2h;
+  res->ms_exchange = 0;
+  res->ms_sweep = ms_sweep;
+  res->ms_total = R.ms_h2d + R.ms_classify + ms_solve + ms_d2h;
+  return ECNE_OK;
+}
+
+extern "C" int ecne_solve(const ecne_problem_t* problem, ecne_result_t* result) {
+  if (!problem || !result) return fail(ECNE_E_BADARG, "null argument");
+  auto t0 = std::chrono::steady_clock::now();
+  ecne_resident_t* h = nullptr;
+  int st = ecne_upload(problem, &h);
+  if (st != ECNE_OK) {
+    result->status = st;
+    return st;
+  }
+  st = ecne_solve_resident(h, result);
+  ecne_free_resident(h);
+  auto t1 = std::chrono::steady_clock::now();
+  if (st == ECNE_OK) result->ms_total = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  return st;
+}
+
+// ---- sharding (wired up in dist.cu-less form: NCCL communicator owned here) ---------------------
+extern "C" int ecne_dist_unique_id(uint8_t out[128]) {
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return fail(ECNE_E_NCCL, "ncclGetUniqueId failed");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out, &id, 128);
+  return ECNE_OK;
+}
+extern "C" int ecne_dist_init(int rank, int world, const uint8_t unique_id[128]) {
+  if (!G.inited) return fail(ECNE_E_CUDA, "call ecne_init first");
+  if (world < 1 || rank < 0 || rank >= world) return fail(ECNE_E_BADARG, "bad rank/world");
+  if (G.comm) {
+    ncclCommDestroy(G.comm);
+    G.comm = nullptr;
+  }
+  G.rank = rank;
+  G.world = world;
+  if (world == 1) return ECNE_OK;
+  ncclUniqueId id;
+  memcpy(&id, unique_id, 128);
+  if (ncclCommInitRank(&G.comm, world, id, rank) != ncclSuccess)
+    return fail(ECNE_E_NCCL, "ncclCommInitRank failed");
+  return ECNE_OK;
+}
+extern "C" int ecne_dist_rank(void) { return G.rank; }
+extern "C" int ecne_dist_world(void) { return G.world; }
+
+// ---- field known-answer hook --------------------------------------------------------------------
+__global__ void k_fr_batch(int op, uint64_t n, const fr::u256* a, const fr::u256* b, fr::u256* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fr::u256 x = a[i], y = b ? b[i] : fr::make_u256(0, 0, 0, 0), r;
+  switch (op) {
+    case 0: r = fr::add(x, y); break;
+    case 1: r = fr::sub(x, y); break;
+    case 2: r = fr::from_mont(fr::mul(fr::to_mont(x), fr::to_mont(y))); break;
+    case 3: r = fr::is_zero(x) ? x : fr::from_mont(fr::inv_mont(fr::to_mont(x))); break;
+    case 4: r = fr::neg(x); break;
+    case 5: r = fr::neg_div(x, y); break;  // divexact(-x, y)
+    default: r = x;
+  }
+  out[i] = r;
+}
+extern "C" int ecne_fr_batch(int op, uint64_t n, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  if (!G.inited) {
+    int st = ecne_init(0);
+    if (st) return st;
+  }
+  if (!a || !out) return fail(ECNE_E_BADARG, "null argument");
+  fr::u256 *da = nullptr, *db = nullptr, *dout = nullptr;
+  Arena t;
+  CKA(t.alloc(&da, n));
+  CKA(t.alloc(&dout, n));
+  CKA(cudaMemcpy(da, a, n * 32, cudaMemcpyHostToDevice));
+  if (b) {
+    CKA(t.alloc(&db, n));
+    CKA(cudaMemcpy(db, b, n * 32, cudaMemcpyHostToDevice));
+  }
+  if (n) k_fr_batch<<<(unsigned int)((n + 127) / 128), 128>>>(op, n, da, db, dout);
+  CKA(cudaDeviceSynchronize());
+  CKA(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
+  t.release();
+  return ECNE_OK;
+}

@@ -1,0 +1,835 @@
+// setup.cu — upload + one-shot classification of a problem (the static half of every rule,
+// SURVEY.md Appendix D): streams the full 36-byte CSR terms once, does all field arithmetic
+// (Montgomery inverse for -intercept/slope, pattern tests against +-2^i mod p), and lays the rows out
+// for the sweep kernels (non-zero terms only; C terms of linear rows sorted by |fold(coef)|).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstring>
+
+#include "engine_host.h"
+
+namespace ecne {
+
+#define LONG_T 32u          // rows with more non-zero terms than this get a whole warp
+#define N_CONST 255u        // 2^k-1 (k = 0..253) and p-1
+#define C3_INLINE_MAX 255u  // longer bit-decomposition candidates go through the 2^i mod p table
+
+#define CK(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e_ = (x);                                                          \
+    if (e_ != cudaSuccess) {                                                       \
+      err = std::string(#x) + ": " + cudaGetErrorString(e_);                       \
+      return ECNE_E_CUDA;                                                          \
+    }                                                                              \
+  } while (0)
+
+struct Raw {  // the problem as uploaded (explicit zeros included)
+  uint32_t N, V;
+  uint64_t nnz;
+  const unsigned long long* seg;  // [3N+1]
+  const uint32_t* col;
+  const fr::u256* coef;
+};
+
+__global__ void k_keep(Raw r, uint32_t* keep) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > r.nnz) return;
+  keep[t] = (t < r.nnz && !fr::is_zero(r.coef[t])) ? 1u : 0u;
+}
+__global__ void k_seg(Raw r, const uint32_t* pos, uint32_t* seg_nz) {
+  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > 3ull * r.N) return;
+  seg_nz[s] = pos[r.seg[s]];
+}
+
+struct ABScan {
+  uint32_t nA, nB, v, maxA, bkey;
+  bool multi;
+  fr::u256 slope_a, icpt_a, slope_b, icpt_b;
+};
+__device__ inline void scan_ab(const Raw& r, uint32_t row, ABScan& o, bool& bad) {
+  o.nA = o.nB = o.v = o.maxA = o.bkey = 0;
+  o.multi = false;
+  o.slope_a = o.icpt_a = o.slope_b = o.icpt_b = fr::make_u256(0, 0, 0, 0);
+  for (int f = 0; f < 2; ++f) {
+    for (uint64_t t = r.seg[3ull * row + f]; t < r.seg[3ull * row + f + 1]; ++t) {
+      uint32_t w = r.col[t];
+      if (w < 1 || w > r.V) {
+        bad = true;
+        continue;
+      }
+      fr::u256 c = r.coef[t];
+      if (fr::is_zero(c)) continue;
+      if (f == 0) {
+        o.nA++;
+      } else {
+        o.nB++;
+        o.bkey = w;
+      }
+      if (w == 1) {
+        if (f == 0)
+          o.icpt_a = c;
+        else
+          o.icpt_b = c;
+      } else {
+        if (f == 0 && w > o.maxA) o.maxA = w;
+        if (o.v == 0) o.v = w;
+        if (o.v != w) {
+          o.multi = true;
+        } else if (f == 0) {
+          o.slope_a = c;
+        } else {
+          o.slope_b = c;
+        }
+      }
+    }
+  }
+}
+
+struct CScan {
+  uint32_t nC, stC, n_non1, x, n_one, n_mone, key_one, key_mone;
+  bool key1_stored;
+  fr::u256 c1, cx;
+};
+__device__ inline void scan_c(const Raw& r, uint32_t row, CScan& o, bool& bad) {
+  o.nC = o.n_non1 = o.x = o.n_one = o.n_mone = o.key_one = o.key_mone = 0;
+  o.key1_stored = false;
+  o.c1 = o.cx = fr::make_u256(0, 0, 0, 0);
+  uint64_t b = r.seg[3ull * row + 2], e = r.seg[3ull * row + 3];
+  o.stC = (uint32_t)(e - b);
+  for (uint64_t t = b; t < e; ++t) {
+    uint32_t w = r.col[t];
+    if (w < 1 || w > r.V) {
+      bad = true;
+      continue;
+    }
+    fr::u256 c = r.coef[t];
+    if (w == 1) {
+      o.key1_stored = true;
+      o.c1 = c;
+    }
+    if (fr::is_zero(c)) continue;
+    o.nC++;
+    if (w != 1) {
+      o.n_non1++;
+      o.x = w;
+      o.cx = c;
+    }
+    if (fr::is_one(c)) {
+      o.n_one++;
+      o.key_one = w;
+    } else if (fr::is_minus_one(c)) {
+      o.n_mone++;
+      o.key_mone = w;
+    }
+  }
+}
+
+// exponent e if v == 2^e (as an integer), else -1
+__device__ __forceinline__ int log2_exact(const fr::u256& v) {
+  if (!fr::is_pow2(v)) return -1;
+  return fr::bitlen(v) - 1;
+}
+
+// Bit-decomposition pattern test (:999-1013) for l <= C3_INLINE_MAX, where 2^i < p for every i used.
+// returns bit0: values == {1} U {-2^i},  bit1: values == {-1} U {2^i}   (i = 0..l-2)
+__device__ inline int c3_pattern_small(const Raw& r, uint32_t row, uint32_t l) {
+  uint64_t b = r.seg[3ull * row + 2], e = r.seg[3ull * row + 3];
+  unsigned long long m1[4] = {0, 0, 0, 0}, m2[4] = {0, 0, 0, 0};
+  int ones = 0, mones = 0;
+  bool ok1 = true, ok2 = true;
+  for (uint64_t t = b; t < e; ++t) {
+    fr::u256 c = r.coef[t];
+    // T1 membership
+    if (fr::is_one(c)) {
+      ones++;
+    } else {
+      fr::u256 n = fr::neg(c);
+      int ex = log2_exact(n);
+      if (ex < 0 || (uint32_t)ex + 1 >= l || ((m1[ex >> 6] >> (ex & 63)) & 1))
+        ok1 = false;
+      else
+        m1[ex >> 6] |= 1ULL << (ex & 63);
+    }
+    // T2 membership
+    if (fr::is_minus_one(c)) {
+      mones++;
+    } else {
+      int ex = log2_exact(c);
+      if (ex < 0 || (uint32_t)ex + 1 >= l || ((m2[ex >> 6] >> (ex & 63)) & 1))
+        ok2 = false;
+      else
+        m2[ex >> 6] |= 1ULL << (ex & 63);
+    }
+  }
+  return ((ok1 && ones == 1) ? 1 : 0) | ((ok2 && mones == 1) ? 2 : 0);
+}
+
+struct Counters {
+  unsigned int n2a, n2b, n_long, max_c, n_c3_long, bad;
+};
+
+__global__ void k_classify(Raw r, uint32_t* rflags, RowAux* aux, Counters* cnt, uint32_t* c3_long) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r.N) return;
+  bool bad = false;
+  ABScan ab;
+  CScan cs;
+  scan_ab(r, row, ab, bad);
+  scan_c(r, row, cs, bad);
+  if (bad) {
+    cnt->bad = 1;
+    rflags[row] = 0;
+    return;
+  }
+  uint32_t rf = 0;
+  RowAux a;
+  a.w1 = a.w2 = a.w3 = a.w4 = a.w5 = a.val_idx = 0;
+  a.rank_a = a.rank_b = 0;
+  const bool linear = ab.nA == 0 && ab.nB == 0;
+  if (linear) rf |= RF_LINEAR;
+  if (cs.nC == 0) {
+    rf |= RF_CEMPTY;
+    // Case 2a statics
+    if (ab.v == 0) {
+      rf |= RF_2A_NOVAR;
+    } else if (!ab.multi) {
+      rf |= RF_2A;
+      a.w1 = ab.v;
+      if (fr::is_zero(ab.slope_a) || fr::is_zero(ab.slope_b)) {
+        rf |= RF_2A_DIVZ;
+      } else {
+        // roots {0,1} without dividing: root == 0 <=> intercept == 0, root == 1 <=> intercept + slope == 0
+        bool a0 = fr::is_zero(ab.icpt_a), b0 = fr::is_zero(ab.icpt_b);
+        bool a1 = fr::is_zero(fr::add(ab.icpt_a, ab.slope_a));
+        bool b1 = fr::is_zero(fr::add(ab.icpt_b, ab.slope_b));
+        if ((a0 && b1) || (a1 && b0)) rf |= RF_2A_BOOL;
+        atomicAdd(&cnt->n2a, 1u);
+      }
+    }
+    // ABZ statics
+    if (ab.nB == 1 && ab.nA <= 2) {
+      rf |= RF_P3;
+      a.w3 = ab.bkey;
+      a.w4 = ab.maxA;
+      if (ab.maxA == 0) rf |= RF_P3_DIVZ;
+    }
+  }
+  if (linear) {
+    if (cs.n_non1 == 1) {
+      rf |= RF_2B;
+      a.w1 = cs.x;
+      atomicAdd(&cnt->n2b, 1u);
+    }
+    const bool inserted_zero = (rf & RF_2B) && !cs.key1_stored;  // c[1] read inserts a zero (:962)
+    const uint32_t l = cs.nC;
+    if (l > 0 && cs.stC == l && !inserted_zero) {
+      if (l <= C3_INLINE_MAX) {
+        int pat = c3_pattern_small(r, row, l);
+        if (pat) {
+          rf |= RF_C3;
+          if (pat & 2) {
+            rf |= RF_C3_FLIP;       // (:1001) is tested first
+            a.w2 = cs.key_mone;     // coefficient 1 after negation
+            a.w5 = cs.key_one;
+          } else {
+            a.w2 = cs.key_one;
+          }
+          if (l == 2) rf |= RF_C3_L2;
+          if (l - 1 >= 254) rf |= RF_C3_TOPBIG;
+        }
+      } else {
+        c3_long[atomicAdd(&cnt->n_c3_long, 1u)] = row;
+      }
+    }
+    if (cs.nC < 3 && cs.stC == 2 && cs.n_one == 1 && cs.n_mone == 1) rf |= RF_4A;
+    if (cs.nC < 4 && cs.stC == 3 && cs.n_one == 1 && cs.n_mone == 2 && cs.key_one == 1) rf |= RF_4B;
+  }
+  // IsZero pair statics (:1493-1536), row i with row i+1
+  if (row + 1 < r.N && cs.nC == 2) {
+    bool bad2 = false;
+    ABScan nb;
+    CScan nc;
+    scan_ab(r, row + 1, nb, bad2);
+    scan_c(r, row + 1, nc, bad2);
+    if (!bad2 && nc.nC == 0 && nb.nB == 1 && nb.bkey != 1) {
+      uint32_t vk = nb.bkey;
+      bool ok = true;
+      // every non-constant key of C_i is vk
+      for (uint64_t t = r.seg[3ull * row + 2]; t < r.seg[3ull * row + 3]; ++t) {
+        if (fr::is_zero(r.coef[t])) continue;
+        uint32_t w = r.col[t];
+        if (w != 1 && w != vk) ok = false;
+      }
+      // a_i == a_{i+1} as stored dictionaries (:1512)
+      uint64_t b0 = r.seg[3ull * row], e0 = r.seg[3ull * row + 1];
+      uint64_t b1 = r.seg[3ull * row + 3], e1 = r.seg[3ull * row + 4];
+      if (e0 - b0 != e1 - b1) ok = false;
+      for (uint64_t t = b0; ok && t < e0; ++t) {
+        bool found = false;
+        for (uint64_t u = b1; u < e1; ++u)
+          if (r.col[u] == r.col[t] && fr::eq(r.coef[u], r.coef[t])) {
+            found = true;
+            break;
+          }
+        if (!found) ok = false;
+      }
+      if (ok) {
+        rf |= RF_P4;
+        a.w4 = vk;
+      }
+    }
+  }
+  uint32_t tot = ab.nA + ab.nB + cs.nC;
+  if (tot > LONG_T) {
+    rf |= RF_LONG;
+    atomicAdd(&cnt->n_long, 1u);
+  }
+  atomicMax(&cnt->max_c, cs.nC);
+  rflags[row] = rf;
+  aux[row] = a;
+}
+
+// Long bit-decomposition candidates: one warp per row, exponents looked up in the sorted table of
+// 2^i mod p (i < tab_n).  smem bitmask of seen exponents per warp.
+struct Pow2Entry {
+  fr::u256 v;
+  uint32_t e;
+  uint32_t pad[7];
+};
+__device__ inline int pow2_lookup(const Pow2Entry* tab, uint32_t n, const fr::u256& v) {
+  int lo = 0, hi = (int)n - 1;
+  while (lo <= hi) {
+    int mid = (lo + hi) >> 1;
+    int c = fr::cmp(tab[mid].v, v);
+    if (c == 0) return (int)tab[mid].e;
+    if (c < 0)
+      lo = mid + 1;
+    else
+      hi = mid - 1;
+  }
+  return -1;
+}
+__global__ void k_classify_c3_long(Raw r, uint32_t* rflags, RowAux* aux, const uint32_t* list,
+                                   uint32_t n_list, const Pow2Entry* tab, uint32_t tab_n,
+                                   uint32_t mask_words) {
+  extern __shared__ unsigned int smem[];
+  const uint32_t warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  if (wid >= n_list) return;
+  unsigned int* m1 = smem + (size_t)warp_in_block * 2 * mask_words;
+  unsigned int* m2 = m1 + mask_words;
+  for (uint32_t i = lane; i < 2 * mask_words; i += 32) m1[i] = 0;
+  __syncwarp();
+  const uint32_t row = list[wid];
+  const uint64_t b = r.seg[3ull * row + 2], e = r.seg[3ull * row + 3];
+  const uint32_t l = (uint32_t)(e - b);
+  uint32_t ones = 0, mones = 0, k_one = 0, k_mone = 0;
+  bool ok1 = true, ok2 = true;
+  for (uint64_t t = b + lane; t < e; t += 32) {
+    fr::u256 c = r.coef[t];
+    if (fr::is_one(c)) {
+      ones++;
+      k_one = r.col[t];
+    } else {
+      int ex = pow2_lookup(tab, tab_n, fr::neg(c));
+      if (ex < 0 || (uint32_t)ex + 1 >= l) {
+        ok1 = false;
+      } else if (atomicOr(m1 + (ex >> 5), 1u << (ex & 31)) & (1u << (ex & 31))) {
+        ok1 = false;
+      }
+    }
+    if (fr::is_minus_one(c)) {
+      mones++;
+      k_mone = r.col[t];
+    } else {
+      int ex = pow2_lookup(tab, tab_n, c);
+      if (ex < 0 || (uint32_t)ex + 1 >= l) {
+        ok2 = false;
+      } else if (atomicOr(m2 + (ex >> 5), 1u << (ex & 31)) & (1u << (ex & 31))) {
+        ok2 = false;
+      }
+    }
+  }
+  ok1 = __all_sync(0xffffffffu, ok1) && __reduce_add_sync(0xffffffffu, ones) == 1;
+  ok2 = __all_sync(0xffffffffu, ok2) && __reduce_add_sync(0xffffffffu, mones) == 1;
+  k_one = __reduce_max_sync(0xffffffffu, k_one);
+  k_mone = __reduce_max_sync(0xffffffffu, k_mone);
+  if (lane == 0 && (ok1 || ok2)) {
+    uint32_t rf = rflags[row] | RF_C3;
+    RowAux a = aux[row];
+    if (ok2) {
+      rf |= RF_C3_FLIP;
+      a.w2 = k_mone;
+      a.w5 = k_one;
+    } else {
+      a.w2 = k_one;
+    }
+    if (l - 1 >= 254) rf |= RF_C3_TOPBIG;
+    rflags[row] = rf;
+    aux[row] = a;
+  }
+}
+
+// roots (2a) and t (2b): the -intercept/slope divisions (:919-920, :961-964)
+__global__ void k_values(Raw r, const uint32_t* rflags, RowAux* aux, fr::u256* roots, fr::u256* tvals,
+                         unsigned int* next2a, unsigned int* next2b) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r.N) return;
+  uint32_t rf = rflags[row];
+  bool bad = false;
+  if ((rf & RF_2A) && !(rf & RF_2A_DIVZ)) {
+    ABScan ab;
+    scan_ab(r, row, ab, bad);
+    unsigned int i = atomicAdd(next2a, 1u);
+    roots[2 * i] = fr::neg_div(ab.icpt_a, ab.slope_a);
+    roots[2 * i + 1] = fr::neg_div(ab.icpt_b, ab.slope_b);
+    aux[row].val_idx = i;
+  }
+  if (rf & RF_2B) {
+    CScan cs;
+    scan_c(r, row, cs, bad);
+    unsigned int i = atomicAdd(next2b, 1u);
+    tvals[N_CONST + i] = fr::neg_div(cs.c1, cs.cx);
+    aux[row].val_idx = i;
+  }
+}
+
+// row of an original term by binary search over the 3N+1 segment offsets
+__device__ __forceinline__ uint32_t seg_of(const unsigned long long* seg, uint32_t nseg, uint64_t t) {
+  uint32_t lo = 0, hi = nseg;  // find last s with seg[s] <= t
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (seg[mid] <= t)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ fr::u256 mag_of(const fr::u256& c, bool flipped) {
+  fr::u256 x = flipped ? fr::neg(c) : c;
+  if (fr::cmp(x, fr::fold_threshold()) > 0) {
+    fr::u256 o;
+    fr::sub_cc(o, fr::modulus(), x);
+    return o;
+  }
+  return x;
+}
+
+// Scatter the non-zero terms into the sweep layout.  C terms of linear rows are placed by their
+// rank in (|fold(coef)|, wire) order so that Case 5 (:1265) walks them sorted.
+__global__ void k_layout(Raw r, const uint32_t* keep, const uint32_t* pos, const uint32_t* seg_nz,
+                         const uint32_t* rflags, uint32_t* col, fr::u256* coef, uint8_t* nontriv) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= r.nnz || !keep[t]) return;
+  uint32_t s = seg_of(r.seg, 3 * r.N, t);
+  while (r.seg[s + 1] <= t) ++s;  // skip empty segments that share the offset
+  uint32_t row = s / 3, form = s % 3;
+  uint32_t dst = pos[t];
+  fr::u256 c = r.coef[t];
+  uint32_t w = r.col[t];
+  uint32_t rf = rflags[row];
+  if (form == 2 && (rf & RF_LINEAR)) {
+    bool fl = (rf & RF_C3_FLIP) != 0;
+    fr::u256 m = mag_of(c, fl);
+    uint32_t rank = 0;
+    for (uint64_t u = r.seg[s]; u < r.seg[s + 1]; ++u) {
+      if (u == t || !keep[u]) continue;
+      int cm = fr::cmp(mag_of(r.coef[u], fl), m);
+      if (cm < 0 || (cm == 0 && r.col[u] < w)) ++rank;
+    }
+    dst = seg_nz[s] + rank;
+  }
+  col[dst] = w;
+  coef[dst] = c;
+  nontriv[w] = 1;
+}
+__global__ void k_mark(const uint32_t* list, uint32_t n, uint8_t* nontriv) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) nontriv[list[i]] = 1;
+}
+__global__ void k_long_rows(uint32_t N, const uint32_t* rflags, uint32_t* out, unsigned int* n) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < N && (rflags[row] & RF_LONG)) out[atomicAdd(n, 1u)] = row;
+}
+
+// ---- bound-value table: sort the candidates, rank the distinct values ---------------------------
+__global__ void k_consts(fr::u256* cand) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < 254)
+    cand[k] = fr::pow2m1((int)k);
+  else if (k == 254)
+    fr::sub_cc(cand[k], fr::modulus(), fr::make_u256(1, 0, 0, 0));
+}
+__global__ void k_limb(const fr::u256* cand, const uint32_t* idx, uint32_t n, int limb,
+                       unsigned long long* keys) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = cand[idx[i]].v[limb];
+}
+__global__ void k_iota(uint32_t* idx, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) idx[i] = i;
+}
+__global__ void k_distinct(const fr::u256* cand, const uint32_t* idx, uint32_t n, uint32_t* flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || !fr::eq(cand[idx[i]], cand[idx[i - 1]])) ? 1u : 0u;
+}
+__global__ void k_ranks(const fr::u256* cand, const uint32_t* idx, const uint32_t* incl, uint32_t n,
+                        uint32_t* rank_of, fr::u256* table) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t rk = incl[i] - 1;
+  rank_of[idx[i]] = rk;
+  if (i == 0 || incl[i] != incl[i - 1]) table[rk] = cand[idx[i]];
+}
+__global__ void k_fill_ranks(uint32_t N, const uint32_t* rflags, RowAux* aux, const uint32_t* rank_of,
+                             const uint32_t* seg_nz) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  uint32_t rf = rflags[row];
+  if (rf & RF_2B) aux[row].rank_a = rank_of[N_CONST + aux[row].val_idx];
+  if ((rf & RF_C3) && !(rf & RF_C3_TOPBIG)) {
+    uint32_t l = seg_nz[3 * row + 3] - seg_nz[3 * row + 2];
+    aux[row].rank_b = rank_of[l - 1];  // 2^(l-1) - 1
+  }
+}
+
+template <class T>
+static cudaError_t h2d(T* dst, const T* src, size_t n, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  return cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+static inline unsigned int nb(uint64_t n, unsigned int t) { return (unsigned int)((n + t - 1) / t); }
+
+int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
+  if (!p || !p->seg_ptr || (p->n_rows && (!p->col || !p->coef))) {
+    err = "null problem arrays";
+    return ECNE_E_BADARG;
+  }
+  const uint64_t N = p->n_rows, V = p->n_vars, nnz = p->seg_ptr[3 * N];
+  if (V < 1 || V >= 0x7fffffffULL || N >= 0x3fffffffULL || nnz >= 0x7fffffffULL) {
+    err = "problem too large for 32-bit indices (rows < 2^30, wires, terms < 2^31)";
+    return ECNE_E_BADARG;
+  }
+  for (uint64_t i = 0; i < p->n_known; ++i)
+    if (p->known[i] < 1 || p->known[i] > V) {
+      err = "BoundsError: known wire outside 1..num_variables (:682)";
+      return ECNE_E_BOUNDS;
+    }
+  for (uint64_t i = 0; i < p->n_targets; ++i)
+    if (p->targets[i] < 1 || p->targets[i] > V) {
+      err = "BoundsError: target wire outside 1..num_variables (:1580)";
+      return ECNE_E_BOUNDS;
+    }
+  const uint64_t n_sp = p->n_specials;
+  const uint64_t n_sp_in = n_sp ? p->sp_in_ptr[n_sp] : 0, n_sp_out = n_sp ? p->sp_out_ptr[n_sp] : 0;
+  for (uint64_t i = 0; i < n_sp_in; ++i)
+    if (p->sp_in[i] < 1 || p->sp_in[i] > V) {
+      err = "BoundsError: special-constraint input outside 1..num_variables (:722)";
+      return ECNE_E_BOUNDS;
+    }
+  for (uint64_t i = 0; i < n_sp_out; ++i)
+    if (p->sp_out[i] < 1 || p->sp_out[i] > V) {
+      err = "BoundsError: special-constraint output outside 1..num_variables (:733)";
+      return ECNE_E_BOUNDS;
+    }
+
+  cudaStream_t s = R->stream;
+  Arena tmp;  // freed on return
+  struct TmpGuard {
+    Arena& a;
+    ~TmpGuard() { a.release(); }
+  } guard{tmp};
+  cudaEvent_t ev0, ev1, ev2;
+  cudaEventCreate(&ev0);
+  cudaEventCreate(&ev1);
+  cudaEventCreate(&ev2);
+  cudaEventRecord(ev0, s);
+
+  // ---- H2D -------------------------------------------------------------------------------
+  unsigned long long* d_seg64;
+  uint32_t* d_col_raw;
+  fr::u256* d_coef_raw;
+  CK(tmp.alloc(&d_seg64, 3 * N + 2));
+  CK(tmp.alloc(&d_col_raw, nnz));
+  CK(tmp.alloc(&d_coef_raw, nnz));
+  CK(h2d(d_seg64, (const unsigned long long*)p->seg_ptr, 3 * N + 1, s));
+  CK(h2d(d_col_raw, p->col, nnz, s));
+  CK(h2d((uint64_t*)d_coef_raw, p->coef, 4 * nnz, s));
+
+  Dev& d = R->d;
+  memset(&d, 0, sizeof(d));
+  d.N = (uint32_t)N;
+  d.V = (uint32_t)V;
+  d.n_known = (uint32_t)p->n_known;
+  d.n_targets = (uint32_t)p->n_targets;
+  d.n_specials = (uint32_t)n_sp;
+  d.secp_solve = p->secp_solve;
+  d.row_lo = 0;
+  d.row_hi = (uint32_t)N;
+  Arena& A = R->arena;
+  uint32_t *d_known, *d_targets, *d_sp_in_ptr, *d_sp_in, *d_sp_out_ptr, *d_sp_out;
+  int32_t* d_sp_kind;
+  CK(A.alloc(&d_known, p->n_known));
+  CK(A.alloc(&d_targets, p->n_targets));
+  CK(h2d(d_known, p->known, p->n_known, s));
+  CK(h2d(d_targets, p->targets, p->n_targets, s));
+  CK(A.alloc(&d_sp_kind, n_sp));
+  CK(A.alloc(&d_sp_in_ptr, n_sp + 1));
+  CK(A.alloc(&d_sp_out_ptr, n_sp + 1));
+  CK(A.alloc(&d_sp_in, n_sp_in));
+  CK(A.alloc(&d_sp_out, n_sp_out));
+  std::vector<uint32_t> ip(n_sp + 1, 0), op(n_sp + 1, 0);
+  for (uint64_t i = 0; i <= n_sp && n_sp; ++i) {
+    ip[i] = (uint32_t)p->sp_in_ptr[i];
+    op[i] = (uint32_t)p->sp_out_ptr[i];
+  }
+  CK(h2d(d_sp_kind, p->sp_kind, n_sp, s));
+  CK(h2d(d_sp_in_ptr, ip.data(), n_sp + 1, s));
+  CK(h2d(d_sp_out_ptr, op.data(), n_sp + 1, s));
+  CK(h2d(d_sp_in, p->sp_in, n_sp_in, s));
+  CK(h2d(d_sp_out, p->sp_out, n_sp_out, s));
+  CK(cudaStreamSynchronize(s));  // ip/op are stack-owned
+  cudaEventRecord(ev1, s);
+  d.known = d_known;
+  d.targets = d_targets;
+  d.sp_kind = d_sp_kind;
+  d.sp_in_ptr = d_sp_in_ptr;
+  d.sp_in = d_sp_in;
+  d.sp_out_ptr = d_sp_out_ptr;
+  d.sp_out = d_sp_out;
+
+  Raw raw;
+  raw.N = (uint32_t)N;
+  raw.V = (uint32_t)V;
+  raw.nnz = nnz;
+  raw.seg = d_seg64;
+  raw.col = d_col_raw;
+  raw.coef = d_coef_raw;
+
+  // ---- non-zero compaction offsets ------------------------------------------------------------
+  uint32_t *d_keep, *d_pos, *d_segnz;
+  CK(tmp.alloc(&d_keep, nnz + 1));
+  CK(tmp.alloc(&d_pos, nnz + 1));
+  CK(A.alloc(&d_segnz, 3 * N + 1));
+  k_keep<<<nb(nnz + 1, 256), 256, 0, s>>>(raw, d_keep);
+  size_t cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, d_keep, d_pos, (int)(nnz + 1), s);
+  void* d_cub;
+  {
+    size_t b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b2, (unsigned long long*)nullptr,
+                                    (unsigned long long*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)std::max<uint64_t>(N + N_CONST, 1024), 0, 64, s);
+    cub_bytes = std::max(cub_bytes, b2);
+    cub_bytes = std::max(cub_bytes, (size_t)1 << 20);
+  }
+  CK(A.alloc((uint8_t**)&d_cub, cub_bytes));
+  R->d_cub = d_cub;
+  R->cub_bytes = cub_bytes;
+  {
+    size_t b = cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(d_cub, b, d_keep, d_pos, (int)(nnz + 1), s));
+  }
+  k_seg<<<nb(3 * N + 1, 256), 256, 0, s>>>(raw, d_pos, d_segnz);
+
+  // ---- classify -------------------------------------------------------------------------------
+  uint32_t* d_rflags;
+  RowAux* d_aux;
+  Counters* d_cnt;
+  uint32_t* d_c3_long;
+  CK(A.alloc(&d_rflags, N));
+  CK(A.alloc(&d_aux, N));
+  CK(tmp.alloc(&d_cnt, 1));
+  CK(tmp.alloc(&d_c3_long, N));
+  CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), s));
+  if (N) k_classify<<<nb(N, 128), 128, 0, s>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long);
+  Counters cnt;
+  CK(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  uint32_t nnz_nz = 0;
+  CK(cudaMemcpyAsync(&nnz_nz, d_pos + nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (cnt.bad) {
+    err = "wire id outside 1..num_variables in a constraint (BoundsError at :681/:829)";
+    return ECNE_E_BOUNDS;
+  }
+  if (cnt.n_c3_long) {
+    // sorted table of 2^i mod p for i < max_c, built on the host (pure constants)
+    uint32_t tn = cnt.max_c;
+    std::vector<Pow2Entry> tab(tn);
+    fr::u256 x = fr::make_u256(1, 0, 0, 0);
+    for (uint32_t i = 0; i < tn; ++i) {
+      tab[i].v = x;
+      tab[i].e = i;
+      x = fr::add(x, x);
+    }
+    std::sort(tab.begin(), tab.end(),
+              [](const Pow2Entry& a, const Pow2Entry& b) { return fr::cmp(a.v, b.v) < 0; });
+    for (uint32_t i = 1; i < tn; ++i)
+      if (fr::eq(tab[i].v, tab[i - 1].v)) {
+        err = "2^i mod p repeats below the longest row length";
+        return ECNE_E_UNSUPPORTED;
+      }
+    Pow2Entry* d_tab;
+    CK(tmp.alloc(&d_tab, tn));
+    CK(cudaMemcpyAsync(d_tab, tab.data(), tn * sizeof(Pow2Entry), cudaMemcpyHostToDevice, s));
+    uint32_t mask_words = (tn + 31) / 32;
+    const int warps = 4;
+    size_t smem = (size_t)warps * 2 * mask_words * sizeof(unsigned int);
+    if (smem > 200 * 1024) {
+      err = "row too long for the bit-decomposition classifier";
+      return ECNE_E_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
+      CK(cudaFuncSetAttribute(k_classify_c3_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_classify_c3_long<<<nb(cnt.n_c3_long, warps), warps * 32, smem, s>>>(
+        raw, d_rflags, d_aux, d_c3_long, cnt.n_c3_long, d_tab, tn, mask_words);
+    CK(cudaStreamSynchronize(s));  // tab is host-owned
+  }
+
+  // ---- static values and the bound table ---------------------------------------------------
+  d.n2a = cnt.n2a;
+  d.n2b = cnt.n2b;
+  fr::u256 *d_roots, *d_tvals;
+  CK(A.alloc(&d_roots, 2 * (size_t)cnt.n2a));
+  CK(A.alloc(&d_tvals, (size_t)N_CONST + cnt.n2b));  // candidates: constants first, then every t
+  unsigned int* d_next;
+  CK(tmp.alloc(&d_next, 2));
+  CK(cudaMemsetAsync(d_next, 0, 2 * sizeof(unsigned int), s));
+  k_consts<<<1, 256, 0, s>>>(d_tvals);
+  if (N) k_values<<<nb(N, 128), 128, 0, s>>>(raw, d_rflags, d_aux, d_roots, d_tvals, d_next, d_next + 1);
+  const uint32_t nc = N_CONST + cnt.n2b;
+  uint32_t *d_idx, *d_idx2, *d_flag, *d_incl, *d_rank_of;
+  unsigned long long *d_k1, *d_k2;
+  fr::u256* d_table;
+  CK(tmp.alloc(&d_idx, nc));
+  CK(tmp.alloc(&d_idx2, nc));
+  CK(tmp.alloc(&d_flag, nc));
+  CK(tmp.alloc(&d_incl, nc));
+  CK(tmp.alloc(&d_rank_of, nc));
+  CK(tmp.alloc(&d_k1, nc));
+  CK(tmp.alloc(&d_k2, nc));
+  CK(A.alloc(&d_table, nc));
+  k_iota<<<nb(nc, 256), 256, 0, s>>>(d_idx, nc);
+  for (int limb = 0; limb < 4; ++limb) {  // LSD radix sort, one stable 64-bit pass per limb
+    k_limb<<<nb(nc, 256), 256, 0, s>>>(d_tvals, d_idx, nc, limb, d_k1);
+    size_t b = cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(d_cub, b, d_k1, d_k2, d_idx, d_idx2, (int)nc, 0, 64, s));
+    std::swap(d_idx, d_idx2);
+  }
+  k_distinct<<<nb(nc, 256), 256, 0, s>>>(d_tvals, d_idx, nc, d_flag);
+  {
+    size_t b = cub_bytes;
+    CK(cub::DeviceScan::InclusiveSum(d_cub, b, d_flag, d_incl, (int)nc, s));
+  }
+  k_ranks<<<nb(nc, 256), 256, 0, s>>>(d_tvals, d_idx, d_incl, nc, d_rank_of, d_table);
+  if (N) k_fill_ranks<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_rflags, d_aux, d_rank_of, d_segnz);
+  uint32_t h_rank[3], h_tn;
+  CK(cudaMemcpyAsync(&h_rank[0], d_rank_of + 0, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_rank[1], d_rank_of + 1, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_rank[2], d_rank_of + 254, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_tn, d_incl + (nc - 1), 4, cudaMemcpyDeviceToHost, s));
+
+  // ---- sweep layout ---------------------------------------------------------------------------
+  uint32_t* d_col;
+  fr::u256* d_coef;
+  uint8_t* d_nontriv;
+  uint32_t* d_long;
+  unsigned int* d_nlong;
+  CK(A.alloc(&d_col, (size_t)nnz_nz));
+  CK(A.alloc(&d_coef, (size_t)nnz_nz));
+  CK(A.alloc(&d_nontriv, V + 4));
+  CK(A.alloc(&d_long, (size_t)cnt.n_long));
+  CK(tmp.alloc(&d_nlong, 1));
+  CK(cudaMemsetAsync(d_nontriv, 0, V + 4, s));
+  CK(cudaMemsetAsync(d_nlong, 0, sizeof(unsigned int), s));
+  if (nnz)
+    k_layout<<<nb(nnz, 256), 256, 0, s>>>(raw, d_keep, d_pos, d_segnz, d_rflags, d_col, d_coef, d_nontriv);
+  if (n_sp_in) k_mark<<<nb(n_sp_in, 256), 256, 0, s>>>(d_sp_in, (uint32_t)n_sp_in, d_nontriv);
+  if (n_sp_out) k_mark<<<nb(n_sp_out, 256), 256, 0, s>>>(d_sp_out, (uint32_t)n_sp_out, d_nontriv);
+  if (p->n_targets) k_mark<<<nb(p->n_targets, 256), 256, 0, s>>>(d_targets, (uint32_t)p->n_targets, d_nontriv);
+  if (cnt.n_long) k_long_rows<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_rflags, d_long, d_nlong);
+
+  // ---- wire state, records, scratch -----------------------------------------------------------
+  for (int b = 0; b < 2; ++b) {
+    CK(A.alloc(&d.F[b], V + 8));
+    CK(A.alloc(&d.B[b], V + 8));
+    CK(A.alloc(&d.LBR[b], V + 1));
+    CK(A.alloc(&d.UBR[b], V + 1));
+  }
+  CK(A.alloc(&d.abz, V + 1));
+  CK(A.alloc(&d.valsrc, V + 1));
+  CK(A.alloc(&d.abz_claim, V + 1));
+  CK(A.alloc(&d.solved, N + 2));
+  CK(A.alloc(&d.sp_solved, n_sp));
+  d.rec_cap = (uint32_t)std::min<uint64_t>(2 * V + 4096, 0x7ffffff0ULL);
+  for (int l = 0; l < 3; ++l) CK(A.alloc(&d.recs[l], d.rec_cap));
+  CK(A.alloc(&d.rec_count, 4));
+  CK(A.alloc(&d.barrier, 4));
+  CK(A.alloc(&d.st, 1));
+  CK(A.alloc(&d.p2_key, N));
+  CK(A.alloc(&d.p2_row, N));
+  CK(A.alloc(&R->d_key2, N));
+  CK(A.alloc(&R->d_row2, N));
+  CK(A.alloc(&R->d_ubits, (V + 63) / 64));
+  CK(A.alloc(&R->d_kbits, (V + 63) / 64));
+  CK(A.alloc(&R->d_counts, 4));
+  CK(cudaMallocHost((void**)&R->h_status, sizeof(Status)));
+  CK(cudaMallocHost((void**)&R->h_counts, 4 * sizeof(unsigned long long)));
+
+  CK(cudaStreamSynchronize(s));
+  d.r0 = h_rank[0];
+  d.r1 = h_rank[1];
+  d.rpm1 = h_rank[2];
+  d.table_n = h_tn;
+  d.nnz = nnz_nz;
+  d.n_long = cnt.n_long;
+  d.seg = d_segnz;
+  d.col = d_col;
+  d.coef = d_coef;
+  d.rflags = d_rflags;
+  d.aux = d_aux;
+  d.long_rows = d_long;
+  d.roots = d_roots;
+  d.tvals = d_tvals + N_CONST;
+  d.table = d_table;
+  d.nontriv = d_nontriv;
+  R->n_rows = N;
+  R->n_vars = V;
+  R->n_targets = p->n_targets;
+  cudaEventRecord(ev2, s);
+  CK(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  R->ms_h2d = ms;
+  cudaEventElapsedTime(&ms, ev1, ev2);
+  R->ms_classify = ms;
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  cudaEventDestroy(ev2);
+  CK(cudaGetLastError());
+  if (d.r0 != 0) {
+    err = "internal: rank of 0 is not 0";
+    return ECNE_E_INTERNAL;
+  }
+  return ECNE_OK;
+}
+
+// Sort the P2 candidates by (key, row): rows first, then a stable pass over the 64-bit keys.
+int p2_sort(Resident* R, uint32_t n, std::string& err) {
+  Dev& d = R->d;
+  cudaStream_t s = R->stream;
+  int row_bits = 1;
+  while ((1ull << row_bits) < (unsigned long long)d.N + 1) ++row_bits;
+  size_t b = R->cub_bytes;
+  CK(cub::DeviceRadixSort::SortPairs(R->d_cub, b, d.p2_row, R->d_row2, d.p2_key, R->d_key2, (int)n, 0,
+                                     row_bits, s));
+  b = R->cub_bytes;
+  CK(cub::DeviceRadixSort::SortPairs(R->d_cub, b, R->d_key2, d.p2_key, R->d_row2, d.p2_row, (int)n, 0, 64, s));
+  return ECNE_OK;
+}
+
+}  // namespace ecne

@@ -1,0 +1,359 @@
+// sweep.cuh — the single-row rule set (the body of the reference's queue loop,
+// /root/reference/src/R1CSConstraintSolver.jl:805-1349) evaluated for one constraint row against a
+// snapshot of the wire state.  One thread per row for ordinary rows (p99 row length is 3), one
+// warp per row — lanes striding the terms, ballot/shuffle reductions — for long rows.
+//
+// Inside one evaluation the cases run in the reference's order and each sees the effects of the
+// earlier ones on this row's own wires (a small register overlay), exactly like one pop.
+#pragma once
+#include "engine.cuh"
+
+namespace ecne {
+
+template <int G>
+struct Grp {
+  static __device__ __forceinline__ uint32_t lane() { return G == 1 ? 0u : (threadIdx.x & 31u); }
+  static __device__ __forceinline__ uint32_t sum(uint32_t x) {
+    if (G == 1) return x;
+    return __reduce_add_sync(0xffffffffu, x);
+  }
+  static __device__ __forceinline__ uint32_t max(uint32_t x) {
+    if (G == 1) return x;
+    return __reduce_max_sync(0xffffffffu, x);
+  }
+  static __device__ __forceinline__ uint32_t min(uint32_t x) {
+    if (G == 1) return x;
+    return __reduce_min_sync(0xffffffffu, x);
+  }
+  static __device__ __forceinline__ bool all(bool p) {
+    if (G == 1) return p;
+    return __all_sync(0xffffffffu, p);
+  }
+  static __device__ __forceinline__ bool any(bool p) {
+    if (G == 1) return p;
+    return __any_sync(0xffffffffu, p);
+  }
+};
+
+// What earlier cases of this evaluation did to the row's own wires (group-uniform).
+struct Overlay {
+  uint32_t w[2], lb[2], ub[2];
+  bool k[2];
+  int n;
+  bool all_unique;  // every C key is unique by now
+  __device__ __forceinline__ int find(uint32_t x) const {
+    if (n > 0 && w[0] == x) return 0;
+    if (n > 1 && w[1] == x) return 1;
+    return -1;
+  }
+  __device__ __forceinline__ void set(uint32_t x, uint32_t l, uint32_t u, bool known) {
+    int i = find(x);
+    if (i < 0) {
+      if (n >= 2) return;  // cannot happen: at most two wires get local bounds
+      i = n++;
+      w[i] = x;
+      k[i] = false;
+    }
+    lb[i] = l;
+    ub[i] = u;
+    k[i] = k[i] || known;
+  }
+};
+
+struct RowCtx {
+  const Dev& d;
+  int rbuf, wbuf, list;
+  uint32_t row, rf, s2, s3;
+  Overlay ov;
+  __device__ __forceinline__ RowCtx(const Dev& dd) : d(dd) {}
+  __device__ __forceinline__ void bounds(uint32_t w, uint32_t& l, uint32_t& u) const {
+    int i = ov.find(w);
+    if (i >= 0) {
+      l = ov.lb[i];
+      u = ov.ub[i];
+    } else {
+      l = ld_u32(d.LBR[rbuf], w);
+      u = ld_u32(d.UBR[rbuf], w);
+    }
+  }
+  __device__ __forceinline__ bool b01(uint32_t w) const {
+    int i = ov.find(w);
+    if (i >= 0) return ov.lb[i] == d.r0 && ov.ub[i] == d.r1;
+    return __ldcg(d.B[rbuf] + w) != 0;
+  }
+  __device__ __forceinline__ bool uniq(uint32_t w) const {
+    return ov.all_unique || (ld_flag(d.F[rbuf], w) & WF_U);
+  }
+  __device__ __forceinline__ bool known(uint32_t w) const {
+    int i = ov.find(w);
+    if (i >= 0 && ov.k[i]) return true;
+    return ld_flag(d.F[rbuf], w) & WF_K;
+  }
+  __device__ __forceinline__ void out(uint32_t w, uint32_t bits, uint32_t l = ECNE_NO_LB,
+                                      uint32_t u = ECNE_NO_UB) const {
+    emit(d, wbuf, list, w, bits, l, u);
+  }
+};
+
+// |flip_coeffs(c)| of :1245-1257 on the (possibly flipped) stored coefficient
+__device__ __forceinline__ fr::u256 case5_mag(const fr::u256& c, bool flipped) {
+  fr::u256 x = flipped ? fr::neg(c) : c;
+  if (fr::cmp(x, fr::fold_threshold()) > 0) {
+    fr::u256 r;
+    fr::sub_cc(r, fr::modulus(), x);
+    return r;
+  }
+  return x;
+}
+
+// one link of the mixed-radix chain (:1266-1272): lo = term `tp`, hi = term `tc`
+__device__ __noinline__ bool case5_pair_ok(const RowCtx& c, uint32_t tp, uint32_t tc) {
+  const Dev& d = c.d;
+  bool flipped = (c.rf & RF_C3_FLIP) != 0;
+  fr::u256 dlo = case5_mag(d.coef[tp], flipped);
+  fr::u256 dhi = case5_mag(d.coef[tc], flipped);
+  if (!fr::divides(dlo, dhi)) return false;
+  uint32_t l, u;
+  c.bounds(d.col[tp], l, u);
+  if (u < l) return true;  // ub - lb negative: the quotient (>= 1) is never <= it
+  fr::u256 range;
+  fr::sub_cc(range, d.table[u], d.table[l]);
+  // fail when hi/lo <= range  <=>  hi <= lo*range
+  return fr::cmp_mul(dlo, range, dhi) < 0;
+}
+// the top test (:1274): fail when d * (ub + 1) > p
+__device__ __noinline__ bool case5_top_ok(const RowCtx& c, uint32_t t) {
+  const Dev& d = c.d;
+  fr::u256 dm = case5_mag(d.coef[t], (c.rf & RF_C3_FLIP) != 0);
+  uint32_t l, u;
+  c.bounds(d.col[t], l, u);
+  fr::u256 ub1;
+  fr::add_cc(ub1, d.table[u], fr::make_u256(1, 0, 0, 0));
+  return fr::cmp_mul(dm, ub1, fr::modulus()) <= 0;
+}
+
+// Case 5 (:1235-1298) on C terms that are stored sorted by magnitude.  Returns true on success.
+template <int G>
+__device__ __noinline__ bool case5(const RowCtx& c) {
+  const Dev& d = c.d;
+  const uint32_t lane = Grp<G>::lane();
+  bool ok = true;
+  uint32_t prev = 0xffffffffu;  // previous selected term (group-uniform)
+  for (uint32_t base = c.s2; base < c.s3; base += G) {
+    uint32_t t = base + lane;
+    bool sel = false;
+    if (t < c.s3) {
+      uint32_t w = d.col[t];
+      if (!c.uniq(w)) {
+        sel = true;
+        if (!c.known(w)) ok = false;  // some unknown key is not is_known (:1260-1264)
+      }
+    }
+    if (G == 1) {
+      if (sel) {
+        if (ok && prev != 0xffffffffu) ok = case5_pair_ok(c, prev, t);
+        prev = t;
+      }
+      if (!ok) return false;
+    } else {
+      uint32_t m = __ballot_sync(0xffffffffu, sel);
+      if (!__all_sync(0xffffffffu, ok)) return false;
+      if (sel) {
+        uint32_t below = m & ((1u << lane) - 1u);
+        uint32_t p = below ? base + (31 - __clz(below)) : prev;
+        if (p != 0xffffffffu) ok = case5_pair_ok(c, p, t);
+      }
+      if (!__all_sync(0xffffffffu, ok)) return false;
+      if (m) prev = base + (31 - __clz(m));
+    }
+  }
+  if (prev == 0xffffffffu) return false;  // no unknown key (:1242-1244)
+  if (!case5_top_ok(c, prev)) return false;
+  return true;
+}
+
+// The rule set on one row.  `rounds_fresh`: nothing.
+template <int G>
+__device__ __forceinline__ void eval_row(const Dev& d, int rbuf, int wbuf, int list, uint32_t row) {
+  const uint32_t lane = Grp<G>::lane();
+  const uint32_t rf = d.rflags[row];
+  uint8_t latch = d.solved[row];
+  if (latch & 1) return;  // equation_solved (:820-822)
+  const uint8_t* F = d.F[rbuf];
+  const uint32_t s0 = d.seg[3 * row], s2 = d.seg[3 * row + 2], s3 = d.seg[3 * row + 3];
+
+  // ---- gather: non-unique counts over A u B and over C --------------------------------------
+  uint32_t nuAB = 0, nuC = 0, wC = 0, kmiss = 0, abzmiss = 0;
+  for (uint32_t t = s0 + lane; t < s2; t += G) nuAB += (ld_flag(F, d.col[t]) & WF_U) ? 0u : 1u;
+  for (uint32_t t = s2 + lane; t < s3; t += G) {
+    uint32_t w = d.col[t];
+    uint32_t f = ld_flag(F, w);
+    if (!(f & WF_U)) {
+      nuC += 1;
+      wC = w;
+      kmiss += (f & WF_K) ? 0u : 1u;
+      abzmiss += (f & WF_ABZ) ? 0u : 1u;
+    }
+  }
+  if (G > 1) {
+    nuAB = Grp<G>::sum(nuAB);
+    nuC = Grp<G>::sum(nuC);
+    wC = Grp<G>::max(wC);
+    kmiss = Grp<G>::sum(kmiss);
+    abzmiss = Grp<G>::sum(abzmiss);
+  }
+
+  RowCtx c(d);
+  c.rbuf = rbuf;
+  c.wbuf = wbuf;
+  c.list = list;
+  c.row = row;
+  c.rf = rf;
+  c.s2 = s2;
+  c.s3 = s3;
+  c.ov.n = 0;
+  c.ov.all_unique = false;
+
+  // ---- Case 1 (:827-873) ------------------------------------------------------------------
+  if (nuAB == 0 && nuC == 1) {
+    if (lane == 0) c.out(wC, WF_U | WF_K);
+    nuC = 0;
+    c.ov.all_unique = true;
+  }
+
+  // ---- Case 2a (:875-942) -----------------------------------------------------------------
+  if (rf & RF_2A_NOVAR) {
+    raise(d, ECNE_E_BOUNDS);
+    return;
+  }
+  if (rf & RF_2A) {
+    const RowAux a = d.aux[row];
+    if (!(ld_flag(F, a.w1) & WF_K)) {
+      if (rf & RF_2A_DIVZ) {
+        raise(d, ECNE_E_DIVZERO);
+        return;
+      }
+      if (lane == 0) {
+        c.out(a.w1, WF_K, ECNE_NO_LB, (rf & RF_2A_BOOL) ? d.r1 : ECNE_NO_UB);
+        d.valsrc[a.w1] = VS_2A | a.val_idx;
+        d.solved[row] = latch | 1;
+      }
+    }
+  }
+  if (!(rf & RF_LINEAR)) return;  // (:944-946)
+  if (!(rf & (RF_2B | RF_C3 | RF_4A | RF_4B)) && nuC == 0) return;
+
+  const RowAux a = d.aux[row];
+  // ---- Case 2b (:949-988) -----------------------------------------------------------------
+  if (rf & RF_2B) {
+    if (!(latch & 2)) {
+      if (lane == 0) {
+        c.out(a.w1, WF_U | WF_K, a.rank_a, a.rank_a);
+        d.valsrc[a.w1] = VS_2B | a.val_idx;
+        d.solved[row] = latch | 2;  // the monotone merge makes a second application a no-op
+      }
+    }
+    c.ov.set(a.w1, a.rank_a, a.rank_a, true);
+  }
+
+  // ---- Case 3 (:991-1076) -----------------------------------------------------------------
+  if (rf & RF_C3) {
+    const int norient = (rf & RF_C3_L2) ? 2 : 1;
+    for (int o = 0; o < norient; ++o) {
+      const uint32_t nk = o == 0 ? a.w2 : a.w5;
+      bool ok = true;
+      for (uint32_t t = s2 + lane; t < s3; t += G) {
+        uint32_t w = d.col[t];
+        if (w != nk && !c.b01(w)) ok = false;
+      }
+      ok = Grp<G>::all(ok);
+      if (!ok) continue;
+      uint32_t l, u;
+      c.bounds(nk, l, u);
+      if (!(rf & RF_C3_TOPBIG) && u > a.rank_b) {  // ub.d > 2^(l-1)-1 (:1035)
+        if (lane == 0) c.out(nk, WF_K, ECNE_NO_LB, a.rank_b);
+        c.ov.set(nk, d.r0, a.rank_b, true);
+      }
+      if (nuC > 0 && c.uniq(nk)) {  // (:1049-1067)
+        for (uint32_t t = s2 + lane; t < s3; t += G) {
+          uint32_t w = d.col[t];
+          if (w != nk && !(ld_flag(F, w) & WF_U)) c.out(w, WF_U | WF_K);
+        }
+        nuC = 0;
+        c.ov.all_unique = true;
+      }
+    }
+  }
+
+  // ---- Case 4a (:1078-1146) / 4b (:1148-1232) ---------------------------------------------
+  if (rf & (RF_4A | RF_4B)) {
+    uint32_t k1, k2;
+    if (rf & RF_4A) {
+      k1 = d.col[s2];
+      k2 = d.col[s2 + 1];
+    } else {
+      uint32_t x0 = d.col[s2], x1 = d.col[s2 + 1], x2 = d.col[s2 + 2];
+      k1 = (x0 == 1) ? x1 : x0;
+      k2 = (x2 == 1) ? x1 : x2;
+    }
+    uint32_t l1, u1, l2, u2;
+    c.bounds(k1, l1, u1);
+    c.bounds(k2, l2, u2);
+    // the `unique` fields agree here: Case 1 above already handled "exactly one non-unique"
+    if (u1 != u2 || l1 != l2) {
+      uint32_t mn = u1 < u2 ? u1 : u2, mx = l1 > l2 ? l1 : l2;
+      bool go = (rf & RF_4A) || (mn == d.r1 && mx == d.r0);  // (:1196-1199)
+      if (go) {
+        if (u1 > mn || l1 < mx) {
+          if (lane == 0) {
+            c.out(k1, WF_K, mx, mn);
+            if (rf & RF_4B) d.valsrc[k1] = VS_ONEZERO;
+          }
+          c.ov.set(k1, mx, mn, true);
+        }
+        if (u2 > mn || l2 < mx) {
+          if (lane == 0) {
+            c.out(k2, WF_K, mx, mn);
+            if (rf & RF_4B) d.valsrc[k2] = VS_ONEZERO;
+          }
+          c.ov.set(k2, mx, mn, true);
+        }
+      }
+    }
+  }
+
+  if (nuC == 0) return;
+  // ---- Case 5 (:1235-1298) ----------------------------------------------------------------
+  bool local_k = (c.ov.n > 0 && c.ov.k[0]) || (c.ov.n > 1 && c.ov.k[1]);
+  if (kmiss == 0 || local_k) {
+    if (case5<G>(c)) {
+      for (uint32_t t = s2 + lane; t < s3; t += G) {
+        uint32_t w = d.col[t];
+        if (!(ld_flag(F, w) & WF_U)) c.out(w, WF_U | WF_K);
+      }
+      return;
+    }
+  }
+  // ---- Case 6 (:1304-1348) ----------------------------------------------------------------
+  if (abzmiss == 0) {
+    uint32_t lo = 0xffffffffu, hi = 0;
+    for (uint32_t t = s2 + lane; t < s3; t += G) {
+      uint32_t w = d.col[t];
+      if (!(ld_flag(F, w) & WF_U)) {
+        uint32_t z = (uint32_t)d.abz[w];
+        lo = z < lo ? z : lo;
+        hi = z > hi ? z : hi;
+      }
+    }
+    lo = Grp<G>::min(lo);
+    hi = Grp<G>::max(hi);
+    if (lo == hi) {
+      for (uint32_t t = s2 + lane; t < s3; t += G) {
+        uint32_t w = d.col[t];
+        if (!(ld_flag(F, w) & WF_U)) c.out(w, WF_U | WF_K);
+      }
+    }
+  }
+}
+
+}  // namespace ecne

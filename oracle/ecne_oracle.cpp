@@ -282,8 +282,10 @@ struct Solver {
     if (new_info) enqueue(x);
   }
 
-  // multiset test of :999-1001/:1013 on the CURRENT stored values of c:
-  //   0 none, 1 == {1} ∪ {-2^i}, 2 == {-1} ∪ {2^i}   (i = 0..l-2)
+  // multiset tests of :999-1001 / :1013 on the CURRENT stored values of c, memoised as a mask:
+  //   bit0: values == {1} U {-2^i}   (target_values),  bit1: values == {-1} U {2^i} (target_values_2)
+  // (i = 0..l-2).  For l == 2 both hold ({1,-1}), so such a row is re-flipped on every pop (:1001 is
+  // tested first), exactly as in the reference.
   int c_pattern(Row& r) {
     if (r.c_pattern >= 0) return r.c_pattern;
     size_t l = r.nzc.size();
@@ -305,10 +307,8 @@ struct Solver {
           if (!eq(x[k], y[k])) return false;
         return true;
       };
-      if (same(vals, t2))
-        res = 2;
-      else if (same(vals, t1))
-        res = 1;
+      if (same(vals, t1)) res |= 1;
+      if (same(vals, t2)) res |= 2;
     }
     r.c_pattern = res;
     return res;
@@ -320,11 +320,11 @@ struct Solver {
     size_t l = r.nzc.size();
     if (l == 0) return;
     int pat = c_pattern(r);
-    if (pat == 2) {  // flip in place (:1003-1010)
+    if (pat & 2) {  // flip in place (:1003-1010); negation maps the two target multisets onto each other
       for (auto& t : r.c) t.c = fneg(t.c);
-      r.c_pattern = pat = 1;
+      r.c_pattern = pat = ((pat & 1) << 1) | ((pat & 2) >> 1);
     }
-    if (pat != 1) return;
+    if (!(pat & 1)) return;
     int64_t nk = -1;
     for (uint32_t w : r.nzc) {
       if (eq(*find(r.c, w), ONE)) {
