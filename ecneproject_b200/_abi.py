@@ -49,7 +49,7 @@ class Result(C.Structure):
         ("constraint_evals", C.c_uint64), ("sweep_launches", C.c_uint64),
         ("ms_h2d", C.c_double), ("ms_classify", C.c_double), ("ms_solve", C.c_double),
         ("ms_d2h", C.c_double), ("ms_exchange", C.c_double), ("ms_total", C.c_double),
-        ("ms_sweep", C.c_double),
+        ("ms_sweep", C.c_double), ("rule_evals", C.c_uint64),
     ]
 
 
@@ -122,12 +122,12 @@ def engine_lib():
     """libecne_b200.so — the CUDA engine.  There is no fallback: missing library is an error."""
     global _engine
     if _engine is None:
-        path = os.path.join(PKG, "libecne_b200.so")
+        path = os.environ.get("ECNE_ENGINE_SO", os.path.join(PKG, "libecne_b200.so"))
         if not os.path.exists(path):
             raise RuntimeError(
                 "libecne_b200.so (the sm_100a CUDA engine) is not built and there is no CPU "
                 "fallback; run `python -m ecneproject_b200.build`")
-        lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        lib = C.CDLL(path)
         Pp = C.POINTER(Problem)
         Rp = C.POINTER(Result)
         lib.ecne_version.restype = C.c_int

@@ -150,7 +150,7 @@ class SolveResult:
         return {k: getattr(c, k) for k in (
             "n_unique_nontrivial", "n_nontrivial", "n_targets_unique", "n_unique", "outer_rounds",
             "inner_rounds", "constraint_evals", "sweep_launches", "ms_h2d", "ms_classify",
-            "ms_solve", "ms_d2h", "ms_exchange", "ms_total", "ms_sweep")}
+            "ms_solve", "ms_d2h", "ms_exchange", "ms_total", "ms_sweep", "rule_evals")}
 
 
 class ProblemHandle:

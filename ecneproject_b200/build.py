@@ -80,9 +80,9 @@ def build_engine(force=False, verbose=False):
         nvcc = nvcc_path()
         if nvcc is None:
             raise RuntimeError("nvcc not found: libecne_b200.so cannot be built (no CPU fallback exists)")
-        cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
+        cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-shared", "--cudart", "shared", "-Xcompiler", "-fPIC",
                "-Xptxas", "-v", "-I", INC, "-I", CSRC] + NVCC_ARCH
-        cmd += ["-o", ENGINE_SO] + src + ["-lnccl", "-lcudart"]
+        cmd += ["-o", ENGINE_SO] + src + ["-ldl"]
         _run(cmd, verbose)
     return ENGINE_SO
 

@@ -1,11 +1,13 @@
 // abi.cu — the C ABI of include/ecne_abi.h and the outer fixpoint loop
 // (/root/reference/src/R1CSConstraintSolver.jl:706-1556) that drives the kernels.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is dlopen()ed on first use (see NcclApi)
 
 #include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "engine_host.h"
 
@@ -25,6 +27,29 @@ struct Global {
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
 } G;
+
+// NCCL is bound at run time, not link time: a host process that also imports PyTorch must end up
+// with ONE libnccl.so.2 (torch bundles 2.28, the system has 2.27), and whichever is already mapped
+// is the one dlopen() hands back.
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (h) return true;
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && CommDestroy && AllGather;
+  }
+} NCCL;
 
 int fail(int status, const std::string& msg) {
   G.err = msg;
@@ -85,7 +110,7 @@ extern "C" int ecne_init(int device) {
 
 extern "C" void ecne_shutdown(void) {
   if (G.comm) {
-    ncclCommDestroy(G.comm);
+    NCCL.CommDestroy(G.comm);
     G.comm = nullptr;
   }
   if (G.stream) {
@@ -150,10 +175,10 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   cudaEventCreate(&e1);
   cudaEventCreate(&e2);
   cudaEventRecord(e0, s);
-  CKA(launch_reset(d, s));
   const int grid = p1_grid_size(G.device);
+  CKA(launch_reset(d, grid, s));
   uint64_t outer = 0, launches = 0, phase_evals = 0;
-  unsigned long long rounds_total = 0, evals_total = 0;
+  unsigned long long rounds_total = 0, evals_total = 0, rule_evals_total = 0;
   int status = ECNE_OK;
   std::string err;
   float ms_sweep = 0;
@@ -168,8 +193,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
     cudaEventRecord(s0, s);
     CKA(launch_p1(d, 0, (unsigned int)G.max_rounds, grid, s));
     cudaEventRecord(s1, s);
-    // P2: linear systems
-    launch_p2_scan(d, 0, s);
+    // P2: linear systems (the candidate scan ran in the sweep kernel's tail)
     CKA(cudaMemcpyAsync(R.h_status, d.st, sizeof(Status), cudaMemcpyDeviceToHost, s));
     CKA(cudaStreamSynchronize(s));
     {
@@ -177,7 +201,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
       cudaEventElapsedTime(&ms, s0, s1);
       ms_sweep += ms;
     }
-    launches += 4;
+    launches += 2;
     if (R.h_status->err) {
       status = -(int)R.h_status->err;
       break;
@@ -217,6 +241,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
     }
     rounds_total = R.h_status->rounds;
     evals_total = R.h_status->evals;
+    rule_evals_total = R.h_status->rule_evals;
     if (R.h_status->changed == 0) break;  // successful_steps did not move (:708-711)
     if ((long long)outer >= G.max_outer) {
       status = ECNE_E_NOCONVERGE;
@@ -234,6 +259,38 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
     cudaEventDestroy(s1);
     return fail(status, err.empty() ? status_text(status) : err);
   }
+#ifdef ECNE_PROFILE
+  {
+    std::vector<unsigned long long> pr((size_t)20000 + 40 * 148 * 4);
+    cudaMemcpy(pr.data(), d.prof, pr.size() * 8, cudaMemcpyDeviceToHost);
+    cudaMemset(d.prof, 0, pr.size() * 8);
+    // last launch's per-block breakdown of its first rounds
+    for (int r = 0; r < 40; ++r)
+      for (int b = 0; b < grid && b < 148; ++b) {
+        unsigned long long* q = &pr[20000 + ((size_t)r * grid + b) * 4];
+        if (q[3]) fprintf(stderr, "[blk] %d %d %llu %llu %llu %llu\n", r, b, q[0], q[1], q[2], q[3]);
+      }
+    {
+      unsigned long long nr = pr[7] < 4000 ? pr[7] : 4000;
+      fprintf(stderr, "[prof] per-round (block 0 thread 0): round cycles | records | sweep-phase cycles | long-row cycles\n");
+      for (unsigned long long i = 0; i < nr; ++i)
+        fprintf(stderr, "[round] %llu %llu %llu %llu %llu\n", i, pr[2048 + 4 * i], pr[2048 + 4 * i + 1],
+                pr[2048 + 4 * i + 2], pr[2048 + 4 * i + 3]);
+    }
+    const char* nm[6] = {"intra_block_wait", "grid_wait", "long_rows", "replay", "sweep", "-"};
+    for (int i = 0; i < 5; ++i) {
+      unsigned long long mx = 0, sum = 0;
+      int arg = 0;
+      for (int b = 0; b < grid; ++b) {
+        unsigned long long v = pr[b * 8 + i];
+        sum += v;
+        if (v > mx) { mx = v; arg = b; }
+      }
+      fprintf(stderr, "[prof] %-17s thread0 cycles: mean %.0f max %llu (block %d) per round mean %.0f max %.0f\n", nm[i],
+              (double)sum / grid, mx, arg, (double)sum / grid / pr[6], (double)mx / pr[6]);
+    }
+  }
+#endif
   // verdict + D2H
   launch_finalize(d, 0, R.d_ubits, R.d_kbits, R.d_counts, s);
   const size_t words = (R.n_vars + 63) / 64;
@@ -277,6 +334,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   res->outer_rounds = outer;
   res->inner_rounds = rounds_total;
   res->constraint_evals = evals_total + phase_evals;
+  res->rule_evals = rule_evals_total + phase_evals;
   res->sweep_launches = launches;
   res->ms_h2d = R.ms_h2d;
   res->ms_classify = R.ms_classify;
@@ -306,8 +364,9 @@ extern "C" int ecne_solve(const ecne_problem_t* problem, ecne_result_t* result) 
 
 // ---- sharding (wired up in dist.cu-less form: NCCL communicator owned here) ---------------------
 extern "C" int ecne_dist_unique_id(uint8_t out[128]) {
+  if (!NCCL.load()) return fail(ECNE_E_NCCL, "cannot load libnccl.so.2");
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return fail(ECNE_E_NCCL, "ncclGetUniqueId failed");
+  if (NCCL.GetUniqueId(&id) != ncclSuccess) return fail(ECNE_E_NCCL, "ncclGetUniqueId failed");
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   memcpy(out, &id, 128);
   return ECNE_OK;
@@ -316,7 +375,7 @@ extern "C" int ecne_dist_init(int rank, int world, const uint8_t unique_id[128])
   if (!G.inited) return fail(ECNE_E_CUDA, "call ecne_init first");
   if (world < 1 || rank < 0 || rank >= world) return fail(ECNE_E_BADARG, "bad rank/world");
   if (G.comm) {
-    ncclCommDestroy(G.comm);
+    NCCL.CommDestroy(G.comm);
     G.comm = nullptr;
   }
   G.rank = rank;
@@ -324,7 +383,8 @@ extern "C" int ecne_dist_init(int rank, int world, const uint8_t unique_id[128])
   if (world == 1) return ECNE_OK;
   ncclUniqueId id;
   memcpy(&id, unique_id, 128);
-  if (ncclCommInitRank(&G.comm, world, id, rank) != ncclSuccess)
+  if (!NCCL.load()) return fail(ECNE_E_NCCL, "cannot load libnccl.so.2");
+  if (NCCL.CommInitRank(&G.comm, world, id, rank) != ncclSuccess)
     return fail(ECNE_E_NCCL, "ncclCommInitRank failed");
   return ECNE_OK;
 }

@@ -37,6 +37,17 @@ enum : uint32_t {
   RF_P3_DIVZ = 1u << 14,   // ... with no non-constant key in A => divexact(_, 0) (:1467)
   RF_P4 = 1u << 15,        // rows (i, i+1) form the IsZero gadget          (:1493-1536)
   RF_LONG = 1u << 16,      // handled by a whole warp
+  RF_FAST = 1u << 17,      // <= 6 terms, no bound pattern: the inline fast path of the sweep
+};
+
+// 32-byte row record streamed by the sweep: flags + the row's wires inline (A u B terms first, then
+// C).  p99 row length is 3, so almost every row is evaluated from this one coalesced 32-byte load
+// plus its state-byte gathers; longer / pattern rows fall back to the CSR arrays.
+#define ROWREC_INLINE 6
+struct __align__(32) RowRec {
+  uint32_t rf;
+  uint8_t nAB, nC, inl, pad;
+  uint32_t c[ROWREC_INLINE];
 };
 
 struct __align__(16) RowAux {
@@ -51,7 +62,7 @@ struct __align__(16) RowAux {
 };
 
 // ---- per-wire flag bits -------------------------------------------------------------------------
-enum : uint32_t { WF_U = 1, WF_K = 2, WF_ABZ = 4 };
+enum : uint32_t { WF_U = 1, WF_K = 2, WF_ABZ = 4, WF_BND = 8 };  // BND: bounds were ever tightened
 
 // update record: OR `bits` into F, max `lbr` into LBR, min `ubr` into UBR
 struct __align__(16) Rec {
@@ -71,10 +82,11 @@ struct Status {            // device-resident, read back once per outer round
   unsigned long long changed;      // state changes of the current outer round ("successful_steps")
   unsigned long long rounds;       // Jacobi rounds of the single-row sweep
   unsigned long long evals;        // rows visited
+  unsigned long long rule_evals;   // rows whose rule set was actually run (not skipped by the filter)
   unsigned int err;                // first error (as -status), 0 = none
   unsigned int p2_cand;            // candidates of the linear-system sweep
   unsigned int rec_overflow;
-  unsigned int pad;
+  unsigned int bepoch;             // number of rounds so far that tightened a bound
 };
 
 struct Dev {
@@ -89,6 +101,9 @@ struct Dev {
   const uint32_t* rflags;
   const RowAux* aux;
   const uint32_t* long_rows;
+  uint8_t* long_done;        // per long row: can never fire again
+  const RowRec* rec;
+  unsigned long long* live;  // per sweep thread: bitmask of its rows that can still fire
   uint8_t* solved;
   // static values
   const fr::u256* roots;  // [n2a][2]
@@ -114,22 +129,36 @@ struct Dev {
   // records: three rotating lists
   Rec* recs[3];
   unsigned int* rec_count;  // [3]
+  unsigned int* bnd_flag;   // [3] set when a round tightened any bound
+  uint32_t* c5sig;          // [N] state signature of the last failed Case-5 evaluation of a row
   uint32_t rec_cap;
   // scratch
   unsigned long long* abz_claim;  // [V+1]
   unsigned long long* p2_key;     // [N] candidate keys
   uint32_t* p2_row;               // [N]
   unsigned int* barrier;          // grid barrier counter
+  unsigned long long* prof;       // [grid][8] per-block cycle counters (ECNE_PROFILE builds only)
   Status* st;
   // sharding: this rank sweeps rows [row_lo, row_hi)
   uint32_t row_lo, row_hi;
 };
 
-// ---- state access (L2-coherent loads: the arrays are written by atomics from other SMs) ---------
+// ---- state access -----------------------------------------------------------------------------------
+// The buffer a round READS is not written during that round (updates go to the other buffer), and
+// rounds are separated by a grid barrier whose acquire makes remote writes visible (and drops the
+// SM's L1 lines) — so ordinary L1-cacheable loads are correct here, exactly as after grid.sync(),
+// and neighbouring rows that touch neighbouring wires share L1 sectors instead of paying one L2
+// sector per state byte.
 __device__ __forceinline__ uint32_t ld_flag(const uint8_t* F, uint32_t w) {
-  return (uint32_t)__ldcg(F + w);
+  uint32_t v;
+  asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(v) : "l"(F + w));
+  return v;
 }
-__device__ __forceinline__ uint32_t ld_u32(const uint32_t* p, uint32_t i) { return __ldcg(p + i); }
+__device__ __forceinline__ uint32_t ld_u32(const uint32_t* p, uint32_t i) {
+  uint32_t v;
+  asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p + i));
+  return v;
+}
 
 __device__ __forceinline__ void raise(const Dev& d, int status) {
   atomicCAS(&d.st->err, 0u, (unsigned int)(-status));
@@ -160,49 +189,114 @@ __device__ __forceinline__ void refresh_b01(const Dev& d, int buf, uint32_t w) {
   }
 }
 
-// Apply one update to buffer `buf`; returns true when it changed anything there.
-__device__ __forceinline__ bool apply_update(const Dev& d, int buf, uint32_t w, uint32_t bits,
+// Apply one update to buffer `buf`; returns bit0: it changed something there, bit1: a bound moved.
+__device__ __forceinline__ uint32_t apply_update(const Dev& d, int buf, uint32_t w, uint32_t bits,
                                              uint32_t lbr, uint32_t ubr) {
   bool ch = false;
-  if (bits) ch |= or_flag(d.F[buf], w, bits) != 0;
+  if (lbr != ECNE_NO_LB || ubr != ECNE_NO_UB) bits |= WF_BND;
   bool bch = false;
   if (lbr != ECNE_NO_LB) bch |= atomicMax(d.LBR[buf] + w, lbr) < lbr;
   if (ubr != ECNE_NO_UB) bch |= atomicMin(d.UBR[buf] + w, ubr) > ubr;
   if (bch) refresh_b01(d, buf, w);
-  return ch | bch;
+  // the flag byte goes last: a reader that sees WF_BND also sees the ranks (both are re-read
+  // from L2 only after the next grid barrier anyway)
+  if (bits) ch |= or_flag(d.F[buf], w, bits) != 0;
+  return ((ch | bch) ? 1u : 0u) | (bch ? 2u : 0u);
 }
 
-// Apply to the write buffer and, when it changed it, log the record for the other buffer.
+// Log an update for the other buffer and apply it to the write buffer.  A row only calls this when
+// its evaluation against the snapshot wants something the snapshot does not have, so every record
+// is a real state change (possibly duplicated by another row of the same round — harmless) and
+// "no record in a round" is exactly "fixpoint".  The flag OR is fire-and-forget (RED) and the slot
+// allocation is the only round trip on the caller's critical path.
 __device__ __forceinline__ void emit(const Dev& d, int wbuf, int list, uint32_t w, uint32_t bits,
                                      uint32_t lbr = ECNE_NO_LB, uint32_t ubr = ECNE_NO_UB) {
-  if (apply_update(d, wbuf, w, bits, lbr, ubr)) {
-    unsigned int i = atomicAdd(d.rec_count + list, 1u);
-    if (i < d.rec_cap) {
-      Rec r;
-      r.wire = w;
-      r.bits = bits;
-      r.lbr = lbr;
-      r.ubr = ubr;
-      d.recs[list][i] = r;
-    } else {
-      d.st->rec_overflow = 1;
-    }
+  const bool bnd = lbr != ECNE_NO_LB || ubr != ECNE_NO_UB;
+  if (bnd) bits |= WF_BND;
+  unsigned int i = atomicAdd(d.rec_count + list, 1u);
+  if (bnd) {
+    d.bnd_flag[list] = 1u;
+    apply_update(d, wbuf, w, bits, lbr, ubr);
+  } else {
+    unsigned int* word = (unsigned int*)(d.F[wbuf] + (w & ~3u));
+    atomicOr(word, bits << ((w & 3u) * 8));  // result unused: compiles to RED
+  }
+  if (i < d.rec_cap) {
+    Rec r;
+    r.wire = w;
+    r.bits = bits;
+    r.lbr = lbr;
+    r.ubr = ubr;
+    d.recs[list][i] = r;
+  } else {
+    d.st->rec_overflow = 1;
   }
 }
 
-// grid-wide barrier for a cooperatively launched (co-resident) grid
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
+#ifdef ECNE_PROFILE
+static __device__ long long g_prof_dummy;
+#define g_prof_intra prof_intra
+#define g_prof_grid prof_grid
+#endif
+// Grid-wide barrier for a cooperatively launched (co-resident) grid, one arrival per block.
+// `bar[0]` counts arrivals; the LAST arriver publishes {epoch, payload} in `bar[32..33]` (another
+// 128-byte line), which is what everybody else polls — the contended atomic line is never polled.
+// The payload is the value of *payload_src read after every block has arrived (the round's record
+// count = the device-wide changed flag; bit 31 = "a bound was tightened this round"), so no second
+// round trip is needed to learn it.
+__device__ __forceinline__ unsigned int grid_barrier(unsigned int* bar, unsigned int& epoch,
+                                                     const unsigned int* payload_src,
+                                                     const unsigned int* flag_src = nullptr
+#ifdef ECNE_PROFILE
+                                                     , long long* pprof = nullptr
+#endif
+) {
+#ifdef ECNE_PROFILE
+  long long prof_intra = 0, prof_grid = 0;
+#endif
+  __shared__ unsigned int s_payload;
+#ifdef ECNE_PROFILE
+  long long ta = clock64();
+#endif
   __syncthreads();
+#ifdef ECNE_PROFILE
+  long long tb = clock64();
+#endif
   if (threadIdx.x == 0) {
-    __threadfence();
-    unsigned int target = (epoch + 1) * gridDim.x;
-    atomicAdd(counter, 1u);
-    while (*((volatile unsigned int*)counter) < target) {
+    epoch += 1;
+    // arrive: one release-RMW (orders this block's writes — bar.sync above made them cumulative)
+    unsigned int old;
+    asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+    unsigned long long* rel = (unsigned long long*)(bar + 32);
+    unsigned int payload;
+    if (old == epoch * gridDim.x - 1) {
+      // last arriver: everybody's records are visible (acquire through the RMW chain)
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      payload = payload_src ? *((volatile const unsigned int*)payload_src) : 0u;
+      if (flag_src && *((volatile const unsigned int*)flag_src)) payload |= 0x80000000u;
+      unsigned long long v = ((unsigned long long)payload << 32) | epoch;
+      asm volatile("st.release.gpu.u64 [%0], %1;" ::"l"(rel), "l"(v) : "memory");
+    } else {
+      unsigned long long v;
+      do {
+        asm volatile("ld.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(rel) : "memory");
+      } while ((unsigned int)(v & 0xffffffffu) < epoch);
+      payload = (unsigned int)(v >> 32);
     }
-    __threadfence();
+    s_payload = payload;
+#ifdef ECNE_PROFILE
+    g_prof_intra += tb - ta;
+    g_prof_grid += clock64() - tb;
+#endif
   }
-  epoch += 1;
   __syncthreads();
+#ifdef ECNE_PROFILE
+  if (threadIdx.x == 0 && pprof) {
+    pprof[0] += prof_intra;
+    pprof[1] += prof_grid;
+  }
+#endif
+  return s_payload;
 }
 
 }  // namespace ecne

@@ -10,12 +10,12 @@
 namespace ecne {
 
 // kernels.cu
-cudaError_t launch_reset(const Dev& d, cudaStream_t s);
+cudaError_t launch_reset(const Dev& d, int grid, cudaStream_t s);
 int p1_grid_size(int device);
+int p1_threads();
 cudaError_t launch_p1(const Dev& d, int rbuf, unsigned int max_rounds, int grid, cudaStream_t s);
 void launch_replay(const Dev& d, int buf, cudaStream_t s);
 void launch_p0(const Dev& d, cudaStream_t s);
-void launch_p2_scan(const Dev& d, int rbuf, cudaStream_t s);
 void launch_p2_groups(const Dev& d, int rbuf, uint32_t n_cand, const unsigned long long* keys,
                       const uint32_t* rows, cudaStream_t s);
 void launch_p3(const Dev& d, int rbuf, cudaStream_t s);

@@ -11,7 +11,7 @@
 
 namespace ecne {
 
-#define LONG_T 32u          // rows with more non-zero terms than this get a whole warp
+#define LONG_T 6u           // rows with more non-zero terms than the inline record holds get a whole warp
 #define N_CONST 255u        // 2^k-1 (k = 0..253) and p-1
 #define C3_INLINE_MAX 255u  // longer bit-decomposition candidates go through the 2^i mod p table
 
@@ -447,6 +447,33 @@ __global__ void k_layout(Raw r, const uint32_t* keep, const uint32_t* pos, const
   coef[dst] = c;
   nontriv[w] = 1;
 }
+// 32-byte sweep records: flags + up to 6 inline wires (A u B first, then C)
+__global__ void k_rowrec(uint32_t N, const uint32_t* seg, const uint32_t* col, uint32_t* rflags, RowRec* rec) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  uint32_t rf = rflags[row];
+  const uint32_t s0 = seg[3 * row], s2 = seg[3 * row + 2], s3 = seg[3 * row + 3];
+  RowRec r;
+  r.pad = 0;
+  for (int j = 0; j < ROWREC_INLINE; ++j) r.c[j] = 1;
+  const uint32_t tot = s3 - s0;
+  if (tot <= ROWREC_INLINE) {
+    r.inl = 1;
+    r.nAB = (uint8_t)(s2 - s0);
+    r.nC = (uint8_t)(s3 - s2);
+    for (uint32_t t = s0; t < s3; ++t) r.c[t - s0] = col[t];
+    // fast-path rows: no bound pattern, or exactly "x = const" (2B alone), or exactly "x - y = 0"
+    // (4A, which always carries the l == 2 Case-3 flags as well)
+    const uint32_t pat = rf & (RF_2B | RF_C3 | RF_4A | RF_4B);
+    if (!(rf & RF_LONG) && (pat == 0 || pat == RF_2B || pat == (RF_4A | RF_C3))) rf |= RF_FAST;
+  } else {
+    r.inl = 0;
+    r.nAB = r.nC = 0;
+  }
+  r.rf = rf;
+  rflags[row] = rf;
+  rec[row] = r;
+}
 __global__ void k_mark(const uint32_t* list, uint32_t n, uint8_t* nontriv) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) nontriv[list[i]] = 1;
@@ -752,6 +779,11 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   if (n_sp_out) k_mark<<<nb(n_sp_out, 256), 256, 0, s>>>(d_sp_out, (uint32_t)n_sp_out, d_nontriv);
   if (p->n_targets) k_mark<<<nb(p->n_targets, 256), 256, 0, s>>>(d_targets, (uint32_t)p->n_targets, d_nontriv);
   if (cnt.n_long) k_long_rows<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_rflags, d_long, d_nlong);
+  RowRec* d_rec;
+  CK(A.alloc(&d_rec, N));
+  if (N) k_rowrec<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_segnz, d_col, d_rflags, d_rec);
+  CK(A.alloc(&d.live, (size_t)p1_grid_size(0) * p1_threads()));
+  CK(A.alloc(&d.long_done, (size_t)cnt.n_long));
 
   // ---- wire state, records, scratch -----------------------------------------------------------
   for (int b = 0; b < 2; ++b) {
@@ -765,10 +797,14 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(A.alloc(&d.abz_claim, V + 1));
   CK(A.alloc(&d.solved, N + 2));
   CK(A.alloc(&d.sp_solved, n_sp));
-  d.rec_cap = (uint32_t)std::min<uint64_t>(2 * V + 4096, 0x7ffffff0ULL);
+  d.rec_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2 * V, nnz) + 4096, 0x7ffffff0ULL);
   for (int l = 0; l < 3; ++l) CK(A.alloc(&d.recs[l], d.rec_cap));
   CK(A.alloc(&d.rec_count, 4));
-  CK(A.alloc(&d.barrier, 4));
+  CK(A.alloc(&d.bnd_flag, 4));
+  CK(A.alloc(&d.c5sig, N));
+  CK(A.alloc(&d.barrier, 64));
+  CK(A.alloc(&d.prof, (size_t)20000 + 40 * 148 * 4));
+  CK(cudaMemsetAsync(d.prof, 0, ((size_t)20000 + 40 * 148 * 4) * sizeof(unsigned long long), s));
   CK(A.alloc(&d.st, 1));
   CK(A.alloc(&d.p2_key, N));
   CK(A.alloc(&d.p2_row, N));
@@ -793,6 +829,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   d.rflags = d_rflags;
   d.aux = d_aux;
   d.long_rows = d_long;
+  d.rec = d_rec;
   d.roots = d_roots;
   d.tvals = d_tvals + N_CONST;
   d.table = d_table;

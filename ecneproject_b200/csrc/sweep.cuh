@@ -35,6 +35,28 @@ struct Grp {
   }
 };
 
+// Walk terms [s, e) of the CSR with G lanes, U terms per lane in flight: all U wire indices are
+// loaded first, then all U state bytes of array `A` (F or B) are gathered, then `fn(wire, byte)`
+// runs.  This turns 2*ceil(n/G) dependent L2 round trips into 2*ceil(n/(G*U)).
+template <int G, int U, class Fn>
+__device__ __forceinline__ void scan_terms(const Dev& d, const uint8_t* A, uint32_t s, uint32_t e,
+                                           uint32_t lane, Fn fn) {
+  for (uint32_t base = s; base < e; base += G * U) {
+    uint32_t w[U], f[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t t = base + (uint32_t)u * G + lane;
+      w[u] = t < e ? d.col[t] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) f[u] = w[u] != 0xffffffffu ? ld_flag(A, w[u]) : 0u;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (w[u] != 0xffffffffu) fn(w[u], f[u]);
+  }
+}
+#define SCAN_U(G) ((G) == 1 ? 4 : 8)
+
 // What earlier cases of this evaluation did to the row's own wires (group-uniform).
 struct Overlay {
   uint32_t w[2], lb[2], ub[2];
@@ -79,7 +101,7 @@ struct RowCtx {
   __device__ __forceinline__ bool b01(uint32_t w) const {
     int i = ov.find(w);
     if (i >= 0) return ov.lb[i] == d.r0 && ov.ub[i] == d.r1;
-    return __ldcg(d.B[rbuf] + w) != 0;
+    return ld_flag(d.B[rbuf], w) != 0;
   }
   __device__ __forceinline__ bool uniq(uint32_t w) const {
     return ov.all_unique || (ld_flag(d.F[rbuf], w) & WF_U);
@@ -172,29 +194,30 @@ __device__ __noinline__ bool case5(const RowCtx& c) {
   return true;
 }
 
-// The rule set on one row.  `rounds_fresh`: nothing.
+// The rule set on one row (generic path: any length, every pattern).
+// Returns true when the row can never fire again (so the caller may stop sweeping it): it is
+// latched as solved, or it has no bound pattern and no non-unique wire left in C.
 template <int G>
-__device__ __forceinline__ void eval_row(const Dev& d, int rbuf, int wbuf, int list, uint32_t row) {
+__device__ __noinline__ bool eval_row(const Dev& d, int rbuf, int wbuf, int list, uint32_t row,
+                                      uint32_t bepoch) {
   const uint32_t lane = Grp<G>::lane();
   const uint32_t rf = d.rflags[row];
   uint8_t latch = d.solved[row];
-  if (latch & 1) return;  // equation_solved (:820-822)
+  if (latch & 1) return true;  // equation_solved (:820-822)
   const uint8_t* F = d.F[rbuf];
   const uint32_t s0 = d.seg[3 * row], s2 = d.seg[3 * row + 2], s3 = d.seg[3 * row + 3];
 
   // ---- gather: non-unique counts over A u B and over C --------------------------------------
   uint32_t nuAB = 0, nuC = 0, wC = 0, kmiss = 0, abzmiss = 0;
-  for (uint32_t t = s0 + lane; t < s2; t += G) nuAB += (ld_flag(F, d.col[t]) & WF_U) ? 0u : 1u;
-  for (uint32_t t = s2 + lane; t < s3; t += G) {
-    uint32_t w = d.col[t];
-    uint32_t f = ld_flag(F, w);
+  scan_terms<G, SCAN_U(G)>(d, F, s0, s2, lane, [&](uint32_t, uint32_t f) { nuAB += (f & WF_U) ? 0u : 1u; });
+  scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
     if (!(f & WF_U)) {
       nuC += 1;
       wC = w;
       kmiss += (f & WF_K) ? 0u : 1u;
       abzmiss += (f & WF_ABZ) ? 0u : 1u;
     }
-  }
+  });
   if (G > 1) {
     nuAB = Grp<G>::sum(nuAB);
     nuC = Grp<G>::sum(nuC);
@@ -224,14 +247,14 @@ __device__ __forceinline__ void eval_row(const Dev& d, int rbuf, int wbuf, int l
   // ---- Case 2a (:875-942) -----------------------------------------------------------------
   if (rf & RF_2A_NOVAR) {
     raise(d, ECNE_E_BOUNDS);
-    return;
+    return true;
   }
   if (rf & RF_2A) {
     const RowAux a = d.aux[row];
     if (!(ld_flag(F, a.w1) & WF_K)) {
       if (rf & RF_2A_DIVZ) {
         raise(d, ECNE_E_DIVZERO);
-        return;
+        return true;
       }
       if (lane == 0) {
         c.out(a.w1, WF_K, ECNE_NO_LB, (rf & RF_2A_BOOL) ? d.r1 : ECNE_NO_UB);
@@ -240,8 +263,9 @@ __device__ __forceinline__ void eval_row(const Dev& d, int rbuf, int wbuf, int l
       }
     }
   }
-  if (!(rf & RF_LINEAR)) return;  // (:944-946)
-  if (!(rf & (RF_2B | RF_C3 | RF_4A | RF_4B)) && nuC == 0) return;
+  const bool plain = !(rf & (RF_2A | RF_2B | RF_C3 | RF_4A | RF_4B));
+  if (!(rf & RF_LINEAR)) return plain && nuC == 0;  // (:944-946)
+  if (plain && nuC == 0) return true;
 
   const RowAux a = d.aux[row];
   // ---- Case 2b (:949-988) -----------------------------------------------------------------
@@ -262,10 +286,12 @@ __device__ __forceinline__ void eval_row(const Dev& d, int rbuf, int wbuf, int l
     for (int o = 0; o < norient; ++o) {
       const uint32_t nk = o == 0 ? a.w2 : a.w5;
       bool ok = true;
-      for (uint32_t t = s2 + lane; t < s3; t += G) {
-        uint32_t w = d.col[t];
-        if (w != nk && !c.b01(w)) ok = false;
-      }
+      scan_terms<G, SCAN_U(G)>(d, d.B[rbuf], s2, s3, lane, [&](uint32_t w, uint32_t b) {
+        if (w == nk) return;
+        const int oi = c.ov.find(w);
+        const bool is01 = oi >= 0 ? (c.ov.lb[oi] == d.r0 && c.ov.ub[oi] == d.r1) : (b != 0);
+        if (!is01) ok = false;
+      });
       ok = Grp<G>::all(ok);
       if (!ok) continue;
       uint32_t l, u;
@@ -275,10 +301,9 @@ __device__ __forceinline__ void eval_row(const Dev& d, int rbuf, int wbuf, int l
         c.ov.set(nk, d.r0, a.rank_b, true);
       }
       if (nuC > 0 && c.uniq(nk)) {  // (:1049-1067)
-        for (uint32_t t = s2 + lane; t < s3; t += G) {
-          uint32_t w = d.col[t];
-          if (w != nk && !(ld_flag(F, w) & WF_U)) c.out(w, WF_U | WF_K);
-        }
+        scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
+          if (w != nk && !(f & WF_U)) c.out(w, WF_U | WF_K);
+        });
         nuC = 0;
         c.ov.all_unique = true;
       }
@@ -322,38 +347,42 @@ __device__ __forceinline__ void eval_row(const Dev& d, int rbuf, int wbuf, int l
     }
   }
 
-  if (nuC == 0) return;
+  if (nuC == 0) return plain;
   // ---- Case 5 (:1235-1298) ----------------------------------------------------------------
   bool local_k = (c.ov.n > 0 && c.ov.k[0]) || (c.ov.n > 1 && c.ov.k[1]);
-  if (kmiss == 0 || local_k) {
+  // Case 5 is a pure function of the row's non-unique set (uniqueness is monotone, so its size
+  // identifies it), their is_known bits (all set here) and bounds: skip it when it already failed
+  // on exactly this state.
+  const uint32_t sig = (bepoch << 12) | (nuC & 0xfffu);
+  if ((kmiss == 0 || local_k) && d.c5sig[row] != sig) {
     if (case5<G>(c)) {
-      for (uint32_t t = s2 + lane; t < s3; t += G) {
-        uint32_t w = d.col[t];
-        if (!(ld_flag(F, w) & WF_U)) c.out(w, WF_U | WF_K);
-      }
-      return;
+      scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
+        if (!(f & WF_U)) c.out(w, WF_U | WF_K);
+      });
+      return plain;
     }
+    if (lane == 0 && kmiss == 0 && !local_k) d.c5sig[row] = sig;
   }
   // ---- Case 6 (:1304-1348) ----------------------------------------------------------------
   if (abzmiss == 0) {
     uint32_t lo = 0xffffffffu, hi = 0;
-    for (uint32_t t = s2 + lane; t < s3; t += G) {
-      uint32_t w = d.col[t];
-      if (!(ld_flag(F, w) & WF_U)) {
+    scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
+      if (!(f & WF_U)) {
         uint32_t z = (uint32_t)d.abz[w];
         lo = z < lo ? z : lo;
         hi = z > hi ? z : hi;
       }
-    }
+    });
     lo = Grp<G>::min(lo);
     hi = Grp<G>::max(hi);
     if (lo == hi) {
-      for (uint32_t t = s2 + lane; t < s3; t += G) {
-        uint32_t w = d.col[t];
-        if (!(ld_flag(F, w) & WF_U)) c.out(w, WF_U | WF_K);
-      }
+      scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
+        if (!(f & WF_U)) c.out(w, WF_U | WF_K);
+      });
+      return plain;
     }
   }
+  return false;
 }
 
 }  // namespace ecne

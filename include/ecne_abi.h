@@ -101,6 +101,8 @@ typedef struct ecne_result {
   uint64_t sweep_launches;      /* kernels launched by this solve                            */
   double ms_h2d, ms_classify, ms_solve, ms_d2h, ms_exchange, ms_total;
   double ms_sweep;              /* device time inside the single-row sweep kernel only       */
+  uint64_t rule_evals;          /* of constraint_evals: rows whose rule set was re-run in full (a
+                                   swept row none of whose wires changed is settled by the filter) */
 } ecne_result_t;
 
 /* ---- life cycle ------------------------------------------------------------------------- */

@@ -740,10 +740,11 @@ struct Solver {
     }
   }
 
-  void run(uint64_t max_pops) {
+  void run(uint64_t max_pops, uint64_t max_outer) {
     int64_t prev = -1;
     while (true) {
       if (prev == (int64_t)steps) break;
+      if (max_outer && outer >= max_outer) break;  // bounded sample for the CPU-baseline timing
       prev = (int64_t)steps;
       ++outer;
       specials_phase();
@@ -774,12 +775,15 @@ struct Solver {
 
 thread_local std::string g_err;
 uint64_t g_max_pops = 0;
+uint64_t g_max_outer = 0;
 uint64_t g_last_counters[32];
 
 }  // namespace
 
 extern "C" const char* ecne_oracle_last_error(void) { return g_err.c_str(); }
 extern "C" void ecne_oracle_set_max_pops(uint64_t n) { g_max_pops = n; }
+// stop after n outer rounds (0 = run to the fixpoint); only for timing a bounded sample
+extern "C" void ecne_oracle_set_max_outer(uint64_t n) { g_max_outer = n; }
 // [0]=pops [1]=sweep visits [2]=steps [3..]=per-rule firing counters (fired[1..14])
 extern "C" void ecne_oracle_counters(uint64_t* out, int n) {
   for (int i = 0; i < n && i < 32; ++i) out[i] = g_last_counters[i];
@@ -796,7 +800,7 @@ extern "C" int ecne_oracle_solve(const ecne_problem_t* problem, ecne_result_t* r
   int status = ECNE_OK;
   try {
     S.setup();
-    S.run(g_max_pops);
+    S.run(g_max_pops, g_max_outer);
   } catch (const OracleError& e) {
     g_err = e.msg;
     status = e.code;
@@ -858,8 +862,30 @@ extern "C" int ecne_oracle_solve(const ecne_problem_t* problem, ecne_result_t* r
   res->outer_rounds = S.outer;
   res->inner_rounds = S.pops;
   res->constraint_evals = S.pops + S.sweep_visits;
+  res->rule_evals = S.pops + S.sweep_visits;
   res->sweep_launches = 0;
   res->ms_h2d = res->ms_classify = res->ms_d2h = res->ms_exchange = res->ms_sweep = 0;
   res->ms_solve = res->ms_total = std::chrono::duration<double, std::milli>(t1 - t0).count();
   return ECNE_OK;
+}
+
+// Field known-answer hook (tests/test_field_kat.py): the oracle's own arithmetic on n elements.
+// op: 0 add, 1 sub, 2 mul, 3 inv (0 -> 0), 4 neg, 5 divexact(-a, b).  a, b, out: [n*4] canonical.
+extern "C" int ecne_oracle_fr(int op, uint64_t n, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  for (uint64_t i = 0; i < n; ++i) {
+    U256 x, y = ZERO, r;
+    memcpy(x.l, a + 4 * i, 32);
+    if (b) memcpy(y.l, b + 4 * i, 32);
+    switch (op) {
+      case 0: r = fadd(x, y); break;
+      case 1: r = fsub(x, y); break;
+      case 2: r = fmul(x, y); break;
+      case 3: r = is_zero(x) ? x : finv(x); break;
+      case 4: r = fneg(x); break;
+      case 5: r = is_zero(y) ? ZERO : fmul(fneg(x), finv(y)); break;
+      default: r = x;
+    }
+    memcpy(out + 4 * i, r.l, 32);
+  }
+  return 0;
 }

@@ -24,6 +24,9 @@ def lib():
         l.ecne_oracle_last_error.restype = C.c_char_p
         l.ecne_oracle_counters.argtypes = [_abi.u64p, C.c_int]
         l.ecne_oracle_set_max_pops.argtypes = [C.c_uint64]
+        l.ecne_oracle_set_max_outer.argtypes = [C.c_uint64]
+        l.ecne_oracle_fr.argtypes = [C.c_int, C.c_uint64, _abi.u64p, _abi.u64p, _abi.u64p]
+        l.ecne_oracle_fr.restype = C.c_int
         _lib = l
     return _lib
 

@@ -1,0 +1,114 @@
+"""Host-side callers of the hot path: the .r1cs loader and abstraction() (libecne_host.so), and that
+both native libraries load and export every symbol the headers declare."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ecneproject_b200 import _abi, api, fixtures
+from helpers import P, from_limbs, py_read_r1cs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols(name):
+    txt = open(os.path.join(ROOT, "include", name)).read()
+    return sorted(set(re.findall(r"\b(ecne_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_engine_exports_every_declared_symbol():
+    lib = _abi.engine_lib()
+    syms = header_symbols("ecne_abi.h")
+    assert set(syms) == set(_abi.ENGINE_SYMBOLS)
+    for s in syms:
+        assert getattr(lib, s) is not None
+    assert lib.ecne_version() == 1
+
+
+def test_host_exports_every_declared_symbol():
+    lib = _abi.host_lib()
+    syms = header_symbols("ecne_host.h")
+    assert set(syms) == set(_abi.HOST_SYMBOLS)
+    for s in syms:
+        assert getattr(lib, s) is not None
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _abi.engine_lib()
+    assert lib.ecne_init(0) == _abi.ECNE_E_CUDA
+    assert b"no CPU fallback" in lib.ecne_last_error()
+    r = api.readR1CS(fixtures.path("trivial_mult.r1cs"))
+    ph = api.ProblemHandle(r, [], r.known, r.targets, r.n_vars)
+    res = api.SolveResult(r.n_vars)
+    assert lib.ecne_solve(C.byref(ph.c), C.byref(res.c)) == _abi.ECNE_E_CUDA
+
+
+@pytest.mark.parametrize("rel", ["trivial_mult.r1cs", "target/division.r1cs", "multiplexer_33.r1cs",
+                                 "poseidon.r1cs", "ecne_circomlib_tests/Num2Bits_strict@bitify.r1cs",
+                                 "ecne_circomlib_tests/Poseidon@poseidon.r1cs", "biglessthan.r1cs"])
+def test_loader_matches_python_restatement(rel):
+    path = fixtures.path(rel)
+    r = api.readR1CS(path)
+    rows, known, targets, n_vars = py_read_r1cs(path)
+    assert r.n_rows == len(rows) and r.n_vars == n_vars
+    assert r.known.tolist() == known and r.targets.tolist() == targets
+    coef = from_limbs(r.coef)
+    for i, forms in enumerate(rows):
+        for f, d in enumerate(forms):
+            s, e = int(r.seg_ptr[3 * i + f]), int(r.seg_ptr[3 * i + f + 1])
+            got = {int(r.col[t]): coef[t] for t in range(s, e)}
+            assert got == d, (i, f)
+
+
+def test_loader_errors():
+    lib = _abi.host_lib()
+    out = C.POINTER(_abi.R1CSStruct)()
+    assert lib.ecne_read_r1cs(b"/nonexistent/x.r1cs", C.byref(out)) == _abi.ECNE_E_IO
+    raw = bytearray(open(fixtures.path("trivial_mult.r1cs"), "rb").read())
+    bad = bytes(raw[:4]) + (2).to_bytes(4, "little") + bytes(raw[8:])
+    buf = (C.c_uint8 * len(bad)).from_buffer_copy(bad)
+    assert lib.ecne_read_r1cs_mem(buf, len(bad), C.byref(out)) == _abi.ECNE_E_ASSERT  # version (:58)
+    bad = bytes(raw[:8]) + (4).to_bytes(4, "little") + bytes(raw[12:])
+    buf = (C.c_uint8 * len(bad)).from_buffer_copy(bad)
+    assert lib.ecne_read_r1cs_mem(buf, len(bad), C.byref(out)) == _abi.ECNE_E_ASSERT  # sections (:62)
+    with pytest.raises(OSError):
+        api.readR1CS("/nonexistent/x.r1cs")
+
+
+def test_abstraction_match_counts():
+    # bench/bench_abstraction.jl:16 asserts exactly one match of bigmultshortlong in bigmultmodp86_3
+    main = api.readR1CS(fixtures.path("bigmultmodp86_3.r1cs"))
+    sub = api.readR1CS(fixtures.path("bigmultshortlong86_3.r1cs"))
+    sp, red = api.abstraction("bigmultmodp", main, sub)
+    assert len(sp) == 1
+    assert red.n_rows == main.n_rows - sub.n_rows
+    name, ins, outs = sp.as_list()[0]
+    assert len(ins) == len(sub.known) - 1 and len(outs) == len(sub.targets)
+
+
+def test_abstraction_trusted_configs():
+    # reduced sizes / special counts of SURVEY.md §8a
+    red, sp, main = api.prepare(fixtures.path("secp256k1.r1cs"),
+                                [fixtures.path("bigmultmodp.r1cs"), fixtures.path("biglessthan.r1cs")],
+                                ["BigMultModP", "BigLessThan"])
+    assert (main.n_rows, red.n_rows, len(sp)) == (15935, 3985, 4)
+    assert [n for n, _, _ in sp.as_list()] == ["BigMultModP"] * 3 + ["BigLessThan"]
+    ped = ["tornadocash_circuits/Pedersen248@pedersen.r1cs", "tornadocash_circuits/Pedersen496@pedersen.r1cs"]
+    red, sp, main = api.prepare(fixtures.path("tornadocash_circuits/withdraw.r1cs"),
+                                [fixtures.path(p) for p in ped], ["Pedersen248", "Pedersen496"])
+    assert (main.n_rows, red.n_rows, len(sp)) == (24129, 1996, 2)
+    # longest trusted circuit is abstracted first (:527)
+    assert sp.as_list()[0][0] == "Pedersen496"
+
+
+def test_abstraction_no_match_is_identity():
+    main = api.readR1CS(fixtures.path("poseidon.r1cs"))
+    sub = api.readR1CS(fixtures.path("multiplexer_33.r1cs"))
+    sp, red = api.abstraction("x", main, sub)
+    assert len(sp) == 0 and red.n_rows == main.n_rows
+    assert np.array_equal(red.col, main.col) and np.array_equal(red.coef, main.coef)

@@ -1,0 +1,73 @@
+"""The oracle is pinned before it is trusted (prompt ③):
+  * every Boolean the reference itself asserts (test/runtests.jl, examples/*.jl, README.md:106);
+  * the survey's independent Python restatement (SURVEY.md Appendix B.1 -> golden/survey_appendix_b.json);
+  * the committed oracle goldens (golden/oracle_goldens.json) that the GPU parity tests diff against.
+"""
+import hashlib
+import json
+import os
+
+import pytest
+
+from configs import CONFIGS
+from ecneproject_b200 import api, fixtures
+import oracle_lib
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SURVEY = json.load(open(os.path.join(GOLD, "survey_appendix_b.json")))
+ORACLE = json.load(open(os.path.join(GOLD, "oracle_goldens.json")))
+
+SMALL = [n for n, c in CONFIGS.items() if not c.get("big")]
+
+
+def run_oracle(name):
+    cfg = CONFIGS[name]
+    reduced, specials, main = api.prepare(fixtures.path(cfg["main"]),
+                                          [fixtures.path(t) for t in cfg.get("trusted", [])],
+                                          cfg.get("trusted_names", []))
+    return oracle_lib.solve(reduced, specials, main.known, main.targets, main.n_vars,
+                            cfg.get("secp_solve", False)), reduced, main
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_oracle_matches_goldens_and_pins(name):
+    res, reduced, main = run_oracle(name)
+    g = ORACLE[name]
+    assert g["status"] == 0
+    assert bool(res.c.verdict) == g["verdict"]
+    assert hashlib.sha256(res.unique_bytes()).hexdigest() == g["sha_unique"]
+    assert hashlib.sha256(res.known_bytes()).hexdigest() == g["sha_known"]
+    assert (res.c.n_unique_nontrivial, res.c.n_nontrivial, res.c.n_targets_unique) == (g["uniq"], g["nontriv"], g["tgt"])
+    assert res.c.outer_rounds == g["rounds"] and int(res.oracle_counters[0]) == g["pops"]
+    assert reduced.n_rows == g["reduced_rows"]
+    pinned = CONFIGS[name].get("pinned")
+    if pinned is not None:  # the reference's own assertion
+        assert bool(res.c.verdict) == pinned[0], f"reference pins {pinned}"
+    if name.startswith("circomlib/"):
+        s = SURVEY[name[len("circomlib/"):]]
+        assert bool(res.c.verdict) == s["verdict"]
+        assert (res.c.n_unique_nontrivial, res.c.n_nontrivial) == (s["uniq"], s["nontriv"])
+        assert (res.c.n_targets_unique, len(main.targets)) == (s["tgt"], s["ntgt"])
+        assert res.c.n_unique == s["n_unique"]
+        assert hashlib.sha256(res.unique_bytes()).hexdigest()[:12] == s["sha12"]
+        assert (res.c.outer_rounds, int(res.oracle_counters[0])) == (s["rounds"], s["pops"])
+
+
+def test_big_goldens_present_and_pinned():
+    # ecdsa takes ~10 s of oracle time + 20 s prep per config: minted by tools/make_goldens.py --with-ecdsa
+    g = ORACLE["ecdsa+secp256k1"]
+    assert g["verdict"] is True  # examples/ecdsa_secp_abstraction.jl:4
+    assert (g["uniq"], g["nontriv"], g["tgt"], g["rounds"], g["pops"]) == (694285, 694311, 6, 28, 1602505)
+    assert g["reduced_rows"] == 694264 and g["n_specials"] == 25
+    g = ORACLE["ecdsa"]
+    assert g["verdict"] is False and (g["uniq"], g["nontriv"], g["rounds"], g["pops"]) == (700612, 1089136, 4, 2747850)
+
+
+def test_secp_without_secp_solve_throws():
+    # UndefVarError(:dsu) at :762 when BigMultModP + BigLessThan specials exist and secp_solve=false
+    cfg = CONFIGS["secp256k1+bmmp+blt"]
+    reduced, specials, main = api.prepare(fixtures.path(cfg["main"]), [fixtures.path(t) for t in cfg["trusted"]],
+                                          cfg["trusted_names"])
+    with pytest.raises(oracle_lib.OracleError) as e:
+        oracle_lib.solve(reduced, specials, main.known, main.targets, main.n_vars, False)
+    assert e.value.status == -4
