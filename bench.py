@@ -59,7 +59,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -97,10 +97,40 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def algorithmic_bytes_per_sweep(n_rows, nnz_nonzero):
-    # compact sweep layout: per row 3 segment offsets (12 B) + flags word (4 B) +
-    # solved latch (1 B); per non-zero term a 4-byte wire index + 1 gathered state byte
-    return 17 * n_rows + 5 * nnz_nonzero
+def algorithmic_bytes_per_eval(n_rows, nnz_nonzero):
+    # sweep layout: one 32-byte row record (flags + <= 6 inline wire ids) per swept row
+    # + 1 gathered state byte per non-zero term.  Bytes that are not moved are not credited: a row the
+    # live mask has retired is neither counted as an eval nor as bytes.
+    return 32.0 + nnz_nonzero / float(n_rows)
+
+
+def tile_problem(np, reduced, specials, main, K):
+    """Block-diagonal tiling of the workload K times (SURVEY.md §8d "S-K"): wire ids offset by
+    k*(n_vars-1), wire 1 shared.  The working set (K x 22 MB of row records) leaves the L2."""
+    V = main.n_vars
+    seg, col, coef = reduced.seg_ptr.astype(np.int64), reduced.col.astype(np.int64), reduced.coef
+
+    class T:
+        pass
+    t = T()
+    t.n_rows = reduced.n_rows * K
+    t.nnz = reduced.nnz * K
+    t.seg_ptr = np.concatenate([[0]] + [seg[1:] + k * seg[-1] for k in range(K)]).astype(np.uint64)
+    t.col = np.concatenate([np.where(col == 1, 1, col + k * (V - 1)) for k in range(K)]).astype(np.uint32)
+    t.coef = np.tile(coef, (K, 1))
+    nv = 1 + (V - 1) * K
+
+    def off(a, k):
+        a = np.asarray(a, dtype=np.int64)
+        return np.where(a == 1, 1, a + k * (V - 1))
+    known = np.unique(np.concatenate([off(main.known, k) for k in range(K)]))
+    targets = np.concatenate([off(main.targets, k) for k in range(K)])
+    sp = []
+    base = specials.as_list()
+    for k in range(K):
+        for n, i, o in base:
+            sp.append((n, off(i, k).tolist(), off(o, k).tolist()))
+    return t, sp, known, targets, nv
 
 
 def run_reference(args):
@@ -151,6 +181,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tile", type=int, default=8,
+                    help="also time a K-times tiled copy of the workload (0 = skip): its working set does not fit the L2")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -241,6 +273,7 @@ def main():
         solve_ms += c.ms_solve
         launches += int(c.sweep_launches)
         evals, rounds, outer = int(c.constraint_evals), int(c.inner_rounds), int(c.outer_rounds)
+        rule_evals = int(c.rule_evals)
     barrier()
     clocks = sampler.stop()
     verdict = bool(res.c.verdict)
@@ -286,13 +319,50 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
     nnz_nonzero = int(np.count_nonzero(reduced.coef.any(axis=1)))
-    bytes_sweep = algorithmic_bytes_per_sweep(reduced.n_rows, nnz_nonzero)
+    b_eval = algorithmic_bytes_per_eval(reduced.n_rows, nnz_nonzero)
     sweep_ms_step = sweep_ms / args.steps
-    achieved = bytes_sweep * rounds / (sweep_ms_step / 1e3) / 1e9 if sweep_ms_step > 0 else 0.0
+    sweep_evals = evals - 3 * reduced.n_rows * outer  # rows swept by k_p1_loop (the rest: P3/P4 kernels + P2 tail)
+    achieved = b_eval * sweep_evals / (sweep_ms_step / 1e3) / 1e9 if sweep_ms_step > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_p1_loop (persistent Jacobi sweep)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "bytes_per_sweep": bytes_sweep, "sweeps_per_step": rounds,
-                "kernel_ms_per_step": sweep_ms_step, "launches_per_step": outer}
+                "peak_source": peak_src, "bytes_per_eval": b_eval, "evals_in_kernel_per_step": sweep_evals,
+                "sweeps_per_step": rounds, "kernel_ms_per_step": sweep_ms_step, "launches_per_step": outer,
+                "note": "the named workload is round-latency bound: 161 dependent rounds, 130 of them change "
+                        "a single wire (DESIGN.md §5); see roofline_tiled for the bandwidth regime"}
+
+    # ---- the same kernel on a tiled copy whose working set does not fit the 126 MB L2 ---------------
+    tiled = None
+    if args.tile and args.tile > 1 and world == 1:
+        K = args.tile
+        t, sp_t, known_t, targets_t, nv_t = tile_problem(np, reduced, specials, main, K)
+        ph_t = api.ProblemHandle(t, sp_t, known_t, targets_t, nv_t, False)
+        res_t = api.SolveResult(nv_t, full_state=False)
+        h_t = C.c_void_p()
+        st = lib.ecne_upload(C.byref(ph_t.c), C.byref(h_t))
+        if st != 0:
+            raise RuntimeError(lib.ecne_last_error().decode())
+        for _ in range(2):
+            lib.ecne_solve_resident(h_t, C.byref(res_t.c))
+        tsw = tso = 0.0
+        reps = 3
+        for _ in range(reps):
+            l2_flush()
+            torch.cuda.synchronize()
+            st = lib.ecne_solve_resident(h_t, C.byref(res_t.c))
+            if st != 0:
+                raise RuntimeError(lib.ecne_last_error().decode())
+            tsw += res_t.c.ms_sweep
+            tso += res_t.c.ms_solve
+        lib.ecne_free_resident(h_t)
+        ev_t = int(res_t.c.constraint_evals)
+        sw_ev_t = ev_t - 3 * t.n_rows * int(res_t.c.outer_rounds)
+        ach_t = b_eval * sw_ev_t / (tsw / reps / 1e3) / 1e9
+        ok_t = int(res_t.c.n_unique) == 1 + K * (n_unique - 1) and bool(res_t.c.verdict) == verdict
+        tiled = {"tile": K, "rows": t.n_rows, "row_record_bytes": 32 * t.n_rows, "evals_per_step": ev_t,
+                 "value": ev_t / (tso / reps / 1e3), "unit": UNIT, "ms_solve": tso / reps,
+                 "kernel_ms_per_step": tsw / reps, "achieved": ach_t, "peak": peak, "frac": ach_t / peak,
+                 "bitmap_is_base_repeated": ok_t}
+        del ph_t, res_t, t
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -303,6 +373,7 @@ def main():
         "config": {"workload": WORKLOAD_NAME, "rows": reduced.n_rows, "rows_before_abstraction": main.n_rows,
                    "wires": main.n_vars, "nnz": nnz_nonzero, "evals_per_step": evals,
                    "outer_rounds": outer, "jacobi_rounds": rounds, "verdict": verdict, "n_unique": n_unique,
+                   "rule_evals_per_step": rule_evals,
                    "l2": "flushed between timed steps (256 MB fill)",
                    "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (row-range sharding: see DESIGN.md §7)",
                    "device_ms_solve_per_step": solve_ms / args.steps},
@@ -313,6 +384,8 @@ def main():
         "roofline": roofline,
         "clocks": clocks,
     }
+    if tiled is not None:
+        line["roofline_tiled"] = tiled
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -23,6 +23,9 @@ struct Global {
   // options
   long long max_rounds = 1000000;     // per P1 launch
   long long max_outer = 100000;
+  // pinned staging shared by every call (the API is single-threaded)
+  void* h_status = nullptr;
+  void* h_counts = nullptr;
   // dist
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
@@ -50,6 +53,15 @@ struct NcclApi {
     return GetUniqueId && CommInitRank && CommDestroy && AllGather;
   }
 } NCCL;
+
+}  // namespace
+namespace ecne {
+SlabPool& slab_pool() {
+  static SlabPool pool;
+  return pool;
+}
+}  // namespace ecne
+namespace {
 
 int fail(int status, const std::string& msg) {
   G.err = msg;
@@ -103,6 +115,8 @@ extern "C" int ecne_init(int device) {
   if (!coop) return fail(ECNE_E_CUDA, "device lacks cooperative launch");
   if (G.stream) cudaStreamDestroy(G.stream);
   CKA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  if (!G.h_status) CKA(cudaMallocHost(&G.h_status, sizeof(Status)));
+  if (!G.h_counts) CKA(cudaMallocHost(&G.h_counts, 4 * sizeof(unsigned long long)));
   G.device = device;
   G.inited = true;
   return ECNE_OK;
@@ -117,6 +131,11 @@ extern "C" void ecne_shutdown(void) {
     cudaStreamDestroy(G.stream);
     G.stream = nullptr;
   }
+  slab_pool().destroy();
+  if (G.h_status) cudaFreeHost(G.h_status);
+  if (G.h_counts) cudaFreeHost(G.h_counts);
+  G.h_status = nullptr;
+  G.h_counts = nullptr;
   G.inited = false;
   G.device = -1;
   G.rank = 0;
@@ -144,12 +163,12 @@ extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out)
   }
   ecne_resident* h = new ecne_resident();
   h->r.stream = G.stream;
+  h->r.h_status = (Status*)G.h_status;
+  h->r.h_counts = (unsigned long long*)G.h_counts;
   std::string err;
   int st = build_resident(problem, &h->r, err);
   if (st != ECNE_OK) {
     h->r.arena.release();
-    if (h->r.h_status) cudaFreeHost(h->r.h_status);
-    if (h->r.h_counts) cudaFreeHost(h->r.h_counts);
     delete h;
     return fail(st, err);
   }
@@ -159,9 +178,8 @@ extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out)
 
 extern "C" void ecne_free_resident(ecne_resident_t* h) {
   if (!h) return;
+  cudaStreamSynchronize(h->r.stream);
   h->r.arena.release();
-  if (h->r.h_status) cudaFreeHost(h->r.h_status);
-  if (h->r.h_counts) cudaFreeHost(h->r.h_counts);
   delete h;
 }
 

@@ -25,24 +25,66 @@ void launch_finalize(const Dev& d, int buf, unsigned long long* ubits, unsigned 
 void launch_export(const Dev& d, int buf, fr::u256* lb, fr::u256* ub, uint8_t* nvalues,
                    fr::u256* values, cudaStream_t s);
 
-// A device allocation arena: every buffer of one resident problem, freed together.
+// Device memory is taken from a process-wide pool of big slabs that survives between calls
+// (SURVEY.md §8b "device memory owned by the library, cached between calls, freed in
+// ecne_shutdown"): an Arena bump-allocates out of slabs it borrows from the pool and hands them back
+// on release(), so a steady-state ecne_solve() performs no cudaMalloc / cudaFree at all.
+struct Slab {
+  char* base = nullptr;
+  size_t size = 0;
+};
+struct SlabPool {
+  std::vector<Slab> free_slabs;
+  cudaError_t acquire(size_t min_bytes, Slab* out) {
+    // best fit among the cached slabs
+    int best = -1;
+    for (size_t i = 0; i < free_slabs.size(); ++i)
+      if (free_slabs[i].size >= min_bytes && (best < 0 || free_slabs[i].size < free_slabs[best].size))
+        best = (int)i;
+    if (best >= 0) {
+      *out = free_slabs[best];
+      free_slabs.erase(free_slabs.begin() + best);
+      return cudaSuccess;
+    }
+    size_t sz = min_bytes < ((size_t)256 << 20) ? ((size_t)256 << 20) : min_bytes;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) return e;
+    out->base = (char*)p;
+    out->size = sz;
+    return cudaSuccess;
+  }
+  void give_back(const Slab& s) { free_slabs.push_back(s); }
+  void destroy() {
+    for (auto& s : free_slabs) cudaFree(s.base);
+    free_slabs.clear();
+  }
+};
+SlabPool& slab_pool();
+
 struct Arena {
-  std::vector<void*> ptrs;
+  std::vector<Slab> slabs;
+  size_t off = 0;  // bump offset inside slabs.back()
   size_t bytes = 0;
   template <class T>
   cudaError_t alloc(T** out, size_t n) {
-    void* p = nullptr;
-    size_t sz = (n ? n : 1) * sizeof(T);
-    cudaError_t e = cudaMalloc(&p, sz);
-    if (e != cudaSuccess) return e;
-    ptrs.push_back(p);
+    size_t sz = ((n ? n : 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (slabs.empty() || off + sz > slabs.back().size) {
+      Slab s;
+      cudaError_t e = slab_pool().acquire(sz, &s);
+      if (e != cudaSuccess) return e;
+      slabs.push_back(s);
+      off = 0;
+    }
+    *out = (T*)(slabs.back().base + off);
+    off += sz;
     bytes += sz;
-    *out = (T*)p;
     return cudaSuccess;
   }
   void release() {
-    for (void* p : ptrs) cudaFree(p);
-    ptrs.clear();
+    for (auto& s : slabs) slab_pool().give_back(s);
+    slabs.clear();
+    off = 0;
     bytes = 0;
   }
 };

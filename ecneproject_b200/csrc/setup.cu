@@ -813,8 +813,6 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(A.alloc(&R->d_ubits, (V + 63) / 64));
   CK(A.alloc(&R->d_kbits, (V + 63) / 64));
   CK(A.alloc(&R->d_counts, 4));
-  CK(cudaMallocHost((void**)&R->h_status, sizeof(Status)));
-  CK(cudaMallocHost((void**)&R->h_counts, 4 * sizeof(unsigned long long)));
 
   CK(cudaStreamSynchronize(s));
   d.r0 = h_rank[0];
