@@ -76,7 +76,7 @@ class SpecialsStruct(C.Structure):
 ENGINE_SYMBOLS = [
     "ecne_version", "ecne_init", "ecne_shutdown", "ecne_last_error", "ecne_solve",
     "ecne_upload", "ecne_solve_resident", "ecne_free_resident",
-    "ecne_dist_unique_id", "ecne_dist_init", "ecne_dist_rank", "ecne_dist_world",
+    "ecne_dist_unique_id", "ecne_dist_init", "ecne_dist_rank", "ecne_dist_world", "ecne_shard_rows",
     "ecne_set_option", "ecne_fr_batch",
 ]
 HOST_SYMBOLS = [
@@ -149,6 +149,8 @@ def engine_lib():
         lib.ecne_dist_init.restype = C.c_int
         lib.ecne_dist_rank.restype = C.c_int
         lib.ecne_dist_world.restype = C.c_int
+        lib.ecne_shard_rows.argtypes = [Pp, C.c_int, C.c_int, u64p, u64p]
+        lib.ecne_shard_rows.restype = C.c_int
         lib.ecne_set_option.argtypes = [C.c_char_p, C.c_int64]
         lib.ecne_set_option.restype = C.c_int
         lib.ecne_fr_batch.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u64p]

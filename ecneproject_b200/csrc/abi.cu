@@ -29,6 +29,12 @@ struct Global {
   // dist
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
+  // exchange channel: one cudaMalloc'ed buffer per rank, mapped into every peer through CUDA IPC
+  //   [0, 4096)            header: mailbox u64[8] @0, xcnt u32[3][8] @256, xepoch u32 @512, scratch int @1024
+  //   4096 + l*xcap*16     record list l (l = 0..2)
+  char* xbuf = nullptr;
+  size_t xcap = 0;  // records per list
+  char* xpeer[ECNE_MAX_WORLD] = {nullptr};
 } G;
 
 // NCCL is bound at run time, not link time: a host process that also imports PyTorch must end up
@@ -40,6 +46,8 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load() {
     if (h) return true;
@@ -49,8 +57,9 @@ struct NcclApi {
     CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
     AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+    AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
     GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
-    return GetUniqueId && CommInitRank && CommDestroy && AllGather;
+    return GetUniqueId && CommInitRank && CommDestroy && AllGather && AllReduce;
   }
 } NCCL;
 
@@ -93,6 +102,11 @@ struct ecne_resident {
   Resident r;
 };
 
+namespace {
+int setup_exchange(Resident& R, size_t cap);
+int dist_barrier(cudaStream_t s);
+}  // namespace
+
 extern "C" int ecne_version(void) { return ECNE_ABI_VERSION; }
 
 extern "C" const char* ecne_last_error(void) { return G.err.c_str(); }
@@ -131,6 +145,12 @@ extern "C" void ecne_shutdown(void) {
     cudaStreamDestroy(G.stream);
     G.stream = nullptr;
   }
+  for (int h = 0; h < ECNE_MAX_WORLD; ++h)
+    if (G.xpeer[h] && G.xpeer[h] != G.xbuf) cudaIpcCloseMemHandle(G.xpeer[h]);
+  if (G.xbuf) cudaFree(G.xbuf);
+  memset(G.xpeer, 0, sizeof(G.xpeer));
+  G.xbuf = nullptr;
+  G.xcap = 0;
   slab_pool().destroy();
   if (G.h_status) cudaFreeHost(G.h_status);
   if (G.h_counts) cudaFreeHost(G.h_counts);
@@ -172,6 +192,21 @@ extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out)
     delete h;
     return fail(st, err);
   }
+  if (G.world > 1) {
+    if (!G.comm) {
+      ecne_free_resident(h);
+      return fail(ECNE_E_NCCL, "ecne_dist_init has not been called");
+    }
+    uint64_t lo = 0, hi = 0;
+    ecne_shard_rows(problem, G.rank, G.world, &lo, &hi);
+    h->r.d.row_lo = (uint32_t)lo;
+    h->r.d.row_hi = (uint32_t)hi;
+    st = setup_exchange(h->r, h->r.d.rec_cap);
+    if (st != ECNE_OK) {
+      ecne_free_resident(h);
+      return st;
+    }
+  }
   *out = h;
   return ECNE_OK;
 }
@@ -195,6 +230,12 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   cudaEventRecord(e0, s);
   const int grid = p1_grid_size(G.device);
   CKA(launch_reset(d, grid, s));
+  if (d.world > 1) {
+    // clear mailbox / counts / epoch, then make sure every rank has done so before anyone posts
+    CKA(cudaMemsetAsync(R.xhdr, 0, 1024, s));
+    int bst = dist_barrier(s);
+    if (bst) return bst;
+  }
   uint64_t outer = 0, launches = 0, phase_evals = 0;
   unsigned long long rounds_total = 0, evals_total = 0, rule_evals_total = 0;
   int status = ECNE_OK;
@@ -211,6 +252,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
     cudaEventRecord(s0, s);
     CKA(launch_p1(d, 0, (unsigned int)G.max_rounds, grid, s));
     cudaEventRecord(s1, s);
+    if (d.world > 1) launch_p2_scan_all(d, s);  // sharded: every rank scans every row (same candidates)
     // P2: linear systems (the candidate scan ran in the sweep kernel's tail)
     CKA(cudaMemcpyAsync(R.h_status, d.st, sizeof(Status), cudaMemcpyDeviceToHost, s));
     CKA(cudaStreamSynchronize(s));
@@ -380,7 +422,30 @@ extern "C" int ecne_solve(const ecne_problem_t* problem, ecne_result_t* result) 
   return st;
 }
 
-// ---- sharding (wired up in dist.cu-less form: NCCL communicator owned here) ---------------------
+// ---- row-range sharding across the GPUs of one box --------------------------------
+extern "C" int ecne_shard_rows(const ecne_problem_t* p, int rank, int world, uint64_t* lo, uint64_t* hi) {
+  if (!p || !lo || !hi || world < 1 || rank < 0 || rank >= world) return fail(ECNE_E_BADARG, "bad argument");
+  const uint64_t N = p->n_rows;
+  const uint64_t total = N ? p->seg_ptr[3 * N] : 0;
+  auto cut = [&](int r) -> uint64_t {  // first row whose prefix term count reaches r/world of the total
+    if (r <= 0) return 0;
+    if (r >= world) return N;
+    const uint64_t want = (uint64_t)(((unsigned __int128)total * (unsigned)r) / (unsigned)world);
+    uint64_t a = 0, b = N;  // smallest row i with seg_ptr[3*i] >= want
+    while (a < b) {
+      uint64_t m = (a + b) / 2;
+      if (p->seg_ptr[3 * m] >= want)
+        b = m;
+      else
+        a = m + 1;
+    }
+    return a;
+  };
+  *lo = cut(rank);
+  *hi = cut(rank + 1);
+  return ECNE_OK;
+}
+
 extern "C" int ecne_dist_unique_id(uint8_t out[128]) {
   if (!NCCL.load()) return fail(ECNE_E_NCCL, "cannot load libnccl.so.2");
   ncclUniqueId id;
@@ -391,7 +456,7 @@ extern "C" int ecne_dist_unique_id(uint8_t out[128]) {
 }
 extern "C" int ecne_dist_init(int rank, int world, const uint8_t unique_id[128]) {
   if (!G.inited) return fail(ECNE_E_CUDA, "call ecne_init first");
-  if (world < 1 || rank < 0 || rank >= world) return fail(ECNE_E_BADARG, "bad rank/world");
+  if (world < 1 || world > ECNE_MAX_WORLD || rank < 0 || rank >= world) return fail(ECNE_E_BADARG, "bad rank/world");
   if (G.comm) {
     NCCL.CommDestroy(G.comm);
     G.comm = nullptr;
@@ -399,15 +464,80 @@ extern "C" int ecne_dist_init(int rank, int world, const uint8_t unique_id[128])
   G.rank = rank;
   G.world = world;
   if (world == 1) return ECNE_OK;
+  if (!unique_id) return fail(ECNE_E_BADARG, "null unique id");
+  if (!NCCL.load()) return fail(ECNE_E_NCCL, "cannot load libnccl.so.2");
   ncclUniqueId id;
   memcpy(&id, unique_id, 128);
-  if (!NCCL.load()) return fail(ECNE_E_NCCL, "cannot load libnccl.so.2");
   if (NCCL.CommInitRank(&G.comm, world, id, rank) != ncclSuccess)
     return fail(ECNE_E_NCCL, "ncclCommInitRank failed");
   return ECNE_OK;
 }
 extern "C" int ecne_dist_rank(void) { return G.rank; }
 extern "C" int ecne_dist_world(void) { return G.world; }
+
+namespace {
+// (Re)build the exchange channel so that every list holds at least `cap` records, and point the
+// resident's record lists / peer tables at it.  Collective: every rank calls it with the same cap.
+int setup_exchange(Resident& R, size_t cap) {
+  Dev& d = R.d;
+  cudaStream_t s = R.stream;
+  if (G.xcap < cap) {
+    for (int h = 0; h < G.world; ++h)
+      if (h != G.rank && G.xpeer[h]) cudaIpcCloseMemHandle(G.xpeer[h]);
+    if (G.xbuf) cudaFree(G.xbuf);
+    memset(G.xpeer, 0, sizeof(G.xpeer));
+    G.xbuf = nullptr;
+    G.xcap = 0;
+    const size_t bytes = 4096 + 3 * cap * sizeof(Rec);
+    CKA(cudaMalloc((void**)&G.xbuf, bytes));
+    CKA(cudaMemset(G.xbuf, 0, 4096));
+    cudaIpcMemHandle_t mine;
+    CKA(cudaIpcGetMemHandle(&mine, G.xbuf));
+    // all-gather the handles through NCCL (device staging lives in the header's scratch area)
+    char* d_all = nullptr;
+    CKA(cudaMalloc((void**)&d_all, sizeof(cudaIpcMemHandle_t) * (size_t)(G.world + 1)));
+    CKA(cudaMemcpyAsync(d_all + sizeof(mine) * G.world, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+    if (NCCL.AllGather(d_all + sizeof(mine) * G.world, d_all, sizeof(mine), ncclChar, G.comm, s) != ncclSuccess)
+      return fail(ECNE_E_NCCL, "ncclAllGather of the IPC handles failed");
+    std::vector<cudaIpcMemHandle_t> all(G.world);
+    CKA(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * G.world, cudaMemcpyDeviceToHost, s));
+    CKA(cudaStreamSynchronize(s));
+    cudaFree(d_all);
+    for (int h = 0; h < G.world; ++h) {
+      if (h == G.rank) {
+        G.xpeer[h] = G.xbuf;
+      } else {
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[h], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+          return fail(ECNE_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        G.xpeer[h] = (char*)p;
+      }
+    }
+    G.xcap = cap;
+  }
+  d.world = G.world;
+  d.rank = G.rank;
+  d.rec_cap = (uint32_t)G.xcap;
+  for (int l = 0; l < 3; ++l) d.recs[l] = (Rec*)(G.xbuf + 4096 + (size_t)l * G.xcap * sizeof(Rec));
+  for (int h = 0; h < G.world; ++h) {
+    d.xflag[h] = (unsigned long long*)G.xpeer[h];
+    for (int l = 0; l < 3; ++l) d.xrecs[h][l] = (Rec*)(G.xpeer[h] + 4096 + (size_t)l * G.xcap * sizeof(Rec));
+  }
+  d.xcnt = (unsigned int*)(G.xbuf + 256);
+  d.xepoch = (unsigned int*)(G.xbuf + 512);
+  R.xhdr = G.xbuf;
+  return ECNE_OK;
+}
+
+// device-side rendezvous of all ranks on the stream (used once per solve, before the first kernel)
+int dist_barrier(cudaStream_t s) {
+  int* scratch = (int*)(G.xbuf + 1024);
+  if (NCCL.AllReduce(scratch, scratch, 1, ncclInt, ncclSum, G.comm, s) != ncclSuccess)
+    return fail(ECNE_E_NCCL, "ncclAllReduce (start barrier) failed");
+  return ECNE_OK;
+}
+}  // namespace
 
 // ---- field known-answer hook --------------------------------------------------------------------
 __global__ void k_fr_batch(int op, uint64_t n, const fr::u256* a, const fr::u256* b, fr::u256* out) {

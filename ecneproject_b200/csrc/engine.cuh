@@ -78,6 +78,8 @@ struct __align__(16) Rec {
 #define VS_2A 0x40000000u  // | roots index: both roots           (:916-922)
 #define VS_2B 0x80000000u  // | tvals index: [t]                  (:967)
 
+#define ECNE_MAX_WORLD 8
+
 struct Status {            // device-resident, read back once per outer round
   unsigned long long changed;      // state changes of the current outer round ("successful_steps")
   unsigned long long rounds;       // Jacobi rounds of the single-row sweep
@@ -141,6 +143,12 @@ struct Dev {
   Status* st;
   // sharding: this rank sweeps rows [row_lo, row_hi)
   uint32_t row_lo, row_hi;
+  // multi-GPU exchange over NVLink peer mappings (world == 1: unused)
+  int world, rank;
+  Rec* xrecs[ECNE_MAX_WORLD][3];             // every rank's three record lists (own entry = recs[])
+  unsigned long long* xflag[ECNE_MAX_WORLD]; // every rank's mailbox [ECNE_MAX_WORLD]; we post into slot [rank]
+  unsigned int* xcnt;                        // [3][ECNE_MAX_WORLD] record counts per list and rank (local copy)
+  unsigned int* xepoch;                      // cross-GPU barrier epoch, persists over the launches of a solve
 };
 
 // ---- state access -----------------------------------------------------------------------------------
@@ -233,6 +241,39 @@ __device__ __forceinline__ void emit(const Dev& d, int wbuf, int list, uint32_t 
   }
 }
 
+// Cross-GPU part of the round barrier, executed by the last local arriver only: post
+// {epoch, bound bit, own record count} into every peer's mailbox (NVLink peer store), then wait until
+// every peer has posted the same epoch into ours.  Returns the total record count (bit 31: a bound
+// moved somewhere) and leaves the per-rank counts in d.xcnt[list][*].
+__device__ __forceinline__ unsigned int cross_gpu_exchange(const Dev& d, unsigned int list,
+                                                           unsigned int own_payload, unsigned int xe) {
+  const unsigned long long word = ((unsigned long long)xe << 32) | own_payload;
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  for (int h = 0; h < d.world; ++h) {
+    unsigned long long* slot = d.xflag[h] + d.rank;
+    asm volatile("st.release.sys.u64 [%0], %1;" ::"l"(slot), "l"(word) : "memory");
+  }
+  unsigned int total = 0, bnd = 0;
+  for (int h = 0; h < d.world; ++h) {
+    const unsigned long long* slot = d.xflag[d.rank] + h;
+    unsigned long long v;
+    unsigned long long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+      if (++spins > (1ULL << 28)) {  // a peer died or diverged: fail loudly instead of hanging the box
+        atomicCAS(&d.st->err, 0u, (unsigned int)(-ECNE_E_NCCL));
+        break;
+      }
+    } while ((unsigned int)(v >> 32) < xe);
+    unsigned int nh = (unsigned int)v & 0x7fffffffu;
+    bnd |= (unsigned int)v & 0x80000000u;
+    d.xcnt[list * ECNE_MAX_WORLD + h] = nh;
+    total += nh;
+  }
+  if (total > 0x7fffffffu) total = 0x7fffffffu;
+  return total | bnd;
+}
+
 #ifdef ECNE_PROFILE
 static __device__ long long g_prof_dummy;
 #define g_prof_intra prof_intra
@@ -246,7 +287,9 @@ static __device__ long long g_prof_dummy;
 // round trip is needed to learn it.
 __device__ __forceinline__ unsigned int grid_barrier(unsigned int* bar, unsigned int& epoch,
                                                      const unsigned int* payload_src,
-                                                     const unsigned int* flag_src = nullptr
+                                                     const unsigned int* flag_src = nullptr,
+                                                     const Dev* xd = nullptr, unsigned int xlist = 0,
+                                                     unsigned int xe = 0
 #ifdef ECNE_PROFILE
                                                      , long long* pprof = nullptr
 #endif
@@ -274,6 +317,7 @@ __device__ __forceinline__ unsigned int grid_barrier(unsigned int* bar, unsigned
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       payload = payload_src ? *((volatile const unsigned int*)payload_src) : 0u;
       if (flag_src && *((volatile const unsigned int*)flag_src)) payload |= 0x80000000u;
+      if (xd) payload = cross_gpu_exchange(*xd, xlist, payload, xe);
       unsigned long long v = ((unsigned long long)payload << 32) | epoch;
       asm volatile("st.release.gpu.u64 [%0], %1;" ::"l"(rel), "l"(v) : "memory");
     } else {

@@ -16,6 +16,7 @@ int p1_threads();
 cudaError_t launch_p1(const Dev& d, int rbuf, unsigned int max_rounds, int grid, cudaStream_t s);
 void launch_replay(const Dev& d, int buf, cudaStream_t s);
 void launch_p0(const Dev& d, cudaStream_t s);
+void launch_p2_scan_all(const Dev& d, cudaStream_t s);
 void launch_p2_groups(const Dev& d, int rbuf, uint32_t n_cand, const unsigned long long* keys,
                       const uint32_t* rows, cudaStream_t s);
 void launch_p3(const Dev& d, int rbuf, cudaStream_t s);
@@ -107,6 +108,8 @@ struct Resident {
   Status* h_status = nullptr;
   unsigned long long* h_counts = nullptr;
   double ms_h2d = 0, ms_classify = 0;
+  // multi-GPU: exchange buffer header (mailbox, counts, epoch) to clear at the start of a solve
+  void* xhdr = nullptr;
 };
 
 // setup.cu: H2D + classification + layout.  Returns an ecne_status.

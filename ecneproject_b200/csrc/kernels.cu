@@ -80,6 +80,15 @@ __device__ __noinline__ void p2_scan_row(const Dev& d, int rbuf, uint32_t row) {
 //   4A rows         x - y = 0: Case 1 + bound intersection, ranks only loaded when a wire's bounds
 //                   were ever tightened (WF_BND); the l == 2 Case-3 pattern these rows also match is
 //                   subsumed by exactly these two steps
+// a record of another rank's list, read over NVLink: never through a (possibly stale) L1 line
+__device__ __forceinline__ Rec ld_peer_rec(const Rec* p) {
+  Rec r;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.wire), "=r"(r.bits), "=r"(r.lbr), "=r"(r.ubr)
+               : "l"(p));
+  return r;
+}
+
 // one bit of a 32-bit bloom filter per wire (multiplicative hash: neighbouring ids spread out)
 __device__ __forceinline__ uint32_t wire_bloom(uint32_t w) { return 1u << ((w * 0x9E3779B1u) >> 27); }
 
@@ -247,6 +256,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
   const uint32_t kmask = per_thread < 64 ? per_thread : 64;
   const uint32_t warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
   unsigned int round = 0;
+  unsigned int xe = d.world > 1 ? *d.xepoch : 0u;  // cross-GPU epoch (same on every rank)
   unsigned long long evals = 0, changed = 0, ruleevals = 0;
   uint32_t bepoch = d.st->bepoch;  // rounds so far that tightened a bound (same value in every thread)
 
@@ -435,12 +445,33 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     __syncthreads();
     if (threadIdx.x == 0 && round < 40)
       d.prof[20000 + ((size_t)round * gridDim.x + blockIdx.x) * 4 + 3] = (unsigned long long)(clock64() - t0);
-    unsigned int n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list, pf);
+    xe += 1;
+    unsigned int n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list,
+                                  d.world > 1 ? &d : nullptr, list, xe, pf);
 #else
-    unsigned int n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list);
+    xe += 1;
+    unsigned int n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list,
+                                  d.world > 1 ? &d : nullptr, list, xe);
 #endif
     bepoch += n >> 31;
     n &= 0x7fffffffu;
+    unsigned int n_own = n;
+    if (d.world > 1) {
+      // pull the peers' records of this round over NVLink and apply them to BOTH local buffers (the
+      // buffer read next round must already contain them), then a local barrier
+      n_own = __ldcg(d.xcnt + list * ECNE_MAX_WORLD + d.rank);
+      for (int h = 0; h < d.world; ++h) {
+        if (h == d.rank) continue;
+        const unsigned int nh = __ldcg(d.xcnt + list * ECNE_MAX_WORLD + h);
+        const Rec* pr = d.xrecs[h][list];
+        for (uint32_t j = tid; j < nh && j < d.rec_cap; j += nthreads) {
+          Rec r = ld_peer_rec(pr + j);
+          apply_update(d, 0, r.wire, r.bits, r.lbr, r.ubr);
+          apply_update(d, 1, r.wire, r.bits, r.lbr, r.ubr);
+        }
+      }
+      grid_barrier(d.barrier, epoch, nullptr);
+    }
 #ifdef ECNE_PROFILE
     if (tid == 0) {
       unsigned long long slot = atomicAdd(&d.prof[7], 1ULL);  // global round index across launches
@@ -458,32 +489,35 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       d.rec_count[(list + 2) % 3] = 0;
       d.bnd_flag[(list + 2) % 3] = 0;
     }
-    if (n > d.rec_cap) n = d.rec_cap;
+    if (n_own > d.rec_cap) n_own = d.rec_cap;
     if (n == 0) break;  // W already holds every earlier record: both buffers are complete
     if (round >= max_rounds) {
       if (tid == 0) raise(d, ECNE_E_NOCONVERGE);
       const Rec* pr = d.recs[list];
-      for (uint32_t i = tid; i < n; i += nthreads) {
+      for (uint32_t i = tid; i < n_own; i += nthreads) {
         Rec r = pr[i];
         apply_update(d, rbuf, r.wire, r.bits, r.lbr, r.ubr);
       }
       break;
     }
-    // frontier filter for the next round: hash set of the wires this round changed
+    // frontier filter for the next round: hash set of the wires this round changed (on any rank)
     filtered = n <= CHG_MAX;
     if (filtered) {
       for (uint32_t j = threadIdx.x; j < CHG_WORDS; j += blockDim.x) sm_chg[j] = 0;
       if (threadIdx.x == 0) s_chg32 = 0;
       __syncthreads();
-      const Rec* cr = d.recs[list];
-      for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-        uint32_t w = cr[j].wire;
-        atomicOr(&sm_chg[(w >> 5) & (CHG_WORDS - 1)], 1u << (w & 31));
-        atomicOr(&s_chg32, wire_bloom(w));
+      for (int h = 0; h < (d.world > 1 ? d.world : 1); ++h) {
+        const Rec* cr = d.world > 1 ? d.xrecs[h][list] : d.recs[list];
+        const unsigned int nh = d.world > 1 ? __ldcg(d.xcnt + list * ECNE_MAX_WORLD + h) : n;
+        for (uint32_t j = threadIdx.x; j < nh && j < d.rec_cap; j += blockDim.x) {
+          uint32_t w = ld_peer_rec(cr + j).wire;
+          atomicOr(&sm_chg[(w >> 5) & (CHG_WORDS - 1)], 1u << (w & 31));
+          atomicOr(&s_chg32, wire_bloom(w));
+        }
       }
       __syncthreads();
     }
-    prev_n = n;
+    prev_n = n_own;
     rbuf = wbuf;
     list = (list + 1) % 3;
   }
@@ -495,7 +529,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
 #endif
   // ---- tail: P2 candidate scan over the rows that are still live (state is at the P1 fixpoint) ----
   grid_barrier(d.barrier, epoch, nullptr);  // the list counters are all zero and visible from here on
-  {
+  if (d.world == 1) {  // sharded runs scan every row on every rank instead (k_p2_scan_all)
     const uint8_t* F = d.F[0];
     for (unsigned long long m = live; m;) {
       const int k = __ffsll((long long)m) - 1;
@@ -559,6 +593,20 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     d.st->rounds += round;
     d.st->changed += changed;
     d.st->bepoch = bepoch;
+    if (d.world > 1) *d.xepoch = xe;
+  }
+}
+
+// P2 candidate scan over ALL rows (multi-GPU runs: every rank computes the same candidates)
+__global__ void k_p2_scan_all(Dev d) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < d.N) {
+    if (!(d.rflags[tid] & RF_LONG) && !(d.solved[tid] & 1)) p2_scan_row<1>(d, 0, tid);
+  }
+  const uint32_t warp = tid >> 5;
+  if (warp < d.n_long) {
+    uint32_t row = d.long_rows[warp];
+    if (!(d.solved[row] & 1)) p2_scan_row<32>(d, 0, row);
   }
 }
 
@@ -919,6 +967,10 @@ void launch_replay(const Dev& d, int buf, cudaStream_t s) {
   k_replay_done<<<1, 1, 0, s>>>(d);
 }
 
+void launch_p2_scan_all(const Dev& d, cudaStream_t s) {
+  uint64_t n = d.N > (uint64_t)d.n_long * 32 ? d.N : (uint64_t)d.n_long * 32;
+  if (n) k_p2_scan_all<<<blocks_for(n, 256), 256, 0, s>>>(d);
+}
 void launch_p0(const Dev& d, cudaStream_t s) {
   if (d.n_specials) k_p0<<<1, 256, 0, s>>>(d);
 }

@@ -130,6 +130,9 @@ int ecne_dist_unique_id(uint8_t out[128]);
 int ecne_dist_init(int rank, int world, const uint8_t unique_id[128]);
 int ecne_dist_rank(void);
 int ecne_dist_world(void);
+/* Pure host helper (no GPU needed): the contiguous row range [lo, hi) that rank `rank` of `world`
+ * sweeps, chosen so that every range holds about the same number of stored terms. */
+int ecne_shard_rows(const ecne_problem_t* problem, int rank, int world, uint64_t* lo, uint64_t* hi);
 
 /* ---- engine knobs (testing / benchmarking) ---------------------------------------------- */
 int ecne_set_option(const char* key, int64_t value);
