@@ -597,6 +597,8 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   d.secp_solve = p->secp_solve;
   d.row_lo = 0;
   d.row_hi = (uint32_t)N;
+  d.world = 1;  // single GPU until ecne_upload() shards the rows (setup_exchange)
+  d.rank = 0;
   Arena& A = R->arena;
   uint32_t *d_known, *d_targets, *d_sp_in_ptr, *d_sp_in, *d_sp_out_ptr, *d_sp_out;
   int32_t* d_sp_kind;
