@@ -3,8 +3,10 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library is dlopen()ed on first use (see NcclApi)
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,6 +25,7 @@ struct Global {
   // options
   long long max_rounds = 1000000;     // per P1 launch
   long long max_outer = 100000;
+  long long sparse_max = -1;          // records per round up to which a round is frontier-driven (-1: rows / 8)
   // pinned staging shared by every call (the API is single-threaded)
   void* h_status = nullptr;
   void* h_counts = nullptr;
@@ -169,6 +172,8 @@ extern "C" int ecne_set_option(const char* key, int64_t value) {
     G.max_rounds = value;
   else if (k == "max_outer")
     G.max_outer = value;
+  else if (k == "sparse_max")
+    G.sparse_max = value;
   else
     return fail(ECNE_E_BADARG, "unknown option " + k);
   return ECNE_OK;
@@ -236,81 +241,62 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
     int bst = dist_barrier(s);
     if (bst) return bst;
   }
-  uint64_t outer = 0, launches = 0, phase_evals = 0;
-  unsigned long long rounds_total = 0, evals_total = 0, rule_evals_total = 0;
+  // the whole fixpoint (:706-1556) is ONE persistent cooperative launch; the host only reads the
+  // status block back when it has finished
+  if (R.table_dirty) {
+    CKA(launch_clear_p2_table(d, s));
+    R.table_dirty = false;
+  }
+  d.max_outer = (uint32_t)std::min<long long>(G.max_outer, 0x7fffffffLL);
+  {
+    const uint32_t rows = d.row_hi - d.row_lo;
+    const long long sm = G.sparse_max >= 0 ? G.sparse_max : std::max<long long>(4096, rows / 8);
+    d.sparse_max = (uint32_t)std::min<long long>(sm, 0x7fffffffLL);
+  }
   int status = ECNE_OK;
   std::string err;
   float ms_sweep = 0;
   cudaEvent_t s0, s1;
   cudaEventCreate(&s0);
   cudaEventCreate(&s1);
-  while (true) {
-    ++outer;
-    // P0 / P0'
-    launch_p0(d, s);
-    // P1: single-row rules to a fixpoint
-    cudaEventRecord(s0, s);
-    CKA(launch_p1(d, 0, (unsigned int)G.max_rounds, grid, s));
-    cudaEventRecord(s1, s);
-    if (d.world > 1) launch_p2_scan_all(d, s);  // sharded: every rank scans every row (same candidates)
-    // P2: linear systems (the candidate scan ran in the sweep kernel's tail)
-    CKA(cudaMemcpyAsync(R.h_status, d.st, sizeof(Status), cudaMemcpyDeviceToHost, s));
-    CKA(cudaStreamSynchronize(s));
-    {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, s0, s1);
-      ms_sweep += ms;
-    }
-    launches += 2;
-    if (R.h_status->err) {
-      status = -(int)R.h_status->err;
-      break;
-    }
-    if (R.h_status->rec_overflow) {
-      status = ECNE_E_INTERNAL;
-      break;
-    }
-    uint32_t n_cand = R.h_status->p2_cand;
-    if (n_cand) {
-      int st = p2_sort(&R, n_cand, err);
-      if (st) {
-        status = st;
-        break;
-      }
-      launch_p2_groups(d, 0, n_cand, d.p2_key, d.p2_row, s);
-      CKA(cudaMemsetAsync(&d.st->p2_cand, 0, sizeof(unsigned int), s));
-      launches += 4;
-    }
-    launch_replay(d, 0, s);
-    // P3: ABZ tags, P4: IsZero pairs
-    launch_p3(d, 0, s);
-    launch_p4(d, 0, s);
-    launch_replay(d, 0, s);
-    launches += 7;
-    phase_evals += 3ull * d.N;
-    CKA(cudaMemcpyAsync(R.h_status, d.st, sizeof(Status), cudaMemcpyDeviceToHost, s));
-    CKA(cudaMemsetAsync(&d.st->changed, 0, sizeof(unsigned long long), s));
-    CKA(cudaStreamSynchronize(s));
-    if (R.h_status->err) {
-      status = -(int)R.h_status->err;
-      break;
-    }
-    if (R.h_status->rec_overflow) {
-      status = ECNE_E_INTERNAL;
-      break;
-    }
-    rounds_total = R.h_status->rounds;
-    evals_total = R.h_status->evals;
-    rule_evals_total = R.h_status->rule_evals;
-    if (R.h_status->changed == 0) break;  // successful_steps did not move (:708-711)
-    if ((long long)outer >= G.max_outer) {
-      status = ECNE_E_NOCONVERGE;
-      break;
+  cudaEventRecord(s0, s);
+  CKA(launch_solve(d, (unsigned int)std::min<long long>(G.max_rounds, 0x7fffffffLL), grid, s));
+  cudaEventRecord(s1, s);
+  CKA(cudaMemcpyAsync(R.h_status, d.st, sizeof(Status), cudaMemcpyDeviceToHost, s));
+  CKA(cudaStreamSynchronize(s));
+  cudaEventElapsedTime(&ms_sweep, s0, s1);
+  if (R.h_status->err)
+    status = -(int)R.h_status->err;
+  else if (R.h_status->rec_overflow)
+    status = ECNE_E_INTERNAL;
+  const uint64_t outer = R.h_status->outer;
+  if (getenv("ECNE_DEBUG_PROF")) {
+    const Status& S = *R.h_status;
+    fprintf(stderr,
+            "[ecne prof] block-0 cycles: dense %llu (%u rounds) sparse %llu (%llu rounds) p2scan %llu p2resolve %llu "
+            "p3claim+replay %llu p3commit+p4 %llu p0+replay %llu solo %llu | outer %u | p2 candidates total %u max %u | "
+            "dense evals %llu evals %llu\n",
+            S.prof[0], S.dense_rounds, S.prof[1], S.rounds - S.dense_rounds, S.prof[2], S.prof[3], S.prof[4], S.prof[5],
+            S.prof[6], S.prof[7], S.outer, S.n_cand_total, S.n_cand_max, S.dense_evals, S.evals);
+    if (atoi(getenv("ECNE_DEBUG_PROF")) > 1) {
+      std::vector<unsigned long long> pr(16000 + 4 * 2000);
+      cudaMemcpy(pr.data(), d.prof, pr.size() * 8, cudaMemcpyDeviceToHost);
+      for (unsigned long long g = 1; g <= S.rounds && g < 4000; ++g)
+        fprintf(stderr, "[round] %llu cycles %llu records %llu dense %llu outer %llu | thread0: rec+head %llu rows %llu replay %llu deg %llu\n", g,
+                pr[4 * g], pr[4 * g + 1], pr[4 * g + 2], pr[4 * g + 3], g < 2000 ? pr[16000 + 4 * g] : 0,
+                g < 2000 ? pr[16000 + 4 * g + 1] : 0, g < 2000 ? pr[16000 + 4 * g + 2] : 0, g < 2000 ? pr[16000 + 4 * g + 3] : 0);
     }
   }
+  const uint64_t launches = 1;
+  // the three whole-set sweeps of every outer round visit: P2 the rows that can still fire (counted by
+  // the kernel), P3 / P4 the rows with the ABZ / IsZero shape
+  const unsigned long long rounds_total = R.h_status->rounds, evals_total = R.h_status->evals,
+                           rule_evals_total = R.h_status->rule_evals;
+  const uint64_t phase_evals = outer * ((uint64_t)d.n_p3 + d.n_p4);
   cudaEventRecord(e1, s);
   res->status = status;
   if (status != ECNE_OK) {
+    R.table_dirty = true;
     cudaStreamSynchronize(s);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -319,38 +305,6 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
     cudaEventDestroy(s1);
     return fail(status, err.empty() ? status_text(status) : err);
   }
-#ifdef ECNE_PROFILE
-  {
-    std::vector<unsigned long long> pr((size_t)20000 + 40 * 148 * 4);
-    cudaMemcpy(pr.data(), d.prof, pr.size() * 8, cudaMemcpyDeviceToHost);
-    cudaMemset(d.prof, 0, pr.size() * 8);
-    // last launch's per-block breakdown of its first rounds
-    for (int r = 0; r < 40; ++r)
-      for (int b = 0; b < grid && b < 148; ++b) {
-        unsigned long long* q = &pr[20000 + ((size_t)r * grid + b) * 4];
-        if (q[3]) fprintf(stderr, "[blk] %d %d %llu %llu %llu %llu\n", r, b, q[0], q[1], q[2], q[3]);
-      }
-    {
-      unsigned long long nr = pr[7] < 4000 ? pr[7] : 4000;
-      fprintf(stderr, "[prof] per-round (block 0 thread 0): round cycles | records | sweep-phase cycles | long-row cycles\n");
-      for (unsigned long long i = 0; i < nr; ++i)
-        fprintf(stderr, "[round] %llu %llu %llu %llu %llu\n", i, pr[2048 + 4 * i], pr[2048 + 4 * i + 1],
-                pr[2048 + 4 * i + 2], pr[2048 + 4 * i + 3]);
-    }
-    const char* nm[6] = {"intra_block_wait", "grid_wait", "long_rows", "replay", "sweep", "-"};
-    for (int i = 0; i < 5; ++i) {
-      unsigned long long mx = 0, sum = 0;
-      int arg = 0;
-      for (int b = 0; b < grid; ++b) {
-        unsigned long long v = pr[b * 8 + i];
-        sum += v;
-        if (v > mx) { mx = v; arg = b; }
-      }
-      fprintf(stderr, "[prof] %-17s thread0 cycles: mean %.0f max %llu (block %d) per round mean %.0f max %.0f\n", nm[i],
-              (double)sum / grid, mx, arg, (double)sum / grid / pr[6], (double)mx / pr[6]);
-    }
-  }
-#endif
   // verdict + D2H
   launch_finalize(d, 0, R.d_ubits, R.d_kbits, R.d_counts, s);
   const size_t words = (R.n_vars + 63) / 64;
@@ -378,9 +332,10 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   cudaEventRecord(e2, s);
   CKA(cudaStreamSynchronize(s));
   CKA(cudaGetLastError());
-  float ms_solve = 0, ms_d2h = 0;
+  float ms_solve = 0, ms_d2h = 0, ms_device = 0;
   cudaEventElapsedTime(&ms_solve, e0, e1);
   cudaEventElapsedTime(&ms_d2h, e1, e2);
+  cudaEventElapsedTime(&ms_device, e0, e2);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaEventDestroy(e2);
@@ -402,6 +357,10 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   res->ms_d2h = ms_d2h;
   res->ms_exchange = 0;
   res->ms_sweep = ms_sweep;
+  res->dense_rounds = R.h_status->dense_rounds;
+  res->dense_evals = R.h_status->dense_evals;
+  res->dense_cycles = R.h_status->dense_cycles;
+  res->ms_device = ms_device;
   res->ms_total = R.ms_h2d + R.ms_classify + ms_solve + ms_d2h;
   return ECNE_OK;
 }

@@ -11,16 +11,11 @@ namespace ecne {
 
 // kernels.cu
 cudaError_t launch_reset(const Dev& d, int grid, cudaStream_t s);
+cudaError_t launch_clear_p2_table(const Dev& d, cudaStream_t s);
 int p1_grid_size(int device);
 int p1_threads();
-cudaError_t launch_p1(const Dev& d, int rbuf, unsigned int max_rounds, int grid, cudaStream_t s);
-void launch_replay(const Dev& d, int buf, cudaStream_t s);
-void launch_p0(const Dev& d, cudaStream_t s);
-void launch_p2_scan_all(const Dev& d, cudaStream_t s);
-void launch_p2_groups(const Dev& d, int rbuf, uint32_t n_cand, const unsigned long long* keys,
-                      const uint32_t* rows, cudaStream_t s);
-void launch_p3(const Dev& d, int rbuf, cudaStream_t s);
-void launch_p4(const Dev& d, int rbuf, cudaStream_t s);
+// the whole fixpoint (:706-1556): one persistent cooperative launch
+cudaError_t launch_solve(const Dev& d, unsigned int max_rounds, int grid, cudaStream_t s);
 void launch_finalize(const Dev& d, int buf, unsigned long long* ubits, unsigned long long* kbits,
                      unsigned long long* counts, cudaStream_t s);
 void launch_export(const Dev& d, int buf, fr::u256* lb, fr::u256* ub, uint8_t* nvalues,
@@ -99,11 +94,10 @@ struct Resident {
   uint64_t n_rows = 0, n_vars = 0, n_targets = 0;
   // finalisation buffers
   unsigned long long *d_ubits = nullptr, *d_kbits = nullptr, *d_counts = nullptr;
-  // CUB temp storage and P2 sort buffers
+  // CUB temp storage (set-up only)
   void* d_cub = nullptr;
   size_t cub_bytes = 0;
-  unsigned long long* d_key2 = nullptr;
-  uint32_t* d_row2 = nullptr;
+  bool table_dirty = false;  // a failed solve may leave entries in the P2 grouping table
   // pinned host staging
   Status* h_status = nullptr;
   unsigned long long* h_counts = nullptr;
@@ -114,6 +108,5 @@ struct Resident {
 
 // setup.cu: H2D + classification + layout.  Returns an ecne_status.
 int build_resident(const ecne_problem_t* p, Resident* r, std::string& err);
-int p2_sort(Resident* r, uint32_t n_cand, std::string& err);
 
 }  // namespace ecne

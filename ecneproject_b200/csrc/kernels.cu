@@ -1,14 +1,14 @@
-// kernels.cu — per-round kernels of the propagation fixpoint.
+// kernels.cu — the propagation fixpoint (/root/reference/src/R1CSConstraintSolver.jl:706-1556) as ONE
+// persistent cooperative kernel, plus the small finalisation / reset kernels.
 //
-//   k_p1_loop     the queue loop (:805-1349) as Jacobi sweeps inside ONE persistent cooperative
-//                 launch: replay last round's records -> sweep all rows -> grid barrier -> repeat
-//                 until a round produces no record (the device-wide changed flag)
-//   k_p0          special constraints (:718-800), in list order inside one block
-//   k_p2_*        linear-system sweep (:1357-1417)
-//   k_p3_*        ABZ tagging sweep (:1425-1483), lowest row wins exactly like the reference
-//   k_p4          IsZero pair sweep (:1492-1550)
-//   k_replay      bring the other state buffer up to date after a phase kernel
-//   k_finalize    verdict (:1558-1597) + packed bitmaps for the D2H
+//   k_solve       P0 -> Jacobi rounds of the single-row rules (:805-1349) to a fixpoint -> P2 -> P3 -> P4,
+//                 repeated while anything changed, all inside one launch: dense rounds sweep every live
+//                 row from shared-memory-resident row records, sparse rounds are driven by the previous
+//                 round's update records through a wire -> rows index; every step ends in a grid barrier
+//                 whose release carries the device-wide count the next step needs
+//   k_pack/...    verdict (:1558-1597) + packed bitmaps for the D2H
+#include <cstring>
+
 #include "engine_host.h"
 #include "sweep.cuh"
 
@@ -17,8 +17,6 @@ namespace ecne {
 #define P1_THREADS 1024
 #define P1_MIN_BLOCKS 1
 #define P1_MAX_KS 6     // 6 rows x 32 B x 1024 threads = 192 KB of the 227 KB shared memory
-#define CHG_WORDS 128   // 4096-bit changed-wire filter
-#define CHG_MAX 512u    // rounds with more records than this are followed by a dense round
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x ^= x >> 33;
@@ -30,33 +28,51 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
 }
 __device__ __forceinline__ void p2_candidate(const Dev& d, uint32_t row, unsigned long long hs,
                                              unsigned long long hx, uint32_t k) {
-  unsigned int i = atomicAdd(&d.st->p2_cand, 1u);
-  d.p2_key[i] = mix64(hs ^ (hx * 0x9e3779b97f4a7c15ULL) ^ k);
+  // candidate list entry + membership in the group of its unknown set (open-addressing table keyed by
+  // the 64-bit set hash; the member list is a stack linked through p2_next)
+  const unsigned long long key = mix64(hs ^ (hx * 0x9e3779b97f4a7c15ULL) ^ k) | 1ULL;  // 0 = empty slot
+  // warp-aggregated slot allocation (every still-open row is a candidate in every outer round)
+  const unsigned int am = __activemask();
+  const unsigned int ln = threadIdx.x & 31u;
+  const int leader = __ffs((int)am) - 1;
+  unsigned int i = 0;
+  if ((int)ln == leader) i = atomicAdd(&d.st->p2_cand, (unsigned int)__popc(am));
+  i = __shfl_sync(am, i, leader) + (unsigned int)__popc(am & ((1u << ln) - 1u));
   d.p2_row[i] = row;
+  d.p2_k[i] = k;
+  uint32_t slot = (uint32_t)(key >> 17) & d.h_mask;
+  while (true) {
+    const unsigned long long prev = atomicCAS(d.h_key + slot, 0ULL, key);
+    if (prev == 0ULL || prev == key) break;
+    slot = (slot + 1) & d.h_mask;
+  }
+  d.p2_slot[i] = slot;
+  atomicAdd(d.h_cnt + slot, 1u);
+  d.p2_next[i] = atomicExch(d.h_head + slot, i + 1);
 }
 
 // P2 qualification of one row through the CSR (generic path): every non-unique wire appears in C
 // only (:1364-1385).  k == 1 is decided on the spot; k >= 2 rows become (set-hash, row) candidates.
 template <int G>
-__device__ __noinline__ void p2_scan_row(const Dev& d, int rbuf, uint32_t row) {
+__device__ __noinline__ void p2_scan_row(const Dev&, int rbuf, int pl, uint32_t row) {
+  const Dev& d = c_dev;
   const uint32_t lane = Grp<G>::lane();
   const uint8_t* F = d.F[rbuf];
   const uint32_t s0 = d.seg[3 * row], s2 = d.seg[3 * row + 2], s3 = d.seg[3 * row + 3];
   uint32_t bad = 0;
-  for (uint32_t t = s0 + lane; t < s2; t += G) bad |= (ld_flag(F, d.col[t]) & WF_U) ? 0u : 1u;
+  scan_terms<G, SCAN_U(G)>(d, F, s0, s2, lane, [&](uint32_t, uint32_t f) { bad |= (f & WF_U) ? 0u : 1u; });
   if (Grp<G>::any(bad != 0)) return;  // a non-unique wire in A or B (:1366, :1378)
   uint32_t k = 0, w1 = 0;
   unsigned long long hs = 0, hx = 0;
-  for (uint32_t t = s2 + lane; t < s3; t += G) {
-    uint32_t w = d.col[t];
-    if (!(ld_flag(F, w) & WF_U)) {
+  scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
+    if (!(f & WF_U)) {
       ++k;
       w1 = w;
       unsigned long long m = mix64(w);
       hs += m;
       hx ^= mix64(m + 0x9e3779b97f4a7c15ULL);
     }
-  }
+  });
   if (G > 1) {
     k = Grp<G>::sum(k);
     w1 = Grp<G>::max(w1);
@@ -67,7 +83,7 @@ __device__ __noinline__ void p2_scan_row(const Dev& d, int rbuf, uint32_t row) {
   }
   if (k == 0 || lane != 0) return;
   if (k == 1) {  // 1x1 "matrix": the stored coefficient is non-zero (:1402)
-    emit(d, 1, 0, w1, WF_U | WF_K);
+    emit(d, 1, pl, w1, WF_U | WF_K);
     return;
   }
   p2_candidate(d, row, hs, hx, k);
@@ -88,9 +104,6 @@ __device__ __forceinline__ Rec ld_peer_rec(const Rec* p) {
                : "l"(p));
   return r;
 }
-
-// one bit of a 32-bit bloom filter per wire (multiplicative hash: neighbouring ids spread out)
-__device__ __forceinline__ uint32_t wire_bloom(uint32_t w) { return 1u << ((w * 0x9E3779B1u) >> 27); }
 
 struct InlineRow {
   uint32_t rf, meta;
@@ -168,6 +181,7 @@ __device__ __forceinline__ bool eval_inline(const Dev& d, int rbuf, int wbuf, in
   }
   // Case 2b (:949-988) on a row with no other pattern: x = t once and for all
   if (rf & RF_2B) {
+    if (d.solved[row] & 2) return true;  // already applied (a sparse round may meet the row again)
     const RowAux a = d.aux[row];
     emit(d, wbuf, list, a.w1, WF_U | WF_K, a.rank_a, a.rank_a);
     d.valsrc[a.w1] = VS_2B | a.val_idx;
@@ -223,437 +237,65 @@ __device__ __forceinline__ bool eval_inline(const Dev& d, int rbuf, int wbuf, in
   return false;
 }
 
-// The queue loop (:805-1349) as Jacobi sweeps in one persistent cooperative launch.
-//   * static row -> thread mapping: thread t owns rows row_lo + t + k*nthreads; a 64-bit register
-//     mask tracks which of them can still fire, so resolved rows cost nothing in later rounds;
-//   * fast path: one coalesced 32-byte RowRec load + the state-byte gathers of its <= 6 wires, two
-//     rows in flight per thread;
-//   * long rows get a warp each, spread over all blocks, first in the round;
-//   * one grid barrier per round; the round's record count (the device-wide changed flag) comes back
-//     with the barrier release;
-//   * tail: the P2 candidate scan (:1357-1388) over the rows that are still live.
-__global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
-    k_p1_loop(Dev d, int rbuf0, unsigned int max_rounds, int ks, int lc_words) {
-  // Shared memory, resident for the whole launch:
-  //   sm_rec   row records of the first `ks` rows of every thread: sm_rec[(2*k + h) * blockDim + thread]
-  //            is half h of the thread's k-th record
-  //   sm_chg   4096-bit hash set of the wires changed by the previous round (the frontier filter)
-  //   sm_lcol  column lists of this block's long rows (as many as fit in lc_words)
-  extern __shared__ uint4 sm_rec[];
-  uint32_t* sm_chg = reinterpret_cast<uint32_t*>(sm_rec + (size_t)(ks > 0 ? ks : 1) * 2 * P1_THREADS);
-  uint32_t* sm_lcol = sm_chg + CHG_WORDS;
-  __shared__ int s_loff[32];       // smem offset of warp j's long row (-1: not cached)
-  __shared__ uint32_t s_llen[32];  // its length
-  __shared__ uint32_t s_chg32;     // 32-bit bloom of the changed wires (first-level filter)
-  unsigned int epoch = 0;
-  int rbuf = rbuf0;
-  unsigned int list = 0;    // list written this round
-  unsigned int prev_n = 0;  // records of the previous round (to replay)
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t nthreads = gridDim.x * blockDim.x;
-  const uint32_t rows = d.row_hi - d.row_lo;
-  const uint32_t per_thread = (rows + nthreads - 1) / nthreads;
-  const uint32_t kmask = per_thread < 64 ? per_thread : 64;
-  const uint32_t warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-  unsigned int round = 0;
-  unsigned int xe = d.world > 1 ? *d.xepoch : 0u;  // cross-GPU epoch (same on every rank)
-  unsigned long long evals = 0, changed = 0, ruleevals = 0;
-  uint32_t bepoch = d.st->bepoch;  // rounds so far that tightened a bound (same value in every thread)
+// ---- phase bodies (device functions of the one persistent kernel) --------------------------------
+// Phase updates are logged in list 3 (the "phase list"): it is the frontier of the next outer round's
+// first Jacobi round, so that round only re-evaluates the rows next to what the phases changed.
+#define PL0 3  // phase list written by even outer rounds (and the prologue); odd rounds write PL0 + 1
 
-  // rows latched by P4 / 2a since the last launch leave the mask; the others are staged in smem
-  unsigned long long live = d.live[tid];
-  uint32_t sig[P1_MAX_KS];  // 32-bit bloom of the wires of the thread's k-th row (registers)
-#pragma unroll
-  for (int k = 0; k < P1_MAX_KS; ++k) {
-    sig[k] = 0xffffffffu;
-    if (k < ks && ((live >> k) & 1ULL)) {
-      uint32_t r = tid + (uint32_t)k * nthreads;
-      if (r >= rows || (d.solved[d.row_lo + r] & 1)) {
-        live &= ~(1ULL << k);
-      } else {
-        const uint4* rp = reinterpret_cast<const uint4*>(d.rec + d.row_lo + r);
-        const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
-        sm_rec[(2 * k) * blockDim.x + threadIdx.x] = q0;
-        sm_rec[(2 * k + 1) * blockDim.x + threadIdx.x] = q1;
-        if (q0.y & 0x10000u)  // inline: unused slots hold the constant wire 1, which never changes
-          sig[k] = wire_bloom(q0.z) | wire_bloom(q0.w) | wire_bloom(q1.x) | wire_bloom(q1.y) |
-                   wire_bloom(q1.z) | wire_bloom(q1.w);
-      }
-    }
-  }
-  for (unsigned long long m = live & (~0ULL << ks); m;) {  // ks <= 6
-    int k = __ffsll((long long)m) - 1;
-    m &= m - 1;
-    uint32_t r = tid + (uint32_t)k * nthreads;
-    if (r >= rows || (d.solved[d.row_lo + r] & 1)) live &= ~(1ULL << k);
-  }
-
-  // stage the column lists of this block's first 32 long rows (warp j owns long row b + j*grid)
-  if (threadIdx.x == 0) {
-    int off = 0;
-    for (uint32_t j = 0; j < 32; ++j) {
-      uint32_t i = blockIdx.x + j * gridDim.x;
-      s_loff[j] = -1;
-      if (i < d.n_long && !d.long_done[i]) {
-        uint32_t row = d.long_rows[i];
-        int len = (int)(d.seg[3 * row + 3] - d.seg[3 * row]);
-        if (off + len <= lc_words) {
-          s_loff[j] = off;
-          s_llen[j] = (uint32_t)len;
-          off += len;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (warp_in_block < 32 && s_loff[warp_in_block] >= 0) {
-    uint32_t row = d.long_rows[blockIdx.x + warp_in_block * gridDim.x];
-    uint32_t s0 = d.seg[3 * row], s3 = d.seg[3 * row + 3];
-    for (uint32_t t = s0 + (threadIdx.x & 31); t < s3; t += 32) sm_lcol[s_loff[warp_in_block] + (t - s0)] = d.col[t];
-  }
-  bool filtered = false;  // this round only evaluates rows that touch a wire changed last round
-  __syncthreads();
-#ifdef ECNE_PROFILE
-  long long pf[6] = {0, 0, 0, 0, 0, 0};  // intra-block wait, grid wait, long rows, replay, sweep, -
-#define PROF_T(x) long long x = clock64()
-#define PROF_ACC(i, a, b) pf[i] += (b) - (a)
-#else
-#define PROF_T(x)
-#define PROF_ACC(i, a, b)
-#endif
-  while (true) {
-    const int wbuf = rbuf ^ 1;
-    const uint8_t* F = d.F[rbuf];
-    PROF_T(t0);
-    // (a) long rows first (their latency overlaps the rest): block b owns long rows b, b+grid, ...
-    for (uint32_t i = blockIdx.x + warp_in_block * gridDim.x, it = 0; i < d.n_long;
-         i += warps_per_block * gridDim.x, ++it) {
-      if (d.long_done[i]) continue;
-      uint32_t row = d.long_rows[i];
-      if (row >= d.row_lo && row < d.row_hi) {
-        if (filtered) {  // does the row touch a changed wire?
-          const bool cached = it == 0 && s_loff[warp_in_block] >= 0;
-          const uint32_t s0 = cached ? 0u : d.seg[3 * row];
-          const uint32_t len = cached ? s_llen[warp_in_block] : d.seg[3 * row + 3] - s0;
-          const uint32_t* cl = cached ? sm_lcol + s_loff[warp_in_block] : d.col + s0;
-          bool hit = false;
-          for (uint32_t t = threadIdx.x & 31; t < len; t += 32) {
-            uint32_t w = cl[t];
-            hit |= (sm_chg[(w >> 5) & (CHG_WORDS - 1)] >> (w & 31)) & 1u;
-          }
-          if (!__any_sync(0xffffffffu, hit)) continue;
-        }
-        bool done = eval_row<32>(d, rbuf, wbuf, (int)list, row, bepoch);
-        if ((threadIdx.x & 31) == 0) {
-          evals += 1;
-          if (done) d.long_done[i] = 1;
-        }
-      }
-    }
-    PROF_T(t1);
-    PROF_ACC(2, t0, t1);
-    // (b) replay the previous round's records into the buffer written this round
-    if (prev_n) {
-      const Rec* pr = d.recs[(list + 2) % 3];
-      // record i goes to block i % grid so that a short list still spreads over every SM
-      for (uint32_t j = threadIdx.x; blockIdx.x + j * gridDim.x < prev_n; j += blockDim.x) {
-        Rec r = pr[blockIdx.x + j * gridDim.x];
-        apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
-      }
-    }
-    PROF_T(t2);
-    PROF_ACC(3, t1, t2);
-    // (c) sweep the rows this thread still owns, two in flight.  In a filtered round a row is first
-    // tested with one AND of its register bloom against the round's changed-set bloom.
-    evals += __popcll(live);
-    unsigned long long todo = live;
-    if (filtered) {
-      const uint32_t chg32 = s_chg32;
-      unsigned long long cand = ~0ULL << ks;  // rows beyond the smem-resident ones are always taken
-#pragma unroll
-      for (int k = 0; k < P1_MAX_KS; ++k)
-        if (sig[k] & chg32) cand |= 1ULL << k;
-      todo &= cand;
-    }
-    for (unsigned long long m = todo; m;) {
-      const int k0 = __ffsll((long long)m) - 1;
-      m &= m - 1;
-      const int k1 = m ? __ffsll((long long)m) - 1 : -1;
-      if (k1 >= 0) m &= m - 1;
-      const int kb = k1 >= 0 ? k1 : k0;
-      const uint32_t row0 = d.row_lo + tid + (uint32_t)k0 * nthreads;
-      const uint32_t row1 = d.row_lo + tid + (uint32_t)kb * nthreads;
-      InlineRow r0, r1;
-      if (k0 < ks)
-        unpack_row(sm_rec[(2 * k0) * blockDim.x + threadIdx.x], sm_rec[(2 * k0 + 1) * blockDim.x + threadIdx.x], r0);
-      else
-        load_row(d, row0, r0);
-      if (kb < ks)
-        unpack_row(sm_rec[(2 * kb) * blockDim.x + threadIdx.x], sm_rec[(2 * kb + 1) * blockDim.x + threadIdx.x], r1);
-      else
-        load_row(d, row1, r1);
-      bool go0 = true, go1 = k1 >= 0;
-      if (filtered) {
-        // Exact shortcut: a row none of whose wires changed state last round evaluates exactly as it
-        // did last round, i.e. to nothing new.  (Non-inline rows keep their wires in the CSR: they
-        // are few and simply always re-evaluated.)
-        if (r0.meta & 0x10000u) {
-          uint32_t h = 0;
-#pragma unroll
-          for (int j = 0; j < ROWREC_INLINE; ++j) h |= (sm_chg[(r0.c[j] >> 5) & (CHG_WORDS - 1)] >> (r0.c[j] & 31)) & 1u;
-          go0 = h != 0;
-        }
-        if (go1 && (r1.meta & 0x10000u)) {
-          uint32_t h = 0;
-#pragma unroll
-          for (int j = 0; j < ROWREC_INLINE; ++j) h |= (sm_chg[(r1.c[j] >> 5) & (CHG_WORDS - 1)] >> (r1.c[j] & 31)) & 1u;
-          go1 = h != 0;
-        }
-        if (!go0 && !go1) continue;
-      }
-      uint32_t f0[ROWREC_INLINE], f1[ROWREC_INLINE];
-      if (go0) gather_row(F, r0, f0);
-      if (go1) gather_row(F, r1, f1);
-      if (go0) {
-        ruleevals += 1;
-        if (eval_inline(d, rbuf, wbuf, (int)list, row0, r0, f0, bepoch)) live &= ~(1ULL << k0);
-      }
-      if (go1) {
-        ruleevals += 1;
-        if (eval_inline(d, rbuf, wbuf, (int)list, row1, r1, f1, bepoch)) live &= ~(1ULL << k1);
-      }
-    }
-    // rows beyond the 64 tracked per thread (only for problems far larger than the machine)
-    for (uint32_t k = kmask; k < per_thread; ++k) {
-      uint32_t r = tid + k * nthreads;
-      if (r < rows) {
-        uint32_t row = d.row_lo + r;
-        if (!(d.rflags[row] & RF_LONG)) eval_row<1>(d, rbuf, wbuf, (int)list, row, bepoch);
-        evals += 1;
-      }
-    }
-    PROF_T(t3);
-    PROF_ACC(4, t2, t3);
-#ifdef ECNE_PROFILE
-    if (threadIdx.x == 0 && round < 40) {
-      // per block: long-row, replay, sweep cycles of this round
-      unsigned long long* q = d.prof + 20000 + ((size_t)round * gridDim.x + blockIdx.x) * 4;
-      q[0] = (unsigned long long)(t1 - t0);
-      q[1] = (unsigned long long)(t2 - t1);
-      q[2] = (unsigned long long)(t3 - t2);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && round < 40)
-      d.prof[20000 + ((size_t)round * gridDim.x + blockIdx.x) * 4 + 3] = (unsigned long long)(clock64() - t0);
-    xe += 1;
-    unsigned int n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list,
-                                  d.world > 1 ? &d : nullptr, list, xe, pf);
-#else
-    xe += 1;
-    unsigned int n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list,
-                                  d.world > 1 ? &d : nullptr, list, xe);
-#endif
-    bepoch += n >> 31;
-    n &= 0x7fffffffu;
-    unsigned int n_own = n;
-    if (d.world > 1) {
-      // pull the peers' records of this round over NVLink and apply them to BOTH local buffers (the
-      // buffer read next round must already contain them), then a local barrier
-      n_own = __ldcg(d.xcnt + list * ECNE_MAX_WORLD + d.rank);
-      for (int h = 0; h < d.world; ++h) {
-        if (h == d.rank) continue;
-        const unsigned int nh = __ldcg(d.xcnt + list * ECNE_MAX_WORLD + h);
-        const Rec* pr = d.xrecs[h][list];
-        for (uint32_t j = tid; j < nh && j < d.rec_cap; j += nthreads) {
-          Rec r = ld_peer_rec(pr + j);
-          apply_update(d, 0, r.wire, r.bits, r.lbr, r.ubr);
-          apply_update(d, 1, r.wire, r.bits, r.lbr, r.ubr);
-        }
-      }
-      grid_barrier(d.barrier, epoch, nullptr);
-    }
-#ifdef ECNE_PROFILE
-    if (tid == 0) {
-      unsigned long long slot = atomicAdd(&d.prof[7], 1ULL);  // global round index across launches
-      if (slot < 4000) {
-        d.prof[2048 + 4 * slot + 0] = (unsigned long long)(clock64() - t0);
-        d.prof[2048 + 4 * slot + 1] = n;
-        d.prof[2048 + 4 * slot + 2] = (unsigned long long)(t3 - t2);
-        d.prof[2048 + 4 * slot + 3] = (unsigned long long)(t1 - t0);
-      }
-    }
-#endif
-    round += 1;
-    changed += n;
-    if (tid == 0) {  // replayed this round; next written in two rounds
-      d.rec_count[(list + 2) % 3] = 0;
-      d.bnd_flag[(list + 2) % 3] = 0;
-    }
-    if (n_own > d.rec_cap) n_own = d.rec_cap;
-    if (n == 0) break;  // W already holds every earlier record: both buffers are complete
-    if (round >= max_rounds) {
-      if (tid == 0) raise(d, ECNE_E_NOCONVERGE);
-      const Rec* pr = d.recs[list];
-      for (uint32_t i = tid; i < n_own; i += nthreads) {
-        Rec r = pr[i];
-        apply_update(d, rbuf, r.wire, r.bits, r.lbr, r.ubr);
-      }
-      break;
-    }
-    // frontier filter for the next round: hash set of the wires this round changed (on any rank)
-    filtered = n <= CHG_MAX;
-    if (filtered) {
-      for (uint32_t j = threadIdx.x; j < CHG_WORDS; j += blockDim.x) sm_chg[j] = 0;
-      if (threadIdx.x == 0) s_chg32 = 0;
-      __syncthreads();
-      for (int h = 0; h < (d.world > 1 ? d.world : 1); ++h) {
-        const Rec* cr = d.world > 1 ? d.xrecs[h][list] : d.recs[list];
-        const unsigned int nh = d.world > 1 ? __ldcg(d.xcnt + list * ECNE_MAX_WORLD + h) : n;
-        for (uint32_t j = threadIdx.x; j < nh && j < d.rec_cap; j += blockDim.x) {
-          uint32_t w = ld_peer_rec(cr + j).wire;
-          atomicOr(&sm_chg[(w >> 5) & (CHG_WORDS - 1)], 1u << (w & 31));
-          atomicOr(&s_chg32, wire_bloom(w));
-        }
-      }
-      __syncthreads();
-    }
-    prev_n = n_own;
-    rbuf = wbuf;
-    list = (list + 1) % 3;
-  }
-  d.live[tid] = live;
-#ifdef ECNE_PROFILE
-  if (threadIdx.x == 0)
-    for (int i = 0; i < 6; ++i) d.prof[blockIdx.x * 8 + i] += (unsigned long long)pf[i];
-  if (threadIdx.x == 0) d.prof[blockIdx.x * 8 + 6] += round;
-#endif
-  // ---- tail: P2 candidate scan over the rows that are still live (state is at the P1 fixpoint) ----
-  grid_barrier(d.barrier, epoch, nullptr);  // the list counters are all zero and visible from here on
-  if (d.world == 1) {  // sharded runs scan every row on every rank instead (k_p2_scan_all)
-    const uint8_t* F = d.F[0];
-    for (unsigned long long m = live; m;) {
-      const int k = __ffsll((long long)m) - 1;
-      m &= m - 1;
-      const uint32_t row = d.row_lo + tid + (uint32_t)k * nthreads;
-      InlineRow r;
-      load_row(d, row, r);
-      if (r.rf & RF_LONG) continue;
-      if (!(r.meta & 0x10000u)) {  // not inline
-        p2_scan_row<1>(d, 0, row);
-        continue;
-      }
-      const uint32_t nAB = r.meta & 0xffu, nT = nAB + ((r.meta >> 8) & 0xffu);
-      uint32_t kk = 0, w1 = 0;
-      bool bad = false;
-      unsigned long long hs = 0, hx = 0;
-#pragma unroll
-      for (int j = 0; j < ROWREC_INLINE; ++j) {
-        if ((uint32_t)j < nT && !(ld_flag(F, r.c[j]) & WF_U)) {
-          if ((uint32_t)j < nAB) {
-            bad = true;
-          } else {
-            ++kk;
-            w1 = r.c[j];
-            unsigned long long mm = mix64(r.c[j]);
-            hs += mm;
-            hx ^= mix64(mm + 0x9e3779b97f4a7c15ULL);
-          }
-        }
-      }
-      if (bad || kk == 0) continue;
-      if (kk == 1)
-        emit(d, 1, 0, w1, WF_U | WF_K);
-      else
-        p2_candidate(d, row, hs, hx, kk);
-    }
-    for (uint32_t k = kmask; k < per_thread; ++k) {
-      uint32_t r = tid + k * nthreads;
-      if (r < rows && !(d.rflags[d.row_lo + r] & RF_LONG) && !(d.solved[d.row_lo + r] & 1))
-        p2_scan_row<1>(d, 0, d.row_lo + r);
-    }
-    for (uint32_t i = blockIdx.x + warp_in_block * gridDim.x; i < d.n_long; i += warps_per_block * gridDim.x) {
-      uint32_t row = d.long_rows[i];
-      if (!d.long_done[i] && row >= d.row_lo && row < d.row_hi) p2_scan_row<32>(d, 0, row);
-    }
-  }
-  // statistics: one atomic per warp
-  evals = evals + __shfl_xor_sync(0xffffffffu, evals, 16);
-  evals = evals + __shfl_xor_sync(0xffffffffu, evals, 8);
-  evals = evals + __shfl_xor_sync(0xffffffffu, evals, 4);
-  evals = evals + __shfl_xor_sync(0xffffffffu, evals, 2);
-  evals = evals + __shfl_xor_sync(0xffffffffu, evals, 1);
-  if ((tid & 31) == 0) atomicAdd(&d.st->evals, evals);
-  ruleevals += __shfl_xor_sync(0xffffffffu, ruleevals, 16);
-  ruleevals += __shfl_xor_sync(0xffffffffu, ruleevals, 8);
-  ruleevals += __shfl_xor_sync(0xffffffffu, ruleevals, 4);
-  ruleevals += __shfl_xor_sync(0xffffffffu, ruleevals, 2);
-  ruleevals += __shfl_xor_sync(0xffffffffu, ruleevals, 1);
-  if ((tid & 31) == 0) atomicAdd(&d.st->rule_evals, ruleevals);
-  if (tid == 0) {
-    d.st->rounds += round;
-    d.st->changed += changed;
-    d.st->bepoch = bepoch;
-    if (d.world > 1) *d.xepoch = xe;
+// log a state change that the caller applied to BOTH buffers itself
+__device__ __forceinline__ void log_rec(const Dev& d, int pl, uint32_t w, uint32_t bits) {
+  unsigned int i = atomicAdd(d.rec_count + pl, 1u);
+  if (i < d.rec_cap) {
+    Rec r;
+    r.wire = w;
+    r.bits = bits;
+    r.lbr = ECNE_NO_LB;
+    r.ubr = ECNE_NO_UB;
+    d.recs[pl][i] = r;
+  } else {
+    d.st->rec_overflow = 1;
   }
 }
+__device__ __forceinline__ uint32_t ld_flag_cg(const uint8_t* F, uint32_t w) { return __ldcg(F + w); }
 
-// P2 candidate scan over ALL rows (multi-GPU runs: every rank computes the same candidates)
-__global__ void k_p2_scan_all(Dev d) {
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid < d.N) {
-    if (!(d.rflags[tid] & RF_LONG) && !(d.solved[tid] & 1)) p2_scan_row<1>(d, 0, tid);
-  }
-  const uint32_t warp = tid >> 5;
-  if (warp < d.n_long) {
-    uint32_t row = d.long_rows[warp];
-    if (!(d.solved[row] & 1)) p2_scan_row<32>(d, 0, row);
-  }
-}
-
-// After a phase kernel wrote its updates to buffer `buf ^ 1` and logged them in list 0: apply them
-// to `buf` too and clear the list.
-__global__ void k_replay(Dev d, int buf) {
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t nthreads = gridDim.x * blockDim.x;
-  unsigned int n = d.rec_count[0];
-  if (n > d.rec_cap) n = d.rec_cap;
-  for (uint32_t i = tid; i < n; i += nthreads) {
-    Rec r = d.recs[0][i];
-    apply_update(d, buf, r.wire, r.bits, r.lbr, r.ubr);
-  }
-}
-__global__ void k_replay_done(Dev d) {
-  d.st->changed += d.rec_count[0];
-  d.rec_count[0] = 0;
-  d.rec_count[1] = 0;
-  d.rec_count[2] = 0;
-  d.bnd_flag[0] = 0;
-}
-
-// ---- P0 / P0' (:718-800): in-order, one block; writes both buffers in place ------------------
-__global__ void k_p0(Dev d) {
-  __shared__ int s_ok;
-  for (uint32_t s = 0; s < d.n_specials; ++s) {
-    if (d.sp_solved[s]) continue;  // uniform: read by all threads from global, written below + barrier
-    if (threadIdx.x == 0) s_ok = 1;
+// P0 / P0' (:718-800): special constraints in list order, one block.  Reads buffer 1 through the L2
+// (an earlier special's outputs are visible to a later one exactly as in the reference), writes both.
+__device__ __noinline__ void phase_p0(const Dev&, int pl) {
+  const Dev& d = c_dev;
+  // The reference walks the specials in list order, so a special sees the outputs of an earlier one
+  // that fired in the same pass (and not those of a later one).  Same here: the warps judge every open
+  // special from `start` on against the current state in parallel, the lowest one that can fire fires,
+  // and the search resumes behind it.
+  __shared__ unsigned int s_first;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint32_t start = 0;
+  while (start < d.n_specials) {
+    if (threadIdx.x == 0) s_first = 0xffffffffu;
     __syncthreads();
-    for (uint32_t k = d.sp_in_ptr[s] + threadIdx.x; k < d.sp_in_ptr[s + 1]; k += blockDim.x)
-      if (!(ld_flag(d.F[0], d.sp_in[k]) & WF_U)) s_ok = 0;
+    for (uint32_t s = start + warp; s < d.n_specials; s += nwarps) {
+      if (__ldcg(d.sp_solved + s)) continue;
+      bool ok = true;
+      for (uint32_t k = d.sp_in_ptr[s] + lane; k < d.sp_in_ptr[s + 1]; k += 32)
+        ok &= (ld_flag_cg(d.F[1], d.sp_in[k]) & WF_U) != 0;
+      if (__all_sync(0xffffffffu, ok) && lane == 0) atomicMin(&s_first, s);
+    }
     __syncthreads();
-    int ok = s_ok;
+    const uint32_t f = s_first;
     __syncthreads();
-    if (!ok) continue;
-    for (uint32_t k = d.sp_out_ptr[s] + threadIdx.x; k < d.sp_out_ptr[s + 1]; k += blockDim.x) {
-      uint32_t w = d.sp_out[k];
+    if (f == 0xffffffffu) break;
+    for (uint32_t k = d.sp_out_ptr[f] + threadIdx.x; k < d.sp_out_ptr[f + 1]; k += blockDim.x) {
+      const uint32_t w = d.sp_out[k];
+      const uint32_t nw = or_flag(d.F[1], w, WF_U | WF_K);
       or_flag(d.F[0], w, WF_U | WF_K);
-      or_flag(d.F[1], w, WF_U | WF_K);
+      if (nw) log_rec(d, pl, w, WF_U | WF_K);
     }
     if (threadIdx.x == 0) {
-      d.sp_solved[s] = 1;
-      d.st->changed += 1;  // successful_steps += 1 (:731)
+      d.sp_solved[f] = 1;
+      atomicAdd(&d.st->prog, 1u);  // successful_steps += 1 (:731)
     }
     __threadfence();
     __syncthreads();
+    start = f + 1;
   }
   // P0': every (BigMultModP, BigLessThan) pair marks the BigLessThan's first three inputs (:750-800)
   if (threadIdx.x == 0) {
@@ -671,18 +313,20 @@ __global__ void k_p0(Dev d) {
           return;
         }
         for (uint32_t k = 0; k < 3; ++k) {
-          uint32_t w = d.sp_in[d.sp_in_ptr[j] + k];
-          uint32_t nw = or_flag(d.F[0], w, WF_U | WF_K);
-          or_flag(d.F[1], w, WF_U | WF_K);
-          if (nw & WF_U) d.st->changed += 1;  // not a successful_step in the reference, but it
-                                              // re-enqueues rows; a state change keeps us looping
+          const uint32_t w = d.sp_in[d.sp_in_ptr[j] + k];
+          const uint32_t nw = or_flag(d.F[1], w, WF_U | WF_K);
+          or_flag(d.F[0], w, WF_U | WF_K);
+          if (nw) {  // not a successful_step in the reference, but it re-enqueues rows (:786-795)
+            log_rec(d, pl, w, WF_U | WF_K);
+            atomicAdd(&d.st->prog, 1u);
+          }
         }
       }
     }
   }
 }
 
-// ---- P2 (:1357-1417): grouping of the candidates found by the sweep kernel's tail -------------
+// ---- P2 (:1357-1417): grouping of the candidates by identical unknown set ------------------------
 // sorted unknown set of a candidate row (k <= KMAX) with the matching coefficients
 __device__ inline uint32_t p2_unknowns(const Dev& d, const uint8_t* F, uint32_t row, uint32_t* vars,
                                        uint32_t* terms, uint32_t kmax) {
@@ -707,27 +351,51 @@ __device__ inline uint32_t p2_unknowns(const Dev& d, const uint8_t* F, uint32_t 
   return k;
 }
 
-// candidates sorted by (key, row): thread at a group start takes the first k rows in index order,
-// checks the sets really are equal, and evaluates slow_det (:1389-1400) = sum over ODD
-// permutations (Combinatorics.parity is 0 for even ones).
-__global__ void k_p2_groups(Dev d, int rbuf, uint32_t n_cand, const unsigned long long* keys,
-                            const uint32_t* rows) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_cand) return;
-  if (i > 0 && keys[i - 1] == keys[i]) return;  // not a group start
-  const uint8_t* F = d.F[rbuf];
+// One group of candidates (all members of table slot `slot`), resolved by the member that was
+// inserted last: the first k rows in index order (the reference triggers when the k-th row of a set
+// arrives and uses exactly those, :1387-1388), slow_det (:1389-1400) = sum over ODD permutations
+// (Combinatorics.parity is 0 for even ones).
+__device__ __noinline__ void p2_resolve_group(const Dev&, int pl, uint32_t c) {
+  const Dev& d = c_dev;
+  const uint32_t slot = d.p2_slot[c];
+  if (__ldcg(d.h_head + slot) != c + 1) return;  // not the group's resolver
+  const uint8_t* F = d.F[0];
+  const uint32_t cnt = __ldcg(d.h_cnt + slot);
+  if (cnt < d.p2_k[c]) return;  // fewer than k rows share this unknown set (almost every group)
   uint32_t vars[ECNE_P2_KMAX], terms[ECNE_P2_KMAX][ECNE_P2_KMAX], v2[ECNE_P2_KMAX];
-  uint32_t k = p2_unknowns(d, F, rows[i], vars, terms[0], ECNE_P2_KMAX);
-  // are there k rows in this group?
-  if (i + k > n_cand || keys[i + k - 1] != keys[i]) return;
+  uint32_t k = p2_unknowns(d, F, d.p2_row[c], vars, terms[0], ECNE_P2_KMAX);
+  if (cnt < k) return;
   if (k > ECNE_P2_KMAX) {
     raise(d, ECNE_E_UNSUPPORTED);
     return;
   }
-  for (uint32_t j = 1; j < k; ++j) {
-    uint32_t kj = p2_unknowns(d, F, rows[i + j], v2, terms[j], ECNE_P2_KMAX);
+  // the k smallest row ids of the member list
+  uint32_t best[ECNE_P2_KMAX];
+  uint32_t nb = 0;
+  for (uint32_t m = c + 1; m != 0; m = __ldcg(d.p2_next + (m - 1))) {
+    const uint32_t r = d.p2_row[m - 1];
+    if (nb < k) {
+      uint32_t j = nb++;
+      while (j > 0 && best[j - 1] > r) {
+        best[j] = best[j - 1];
+        --j;
+      }
+      best[j] = r;
+    } else if (r < best[k - 1]) {
+      uint32_t j = k - 1;
+      while (j > 0 && best[j - 1] > r) {
+        best[j] = best[j - 1];
+        --j;
+      }
+      best[j] = r;
+    }
+  }
+  if (nb < k) return;
+  for (uint32_t j = 0; j < k; ++j) {
+    uint32_t kj = p2_unknowns(d, F, best[j], j == 0 ? vars : v2, terms[j], ECNE_P2_KMAX);
     bool same = kj == k;
-    for (uint32_t x = 0; same && x < k; ++x) same = v2[x] == vars[x];
+    if (j > 0)
+      for (uint32_t x = 0; same && x < k; ++x) same = v2[x] == vars[x];
     if (!same) {  // 64-bit set-hash collision: refuse to guess
       raise(d, ECNE_E_INTERNAL);
       return;
@@ -763,55 +431,637 @@ __global__ void k_p2_groups(Dev d, int rbuf, uint32_t n_cand, const unsigned lon
     }
   }
   if (!fr::is_zero(res)) {
-    for (uint32_t j = 0; j < k; ++j) emit(d, rbuf ^ 1, 0, vars[j], WF_U | WF_K);
+    for (uint32_t j = 0; j < k; ++j) emit(d, 1, pl, vars[j], WF_U | WF_K);
   }
 }
 
-// ---- P3 (:1425-1483) ------------------------------------------------------------------------
-__global__ void k_p3_claim(Dev d, int rbuf) {
-  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= d.N) return;
-  uint32_t rf = d.rflags[row];
-  if (!(rf & RF_P3)) return;
+// ---- P3 (:1425-1483): the lowest row tags a wire, exactly the reference's order -------------------
+__device__ __forceinline__ void p3_claim_row(const Dev& d, uint32_t row) {
+  const uint32_t rf = d.rflags[row];
   const RowAux a = d.aux[row];
-  if (ld_flag(d.F[rbuf], a.w3) & WF_U) return;  // unique_b (:1448)
-  if (rf & RF_P3_DIVZ) {                         // divexact(-intercept, 0) (:1467)
+  if (ld_flag(d.F[1], a.w3) & WF_U) return;  // unique_b (:1448)
+  if (rf & RF_P3_DIVZ) {                      // divexact(-intercept, 0) (:1467)
     raise(d, ECNE_E_DIVZERO);
     return;
   }
   atomicMin(d.abz_claim + a.w3, ((unsigned long long)row << 32) | a.w4);
 }
-__global__ void k_p3_commit(Dev d, int rbuf) {
-  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= d.N) return;
-  uint32_t rf = d.rflags[row];
-  if (!(rf & RF_P3) || (rf & RF_P3_DIVZ)) return;
+__device__ __forceinline__ void p3_commit_row(const Dev& d, int pl, uint32_t row) {
+  const uint32_t rf = d.rflags[row];
+  if (rf & RF_P3_DIVZ) return;
   const RowAux a = d.aux[row];
-  if (ld_flag(d.F[rbuf], a.w3) & WF_U) return;
-  unsigned long long cl = d.abz_claim[a.w3];
+  if (ld_flag(d.F[0], a.w3) & WF_U) return;
+  unsigned long long cl = __ldcg(d.abz_claim + a.w3);
   if ((uint32_t)(cl >> 32) != row) return;  // a lower row tags this wire first
   d.abz_claim[a.w3] = ~0ULL;
-  if (d.abz[a.w3] != -1) return;            // (:1469-1473)
+  if (d.abz[a.w3] != -1) return;  // (:1469-1473)
   d.abz[a.w3] = (int32_t)a.w4;
   or_flag(d.F[0], a.w3, WF_K | WF_ABZ);
   or_flag(d.F[1], a.w3, WF_K | WF_ABZ);
-  atomicAdd(&d.st->changed, 1ULL);
+  log_rec(d, pl, a.w3, WF_K | WF_ABZ);
 }
-
-// ---- P4 (:1492-1550) ------------------------------------------------------------------------
-__global__ void k_p4(Dev d, int rbuf) {
-  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= d.N) return;
-  if (!(d.rflags[row] & RF_P4)) return;
-  const uint8_t* F = d.F[rbuf];
+// ---- P4 (:1492-1550) ------------------------------------------------------------------------------
+__device__ __forceinline__ bool p4_row(const Dev& d, int pl, uint32_t row) {
+  const uint8_t* F = d.F[0];
+  if (d.solved[row] & 1) return false;  // fired before: vk is unique
+  const uint32_t vk = d.aux[row].w4;
+  if (ld_flag(F, vk) & WF_U) return false;
   const uint32_t s0 = d.seg[3 * row], s1 = d.seg[3 * row + 1];
   for (uint32_t t = s0; t < s1; ++t)
-    if (!(ld_flag(F, d.col[t]) & WF_U)) return;  // a_unique (:1502-1511)
-  uint32_t vk = d.aux[row].w4;
-  if (ld_flag(F, vk) & WF_U) return;
-  emit(d, rbuf ^ 1, 0, vk, WF_U | WF_K);
+    if (!(ld_flag(F, d.col[t]) & WF_U)) return false;  // a_unique (:1502-1511)
+  emit(d, 1, pl, vk, WF_U | WF_K);
   d.solved[row] |= 1;  // equation_solved[i], [i+1] (:1541-1542)
   d.solved[row + 1] |= 1;
+  return true;
+}
+
+// grid barrier, then the value of *src as every block left it before the barrier
+__device__ __forceinline__ unsigned int sync_and_load(const Dev& d, const unsigned int* src) {
+  grid_sync_flip(d.barrier + 64);
+  return src ? __ldcg(src) : 0u;
+}
+
+// One short row next to a changed wire, evaluated by one thread (sparse rounds).  Long rows are
+// queued once per round (long_stamp) for a whole warp.
+#define SP_LONG_CAP 256
+#define SP_HEAVY_CAP 64
+#define HEAVY_DEG 24u
+#define SOLO_MAX 96u    // frontiers up to this size are swept by block 0 alone (one warp per record), without grid barriers
+__device__ __forceinline__ void sparse_row(const Dev& d, int rbuf, int wbuf, int list, uint32_t row,
+                                           uint32_t bepoch, unsigned int gr, uint32_t* s_long,
+                                           unsigned int* s_nlong, unsigned long long& evals) {
+  if (row == 0xffffffffu || row < d.row_lo || row >= d.row_hi) return;
+  const uint4* rp = reinterpret_cast<const uint4*>(d.rec + row);
+  const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
+  const uint32_t latched = __ldcg(d.solved + row);  // in flight together with the record
+  InlineRow ir;
+  unpack_row(q0, q1, ir);
+  if (ir.rf & RF_LONG) {
+    const uint32_t li = ir.c[0];
+    if (__ldcg(d.long_done + li)) return;
+    if (atomicExch(d.long_stamp + li, gr) == gr) return;  // already queued this round
+    const unsigned int slot = atomicAdd(s_nlong, 1u);
+    if (slot < SP_LONG_CAP) {
+      s_long[slot] = row;
+    } else {  // queue full: the (slow) one-thread walk is still exact
+      evals += 1;
+      if (eval_row<1>(d, rbuf, wbuf, list, row, bepoch)) d.long_done[li] = 1;
+    }
+    return;
+  }
+  if (latched & 1) return;  // equation_solved (:820-822)
+  uint32_t f[ROWREC_INLINE];
+  gather_row(d.F[rbuf], ir, f);
+  evals += 1;
+  eval_inline(d, rbuf, wbuf, list, row, ir, f, bepoch);
+}
+
+// A frontier-driven Jacobi round: every record of the previous round (a state change of one wire) is
+// taken by one thread, which evaluates the rows the wire -> rows index lists for that wire against
+// buffer `rbuf` and then replays the record into the other buffer.  `solo`: block 0 runs the round
+// alone (record i -> thread i); otherwise record i -> block i % grid.  Returns this thread's row visits.
+__device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, unsigned int list,
+                                                        unsigned int prev_list, unsigned int prev_n,
+                                                        uint32_t bepoch, unsigned int gr, bool solo) {
+  const Dev& d = c_dev;
+  __shared__ uint32_t s_long[SP_LONG_CAP];
+  __shared__ uint32_t s_heavy[SP_HEAVY_CAP];
+  __shared__ unsigned int s_nlong, s_nheavy;
+  const int wbuf = rbuf ^ 1;
+  // one WARP per record: its lanes take the rows listed for the record's wire (one row each, so the
+  // dependent loads of all of them are in flight together) and one more lane replays the record
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t first = solo ? warp : blockIdx.x + warp * gridDim.x;
+  const uint32_t stride = solo ? nwarps : gridDim.x * nwarps;
+  if (threadIdx.x == 0) {
+    s_nlong = 0;
+    s_nheavy = 0;
+  }
+  __syncthreads();
+  unsigned long long ev = 0;
+  const int nsrc = (d.world > 1 && prev_list < PL0) ? d.world : 1;
+  for (int h = 0; h < nsrc; ++h) {
+    const bool own = nsrc == 1 || h == d.rank;
+    const Rec* pr = nsrc == 1 ? d.recs[prev_list] : d.xrecs[h][prev_list];
+    unsigned int nh = nsrc == 1 ? prev_n : __ldcg(d.xcnt + prev_list * ECNE_MAX_WORLD + h);
+    if (nh > d.rec_cap) nh = d.rec_cap;
+    for (uint32_t i = first; i < nh; i += stride) {
+#ifdef ECNE_PROFILE
+      long long q0 = clock64();
+#endif
+      const Rec r = ld_peer_rec(pr + i);
+      // {rows listed for the wire, the first three of them}: one 16-byte load covers 97 % of the wires
+      const uint4 hd = __ldcg(reinterpret_cast<const uint4*>(d.inv_head) + r.wire);
+#ifdef ECNE_PROFILE
+      long long q1 = clock64() + (hd.x & 0);
+#endif
+      bool queued = false;
+      if (hd.x > HEAVY_DEG) {
+        unsigned int slot = 0;
+        if (lane == 0) slot = atomicAdd(&s_nheavy, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot < SP_HEAVY_CAP) {
+          if (lane == 0) s_heavy[slot] = r.wire;
+          queued = true;
+        }
+      }
+      if (!queued) {
+        for (uint32_t q = lane; q < hd.x; q += 32) {
+          uint32_t row;
+          if (q == 0) row = hd.y;
+          else if (q == 1) row = hd.z;
+          else if (q == 2) row = hd.w;
+          else row = d.inv_row[d.inv_ptr[r.wire] + q];
+          sparse_row(d, rbuf, wbuf, (int)list, row, bepoch, gr, s_long, &s_nlong, ev);
+        }
+      }
+#ifdef ECNE_PROFILE
+      long long q2 = clock64();
+#endif
+      // the replay, by a lane that has no row to evaluate when there is one
+      if (own && lane == (hd.x < 31u ? hd.x : 31u)) apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
+#ifdef ECNE_PROFILE
+      if (solo && threadIdx.x == 0 && gr < 2000) {
+        d.prof[16000 + 4 * gr + 0] = (unsigned long long)(q1 - q0);   // record + head loads
+        d.prof[16000 + 4 * gr + 1] = (unsigned long long)(q2 - q1);   // row evaluations
+        d.prof[16000 + 4 * gr + 2] = (unsigned long long)(clock64() - q2);  // replay
+        d.prof[16000 + 4 * gr + 3] = hd.x;
+      }
+#endif
+    }
+  }
+  __syncthreads();
+  {  // wires with many rows: the whole block strides their row lists
+    const unsigned int nhv = s_nheavy < SP_HEAVY_CAP ? s_nheavy : SP_HEAVY_CAP;
+    for (unsigned int x = 0; x < nhv; ++x) {
+      const uint32_t w = s_heavy[x];
+      const uint32_t lo = d.inv_ptr[w], hi = d.inv_ptr[w + 1];
+      for (uint32_t q = lo + threadIdx.x; q < hi; q += blockDim.x)
+        sparse_row(d, rbuf, wbuf, (int)list, d.inv_row[q], bepoch, gr, s_long, &s_nlong, ev);
+    }
+  }
+  __syncthreads();
+  {  // queued long rows: one warp each
+    const unsigned int nlq = s_nlong < SP_LONG_CAP ? s_nlong : SP_LONG_CAP;
+    for (unsigned int x = threadIdx.x >> 5; x < nlq; x += blockDim.x >> 5) {
+      const uint32_t row = s_long[x];
+      const bool done = eval_row<32>(d, rbuf, wbuf, (int)list, row, bepoch);
+      if ((threadIdx.x & 31u) == 0) {
+        ev += 1;
+        if (done) d.long_done[d.rec[row].c[0]] = 1;
+      }
+    }
+  }
+  return ev;
+}
+
+// The whole fixpoint (:706-1556) as ONE persistent cooperative launch (148 blocks x 1024 threads):
+//
+//   P0 -> [Jacobi rounds of the single-row rules until no record] -> P2 -> P3 -> P4 -> repeat while
+//   anything changed, every arrow a grid barrier whose release carries the count the next step needs.
+//
+// Jacobi rounds come in two kinds.  A DENSE round sweeps every row that can still fire: static
+// row -> thread mapping, the thread's first <= 6 row records resident in shared memory for the whole
+// solve, a 64-bit register mask of its live rows, long rows (> 6 terms) one warp each.  A SPARSE round
+// is driven by the previous round's update records: a row none of whose wires changed evaluates to
+// exactly what it evaluated to before, so only the rows the wire -> rows index lists next to a changed
+// wire are evaluated (one thread per record).  Both read buffer R, write buffer W and log records;
+// the records are replayed into the other buffer during the next round (one barrier per round).
+__global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
+    k_solve(unsigned int max_rounds, int ks, int lc_words) {
+  const Dev& d = c_dev;
+  extern __shared__ uint4 sm_rec[];  // sm_rec[(2*k + h) * blockDim + thread]: half h of the thread's k-th record
+  uint32_t* sm_lcol = reinterpret_cast<uint32_t*>(sm_rec + (size_t)(ks > 0 ? ks : 1) * 2 * P1_THREADS);
+  __shared__ int s_loff[32];       // smem offset of warp j's first long row (-1: not cached)
+  __shared__ uint32_t s_llen[32];  // its length
+  __shared__ unsigned int s_solo[2];
+  unsigned int epoch = 0;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  const uint32_t rows = d.row_hi - d.row_lo;
+  const uint32_t per_thread = (rows + nthreads - 1) / nthreads;
+  const uint32_t kmask = per_thread < 64 ? per_thread : 64;
+  const uint32_t warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned int xe = d.world > 1 ? *d.xepoch : 0u;  // cross-GPU epoch (same on every rank)
+  unsigned long long evals = 0, ruleevals = 0, devals = 0, dcycles = 0;
+  unsigned int rounds_total = 0, dense_rounds = 0;
+  unsigned int gr = 0;  // Jacobi round counter of the solve (stamps the long-row queue)
+  uint32_t bepoch = 0;  // rounds so far that tightened a bound (same value in every thread)
+
+  // ---- stage: live mask + the smem-resident row records ---------------------------------------
+  unsigned long long live = 0;
+  for (uint32_t k = 0; k < kmask; ++k)
+    if (tid + k * nthreads < rows) live |= 1ULL << k;
+#pragma unroll
+  for (int k = 0; k < P1_MAX_KS; ++k) {
+    if (k < ks && ((live >> k) & 1ULL)) {
+      const uint32_t r = tid + (uint32_t)k * nthreads;
+      const uint4* rp = reinterpret_cast<const uint4*>(d.rec + d.row_lo + r);
+      sm_rec[(2 * k) * blockDim.x + threadIdx.x] = __ldg(rp);
+      sm_rec[(2 * k + 1) * blockDim.x + threadIdx.x] = __ldg(rp + 1);
+    }
+  }
+  // column lists of this block's first 32 long rows (warp j owns long row b + j*grid)
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (uint32_t j = 0; j < 32; ++j) {
+      uint32_t i = blockIdx.x + j * gridDim.x;
+      s_loff[j] = -1;
+      if (i < d.n_long) {
+        uint32_t row = d.long_rows[i];
+        int len = (int)(d.seg[3 * row + 3] - d.seg[3 * row]);
+        if (off + len <= lc_words) {
+          s_loff[j] = off;
+          s_llen[j] = (uint32_t)len;
+          off += len;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp_in_block < 32 && s_loff[warp_in_block] >= 0) {
+    uint32_t row = d.long_rows[blockIdx.x + warp_in_block * gridDim.x];
+    uint32_t s0 = d.seg[3 * row], s3 = d.seg[3 * row + 3];
+    for (uint32_t t = s0 + lane; t < s3; t += 32) sm_lcol[s_loff[warp_in_block] + (t - s0)] = d.col[t];
+  }
+  // ---- prologue: P0 of the first outer round ------------------------------------------------------
+  if (blockIdx.x == 0) phase_p0(d, PL0);
+  unsigned int n_pl = sync_and_load(d, d.rec_count + PL0);
+  unsigned int prog_prev = 0, outer = 0, p4_seen = 0;
+  bool stop = false;
+  unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned int cand_total = 0, cand_max = 0;
+  long long tp = clock64();
+#define PROF(i)                               \
+  do {                                        \
+    long long t_ = clock64();                 \
+    pf[i] += (unsigned long long)(t_ - tp);   \
+    tp = t_;                                  \
+  } while (0)
+
+  while (!stop) {
+    ++outer;
+    const int pl_r = PL0 + (int)((outer - 1) & 1u);  // phase list read by this round's first Jacobi round
+    const int pl = PL0 + (int)(outer & 1u);          // ... written by this round's phases
+    // =============================== P1: Jacobi rounds to a fixpoint ===============================
+    if (outer == 1 || n_pl > 0) {
+      int rbuf = 0;
+      unsigned int list = 0, prev_list = (unsigned int)pl_r, prev_n = n_pl > d.rec_cap ? d.rec_cap : n_pl;
+      bool dense = outer == 1 || n_pl > d.sparse_max;
+      unsigned int round = 0;
+      while (true) {
+        if (!dense && d.world == 1 && prev_n <= SOLO_MAX) {
+          // ---- solo: while the frontier stays small, block 0 runs the Jacobi rounds alone; a round
+          // boundary is a block barrier + one release fence + one acquire load (which also drops this
+          // SM's L1 lines, as the grid barrier does) instead of a grid barrier
+          unsigned int n = 0;
+          if (blockIdx.x == 0) {
+            while (true) {
+              gr += 1;
+              const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, true);
+              evals += ev;
+              ruleevals += ev;
+              __syncthreads();
+              if (threadIdx.x == 0) {
+                unsigned int cnt, bf;
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cnt) : "l"(d.rec_count + list) : "memory");
+                asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(bf) : "l"(d.bnd_flag + list) : "memory");
+                s_solo[0] = cnt;
+                s_solo[1] = bf;
+                d.rec_count[prev_list] = 0;  // consumed; next written two rounds from now
+                d.bnd_flag[prev_list] = 0;
+                d.st->prog += cnt;
+              }
+              __syncthreads();
+              n = s_solo[0];
+              bepoch += s_solo[1] ? 1u : 0u;
+              round += 1;
+              if (n == 0 || n > SOLO_MAX || round >= max_rounds) break;
+              prev_list = list;
+              prev_n = n;
+              list = (list + 1) % 3;
+              rbuf ^= 1;
+            }
+            if (threadIdx.x == 0) {  // where the other blocks pick the loop up again
+              d.st->solo[0] = n;
+              d.st->solo[1] = list;
+              d.st->solo[2] = (unsigned int)rbuf;
+              d.st->solo[3] = round;
+              d.st->solo[4] = bepoch;
+              d.st->solo[5] = gr;
+            }
+          }
+          grid_sync_flip(d.barrier + 64);
+          n = __ldcg(&d.st->solo[0]);
+          list = __ldcg(&d.st->solo[1]);
+          rbuf = (int)__ldcg(&d.st->solo[2]);
+          round = __ldcg(&d.st->solo[3]);
+          bepoch = __ldcg(&d.st->solo[4]);
+          gr = __ldcg(&d.st->solo[5]);
+          PROF(7);
+          if (n == 0) break;
+          if (round >= max_rounds) {
+            if (tid == 0) raise(d, ECNE_E_NOCONVERGE);
+            break;
+          }
+          prev_list = list;
+          prev_n = n > d.rec_cap ? d.rec_cap : n;
+          list = (list + 1) % 3;
+          rbuf ^= 1;
+          dense = n > d.sparse_max;
+          continue;
+        }
+        const int wbuf = rbuf ^ 1;
+        const uint8_t* F = d.F[rbuf];
+        gr += 1;
+        long long tc0 = 0;
+        if (dense && tid == 0) tc0 = clock64();
+        if (dense) {
+          // (a) long rows first (their latency overlaps the rest): block b owns long rows b, b+grid, ...
+          for (uint32_t i = blockIdx.x + warp_in_block * gridDim.x; i < d.n_long; i += warps_per_block * gridDim.x) {
+            if (d.long_done[i]) continue;
+            const uint32_t row = d.long_rows[i];
+            if (row >= d.row_lo && row < d.row_hi) {
+              const bool done = eval_row<32>(d, rbuf, wbuf, (int)list, row, bepoch);
+              if (lane == 0) {
+                evals += 1;
+                devals += 1;
+                ruleevals += 1;
+                if (done) d.long_done[i] = 1;
+              }
+            }
+          }
+          // (b) replay the previous round's own records into the buffer written this round
+          if (prev_n) {
+            const Rec* pr = d.recs[prev_list];
+            for (uint32_t j = threadIdx.x; blockIdx.x + j * gridDim.x < prev_n; j += blockDim.x) {
+              Rec r = pr[blockIdx.x + j * gridDim.x];
+              apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
+            }
+          }
+          // (c) sweep the rows this thread still owns, two in flight
+          const unsigned int nl = (unsigned int)__popcll(live);
+          evals += nl;
+          devals += nl;
+          ruleevals += nl;
+          for (unsigned long long m = live; m;) {
+            const int k0 = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const int k1 = m ? __ffsll((long long)m) - 1 : -1;
+            if (k1 >= 0) m &= m - 1;
+            const int kb = k1 >= 0 ? k1 : k0;
+            const uint32_t row0 = d.row_lo + tid + (uint32_t)k0 * nthreads;
+            const uint32_t row1 = d.row_lo + tid + (uint32_t)kb * nthreads;
+            InlineRow r0, r1;
+            if (k0 < ks)
+              unpack_row(sm_rec[(2 * k0) * blockDim.x + threadIdx.x], sm_rec[(2 * k0 + 1) * blockDim.x + threadIdx.x], r0);
+            else
+              load_row(d, row0, r0);
+            if (kb < ks)
+              unpack_row(sm_rec[(2 * kb) * blockDim.x + threadIdx.x], sm_rec[(2 * kb + 1) * blockDim.x + threadIdx.x], r1);
+            else
+              load_row(d, row1, r1);
+            uint32_t f0[ROWREC_INLINE], f1[ROWREC_INLINE];
+            gather_row(F, r0, f0);
+            if (k1 >= 0) gather_row(F, r1, f1);
+            if (eval_inline(d, rbuf, wbuf, (int)list, row0, r0, f0, bepoch)) live &= ~(1ULL << k0);
+            if (k1 >= 0 && eval_inline(d, rbuf, wbuf, (int)list, row1, r1, f1, bepoch)) live &= ~(1ULL << k1);
+          }
+          // rows beyond the 64 tracked per thread (only for problems far larger than the machine)
+          for (uint32_t k = kmask; k < per_thread; ++k) {
+            uint32_t r = tid + k * nthreads;
+            if (r < rows) {
+              uint32_t row = d.row_lo + r;
+              if (!(d.rflags[row] & RF_LONG) && !(d.solved[row] & 1)) eval_row<1>(d, rbuf, wbuf, (int)list, row, bepoch);
+              evals += 1;
+              devals += 1;
+              ruleevals += 1;
+            }
+          }
+        } else {
+          const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, false);
+          evals += ev;
+          ruleevals += ev;
+        }
+        xe += 1;
+        unsigned int n;
+        if (d.world > 1) {
+          n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list, &d, list, xe);
+          bepoch += n >> 31;
+          n &= 0x7fffffffu;
+        } else {
+          grid_sync_flip(d.barrier + 64);
+          n = __ldcg(d.rec_count + list);
+          bepoch += __ldcg(d.bnd_flag + list) ? 1u : 0u;
+        }
+        unsigned int n_own = n;
+        if (d.world > 1) {
+          // pull the peers' records of this round over NVLink and apply them to BOTH local buffers (the
+          // buffer read next round must already contain them), then a local barrier
+          n_own = __ldcg(d.xcnt + list * ECNE_MAX_WORLD + d.rank);
+          for (int h = 0; h < d.world; ++h) {
+            if (h == d.rank) continue;
+            const unsigned int nh = __ldcg(d.xcnt + list * ECNE_MAX_WORLD + h);
+            const Rec* pr = d.xrecs[h][list];
+            for (uint32_t j = tid; j < nh && j < d.rec_cap; j += nthreads) {
+              Rec r = ld_peer_rec(pr + j);
+              apply_update(d, 0, r.wire, r.bits, r.lbr, r.ubr);
+              apply_update(d, 1, r.wire, r.bits, r.lbr, r.ubr);
+            }
+          }
+          grid_barrier(d.barrier, epoch, nullptr);
+        }
+        if (tid == 0 && d.prof && gr < 4000) {
+          d.prof[4 * gr + 0] = (unsigned long long)(clock64() - tp);
+          d.prof[4 * gr + 1] = n;
+          d.prof[4 * gr + 2] = dense ? 1 : 0;
+          d.prof[4 * gr + 3] = outer;
+        }
+        if (dense) {
+          dense_rounds += 1;
+          if (tid == 0) dcycles += (unsigned long long)(clock64() - tc0);
+          PROF(0);
+        } else {
+          PROF(1);
+        }
+        round += 1;
+        if (tid == 0) {  // the list read this round is consumed; it is next written two rounds from now
+          d.rec_count[prev_list] = 0;
+          d.bnd_flag[prev_list] = 0;
+          d.st->prog += n;
+        }
+        if (n_own > d.rec_cap) n_own = d.rec_cap;
+        if (n == 0) break;  // W already holds every earlier record: both buffers are complete
+        if (round >= max_rounds) {
+          if (tid == 0) raise(d, ECNE_E_NOCONVERGE);
+          break;
+        }
+        prev_list = list;
+        prev_n = n_own;
+        list = (list + 1) % 3;
+        rbuf = wbuf;
+        dense = n > d.sparse_max;
+      }
+      rounds_total += round;
+    }
+    // =============================== P2: linear systems (:1357-1417) ===============================
+    // candidate scan over the rows that can still fire (state is at the P1 fixpoint, in both buffers)
+    {
+      const uint8_t* F = d.F[0];
+      if (d.world == 1) {
+        for (unsigned long long m = live; m;) {
+          const int k = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          const uint32_t row = d.row_lo + tid + (uint32_t)k * nthreads;
+          InlineRow r;
+          if (k < ks)
+            unpack_row(sm_rec[(2 * k) * blockDim.x + threadIdx.x], sm_rec[(2 * k + 1) * blockDim.x + threadIdx.x], r);
+          else
+            load_row(d, row, r);
+          if (r.rf & RF_LONG) continue;
+          if (!(r.meta & 0x10000u)) {  // not inline
+            if (!(d.solved[row] & 1)) p2_scan_row<1>(d, 0, pl, row);
+            continue;
+          }
+          const uint32_t nAB = r.meta & 0xffu, nT = nAB + ((r.meta >> 8) & 0xffu);
+          uint32_t kk = 0, w1 = 0;
+          bool bad = false;
+          unsigned long long hs = 0, hx = 0;
+#pragma unroll
+          for (int j = 0; j < ROWREC_INLINE; ++j) {
+            if ((uint32_t)j < nT && !(ld_flag(F, r.c[j]) & WF_U)) {
+              if ((uint32_t)j < nAB) {
+                bad = true;
+              } else {
+                ++kk;
+                w1 = r.c[j];
+                unsigned long long mm = mix64(r.c[j]);
+                hs += mm;
+                hx ^= mix64(mm + 0x9e3779b97f4a7c15ULL);
+              }
+            }
+          }
+          if (bad || kk == 0) continue;
+          if (d.solved[row] & 1) continue;  // equation_solved rows take no part (:1360)
+          if (kk == 1)
+            emit(d, 1, pl, w1, WF_U | WF_K);
+          else
+            p2_candidate(d, row, hs, hx, kk);
+        }
+        for (uint32_t k = kmask; k < per_thread; ++k) {
+          uint32_t r = tid + k * nthreads;
+          if (r < rows && !(d.rflags[d.row_lo + r] & RF_LONG) && !(d.solved[d.row_lo + r] & 1))
+            p2_scan_row<1>(d, 0, pl, d.row_lo + r);
+        }
+      } else {  // sharded: every rank scans every row (same candidates everywhere)
+        for (uint32_t row = tid; row < d.N; row += nthreads)
+          if (!(d.rflags[row] & RF_LONG) && !(d.solved[row] & 1)) p2_scan_row<1>(d, 0, pl, row);
+      }
+      for (uint32_t i = blockIdx.x + warp_in_block * gridDim.x; i < d.n_long; i += warps_per_block * gridDim.x) {
+        const uint32_t row = d.long_rows[i];
+        if (d.solved[row] & 1) continue;
+        if (d.world == 1 && d.long_done[i]) continue;
+        p2_scan_row<32>(d, 0, pl, row);
+      }
+    }
+    unsigned int n_cand = sync_and_load(d, &d.st->p2_cand);
+    if (n_cand > d.N) n_cand = d.N;
+    cand_total += n_cand;
+    cand_max = n_cand > cand_max ? n_cand : cand_max;
+    PROF(2);
+    for (uint32_t c = tid; c < n_cand; c += nthreads) p2_resolve_group(d, pl, c);
+    const unsigned int n_x = sync_and_load(d, d.rec_count + pl);
+    PROF(3);
+    // replay the P2 updates into buffer 0, clear the table, P3 claim (reads buffer 1: complete, untouched
+    // here).  P3 can only ever tag in the first outer round: a wire it looks at is either unique (for
+    // good) or was tagged then, so later rounds skip it — and with nothing to replay, the barrier too.
+    const bool p3_round = outer == 1;
+    {
+      const unsigned int nx = n_x > d.rec_cap ? d.rec_cap : n_x;
+      for (uint32_t i = tid; i < nx; i += nthreads) {
+        Rec r = d.recs[pl][i];
+        apply_update(d, 0, r.wire, r.bits, r.lbr, r.ubr);
+      }
+      for (uint32_t c = tid; c < n_cand; c += nthreads) {
+        const uint32_t slot = d.p2_slot[c];
+        d.h_key[slot] = 0ULL;
+        d.h_cnt[slot] = 0;
+        d.h_head[slot] = 0;
+      }
+      if (tid == 0) d.st->p2_cand = 0;
+      if (p3_round)
+        for (uint32_t i = tid; i < d.n_p3; i += nthreads) p3_claim_row(d, d.p3_rows[i]);
+    }
+    if (p3_round || n_x > 0) sync_and_load(d, nullptr);
+    PROF(4);
+    // P3 commit (reads buffer 0, writes K|ABZ to both) and P4 (reads buffer 0, U|K to buffer 1)
+    {
+      if (p3_round)
+        for (uint32_t i = tid; i < d.n_p3; i += nthreads) p3_commit_row(d, pl, d.p3_rows[i]);
+      bool fired = false;
+      for (uint32_t i = tid; i < d.n_p4; i += nthreads) fired |= p4_row(d, pl, d.p4_rows[i]);
+      if (fired) atomicAdd(&d.st->p4_fired, 1u);
+    }
+    const unsigned int n_y = sync_and_load(d, d.rec_count + pl);
+    PROF(5);
+    // replay the P4 updates into buffer 0; block 0 runs the next outer round's P0 (buffer 1 is complete)
+    {
+      const unsigned int nx = n_x > d.rec_cap ? d.rec_cap : n_x, ny = n_y > d.rec_cap ? d.rec_cap : n_y;
+      for (uint32_t i = nx + tid; i < ny; i += nthreads) {
+        Rec r = d.recs[pl][i];
+        apply_update(d, 0, r.wire, r.bits, r.lbr, r.ubr);
+      }
+      if (tid == 0) atomicAdd(&d.st->prog, n_y);
+      if (blockIdx.x == 0) {
+        __syncthreads();  // prog += n_y is ordered before P0's atomics on it
+        phase_p0(d, pl);
+      }
+    }
+    n_pl = sync_and_load(d, d.rec_count + pl);
+    PROF(6);
+    const unsigned int prog = __ldcg(&d.st->prog);
+    const unsigned int err = __ldcg(&d.st->err) | __ldcg(&d.st->rec_overflow);
+    if (err || prog == prog_prev) stop = true;  // successful_steps did not move (:708-711)
+    prog_prev = prog;
+    if (!stop && outer >= d.max_outer) {
+      if (tid == 0) raise(d, ECNE_E_NOCONVERGE);
+      stop = true;
+    }
+    // rows latched by P4 leave the live masks (equation_solved, :820-822)
+    const unsigned int p4f = __ldcg(&d.st->p4_fired);
+    if (!stop && p4f != p4_seen) {
+      p4_seen = p4f;
+      for (unsigned long long m = live; m;) {
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (d.solved[d.row_lo + tid + (uint32_t)k * nthreads] & 1) live &= ~(1ULL << k);
+      }
+    }
+  }
+  // ---- statistics: one atomic per warp ---------------------------------------------------------------
+  for (int o = 16; o > 0; o >>= 1) {
+    evals += __shfl_xor_sync(0xffffffffu, evals, o);
+    ruleevals += __shfl_xor_sync(0xffffffffu, ruleevals, o);
+    devals += __shfl_xor_sync(0xffffffffu, devals, o);
+  }
+  if (lane == 0) {
+    atomicAdd(&d.st->evals, evals);
+    atomicAdd(&d.st->rule_evals, ruleevals);
+    atomicAdd(&d.st->dense_evals, devals);
+  }
+  if (tid == 0) {
+    d.st->rounds = rounds_total;
+    d.st->outer = outer;
+    d.st->dense_rounds = dense_rounds;
+    d.st->dense_cycles = dcycles;
+    d.st->bepoch = bepoch;
+    for (int i = 0; i < 8; ++i) d.st->prof[i] = pf[i];
+    d.st->n_cand_total = cand_total;
+    d.st->n_cand_max = cand_max;
+    if (d.world > 1) *d.xepoch = xe;
+  }
 }
 
 // ---- finalisation ---------------------------------------------------------------------------
@@ -899,14 +1149,6 @@ __global__ void k_reset_wires(Dev d) {
     d.abz_claim[w] = ~0ULL;
   }
 }
-__global__ void k_reset_live(Dev d, uint32_t nthreads) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nthreads) return;
-  uint32_t rows = d.row_hi - d.row_lo;
-  uint32_t per_thread = (rows + nthreads - 1) / nthreads;
-  uint32_t k = per_thread < 64 ? per_thread : 64;
-  d.live[t] = k >= 64 ? ~0ULL : ((1ULL << k) - 1ULL);
-}
 __global__ void k_reset_known(Dev d) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.n_known) return;
@@ -920,72 +1162,63 @@ __global__ void k_reset_known(Dev d) {
 static inline unsigned int blocks_for(uint64_t n, unsigned int t) { return (unsigned int)((n + t - 1) / t); }
 
 cudaError_t launch_reset(const Dev& d, int grid, cudaStream_t s) {
+  (void)grid;
   k_reset_wires<<<blocks_for((uint64_t)d.V + 4, 256), 256, 0, s>>>(d);
-  k_reset_live<<<blocks_for((uint64_t)grid * P1_THREADS, 256), 256, 0, s>>>(d, (uint32_t)grid * P1_THREADS);
   if (d.n_known) k_reset_known<<<blocks_for(d.n_known, 256), 256, 0, s>>>(d);
   cudaMemsetAsync(d.solved, 0, (size_t)d.N + 1, s);
   if (d.n_long) cudaMemsetAsync(d.long_done, 0, d.n_long, s);
+  if (d.n_long) cudaMemsetAsync(d.long_stamp, 0, (size_t)d.n_long * sizeof(unsigned int), s);
   if (d.n_specials) cudaMemsetAsync(d.sp_solved, 0, d.n_specials, s);
-  cudaMemsetAsync(d.rec_count, 0, 3 * sizeof(unsigned int), s);
-  cudaMemsetAsync(d.bnd_flag, 0, 3 * sizeof(unsigned int), s);
+  cudaMemsetAsync(d.rec_count, 0, 8 * sizeof(unsigned int), s);
+  cudaMemsetAsync(d.bnd_flag, 0, 8 * sizeof(unsigned int), s);
   cudaMemsetAsync(d.c5sig, 0xff, (size_t)(d.N ? d.N : 1) * sizeof(uint32_t), s);
   cudaMemsetAsync(d.st, 0, sizeof(Status), s);
   return cudaGetLastError();
 }
+cudaError_t launch_clear_p2_table(const Dev& d, cudaStream_t s) {
+  const size_t cap = (size_t)d.h_mask + 1;
+  cudaMemsetAsync(d.h_key, 0, cap * sizeof(unsigned long long), s);
+  cudaMemsetAsync(d.h_cnt, 0, cap * sizeof(uint32_t), s);
+  cudaMemsetAsync(d.h_head, 0, cap * sizeof(uint32_t), s);
+  return cudaGetLastError();
+}
 
 int p1_threads() { return P1_THREADS; }
+static size_t solve_max_smem() { return (size_t)P1_MAX_KS * 2 * sizeof(uint4) * P1_THREADS + 28 * 1024; }  // 220 KB
 int p1_grid_size(int device) {
   static int cached = 0;
   if (cached) return cached;
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  cudaFuncSetAttribute(k_p1_loop, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       P1_MAX_KS * 2 * (int)sizeof(uint4) * P1_THREADS + 28 * 1024);
+  cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_max_smem());
   cached = sms;  // one 1024-thread block per SM (persistent, cooperative)
   return cached;
 }
 
-cudaError_t launch_p1(const Dev& d, int rbuf, unsigned int max_rounds, int grid, cudaStream_t s) {
-  cudaMemsetAsync(d.barrier, 0, 64 * sizeof(unsigned int), s);
-  Dev dd = d;
-  int rb = rbuf;
+// the whole fixpoint: one cooperative launch
+cudaError_t launch_solve(const Dev& d, unsigned int max_rounds, int grid, cudaStream_t s) {
+  cudaMemsetAsync(d.barrier, 0, 128 * sizeof(unsigned int), s);
+  // the descriptor goes to constant memory (skipped when it is what the last solve used)
+  static Dev last;
+  static bool have_last = false;
+  if (!have_last || memcmp(&last, &d, sizeof(Dev)) != 0) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_dev, &d, sizeof(Dev), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    memcpy(&last, &d, sizeof(Dev));
+    have_last = true;
+  }
   unsigned int mr = max_rounds;
   const uint32_t rows = d.row_hi - d.row_lo;
   const uint32_t nthreads = (uint32_t)grid * P1_THREADS;
   int ks = (int)((rows + nthreads - 1) / nthreads);
   if (ks > P1_MAX_KS) ks = P1_MAX_KS;
   const size_t rec_bytes = (size_t)(ks > 0 ? ks : 1) * 2 * sizeof(uint4) * P1_THREADS;
-  const size_t max_smem = (size_t)P1_MAX_KS * 2 * sizeof(uint4) * P1_THREADS + 28 * 1024;  // 220 KB
-  int lc_words = (int)((max_smem - rec_bytes - CHG_WORDS * 4) / 4);
-  size_t smem = rec_bytes + CHG_WORDS * 4 + (size_t)lc_words * 4;
-  void* args[] = {&dd, &rb, &mr, &ks, &lc_words};
-  return cudaLaunchCooperativeKernel((void*)k_p1_loop, dim3(grid), dim3(P1_THREADS), args, smem, s);
+  int lc_words = (int)((solve_max_smem() - rec_bytes) / 4);
+  size_t smem = rec_bytes + (size_t)lc_words * 4;
+  void* args[] = {&mr, &ks, &lc_words};
+  return cudaLaunchCooperativeKernel((void*)k_solve, dim3(grid), dim3(P1_THREADS), args, smem, s);
 }
 
-void launch_replay(const Dev& d, int buf, cudaStream_t s) {
-  k_replay<<<148, 256, 0, s>>>(d, buf);
-  k_replay_done<<<1, 1, 0, s>>>(d);
-}
-
-void launch_p2_scan_all(const Dev& d, cudaStream_t s) {
-  uint64_t n = d.N > (uint64_t)d.n_long * 32 ? d.N : (uint64_t)d.n_long * 32;
-  if (n) k_p2_scan_all<<<blocks_for(n, 256), 256, 0, s>>>(d);
-}
-void launch_p0(const Dev& d, cudaStream_t s) {
-  if (d.n_specials) k_p0<<<1, 256, 0, s>>>(d);
-}
-void launch_p2_groups(const Dev& d, int rbuf, uint32_t n_cand, const unsigned long long* keys,
-                      const uint32_t* rows, cudaStream_t s) {
-  if (n_cand) k_p2_groups<<<blocks_for(n_cand, 128), 128, 0, s>>>(d, rbuf, n_cand, keys, rows);
-}
-void launch_p3(const Dev& d, int rbuf, cudaStream_t s) {
-  if (!d.N) return;
-  k_p3_claim<<<blocks_for(d.N, 256), 256, 0, s>>>(d, rbuf);
-  k_p3_commit<<<blocks_for(d.N, 256), 256, 0, s>>>(d, rbuf);
-}
-void launch_p4(const Dev& d, int rbuf, cudaStream_t s) {
-  if (d.N) k_p4<<<blocks_for(d.N, 256), 256, 0, s>>>(d, rbuf);
-}
 void launch_finalize(const Dev& d, int buf, unsigned long long* ubits, unsigned long long* kbits,
                      unsigned long long* counts, cudaStream_t s) {
   cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), s);

@@ -483,6 +483,53 @@ __global__ void k_long_rows(uint32_t N, const uint32_t* rflags, uint32_t* out, u
   if (row < N && (rflags[row] & RF_LONG)) out[atomicAdd(n, 1u)] = row;
 }
 
+// long rows keep their index into long_rows[] in the (otherwise unused) first inline slot
+__global__ void k_long_index(uint32_t n, const uint32_t* long_rows, RowRec* rec) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rec[long_rows[i]].c[0] = i;
+}
+// static lists of the rows with the P3 (ABZ) and P4 (IsZero pair) shapes
+__global__ void k_phase_rows(uint32_t N, const uint32_t* rflags, uint32_t* p3, uint32_t* p4, unsigned int* n) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  uint32_t rf = rflags[row];
+  if (rf & RF_P3) p3[atomicAdd(n + 0, 1u)] = row;
+  if (rf & RF_P4) p4[atomicAdd(n + 1, 1u)] = row;
+}
+// wire -> rows index over the non-zero terms (the constant wire 1 never changes state: left out)
+__global__ void k_inv_count(uint32_t nnz, const uint32_t* col, uint32_t* cnt) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nnz && col[t] != 1) atomicAdd(cnt + col[t], 1u);
+}
+__global__ void k_inv_fill(uint32_t N, const uint32_t* seg, const uint32_t* col, const uint32_t* inv_ptr,
+                           uint32_t* cursor, uint32_t* inv_row) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  const uint32_t s0 = seg[3 * row], s3 = seg[3 * row + 3];
+  for (uint32_t t = s0; t < s3; ++t) {
+    const uint32_t w = col[t];
+    if (w == 1) continue;
+    bool dup = false;  // a wire that occurs in several forms of a short row is listed once
+    if (s3 - s0 <= 8)
+      for (uint32_t u = s0; u < t; ++u) dup |= col[u] == w;
+    if (dup) continue;
+    inv_row[inv_ptr[w] + atomicAdd(cursor + w, 1u)] = row;
+  }
+}
+
+__global__ void k_inv_head(uint32_t nw, const uint32_t* inv_ptr, const uint32_t* filled, const uint32_t* inv_row,
+                           uint4* head) {
+  uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  const uint32_t lo = inv_ptr[w], n = filled[w];
+  uint4 h;
+  h.x = n;
+  h.y = n > 0 ? inv_row[lo] : 0xffffffffu;
+  h.z = n > 1 ? inv_row[lo + 1] : 0xffffffffu;
+  h.w = n > 2 ? inv_row[lo + 2] : 0xffffffffu;
+  head[w] = h;
+}
+
 // ---- bound-value table: sort the candidates, rank the distinct values ---------------------------
 __global__ void k_consts(fr::u256* cand) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -784,8 +831,62 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   RowRec* d_rec;
   CK(A.alloc(&d_rec, N));
   if (N) k_rowrec<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_segnz, d_col, d_rflags, d_rec);
+  if (cnt.n_long) k_long_index<<<nb(cnt.n_long, 256), 256, 0, s>>>(cnt.n_long, d_long, d_rec);
   CK(A.alloc(&d.live, (size_t)p1_grid_size(0) * p1_threads()));
   CK(A.alloc(&d.long_done, (size_t)cnt.n_long));
+  CK(A.alloc(&d.long_stamp, (size_t)cnt.n_long));
+  // static P3 / P4 row lists
+  uint32_t *d_p3, *d_p4;
+  unsigned int* d_nphase;
+  CK(A.alloc(&d_p3, N));
+  CK(A.alloc(&d_p4, N));
+  CK(tmp.alloc(&d_nphase, 2));
+  CK(cudaMemsetAsync(d_nphase, 0, 2 * sizeof(unsigned int), s));
+  if (N) k_phase_rows<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_rflags, d_p3, d_p4, d_nphase);
+  unsigned int h_nphase[2] = {0, 0};
+  CK(cudaMemcpyAsync(h_nphase, d_nphase, sizeof(h_nphase), cudaMemcpyDeviceToHost, s));
+  // wire -> rows index (count, scan, fill)
+  uint32_t *d_inv_ptr, *d_inv_row, *d_inv_cur;
+  CK(A.alloc(&d_inv_ptr, V + 3));
+  CK(A.alloc(&d_inv_row, (size_t)nnz_nz + 1));
+  CK(tmp.alloc(&d_inv_cur, V + 3));
+  CK(cudaMemsetAsync(d_inv_cur, 0, (V + 3) * sizeof(uint32_t), s));
+  if (nnz_nz) k_inv_count<<<nb(nnz_nz, 256), 256, 0, s>>>(nnz_nz, d_col, d_inv_cur);
+  {
+    size_t b = cub_bytes, need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, d_inv_cur, d_inv_ptr, (int)(V + 2), s);
+    if (need > b) {
+      err = "internal: scan scratch too small";
+      return ECNE_E_INTERNAL;
+    }
+    CK(cub::DeviceScan::ExclusiveSum(d_cub, b, d_inv_cur, d_inv_ptr, (int)(V + 2), s));
+  }
+  CK(cudaMemsetAsync(d_inv_cur, 0, (V + 3) * sizeof(uint32_t), s));
+  CK(cudaMemsetAsync(d_inv_row, 0xff, ((size_t)nnz_nz + 1) * sizeof(uint32_t), s));  // 0xffffffff = unused slot
+  if (N) k_inv_fill<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_segnz, d_col, d_inv_ptr, d_inv_cur, d_inv_row);
+  uint4* d_inv_head;
+  CK(A.alloc(&d_inv_head, V + 2));
+  k_inv_head<<<nb(V + 2, 256), 256, 0, s>>>((uint32_t)(V + 2), d_inv_ptr, d_inv_cur, d_inv_row, d_inv_head);
+  d.inv_ptr = d_inv_ptr;
+  d.inv_row = d_inv_row;
+  d.inv_head = d_inv_head;
+  d.p3_rows = d_p3;
+  d.p4_rows = d_p4;
+  // P2 grouping table: power of two >= 2 N slots
+  {
+    uint32_t cap = 1024;
+    while (cap < 2 * (uint64_t)N && cap < (1u << 30)) cap <<= 1;
+    d.h_mask = cap - 1;
+    CK(A.alloc(&d.h_key, (size_t)cap));
+    CK(A.alloc(&d.h_cnt, (size_t)cap));
+    CK(A.alloc(&d.h_head, (size_t)cap));
+    CK(cudaMemsetAsync(d.h_key, 0, (size_t)cap * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(d.h_cnt, 0, (size_t)cap * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(d.h_head, 0, (size_t)cap * sizeof(uint32_t), s));
+    CK(A.alloc(&d.p2_next, N));
+    CK(A.alloc(&d.p2_slot, N));
+    CK(A.alloc(&d.p2_k, N));
+  }
 
   // ---- wire state, records, scratch -----------------------------------------------------------
   for (int b = 0; b < 2; ++b) {
@@ -800,18 +901,15 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(A.alloc(&d.solved, N + 2));
   CK(A.alloc(&d.sp_solved, n_sp));
   d.rec_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2 * V, nnz) + 4096, 0x7ffffff0ULL);
-  for (int l = 0; l < 3; ++l) CK(A.alloc(&d.recs[l], d.rec_cap));
-  CK(A.alloc(&d.rec_count, 4));
-  CK(A.alloc(&d.bnd_flag, 4));
+  for (int l = 0; l < 5; ++l) CK(A.alloc(&d.recs[l], d.rec_cap));
+  CK(A.alloc(&d.rec_count, 8));
+  CK(A.alloc(&d.bnd_flag, 8));
   CK(A.alloc(&d.c5sig, N));
-  CK(A.alloc(&d.barrier, 64));
+  CK(A.alloc(&d.barrier, 128));
   CK(A.alloc(&d.prof, (size_t)20000 + 40 * 148 * 4));
   CK(cudaMemsetAsync(d.prof, 0, ((size_t)20000 + 40 * 148 * 4) * sizeof(unsigned long long), s));
   CK(A.alloc(&d.st, 1));
-  CK(A.alloc(&d.p2_key, N));
   CK(A.alloc(&d.p2_row, N));
-  CK(A.alloc(&R->d_key2, N));
-  CK(A.alloc(&R->d_row2, N));
   CK(A.alloc(&R->d_ubits, (V + 63) / 64));
   CK(A.alloc(&R->d_kbits, (V + 63) / 64));
   CK(A.alloc(&R->d_counts, 4));
@@ -823,6 +921,8 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   d.table_n = h_tn;
   d.nnz = nnz_nz;
   d.n_long = cnt.n_long;
+  d.n_p3 = h_nphase[0];
+  d.n_p4 = h_nphase[1];
   d.seg = d_segnz;
   d.col = d_col;
   d.coef = d_coef;
@@ -852,20 +952,6 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
     err = "internal: rank of 0 is not 0";
     return ECNE_E_INTERNAL;
   }
-  return ECNE_OK;
-}
-
-// Sort the P2 candidates by (key, row): rows first, then a stable pass over the 64-bit keys.
-int p2_sort(Resident* R, uint32_t n, std::string& err) {
-  Dev& d = R->d;
-  cudaStream_t s = R->stream;
-  int row_bits = 1;
-  while ((1ull << row_bits) < (unsigned long long)d.N + 1) ++row_bits;
-  size_t b = R->cub_bytes;
-  CK(cub::DeviceRadixSort::SortPairs(R->d_cub, b, d.p2_row, R->d_row2, d.p2_key, R->d_key2, (int)n, 0,
-                                     row_bits, s));
-  b = R->cub_bytes;
-  CK(cub::DeviceRadixSort::SortPairs(R->d_cub, b, R->d_key2, d.p2_key, R->d_row2, d.p2_row, (int)n, 0, 64, s));
   return ECNE_OK;
 }
 

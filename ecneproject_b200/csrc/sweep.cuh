@@ -10,6 +10,12 @@
 
 namespace ecne {
 
+// The problem descriptor of the running solve lives in constant memory: every device function reads
+// its pointers and sizes through the constant cache instead of a by-reference copy of a 900-byte kernel
+// parameter in local memory (which costs an L2 round trip per field after every L1 invalidation).
+// One solve runs at a time per process (the API is single-threaded).
+__constant__ Dev c_dev;
+
 template <int G>
 struct Grp {
   static __device__ __forceinline__ uint32_t lane() { return G == 1 ? 0u : (threadIdx.x & 31u); }
@@ -83,12 +89,11 @@ struct Overlay {
 };
 
 struct RowCtx {
-  const Dev& d;
   int rbuf, wbuf, list;
   uint32_t row, rf, s2, s3;
   Overlay ov;
-  __device__ __forceinline__ RowCtx(const Dev& dd) : d(dd) {}
   __device__ __forceinline__ void bounds(uint32_t w, uint32_t& l, uint32_t& u) const {
+    const Dev& d = c_dev;
     int i = ov.find(w);
     if (i >= 0) {
       l = ov.lb[i];
@@ -99,21 +104,24 @@ struct RowCtx {
     }
   }
   __device__ __forceinline__ bool b01(uint32_t w) const {
+    const Dev& d = c_dev;
     int i = ov.find(w);
     if (i >= 0) return ov.lb[i] == d.r0 && ov.ub[i] == d.r1;
     return ld_flag(d.B[rbuf], w) != 0;
   }
   __device__ __forceinline__ bool uniq(uint32_t w) const {
+    const Dev& d = c_dev;
     return ov.all_unique || (ld_flag(d.F[rbuf], w) & WF_U);
   }
   __device__ __forceinline__ bool known(uint32_t w) const {
+    const Dev& d = c_dev;
     int i = ov.find(w);
     if (i >= 0 && ov.k[i]) return true;
     return ld_flag(d.F[rbuf], w) & WF_K;
   }
   __device__ __forceinline__ void out(uint32_t w, uint32_t bits, uint32_t l = ECNE_NO_LB,
                                       uint32_t u = ECNE_NO_UB) const {
-    emit(d, wbuf, list, w, bits, l, u);
+    emit(c_dev, wbuf, list, w, bits, l, u);
   }
 };
 
@@ -130,7 +138,7 @@ __device__ __forceinline__ fr::u256 case5_mag(const fr::u256& c, bool flipped) {
 
 // one link of the mixed-radix chain (:1266-1272): lo = term `tp`, hi = term `tc`
 __device__ __noinline__ bool case5_pair_ok(const RowCtx& c, uint32_t tp, uint32_t tc) {
-  const Dev& d = c.d;
+  const Dev& d = c_dev;
   bool flipped = (c.rf & RF_C3_FLIP) != 0;
   fr::u256 dlo = case5_mag(d.coef[tp], flipped);
   fr::u256 dhi = case5_mag(d.coef[tc], flipped);
@@ -145,7 +153,7 @@ __device__ __noinline__ bool case5_pair_ok(const RowCtx& c, uint32_t tp, uint32_
 }
 // the top test (:1274): fail when d * (ub + 1) > p
 __device__ __noinline__ bool case5_top_ok(const RowCtx& c, uint32_t t) {
-  const Dev& d = c.d;
+  const Dev& d = c_dev;
   fr::u256 dm = case5_mag(d.coef[t], (c.rf & RF_C3_FLIP) != 0);
   uint32_t l, u;
   c.bounds(d.col[t], l, u);
@@ -157,7 +165,7 @@ __device__ __noinline__ bool case5_top_ok(const RowCtx& c, uint32_t t) {
 // Case 5 (:1235-1298) on C terms that are stored sorted by magnitude.  Returns true on success.
 template <int G>
 __device__ __noinline__ bool case5(const RowCtx& c) {
-  const Dev& d = c.d;
+  const Dev& d = c_dev;
   const uint32_t lane = Grp<G>::lane();
   bool ok = true;
   uint32_t prev = 0xffffffffu;  // previous selected term (group-uniform)
@@ -198,8 +206,9 @@ __device__ __noinline__ bool case5(const RowCtx& c) {
 // Returns true when the row can never fire again (so the caller may stop sweeping it): it is
 // latched as solved, or it has no bound pattern and no non-unique wire left in C.
 template <int G>
-__device__ __noinline__ bool eval_row(const Dev& d, int rbuf, int wbuf, int list, uint32_t row,
+__device__ __noinline__ bool eval_row(const Dev&, int rbuf, int wbuf, int list, uint32_t row,
                                       uint32_t bepoch) {
+  const Dev& d = c_dev;
   const uint32_t lane = Grp<G>::lane();
   const uint32_t rf = d.rflags[row];
   uint8_t latch = d.solved[row];
@@ -226,7 +235,7 @@ __device__ __noinline__ bool eval_row(const Dev& d, int rbuf, int wbuf, int list
     abzmiss = Grp<G>::sum(abzmiss);
   }
 
-  RowCtx c(d);
+  RowCtx c;
   c.rbuf = rbuf;
   c.wbuf = wbuf;
   c.list = list;

@@ -98,11 +98,17 @@ typedef struct ecne_result {
   uint64_t outer_rounds;        /* iterations of the `while true` at :706                    */
   uint64_t inner_rounds;        /* Jacobi rounds of the single-row rule sweep                */
   uint64_t constraint_evals;    /* rows visited by sweep/phase kernels        */
-  uint64_t sweep_launches;      /* kernels launched by this solve                            */
+  uint64_t sweep_launches;      /* launches of the persistent solve kernel (1)               */
   double ms_h2d, ms_classify, ms_solve, ms_d2h, ms_exchange, ms_total;
   double ms_sweep;              /* device time inside the single-row sweep kernel only       */
-  uint64_t rule_evals;          /* of constraint_evals: rows whose rule set was re-run in full (a
-                                   swept row none of whose wires changed is settled by the filter) */
+  uint64_t rule_evals;          /* of constraint_evals: rows whose rule set was run in full       */
+  /* the sweep kernel's two kinds of Jacobi round: dense rounds sweep every row that can still fire,
+   * the others are driven by the previous round's update records */
+  uint64_t dense_rounds;        /* number of dense rounds                                          */
+  uint64_t dense_evals;         /* rows visited by them                                            */
+  uint64_t dense_cycles;        /* SM cycles (clock64, block 0) spent in them, barrier included    */
+  double ms_device;             /* CUDA-event time of the whole call on the engine's stream: reset,
+                                   all rounds, verdict kernels and the D2H of the bitmaps           */
 } ecne_result_t;
 
 /* ---- life cycle ------------------------------------------------------------------------- */

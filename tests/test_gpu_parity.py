@@ -126,13 +126,20 @@ def test_resident_solve_is_repeatable():
     ph = api.ProblemHandle(reduced, specials, main.known, main.targets, main.n_vars, secp)
     h = C.c_void_p()
     assert lib.ecne_upload(C.byref(ph.c), C.byref(h)) == 0
-    outs = []
+    outs, evals = [], []
     for _ in range(3):
         res = api.SolveResult(main.n_vars)
         assert lib.ecne_solve_resident(h, C.byref(res.c)) == 0
-        outs.append((res.unique_bytes(), res.known_bytes(), res.c.inner_rounds, res.c.constraint_evals))
+        outs.append((res.unique_bytes(), res.known_bytes(), res.c.inner_rounds, res.c.outer_rounds))
+        evals.append(res.c.constraint_evals)
     lib.ecne_free_resident(h)
-    assert outs[0] == outs[1] == outs[2]
+    for o in outs[1:]:
+        assert o[0] == outs[0][0], "unique bitmap differs between two solves of the same resident problem"
+        assert o[1] == outs[0][1], "is_known bitmap differs between two solves of the same resident problem"
+        assert o[2:] == outs[0][2:], (o[2:], outs[0][2:])
+    # the number of row visits of a frontier-driven round depends on which of two racing rows logs a
+    # wire first (one record or two); the state it reaches does not
+    assert max(evals) - min(evals) <= 0.02 * max(evals)
     assert hashlib.sha256(outs[0][0]).hexdigest() == GOLD["tornado/merkleTree"]["sha_unique"]
 
 
