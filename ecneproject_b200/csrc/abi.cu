@@ -278,13 +278,30 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
             "dense evals %llu evals %llu\n",
             S.prof[0], S.dense_rounds, S.prof[1], S.rounds - S.dense_rounds, S.prof[2], S.prof[3], S.prof[4], S.prof[5],
             S.prof[6], S.prof[7], S.outer, S.n_cand_total, S.n_cand_max, S.dense_evals, S.evals);
+    if (atoi(getenv("ECNE_DEBUG_PROF")) > 2) {
+      std::vector<unsigned long long> pr(28000 + 12 * 148 * 4);
+      cudaMemcpy(pr.data(), d.prof, pr.size() * 8, cudaMemcpyDeviceToHost);
+      for (int r = 0; r < 12; ++r) {
+        unsigned long long mx[3] = {0, 0, 0}, sum[3] = {0, 0, 0}, g = 0;
+        for (int b = 0; b < 148; ++b)
+          for (int k = 0; k < 3; ++k) {
+            unsigned long long v = pr[28000 + ((size_t)r * 148 + b) * 4 + k];
+            mx[k] = v > mx[k] ? v : mx[k];
+            sum[k] += v;
+            g = pr[28000 + ((size_t)r * 148 + b) * 4 + 3];
+          }
+        if (g) fprintf(stderr, "[dense] round %llu: long rows mean %llu max %llu | replay mean %llu max %llu | sweep mean %llu max %llu\n", g,
+                       sum[0] / 148, mx[0], sum[1] / 148, mx[1], sum[2] / 148, mx[2]);
+      }
+    }
     if (atoi(getenv("ECNE_DEBUG_PROF")) > 1) {
-      std::vector<unsigned long long> pr(16000 + 4 * 2000);
+      std::vector<unsigned long long> pr(28000 + 12 * 148 * 4);
       cudaMemcpy(pr.data(), d.prof, pr.size() * 8, cudaMemcpyDeviceToHost);
       for (unsigned long long g = 1; g <= S.rounds && g < 4000; ++g)
-        fprintf(stderr, "[round] %llu cycles %llu records %llu dense %llu outer %llu | thread0: rec+head %llu rows %llu replay %llu deg %llu\n", g,
+        fprintf(stderr, "[round] %llu cycles %llu records %llu dense %llu outer %llu | thread0: rec+head %llu rows %llu replay %llu deg %llu | solo: round-body %llu bar %llu fence %llu acquire %llu\n", g,
                 pr[4 * g], pr[4 * g + 1], pr[4 * g + 2], pr[4 * g + 3], g < 2000 ? pr[16000 + 4 * g] : 0,
-                g < 2000 ? pr[16000 + 4 * g + 1] : 0, g < 2000 ? pr[16000 + 4 * g + 2] : 0, g < 2000 ? pr[16000 + 4 * g + 3] : 0);
+                g < 2000 ? pr[16000 + 4 * g + 1] : 0, g < 2000 ? pr[16000 + 4 * g + 2] : 0, g < 2000 ? pr[16000 + 4 * g + 3] : 0, g < 1000 ? pr[24000 + 4 * g] : 0, g < 1000 ? pr[24000 + 4 * g + 1] : 0,
+                g < 1000 ? pr[24000 + 4 * g + 2] : 0, g < 1000 ? pr[24000 + 4 * g + 3] : 0);
     }
   }
   const uint64_t launches = 1;

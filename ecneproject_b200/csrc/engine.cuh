@@ -62,7 +62,13 @@ struct __align__(16) RowAux {
 };
 
 // ---- per-wire flag bits -------------------------------------------------------------------------
-enum : uint32_t { WF_U = 1, WF_K = 2, WF_ABZ = 4, WF_BND = 8 };  // BND: bounds were ever tightened
+enum : uint32_t { WF_U = 1, WF_K = 2, WF_ABZ = 4, WF_BND = 8,  // BND: bounds were ever tightened
+                  // the derived test "lb == 0 && ub == 1" (Case 3 asks it of every bit, :1024) as two OR-monotone
+                  // bits: UB01 = some update brought ub down to <= 1; NOT01 = some update made lb > 0 or ub < 1.
+                  // bounds == [0,1]  <=>  UB01 && !NOT01 (lb only grows from 0, ub only shrinks from p-1)
+                  WF_UB01 = 0x10, WF_NOT01 = 0x20,
+                  WF_HEAVY = 0x80 };  // static: the wire occurs in more than HEAVY_DEG rows (set at reset, never by a rule)
+#define HEAVY_DEG 24u
 
 // update record: OR `bits` into F, max `lbr` into LBR, min `ubr` into UBR
 struct __align__(16) Rec {
@@ -122,7 +128,6 @@ struct Dev {
   const fr::u256* table;  // [table_n] sorted distinct bound values
   // wires (double buffered)
   uint8_t* F[2];
-  uint8_t* B[2];
   uint32_t* LBR[2];
   uint32_t* UBR[2];
   int32_t* abz;
@@ -200,6 +205,13 @@ __device__ __forceinline__ void raise(const Dev& d, int status) {
   atomicCAS(&d.st->err, 0u, (unsigned int)(-status));
 }
 
+// OR bits into a byte of F; returns the byte as it was before
+__device__ __forceinline__ uint32_t or_flag_old(uint8_t* F, uint32_t w, uint32_t bits) {
+  unsigned int* word = (unsigned int*)(F + (w & ~3u));
+  unsigned int sh = (w & 3u) * 8;
+  unsigned int old = atomicOr(word, bits << sh);
+  return (old >> sh) & 0xffu;
+}
 // OR bits into a byte of F; returns the bits that were newly set
 __device__ __forceinline__ uint32_t or_flag(uint8_t* F, uint32_t w, uint32_t bits) {
   unsigned int* word = (unsigned int*)(F + (w & ~3u));
@@ -208,75 +220,7 @@ __device__ __forceinline__ uint32_t or_flag(uint8_t* F, uint32_t w, uint32_t bit
   return bits & ~((old >> sh) & 0xffu);
 }
 
-// Recompute the derived "bounds == [0,1]" byte after a rank update.  lb only grows and ub only
-// shrinks, so re-reading until stable makes the last writer publish the final value.
-__device__ __forceinline__ void refresh_b01(const Dev& d, int buf, uint32_t w) {
-  volatile uint32_t* lb = d.LBR[buf];
-  volatile uint32_t* ub = d.UBR[buf];
-  volatile uint8_t* b = d.B[buf];
-  uint32_t l = lb[w], u = ub[w];
-  while (true) {
-    b[w] = (l == d.r0 && u == d.r1) ? 1 : 0;
-    __threadfence();
-    uint32_t l2 = lb[w], u2 = ub[w];
-    if (l2 == l && u2 == u) break;
-    l = l2;
-    u = u2;
-  }
-}
-
-// Apply one update to buffer `buf`; returns bit0: it changed something there, bit1: a bound moved.
-__device__ __forceinline__ uint32_t apply_update(const Dev& d, int buf, uint32_t w, uint32_t bits,
-                                             uint32_t lbr, uint32_t ubr) {
-  bool ch = false;
-  if (lbr != ECNE_NO_LB || ubr != ECNE_NO_UB) bits |= WF_BND;
-  bool bch = false;
-  if (lbr != ECNE_NO_LB) bch |= atomicMax(d.LBR[buf] + w, lbr) < lbr;
-  if (ubr != ECNE_NO_UB) bch |= atomicMin(d.UBR[buf] + w, ubr) > ubr;
-  if (bch) refresh_b01(d, buf, w);
-  // the flag byte goes last: a reader that sees WF_BND also sees the ranks (both are re-read
-  // from L2 only after the next grid barrier anyway)
-  if (bits) ch |= or_flag(d.F[buf], w, bits) != 0;
-  return ((ch | bch) ? 1u : 0u) | (bch ? 2u : 0u);
-}
-
-// Apply an update to the write buffer and, when it changed anything there, log it for the other
-// buffer.  A row only calls this when its evaluation against the snapshot wants something the snapshot
-// does not have; the write buffer can already hold it only because another row of the SAME round got
-// there first, so "first writer logs" makes the round's records an exact, duplicate-free list of state
-// changes: "no record in a round" is exactly "fixpoint", and the records are the next round's frontier.
-__device__ __forceinline__ void emit(const Dev& d, int wbuf, int list, uint32_t w, uint32_t bits,
-                                     uint32_t lbr = ECNE_NO_LB, uint32_t ubr = ECNE_NO_UB) {
-  const bool bnd = lbr != ECNE_NO_LB || ubr != ECNE_NO_UB;
-  bool ch;
-  if (bnd) {
-    bits |= WF_BND;
-    const uint32_t r = apply_update(d, wbuf, w, bits, lbr, ubr);
-    ch = (r & 1u) != 0;
-    if (r & 2u) d.bnd_flag[list] = 1u;
-  } else {
-    ch = or_flag(d.F[wbuf], w, bits) != 0;
-  }
-  if (!ch) return;
-  // warp-aggregated slot allocation: the lanes that reach this point together take one atomic (a round
-  // that changes 300 k wires would otherwise serialise 300 k RMWs on one L2 address)
-  const unsigned int am = __activemask();
-  const unsigned int lane = threadIdx.x & 31u;
-  const int leader = __ffs((int)am) - 1;
-  unsigned int i = 0;
-  if ((int)lane == leader) i = atomicAdd(d.rec_count + list, (unsigned int)__popc(am));
-  i = __shfl_sync(am, i, leader) + (unsigned int)__popc(am & ((1u << lane) - 1u));
-  if (i < d.rec_cap) {
-    Rec r;
-    r.wire = w;
-    r.bits = bits;
-    r.lbr = lbr;
-    r.ubr = ubr;
-    d.recs[list][i] = r;
-  } else {
-    d.st->rec_overflow = 1;
-  }
-}
+__device__ __forceinline__ bool is01(uint32_t f) { return (f & (WF_UB01 | WF_NOT01)) == WF_UB01; }
 
 // Cross-GPU part of the round barrier, executed by the last local arriver only: post
 // {epoch, bound bit, own record count} into every peer's mailbox (NVLink peer store), then wait until
@@ -353,7 +297,7 @@ __device__ __forceinline__ unsigned int grid_barrier(unsigned int* bar, unsigned
       // last arriver: everybody's records are visible (acquire through the RMW chain)
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       payload = payload_src ? *((volatile const unsigned int*)payload_src) : 0u;
-      if (flag_src && *((volatile const unsigned int*)flag_src)) payload |= 0x80000000u;
+      if (flag_src && (*((volatile const unsigned int*)flag_src) & 1u)) payload |= 0x80000000u;
       if (xd) payload = cross_gpu_exchange(*xd, xlist, payload, xe);
       unsigned long long v = ((unsigned long long)payload << 32) | epoch;
       asm volatile("st.release.gpu.u64 [%0], %1;" ::"l"(rel), "l"(v) : "memory");

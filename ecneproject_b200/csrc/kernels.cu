@@ -129,8 +129,9 @@ __device__ __forceinline__ void gather_row(const uint8_t* F, const InlineRow& r,
   for (int j = 0; j < ROWREC_INLINE; ++j)
     f[j] = ((r.rf & RF_FAST) && (uint32_t)j < nT) ? ld_flag(F, r.c[j]) : (WF_U | WF_K | WF_ABZ);
 }
-__device__ __forceinline__ bool eval_inline(const Dev& d, int rbuf, int wbuf, int list, uint32_t row,
+__device__ __forceinline__ bool eval_inline(const Dev&, int rbuf, int wbuf, int list, uint32_t row,
                                             const InlineRow& r, const uint32_t* f, uint32_t bepoch) {
+  const Dev& d = c_dev;
   const uint32_t rf = r.rf;
   if (!(rf & RF_FAST)) {
     if (rf & RF_LONG) return true;  // swept by a whole warp instead
@@ -244,6 +245,7 @@ __device__ __forceinline__ bool eval_inline(const Dev& d, int rbuf, int wbuf, in
 
 // log a state change that the caller applied to BOTH buffers itself
 __device__ __forceinline__ void log_rec(const Dev& d, int pl, uint32_t w, uint32_t bits) {
+  if (d.inv_head[w].x > HEAVY_DEG) atomicOr(d.bnd_flag + pl, 2u);
   unsigned int i = atomicAdd(d.rec_count + pl, 1u);
   if (i < d.rec_cap) {
     Rec r;
@@ -260,37 +262,67 @@ __device__ __forceinline__ uint32_t ld_flag_cg(const uint8_t* F, uint32_t w) { r
 
 // P0 / P0' (:718-800): special constraints in list order, one block.  Reads buffer 1 through the L2
 // (an earlier special's outputs are visible to a later one exactly as in the reference), writes both.
-__device__ __noinline__ void phase_p0(const Dev&, int pl) {
+#define SPC_N 64     // specials whose wire lists block 0 keeps in shared memory
+#define SPC_IN 1024
+#define SPC_OUT 512
+struct SpecialsCache {
+  uint32_t in_ptr[SPC_N + 1], out_ptr[SPC_N + 1];
+  uint32_t in[SPC_IN], out[SPC_OUT];
+  uint8_t solved[SPC_N];
+  int ok;  // the lists fit
+};
+__device__ __forceinline__ void specials_cache_fill(const Dev& d, SpecialsCache& c) {
+  const bool fits = d.n_specials <= SPC_N && (d.n_specials == 0 || (d.sp_in_ptr[d.n_specials] <= SPC_IN &&
+                                                                     d.sp_out_ptr[d.n_specials] <= SPC_OUT));
+  if (threadIdx.x == 0) c.ok = fits ? 1 : 0;
+  if (fits) {
+    for (uint32_t i = threadIdx.x; i <= d.n_specials; i += blockDim.x) {
+      c.in_ptr[i] = d.sp_in_ptr[i];
+      c.out_ptr[i] = d.sp_out_ptr[i];
+      if (i < d.n_specials) c.solved[i] = 0;
+    }
+    const uint32_t ni = d.n_specials ? d.sp_in_ptr[d.n_specials] : 0, no = d.n_specials ? d.sp_out_ptr[d.n_specials] : 0;
+    for (uint32_t i = threadIdx.x; i < ni; i += blockDim.x) c.in[i] = d.sp_in[i];
+    for (uint32_t i = threadIdx.x; i < no; i += blockDim.x) c.out[i] = d.sp_out[i];
+  }
+  __syncthreads();
+}
+
+__device__ __noinline__ void phase_p0(const Dev&, int pl, SpecialsCache& sc) {
   const Dev& d = c_dev;
   // The reference walks the specials in list order, so a special sees the outputs of an earlier one
   // that fired in the same pass (and not those of a later one).  Same here: the warps judge every open
   // special from `start` on against the current state in parallel, the lowest one that can fire fires,
-  // and the search resumes behind it.
+  // and the search resumes behind it.  The wire lists are read from shared memory when they fit.
   __shared__ unsigned int s_first;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool cached = sc.ok != 0;
   uint32_t start = 0;
   while (start < d.n_specials) {
     if (threadIdx.x == 0) s_first = 0xffffffffu;
     __syncthreads();
     for (uint32_t s = start + warp; s < d.n_specials; s += nwarps) {
-      if (__ldcg(d.sp_solved + s)) continue;
+      if (cached ? sc.solved[s] : __ldcg(d.sp_solved + s)) continue;
+      const uint32_t k0 = cached ? sc.in_ptr[s] : d.sp_in_ptr[s], k1 = cached ? sc.in_ptr[s + 1] : d.sp_in_ptr[s + 1];
       bool ok = true;
-      for (uint32_t k = d.sp_in_ptr[s] + lane; k < d.sp_in_ptr[s + 1]; k += 32)
-        ok &= (ld_flag_cg(d.F[1], d.sp_in[k]) & WF_U) != 0;
+      for (uint32_t k = k0 + lane; k < k1; k += 32)
+        ok &= (ld_flag_cg(d.F[1], cached ? sc.in[k] : d.sp_in[k]) & WF_U) != 0;
       if (__all_sync(0xffffffffu, ok) && lane == 0) atomicMin(&s_first, s);
     }
     __syncthreads();
     const uint32_t f = s_first;
     __syncthreads();
     if (f == 0xffffffffu) break;
-    for (uint32_t k = d.sp_out_ptr[f] + threadIdx.x; k < d.sp_out_ptr[f + 1]; k += blockDim.x) {
-      const uint32_t w = d.sp_out[k];
+    const uint32_t o0 = cached ? sc.out_ptr[f] : d.sp_out_ptr[f], o1 = cached ? sc.out_ptr[f + 1] : d.sp_out_ptr[f + 1];
+    for (uint32_t k = o0 + threadIdx.x; k < o1; k += blockDim.x) {
+      const uint32_t w = cached ? sc.out[k] : d.sp_out[k];
       const uint32_t nw = or_flag(d.F[1], w, WF_U | WF_K);
       or_flag(d.F[0], w, WF_U | WF_K);
       if (nw) log_rec(d, pl, w, WF_U | WF_K);
     }
     if (threadIdx.x == 0) {
       d.sp_solved[f] = 1;
+      if (cached) sc.solved[f] = 1;
       atomicAdd(&d.st->prog, 1u);  // successful_steps += 1 (:731)
     }
     __threadfence();
@@ -485,11 +517,11 @@ __device__ __forceinline__ unsigned int sync_and_load(const Dev& d, const unsign
 // queued once per round (long_stamp) for a whole warp.
 #define SP_LONG_CAP 256
 #define SP_HEAVY_CAP 64
-#define HEAVY_DEG 24u
 #define SOLO_MAX 96u    // frontiers up to this size are swept by block 0 alone (one warp per record), without grid barriers
-__device__ __forceinline__ void sparse_row(const Dev& d, int rbuf, int wbuf, int list, uint32_t row,
+__device__ __forceinline__ void sparse_row(const Dev&, int rbuf, int wbuf, int list, uint32_t row,
                                            uint32_t bepoch, unsigned int gr, uint32_t* s_long,
                                            unsigned int* s_nlong, unsigned long long& evals) {
+  const Dev& d = c_dev;
   if (row == 0xffffffffu || row < d.row_lo || row >= d.row_hi) return;
   const uint4* rp = reinterpret_cast<const uint4*>(d.rec + row);
   const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
@@ -628,12 +660,9 @@ __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, un
 // wire are evaluated (one thread per record).  Both read buffer R, write buffer W and log records;
 // the records are replayed into the other buffer during the next round (one barrier per round).
 __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
-    k_solve(unsigned int max_rounds, int ks, int lc_words) {
+    k_solve(unsigned int max_rounds, int ks) {
   const Dev& d = c_dev;
   extern __shared__ uint4 sm_rec[];  // sm_rec[(2*k + h) * blockDim + thread]: half h of the thread's k-th record
-  uint32_t* sm_lcol = reinterpret_cast<uint32_t*>(sm_rec + (size_t)(ks > 0 ? ks : 1) * 2 * P1_THREADS);
-  __shared__ int s_loff[32];       // smem offset of warp j's first long row (-1: not cached)
-  __shared__ uint32_t s_llen[32];  // its length
   __shared__ unsigned int s_solo[2];
   unsigned int epoch = 0;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -662,31 +691,13 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       sm_rec[(2 * k + 1) * blockDim.x + threadIdx.x] = __ldg(rp + 1);
     }
   }
-  // column lists of this block's first 32 long rows (warp j owns long row b + j*grid)
-  if (threadIdx.x == 0) {
-    int off = 0;
-    for (uint32_t j = 0; j < 32; ++j) {
-      uint32_t i = blockIdx.x + j * gridDim.x;
-      s_loff[j] = -1;
-      if (i < d.n_long) {
-        uint32_t row = d.long_rows[i];
-        int len = (int)(d.seg[3 * row + 3] - d.seg[3 * row]);
-        if (off + len <= lc_words) {
-          s_loff[j] = off;
-          s_llen[j] = (uint32_t)len;
-          off += len;
-        }
-      }
-    }
-  }
   __syncthreads();
-  if (warp_in_block < 32 && s_loff[warp_in_block] >= 0) {
-    uint32_t row = d.long_rows[blockIdx.x + warp_in_block * gridDim.x];
-    uint32_t s0 = d.seg[3 * row], s3 = d.seg[3 * row + 3];
-    for (uint32_t t = s0 + lane; t < s3; t += 32) sm_lcol[s_loff[warp_in_block] + (t - s0)] = d.col[t];
-  }
   // ---- prologue: P0 of the first outer round ------------------------------------------------------
-  if (blockIdx.x == 0) phase_p0(d, PL0);
+  __shared__ SpecialsCache s_spc;
+  if (blockIdx.x == 0) {
+    specials_cache_fill(d, s_spc);
+    phase_p0(d, PL0, s_spc);
+  }
   unsigned int n_pl = sync_and_load(d, d.rec_count + PL0);
   unsigned int prog_prev = 0, outer = 0, p4_seen = 0;
   bool stop = false;
@@ -708,7 +719,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     if (outer == 1 || n_pl > 0) {
       int rbuf = 0;
       unsigned int list = 0, prev_list = (unsigned int)pl_r, prev_n = n_pl > d.rec_cap ? d.rec_cap : n_pl;
-      bool dense = outer == 1 || n_pl > d.sparse_max;
+      bool dense = outer == 1 || n_pl > d.sparse_max || (__ldcg(d.bnd_flag + pl_r) & 2u) != 0;
       unsigned int round = 0;
       while (true) {
         if (!dense && d.world == 1 && prev_n <= SOLO_MAX) {
@@ -719,26 +730,58 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           if (blockIdx.x == 0) {
             while (true) {
               gr += 1;
+#ifdef ECNE_PROFILE
+              long long z0 = clock64(), z1 = 0, z2 = 0, z3 = 0, z4 = 0;
+#endif
               const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, true);
               evals += ev;
               ruleevals += ev;
+#ifdef ECNE_PROFILE
+              z1 = clock64();
+#endif
               __syncthreads();
               if (threadIdx.x == 0) {
                 unsigned int cnt, bf;
+#ifdef ECNE_PROFILE
+                z2 = clock64();
+#endif
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#ifdef ECNE_PROFILE
+                z3 = clock64();
+#endif
                 asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cnt) : "l"(d.rec_count + list) : "memory");
                 asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(bf) : "l"(d.bnd_flag + list) : "memory");
                 s_solo[0] = cnt;
                 s_solo[1] = bf;
+#ifdef ECNE_PROFILE
+                z4 = clock64();
+                if (gr < 1000) {
+                  d.prof[24000 + 4 * gr + 0] = (unsigned long long)(z1 - z0);  // sparse_round
+                  d.prof[24000 + 4 * gr + 1] = (unsigned long long)(z2 - z1);  // block barrier
+                  d.prof[24000 + 4 * gr + 2] = (unsigned long long)(z3 - z2);  // fence
+                  d.prof[24000 + 4 * gr + 3] = (unsigned long long)(z4 - z3);  // acquire + flag loads
+                }
+#endif
                 d.rec_count[prev_list] = 0;  // consumed; next written two rounds from now
                 d.bnd_flag[prev_list] = 0;
-                d.st->prog += cnt;
+                atomicAdd(&d.st->prog, cnt);
               }
               __syncthreads();
               n = s_solo[0];
-              bepoch += s_solo[1] ? 1u : 0u;
+              bepoch += s_solo[1] & 1u;
               round += 1;
-              if (n == 0 || n > SOLO_MAX || round >= max_rounds) break;
+#ifdef ECNE_PROFILE
+              if (threadIdx.x == 0 && gr < 4000) {
+                long long t_ = clock64();
+                d.prof[4 * gr + 0] = (unsigned long long)(t_ - tp);
+                d.prof[4 * gr + 1] = n;
+                d.prof[4 * gr + 2] = 2;
+                d.prof[4 * gr + 3] = outer;
+                pf[7] += (unsigned long long)(t_ - tp);
+                tp = t_;
+              }
+#endif
+              if (n == 0 || n > SOLO_MAX || (s_solo[1] & 2u) || round >= max_rounds) break;
               prev_list = list;
               prev_n = n;
               list = (list + 1) % 3;
@@ -751,6 +794,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               d.st->solo[3] = round;
               d.st->solo[4] = bepoch;
               d.st->solo[5] = gr;
+              d.st->solo[6] = s_solo[1] & 2u;
             }
           }
           grid_sync_flip(d.barrier + 64);
@@ -760,6 +804,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           round = __ldcg(&d.st->solo[3]);
           bepoch = __ldcg(&d.st->solo[4]);
           gr = __ldcg(&d.st->solo[5]);
+          const unsigned int hv = __ldcg(&d.st->solo[6]);
           PROF(7);
           if (n == 0) break;
           if (round >= max_rounds) {
@@ -770,7 +815,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           prev_n = n > d.rec_cap ? d.rec_cap : n;
           list = (list + 1) % 3;
           rbuf ^= 1;
-          dense = n > d.sparse_max;
+          dense = n > d.sparse_max || hv != 0;
           continue;
         }
         const int wbuf = rbuf ^ 1;
@@ -793,6 +838,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               }
             }
           }
+#ifdef ECNE_PROFILE
+          long long dz1 = clock64();
+#endif
           // (b) replay the previous round's own records into the buffer written this round
           if (prev_n) {
             const Rec* pr = d.recs[prev_list];
@@ -801,6 +849,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
             }
           }
+#ifdef ECNE_PROFILE
+          long long dz2 = clock64();
+#endif
           // (c) sweep the rows this thread still owns, two in flight
           const unsigned int nl = (unsigned int)__popcll(live);
           evals += nl;
@@ -840,6 +891,16 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               ruleevals += 1;
             }
           }
+#ifdef ECNE_PROFILE
+          if (threadIdx.x == 0 && dense_rounds < 40) {
+            unsigned long long* q = d.prof + 28000 + ((size_t)dense_rounds * gridDim.x + blockIdx.x) * 4;
+            long long dz3 = clock64();
+            q[0] = (unsigned long long)(dz1 - tp);  // long rows (from round start)
+            q[1] = (unsigned long long)(dz2 - dz1);
+            q[2] = (unsigned long long)(dz3 - dz2);
+            q[3] = gr;
+          }
+#endif
         } else {
           const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, false);
           evals += ev;
@@ -847,6 +908,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         }
         xe += 1;
         unsigned int n;
+        bool heavy = false;  // a wire with very many rows changed: sweep densely instead of chasing its list
         if (d.world > 1) {
           n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list, &d, list, xe);
           bepoch += n >> 31;
@@ -854,7 +916,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         } else {
           grid_sync_flip(d.barrier + 64);
           n = __ldcg(d.rec_count + list);
-          bepoch += __ldcg(d.bnd_flag + list) ? 1u : 0u;
+          const unsigned int bf = __ldcg(d.bnd_flag + list);
+          bepoch += bf & 1u;
+          heavy = (bf & 2u) != 0;
         }
         unsigned int n_own = n;
         if (d.world > 1) {
@@ -890,7 +954,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         if (tid == 0) {  // the list read this round is consumed; it is next written two rounds from now
           d.rec_count[prev_list] = 0;
           d.bnd_flag[prev_list] = 0;
-          d.st->prog += n;
+          atomicAdd(&d.st->prog, n);
         }
         if (n_own > d.rec_cap) n_own = d.rec_cap;
         if (n == 0) break;  // W already holds every earlier record: both buffers are complete
@@ -902,7 +966,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         prev_n = n_own;
         list = (list + 1) % 3;
         rbuf = wbuf;
-        dense = n > d.sparse_max;
+        dense = n > d.sparse_max || heavy;
       }
       rounds_total += round;
     }
@@ -1016,7 +1080,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       if (tid == 0) atomicAdd(&d.st->prog, n_y);
       if (blockIdx.x == 0) {
         __syncthreads();  // prog += n_y is ordered before P0's atomics on it
-        phase_p0(d, pl);
+        phase_p0(d, pl, s_spc);
       }
     }
     n_pl = sync_and_load(d, d.rec_count + pl);
@@ -1135,10 +1199,9 @@ __global__ void k_export(Dev d, int buf, fr::u256* lb, fr::u256* ub, uint8_t* nv
 __global__ void k_reset_wires(Dev d) {
   uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w > d.V + 3) return;
-  d.F[0][w] = 0;
-  d.F[1][w] = 0;
-  d.B[0][w] = 0;
-  d.B[1][w] = 0;
+  const uint8_t hv = (w <= d.V && d.inv_head[w].x > HEAVY_DEG) ? (uint8_t)WF_HEAVY : (uint8_t)0;
+  d.F[0][w] = hv;
+  d.F[1][w] = hv;
   if (w <= d.V) {
     d.LBR[0][w] = d.r0;
     d.LBR[1][w] = d.r0;
@@ -1184,7 +1247,7 @@ cudaError_t launch_clear_p2_table(const Dev& d, cudaStream_t s) {
 }
 
 int p1_threads() { return P1_THREADS; }
-static size_t solve_max_smem() { return (size_t)P1_MAX_KS * 2 * sizeof(uint4) * P1_THREADS + 28 * 1024; }  // 220 KB
+static size_t solve_max_smem() { return (size_t)P1_MAX_KS * 2 * sizeof(uint4) * P1_THREADS; }  // 192 KB of row records
 int p1_grid_size(int device) {
   static int cached = 0;
   if (cached) return cached;
@@ -1213,9 +1276,8 @@ cudaError_t launch_solve(const Dev& d, unsigned int max_rounds, int grid, cudaSt
   int ks = (int)((rows + nthreads - 1) / nthreads);
   if (ks > P1_MAX_KS) ks = P1_MAX_KS;
   const size_t rec_bytes = (size_t)(ks > 0 ? ks : 1) * 2 * sizeof(uint4) * P1_THREADS;
-  int lc_words = (int)((solve_max_smem() - rec_bytes) / 4);
-  size_t smem = rec_bytes + (size_t)lc_words * 4;
-  void* args[] = {&mr, &ks, &lc_words};
+  size_t smem = rec_bytes;
+  void* args[] = {&mr, &ks};
   return cudaLaunchCooperativeKernel((void*)k_solve, dim3(grid), dim3(P1_THREADS), args, smem, s);
 }
 

@@ -891,7 +891,6 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   // ---- wire state, records, scratch -----------------------------------------------------------
   for (int b = 0; b < 2; ++b) {
     CK(A.alloc(&d.F[b], V + 8));
-    CK(A.alloc(&d.B[b], V + 8));
     CK(A.alloc(&d.LBR[b], V + 1));
     CK(A.alloc(&d.UBR[b], V + 1));
   }
@@ -906,8 +905,8 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(A.alloc(&d.bnd_flag, 8));
   CK(A.alloc(&d.c5sig, N));
   CK(A.alloc(&d.barrier, 128));
-  CK(A.alloc(&d.prof, (size_t)20000 + 40 * 148 * 4));
-  CK(cudaMemsetAsync(d.prof, 0, ((size_t)20000 + 40 * 148 * 4) * sizeof(unsigned long long), s));
+  CK(A.alloc(&d.prof, (size_t)28000 + 40 * 148 * 4));
+  CK(cudaMemsetAsync(d.prof, 0, ((size_t)28000 + 40 * 148 * 4) * sizeof(unsigned long long), s));
   CK(A.alloc(&d.st, 1));
   CK(A.alloc(&d.p2_row, N));
   CK(A.alloc(&R->d_ubits, (V + 63) / 64));

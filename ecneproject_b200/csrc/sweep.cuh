@@ -16,6 +16,83 @@ namespace ecne {
 // One solve runs at a time per process (the API is single-threaded).
 __constant__ Dev c_dev;
 
+// Apply one update {OR bits into F, max lbr into LBR, min ubr into UBR} to buffer `buf`.  The bits of
+// the derived test "bounds == [0,1]" follow from the update's own values, so every part is a
+// commutative, monotone RMW: no ordering between concurrent updates of a wire is needed.
+// want_old = false (replays): fire-and-forget REDs.  want_old = true: returns bit0: the update changed
+// something in `buf`, bit1: a bound moved, bit2: the wire is a heavy one (WF_HEAVY).
+template <bool want_old>
+__device__ __noinline__ uint32_t apply_update_t(int buf, uint32_t w, uint32_t bits, uint32_t lbr, uint32_t ubr) {
+  const Dev& d = c_dev;
+  bool bch = false;
+  if (lbr != ECNE_NO_LB || ubr != ECNE_NO_UB) {
+    bits |= WF_BND;
+    if (ubr != ECNE_NO_UB && ubr <= d.r1) bits |= WF_UB01;
+    if ((ubr != ECNE_NO_UB && ubr < d.r1) || (lbr != ECNE_NO_LB && lbr > d.r0)) bits |= WF_NOT01;
+    if (want_old) {
+      if (lbr != ECNE_NO_LB) bch |= atomicMax(d.LBR[buf] + w, lbr) < lbr;
+      if (ubr != ECNE_NO_UB) bch |= atomicMin(d.UBR[buf] + w, ubr) > ubr;
+    } else {
+      if (lbr != ECNE_NO_LB) atomicMax(d.LBR[buf] + w, lbr);
+      if (ubr != ECNE_NO_UB) atomicMin(d.UBR[buf] + w, ubr);
+    }
+  }
+  uint32_t ret = bch ? 3u : 0u;
+  if (bits) {
+    unsigned int* word = (unsigned int*)(d.F[buf] + (w & ~3u));
+    const unsigned int sh = (w & 3u) * 8;
+    if (want_old) {
+      const uint32_t old = (atomicOr(word, bits << sh) >> sh) & 0xffu;
+      if (bits & ~old) ret |= 1u;
+      if (old & WF_HEAVY) ret |= 4u;
+    } else {
+      atomicOr(word, bits << sh);  // result unused: compiles to RED
+    }
+  }
+  return ret;
+}
+__device__ __forceinline__ void apply_update(const Dev&, int buf, uint32_t w, uint32_t bits, uint32_t lbr,
+                                             uint32_t ubr) {
+  apply_update_t<false>(buf, w, bits, lbr, ubr);
+}
+
+// Apply an update to the write buffer and, when it changed anything there, log it for the other
+// buffer.  A row only calls this when its evaluation against the snapshot wants something the snapshot
+// does not have; the write buffer can already hold it only because another row of the SAME round got
+// there first, so "first writer logs" makes the round's records an exact, duplicate-free list of state
+// changes: "no record in a round" is exactly "fixpoint", and the records are the next round's frontier.
+// One copy of this code in the kernel (the fixpoint kernel is instruction-cache bound in its serial
+// stretches: every inlined copy costs more than the call).
+__device__ __noinline__ void emit_impl(int wbuf, int list, uint32_t w, uint32_t bits, uint32_t lbr, uint32_t ubr) {
+  const Dev& d = c_dev;
+  const uint32_t r = apply_update_t<true>(wbuf, w, bits, lbr, ubr);
+  if (r & 2u) atomicOr(d.bnd_flag + list, 1u);  // a bound moved this round
+  if (!(r & 1u)) return;
+  if (r & 4u) atomicOr(d.bnd_flag + list, 2u);  // a heavy wire changed: the next round is dense
+  // warp-aggregated slot allocation: the lanes that reach this point together take one atomic (a round
+  // that changes 300 k wires would otherwise serialise 300 k RMWs on one L2 address)
+  const unsigned int am = __activemask();
+  const unsigned int lane = threadIdx.x & 31u;
+  const int leader = __ffs((int)am) - 1;
+  unsigned int i = 0;
+  if ((int)lane == leader) i = atomicAdd(d.rec_count + list, (unsigned int)__popc(am));
+  i = __shfl_sync(am, i, leader) + (unsigned int)__popc(am & ((1u << lane) - 1u));
+  if (i < d.rec_cap) {
+    Rec rr;
+    rr.wire = w;
+    rr.bits = (lbr != ECNE_NO_LB || ubr != ECNE_NO_UB) ? (bits | WF_BND) : bits;
+    rr.lbr = lbr;
+    rr.ubr = ubr;
+    d.recs[list][i] = rr;
+  } else {
+    d.st->rec_overflow = 1;
+  }
+}
+__device__ __forceinline__ void emit(const Dev&, int wbuf, int list, uint32_t w, uint32_t bits,
+                                     uint32_t lbr = ECNE_NO_LB, uint32_t ubr = ECNE_NO_UB) {
+  emit_impl(wbuf, list, w, bits, lbr, ubr);
+}
+
 template <int G>
 struct Grp {
   static __device__ __forceinline__ uint32_t lane() { return G == 1 ? 0u : (threadIdx.x & 31u); }
@@ -107,7 +184,7 @@ struct RowCtx {
     const Dev& d = c_dev;
     int i = ov.find(w);
     if (i >= 0) return ov.lb[i] == d.r0 && ov.ub[i] == d.r1;
-    return ld_flag(d.B[rbuf], w) != 0;
+    return is01(ld_flag(d.F[rbuf], w));
   }
   __device__ __forceinline__ bool uniq(uint32_t w) const {
     const Dev& d = c_dev;
@@ -295,11 +372,11 @@ __device__ __noinline__ bool eval_row(const Dev&, int rbuf, int wbuf, int list, 
     for (int o = 0; o < norient; ++o) {
       const uint32_t nk = o == 0 ? a.w2 : a.w5;
       bool ok = true;
-      scan_terms<G, SCAN_U(G)>(d, d.B[rbuf], s2, s3, lane, [&](uint32_t w, uint32_t b) {
+      scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
         if (w == nk) return;
         const int oi = c.ov.find(w);
-        const bool is01 = oi >= 0 ? (c.ov.lb[oi] == d.r0 && c.ov.ub[oi] == d.r1) : (b != 0);
-        if (!is01) ok = false;
+        const bool bit = oi >= 0 ? (c.ov.lb[oi] == d.r0 && c.ov.ub[oi] == d.r1) : is01(f);
+        if (!bit) ok = false;
       });
       ok = Grp<G>::all(ok);
       if (!ok) continue;
