@@ -8,12 +8,19 @@ One step = one full run of the hot path (SolveConstraintsSymbolic) on the worklo
 `ecdsa.r1cs + trusted secp256k1.r1cs` (BASELINE.json configs[4]; 1 092 639 rows -> 694 264 after
 abstraction; the configuration the `metric` is quoted on — it fits one GPU).
 
-  value   constraint-evals/s (rows visited by sweep/phase kernels / time), inputs resident in HBM
-          (ecne_upload once, ecne_solve_resident per step).  L2 is flushed between timed steps.
+  value   constraint-evals/s (rows visited by the solve kernel / time), inputs resident in HBM
+          (ecne_upload once, ecne_solve_resident per step), timed with CUDA events on the engine's own
+          stream (ecne_result.ms_device: reset + the persistent solve kernel + verdict + D2H of the
+          bitmaps), max over ranks.  L2 is flushed between timed steps.
   e2e     the same metric through the reference-facing C-ABI call ecne_solve() with HOST buffers:
-          H2D of the CSR from pinned memory + classify + all rounds + D2H of the bitmaps, per step.
-  roofline  the sweep kernel (k_p1_loop): algorithmic bytes of the compact sweep layout
-          (17 B/row + 5 B/term) x Jacobi rounds / CUDA-event time of the launches.
+          H2D of the CSR from pinned memory + classify + the solve + D2H of the bitmaps, per step.
+  roofline  the solve kernel (k_solve, one launch per step): algorithmic bytes of the compact sweep
+          layout (32 B row record + 1 B per term) x rows it visited / its CUDA-event
+          time.  roofline.dense_rounds is the same for the dense Jacobi rounds alone (in-kernel
+          clock64), the only part of the solve that streams rows.
+  N > 1   the rows are sharded by stored-term balance (ecne_shard_rows), wire state is replicated and
+          the per-round update records are exchanged over NVLink inside the solve kernel: the SAME
+          problem is split, so "scaling" is "strong".
   cpu_baseline  oracle/ (a single-threaded C++ port of the reference's Julia) on the same workload,
           timed on this box's host, rank 0, N=1 only.
 """
@@ -200,9 +207,16 @@ def main():
         return 1
     torch.cuda.set_device(local)
     dist = None
+    lib = _abi.engine_lib()
     if world > 1:
         import torch.distributed as dist
+        from ecneproject_b200 import dist as edist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        edist.init_from_torch(local)   # ecne_init + the engine's own communicator / peer mappings
+    else:
+        st = lib.ecne_init(local)
+        if st != 0:
+            raise RuntimeError(lib.ecne_last_error().decode())
 
     def barrier():
         if dist is not None:
@@ -210,10 +224,6 @@ def main():
         torch.cuda.synchronize()
 
     reduced, specials, main = load_problem()
-    lib = _abi.engine_lib()
-    st = lib.ecne_init(local)
-    if st != 0:
-        raise RuntimeError(lib.ecne_last_error().decode())
 
     # ---- pinned host copies of the inputs for the e2e leg ---------------------------------------
     def pinned(a):
@@ -255,34 +265,38 @@ def main():
 
     for _ in range(args.warmup):
         l2_flush()
+        barrier()
         step_resident()
     sampler = ClockSampler(local)
     sampler.start()
-    t_total = 0.0
+    t_wall = t_dev = 0.0
     sweep_ms = solve_ms = 0.0
     launches = 0
-    evals = rounds = 0
+    dense_cycles = dense_evals = dense_rounds = 0
     for _ in range(args.steps):
         l2_flush()
         barrier()
         t0 = time.perf_counter()
         c = step_resident()
         torch.cuda.synchronize()
-        t_total += time.perf_counter() - t0
+        t_wall += time.perf_counter() - t0
+        t_dev += c.ms_device          # CUDA events on the engine's stream, around the whole call
         sweep_ms += c.ms_sweep
         solve_ms += c.ms_solve
         launches += int(c.sweep_launches)
         evals, rounds, outer = int(c.constraint_evals), int(c.inner_rounds), int(c.outer_rounds)
         rule_evals = int(c.rule_evals)
+        dense_cycles += int(c.dense_cycles)
+        dense_evals, dense_rounds = int(c.dense_evals), int(c.dense_rounds)
     barrier()
     clocks = sampler.stop()
     verdict = bool(res.c.verdict)
     n_unique = int(res.c.n_unique)
-    nnz_nz = None
 
     # ---- e2e leg: host buffers in, host buffers out -------------------------------------------------
     res2 = api.SolveResult(main.n_vars, full_state=False)
     for _ in range(2):
+        barrier()
         lib.ecne_solve(C.byref(ph.c), C.byref(res2.c))
     t_e2e = 0.0
     e2e_steps = max(3, min(args.steps, 10))
@@ -301,16 +315,20 @@ def main():
     assert res2.unique_bits.tobytes() == res.unique_bits.tobytes()
     lib.ecne_free_resident(handle)
 
-    ms_step = 1e3 * t_total / args.steps
-    # max over ranks
-    if dist is not None:
-        t = torch.tensor([ms_step, e2e_ms], device="cuda", dtype=torch.float64)
+    ms_step = t_dev / args.steps
+    ms_wall = 1e3 * t_wall / args.steps
+    total_evals = evals
+    if dist is not None:   # max over ranks of the times, sum over ranks of the rows each rank visited
+        t = torch.tensor([ms_step, e2e_ms, ms_wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_ms = float(t[0]), float(t[1])
-    value = world * evals / (ms_step / 1e3)
-    e2e_value = world * evals / (e2e_ms / 1e3)
+        ms_step, e2e_ms, ms_wall = float(t[0]), float(t[1]), float(t[2])
+        e = torch.tensor([evals], device="cuda", dtype=torch.int64)
+        dist.all_reduce(e, op=dist.ReduceOp.SUM)
+        total_evals = int(e[0])
+    value = total_evals / (ms_step / 1e3)
+    e2e_value = total_evals / (e2e_ms / 1e3)
 
-    # ---- roofline of the sweep kernel ---------------------------------------------------------------
+    # ---- roofline of the solve kernel ---------------------------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -321,14 +339,20 @@ def main():
     nnz_nonzero = int(np.count_nonzero(reduced.coef.any(axis=1)))
     b_eval = algorithmic_bytes_per_eval(reduced.n_rows, nnz_nonzero)
     sweep_ms_step = sweep_ms / args.steps
-    sweep_evals = evals - 3 * reduced.n_rows * outer  # rows swept by k_p1_loop (the rest: P3/P4 kernels + P2 tail)
-    achieved = b_eval * sweep_evals / (sweep_ms_step / 1e3) / 1e9 if sweep_ms_step > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_p1_loop (persistent Jacobi sweep)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "bytes_per_eval": b_eval, "evals_in_kernel_per_step": sweep_evals,
-                "sweeps_per_step": rounds, "kernel_ms_per_step": sweep_ms_step, "launches_per_step": outer,
-                "note": "the named workload is round-latency bound: 161 dependent rounds, 130 of them change "
-                        "a single wire (DESIGN.md §5); see roofline_tiled for the bandwidth regime"}
+    achieved = b_eval * evals / (sweep_ms_step / 1e3) / 1e9 if sweep_ms_step > 0 else 0.0
+    sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    dense_ms = dense_cycles / args.steps / (sm_mhz * 1e3) if sm_mhz else 0.0
+    dense_ach = b_eval * dense_evals / (dense_ms / 1e3) / 1e9 if dense_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_solve (the whole fixpoint, one persistent cooperative launch)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "bytes_per_eval": b_eval, "evals_in_kernel_per_step": evals,
+                "jacobi_rounds_per_step": rounds, "kernel_ms_per_step": sweep_ms_step, "launches_per_step": 1,
+                "dense_rounds": {"rounds": dense_rounds, "evals": dense_evals, "ms": dense_ms,
+                                 "achieved": dense_ach, "frac": dense_ach / peak,
+                                 "how": "clock64 in block 0 around the dense rounds / SM clock sampled by nvidia-smi"},
+                "note": "the named workload is a dependency chain: %d dependent Jacobi rounds, all but %d of them "
+                        "driven by <= 100 update records; the kernel is bound by the latency of a round, not by "
+                        "HBM (DESIGN.md §5); see roofline_tiled for the bandwidth regime" % (rounds, dense_rounds)}
 
     # ---- the same kernel on a tiled copy whose working set does not fit the 126 MB L2 ---------------
     tiled = None
@@ -355,19 +379,22 @@ def main():
             tso += res_t.c.ms_solve
         lib.ecne_free_resident(h_t)
         ev_t = int(res_t.c.constraint_evals)
-        sw_ev_t = ev_t - 3 * t.n_rows * int(res_t.c.outer_rounds)
-        ach_t = b_eval * sw_ev_t / (tsw / reps / 1e3) / 1e9
+        ach_t = b_eval * ev_t / (tsw / reps / 1e3) / 1e9
+        d_ms_t = int(res_t.c.dense_cycles) / (sm_mhz * 1e3) if sm_mhz else 0.0
+        d_ach_t = b_eval * int(res_t.c.dense_evals) / (d_ms_t / 1e3) / 1e9 if d_ms_t > 0 else 0.0
         ok_t = int(res_t.c.n_unique) == 1 + K * (n_unique - 1) and bool(res_t.c.verdict) == verdict
         tiled = {"tile": K, "rows": t.n_rows, "row_record_bytes": 32 * t.n_rows, "evals_per_step": ev_t,
                  "value": ev_t / (tso / reps / 1e3), "unit": UNIT, "ms_solve": tso / reps,
                  "kernel_ms_per_step": tsw / reps, "achieved": ach_t, "peak": peak, "frac": ach_t / peak,
+                 "dense_rounds": {"rounds": int(res_t.c.dense_rounds), "evals": int(res_t.c.dense_evals),
+                                  "ms": d_ms_t, "achieved": d_ach_t, "frac": d_ach_t / peak},
                  "bitmap_is_base_repeated": ok_t}
         del ph_t, res_t, t
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
         "dtype": "u256 (4x64-bit limbs, BN254 scalar field; sweep works on u8/u32 state)",
         "data": "real circuit (reference fixture ecdsa.r1cs), no synthetic data needed",
         "config": {"workload": WORKLOAD_NAME, "rows": reduced.n_rows, "rows_before_abstraction": main.n_rows,
@@ -375,11 +402,16 @@ def main():
                    "outer_rounds": outer, "jacobi_rounds": rounds, "verdict": verdict, "n_unique": n_unique,
                    "rule_evals_per_step": rule_evals,
                    "l2": "flushed between timed steps (256 MB fill)",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (row-range sharding: see DESIGN.md §7)",
-                   "device_ms_solve_per_step": solve_ms / args.steps},
+                   "parallelism": "1 GPU" if world == 1 else
+                   f"{world} GPUs: rows sharded by stored-term balance, wire state replicated, per-round update "
+                   "records exchanged over NVLink inside the solve kernel (DESIGN.md §7)",
+                   "timing": "CUDA events on the engine's stream around each whole call (ecne_result.ms_device), max over ranks",
+                   "wall_ms_per_step": ms_wall, "device_ms_solve_per_step": solve_ms / args.steps,
+                   "seconds_to_verdict_resident": ms_wall / 1e3},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "ms_h2d": h2d_ms,
-                "ms_classify": classify_ms},
+                "ms_classify": classify_ms, "seconds_to_verdict": e2e_ms / 1e3,
+                "timing": "host clock around ecne_solve() (pinned host buffers in, host bitmaps out), max over ranks"},
         "gpu_launches": launches,
         "roofline": roofline,
         "clocks": clocks,

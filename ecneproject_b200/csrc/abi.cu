@@ -304,7 +304,8 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
                 g < 1000 ? pr[24000 + 4 * g + 2] : 0, g < 1000 ? pr[24000 + 4 * g + 3] : 0);
     }
   }
-  const uint64_t launches = 1;
+  // kernels of one call: reset (wires, known), the persistent solve, verdict (pack, targets)
+  const uint64_t launches = 1 + 1 + (d.n_known ? 1 : 0) + 1 + (d.n_targets ? 1 : 0);
   // the three whole-set sweeps of every outer round visit: P2 the rows that can still fire (counted by
   // the kernel), P3 / P4 the rows with the ABZ / IsZero shape
   const unsigned long long rounds_total = R.h_status->rounds, evals_total = R.h_status->evals,

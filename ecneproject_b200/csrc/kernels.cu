@@ -975,6 +975,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     {
       const uint8_t* F = d.F[0];
       if (d.world == 1) {
+        evals += (unsigned int)__popcll(live);  // one visit of the linear-system sweep per row (:1359)
         for (unsigned long long m = live; m;) {
           const int k = __ffsll((long long)m) - 1;
           m &= m - 1;
@@ -1021,7 +1022,10 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         }
       } else {  // sharded: every rank scans every row (same candidates everywhere)
         for (uint32_t row = tid; row < d.N; row += nthreads)
-          if (!(d.rflags[row] & RF_LONG) && !(d.solved[row] & 1)) p2_scan_row<1>(d, 0, pl, row);
+          if (!(d.rflags[row] & RF_LONG) && !(d.solved[row] & 1)) {
+            p2_scan_row<1>(d, 0, pl, row);
+            if (row >= d.row_lo && row < d.row_hi) evals += 1;  // replicated work is counted once
+          }
       }
       for (uint32_t i = blockIdx.x + warp_in_block * gridDim.x; i < d.n_long; i += warps_per_block * gridDim.x) {
         const uint32_t row = d.long_rows[i];

@@ -98,7 +98,7 @@ typedef struct ecne_result {
   uint64_t outer_rounds;        /* iterations of the `while true` at :706                    */
   uint64_t inner_rounds;        /* Jacobi rounds of the single-row rule sweep                */
   uint64_t constraint_evals;    /* rows visited by sweep/phase kernels        */
-  uint64_t sweep_launches;      /* launches of the persistent solve kernel (1)               */
+  uint64_t sweep_launches;      /* kernels launched by this call (reset, ONE solve, verdict) */
   double ms_h2d, ms_classify, ms_solve, ms_d2h, ms_exchange, ms_total;
   double ms_sweep;              /* device time inside the single-row sweep kernel only       */
   uint64_t rule_evals;          /* of constraint_evals: rows whose rule set was run in full       */
