@@ -419,6 +419,8 @@ __device__ __forceinline__ fr::u256 mag_of(const fr::u256& c, bool flipped) {
   return x;
 }
 
+#define LAYOUT_LONG_MIN 64u    // C segments longer than this are ranked by a block in shared memory
+#define LAYOUT_LONG_MAX 4096u  // ... as long as they fit there (45 B per term, padded to a power of two)
 // Scatter the non-zero terms into the sweep layout.  C terms of linear rows are placed by their
 // rank in (|fold(coef)|, wire) order so that Case 5 (:1265) walks them sorted.
 __global__ void k_layout(Raw r, const uint32_t* keep, const uint32_t* pos, const uint32_t* seg_nz,
@@ -433,6 +435,8 @@ __global__ void k_layout(Raw r, const uint32_t* keep, const uint32_t* pos, const
   uint32_t w = r.col[t];
   uint32_t rf = rflags[row];
   if (form == 2 && (rf & RF_LINEAR)) {
+    const uint64_t seg_len = r.seg[s + 1] - r.seg[s];
+    if (seg_len > LAYOUT_LONG_MIN && seg_len <= LAYOUT_LONG_MAX) return;  // k_layout_long ranks these in smem
     bool fl = (rf & RF_C3_FLIP) != 0;
     fr::u256 m = mag_of(c, fl);
     uint32_t rank = 0;
@@ -446,6 +450,73 @@ __global__ void k_layout(Raw r, const uint32_t* keep, const uint32_t* pos, const
   col[dst] = w;
   coef[dst] = c;
   nontriv[w] = 1;
+}
+// The C segment of one long linear row: magnitudes and wires go to shared memory once and a bitonic
+// network sorts an index permutation by (dropped?, |fold(coef)|, wire) — the kept terms come out in
+// exactly the order k_layout's rank computation gives, in O(n log^2 n) on-chip compares.
+__device__ __forceinline__ bool layout_less(const fr::u256* mag, const uint32_t* wv, const uint8_t* kp, uint32_t n,
+                                            uint32_t a, uint32_t b) {
+  const bool ka = a < n && kp[a], kb = b < n && kp[b];
+  if (ka != kb) return ka;  // kept terms first; padding and dropped zeros last
+  if (!ka) return a < b;
+  const int cm = fr::cmp(mag[a], mag[b]);
+  if (cm != 0) return cm < 0;
+  if (wv[a] != wv[b]) return wv[a] < wv[b];
+  return a < b;
+}
+__global__ void k_layout_long(Raw r, const uint32_t* keep, const uint32_t* seg_nz, const uint32_t* rflags,
+                              const uint32_t* long_rows, uint32_t n_long, uint32_t* col, fr::u256* coef,
+                              uint8_t* nontriv) {
+  extern __shared__ unsigned long long sm_u64[];
+  if (blockIdx.x >= n_long) return;
+  const uint32_t row = long_rows[blockIdx.x];
+  const uint32_t rf = rflags[row];
+  if (!(rf & RF_LINEAR)) return;
+  const uint32_t s = 3 * row + 2;
+  const uint64_t b = r.seg[s], e = r.seg[s + 1];
+  const uint32_t n = (uint32_t)(e - b);
+  if (n <= LAYOUT_LONG_MIN || n > LAYOUT_LONG_MAX) return;
+  uint32_t np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  fr::u256* mag = reinterpret_cast<fr::u256*>(sm_u64);
+  uint32_t* wv = reinterpret_cast<uint32_t*>(mag + n);
+  uint32_t* idx = wv + n;
+  uint8_t* kp = reinterpret_cast<uint8_t*>(idx + np2);
+  const bool fl = (rf & RF_C3_FLIP) != 0;
+  for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) {
+    idx[i] = i;
+    if (i < n) {
+      mag[i] = mag_of(r.coef[b + i], fl);
+      wv[i] = r.col[b + i];
+      kp[i] = (uint8_t)keep[b + i];
+    }
+  }
+  __syncthreads();
+  for (uint32_t k = 2; k <= np2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t a = idx[i], c = idx[ixj];
+          const bool up = (i & k) == 0;
+          const bool a_after_c = layout_less(mag, wv, kp, n, c, a);
+          if (a_after_c == up) {
+            idx[i] = c;
+            idx[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t p = threadIdx.x; p < n; p += blockDim.x) {
+    const uint32_t el = idx[p];
+    if (el >= n || !kp[el]) continue;
+    const uint32_t dst = seg_nz[s] + p;  // kept terms occupy the first positions of the sorted order
+    col[dst] = wv[el];
+    coef[dst] = r.coef[b + el];
+    nontriv[wv[el]] = 1;
+  }
 }
 // 32-byte sweep records: flags + up to 6 inline wires (A u B first, then C)
 __global__ void k_rowrec(uint32_t N, const uint32_t* seg, const uint32_t* col, uint32_t* rflags, RowRec* rec) {
@@ -496,6 +567,7 @@ __global__ void k_phase_rows(uint32_t N, const uint32_t* rflags, uint32_t* p3, u
   if (rf & RF_P3) p3[atomicAdd(n + 0, 1u)] = row;
   if (rf & RF_P4) p4[atomicAdd(n + 1, 1u)] = row;
 }
+#define INV_LONG_MIN 32u
 // wire -> rows index over the non-zero terms (the constant wire 1 never changes state: left out)
 __global__ void k_inv_count(uint32_t nnz, const uint32_t* col, uint32_t* cnt) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -506,6 +578,7 @@ __global__ void k_inv_fill(uint32_t N, const uint32_t* seg, const uint32_t* col,
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= N) return;
   const uint32_t s0 = seg[3 * row], s3 = seg[3 * row + 3];
+  if (s3 - s0 > INV_LONG_MIN) return;  // k_inv_fill_long
   for (uint32_t t = s0; t < s3; ++t) {
     const uint32_t w = col[t];
     if (w == 1) continue;
@@ -513,6 +586,19 @@ __global__ void k_inv_fill(uint32_t N, const uint32_t* seg, const uint32_t* col,
     if (s3 - s0 <= 8)
       for (uint32_t u = s0; u < t; ++u) dup |= col[u] == w;
     if (dup) continue;
+    inv_row[inv_ptr[w] + atomicAdd(cursor + w, 1u)] = row;
+  }
+}
+// rows with many terms: one block per row, threads striding its terms
+__global__ void k_inv_fill_long(const uint32_t* long_rows, uint32_t n_long, const uint32_t* seg, const uint32_t* col,
+                                const uint32_t* inv_ptr, uint32_t* cursor, uint32_t* inv_row) {
+  if (blockIdx.x >= n_long) return;
+  const uint32_t row = long_rows[blockIdx.x];
+  const uint32_t s0 = seg[3 * row], s3 = seg[3 * row + 3];
+  if (s3 - s0 <= INV_LONG_MIN) return;
+  for (uint32_t t = s0 + threadIdx.x; t < s3; t += blockDim.x) {
+    const uint32_t w = col[t];
+    if (w == 1) continue;
     inv_row[inv_ptr[w] + atomicAdd(cursor + w, 1u)] = row;
   }
 }
@@ -570,6 +656,13 @@ __global__ void k_fill_ranks(uint32_t N, const uint32_t* rflags, RowAux* aux, co
     aux[row].rank_b = rank_of[l - 1];  // 2^(l-1) - 1
   }
 }
+
+struct ValLess {  // order of the candidate bound values (ties: any order, equal values share a rank)
+  const fr::u256* v;
+  __device__ __forceinline__ bool operator()(const uint32_t& a, const uint32_t& b) const {
+    return fr::cmp(v[a], v[b]) < 0;
+  }
+};
 
 template <class T>
 static cudaError_t h2d(T* dst, const T* src, size_t n, cudaStream_t s) {
@@ -790,11 +883,13 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(tmp.alloc(&d_k2, nc));
   CK(A.alloc(&d_table, nc));
   k_iota<<<nb(nc, 256), 256, 0, s>>>(d_idx, nc);
-  for (int limb = 0; limb < 4; ++limb) {  // LSD radix sort, one stable 64-bit pass per limb
-    k_limb<<<nb(nc, 256), 256, 0, s>>>(d_tvals, d_idx, nc, limb, d_k1);
-    size_t b = cub_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(d_cub, b, d_k1, d_k2, d_idx, d_idx2, (int)nc, 0, 64, s));
-    std::swap(d_idx, d_idx2);
+  {  // one merge sort of the index permutation with a 256-bit comparator (a handful of launches; an LSD
+     // radix sort over four 64-bit limbs costs 40 launch-bound passes for these ~10^5 values)
+    size_t need = 0;
+    cub::DeviceMergeSort::SortKeys((void*)nullptr, need, d_idx, (int)nc, ValLess{d_tvals}, s);
+    void* d_ms = d_cub;
+    if (need > cub_bytes) CK(tmp.alloc((uint8_t**)&d_ms, need));
+    CK(cub::DeviceMergeSort::SortKeys(d_ms, need, d_idx, (int)nc, ValLess{d_tvals}, s));
   }
   k_distinct<<<nb(nc, 256), 256, 0, s>>>(d_tvals, d_idx, nc, d_flag);
   {
@@ -822,12 +917,19 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(tmp.alloc(&d_nlong, 1));
   CK(cudaMemsetAsync(d_nontriv, 0, V + 4, s));
   CK(cudaMemsetAsync(d_nlong, 0, sizeof(unsigned int), s));
+  if (cnt.n_long) k_long_rows<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_rflags, d_long, d_nlong);
   if (nnz)
     k_layout<<<nb(nnz, 256), 256, 0, s>>>(raw, d_keep, d_pos, d_segnz, d_rflags, d_col, d_coef, d_nontriv);
+  if (cnt.n_long) {
+    // shared memory for the longest segment the kernel accepts (both kernels apply the same length test)
+    const size_t smem = (size_t)LAYOUT_LONG_MAX * (sizeof(fr::u256) + 2 * sizeof(uint32_t) + 1) + 64;  // 168 KB
+    CK(cudaFuncSetAttribute(k_layout_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_layout_long<<<cnt.n_long, 1024, smem, s>>>(raw, d_keep, d_segnz, d_rflags, d_long, cnt.n_long, d_col, d_coef,
+                                                 d_nontriv);
+  }
   if (n_sp_in) k_mark<<<nb(n_sp_in, 256), 256, 0, s>>>(d_sp_in, (uint32_t)n_sp_in, d_nontriv);
   if (n_sp_out) k_mark<<<nb(n_sp_out, 256), 256, 0, s>>>(d_sp_out, (uint32_t)n_sp_out, d_nontriv);
   if (p->n_targets) k_mark<<<nb(p->n_targets, 256), 256, 0, s>>>(d_targets, (uint32_t)p->n_targets, d_nontriv);
-  if (cnt.n_long) k_long_rows<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_rflags, d_long, d_nlong);
   RowRec* d_rec;
   CK(A.alloc(&d_rec, N));
   if (N) k_rowrec<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_segnz, d_col, d_rflags, d_rec);
@@ -864,6 +966,8 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(cudaMemsetAsync(d_inv_cur, 0, (V + 3) * sizeof(uint32_t), s));
   CK(cudaMemsetAsync(d_inv_row, 0xff, ((size_t)nnz_nz + 1) * sizeof(uint32_t), s));  // 0xffffffff = unused slot
   if (N) k_inv_fill<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_segnz, d_col, d_inv_ptr, d_inv_cur, d_inv_row);
+  if (cnt.n_long)
+    k_inv_fill_long<<<cnt.n_long, 256, 0, s>>>(d_long, cnt.n_long, d_segnz, d_col, d_inv_ptr, d_inv_cur, d_inv_row);
   uint4* d_inv_head;
   CK(A.alloc(&d_inv_head, V + 2));
   k_inv_head<<<nb(V + 2, 256), 256, 0, s>>>((uint32_t)(V + 2), d_inv_ptr, d_inv_cur, d_inv_row, d_inv_head);
