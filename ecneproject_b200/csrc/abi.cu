@@ -528,6 +528,8 @@ __global__ void k_fr_batch(int op, uint64_t n, const fr::u256* a, const fr::u256
     case 3: r = fr::is_zero(x) ? x : fr::from_mont(fr::inv_mont(fr::to_mont(x))); break;
     case 4: r = fr::neg(x); break;
     case 5: r = fr::neg_div(x, y); break;  // divexact(-x, y)
+    case 6: r = fr::make_u256(fr::divides(y, x) ? 1 : 0, 0, 0, 0); break;  // plain integers: y | x  (y != 0)
+    case 7: r = fr::make_u256((uint64_t)(fr::cmp_mul(x, y, fr::modulus()) + 1), 0, 0, 0); break;  // sign(x*y - p) + 1
     default: r = x;
   }
   out[i] = r;

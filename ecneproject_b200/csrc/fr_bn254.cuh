@@ -255,6 +255,18 @@ __host__ __device__ __forceinline__ u256 shl1(const u256& a) {
   return make_u256(a.v[0] << 1, (a.v[1] << 1) | (a.v[0] >> 63), (a.v[2] << 1) | (a.v[1] >> 63),
                    (a.v[3] << 1) | (a.v[2] >> 63));
 }
+// a >> k, k in [0, 256)
+__host__ __device__ __forceinline__ u256 shr(const u256& a, int k) {
+  const int w = k >> 6, b = k & 63;
+  u256 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint64_t lo = (i + w < 4) ? a.v[(i + w) & 3] : 0ULL;
+    const uint64_t hi = (i + w + 1 < 4) ? a.v[(i + w + 1) & 3] : 0ULL;
+    r.v[i] = b ? ((lo >> b) | (hi << (64 - b))) : lo;
+  }
+  return r;
+}
 // 2^k - 1 as an integer, k in [0, 256)
 __host__ __device__ __forceinline__ u256 pow2m1(int k) {
   u256 r;
@@ -279,8 +291,15 @@ __host__ __device__ inline bool divides(const u256& b, const u256& a) {
     u256 m = pow2m1(lb - 1);
     return ((a.v[0] & m.v[0]) | (a.v[1] & m.v[1]) | (a.v[2] & m.v[2]) | (a.v[3] & m.v[3])) == 0;
   }
-  u256 r = make_u256(0, 0, 0, 0);
-  for (int i = la - 1; i >= 0; --i) {
+  // restoring division, starting from the top lb bits of a: la - lb + 1 compare-subtract steps instead of
+  // la (Case 5 divides neighbouring magnitudes of a sorted chain: their lengths are close)
+  const int k = la - lb;
+  u256 r = shr(a, k);
+  {
+    u256 t;
+    if (!sub_cc(t, r, b)) r = t;
+  }
+  for (int i = k - 1; i >= 0; --i) {
     uint64_t top = r.v[3] >> 63;
     r = shl1(r);
     r.v[0] |= (a.v[i >> 6] >> (i & 63)) & 1;

@@ -647,6 +647,130 @@ __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, un
   return ev;
 }
 
+// Rounds whose frontier is at most 32 records are run by WARP 0 of block 0 alone (most of ecdsa's rounds
+// change one or six wires): the (record, listed row) pairs are dealt out one per lane, a long row among
+// them is then evaluated by the whole warp, and the round boundary is __syncwarp + release fence + acquire load — no
+// block barrier, no shared-memory queues.  Runs rounds until the frontier is empty or outgrows it and
+// leaves the state of the LAST round it ran in `st` (shared memory), exactly as a block-solo round would.
+#define WARP_SOLO_MAX 32u
+struct SoloState {
+  unsigned int n, list, rbuf, round, bepoch, gr, hv, prev_list;
+};
+__device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int prev_n, unsigned int max_rounds,
+                                       unsigned long long* evals_io) {
+  const Dev& d = c_dev;
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned int n = prev_n, list = st->list, prev_list = st->prev_list, round = st->round, bepoch = st->bepoch,
+               gr = st->gr, hv = 0;
+  int rbuf = (int)st->rbuf;
+  unsigned long long ev = 0;
+  while (true) {
+    gr += 1;
+    const int wbuf = rbuf ^ 1;
+    // lane i holds record i and the head of its wire's row list; the (record, listed row) pairs are then
+    // dealt out one per lane, so every row of the frontier is evaluated in the same step
+    const bool have = lane < n;
+    Rec r;
+    r.wire = 1;
+    r.bits = 0;
+    r.lbr = ECNE_NO_LB;
+    r.ubr = ECNE_NO_UB;
+    uint4 hd = make_uint4(0, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (have) {
+      r = ld_peer_rec(d.recs[prev_list] + lane);
+      hd = __ldcg(reinterpret_cast<const uint4*>(d.inv_head) + r.wire);
+    }
+    unsigned int incl = hd.x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned int excl = incl - hd.x;
+    for (unsigned int base = 0; base < total; base += 32) {
+      const unsigned int p = base + lane;
+      int j = 0;  // the record whose range [excl, incl) holds pair p
+#pragma unroll
+      for (int k = 0; k < 31; ++k) {
+        const unsigned int e = __shfl_sync(0xffffffffu, incl, k);
+        if (p >= e) j = k + 1;
+      }
+      const uint32_t wj = __shfl_sync(0xffffffffu, r.wire, j);
+      const uint32_t hy = __shfl_sync(0xffffffffu, hd.y, j), hz = __shfl_sync(0xffffffffu, hd.z, j),
+                     hw = __shfl_sync(0xffffffffu, hd.w, j);
+      const unsigned int q = p - __shfl_sync(0xffffffffu, excl, j);
+      uint32_t row = 0xffffffffu;
+      bool is_long = false;
+      if (p < total) {
+        if (q == 0) row = hy;
+        else if (q == 1) row = hz;
+        else if (q == 2) row = hw;
+        else row = d.inv_row[d.inv_ptr[wj] + q];
+        if (row != 0xffffffffu && row >= d.row_lo && row < d.row_hi) {
+          const uint4* rp = reinterpret_cast<const uint4*>(d.rec + row);
+          const uint4 q0v = __ldg(rp), q1v = __ldg(rp + 1);
+          const uint32_t latched = __ldcg(d.solved + row);
+          InlineRow ir;
+          unpack_row(q0v, q1v, ir);
+          if (ir.rf & RF_LONG) {
+            const uint32_t li = ir.c[0];
+            is_long = !__ldcg(d.long_done + li) && atomicExch(d.long_stamp + li, gr) != gr;
+          } else if (!(latched & 1)) {
+            uint32_t f[ROWREC_INLINE];
+            gather_row(d.F[rbuf], ir, f);
+            ev += 1;
+            eval_inline(d, rbuf, wbuf, (int)list, row, ir, f, bepoch);
+          }
+        }
+      }
+      unsigned int m = __ballot_sync(0xffffffffu, is_long);
+      while (m) {
+        const int src = __ffs((int)m) - 1;
+        m &= m - 1;
+        const uint32_t lrow = __shfl_sync(0xffffffffu, row, src);
+        const bool done = eval_row<32>(d, rbuf, wbuf, (int)list, lrow, bepoch);
+        if (lane == 0) {
+          ev += 1;
+          if (done) d.long_done[d.rec[lrow].c[0]] = 1;
+        }
+      }
+    }
+    if (have) apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);  // the replay
+    __syncwarp();
+    unsigned int cnt = 0, bf = 0;
+    if (lane == 0) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cnt) : "l"(d.rec_count + list) : "memory");
+      asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(bf) : "l"(d.bnd_flag + list) : "memory");
+      d.rec_count[prev_list] = 0;  // consumed; next written two rounds from now
+      d.bnd_flag[prev_list] = 0;
+      atomicAdd(&d.st->prog, cnt);
+    }
+    cnt = __shfl_sync(0xffffffffu, cnt, 0);
+    bf = __shfl_sync(0xffffffffu, bf, 0);
+    bepoch += bf & 1u;
+    hv = bf & 2u;
+    round += 1;
+    n = cnt;
+    if (n == 0 || n > WARP_SOLO_MAX || hv || round >= max_rounds) break;
+    prev_list = list;
+    list = (list + 1) % 3;
+    rbuf ^= 1;
+  }
+  *evals_io += ev;
+  if (lane == 0) {
+    st->n = n;
+    st->list = list;
+    st->rbuf = (unsigned int)rbuf;
+    st->round = round;
+    st->bepoch = bepoch;
+    st->gr = gr;
+    st->hv = hv;
+    st->prev_list = prev_list;
+  }
+}
+
 // The whole fixpoint (:706-1556) as ONE persistent cooperative launch (148 blocks x 1024 threads):
 //
 //   P0 -> [Jacobi rounds of the single-row rules until no record] -> P2 -> P3 -> P4 -> repeat while
@@ -664,6 +788,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
   const Dev& d = c_dev;
   extern __shared__ uint4 sm_rec[];  // sm_rec[(2*k + h) * blockDim + thread]: half h of the thread's k-th record
   __shared__ unsigned int s_solo[2];
+  __shared__ SoloState s_ws;
   unsigned int epoch = 0;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
@@ -729,6 +854,46 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           unsigned int n = 0;
           if (blockIdx.x == 0) {
             while (true) {
+              if (prev_n <= WARP_SOLO_MAX) {
+                // one or two records: warp 0 chases them alone, for as many rounds as that stays so
+                if (threadIdx.x == 0) {
+                  s_ws.list = list;
+                  s_ws.prev_list = prev_list;
+                  s_ws.rbuf = (unsigned int)rbuf;
+                  s_ws.round = round;
+                  s_ws.bepoch = bepoch;
+                  s_ws.gr = gr;
+                }
+                __syncthreads();
+                if (warp_in_block == 0) {
+                  unsigned long long ev = 0;
+                  warp_solo(d, &s_ws, prev_n, max_rounds, &ev);
+                  evals += ev;
+                  ruleevals += ev;
+                }
+                __syncthreads();
+                n = s_ws.n;
+                list = s_ws.list;
+                rbuf = (int)s_ws.rbuf;
+                round = s_ws.round;
+                bepoch = s_ws.bepoch;
+                gr = s_ws.gr;
+                s_solo[1] = s_ws.hv;
+#ifdef ECNE_PROFILE
+                if (threadIdx.x == 0) {
+                  long long t_ = clock64();
+                  pf[7] += (unsigned long long)(t_ - tp);
+                  tp = t_;
+                }
+#endif
+                __syncthreads();
+                if (n == 0 || n > SOLO_MAX || (s_solo[1] & 2u) || round >= max_rounds) break;
+                prev_list = list;
+                prev_n = n;
+                list = (list + 1) % 3;
+                rbuf ^= 1;
+                continue;
+              }
               gr += 1;
 #ifdef ECNE_PROFILE
               long long z0 = clock64(), z1 = 0, z2 = 0, z3 = 0, z4 = 0;
@@ -824,20 +989,6 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         long long tc0 = 0;
         if (dense && tid == 0) tc0 = clock64();
         if (dense) {
-          // (a) long rows first (their latency overlaps the rest): block b owns long rows b, b+grid, ...
-          for (uint32_t i = blockIdx.x + warp_in_block * gridDim.x; i < d.n_long; i += warps_per_block * gridDim.x) {
-            if (d.long_done[i]) continue;
-            const uint32_t row = d.long_rows[i];
-            if (row >= d.row_lo && row < d.row_hi) {
-              const bool done = eval_row<32>(d, rbuf, wbuf, (int)list, row, bepoch);
-              if (lane == 0) {
-                evals += 1;
-                devals += 1;
-                ruleevals += 1;
-                if (done) d.long_done[i] = 1;
-              }
-            }
-          }
 #ifdef ECNE_PROFILE
           long long dz1 = clock64();
 #endif
@@ -892,12 +1043,30 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
             }
           }
 #ifdef ECNE_PROFILE
+          long long dz4 = clock64();
+#endif
+          // (a) long rows last, one warp each: block b owns long rows b, b+grid, ...  (not first: in a round that
+          // changes 300 k wires their ~30 dependent loads would crawl through the sweep's atomic traffic)
+          for (uint32_t i = blockIdx.x + warp_in_block * gridDim.x; i < d.n_long; i += warps_per_block * gridDim.x) {
+            if (d.long_done[i]) continue;
+            const uint32_t row = d.long_rows[i];
+            if (row >= d.row_lo && row < d.row_hi) {
+              const bool done = eval_row<32>(d, rbuf, wbuf, (int)list, row, bepoch);
+              if (lane == 0) {
+                evals += 1;
+                devals += 1;
+                ruleevals += 1;
+                if (done) d.long_done[i] = 1;
+              }
+            }
+          }
+#ifdef ECNE_PROFILE
           if (threadIdx.x == 0 && dense_rounds < 40) {
             unsigned long long* q = d.prof + 28000 + ((size_t)dense_rounds * gridDim.x + blockIdx.x) * 4;
             long long dz3 = clock64();
-            q[0] = (unsigned long long)(dz1 - tp);  // long rows (from round start)
-            q[1] = (unsigned long long)(dz2 - dz1);
-            q[2] = (unsigned long long)(dz3 - dz2);
+            q[0] = (unsigned long long)(dz3 - dz4);  // long rows
+            q[1] = (unsigned long long)(dz2 - dz1);  // replay
+            q[2] = (unsigned long long)(dz4 - dz2);  // sweep
             q[3] = gr;
           }
 #endif

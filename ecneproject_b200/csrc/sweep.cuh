@@ -66,9 +66,11 @@ __device__ __forceinline__ void apply_update(const Dev&, int buf, uint32_t w, ui
 __device__ __noinline__ void emit_impl(int wbuf, int list, uint32_t w, uint32_t bits, uint32_t lbr, uint32_t ubr) {
   const Dev& d = c_dev;
   const uint32_t r = apply_update_t<true>(wbuf, w, bits, lbr, ubr);
-  if (r & 2u) atomicOr(d.bnd_flag + list, 1u);  // a bound moved this round
+  // round flags (bit0: a bound moved, bit1: a heavy wire changed => the next round is dense): set once —
+  // 160 k rows fix a bound in ecdsa's first round, and 160 k REDs on one address serialise in one L2 slice
+  const uint32_t want = ((r & 2u) ? 1u : 0u) | (((r & 1u) && (r & 4u)) ? 2u : 0u);
+  if (want && (__ldcg(d.bnd_flag + list) & want) != want) atomicOr(d.bnd_flag + list, want);
   if (!(r & 1u)) return;
-  if (r & 4u) atomicOr(d.bnd_flag + list, 2u);  // a heavy wire changed: the next round is dense
   // warp-aggregated slot allocation: the lanes that reach this point together take one atomic (a round
   // that changes 300 k wires would otherwise serialise 300 k RMWs on one L2 address)
   const unsigned int am = __activemask();

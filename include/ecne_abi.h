@@ -144,7 +144,9 @@ int ecne_shard_rows(const ecne_problem_t* problem, int rank, int world, uint64_t
 int ecne_set_option(const char* key, int64_t value);
 
 /* ---- field-arithmetic known-answer hooks: run the device Montgomery code on n elements ----
- * op: 0 add, 1 sub, 2 mul, 3 inv (b ignored), 4 neg (b ignored).  a, b, out: [n*4] canonical. */
+ * op: 0 add, 1 sub, 2 mul, 3 inv (b ignored), 4 neg (b ignored), 5 divexact(-a, b); the plain 256-bit
+ * integer helpers of Case 5 (:1266-1274): 6 -> 1 if b divides a else 0 (b != 0), 7 -> sign(a*b - p) + 1.
+ * a, b, out: [n*4] canonical. */
 int ecne_fr_batch(int op, uint64_t n, const uint64_t* a, const uint64_t* b, uint64_t* out);
 
 #ifdef __cplusplus

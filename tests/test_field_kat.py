@@ -68,3 +68,43 @@ def test_device_field_ops(op):
                            out.ctypes.data_as(_abi.u64p))
     assert st == 0, lib.ecne_last_error()
     assert from_limbs(out) == expected(op, a, b)
+
+
+@pytest.mark.gpu
+def test_device_integer_helpers_of_case5():
+    """The plain 256-bit integer divisibility / product-compare used by the mixed-radix rule (:1266-1274)."""
+    import random
+    rng = random.Random(7)
+    a, b = [], []
+    for i in range(6000):
+        kind = i % 6
+        if kind == 0:      # exact multiples with nearby lengths (what a sorted coefficient chain produces)
+            y = rng.getrandbits(rng.randint(1, 200)) | 1
+            x = y * rng.randint(1, 1 << rng.randint(0, 50))
+        elif kind == 1:    # near misses
+            y = rng.getrandbits(rng.randint(2, 200)) | 2
+            x = y * rng.randint(1, 1 << 40) + rng.randint(1, y - 1)
+        elif kind == 2:    # powers of two
+            y = 1 << rng.randint(0, 250)
+            x = rng.getrandbits(253) & ~((1 << rng.randint(0, 252)) - 1)
+        elif kind == 3:    # random field-size values
+            y = rng.randrange(1, P)
+            x = rng.randrange(0, P)
+        elif kind == 4:    # divisor longer than the dividend, zero dividend
+            y = rng.getrandbits(200) | (1 << 199)
+            x = rng.choice([0, rng.getrandbits(100)])
+        else:              # equal values, one
+            y = rng.choice([1, rng.randrange(1, P)])
+            x = y if rng.random() < 0.5 else rng.randrange(0, P)
+        a.append(x % (1 << 256))
+        b.append(y)
+    A, B = to_limbs(a), to_limbs(b)
+    lib = _abi.engine_lib()
+    out = np.zeros_like(A)
+    assert lib.ecne_fr_batch(6, len(a), A.ctypes.data_as(_abi.u64p), B.ctypes.data_as(_abi.u64p),
+                             out.ctypes.data_as(_abi.u64p)) == 0, lib.ecne_last_error()
+    assert from_limbs(out) == [1 if x % y == 0 else 0 for x, y in zip(a, b)]
+    out = np.zeros_like(A)
+    assert lib.ecne_fr_batch(7, len(a), A.ctypes.data_as(_abi.u64p), B.ctypes.data_as(_abi.u64p),
+                             out.ctypes.data_as(_abi.u64p)) == 0, lib.ecne_last_error()
+    assert from_limbs(out) == [(x * y > P) - (x * y < P) + 1 for x, y in zip(a, b)]

@@ -9,6 +9,9 @@ name = sys.argv[1]; reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 cfg = CONFIGS[name]
 reduced, specials, main = api.prepare(fixtures.path(cfg["main"]), [fixtures.path(t) for t in cfg.get("trusted", [])], cfg.get("trusted_names", []))
 lib = api._engine()
+for kv in sys.argv[3:]:  # engine knobs: key=value (ecne_set_option)
+    k, v = kv.split('=')
+    assert lib.ecne_set_option(k.encode(), int(v)) == 0, lib.ecne_last_error()
 ph = api.ProblemHandle(reduced, specials, main.known, main.targets, main.n_vars, cfg.get("secp_solve", False))
 h = C.c_void_p()
 assert lib.ecne_upload(C.byref(ph.c), C.byref(h)) == 0, lib.ecne_last_error()
