@@ -25,7 +25,7 @@ struct Global {
   // options
   long long max_rounds = 1000000;     // per P1 launch
   long long max_outer = 100000;
-  long long sparse_max = -1;          // records per round up to which a round is frontier-driven (-1: rows / 8)
+  long long sparse_max = -1;          // records per round up to which a round is frontier-driven (-1: rows / 32)
   // pinned staging shared by every call (the API is single-threaded)
   void* h_status = nullptr;
   void* h_counts = nullptr;
@@ -250,7 +250,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   d.max_outer = (uint32_t)std::min<long long>(G.max_outer, 0x7fffffffLL);
   {
     const uint32_t rows = d.row_hi - d.row_lo;
-    const long long sm = G.sparse_max >= 0 ? G.sparse_max : std::max<long long>(4096, rows / 8);
+    const long long sm = G.sparse_max >= 0 ? G.sparse_max : std::max<long long>(4096, rows / 32);
     d.sparse_max = (uint32_t)std::min<long long>(sm, 0x7fffffffLL);
   }
   int status = ECNE_OK;
@@ -279,8 +279,20 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
             S.prof[0], S.dense_rounds, S.prof[1], S.rounds - S.dense_rounds, S.prof[2], S.prof[3], S.prof[4], S.prof[5],
             S.prof[6], S.prof[7], S.outer, S.n_cand_total, S.n_cand_max, S.dense_evals, S.evals);
     if (atoi(getenv("ECNE_DEBUG_PROF")) > 2) {
-      std::vector<unsigned long long> pr(28000 + 12 * 148 * 4);
+      std::vector<unsigned long long> pr(28000 + 24 * 148 * 4);
       cudaMemcpy(pr.data(), d.prof, pr.size() * 8, cudaMemcpyDeviceToHost);
+      for (int r = 12; r < 24; ++r) {
+        unsigned long long mx[3] = {0, 0, 0}, sum[3] = {0, 0, 0}, g = 0;
+        for (int b = 0; b < 148; ++b)
+          for (int k = 0; k < 3; ++k) {
+            unsigned long long v = pr[28000 + ((size_t)r * 148 + b) * 4 + k];
+            mx[k] = v > mx[k] ? v : mx[k];
+            sum[k] += v;
+            g = pr[28000 + ((size_t)r * 148 + b) * 4 + 3];
+          }
+        if (g) fprintf(stderr, "[p2scan] outer %llu: short rows mean %llu max %llu | long rows mean %llu max %llu | pre mean %llu max %llu\n", g,
+                       sum[0] / 148, mx[0], sum[1] / 148, mx[1], sum[2] / 148, mx[2]);
+      }
       for (int r = 0; r < 12; ++r) {
         unsigned long long mx[3] = {0, 0, 0}, sum[3] = {0, 0, 0}, g = 0;
         for (int b = 0; b < 148; ++b)

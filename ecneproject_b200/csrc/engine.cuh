@@ -86,6 +86,12 @@ struct __align__(16) Rec {
 
 #define ECNE_MAX_WORLD 8
 
+// result of the P2 candidate scan of a long row, with the Jacobi round counter at the time of the scan
+struct __align__(16) LongP2 {
+  unsigned long long hs, hx;
+  uint32_t k, w1, gr, bad;
+};
+
 struct Status {            // device-resident, read back once per outer round
   unsigned long long changed;      // state changes of the current outer round ("successful_steps")
   unsigned long long rounds;       // Jacobi rounds of the single-row sweep
@@ -147,6 +153,7 @@ struct Dev {
   const uint32_t* inv_row;  // [inv_ptr[V + 1]]
   const uint4* inv_head;    // [V + 2] {rows listed, first three rows}: one load for almost every wire
   unsigned int* long_stamp; // [n_long] last round that queued the long row (dedupe inside a sparse round)
+  LongP2* long_p2;          // [n_long] the row's last P2 scan (reused while none of its wires has changed)
   // rows with the P3 / P4 shape (static lists)
   const uint32_t* p3_rows;
   const uint32_t* p4_rows;

@@ -53,35 +53,65 @@ __device__ __forceinline__ void p2_candidate(const Dev& d, uint32_t row, unsigne
 
 // P2 qualification of one row through the CSR (generic path): every non-unique wire appears in C
 // only (:1364-1385).  k == 1 is decided on the spot; k >= 2 rows become (set-hash, row) candidates.
+// `cache` (long rows, single GPU): the scan of a long row walks up to 1025 terms, and its outcome only
+// depends on which of the row's wires are unique — so it is reused until a Jacobi round has looked at the
+// row again (long_stamp: a sparse round queued it because one of its wires changed; `dense_gr`: a dense
+// round swept everything).
 template <int G>
-__device__ __noinline__ void p2_scan_row(const Dev&, int rbuf, int pl, uint32_t row) {
+__device__ __noinline__ void p2_scan_row(const Dev&, int rbuf, int pl, uint32_t row, LongP2* cache = nullptr,
+                                         unsigned int stamp = 0, unsigned int dense_gr = 0, unsigned int gr = 0) {
   const Dev& d = c_dev;
   const uint32_t lane = Grp<G>::lane();
-  const uint8_t* F = d.F[rbuf];
-  const uint32_t s0 = d.seg[3 * row], s2 = d.seg[3 * row + 2], s3 = d.seg[3 * row + 3];
-  uint32_t bad = 0;
-  scan_terms<G, SCAN_U(G)>(d, F, s0, s2, lane, [&](uint32_t, uint32_t f) { bad |= (f & WF_U) ? 0u : 1u; });
-  if (Grp<G>::any(bad != 0)) return;  // a non-unique wire in A or B (:1366, :1378)
-  uint32_t k = 0, w1 = 0;
+  uint32_t k = 0, w1 = 0, bad = 0;
   unsigned long long hs = 0, hx = 0;
-  scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
-    if (!(f & WF_U)) {
-      ++k;
-      w1 = w;
-      unsigned long long m = mix64(w);
-      hs += m;
-      hx ^= mix64(m + 0x9e3779b97f4a7c15ULL);
-    }
-  });
-  if (G > 1) {
-    k = Grp<G>::sum(k);
-    w1 = Grp<G>::max(w1);
-    for (int o = 16; o > 0; o >>= 1) {
-      hs += __shfl_xor_sync(0xffffffffu, hs, o);
-      hx ^= __shfl_xor_sync(0xffffffffu, hx, o);
+  bool reuse = false;
+  if (cache) {
+    const LongP2 c = *cache;
+    if (c.gr != 0 && stamp < c.gr && dense_gr < c.gr) {
+      reuse = true;
+      k = c.k;
+      w1 = c.w1;
+      hs = c.hs;
+      hx = c.hx;
+      bad = c.bad;
     }
   }
-  if (k == 0 || lane != 0) return;
+  if (!reuse) {
+    const uint8_t* F = d.F[rbuf];
+    const uint32_t s0 = d.seg[3 * row], s2 = d.seg[3 * row + 2], s3 = d.seg[3 * row + 3];
+    scan_terms<G, SCAN_U(G)>(d, F, s0, s2, lane, [&](uint32_t, uint32_t f) { bad |= (f & WF_U) ? 0u : 1u; });
+    bad = Grp<G>::any(bad != 0) ? 1u : 0u;  // a non-unique wire in A or B (:1366, :1378)
+    if (!bad) {
+      scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
+        if (!(f & WF_U)) {
+          ++k;
+          w1 = w;
+          unsigned long long m = mix64(w);
+          hs += m;
+          hx ^= mix64(m + 0x9e3779b97f4a7c15ULL);
+        }
+      });
+      if (G > 1) {
+        k = Grp<G>::sum(k);
+        w1 = Grp<G>::max(w1);
+        for (int o = 16; o > 0; o >>= 1) {
+          hs += __shfl_xor_sync(0xffffffffu, hs, o);
+          hx ^= __shfl_xor_sync(0xffffffffu, hx, o);
+        }
+      }
+    }
+    if (cache && lane == 0) {
+      LongP2 c;
+      c.hs = hs;
+      c.hx = hx;
+      c.k = k;
+      c.w1 = w1;
+      c.gr = gr + 1;  // scanned after round gr: anything stamped up to gr is included
+      c.bad = bad;
+      *cache = c;
+    }
+  }
+  if (bad || k == 0 || lane != 0) return;
   if (k == 1) {  // 1x1 "matrix": the stored coefficient is non-zero (:1402)
     emit(d, 1, pl, w1, WF_U | WF_K);
     return;
@@ -269,12 +299,21 @@ struct SpecialsCache {
   uint32_t in_ptr[SPC_N + 1], out_ptr[SPC_N + 1];
   uint32_t in[SPC_IN], out[SPC_OUT];
   uint8_t solved[SPC_N];
-  int ok;  // the lists fit
+  int ok;         // the lists fit
+  int has_pairs;  // the list holds a BigMultModP and a BigLessThan (P0' has something to do)
 };
 __device__ __forceinline__ void specials_cache_fill(const Dev& d, SpecialsCache& c) {
   const bool fits = d.n_specials <= SPC_N && (d.n_specials == 0 || (d.sp_in_ptr[d.n_specials] <= SPC_IN &&
                                                                      d.sp_out_ptr[d.n_specials] <= SPC_OUT));
-  if (threadIdx.x == 0) c.ok = fits ? 1 : 0;
+  if (threadIdx.x == 0) {
+    c.ok = fits ? 1 : 0;
+    bool m = false, l = false;
+    for (uint32_t i = 0; i < d.n_specials; ++i) {
+      m |= d.sp_kind[i] == ECNE_SPECIAL_BIGMULTMODP;
+      l |= d.sp_kind[i] == ECNE_SPECIAL_BIGLESSTHAN;
+    }
+    c.has_pairs = (m && l) ? 1 : 0;
+  }
   if (fits) {
     for (uint32_t i = threadIdx.x; i <= d.n_specials; i += blockDim.x) {
       c.in_ptr[i] = d.sp_in_ptr[i];
@@ -330,7 +369,7 @@ __device__ __noinline__ void phase_p0(const Dev&, int pl, SpecialsCache& sc) {
     start = f + 1;
   }
   // P0': every (BigMultModP, BigLessThan) pair marks the BigLessThan's first three inputs (:750-800)
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && sc.has_pairs) {
     for (uint32_t i = 0; i < d.n_specials; ++i) {
       if (d.sp_kind[i] != ECNE_SPECIAL_BIGMULTMODP) continue;
       for (uint32_t j = 0; j < d.n_specials; ++j) {
@@ -801,6 +840,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
   unsigned long long evals = 0, ruleevals = 0, devals = 0, dcycles = 0;
   unsigned int rounds_total = 0, dense_rounds = 0;
   unsigned int gr = 0;  // Jacobi round counter of the solve (stamps the long-row queue)
+  unsigned int last_dense_gr = 0;
   uint32_t bepoch = 0;  // rounds so far that tightened a bound (same value in every thread)
 
   // ---- stage: live mask + the smem-resident row records ---------------------------------------
@@ -1114,6 +1154,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         }
         if (dense) {
           dense_rounds += 1;
+          last_dense_gr = gr;
           if (tid == 0) dcycles += (unsigned long long)(clock64() - tc0);
           PROF(0);
         } else {
@@ -1141,48 +1182,70 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     }
     // =============================== P2: linear systems (:1357-1417) ===============================
     // candidate scan over the rows that can still fire (state is at the P1 fixpoint, in both buffers)
+#ifdef ECNE_PROFILE
+    long long pz0 = 0, pz1 = 0;
+#endif
     {
       const uint8_t* F = d.F[0];
+#ifdef ECNE_PROFILE
+      pz0 = clock64();
+#endif
       if (d.world == 1) {
         evals += (unsigned int)__popcll(live);  // one visit of the linear-system sweep per row (:1359)
+        // two rows in flight; all six state bytes of a row are gathered before any is looked at (unused
+        // slots hold the constant wire 1, which is unique)
         for (unsigned long long m = live; m;) {
-          const int k = __ffsll((long long)m) - 1;
+          int kk2[2];
+          kk2[0] = __ffsll((long long)m) - 1;
           m &= m - 1;
-          const uint32_t row = d.row_lo + tid + (uint32_t)k * nthreads;
-          InlineRow r;
-          if (k < ks)
-            unpack_row(sm_rec[(2 * k) * blockDim.x + threadIdx.x], sm_rec[(2 * k + 1) * blockDim.x + threadIdx.x], r);
-          else
-            load_row(d, row, r);
-          if (r.rf & RF_LONG) continue;
-          if (!(r.meta & 0x10000u)) {  // not inline
-            if (!(d.solved[row] & 1)) p2_scan_row<1>(d, 0, pl, row);
-            continue;
-          }
-          const uint32_t nAB = r.meta & 0xffu, nT = nAB + ((r.meta >> 8) & 0xffu);
-          uint32_t kk = 0, w1 = 0;
-          bool bad = false;
-          unsigned long long hs = 0, hx = 0;
+          kk2[1] = m ? __ffsll((long long)m) - 1 : -1;
+          if (kk2[1] >= 0) m &= m - 1;
+          InlineRow rr[2];
+          uint32_t ff[2][ROWREC_INLINE];
 #pragma unroll
-          for (int j = 0; j < ROWREC_INLINE; ++j) {
-            if ((uint32_t)j < nT && !(ld_flag(F, r.c[j]) & WF_U)) {
-              if ((uint32_t)j < nAB) {
-                bad = true;
-              } else {
-                ++kk;
-                w1 = r.c[j];
-                unsigned long long mm = mix64(r.c[j]);
-                hs += mm;
-                hx ^= mix64(mm + 0x9e3779b97f4a7c15ULL);
+          for (int h = 0; h < 2; ++h) {
+            const int k = kk2[h] >= 0 ? kk2[h] : kk2[0];
+            if (k < ks)
+              unpack_row(sm_rec[(2 * k) * blockDim.x + threadIdx.x], sm_rec[(2 * k + 1) * blockDim.x + threadIdx.x], rr[h]);
+            else
+              load_row(d, d.row_lo + tid + (uint32_t)k * nthreads, rr[h]);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < ROWREC_INLINE; ++j)
+              ff[h][j] = (rr[h].meta & 0x10000u) ? ld_flag(F, rr[h].c[j]) : (uint32_t)WF_U;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (kk2[h] < 0) continue;
+            const InlineRow& r = rr[h];
+            const uint32_t row = d.row_lo + tid + (uint32_t)kk2[h] * nthreads;
+            if (r.rf & RF_LONG) continue;
+            const uint32_t nAB = r.meta & 0xffu;
+            uint32_t kk = 0, w1 = 0;
+            bool bad = false;
+            unsigned long long hs = 0, hx = 0;
+#pragma unroll
+            for (int j = 0; j < ROWREC_INLINE; ++j) {
+              if (!(ff[h][j] & WF_U)) {
+                if ((uint32_t)j < nAB) {
+                  bad = true;
+                } else {
+                  ++kk;
+                  w1 = r.c[j];
+                  unsigned long long mm = mix64(r.c[j]);
+                  hs += mm;
+                  hx ^= mix64(mm + 0x9e3779b97f4a7c15ULL);
+                }
               }
             }
+            if (bad || kk == 0) continue;
+            if (d.solved[row] & 1) continue;  // equation_solved rows take no part (:1360)
+            if (kk == 1)
+              emit(d, 1, pl, w1, WF_U | WF_K);
+            else
+              p2_candidate(d, row, hs, hx, kk);
           }
-          if (bad || kk == 0) continue;
-          if (d.solved[row] & 1) continue;  // equation_solved rows take no part (:1360)
-          if (kk == 1)
-            emit(d, 1, pl, w1, WF_U | WF_K);
-          else
-            p2_candidate(d, row, hs, hx, kk);
         }
         for (uint32_t k = kmask; k < per_thread; ++k) {
           uint32_t r = tid + k * nthreads;
@@ -1196,13 +1259,29 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
             if (row >= d.row_lo && row < d.row_hi) evals += 1;  // replicated work is counted once
           }
       }
+#ifdef ECNE_PROFILE
+      pz1 = clock64();
+#endif
       for (uint32_t i = blockIdx.x + warp_in_block * gridDim.x; i < d.n_long; i += warps_per_block * gridDim.x) {
         const uint32_t row = d.long_rows[i];
         if (d.solved[row] & 1) continue;
         if (d.world == 1 && d.long_done[i]) continue;
-        p2_scan_row<32>(d, 0, pl, row);
+        if (d.world == 1)
+          p2_scan_row<32>(d, 0, pl, row, d.long_p2 + i, __ldcg(d.long_stamp + i), last_dense_gr, gr);
+        else
+          p2_scan_row<32>(d, 0, pl, row);
       }
     }
+#ifdef ECNE_PROFILE
+    if (threadIdx.x == 0 && outer < 12) {
+      unsigned long long* q = d.prof + 28000 + ((size_t)(12 + outer) * gridDim.x + blockIdx.x) * 4;
+      long long pz2 = clock64();
+      q[0] = (unsigned long long)(pz1 - pz0);  // short rows
+      q[1] = (unsigned long long)(pz2 - pz1);  // long rows
+      q[2] = (unsigned long long)(pz0 - tp);   // wait before the scan (block 0: since the last PROF point)
+      q[3] = outer;
+    }
+#endif
     unsigned int n_cand = sync_and_load(d, &d.st->p2_cand);
     if (n_cand > d.N) n_cand = d.N;
     cand_total += n_cand;
@@ -1404,6 +1483,7 @@ cudaError_t launch_reset(const Dev& d, int grid, cudaStream_t s) {
   cudaMemsetAsync(d.solved, 0, (size_t)d.N + 1, s);
   if (d.n_long) cudaMemsetAsync(d.long_done, 0, d.n_long, s);
   if (d.n_long) cudaMemsetAsync(d.long_stamp, 0, (size_t)d.n_long * sizeof(unsigned int), s);
+  if (d.n_long) cudaMemsetAsync(d.long_p2, 0, (size_t)d.n_long * sizeof(LongP2), s);
   if (d.n_specials) cudaMemsetAsync(d.sp_solved, 0, d.n_specials, s);
   cudaMemsetAsync(d.rec_count, 0, 8 * sizeof(unsigned int), s);
   cudaMemsetAsync(d.bnd_flag, 0, 8 * sizeof(unsigned int), s);

@@ -937,6 +937,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(A.alloc(&d.live, (size_t)p1_grid_size(0) * p1_threads()));
   CK(A.alloc(&d.long_done, (size_t)cnt.n_long));
   CK(A.alloc(&d.long_stamp, (size_t)cnt.n_long));
+  CK(A.alloc(&d.long_p2, (size_t)cnt.n_long));
   // static P3 / P4 row lists
   uint32_t *d_p3, *d_p4;
   unsigned int* d_nphase;
