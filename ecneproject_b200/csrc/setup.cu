@@ -168,16 +168,103 @@ __device__ inline int c3_pattern_small(const Raw& r, uint32_t row, uint32_t l) {
 
 struct Counters {
   unsigned int n2a, n2b, n_long, max_c, n_c3_long, bad;
+  unsigned int n_longc;  // rows handed to k_classify_long
 };
 
-__global__ void k_classify(Raw r, uint32_t* rflags, RowAux* aux, Counters* cnt, uint32_t* c3_long) {
+#define CLASSIFY_LONG_C 64u  // rows whose stored C segment is longer get a warp (k_classify_long)
+// everything after the two scans of a row: flags, aux, counters
+__device__ __forceinline__ void classify_decide(const Raw& r, uint32_t row, const ABScan& ab, const CScan& cs, bool bad,
+                                            uint32_t* rflags, RowAux* aux, Counters* cnt, uint32_t* c3_long);
+
+__global__ void k_classify(Raw r, uint32_t* rflags, RowAux* aux, Counters* cnt, uint32_t* c3_long, uint32_t* longc) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= r.N) return;
+  if (r.seg[3ull * row + 3] - r.seg[3ull * row + 2] > CLASSIFY_LONG_C) {  // k_classify_long
+    longc[atomicAdd(&cnt->n_longc, 1u)] = row;
+    return;
+  }
   bool bad = false;
   ABScan ab;
   CScan cs;
   scan_ab(r, row, ab, bad);
   scan_c(r, row, cs, bad);
+  classify_decide(r, row, ab, cs, bad, rflags, aux, cnt, c3_long);
+}
+
+__device__ __forceinline__ void classify_long_row(const Raw& r, uint32_t row, uint32_t lane, uint32_t* rflags, RowAux* aux,
+                                                  Counters* cnt, uint32_t* c3_long);
+// One warp per row with a long C segment: the lanes stride the stored terms and their partial scans are
+// merged (counts by sum, "last key with ..." by the largest term index), then lane 0 decides as above.
+__global__ void k_classify_long(Raw r, uint32_t* rflags, RowAux* aux, Counters* cnt, uint32_t* c3_long,
+                                const uint32_t* longc) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned int n_rows = *((volatile unsigned int*)&cnt->n_longc);
+  for (uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; li < n_rows; li += nwarps) classify_long_row(r, longc[li], lane, rflags, aux, cnt, c3_long);
+}
+__device__ __forceinline__ void classify_long_row(const Raw& r, uint32_t row, uint32_t lane, uint32_t* rflags, RowAux* aux,
+                                                  Counters* cnt, uint32_t* c3_long) {
+  const uint64_t b = r.seg[3ull * row + 2], e = r.seg[3ull * row + 3];
+  uint32_t nC = 0, n_non1 = 0, n_one = 0, n_mone = 0;
+  unsigned long long last_x = 0, last_one = 0, last_mone = 0;  // (term index + 1) << 32 | wire
+  bool bad = false, key1 = false;
+  for (uint64_t t = b + lane; t < e; t += 32) {
+    const uint32_t w = r.col[t];
+    if (w < 1 || w > r.V) {
+      bad = true;
+      continue;
+    }
+    const fr::u256 c = r.coef[t];
+    if (w == 1) key1 = true;
+    if (fr::is_zero(c)) continue;
+    const unsigned long long tag = ((unsigned long long)(t - b + 1) << 32) | w;
+    nC++;
+    if (w != 1) {
+      n_non1++;
+      last_x = tag;
+    }
+    if (fr::is_one(c)) {
+      n_one++;
+      last_one = tag;
+    } else if (fr::is_minus_one(c)) {
+      n_mone++;
+      last_mone = tag;
+    }
+  }
+  nC = __reduce_add_sync(0xffffffffu, nC);
+  n_non1 = __reduce_add_sync(0xffffffffu, n_non1);
+  n_one = __reduce_add_sync(0xffffffffu, n_one);
+  n_mone = __reduce_add_sync(0xffffffffu, n_mone);
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long v;
+    v = __shfl_xor_sync(0xffffffffu, last_x, o);
+    last_x = v > last_x ? v : last_x;
+    v = __shfl_xor_sync(0xffffffffu, last_one, o);
+    last_one = v > last_one ? v : last_one;
+    v = __shfl_xor_sync(0xffffffffu, last_mone, o);
+    last_mone = v > last_mone ? v : last_mone;
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  key1 = __any_sync(0xffffffffu, key1);
+  if (lane != 0) return;
+  ABScan ab;
+  scan_ab(r, row, ab, bad);
+  CScan cs;
+  cs.nC = nC;
+  cs.stC = (uint32_t)(e - b);
+  cs.n_non1 = n_non1;
+  cs.x = (uint32_t)last_x;
+  cs.n_one = n_one;
+  cs.n_mone = n_mone;
+  cs.key_one = (uint32_t)last_one;
+  cs.key_mone = (uint32_t)last_mone;
+  cs.key1_stored = key1;
+  cs.c1 = cs.cx = fr::make_u256(0, 0, 0, 0);  // only read for rows with a single non-constant key (never long)
+  classify_decide(r, row, ab, cs, bad, rflags, aux, cnt, c3_long);
+}
+
+__device__ __forceinline__ void classify_decide(const Raw& r, uint32_t row, const ABScan& ab, const CScan& cs, bool bad,
+                                            uint32_t* rflags, RowAux* aux, Counters* cnt, uint32_t* c3_long) {
   if (bad) {
     cnt->bad = 1;
     rflags[row] = 0;
@@ -815,7 +902,10 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(tmp.alloc(&d_cnt, 1));
   CK(tmp.alloc(&d_c3_long, N));
   CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), s));
-  if (N) k_classify<<<nb(N, 128), 128, 0, s>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long);
+  uint32_t* d_longc;
+  CK(tmp.alloc(&d_longc, N));
+  if (N) k_classify<<<nb(N, 128), 128, 0, s>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long, d_longc);
+  if (N) k_classify_long<<<148, 256, 0, s>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long, d_longc);
   Counters cnt;
   CK(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
   uint32_t nnz_nz = 0;
@@ -868,8 +958,23 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   unsigned int* d_next;
   CK(tmp.alloc(&d_next, 2));
   CK(cudaMemsetAsync(d_next, 0, 2 * sizeof(unsigned int), s));
-  k_consts<<<1, 256, 0, s>>>(d_tvals);
-  if (N) k_values<<<nb(N, 128), 128, 0, s>>>(raw, d_rflags, d_aux, d_roots, d_tvals, d_next, d_next + 1);
+  // The bound-table chain (values -> sort -> ranks) only depends on the classification, and the sweep
+  // layout below does not depend on it: it runs on a side stream, concurrently with the layout kernels.
+  static cudaStream_t s2 = nullptr;
+  static int s2_dev = -1;
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (!s2 || s2_dev != cur_dev) {  // one side stream per process (one process per GPU)
+    CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    s2_dev = cur_dev;
+  }
+  cudaEvent_t ev_fork, ev_join;
+  cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+  cudaEventRecord(ev_fork, s);
+  cudaStreamWaitEvent(s2, ev_fork, 0);
+  k_consts<<<1, 256, 0, s2>>>(d_tvals);
+  if (N) k_values<<<nb(N, 128), 128, 0, s2>>>(raw, d_rflags, d_aux, d_roots, d_tvals, d_next, d_next + 1);
   const uint32_t nc = N_CONST + cnt.n2b;
   uint32_t *d_idx, *d_idx2, *d_flag, *d_incl, *d_rank_of;
   unsigned long long *d_k1, *d_k2;
@@ -882,27 +987,27 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(tmp.alloc(&d_k1, nc));
   CK(tmp.alloc(&d_k2, nc));
   CK(A.alloc(&d_table, nc));
-  k_iota<<<nb(nc, 256), 256, 0, s>>>(d_idx, nc);
+  void* d_ms = nullptr;
+  size_t d_ms_bytes = 0;
+  k_iota<<<nb(nc, 256), 256, 0, s2>>>(d_idx, nc);
   {  // one merge sort of the index permutation with a 256-bit comparator (a handful of launches; an LSD
      // radix sort over four 64-bit limbs costs 40 launch-bound passes for these ~10^5 values)
     size_t need = 0;
-    cub::DeviceMergeSort::SortKeys((void*)nullptr, need, d_idx, (int)nc, ValLess{d_tvals}, s);
-    void* d_ms = d_cub;
-    if (need > cub_bytes) CK(tmp.alloc((uint8_t**)&d_ms, need));
-    CK(cub::DeviceMergeSort::SortKeys(d_ms, need, d_idx, (int)nc, ValLess{d_tvals}, s));
+    cub::DeviceMergeSort::SortKeys((void*)nullptr, need, d_idx, (int)nc, ValLess{d_tvals}, s2);
+    need = std::max<size_t>(need, (size_t)1 << 20);  // own scratch: d_cub is in use on the main stream
+    CK(tmp.alloc((uint8_t**)&d_ms, need));
+    d_ms_bytes = need;
+    CK(cub::DeviceMergeSort::SortKeys(d_ms, need, d_idx, (int)nc, ValLess{d_tvals}, s2));
   }
-  k_distinct<<<nb(nc, 256), 256, 0, s>>>(d_tvals, d_idx, nc, d_flag);
+  k_distinct<<<nb(nc, 256), 256, 0, s2>>>(d_tvals, d_idx, nc, d_flag);
   {
-    size_t b = cub_bytes;
-    CK(cub::DeviceScan::InclusiveSum(d_cub, b, d_flag, d_incl, (int)nc, s));
+    size_t b = d_ms_bytes;
+    CK(cub::DeviceScan::InclusiveSum(d_ms, b, d_flag, d_incl, (int)nc, s2));
   }
-  k_ranks<<<nb(nc, 256), 256, 0, s>>>(d_tvals, d_idx, d_incl, nc, d_rank_of, d_table);
-  if (N) k_fill_ranks<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_rflags, d_aux, d_rank_of, d_segnz);
+  k_ranks<<<nb(nc, 256), 256, 0, s2>>>(d_tvals, d_idx, d_incl, nc, d_rank_of, d_table);
+  if (N) k_fill_ranks<<<nb(N, 256), 256, 0, s2>>>((uint32_t)N, d_rflags, d_aux, d_rank_of, d_segnz);
   uint32_t h_rank[3], h_tn;
-  CK(cudaMemcpyAsync(&h_rank[0], d_rank_of + 0, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&h_rank[1], d_rank_of + 1, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&h_rank[2], d_rank_of + 254, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&h_tn, d_incl + (nc - 1), 4, cudaMemcpyDeviceToHost, s));
+  cudaEventRecord(ev_join, s2);
 
   // ---- sweep layout ---------------------------------------------------------------------------
   uint32_t* d_col;
@@ -1018,7 +1123,15 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(A.alloc(&R->d_kbits, (V + 63) / 64));
   CK(A.alloc(&R->d_counts, 4));
 
+  cudaStreamWaitEvent(s, ev_join, 0);  // the timing event below covers the side chain too
+  CK(cudaMemcpyAsync(&h_rank[0], d_rank_of + 0, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_rank[1], d_rank_of + 1, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_rank[2], d_rank_of + 254, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_tn, d_incl + (nc - 1), 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  CK(cudaStreamSynchronize(s2));
+  cudaEventDestroy(ev_fork);
+  cudaEventDestroy(ev_join);
   d.r0 = h_rank[0];
   d.r1 = h_rank[1];
   d.rpm1 = h_rank[2];
