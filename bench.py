@@ -150,8 +150,9 @@ def run_reference(args):
     import oracle_lib
     reduced, specials, main = load_problem()
     lib = oracle_lib.lib()
-    # bounded sample: full solve is ~10 s; fall back to the first outer round when K+W is large
-    full = (args.steps + args.warmup) <= 12
+    # bounded sample: a full solve is ~4.5 s of one host core; fall back to the first outer round (the
+    # queue loop over every row + the three whole-set sweeps) when K + W full solves would take minutes
+    full = (args.steps + args.warmup) <= 40
     lib.ecne_oracle_set_max_outer(0 if full else 1)
     sample = ("full solve (28 outer rounds, 59.9 M evals)" if full else
               "first outer round only (queue loop + the three sweeps)")

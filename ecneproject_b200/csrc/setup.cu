@@ -171,6 +171,11 @@ struct Counters {
   unsigned int n_longc;  // rows handed to k_classify_long
 };
 
+// one atomic per converged group of lanes instead of one per row (160 k rows count themselves as 2b)
+__device__ __forceinline__ void warp_count(unsigned int* ctr) {
+  const unsigned int am = __activemask();
+  if ((threadIdx.x & 31u) == (unsigned int)(__ffs((int)am) - 1)) atomicAdd(ctr, (unsigned int)__popc(am));
+}
 #define CLASSIFY_LONG_C 64u  // rows whose stored C segment is longer get a warp (k_classify_long)
 // everything after the two scans of a row: flags, aux, counters
 __device__ __forceinline__ void classify_decide(const Raw& r, uint32_t row, const ABScan& ab, const CScan& cs, bool bad,
@@ -307,7 +312,7 @@ __device__ __forceinline__ void classify_decide(const Raw& r, uint32_t row, cons
     if (cs.n_non1 == 1) {
       rf |= RF_2B;
       a.w1 = cs.x;
-      atomicAdd(&cnt->n2b, 1u);
+      warp_count(&cnt->n2b);
     }
     const bool inserted_zero = (rf & RF_2B) && !cs.key1_stored;  // c[1] read inserts a zero (:962)
     const uint32_t l = cs.nC;
@@ -373,7 +378,7 @@ __device__ __forceinline__ void classify_decide(const Raw& r, uint32_t row, cons
     rf |= RF_LONG;
     atomicAdd(&cnt->n_long, 1u);
   }
-  atomicMax(&cnt->max_c, cs.nC);
+  if (cs.nC > C3_INLINE_MAX) atomicMax(&cnt->max_c, cs.nC);  // sizes the 2^i mod p table of the long candidates
   rflags[row] = rf;
   aux[row] = a;
 }
