@@ -159,13 +159,18 @@ __device__ __forceinline__ void gather_row(const uint8_t* F, const InlineRow& r,
   for (int j = 0; j < ROWREC_INLINE; ++j)
     f[j] = ((r.rf & RF_FAST) && (uint32_t)j < nT) ? ld_flag(F, r.c[j]) : (WF_U | WF_K | WF_ABZ);
 }
-__device__ __forceinline__ bool eval_inline(const Dev&, int rbuf, int wbuf, int list, uint32_t row,
+// Returns EI_DONE when the row can never fire again, EI_GENERIC when the caller still has to run the
+// generic evaluator on it (a dense sweep defers those so that one such lane does not stall its warp in
+// every iteration), 0 otherwise.
+#define EI_DONE 1u
+#define EI_GENERIC 2u
+__device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, int wbuf, int list, uint32_t row,
                                             const InlineRow& r, const uint32_t* f, uint32_t bepoch) {
   const Dev& d = c_dev;
   const uint32_t rf = r.rf;
   if (!(rf & RF_FAST)) {
-    if (rf & RF_LONG) return true;  // swept by a whole warp instead
-    return eval_row<1>(d, rbuf, wbuf, list, row, bepoch);
+    if (rf & RF_LONG) return EI_DONE;  // swept by a whole warp instead
+    return EI_GENERIC;
   }
   const uint32_t nAB = r.meta & 0xffu, nT = nAB + ((r.meta >> 8) & 0xffu);
   uint32_t nuAB = 0, nuC = 0, wC = 0, kmiss = 0, abzmiss = 0;
@@ -264,8 +269,8 @@ __device__ __forceinline__ bool eval_inline(const Dev&, int rbuf, int wbuf, int 
   }
   if (nuC == 0) return true;  // no non-unique wire left in C: Cases 1/5/6 can never fire again
   // Cases 5 / 6 (:1235-1348) need every non-unique key known resp. ABZ-tagged: rare, generic path
-  if ((rf & RF_LINEAR) && (kmiss == 0 || abzmiss == 0)) eval_row<1>(d, rbuf, wbuf, list, row, bepoch);
-  return false;
+  if ((rf & RF_LINEAR) && (kmiss == 0 || abzmiss == 0)) return EI_GENERIC;
+  return 0u;
 }
 
 // ---- phase bodies (device functions of the one persistent kernel) --------------------------------
@@ -584,7 +589,7 @@ __device__ __forceinline__ void sparse_row(const Dev&, int rbuf, int wbuf, int l
   uint32_t f[ROWREC_INLINE];
   gather_row(d.F[rbuf], ir, f);
   evals += 1;
-  eval_inline(d, rbuf, wbuf, list, row, ir, f, bepoch);
+  if (eval_inline(d, rbuf, wbuf, list, row, ir, f, bepoch) & EI_GENERIC) eval_row<1>(d, rbuf, wbuf, list, row, bepoch);
 }
 
 // A frontier-driven Jacobi round: every record of the previous round (a state change of one wire) is
@@ -759,7 +764,8 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
             uint32_t f[ROWREC_INLINE];
             gather_row(d.F[rbuf], ir, f);
             ev += 1;
-            eval_inline(d, rbuf, wbuf, (int)list, row, ir, f, bepoch);
+            if (eval_inline(d, rbuf, wbuf, (int)list, row, ir, f, bepoch) & EI_GENERIC)
+              eval_row<1>(d, rbuf, wbuf, (int)list, row, bepoch);
           }
         }
       }
@@ -1048,6 +1054,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           evals += nl;
           devals += nl;
           ruleevals += nl;
+          unsigned long long slow = 0;
           for (unsigned long long m = live; m;) {
             const int k0 = __ffsll((long long)m) - 1;
             m &= m - 1;
@@ -1068,8 +1075,29 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
             uint32_t f0[ROWREC_INLINE], f1[ROWREC_INLINE];
             gather_row(F, r0, f0);
             if (k1 >= 0) gather_row(F, r1, f1);
-            if (eval_inline(d, rbuf, wbuf, (int)list, row0, r0, f0, bepoch)) live &= ~(1ULL << k0);
-            if (k1 >= 0 && eval_inline(d, rbuf, wbuf, (int)list, row1, r1, f1, bepoch)) live &= ~(1ULL << k1);
+            const uint32_t e0 = eval_inline(d, rbuf, wbuf, (int)list, row0, r0, f0, bepoch);
+            if (e0 & EI_DONE) live &= ~(1ULL << k0);
+            if (e0 & EI_GENERIC) slow |= 1ULL << k0;
+            if (k1 >= 0) {
+              const uint32_t e1 = eval_inline(d, rbuf, wbuf, (int)list, row1, r1, f1, bepoch);
+              if (e1 & EI_DONE) live &= ~(1ULL << k1);
+              if (e1 & EI_GENERIC) slow |= 1ULL << k1;
+            }
+          }
+          // the rows that need the generic evaluator (bit-decomposition patterns, x + y = 1, Case 5/6
+          // candidates), all lanes together: inside the loop above one such lane would stall its warp in
+          // almost every iteration
+          for (unsigned long long m = slow; m;) {
+            const int k = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const uint32_t row = d.row_lo + tid + (uint32_t)k * nthreads;
+            const bool done = eval_row<1>(d, rbuf, wbuf, (int)list, row, bepoch);
+            bool fast;
+            if (k < ks)
+              fast = (sm_rec[(2 * k) * blockDim.x + threadIdx.x].x & RF_FAST) != 0;
+            else
+              fast = (d.rflags[row] & RF_FAST) != 0;
+            if (done && !fast) live &= ~(1ULL << k);  // fast-path rows stay: bounds may still travel through them
           }
           // rows beyond the 64 tracked per thread (only for problems far larger than the machine)
           for (uint32_t k = kmask; k < per_thread; ++k) {
