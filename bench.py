@@ -348,7 +348,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the one k_solve launch of a solve, from the
                 # `ncu --set full` capture committed as profiles/r01_k_solve_ncu_full.csv (not measured live)
-                "traffic": 218.2e6 if world == 1 else None,
+                "traffic": 167.0e6 if world == 1 else None,
                 "peak_source": peak_src, "bytes_per_eval": b_eval, "evals_in_kernel_per_step": evals,
                 "jacobi_rounds_per_step": rounds, "kernel_ms_per_step": sweep_ms_step, "launches_per_step": 1,
                 "dense_rounds": {"rounds": dense_rounds, "evals": dense_evals, "ms": dense_ms,

@@ -1411,31 +1411,30 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
 // ---- finalisation ---------------------------------------------------------------------------
 __global__ void k_pack(Dev d, int buf, unsigned long long* ubits, unsigned long long* kbits,
                        unsigned long long* counts) {
-  // one thread per 64 wires
-  uint32_t word = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nwords = (d.V + 63) / 64;
-  if (word >= nwords) return;
-  unsigned long long u = 0, k = 0;
-  uint32_t nu = 0, nnt = 0, nunt = 0;
-  for (uint32_t b = 0; b < 64; ++b) {
-    uint32_t w = word * 64 + b + 1;
-    if (w > d.V) break;
-    uint32_t f = d.F[buf][w];
-    if (f & WF_U) {
-      u |= 1ULL << b;
-      ++nu;
-    }
-    if (f & WF_K) k |= 1ULL << b;
-    if (d.nontriv[w]) {
-      ++nnt;
-      if (f & WF_U) ++nunt;
-    }
+  // one thread per wire (coalesced byte loads), a ballot packs 32 of them; the two warps of a 64-wire
+  // word write its halves; counters are reduced per block
+  __shared__ unsigned int s_cnt[3];
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // wire i + 1
+  const uint32_t nbits = ((d.V + 63) / 64) * 64;
+  uint32_t f = 0, nt = 0;
+  if (i < d.V) {
+    f = d.F[buf][i + 1];
+    nt = d.nontriv[i + 1];
   }
-  ubits[word] = u;
-  kbits[word] = k;
-  atomicAdd(counts + 0, (unsigned long long)nu);
-  atomicAdd(counts + 1, (unsigned long long)nnt);
-  atomicAdd(counts + 2, (unsigned long long)nunt);
+  const unsigned int mu = __ballot_sync(0xffffffffu, (f & WF_U) != 0);
+  const unsigned int mk = __ballot_sync(0xffffffffu, (f & WF_K) != 0);
+  const unsigned int mn = __ballot_sync(0xffffffffu, nt != 0);
+  if ((threadIdx.x & 31u) == 0 && i < nbits) {
+    reinterpret_cast<unsigned int*>(ubits)[i >> 5] = mu;  // little endian: half (i / 32) & 1 of word i / 64
+    reinterpret_cast<unsigned int*>(kbits)[i >> 5] = mk;
+    atomicAdd(&s_cnt[0], (unsigned int)__popc(mu));
+    atomicAdd(&s_cnt[1], (unsigned int)__popc(mn));
+    atomicAdd(&s_cnt[2], (unsigned int)__popc(mu & mn));
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 __global__ void k_targets(Dev d, int buf, unsigned long long* counts) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1565,7 +1564,7 @@ cudaError_t launch_solve(const Dev& d, unsigned int max_rounds, int grid, cudaSt
 void launch_finalize(const Dev& d, int buf, unsigned long long* ubits, unsigned long long* kbits,
                      unsigned long long* counts, cudaStream_t s) {
   cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), s);
-  k_pack<<<blocks_for((d.V + 63) / 64, 128), 128, 0, s>>>(d, buf, ubits, kbits, counts);
+  k_pack<<<blocks_for((uint64_t)((d.V + 63) / 64) * 64, 256), 256, 0, s>>>(d, buf, ubits, kbits, counts);
   if (d.n_targets) k_targets<<<blocks_for(d.n_targets, 128), 128, 0, s>>>(d, buf, counts);
 }
 void launch_export(const Dev& d, int buf, fr::u256* lb, fr::u256* ub, uint8_t* nvalues,
