@@ -209,7 +209,13 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     lib = _abi.engine_lib()
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout when a communicator is created: keep stdout for the one
+        # JSON line of the contract
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         from ecneproject_b200 import dist as edist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -434,8 +440,11 @@ def main():
                                           f"{int(o.c.constraint_evals)} evals in {dt:.2f} s",
                                 "seconds_to_verdict": dt, "host_cpus": os.cpu_count(),
                                 "matches_gpu_bitmap": o.unique_bits.tobytes() == res.unique_bits.tobytes()}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0

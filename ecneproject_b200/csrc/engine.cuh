@@ -189,6 +189,11 @@ struct Dev {
   unsigned long long* xflag[ECNE_MAX_WORLD]; // every rank's mailbox [ECNE_MAX_WORLD]; we post into slot [rank]
   unsigned int* xcnt;                        // [3][ECNE_MAX_WORLD] record counts per list and rank (local copy)
   unsigned int* xepoch;                      // cross-GPU barrier epoch, persists over the launches of a solve
+  // sharded runs: per-list "this wire already has a record in the list" bytes and the count of distinct
+  // wires a round changed.  Unlike the record count (two racing rows log a wire once or twice) that count
+  // is the same on every rank, so every rank takes the same sharded / replicated decision for a round.
+  uint8_t* wflag[5];
+  unsigned int* dcnt;                        // [8]
 };
 
 // ---- state access -----------------------------------------------------------------------------------
@@ -236,15 +241,20 @@ __device__ __forceinline__ bool is01(uint32_t f) { return (f & (WF_UB01 | WF_NOT
 __device__ __forceinline__ unsigned int cross_gpu_exchange(const Dev& d, unsigned int list,
                                                            unsigned int own_payload, unsigned int xe) {
   const unsigned long long word = ((unsigned long long)xe << 32) | own_payload;
+  // second word: distinct wires this rank's rows changed (bit 31: a heavy wire among them)
+  unsigned int own_d = *((volatile const unsigned int*)(d.dcnt + list)) & 0x7fffffffu;
+  if (*((volatile const unsigned int*)(d.bnd_flag + list)) & 2u) own_d |= 0x80000000u;
+  const unsigned long long word2 = ((unsigned long long)xe << 32) | own_d;
   asm volatile("fence.acq_rel.sys;" ::: "memory");
   for (int h = 0; h < d.world; ++h) {
     unsigned long long* slot = d.xflag[h] + d.rank;
+    asm volatile("st.relaxed.sys.u64 [%0], %1;" ::"l"(slot + ECNE_MAX_WORLD), "l"(word2) : "memory");
     asm volatile("st.release.sys.u64 [%0], %1;" ::"l"(slot), "l"(word) : "memory");
   }
-  unsigned int total = 0, bnd = 0;
+  unsigned int total = 0, bnd = 0, dtot = 0, heavy = 0;
   for (int h = 0; h < d.world; ++h) {
     const unsigned long long* slot = d.xflag[d.rank] + h;
-    unsigned long long v;
+    unsigned long long v, v2;
     unsigned long long spins = 0;
     do {
       asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
@@ -253,11 +263,16 @@ __device__ __forceinline__ unsigned int cross_gpu_exchange(const Dev& d, unsigne
         break;
       }
     } while ((unsigned int)(v >> 32) < xe);
+    asm volatile("ld.relaxed.sys.u64 %0, [%1];" : "=l"(v2) : "l"(slot + ECNE_MAX_WORLD) : "memory");  // stored before v
     unsigned int nh = (unsigned int)v & 0x7fffffffu;
     bnd |= (unsigned int)v & 0x80000000u;
     d.xcnt[list * ECNE_MAX_WORLD + h] = nh;
     total += nh;
+    dtot += (unsigned int)v2 & 0x7fffffffu;
+    heavy |= (unsigned int)v2 & 0x80000000u;
   }
+  d.xcnt[3 * ECNE_MAX_WORLD + 0] = dtot;
+  d.xcnt[3 * ECNE_MAX_WORLD + 1] = heavy ? 1u : 0u;
   if (total > 0x7fffffffu) total = 0x7fffffffu;
   return total | bnd;
 }

@@ -281,6 +281,11 @@ __device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, int wbuf, 
 // log a state change that the caller applied to BOTH buffers itself
 __device__ __forceinline__ void log_rec(const Dev& d, int pl, uint32_t w, uint32_t bits) {
   if (d.inv_head[w].x > HEAVY_DEG) atomicOr(d.bnd_flag + pl, 2u);
+  if (d.world > 1) {
+    unsigned int* word = (unsigned int*)(d.wflag[pl] + (w & ~3u));
+    const unsigned int sh = (w & 3u) * 8;
+    if (!((atomicOr(word, 1u << sh) >> sh) & 1u)) atomicAdd(d.dcnt + pl, 1u);
+  }
   unsigned int i = atomicAdd(d.rec_count + pl, 1u);
   if (i < d.rec_cap) {
     Rec r;
@@ -564,9 +569,9 @@ __device__ __forceinline__ unsigned int sync_and_load(const Dev& d, const unsign
 #define SOLO_MAX 96u    // frontiers up to this size are swept by block 0 alone (one warp per record), without grid barriers
 __device__ __forceinline__ void sparse_row(const Dev&, int rbuf, int wbuf, int list, uint32_t row,
                                            uint32_t bepoch, unsigned int gr, uint32_t* s_long,
-                                           unsigned int* s_nlong, unsigned long long& evals) {
+                                           unsigned int* s_nlong, unsigned long long& evals, bool all_rows) {
   const Dev& d = c_dev;
-  if (row == 0xffffffffu || row < d.row_lo || row >= d.row_hi) return;
+  if (row == 0xffffffffu || (!all_rows && (row < d.row_lo || row >= d.row_hi))) return;
   const uint4* rp = reinterpret_cast<const uint4*>(d.rec + row);
   const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
   const uint32_t latched = __ldcg(d.solved + row);  // in flight together with the record
@@ -598,7 +603,8 @@ __device__ __forceinline__ void sparse_row(const Dev&, int rbuf, int wbuf, int l
 // alone (record i -> thread i); otherwise record i -> block i % grid.  Returns this thread's row visits.
 __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, unsigned int list,
                                                         unsigned int prev_list, unsigned int prev_n,
-                                                        uint32_t bepoch, unsigned int gr, bool solo) {
+                                                        uint32_t bepoch, unsigned int gr, bool solo,
+                                                        bool prev_sharded) {
   const Dev& d = c_dev;
   __shared__ uint32_t s_long[SP_LONG_CAP];
   __shared__ uint32_t s_heavy[SP_HEAVY_CAP];
@@ -615,7 +621,9 @@ __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, un
   }
   __syncthreads();
   unsigned long long ev = 0;
-  const int nsrc = (d.world > 1 && prev_list < PL0) ? d.world : 1;
+  // a list written by a sharded round is spread over the ranks' buffers; one written by replicated rounds
+  // (solo, every rank evaluates every row) or by the phases is complete locally
+  const int nsrc = (d.world > 1 && prev_sharded) ? d.world : 1;
   for (int h = 0; h < nsrc; ++h) {
     const bool own = nsrc == 1 || h == d.rank;
     const Rec* pr = nsrc == 1 ? d.recs[prev_list] : d.xrecs[h][prev_list];
@@ -648,14 +656,17 @@ __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, un
           else if (q == 1) row = hd.z;
           else if (q == 2) row = hd.w;
           else row = d.inv_row[d.inv_ptr[r.wire] + q];
-          sparse_row(d, rbuf, wbuf, (int)list, row, bepoch, gr, s_long, &s_nlong, ev);
+          sparse_row(d, rbuf, wbuf, (int)list, row, bepoch, gr, s_long, &s_nlong, ev, solo);
         }
       }
 #ifdef ECNE_PROFILE
       long long q2 = clock64();
 #endif
       // the replay, by a lane that has no row to evaluate when there is one
-      if (own && lane == (hd.x < 31u ? hd.x : 31u)) apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
+      if (own && lane == (hd.x < 31u ? hd.x : 31u)) {
+        apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
+        consume_rec(d, prev_list, r.wire);
+      }
 #ifdef ECNE_PROFILE
       if (solo && threadIdx.x == 0 && gr < 2000) {
         d.prof[16000 + 4 * gr + 0] = (unsigned long long)(q1 - q0);   // record + head loads
@@ -673,7 +684,7 @@ __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, un
       const uint32_t w = s_heavy[x];
       const uint32_t lo = d.inv_ptr[w], hi = d.inv_ptr[w + 1];
       for (uint32_t q = lo + threadIdx.x; q < hi; q += blockDim.x)
-        sparse_row(d, rbuf, wbuf, (int)list, d.inv_row[q], bepoch, gr, s_long, &s_nlong, ev);
+        sparse_row(d, rbuf, wbuf, (int)list, d.inv_row[q], bepoch, gr, s_long, &s_nlong, ev, solo);
     }
   }
   __syncthreads();
@@ -691,6 +702,36 @@ __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, un
   return ev;
 }
 
+// The P2 test of one short row from its inline record and the six gathered state bytes (:1364-1385): every
+// non-unique wire appears in C only; k == 1 is decided on the spot, k >= 2 rows become candidates.
+__device__ __forceinline__ void p2_scan_short(const Dev& d, int pl, uint32_t row, const InlineRow& r, const uint32_t* ff) {
+  if (r.rf & RF_LONG) return;
+  const uint32_t nAB = r.meta & 0xffu;
+  uint32_t kk = 0, w1 = 0;
+  bool bad = false;
+  unsigned long long hs = 0, hx = 0;
+#pragma unroll
+  for (int j = 0; j < ROWREC_INLINE; ++j) {
+    if (!(ff[j] & WF_U)) {
+      if ((uint32_t)j < nAB) {
+        bad = true;
+      } else {
+        ++kk;
+        w1 = r.c[j];
+        unsigned long long mm = mix64(r.c[j]);
+        hs += mm;
+        hx ^= mix64(mm + 0x9e3779b97f4a7c15ULL);
+      }
+    }
+  }
+  if (bad || kk == 0) return;
+  if (d.solved[row] & 1) return;  // equation_solved rows take no part (:1360)
+  if (kk == 1)
+    emit(d, 1, pl, w1, WF_U | WF_K);
+  else
+    p2_candidate(d, row, hs, hx, kk);
+}
+
 // Rounds whose frontier is at most 32 records are run by WARP 0 of block 0 alone (most of ecdsa's rounds
 // change one or six wires): the (record, listed row) pairs are dealt out one per lane, a long row among
 // them is then evaluated by the whole warp, and the round boundary is __syncwarp + release fence + acquire load — no
@@ -699,13 +740,14 @@ __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, un
 #define WARP_SOLO_MAX 32u
 struct SoloState {
   unsigned int n, list, rbuf, round, bepoch, gr, hv, prev_list;
+  unsigned int dn;  // distinct wires the last round changed (== n on one GPU)
 };
 __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int prev_n, unsigned int max_rounds,
                                        unsigned long long* evals_io) {
   const Dev& d = c_dev;
   const uint32_t lane = threadIdx.x & 31u;
   unsigned int n = prev_n, list = st->list, prev_list = st->prev_list, round = st->round, bepoch = st->bepoch,
-               gr = st->gr, hv = 0;
+               gr = st->gr, hv = 0, dn = 0;
   int rbuf = (int)st->rbuf;
   unsigned long long ev = 0;
   while (true) {
@@ -751,7 +793,7 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
         else if (q == 1) row = hz;
         else if (q == 2) row = hw;
         else row = d.inv_row[d.inv_ptr[wj] + q];
-        if (row != 0xffffffffu && row >= d.row_lo && row < d.row_hi) {
+        if (row != 0xffffffffu) {  // every row, also on a sharded run: solo rounds are replicated
           const uint4* rp = reinterpret_cast<const uint4*>(d.rec + row);
           const uint4 q0v = __ldg(rp), q1v = __ldg(rp + 1);
           const uint32_t latched = __ldcg(d.solved + row);
@@ -781,19 +823,25 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
         }
       }
     }
-    if (have) apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);  // the replay
+    if (have) {  // the replay
+      apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
+      consume_rec(d, prev_list, r.wire);
+    }
     __syncwarp();
     unsigned int cnt = 0, bf = 0;
     if (lane == 0) {
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cnt) : "l"(d.rec_count + list) : "memory");
       asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(bf) : "l"(d.bnd_flag + list) : "memory");
+      if (d.world > 1) asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(dn) : "l"(d.dcnt + list) : "memory");
       d.rec_count[prev_list] = 0;  // consumed; next written two rounds from now
       d.bnd_flag[prev_list] = 0;
+      d.dcnt[prev_list] = 0;
       atomicAdd(&d.st->prog, cnt);
     }
     cnt = __shfl_sync(0xffffffffu, cnt, 0);
     bf = __shfl_sync(0xffffffffu, bf, 0);
+    dn = d.world > 1 ? __shfl_sync(0xffffffffu, dn, 0) : cnt;
     bepoch += bf & 1u;
     hv = bf & 2u;
     round += 1;
@@ -813,6 +861,7 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
     st->gr = gr;
     st->hv = hv;
     st->prev_list = prev_list;
+    st->dn = dn;
   }
 }
 
@@ -832,7 +881,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     k_solve(unsigned int max_rounds, int ks) {
   const Dev& d = c_dev;
   extern __shared__ uint4 sm_rec[];  // sm_rec[(2*k + h) * blockDim + thread]: half h of the thread's k-th record
-  __shared__ unsigned int s_solo[2];
+  __shared__ unsigned int s_solo[3];  // records, round flags, distinct wires of a solo round
   __shared__ SoloState s_ws;
   unsigned int epoch = 0;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -890,18 +939,22 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     if (outer == 1 || n_pl > 0) {
       int rbuf = 0;
       unsigned int list = 0, prev_list = (unsigned int)pl_r, prev_n = n_pl > d.rec_cap ? d.rec_cap : n_pl;
-      bool dense = outer == 1 || n_pl > d.sparse_max || (__ldcg(d.bnd_flag + pl_r) & 2u) != 0;
+      // `dn`: the number of distinct wires the previous round changed.  Mode decisions (dense / sparse /
+      // solo) use it instead of the record count on sharded runs, because it is the same on every rank
+      unsigned int prev_dn = d.world > 1 ? __ldcg(d.dcnt + pl_r) : n_pl;
+      bool prev_sharded = false;  // the phase list is complete on every rank
+      bool dense = outer == 1 || prev_dn > d.sparse_max || (__ldcg(d.bnd_flag + pl_r) & 2u) != 0;
       unsigned int round = 0;
       while (true) {
-        if (!dense && d.world == 1 && prev_n <= SOLO_MAX) {
+        if (!dense && prev_dn <= SOLO_MAX) {
           // ---- solo: while the frontier stays small, block 0 runs the Jacobi rounds alone; a round
           // boundary is a block barrier + one release fence + one acquire load (which also drops this
           // SM's L1 lines, as the grid barrier does) instead of a grid barrier
           unsigned int n = 0;
           if (blockIdx.x == 0) {
             while (true) {
-              if (prev_n <= WARP_SOLO_MAX) {
-                // one or two records: warp 0 chases them alone, for as many rounds as that stays so
+              if (prev_n <= WARP_SOLO_MAX && !prev_sharded) {
+                // at most 32 records: warp 0 chases them alone, for as many rounds as that stays so
                 if (threadIdx.x == 0) {
                   s_ws.list = list;
                   s_ws.prev_list = prev_list;
@@ -925,6 +978,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
                 bepoch = s_ws.bepoch;
                 gr = s_ws.gr;
                 s_solo[1] = s_ws.hv;
+                s_solo[2] = s_ws.dn;
 #ifdef ECNE_PROFILE
                 if (threadIdx.x == 0) {
                   long long t_ = clock64();
@@ -933,7 +987,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
                 }
 #endif
                 __syncthreads();
-                if (n == 0 || n > SOLO_MAX || (s_solo[1] & 2u) || round >= max_rounds) break;
+                if (n == 0 || s_solo[2] > SOLO_MAX || (s_solo[1] & 2u) || round >= max_rounds) break;
                 prev_list = list;
                 prev_n = n;
                 list = (list + 1) % 3;
@@ -944,7 +998,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
 #ifdef ECNE_PROFILE
               long long z0 = clock64(), z1 = 0, z2 = 0, z3 = 0, z4 = 0;
 #endif
-              const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, true);
+              const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, true, prev_sharded);
               evals += ev;
               ruleevals += ev;
 #ifdef ECNE_PROFILE
@@ -962,8 +1016,11 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
 #endif
                 asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cnt) : "l"(d.rec_count + list) : "memory");
                 asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(bf) : "l"(d.bnd_flag + list) : "memory");
+                unsigned int dnv = cnt;
+                if (d.world > 1) asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(dnv) : "l"(d.dcnt + list) : "memory");
                 s_solo[0] = cnt;
                 s_solo[1] = bf;
+                s_solo[2] = dnv;
 #ifdef ECNE_PROFILE
                 z4 = clock64();
                 if (gr < 1000) {
@@ -975,6 +1032,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
 #endif
                 d.rec_count[prev_list] = 0;  // consumed; next written two rounds from now
                 d.bnd_flag[prev_list] = 0;
+                d.dcnt[prev_list] = 0;
                 atomicAdd(&d.st->prog, cnt);
               }
               __syncthreads();
@@ -992,9 +1050,10 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
                 tp = t_;
               }
 #endif
-              if (n == 0 || n > SOLO_MAX || (s_solo[1] & 2u) || round >= max_rounds) break;
+              if (n == 0 || s_solo[2] > SOLO_MAX || (s_solo[1] & 2u) || round >= max_rounds) break;
               prev_list = list;
               prev_n = n;
+              prev_sharded = false;  // written by this (replicated) round: complete locally
               list = (list + 1) % 3;
               rbuf ^= 1;
             }
@@ -1006,6 +1065,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               d.st->solo[4] = bepoch;
               d.st->solo[5] = gr;
               d.st->solo[6] = s_solo[1] & 2u;
+              d.st->solo[7] = s_solo[2];
             }
           }
           grid_sync_flip(d.barrier + 64);
@@ -1016,6 +1076,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           bepoch = __ldcg(&d.st->solo[4]);
           gr = __ldcg(&d.st->solo[5]);
           const unsigned int hv = __ldcg(&d.st->solo[6]);
+          const unsigned int sdn = __ldcg(&d.st->solo[7]);
           PROF(7);
           if (n == 0) break;
           if (round >= max_rounds) {
@@ -1026,7 +1087,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           prev_n = n > d.rec_cap ? d.rec_cap : n;
           list = (list + 1) % 3;
           rbuf ^= 1;
-          dense = n > d.sparse_max || hv != 0;
+          prev_dn = sdn;
+          prev_sharded = false;
+          dense = sdn > d.sparse_max || hv != 0;
           continue;
         }
         const int wbuf = rbuf ^ 1;
@@ -1044,6 +1107,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
             for (uint32_t j = threadIdx.x; blockIdx.x + j * gridDim.x < prev_n; j += blockDim.x) {
               Rec r = pr[blockIdx.x + j * gridDim.x];
               apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
+              consume_rec(d, prev_list, r.wire);
             }
           }
 #ifdef ECNE_PROFILE
@@ -1139,23 +1203,27 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           }
 #endif
         } else {
-          const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, false);
+          const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, false, prev_sharded);
           evals += ev;
           ruleevals += ev;
         }
         xe += 1;
         unsigned int n;
         bool heavy = false;  // a wire with very many rows changed: sweep densely instead of chasing its list
+        unsigned int dn;
         if (d.world > 1) {
           n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list, &d, list, xe);
           bepoch += n >> 31;
           n &= 0x7fffffffu;
+          dn = __ldcg(d.xcnt + 3 * ECNE_MAX_WORLD + 0);  // distinct wires changed, summed over the ranks
+          heavy = __ldcg(d.xcnt + 3 * ECNE_MAX_WORLD + 1) != 0;
         } else {
           grid_sync_flip(d.barrier + 64);
           n = __ldcg(d.rec_count + list);
           const unsigned int bf = __ldcg(d.bnd_flag + list);
           bepoch += bf & 1u;
           heavy = (bf & 2u) != 0;
+          dn = n;
         }
         unsigned int n_own = n;
         if (d.world > 1) {
@@ -1192,6 +1260,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         if (tid == 0) {  // the list read this round is consumed; it is next written two rounds from now
           d.rec_count[prev_list] = 0;
           d.bnd_flag[prev_list] = 0;
+          d.dcnt[prev_list] = 0;
           atomicAdd(&d.st->prog, n);
         }
         if (n_own > d.rec_cap) n_own = d.rec_cap;
@@ -1204,7 +1273,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         prev_n = n_own;
         list = (list + 1) % 3;
         rbuf = wbuf;
-        dense = n > d.sparse_max || heavy;
+        prev_dn = dn;
+        prev_sharded = d.world > 1;  // a grid round on a sharded run leaves its records spread over the ranks
+        dense = dn > d.sparse_max || heavy;
       }
       rounds_total += round;
     }
@@ -1244,48 +1315,34 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
             for (int j = 0; j < ROWREC_INLINE; ++j)
               ff[h][j] = (rr[h].meta & 0x10000u) ? ld_flag(F, rr[h].c[j]) : (uint32_t)WF_U;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (kk2[h] < 0) continue;
-            const InlineRow& r = rr[h];
-            const uint32_t row = d.row_lo + tid + (uint32_t)kk2[h] * nthreads;
-            if (r.rf & RF_LONG) continue;
-            const uint32_t nAB = r.meta & 0xffu;
-            uint32_t kk = 0, w1 = 0;
-            bool bad = false;
-            unsigned long long hs = 0, hx = 0;
-#pragma unroll
-            for (int j = 0; j < ROWREC_INLINE; ++j) {
-              if (!(ff[h][j] & WF_U)) {
-                if ((uint32_t)j < nAB) {
-                  bad = true;
-                } else {
-                  ++kk;
-                  w1 = r.c[j];
-                  unsigned long long mm = mix64(r.c[j]);
-                  hs += mm;
-                  hx ^= mix64(mm + 0x9e3779b97f4a7c15ULL);
-                }
-              }
-            }
-            if (bad || kk == 0) continue;
-            if (d.solved[row] & 1) continue;  // equation_solved rows take no part (:1360)
-            if (kk == 1)
-              emit(d, 1, pl, w1, WF_U | WF_K);
-            else
-              p2_candidate(d, row, hs, hx, kk);
-          }
+          for (int h = 0; h < 2; ++h)
+            if (kk2[h] >= 0) p2_scan_short(d, pl, d.row_lo + tid + (uint32_t)kk2[h] * nthreads, rr[h], ff[h]);
         }
         for (uint32_t k = kmask; k < per_thread; ++k) {
           uint32_t r = tid + k * nthreads;
           if (r < rows && !(d.rflags[d.row_lo + r] & RF_LONG) && !(d.solved[d.row_lo + r] & 1))
             p2_scan_row<1>(d, 0, pl, d.row_lo + r);
         }
-      } else {  // sharded: every rank scans every row (same candidates everywhere)
-        for (uint32_t row = tid; row < d.N; row += nthreads)
-          if (!(d.rflags[row] & RF_LONG) && !(d.solved[row] & 1)) {
-            p2_scan_row<1>(d, 0, pl, row);
-            if (row >= d.row_lo && row < d.row_hi) evals += 1;  // replicated work is counted once
-          }
+      } else {
+        // sharded: every rank scans every row (same candidates everywhere, no exchange), streaming the
+        // inline row records from HBM/L2, two rows in flight
+        for (uint32_t row0 = tid; row0 < d.N; row0 += 2 * nthreads) {
+          const uint32_t row1 = row0 + nthreads;
+          const bool two = row1 < d.N;
+          InlineRow rr[2];
+          uint32_t ff[2][ROWREC_INLINE];
+          load_row(d, row0, rr[0]);
+          load_row(d, two ? row1 : row0, rr[1]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < ROWREC_INLINE; ++j)
+              ff[h][j] = (rr[h].meta & 0x10000u) ? ld_flag(F, rr[h].c[j]) : (uint32_t)WF_U;
+          p2_scan_short(d, pl, row0, rr[0], ff[0]);
+          if (two) p2_scan_short(d, pl, row1, rr[1], ff[1]);
+          // replicated work is counted once, by the rank that owns the row
+          evals += (row0 >= d.row_lo && row0 < d.row_hi) + (two && row1 >= d.row_lo && row1 < d.row_hi);
+        }
       }
 #ifdef ECNE_PROFILE
       pz1 = clock64();
@@ -1513,6 +1570,9 @@ cudaError_t launch_reset(const Dev& d, int grid, cudaStream_t s) {
   if (d.n_long) cudaMemsetAsync(d.long_p2, 0, (size_t)d.n_long * sizeof(LongP2), s);
   if (d.n_specials) cudaMemsetAsync(d.sp_solved, 0, d.n_specials, s);
   cudaMemsetAsync(d.rec_count, 0, 8 * sizeof(unsigned int), s);
+  cudaMemsetAsync(d.dcnt, 0, 8 * sizeof(unsigned int), s);
+  if (d.world > 1)
+    for (int l = 0; l < 5; ++l) cudaMemsetAsync(d.wflag[l], 0, (size_t)d.V + 8, s);
   cudaMemsetAsync(d.bnd_flag, 0, 8 * sizeof(unsigned int), s);
   cudaMemsetAsync(d.c5sig, 0xff, (size_t)(d.N ? d.N : 1) * sizeof(uint32_t), s);
   cudaMemsetAsync(d.st, 0, sizeof(Status), s);

@@ -1117,6 +1117,8 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   d.rec_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2 * V, nnz) + 4096, 0x7ffffff0ULL);
   for (int l = 0; l < 5; ++l) CK(A.alloc(&d.recs[l], d.rec_cap));
   CK(A.alloc(&d.rec_count, 8));
+  CK(A.alloc(&d.dcnt, 8));
+  for (int l = 0; l < 5; ++l) CK(A.alloc(&d.wflag[l], V + 8));
   CK(A.alloc(&d.bnd_flag, 8));
   CK(A.alloc(&d.c5sig, N));
   CK(A.alloc(&d.barrier, 128));

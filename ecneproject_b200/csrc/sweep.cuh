@@ -55,6 +55,14 @@ __device__ __forceinline__ void apply_update(const Dev&, int buf, uint32_t w, ui
                                              uint32_t ubr) {
   apply_update_t<false>(buf, w, bits, lbr, ubr);
 }
+// a record of list `list` has been consumed (replayed): its wire may be counted again when the list is
+// written next (two rounds from now)
+__device__ __forceinline__ void consume_rec(const Dev& d, unsigned int list, uint32_t w) {
+  if (d.world > 1) {
+    unsigned int* word = (unsigned int*)(d.wflag[list] + (w & ~3u));
+    atomicAnd(word, ~(0xffu << ((w & 3u) * 8)));
+  }
+}
 
 // Apply an update to the write buffer and, when it changed anything there, log it for the other
 // buffer.  A row only calls this when its evaluation against the snapshot wants something the snapshot
@@ -71,6 +79,11 @@ __device__ __noinline__ void emit_impl(int wbuf, int list, uint32_t w, uint32_t 
   const uint32_t want = ((r & 2u) ? 1u : 0u) | (((r & 1u) && (r & 4u)) ? 2u : 0u);
   if (want && (__ldcg(d.bnd_flag + list) & want) != want) atomicOr(d.bnd_flag + list, want);
   if (!(r & 1u)) return;
+  if (d.world > 1) {  // sharded runs count the distinct wires a round changed (same number on every rank)
+    unsigned int* word = (unsigned int*)(d.wflag[list] + (w & ~3u));
+    const unsigned int sh = (w & 3u) * 8;
+    if (!((atomicOr(word, 1u << sh) >> sh) & 1u)) atomicAdd(d.dcnt + list, 1u);
+  }
   // warp-aggregated slot allocation: the lanes that reach this point together take one atomic (a round
   // that changes 300 k wires would otherwise serialise 300 k RMWs on one L2 address)
   const unsigned int am = __activemask();
