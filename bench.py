@@ -408,7 +408,7 @@ def main():
         "dtype": "u256 (4x64-bit limbs, BN254 scalar field; sweep works on u8/u32 state)",
         "data": "real circuit (reference fixture ecdsa.r1cs), no synthetic data needed",
         "config": {"workload": WORKLOAD_NAME, "rows": reduced.n_rows, "rows_before_abstraction": main.n_rows,
-                   "wires": main.n_vars, "nnz": nnz_nonzero, "evals_per_step": evals,
+                   "wires": main.n_vars, "nnz": nnz_nonzero, "evals_per_step": total_evals,
                    "outer_rounds": outer, "jacobi_rounds": rounds, "verdict": verdict, "n_unique": n_unique,
                    "rule_evals_per_step": rule_evals,
                    "l2": "flushed between timed steps (256 MB fill)",

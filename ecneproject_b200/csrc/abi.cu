@@ -249,8 +249,8 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   }
   d.max_outer = (uint32_t)std::min<long long>(G.max_outer, 0x7fffffffLL);
   {
-    const uint32_t rows = d.row_hi - d.row_lo;
-    const long long sm = G.sparse_max >= 0 ? G.sparse_max : std::max<long long>(4096, rows / 32);
+    // from the whole problem, not the shard: every rank must take the same dense / sparse decision
+    const long long sm = G.sparse_max >= 0 ? G.sparse_max : std::max<long long>(4096, (long long)d.N / 32);
     d.sparse_max = (uint32_t)std::min<long long>(sm, 0x7fffffffLL);
   }
   int status = ECNE_OK;
@@ -322,7 +322,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   // the kernel), P3 / P4 the rows with the ABZ / IsZero shape
   const unsigned long long rounds_total = R.h_status->rounds, evals_total = R.h_status->evals,
                            rule_evals_total = R.h_status->rule_evals;
-  const uint64_t phase_evals = outer * ((uint64_t)d.n_p3 + d.n_p4);
+  const uint64_t phase_evals = d.rank == 0 ? outer * ((uint64_t)d.n_p3 + d.n_p4) : 0;  // replicated: counted once
   cudaEventRecord(e1, s);
   res->status = status;
   if (status != ECNE_OK) {

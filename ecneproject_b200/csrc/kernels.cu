@@ -967,8 +967,10 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
                 if (warp_in_block == 0) {
                   unsigned long long ev = 0;
                   warp_solo(d, &s_ws, prev_n, max_rounds, &ev);
-                  evals += ev;
-                  ruleevals += ev;
+                  if (d.rank == 0) {  // replicated work is counted once
+                    evals += ev;
+                    ruleevals += ev;
+                  }
                 }
                 __syncthreads();
                 n = s_ws.n;
@@ -999,8 +1001,10 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               long long z0 = clock64(), z1 = 0, z2 = 0, z3 = 0, z4 = 0;
 #endif
               const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, true, prev_sharded);
-              evals += ev;
-              ruleevals += ev;
+              if (d.rank == 0) {  // replicated work is counted once
+                evals += ev;
+                ruleevals += ev;
+              }
 #ifdef ECNE_PROFILE
               z1 = clock64();
 #endif
