@@ -3,7 +3,9 @@
 // Layout.  Everything is SoA and sized once per problem:
 //   rows   seg[3N+1] u32 | rflags[N] u32 | aux[N] 32 B | col[nnz] u32 | coef[nnz] 32 B (canonical)
 //          only NON-ZERO terms; C terms of linear rows are stored sorted by |fold(coef)| (Case 5)
-//   wires  F[2][V+4] u8  (U,K,ABZ bits; OR-monotone)    B[2][V+4] u8 (derived "bounds == [0,1]")
+//          rec[N] 32 B row records (flags + <= 6 inline wires): what the solve kernel streams
+//          inv_head[V+2] 16 B | inv_ptr | inv_row   wire -> rows index (the frontier of a sparse round)
+//   wires  F[2][V+4] u8  (U, K, ABZ, BND, UB01/NOT01, HEAVY bits; OR-monotone)
 //          LBR/UBR[2][V+1] u32 ranks into the sorted table of every bound value that can occur
 //          abz[V+1] i32 | valsrc[V+1] u32
 //   double buffering: a Jacobi round reads buffer R and writes buffer W; the update records of a
@@ -92,7 +94,7 @@ struct __align__(16) LongP2 {
   uint32_t k, w1, gr, bad;
 };
 
-struct Status {            // device-resident, read back once per outer round
+struct Status {            // device-resident, read back once per solve
   unsigned long long changed;      // state changes of the current outer round ("successful_steps")
   unsigned long long rounds;       // Jacobi rounds of the single-row sweep
   unsigned long long evals;        // rows visited
@@ -126,7 +128,6 @@ struct Dev {
   const uint32_t* long_rows;
   uint8_t* long_done;        // per long row: can never fire again
   const RowRec* rec;
-  unsigned long long* live;  // per sweep thread: bitmask of its rows that can still fire
   uint8_t* solved;
   // static values
   const fr::u256* roots;  // [n2a][2]
@@ -179,7 +180,7 @@ struct Dev {
   unsigned long long* abz_claim;  // [V+1]
   uint32_t* p2_row;               // [N]
   unsigned int* barrier;          // grid barrier counter
-  unsigned long long* prof;       // [grid][8] per-block cycle counters (ECNE_PROFILE builds only)
+  unsigned long long* prof;       // per-round / per-block cycle counters (ECNE_PROFILE builds, ECNE_DEBUG_PROF)
   Status* st;
   // sharding: this rank sweeps rows [row_lo, row_hi)
   uint32_t row_lo, row_hi;

@@ -1044,7 +1044,6 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(A.alloc(&d_rec, N));
   if (N) k_rowrec<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_segnz, d_col, d_rflags, d_rec);
   if (cnt.n_long) k_long_index<<<nb(cnt.n_long, 256), 256, 0, s>>>(cnt.n_long, d_long, d_rec);
-  CK(A.alloc(&d.live, (size_t)p1_grid_size(0) * p1_threads()));
   CK(A.alloc(&d.long_done, (size_t)cnt.n_long));
   CK(A.alloc(&d.long_stamp, (size_t)cnt.n_long));
   CK(A.alloc(&d.long_p2, (size_t)cnt.n_long));
