@@ -52,7 +52,7 @@ def build_host(force=False, verbose=False):
     src = [os.path.join(CSRC, "host_r1cs.cpp")]
     deps = src + _sources(INC, (".h",))
     if force or _newer(HOST_SO, deps):
-        _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", INC, "-o", HOST_SO] + src, verbose)
+        _run(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-I", INC, "-o", HOST_SO] + src, verbose)
     return HOST_SO
 
 

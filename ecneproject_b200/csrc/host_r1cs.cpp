@@ -8,6 +8,11 @@
 #include "ecne_host.h"
 #include "ecne_abi.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +20,7 @@
 #include <map>
 #include <string>
 #include <unordered_map>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -61,6 +67,28 @@ inline uint32_t rd32(const uint8_t* p) {
   return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 inline uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+
+// Run fn(begin, end) over [0, n) on the host cores (the reference is single-threaded Julia; this is the
+// optional fast path of SURVEY.md §8f, and a 142 MB circuit is mostly memory traffic).
+template <class Fn>
+void parallel_chunks(uint64_t n, uint64_t min_chunk, Fn fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 1;
+  uint64_t nt = std::min<uint64_t>(hw, std::max<uint64_t>(1, n / std::max<uint64_t>(1, min_chunk)));
+  if (nt <= 1) {
+    fn((uint64_t)0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const uint64_t per = (n + nt - 1) / nt;
+  for (uint64_t t = 0; t < nt; ++t) {
+    const uint64_t b = t * per, e = std::min(n, b + per);
+    if (b >= e) break;
+    th.emplace_back([=]() { fn(b, e); });
+  }
+  for (auto& x : th) x.join();
+}
 
 template <class T>
 T* dup_vec(const std::vector<T>& v) {
@@ -136,6 +164,97 @@ extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t*
   uint32_t n_cons = rd32(arr + s1 + 24);
 
   uint64_t s2 = starts[2] + 12;
+  {
+    // Fast path: one serial walk over the per-form term counts fixes every offset, then the host cores
+    // fill the arrays in place.  A form that repeats a wire (Dict assignment overwrites, ParseR1CS.jl:110)
+    // changes the lengths: such files take the serial path below.
+    const uint64_t nseg = 3 * (uint64_t)n_cons;
+    uint64_t* segp = (uint64_t*)malloc((nseg + 1) * sizeof(uint64_t));
+    std::vector<uint64_t> raw(nseg);
+    uint64_t pos = s2, total = 0;
+    bool ok = segp != nullptr;
+    for (uint64_t sgi = 0; ok && sgi < nseg; ++sgi) {
+      if (!need(pos, 4)) { ok = false; break; }
+      const uint32_t n = rd32(arr + pos);
+      if (!need(pos + 4, (uint64_t)n * 36)) { ok = false; break; }
+      raw[sgi] = pos;
+      segp[sgi] = total;
+      total += n ? n : 1;
+      pos += 4 + (uint64_t)n * 36;
+    }
+    if (ok && total < 0x7fffffffULL) {
+      segp[nseg] = total;
+      uint32_t* colp = (uint32_t*)malloc(std::max<uint64_t>(1, total) * sizeof(uint32_t));
+      uint64_t* coefp = (uint64_t*)malloc(std::max<uint64_t>(1, total) * 4 * sizeof(uint64_t));
+      std::vector<uint8_t> dup_flag(1, 0);
+      uint8_t* dupf = dup_flag.data();
+      const uint64_t* rawp = raw.data();
+      parallel_chunks(nseg, 1 << 14, [=](uint64_t b, uint64_t e) {
+        std::vector<uint32_t> tmp;
+        for (uint64_t sgi = b; sgi < e; ++sgi) {
+          const uint8_t* q = arr + rawp[sgi];
+          const uint32_t n = rd32(q);
+          q += 4;
+          uint64_t o = segp[sgi];
+          if (n == 0) {  // explicit zero on key 1 (ParseR1CS.jl:113-115)
+            colp[o] = 1;
+            coefp[4 * o] = coefp[4 * o + 1] = coefp[4 * o + 2] = coefp[4 * o + 3] = 0;
+            continue;
+          }
+          for (uint32_t t = 0; t < n; ++t, q += 36, ++o) {
+            uint64_t c[4];
+            memcpy(c, q + 4, 32);       // 32 bytes hard-coded (ParseR1CS.jl:109)
+            while (geq_p(c)) sub_p(c);  // F(coeff) reduces (ParseR1CS.jl:111)
+            colp[o] = rd32(q) + 1;
+            memcpy(coefp + 4 * o, c, 32);
+          }
+          if (n > 1) {  // a repeated wire?
+            const uint32_t* cc = colp + segp[sgi];
+            bool dup = false;
+            if (n <= 8) {
+              for (uint32_t i = 0; i < n && !dup; ++i)
+                for (uint32_t j = i + 1; j < n; ++j)
+                  if (cc[i] == cc[j]) { dup = true; break; }
+            } else {
+              tmp.assign(cc, cc + n);
+              std::sort(tmp.begin(), tmp.end());
+              for (uint32_t i = 1; i < n; ++i)
+                if (tmp[i] == tmp[i - 1]) { dup = true; break; }
+            }
+            if (dup) *dupf = 1;  // benign race: every writer stores 1
+          }
+        }
+      });
+      if (!dup_flag[0]) {
+        ecne_r1cs_t* r = (ecne_r1cs_t*)calloc(1, sizeof(ecne_r1cs_t));
+        r->n_rows = n_cons;
+        r->n_vars = (uint64_t)n_wires + 1;
+        r->nnz = total;
+        r->seg_ptr = segp;
+        r->col = colp;
+        r->coef = coefp;
+        std::vector<uint32_t> known, targets;
+        known.push_back(1);
+        for (uint64_t i = 2 + (uint64_t)pub_out; i <= 1 + (uint64_t)pub_out + pub_in + prv_in; ++i)
+          known.push_back((uint32_t)i);
+        for (uint64_t i = 2; i <= 1 + (uint64_t)pub_out; ++i) targets.push_back((uint32_t)i);
+        r->known = dup_vec(known);
+        r->n_known = known.size();
+        r->targets = dup_vec(targets);
+        r->n_targets = targets.size();
+        r->n_pub_out = pub_out;
+        r->n_pub_in = pub_in;
+        r->n_prv_in = prv_in;
+        r->field_size = field_size;
+        r->n_labels = n_labels;
+        *out = r;
+        return ECNE_OK;
+      }
+      free(colp);
+      free(coefp);
+    }
+    free(segp);  // truncated file or repeated wires: the serial walk below reports / handles it
+  }
   std::vector<uint64_t> seg;
   seg.reserve(3 * (size_t)n_cons + 1);
   std::vector<uint32_t> col;
@@ -214,16 +333,26 @@ extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t*
 
 extern "C" int ecne_read_r1cs(const char* path, ecne_r1cs_t** out) {
   if (!path || !out) return fail(ECNE_E_BADARG, "null argument");
-  FILE* f = fopen(path, "rb");
-  if (!f) return fail(ECNE_E_IO, std::string("cannot open ") + path);
-  fseek(f, 0, SEEK_END);
-  long sz = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  std::vector<uint8_t> buf((size_t)sz);
-  size_t got = sz ? fread(buf.data(), 1, (size_t)sz, f) : 0;
-  fclose(f);
-  if (got != (size_t)sz) return fail(ECNE_E_IO, std::string("short read on ") + path);
-  return ecne_read_r1cs_mem(buf.data(), buf.size(), out);
+  // map the file instead of copying it: the parser touches every byte exactly once
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(ECNE_E_IO, std::string("cannot open ") + path);
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    return fail(ECNE_E_IO, std::string("cannot stat ") + path);
+  }
+  const size_t sz = (size_t)st.st_size;
+  if (sz == 0) {
+    close(fd);
+    uint8_t none = 0;
+    return ecne_read_r1cs_mem(&none, 0, out);
+  }
+  void* m = mmap(nullptr, sz, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return fail(ECNE_E_IO, std::string("cannot map ") + path);
+  const int st_code = ecne_read_r1cs_mem((const uint8_t*)m, sz, out);
+  munmap(m, sz);
+  return st_code;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -379,7 +508,13 @@ extern "C" int ecne_abstraction(int32_t kind, const ecne_r1cs_t* cons, const ecn
   const uint64_t N = cons->n_rows, n = sub->n_rows;
   std::vector<Fe> t1, t2;
   std::vector<uint64_t> hc(N), hs(n);
-  for (uint64_t i = 0; i < N; ++i) hc[i] = row_hash(cons, i, t1);
+  {  // row hashes on the host cores (each worker with its own scratch)
+    uint64_t* hcp = hc.data();
+    parallel_chunks(N, 1 << 13, [=](uint64_t b, uint64_t e) {
+      std::vector<Fe> tmp;
+      for (uint64_t i = b; i < e; ++i) hcp[i] = row_hash(cons, i, tmp);
+    });
+  }
   for (uint64_t i = 0; i < n; ++i) hs[i] = row_hash(sub, i, t1);
 
   // candidates: the first n-1 row hashes line up (:259-270)
@@ -396,74 +531,112 @@ extern "C" int ecne_abstraction(int32_t kind, const ecne_r1cs_t* cons, const ecn
       if (ok) candidates.push_back(i);
     }
   }
-  std::vector<VarSig> orig, curv;
+  std::vector<VarSig> orig;
   appearance(sub, 0, n, orig);
   struct Match {
     uint64_t start;
+    bool works;
     std::unordered_map<uint32_t, uint32_t> map;  // sub wire -> main wire
   };
-  std::vector<Match> matches;
-  for (uint64_t i : candidates) {
-    bool works = true;
-    for (uint64_t j = 0; j < n && works; ++j)
-      for (int f = 0; f < 3; ++f)
-        if (!same_nonzero_multiset(cons, 3 * (i + j) + f, sub, 3 * j + f, t1, t2)) {
-          works = false;
-          break;
+  // every candidate is verified independently (:301-351): coefficient multisets per slot, then the
+  // per-variable appearance signatures
+  std::vector<Match> verified(candidates.size());
+  {
+    Match* vp = verified.data();
+    const uint64_t* cp = candidates.data();
+    const std::vector<VarSig>* origp = &orig;
+    parallel_chunks(candidates.size(), 1, [=](uint64_t b, uint64_t e) {
+      std::vector<Fe> u1, u2;
+      std::vector<VarSig> curv;
+      for (uint64_t ci = b; ci < e; ++ci) {
+        const uint64_t i = cp[ci];
+        Match& m = vp[ci];
+        m.start = i;
+        m.works = true;
+        for (uint64_t j = 0; j < n && m.works; ++j)
+          for (int f = 0; f < 3; ++f)
+            if (!same_nonzero_multiset(cons, 3 * (i + j) + f, sub, 3 * j + f, u1, u2)) {
+              m.works = false;
+              break;
+            }
+        if (!m.works) continue;
+        appearance(cons, i, n, curv);
+        if (curv.size() != origp->size()) {
+          m.works = false;
+          continue;
         }
-    if (!works) continue;
-    appearance(cons, i, n, curv);
-    if (curv.size() != orig.size()) continue;
-    for (size_t k = 0; k < curv.size(); ++k)
-      if (cmp_sig(curv[k].sig, orig[k].sig) != 0) {
-        works = false;
-        break;
+        for (size_t k = 0; k < curv.size(); ++k)
+          if (cmp_sig(curv[k].sig, (*origp)[k].sig) != 0) {
+            m.works = false;
+            break;
+          }
+        if (!m.works) continue;
+        for (size_t k = 0; k < curv.size(); ++k) m.map.emplace((*origp)[k].var, curv[k].var);
       }
-    if (!works) continue;
-    Match m;
-    m.start = i;
-    for (size_t k = 0; k < curv.size(); ++k) m.map.emplace(orig[k].var, curv[k].var);
-    matches.push_back(std::move(m));
+    });
   }
+  std::vector<Match> matches;
+  for (auto& m : verified)
+    if (m.works) matches.push_back(std::move(m));
 
-  // the walk (:357-388), including the stall after an overlapping match (:370)
-  std::vector<uint64_t> seg;
-  std::vector<uint32_t> col;
-  std::vector<uint64_t> coef;
-  seg.push_back(0);
-  size_t cur = 0;
-  uint64_t i = 0, added = 0;
-  while (i < N) {
-    if (cur >= matches.size() || i != matches[cur].start) {
-      for (int f = 0; f < 3; ++f) {
-        uint64_t s = 3 * i + f;
-        col.insert(col.end(), cons->col + cons->seg_ptr[s], cons->col + cons->seg_ptr[s + 1]);
-        coef.insert(coef.end(), cons->coef + 4 * cons->seg_ptr[s],
-                    cons->coef + 4 * cons->seg_ptr[s + 1]);
-        seg.push_back(col.size());
-      }
-      i += 1;
-    } else {
-      std::vector<uint32_t> in, outv;
-      for (uint64_t k = 0; k < sub->n_known; ++k) {
-        uint32_t x = sub->known[k];
-        if (x == 1) continue;
-        auto it = matches[cur].map.find(x);
-        if (it == matches[cur].map.end())
-          return fail(ECNE_E_KEYERROR, "KeyError: trusted input wire never appears (:381)");
-        in.push_back(it->second);
-      }
-      for (uint64_t k = 0; k < sub->n_targets; ++k) {
-        auto it = matches[cur].map.find(sub->targets[k]);
-        if (it == matches[cur].map.end())
-          return fail(ECNE_E_KEYERROR, "KeyError: trusted output wire never appears (:382)");
-        outv.push_back(it->second);
-      }
-      specials_push(specials, kind, in, outv);
-      ++added;
-      i += n;
+  // the walk (:357-388), including the stall after an overlapping match (:370): first which windows it
+  // consumes, then the output is sized once and the kept runs of rows are copied
+  std::vector<uint64_t> consumed;  // indices into matches
+  {
+    size_t cur = 0;
+    uint64_t i = 0;
+    while (i < N && cur < matches.size()) {
+      if (matches[cur].start < i) break;  // starts inside a consumed window: cur never advances again
+      i = matches[cur].start + n;         // rows up to the window are kept, the window is replaced
+      consumed.push_back(cur);
       cur += 1;
     }
+  }
+  uint64_t added = 0;
+  for (uint64_t ci : consumed) {
+    std::vector<uint32_t> in, outv;
+    for (uint64_t k = 0; k < sub->n_known; ++k) {
+      uint32_t x = sub->known[k];
+      if (x == 1) continue;
+      auto it = matches[ci].map.find(x);
+      if (it == matches[ci].map.end())
+        return fail(ECNE_E_KEYERROR, "KeyError: trusted input wire never appears (:381)");
+      in.push_back(it->second);
+    }
+    for (uint64_t k = 0; k < sub->n_targets; ++k) {
+      auto it = matches[ci].map.find(sub->targets[k]);
+      if (it == matches[ci].map.end())
+        return fail(ECNE_E_KEYERROR, "KeyError: trusted output wire never appears (:382)");
+      outv.push_back(it->second);
+    }
+    specials_push(specials, kind, in, outv);
+    ++added;
+  }
+  const uint64_t rows_out = N - (uint64_t)consumed.size() * n;
+  uint64_t terms_out = cons->seg_ptr[3 * N];
+  for (uint64_t ci : consumed)
+    terms_out -= cons->seg_ptr[3 * (matches[ci].start + n)] - cons->seg_ptr[3 * matches[ci].start];
+  std::vector<uint64_t> seg(3 * rows_out + 1);
+  std::vector<uint32_t> col(terms_out);
+  std::vector<uint64_t> coef(4 * terms_out);
+  {
+    uint64_t row_dst = 0, term_dst = 0, row_src = 0;
+    auto copy_run = [&](uint64_t r0, uint64_t r1) {  // rows [r0, r1) of cons are kept
+      if (r1 <= r0) return;
+      const uint64_t t0 = cons->seg_ptr[3 * r0], t1e = cons->seg_ptr[3 * r1];
+      memcpy(col.data() + term_dst, cons->col + t0, (t1e - t0) * sizeof(uint32_t));
+      memcpy(coef.data() + 4 * term_dst, cons->coef + 4 * t0, (t1e - t0) * 4 * sizeof(uint64_t));
+      for (uint64_t sgi = 3 * r0; sgi < 3 * r1; ++sgi)
+        seg[3 * row_dst + (sgi - 3 * r0)] = cons->seg_ptr[sgi] - t0 + term_dst;
+      row_dst += r1 - r0;
+      term_dst += t1e - t0;
+    };
+    for (uint64_t ci : consumed) {
+      copy_run(row_src, matches[ci].start);
+      row_src = matches[ci].start + n;
+    }
+    copy_run(row_src, N);
+    seg[3 * rows_out] = term_dst;
   }
   std::vector<uint32_t> known(cons->known, cons->known + cons->n_known);
   std::vector<uint32_t> targets(cons->targets, cons->targets + cons->n_targets);
