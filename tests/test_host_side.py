@@ -112,3 +112,69 @@ def test_abstraction_no_match_is_identity():
     sp, red = api.abstraction("x", main, sub)
     assert len(sp) == 0 and red.n_rows == main.n_rows
     assert np.array_equal(red.col, main.col) and np.array_equal(red.coef, main.coef)
+
+
+def _mk_r1cs(rows, n_wires, pub_out=1, pub_in=1, prv_in=1):
+    """Serialise rows = [(A, B, C)] with each form a list of (wire0, int) into the iden3 .r1cs layout
+    (ParseR1CS.jl:50-124); wire ids are 0-based on disk."""
+    cons = b""
+    for forms in rows:
+        for form in forms:
+            cons += len(form).to_bytes(4, "little")
+            for w, c in form:
+                cons += w.to_bytes(4, "little") + (c % (1 << 256)).to_bytes(32, "little")
+    prime = (21888242871839275222246405745257275088548364400416034343698204186575808495617).to_bytes(32, "little")
+    hdr = (32).to_bytes(4, "little") + prime + n_wires.to_bytes(4, "little") + pub_out.to_bytes(4, "little") + \
+        pub_in.to_bytes(4, "little") + prv_in.to_bytes(4, "little") + (n_wires).to_bytes(8, "little") + \
+        len(rows).to_bytes(4, "little")
+    wmap = b"".join(i.to_bytes(8, "little") for i in range(n_wires))
+    out = b"r1cs" + (1).to_bytes(4, "little") + (3).to_bytes(4, "little")
+    for ty, body in ((1, hdr), (2, cons), (3, wmap)):
+        out += ty.to_bytes(4, "little") + len(body).to_bytes(8, "little") + body
+    return out
+
+
+def _read_mem(blob):
+    lib = _abi.host_lib()
+    out = C.POINTER(_abi.R1CSStruct)()
+    buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+    st = lib.ecne_read_r1cs_mem(buf, len(blob), C.byref(out))
+    return st, (api.R1CS(out) if st == 0 else None)
+
+
+def test_loader_edge_forms():
+    """Empty forms store an explicit zero on key 1 (ParseR1CS.jl:113-115), coefficients >= p are reduced
+    (:111), a wire repeated inside one form keeps its LAST value (Dict assignment, :110) — the last case takes
+    the serial path of the loader, the others its parallel fast path."""
+    from helpers import P
+    rows = [
+        ([(1, 3)], [(2, 5)], []),                                  # empty C
+        ([], [], [(3, P + 7), (1, 2 * P + 1)]),                    # values above p
+        ([(2, 1), (2, 9)], [(1, 1)], [(3, 1), (1, 4), (3, 6)]),    # repeated wires
+    ] + [([(1, 1)], [(2, 1)], [(k % 4, k + 1) for k in range(12)])]  # a longer form with repeats (sort path)
+    st, r = _read_mem(_mk_r1cs(rows, n_wires=4))
+    assert st == 0
+    coef = from_limbs(r.coef)
+
+    def form(i, f):
+        s, e = int(r.seg_ptr[3 * i + f]), int(r.seg_ptr[3 * i + f + 1])
+        return {int(r.col[t]): coef[t] for t in range(s, e)}, e - s
+    assert form(0, 2) == ({1: 0}, 1)
+    assert form(1, 0) == ({1: 0}, 1) and form(1, 1) == ({1: 0}, 1)
+    assert form(1, 2)[0] == {4: 7, 2: 1}
+    assert form(2, 0) == ({3: 9}, 1)                 # the later value wins, one key
+    assert form(2, 2)[0] == {4: 6, 2: 4}
+    assert form(3, 2)[0] == {1: 9, 2: 10, 3: 11, 4: 12}
+    assert r.known.tolist() == [1, 3, 4] and r.targets.tolist() == [2]
+    # the same content without repeated wires goes through the fast path and must agree form by form
+    st2, r2 = _read_mem(_mk_r1cs(rows[:2], n_wires=4))
+    assert st2 == 0 and r2.n_rows == 2
+    assert r2.seg_ptr.tolist() == r.seg_ptr[:7].tolist()
+    assert r2.col.tolist() == r.col[:int(r.seg_ptr[6])].tolist()
+
+
+def test_loader_truncated_file_is_a_bounds_error():
+    blob = _mk_r1cs([([(1, 3)], [(2, 5)], [(3, 1)])] * 4, n_wires=4)
+    for cut in (len(blob) - 8 * 4 - 20, len(blob) - 8 * 4 - 12 - 36 * 5, 40, 11):
+        st, _ = _read_mem(blob[:cut])
+        assert st in (_abi.ECNE_E_BOUNDS, _abi.ECNE_E_ASSERT), (cut, st)
