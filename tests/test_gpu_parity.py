@@ -272,3 +272,23 @@ def test_tiled_system_is_repeated_bitmap():
         assert np.array_equal(ut[1 + k * (V - 1): 1 + (k + 1) * (V - 1)], ub[1:]), k
     assert res.verdict is True and res.c.n_targets_unique == K * base.c.n_targets_unique
     assert res.c.outer_rounds == base.c.outer_rounds and res.c.inner_rounds == base.c.inner_rounds
+
+
+@pytest.mark.parametrize("name", ["secp256k1+bmmp+blt", "root/poseidon", "circomlib/EdDSAPoseidonVerifier@eddsaposeidon"])
+def test_repeated_solves_are_bit_stable(name):
+    """The solve kernel switches between dense, grid-sparse, block-solo and warp-solo rounds on counts that
+    depend on which of two racing rows logs a wire first; the STATE it reaches must not: 12 solves of the
+    same resident problem give the same bitmaps and round counts (tools/stress.py does this at length)."""
+    (reduced, specials, main), secp = prepare(name)
+    lib = api._engine()
+    ph = api.ProblemHandle(reduced, specials, main.known, main.targets, main.n_vars, secp)
+    h = C.c_void_p()
+    assert lib.ecne_upload(C.byref(ph.c), C.byref(h)) == 0
+    seen = set()
+    for _ in range(12):
+        res = api.SolveResult(main.n_vars)
+        assert lib.ecne_solve_resident(h, C.byref(res.c)) == 0
+        seen.add((res.unique_bytes(), res.known_bytes(), int(res.c.inner_rounds), int(res.c.outer_rounds)))
+    lib.ecne_free_resident(h)
+    assert len(seen) == 1
+    assert hashlib.sha256(next(iter(seen))[0]).hexdigest() == GOLD[name]["sha_unique"]
