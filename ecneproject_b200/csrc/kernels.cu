@@ -7,6 +7,7 @@
 //                 round's update records through a wire -> rows index; every step ends in a grid barrier
 //                 whose release carries the device-wide count the next step needs
 //   k_pack/...    verdict (:1558-1597) + packed bitmaps for the D2H
+#include <algorithm>
 #include <cstring>
 
 #include "engine_host.h"
@@ -1536,21 +1537,47 @@ __global__ void k_export(Dev d, int buf, fr::u256* lb, fr::u256* ub, uint8_t* nv
 }
 
 // ---- state reset ----------------------------------------------------------------------------
-__global__ void k_reset_wires(Dev d) {
-  uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w > d.V + 3) return;
-  const uint8_t hv = (w <= d.V && d.inv_head[w].x > HEAVY_DEG) ? (uint8_t)WF_HEAVY : (uint8_t)0;
-  d.F[0][w] = hv;
-  d.F[1][w] = hv;
-  if (w <= d.V) {
-    d.LBR[0][w] = d.r0;
-    d.LBR[1][w] = d.r0;
-    d.UBR[0][w] = d.rpm1;
-    d.UBR[1][w] = d.rpm1;
-    d.abz[w] = -1;
-    d.valsrc[w] = VS_NONE;
-    d.abz_claim[w] = ~0ULL;
+// Everything a solve starts from, in ONE launch (a dozen small memsets cost more than the kernel): wire
+// state, row latches, the Case-5 cache, long-row bookkeeping, special latches, record counters, the
+// barrier words and the status block.
+__global__ void k_reset_all(Dev d) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= d.V + 3) {  // wires
+    const uint8_t hv = (i <= d.V && d.inv_head[i].x > HEAVY_DEG) ? (uint8_t)WF_HEAVY : (uint8_t)0;
+    d.F[0][i] = hv;
+    d.F[1][i] = hv;
+    if (i <= d.V) {
+      d.LBR[0][i] = d.r0;
+      d.LBR[1][i] = d.r0;
+      d.UBR[0][i] = d.rpm1;
+      d.UBR[1][i] = d.rpm1;
+      d.abz[i] = -1;
+      d.valsrc[i] = VS_NONE;
+      d.abz_claim[i] = ~0ULL;
+    }
+    if (d.world > 1) {
+#pragma unroll
+      for (int l = 0; l < 5; ++l) d.wflag[l][i] = 0;
+    }
   }
+  if (i <= d.N) d.solved[i] = 0;  // rows
+  if (i < d.N) d.c5sig[i] = 0xffffffffu;
+  if (i < d.n_long) {
+    d.long_done[i] = 0;
+    d.long_stamp[i] = 0;
+    LongP2 z;
+    z.hs = z.hx = 0;
+    z.k = z.w1 = z.gr = z.bad = 0;
+    d.long_p2[i] = z;
+  }
+  if (i < d.n_specials) d.sp_solved[i] = 0;
+  if (i < 8) {
+    d.rec_count[i] = 0;
+    d.dcnt[i] = 0;
+    d.bnd_flag[i] = 0;
+  }
+  if (i < 128) d.barrier[i] = 0;
+  if (i < sizeof(Status) / sizeof(unsigned int)) reinterpret_cast<unsigned int*>(d.st)[i] = 0;
 }
 __global__ void k_reset_known(Dev d) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1566,20 +1593,13 @@ static inline unsigned int blocks_for(uint64_t n, unsigned int t) { return (unsi
 
 cudaError_t launch_reset(const Dev& d, int grid, cudaStream_t s) {
   (void)grid;
-  k_reset_wires<<<blocks_for((uint64_t)d.V + 4, 256), 256, 0, s>>>(d);
+  uint64_t n = (uint64_t)d.V + 4;
+  n = std::max<uint64_t>(n, (uint64_t)d.N + 1);
+  n = std::max<uint64_t>(n, d.n_long);
+  n = std::max<uint64_t>(n, d.n_specials);
+  n = std::max<uint64_t>(n, 128);
+  k_reset_all<<<blocks_for(n, 256), 256, 0, s>>>(d);
   if (d.n_known) k_reset_known<<<blocks_for(d.n_known, 256), 256, 0, s>>>(d);
-  cudaMemsetAsync(d.solved, 0, (size_t)d.N + 1, s);
-  if (d.n_long) cudaMemsetAsync(d.long_done, 0, d.n_long, s);
-  if (d.n_long) cudaMemsetAsync(d.long_stamp, 0, (size_t)d.n_long * sizeof(unsigned int), s);
-  if (d.n_long) cudaMemsetAsync(d.long_p2, 0, (size_t)d.n_long * sizeof(LongP2), s);
-  if (d.n_specials) cudaMemsetAsync(d.sp_solved, 0, d.n_specials, s);
-  cudaMemsetAsync(d.rec_count, 0, 8 * sizeof(unsigned int), s);
-  cudaMemsetAsync(d.dcnt, 0, 8 * sizeof(unsigned int), s);
-  if (d.world > 1)
-    for (int l = 0; l < 5; ++l) cudaMemsetAsync(d.wflag[l], 0, (size_t)d.V + 8, s);
-  cudaMemsetAsync(d.bnd_flag, 0, 8 * sizeof(unsigned int), s);
-  cudaMemsetAsync(d.c5sig, 0xff, (size_t)(d.N ? d.N : 1) * sizeof(uint32_t), s);
-  cudaMemsetAsync(d.st, 0, sizeof(Status), s);
   return cudaGetLastError();
 }
 cudaError_t launch_clear_p2_table(const Dev& d, cudaStream_t s) {
@@ -1604,7 +1624,6 @@ int p1_grid_size(int device) {
 
 // the whole fixpoint: one cooperative launch
 cudaError_t launch_solve(const Dev& d, unsigned int max_rounds, int grid, cudaStream_t s) {
-  cudaMemsetAsync(d.barrier, 0, 128 * sizeof(unsigned int), s);
   // the descriptor goes to constant memory (skipped when it is what the last solve used)
   static Dev last;
   static bool have_last = false;
