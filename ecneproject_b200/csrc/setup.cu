@@ -920,40 +920,6 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
     err = "wire id outside 1..num_variables in a constraint (BoundsError at :681/:829)";
     return ECNE_E_BOUNDS;
   }
-  if (cnt.n_c3_long) {
-    // sorted table of 2^i mod p for i < max_c, built on the host (pure constants)
-    uint32_t tn = cnt.max_c;
-    std::vector<Pow2Entry> tab(tn);
-    fr::u256 x = fr::make_u256(1, 0, 0, 0);
-    for (uint32_t i = 0; i < tn; ++i) {
-      tab[i].v = x;
-      tab[i].e = i;
-      x = fr::add(x, x);
-    }
-    std::sort(tab.begin(), tab.end(),
-              [](const Pow2Entry& a, const Pow2Entry& b) { return fr::cmp(a.v, b.v) < 0; });
-    for (uint32_t i = 1; i < tn; ++i)
-      if (fr::eq(tab[i].v, tab[i - 1].v)) {
-        err = "2^i mod p repeats below the longest row length";
-        return ECNE_E_UNSUPPORTED;
-      }
-    Pow2Entry* d_tab;
-    CK(tmp.alloc(&d_tab, tn));
-    CK(cudaMemcpyAsync(d_tab, tab.data(), tn * sizeof(Pow2Entry), cudaMemcpyHostToDevice, s));
-    uint32_t mask_words = (tn + 31) / 32;
-    const int warps = 4;
-    size_t smem = (size_t)warps * 2 * mask_words * sizeof(unsigned int);
-    if (smem > 200 * 1024) {
-      err = "row too long for the bit-decomposition classifier";
-      return ECNE_E_UNSUPPORTED;
-    }
-    if (smem > 48 * 1024)
-      CK(cudaFuncSetAttribute(k_classify_c3_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_classify_c3_long<<<nb(cnt.n_c3_long, warps), warps * 32, smem, s>>>(
-        raw, d_rflags, d_aux, d_c3_long, cnt.n_c3_long, d_tab, tn, mask_words);
-    CK(cudaStreamSynchronize(s));  // tab is host-owned
-  }
-
   // ---- static values and the bound table ---------------------------------------------------
   d.n2a = cnt.n2a;
   d.n2b = cnt.n2b;
@@ -1010,6 +976,49 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
     CK(cub::DeviceScan::InclusiveSum(d_ms, b, d_flag, d_incl, (int)nc, s2));
   }
   k_ranks<<<nb(nc, 256), 256, 0, s2>>>(d_tvals, d_idx, d_incl, nc, d_rank_of, d_table);
+  // Long bit-decomposition candidates (main stream, while the side stream sorts the bound values)
+  std::vector<Pow2Entry> tab;
+  cudaEvent_t ev_c3;
+  cudaEventCreateWithFlags(&ev_c3, cudaEventDisableTiming);
+  if (cnt.n_c3_long) {
+    // sorted table of 2^i mod p for i < max_c, built on the host (pure constants)
+    uint32_t tn = cnt.max_c;
+    tab.resize(tn);
+    fr::u256 x = fr::make_u256(1, 0, 0, 0);
+    for (uint32_t i = 0; i < tn; ++i) {
+      tab[i].v = x;
+      tab[i].e = i;
+      x = fr::add(x, x);
+    }
+    std::sort(tab.begin(), tab.end(),
+              [](const Pow2Entry& a, const Pow2Entry& b) { return fr::cmp(a.v, b.v) < 0; });
+    for (uint32_t i = 1; i < tn; ++i)
+      if (fr::eq(tab[i].v, tab[i - 1].v)) {
+        err = "2^i mod p repeats below the longest row length";
+        cudaStreamSynchronize(s2);  // the side chain works in `tmp`, which is released on return
+        cudaStreamSynchronize(s);
+        return ECNE_E_UNSUPPORTED;
+      }
+    Pow2Entry* d_tab;
+    CK(tmp.alloc(&d_tab, tn));
+    CK(cudaMemcpyAsync(d_tab, tab.data(), tn * sizeof(Pow2Entry), cudaMemcpyHostToDevice, s));
+    uint32_t mask_words = (tn + 31) / 32;
+    const int warps = 4;
+    size_t smem = (size_t)warps * 2 * mask_words * sizeof(unsigned int);
+    if (smem > 200 * 1024) {
+      err = "row too long for the bit-decomposition classifier";
+      cudaStreamSynchronize(s2);
+      cudaStreamSynchronize(s);
+      return ECNE_E_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
+      CK(cudaFuncSetAttribute(k_classify_c3_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_classify_c3_long<<<nb(cnt.n_c3_long, warps), warps * 32, smem, s>>>(
+        raw, d_rflags, d_aux, d_c3_long, cnt.n_c3_long, d_tab, tn, mask_words);
+    cudaEventRecord(ev_c3, s);  // (`tab` lives until the function's final synchronisation)
+  }
+
+  if (cnt.n_c3_long) cudaStreamWaitEvent(s2, ev_c3, 0);  // k_fill_ranks reads the C3 flags of those rows
   if (N) k_fill_ranks<<<nb(N, 256), 256, 0, s2>>>((uint32_t)N, d_rflags, d_aux, d_rank_of, d_segnz);
   uint32_t h_rank[3], h_tn;
   cudaEventRecord(ev_join, s2);
@@ -1138,6 +1147,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(cudaStreamSynchronize(s2));
   cudaEventDestroy(ev_fork);
   cudaEventDestroy(ev_join);
+  cudaEventDestroy(ev_c3);
   d.r0 = h_rank[0];
   d.r1 = h_rank[1];
   d.rpm1 = h_rank[2];
