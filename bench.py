@@ -66,7 +66,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -270,12 +270,14 @@ def main():
             raise RuntimeError(lib.ecne_last_error().decode())
         return res.c
 
+    # clocks / throttle reasons are sampled from the first warm-up step to the end of the e2e leg (the timed
+    # regions are tens of milliseconds: too short for nvidia-smi's sampling period on their own)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         l2_flush()
         barrier()
         step_resident()
-    sampler = ClockSampler(local)
-    sampler.start()
     t_wall = t_dev = 0.0
     sweep_ms = solve_ms = 0.0
     launches = 0
@@ -296,7 +298,6 @@ def main():
         dense_cycles += int(c.dense_cycles)
         dense_evals, dense_rounds = int(c.dense_evals), int(c.dense_rounds)
     barrier()
-    clocks = sampler.stop()
     verdict = bool(res.c.verdict)
     n_unique = int(res.c.n_unique)
 
@@ -317,6 +318,7 @@ def main():
         if st != 0:
             raise RuntimeError(lib.ecne_last_error().decode())
     barrier()
+    clocks = sampler.stop()
     e2e_ms = 1e3 * t_e2e / e2e_steps
     h2d_ms, classify_ms = res2.c.ms_h2d, res2.c.ms_classify
     assert res2.unique_bits.tobytes() == res.unique_bits.tobytes()
