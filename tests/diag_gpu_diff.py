@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Diagnose a parity failure: run engine + oracle with full state and print differing wires."""
+"""Diagnose a parity failure: run engine + oracle with full state and print differing wires.
+(Lives under tests/: it executes the oracle, which only test infrastructure may do.)  Usage: python tests/diag_gpu_diff.py <config> [limit]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

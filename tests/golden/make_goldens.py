@@ -8,7 +8,8 @@
    (circomlib corpus + root / tornado / trusted-function configs): verdict, counts, SHA-256 of the
    unique and known bitmaps, per-rule firing counters.  The GPU engine is diffed against these.
 
-Run here (CPU):  python tools/make_goldens.py [--with-ecdsa]
+Run here (CPU):  python tests/golden/make_goldens.py [--with-ecdsa]
+(lives under tests/: it executes the oracle, which only test infrastructure may do)
 """
 import hashlib
 import json
@@ -17,7 +18,7 @@ import re
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

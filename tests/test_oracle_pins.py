@@ -54,7 +54,7 @@ def test_oracle_matches_goldens_and_pins(name):
 
 
 def test_big_goldens_present_and_pinned():
-    # ecdsa takes ~10 s of oracle time + 20 s prep per config: minted by tools/make_goldens.py --with-ecdsa
+    # ecdsa takes ~10 s of oracle time + 20 s prep per config: minted by tests/golden/make_goldens.py --with-ecdsa
     g = ORACLE["ecdsa+secp256k1"]
     assert g["verdict"] is True  # examples/ecdsa_secp_abstraction.jl:4
     assert (g["uniq"], g["nontriv"], g["tgt"], g["rounds"], g["pops"]) == (694285, 694311, 6, 28, 1602505)
