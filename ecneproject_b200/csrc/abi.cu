@@ -25,6 +25,7 @@ struct Global {
   // options
   long long max_rounds = 1000000;     // per P1 launch
   long long max_outer = 100000;
+  long long grid_blocks = 0;          // testing knob: launch the solve kernel with fewer blocks than SMs (0: one per SM)
   long long sparse_max = -1;          // records per round up to which a round is frontier-driven (-1: rows / 32)
   // pinned staging shared by every call (the API is single-threaded)
   void* h_status = nullptr;
@@ -174,6 +175,8 @@ extern "C" int ecne_set_option(const char* key, int64_t value) {
     G.max_outer = value;
   else if (k == "sparse_max")
     G.sparse_max = value;
+  else if (k == "grid_blocks")
+    G.grid_blocks = value;
   else
     return fail(ECNE_E_BADARG, "unknown option " + k);
   return ECNE_OK;
@@ -233,7 +236,8 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   cudaEventCreate(&e1);
   cudaEventCreate(&e2);
   cudaEventRecord(e0, s);
-  const int grid = p1_grid_size(G.device);
+  int grid = p1_grid_size(G.device);
+  if (G.grid_blocks > 0 && G.grid_blocks < grid) grid = (int)G.grid_blocks;
   CKA(launch_reset(d, grid, s));
   if (d.world > 1) {
     // clear mailbox / counts / epoch, then make sure every rank has done so before anyone posts

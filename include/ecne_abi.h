@@ -140,7 +140,10 @@ int ecne_dist_world(void);
  * sweeps, chosen so that every range holds about the same number of stored terms. */
 int ecne_shard_rows(const ecne_problem_t* problem, int rank, int world, uint64_t* lo, uint64_t* hi);
 
-/* ---- engine knobs (testing / benchmarking) ---------------------------------------------- */
+/* ---- engine knobs (testing / benchmarking) ----------------------------------------------
+ * "max_rounds" / "max_outer": round guards (ECNE_E_NOCONVERGE when hit); "sparse_max": a Jacobi round
+ * whose frontier has at most this many changed wires is frontier-driven instead of a dense sweep (-1: rows/32,
+ * 0: always dense); "grid_blocks": launch the solve kernel with fewer blocks than SMs (0: one per SM). */
 int ecne_set_option(const char* key, int64_t value);
 
 /* ---- field-arithmetic known-answer hooks: run the device Montgomery code on n elements ----

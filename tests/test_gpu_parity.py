@@ -272,6 +272,17 @@ def test_tiled_system_is_repeated_bitmap():
         assert np.array_equal(ut[1 + k * (V - 1): 1 + (k + 1) * (V - 1)], ub[1:]), k
     assert res.verdict is True and res.c.n_targets_unique == K * base.c.n_targets_unique
     assert res.c.outer_rounds == base.c.outer_rounds and res.c.inner_rounds == base.c.inner_rounds
+    # the same 255 040 rows squeezed into one and into three blocks: 249 resp. 83 rows per thread, beyond the
+    # 64 a live mask tracks — the paths a problem of more than 9.7 M rows per GPU takes on the full grid
+    for blocks in (1, 3):
+        assert lib.ecne_set_option(b"grid_blocks", blocks) == 0
+        try:
+            res2 = api.SolveResult(nv)
+            assert lib.ecne_solve(C.byref(ph.c), C.byref(res2.c)) == 0, lib.ecne_last_error()
+            assert res2.unique_bytes() == res.unique_bytes() and res2.known_bytes() == res.known_bytes()
+            assert res2.verdict is True
+        finally:
+            lib.ecne_set_option(b"grid_blocks", 0)
 
 
 @pytest.mark.parametrize("name", ["secp256k1+bmmp+blt", "root/poseidon", "circomlib/EdDSAPoseidonVerifier@eddsaposeidon"])
@@ -292,3 +303,23 @@ def test_repeated_solves_are_bit_stable(name):
     lib.ecne_free_resident(h)
     assert len(seen) == 1
     assert hashlib.sha256(next(iter(seen))[0]).hexdigest() == GOLD[name]["sha_unique"]
+
+
+@pytest.mark.parametrize("blocks,sparse_max", [(1, -1), (2, 0), (3, 1 << 30)])
+@pytest.mark.parametrize("name", ["secp256k1+bmmp+blt", "tornado/withdraw+pedersen", "root/bigmult86_3",
+                                  "circomlib/EdDSAPoseidonVerifier@eddsaposeidon"])
+def test_engine_knobs_do_not_change_the_result(name, blocks, sparse_max):
+    """The same circuits with the solve kernel squeezed into 1-3 blocks (so that a thread owns more rows than
+    its 64-bit live mask tracks and more than shared memory holds: the paths a >10 M-row problem takes), and
+    with every round forced dense (sparse_max = 0) or frontier-driven (sparse_max = huge)."""
+    lib = api._engine()
+    assert lib.ecne_set_option(b"grid_blocks", blocks) == 0
+    assert lib.ecne_set_option(b"sparse_max", sparse_max) == 0
+    try:
+        (reduced, specials, main), secp = prepare(name)
+        st, res = gpu_solve(reduced, specials, main, secp)
+        assert st == 0, lib.ecne_last_error()
+        check_against_gold(name, res)
+    finally:
+        lib.ecne_set_option(b"grid_blocks", 0)
+        lib.ecne_set_option(b"sparse_max", -1)
