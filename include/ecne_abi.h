@@ -128,10 +128,13 @@ int ecne_solve_resident(ecne_resident_t* r, ecne_result_t* result);
 void ecne_free_resident(ecne_resident_t* r);
 
 /* ---- row-range sharding across the GPUs of one box ------------------------
- * Every rank is given the WHOLE problem by its host and keeps rows [lo, hi) chosen by nnz
- * balance; wire state is replicated and the per-round update records are exchanged with one
- * ncclAllGather.  unique_id is the 128-byte ncclUniqueId made by rank 0 (ecne_dist_unique_id)
- * and broadcast by the host (torch.distributed / MPI / Julia Distributed). */
+ * One process per GPU.  Every rank is given the WHOLE problem by its host and sweeps rows [lo, hi)
+ * chosen by nnz balance; wire state is replicated.  Rounds with a large frontier are sharded: their
+ * update records are exchanged over NVLink peer mappings inside the solve kernel (one exchange per
+ * round); rounds with a small frontier are run replicated on every rank without any exchange.
+ * NCCL only bootstraps: unique_id is the 128-byte ncclUniqueId made by rank 0 (ecne_dist_unique_id)
+ * and broadcast by the host (torch.distributed / MPI / Julia Distributed); the engine all-gathers
+ * its CUDA IPC handles through it.  ecne_upload() and ecne_solve*() are collective calls. */
 int ecne_dist_unique_id(uint8_t out[128]);
 int ecne_dist_init(int rank, int world, const uint8_t unique_id[128]);
 int ecne_dist_rank(void);
