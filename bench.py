@@ -42,12 +42,29 @@ METRIC = "constraint_evals_per_sec_ecdsa"
 UNIT = "constraint-evals/s"
 
 
+PREP = {}
+
+
 def load_problem():
+    """readR1CS + abstraction through the native host fast path (include/ecne_host.h); outside every timed
+    region — its wall time is reported as config.host_prep_seconds for context."""
     from ecneproject_b200 import api, fixtures
+    t0 = time.perf_counter()
     reduced, specials, main = api.prepare(fixtures.path(WORKLOAD["main"]),
                                           [fixtures.path(t) for t in WORKLOAD["trusted"]],
                                           WORKLOAD["trusted_names"])
+    PREP["read_and_abstraction"] = time.perf_counter() - t0
     return reduced, specials, main
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 class ClockSampler:
@@ -174,7 +191,8 @@ def run_reference(args):
         "data": "real circuit (reference fixture ecdsa.r1cs), no synthetic data needed",
         "config": {"workload": WORKLOAD_NAME, "rows": reduced.n_rows, "wires": main.n_vars,
                    "evals_per_step": evals},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count(), "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -419,6 +437,7 @@ def main():
                    "records exchanged over NVLink inside the solve kernel (DESIGN.md §7)",
                    "timing": "CUDA events on the engine's stream around each whole call (ecne_result.ms_device), max over ranks",
                    "wall_ms_per_step": ms_wall, "device_ms_solve_per_step": solve_ms / args.steps,
+                   "host_prep_seconds": PREP.get("read_and_abstraction"),
                    "seconds_to_verdict_resident": ms_wall / 1e3},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "ms_h2d": h2d_ms,
@@ -440,7 +459,7 @@ def main():
         line["cpu_baseline"] = {"value": int(o.c.constraint_evals) / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": "one full solve of the same workload by oracle/ (C++ port of the Julia), "
                                           f"{int(o.c.constraint_evals)} evals in {dt:.2f} s",
-                                "seconds_to_verdict": dt, "host_cpus": os.cpu_count(),
+                                "seconds_to_verdict": dt, "host_cpus": os.cpu_count(), "cpu_model": cpu_model(),
                                 "matches_gpu_bitmap": o.unique_bits.tobytes() == res.unique_bits.tobytes()}
     if saved_stdout is not None:
         sys.stdout.flush()
