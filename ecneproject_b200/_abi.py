@@ -66,6 +66,15 @@ class R1CSStruct(C.Structure):
     ]
 
 
+class Report(C.Structure):
+    """ecne_report_t (include/ecne_abi.h): the rows and wires of the "Bad Constraints" listing."""
+    _fields_ = [
+        ("bad_row_bits", u64p), ("cap_wires", C.c_uint64), ("wire", u32p), ("flags", u8p),
+        ("lb", u64p), ("ub", u64p), ("nvalues", u8p), ("values", u64p),
+        ("n_bad_rows", C.c_uint64), ("n_wires", C.c_uint64),
+    ]
+
+
 class SpecialsStruct(C.Structure):
     _fields_ = [
         ("n", C.c_uint64), ("kind", i32p), ("in_ptr", u64p), ("in_", u32p),
@@ -77,7 +86,7 @@ class SpecialsStruct(C.Structure):
 # every symbol include/ecne_abi.h declares (tests check the built library exports all of them)
 ENGINE_SYMBOLS = [
     "ecne_version", "ecne_init", "ecne_shutdown", "ecne_last_error", "ecne_solve",
-    "ecne_upload", "ecne_solve_resident", "ecne_free_resident",
+    "ecne_upload", "ecne_solve_resident", "ecne_free_resident", "ecne_report_resident",
     "ecne_dist_unique_id", "ecne_dist_init", "ecne_dist_rank", "ecne_dist_world", "ecne_shard_rows",
     "ecne_set_option", "ecne_fr_batch",
 ]
@@ -145,6 +154,8 @@ def engine_lib():
         lib.ecne_solve_resident.restype = C.c_int
         lib.ecne_free_resident.argtypes = [C.c_void_p]
         lib.ecne_free_resident.restype = None
+        lib.ecne_report_resident.argtypes = [C.c_void_p, C.POINTER(Report)]
+        lib.ecne_report_resident.restype = C.c_int
         lib.ecne_dist_unique_id.argtypes = [u8p]
         lib.ecne_dist_unique_id.restype = C.c_int
         lib.ecne_dist_init.argtypes = [C.c_int, C.c_int, u8p]

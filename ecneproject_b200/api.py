@@ -9,6 +9,7 @@ maintainer would use instead):
   SolveConstraintsSymbolic(...)       R1CSConstraintSolver.jl:583-1646     -> bool   (THE hot path: one
                                                                            ecne_solve call)
   solveWithTrustedFunctions(...)      R1CSConstraintSolver.jl:502-581      -> bool
+  printState / printEquation / the "Bad Constraints" listing   :396-456, :1599-1644 (ecne_report_resident)
 
 Everything that computes runs in native code: libecne_host.so (parser, abstraction) and
 libecne_b200.so (sm_100a CUDA engine).  There is no Python or CPU fallback for the solver.
@@ -203,6 +204,133 @@ class ProblemHandle:
 # ---------------------------------------------------------------------------------------------
 # the mirrored reference functions
 # ---------------------------------------------------------------------------------------------
+class BadConstraints:
+    """The rows and wires of the reference's "Bad Constraints" listing (:1599-1635), found and compacted
+    on the device by ecne_report_resident: `rows` are the 0-based ids of the constraints that mention a
+    wire that is not unique, `wire` the 1-based ids (ascending, wire 1 left out) of the wires of those
+    rows, with their final VariableState."""
+
+    def __init__(self, handle, n_rows):
+        lib = _engine()
+        self.row_bits = np.zeros((n_rows + 63) // 64, dtype=np.uint64)
+        rep = _abi.Report()
+        rep.bad_row_bits = self.row_bits.ctypes.data_as(_abi.u64p)
+        st = lib.ecne_report_resident(handle, C.byref(rep))   # pass 1: bitmap + counts
+        if st != 0:
+            _raise(st, lib.ecne_last_error().decode())
+        n = int(rep.n_wires)
+        self.n_bad_rows = int(rep.n_bad_rows)
+        self.wire = np.zeros(n, dtype=np.uint32)
+        self.flags = np.zeros(n, dtype=np.uint8)
+        self.lb = np.zeros((n, 4), dtype=np.uint64)
+        self.ub = np.zeros((n, 4), dtype=np.uint64)
+        self.nvalues = np.zeros(n, dtype=np.uint8)
+        self.values = np.zeros((n, 2, 4), dtype=np.uint64)
+        if n:
+            rep.cap_wires = n
+            rep.wire = self.wire.ctypes.data_as(_abi.u32p)
+            rep.flags = self.flags.ctypes.data_as(_abi.u8p)
+            rep.lb = self.lb.ctypes.data_as(_abi.u64p)
+            rep.ub = self.ub.ctypes.data_as(_abi.u64p)
+            rep.nvalues = self.nvalues.ctypes.data_as(_abi.u8p)
+            rep.values = self.values.ctypes.data_as(_abi.u64p)
+            st = lib.ecne_report_resident(handle, C.byref(rep))   # pass 2: the compacted state
+            if st != 0:
+                _raise(st, lib.ecne_last_error().decode())
+        bits = np.unpackbits(self.row_bits.view(np.uint8), bitorder="little")[:n_rows]
+        self.rows = np.flatnonzero(bits)
+
+    def state(self, w):
+        """(unique, lb, ub, values) of a listed wire."""
+        i = int(np.searchsorted(self.wire, w))
+        if i >= len(self.wire) or int(self.wire[i]) != w:
+            raise KeyError(w)
+        return (bool(self.flags[i] & 1), _int(self.lb[i]), _int(self.ub[i]),
+                [_int(self.values[i, k]) for k in range(int(self.nvalues[i]))])
+
+
+_P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+# fix_number's threshold (:421-429) is NOT p - something round: the constant is restated digit for digit
+_FIX_NUMBER_ABOVE = 21888242871839275222246405745257275088548363400416034343698204186575808495517
+
+
+def _int(limbs):
+    return int.from_bytes(np.ascontiguousarray(limbs, dtype=np.uint64).tobytes(), "little")
+
+
+def fix_number(x):
+    """:421-429."""
+    return x - _P if x > _FIX_NUMBER_ABOVE else x
+
+
+def format_state(unique, lb, ub, values):
+    """printState (:396-419) as a string (Julia prints Bool as true/false, a BigInt vector as BigInt[..])."""
+    out = ["Uniquely Determined: " + ("true" if unique else "false")]
+    if lb == 0 and ub == _P - 1:
+        out.append("Bounds: None")
+    else:
+        out.append(f"Bounds: [{lb}, {ub}]")
+    if values:
+        out.append("All possible values: BigInt[" + ", ".join(str(v) for v in sorted(values)) + "]")
+    out.append("")
+    return "\n".join(out) + "\n"
+
+
+def read_sym(input_sym):
+    """The CSV read of :1603-1607: fourth column of every line = the signal name of wire (line + 1)."""
+    with open(input_sym) as f:
+        return [ln.rstrip("\n").split(",", 3)[3] for ln in f if ln.strip()]
+
+
+def format_equation(constraints, row, index_to_signal):
+    """printEquation (:431-456).  Terms are printed in stored order (the reference iterates a Julia Set:
+    its order is a hash order no caller can rely on)."""
+    def lin(k):
+        b, e = int(constraints.seg_ptr[3 * row + k]), int(constraints.seg_ptr[3 * row + k + 1])
+        terms = []
+        for j in range(b, e):
+            c = _int(constraints.coef[j])
+            if c == 0:
+                continue
+            key = int(constraints.col[j]) - 1
+            terms.append(f"{fix_number(c)} * {index_to_signal[key - 1] if key > 0 else 1}")
+        return "(" + " + ".join(terms) + ")" if terms else "0"
+    return lin(0) + " * " + lin(1) + " = " + lin(2)
+
+
+def row_variables(constraints, row):
+    """getVariables (:36-56) of one row, ascending (the reference's Set has no defined order)."""
+    b, e = int(constraints.seg_ptr[3 * row]), int(constraints.seg_ptr[3 * row + 3])
+    nz = constraints.coef[b:e].any(axis=1)
+    return np.unique(constraints.col[b:e][nz])
+
+
+def format_listing(constraints, bad, result, index_to_signal):
+    """Everything :1609-1643 prints after the "------ Bad Constraints ------" header."""
+    out = []
+    for row in bad.rows:
+        row = int(row)
+        out.append(f"constraint #{row + 1}\n")
+        out.append(format_equation(constraints, row, index_to_signal) + "\n")
+        for j in row_variables(constraints, row):
+            j = int(j)
+            if j == 1:
+                continue
+            out.append(index_to_signal[j - 2] + "\n")
+            out.append(format_state(*bad.state(j)))
+    out.append("------ All Variables ------\n\n")
+    nz = constraints.coef.any(axis=1)
+    ubits = np.unpackbits(result.unique_bits.view(np.uint8), bitorder="little")
+    for i in np.unique(constraints.col[nz]):
+        i = int(i)
+        if i == 1:
+            continue
+        out.append(index_to_signal[i - 2] + "\n")
+        vals = [_int(result.values[i - 1, k]) for k in range(int(result.nvalues[i - 1]))]
+        out.append(format_state(bool(ubits[i - 1]), _int(result.lb[i - 1]), _int(result.ub[i - 1]), vals))
+    return "".join(out)
+
+
 def readR1CS(filename):
     """ParseR1CS.readR1CS (ParseR1CS.jl:50).  The reference returns (equations, knowns, outs,
     num_wires+1); here those four live on the returned R1CS (.known, .targets, .n_vars)."""
@@ -247,6 +375,7 @@ def _engine():
 
 
 last_result = None
+last_bad_constraints = None
 
 
 def SolveConstraintsSymbolic(constraints, special_constraints, known_variables, debug=False,
@@ -254,19 +383,42 @@ def SolveConstraintsSymbolic(constraints, special_constraints, known_variables, 
                              secp_solve=False, full_state=False):
     """R1CSConstraintSolver.jl:583-1646, executed by the CUDA engine through ecne_solve.
 
-    Returns function_good (:1645).  The full per-wire state of the call is kept in
-    `ecneproject_b200.api.last_result` (a SolveResult) for the report path (:1599-1644)."""
-    global last_result
+    Returns function_good (:1645).  With a non-empty `input_sym` the listing of :1599-1644 is printed as
+    the reference prints it (a missing file raises, as CSV.File does); the rows and wires of its first part
+    come compacted from the device (ecne_report_resident) and are kept in `api.last_bad_constraints`.  The
+    per-wire state of the call is kept in `ecneproject_b200.api.last_result` (a SolveResult)."""
+    global last_result, last_bad_constraints
+    listing = input_sym != ""
+    index_to_signal = read_sym(input_sym) if listing else None   # a bad path fails before any GPU work
     lib = _engine()
     ph = ProblemHandle(constraints, special_constraints, known_variables, target_variables,
                        num_variables, secp_solve, debug)
-    res = SolveResult(int(num_variables), full_state=full_state)
-    st = lib.ecne_solve(C.byref(ph.c), C.byref(res.c))
-    if st != 0:
-        _raise(st, lib.ecne_last_error().decode())
+    res = SolveResult(int(num_variables), full_state=full_state or listing)
+    bad = None
+    if not listing:
+        st = lib.ecne_solve(C.byref(ph.c), C.byref(res.c))
+        if st != 0:
+            _raise(st, lib.ecne_last_error().decode())
+    else:
+        h = C.c_void_p()
+        st = lib.ecne_upload(C.byref(ph.c), C.byref(h))
+        if st != 0:
+            _raise(st, lib.ecne_last_error().decode())
+        try:
+            st = lib.ecne_solve_resident(h, C.byref(res.c))
+            if st != 0:
+                _raise(st, lib.ecne_last_error().decode())
+            bad = BadConstraints(h, len(constraints))
+        finally:
+            lib.ecne_free_resident(h)
     last_result = res
+    last_bad_constraints = bad
     print(f"Solved for {res.c.n_unique_nontrivial} variables out of {res.c.n_nontrivial} total variables")
     print(f"Solved for {res.c.n_targets_unique} target variables out of {len(target_variables)} total target variables")
+    print("------ Bad Constraints ------")
+    print()
+    if listing:
+        print(format_listing(constraints, bad, res, index_to_signal), end="")
     return res.verdict
 
 

@@ -230,6 +230,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   if (!h || !res || !res->unique_bits || !res->known_bits) return fail(ECNE_E_BADARG, "null argument");
   Resident& R = h->r;
   Dev& d = R.d;
+  R.have_state = false;
   cudaStream_t s = R.stream;
   cudaEvent_t e0, e1, e2;
   cudaEventCreate(&e0);
@@ -396,6 +397,60 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   res->dense_cycles = R.h_status->dense_cycles;
   res->ms_device = ms_device;
   res->ms_total = R.ms_h2d + R.ms_classify + ms_solve + ms_d2h;
+  R.have_state = true;
+  return ECNE_OK;
+}
+
+// ---- report path (:1599-1635) ----------------------------------------------------------------------
+extern "C" int ecne_report_resident(ecne_resident_t* h, ecne_report_t* rep) {
+  if (!h || !rep || !rep->bad_row_bits) return fail(ECNE_E_BADARG, "null argument");
+  Resident& R = h->r;
+  const Dev& d = R.d;
+  if (!R.have_state) return fail(ECNE_E_BADARG, "ecne_report_resident: no successful solve on this handle");
+  cudaStream_t s = R.stream;
+  Arena t;
+  struct Release {
+    Arena& a;
+    ~Release() { a.release(); }
+  } release{t};
+  const size_t row_words = ((size_t)R.n_rows + 63) / 64;  // 64-bit words of the row bitmap
+  unsigned int *d_rows = nullptr, *d_mark = nullptr;
+  uint32_t* d_wires = nullptr;
+  unsigned long long* d_counts = nullptr;
+  CKA(t.alloc(&d_rows, 2 * row_words));
+  CKA(t.alloc(&d_mark, ((size_t)d.V + 31) / 32));
+  CKA(t.alloc(&d_wires, (size_t)d.V));
+  CKA(t.alloc(&d_counts, 2));
+  launch_bad_rows(d, 0, d_rows, d_mark, d_wires, d_counts, s);
+  unsigned long long counts[2] = {0, 0};
+  CKA(cudaMemcpyAsync(rep->bad_row_bits, d_rows, row_words * 8, cudaMemcpyDeviceToHost, s));
+  CKA(cudaMemcpyAsync(counts, d_counts, sizeof(counts), cudaMemcpyDeviceToHost, s));
+  CKA(cudaStreamSynchronize(s));
+  CKA(cudaGetLastError());
+  rep->n_bad_rows = counts[0];
+  rep->n_wires = counts[1];
+  if (!rep->wire) return ECNE_OK;  // bitmap and counts only
+  if (rep->cap_wires < counts[1])
+    return fail(ECNE_E_BADARG, "ecne_report_resident: cap_wires " + std::to_string(rep->cap_wires) + " < n_wires " +
+                                   std::to_string(counts[1]));
+  const size_t n = (size_t)counts[1];
+  if (n == 0) return ECNE_OK;
+  uint8_t *df = nullptr, *dn = nullptr;
+  fr::u256 *dl = nullptr, *du = nullptr, *dv = nullptr;
+  if (rep->flags) CKA(t.alloc(&df, n));
+  if (rep->lb) CKA(t.alloc(&dl, n));
+  if (rep->ub) CKA(t.alloc(&du, n));
+  if (rep->nvalues) CKA(t.alloc(&dn, n));
+  if (rep->values) CKA(t.alloc(&dv, 2 * n));
+  launch_report_export(d, 0, d_wires, (uint32_t)n, df, dl, du, dn, dv, s);
+  CKA(cudaMemcpyAsync(rep->wire, d_wires, n * 4, cudaMemcpyDeviceToHost, s));
+  if (df) CKA(cudaMemcpyAsync(rep->flags, df, n, cudaMemcpyDeviceToHost, s));
+  if (dl) CKA(cudaMemcpyAsync(rep->lb, dl, n * 32, cudaMemcpyDeviceToHost, s));
+  if (du) CKA(cudaMemcpyAsync(rep->ub, du, n * 32, cudaMemcpyDeviceToHost, s));
+  if (dn) CKA(cudaMemcpyAsync(rep->nvalues, dn, n, cudaMemcpyDeviceToHost, s));
+  if (dv) CKA(cudaMemcpyAsync(rep->values, dv, n * 64, cudaMemcpyDeviceToHost, s));
+  CKA(cudaStreamSynchronize(s));
+  CKA(cudaGetLastError());
   return ECNE_OK;
 }
 

@@ -21,6 +21,13 @@ void launch_finalize(const Dev& d, int buf, unsigned long long* ubits, unsigned 
 void launch_export(const Dev& d, int buf, fr::u256* lb, fr::u256* ub, uint8_t* nvalues,
                    fr::u256* values, cudaStream_t s);
 
+// report path (:1599-1635): rows that mention a non-unique wire (bitmap), their wires in ascending order
+// (counts[0] = rows listed, counts[1] = wires listed), then the state of those wires
+void launch_bad_rows(const Dev& d, int buf, unsigned int* row_bits, unsigned int* wire_mark, uint32_t* wires,
+                     unsigned long long* counts, cudaStream_t s);
+void launch_report_export(const Dev& d, int buf, const uint32_t* wires, uint32_t n, uint8_t* flags, fr::u256* lb,
+                          fr::u256* ub, uint8_t* nvalues, fr::u256* values, cudaStream_t s);
+
 // Device memory is taken from a process-wide pool of big slabs that survives between calls
 // (SURVEY.md §8b "device memory owned by the library, cached between calls, freed in
 // ecne_shutdown"): an Arena bump-allocates out of slabs it borrows from the pool and hands them back
@@ -98,6 +105,7 @@ struct Resident {
   void* d_cub = nullptr;
   size_t cub_bytes = 0;
   bool table_dirty = false;  // a failed solve may leave entries in the P2 grouping table
+  bool have_state = false;   // buffer 0 holds the final state of a successful solve (report path)
   // pinned host staging
   Status* h_status = nullptr;
   unsigned long long* h_counts = nullptr;

@@ -1504,6 +1504,27 @@ __global__ void k_targets(Dev d, int buf, unsigned long long* counts) {
   if (d.F[buf][d.targets[i]] & WF_U) atomicAdd(counts + 3, 1ULL);
 }
 // materialise lb/ub/values/nvalues from ranks and value sources
+__device__ __forceinline__ uint8_t wire_values(const Dev& d, uint32_t w, fr::u256& v0, fr::u256& v1) {
+  const uint32_t vsrc = d.valsrc[w];
+  uint8_t n = 0;
+  v0 = fr::make_u256(0, 0, 0, 0);
+  v1 = v0;
+  if (vsrc == VS_ONE) {
+    n = 1;
+    v0 = fr::make_u256(1, 0, 0, 0);
+  } else if (vsrc == VS_ONEZERO) {
+    n = 2;
+    v0 = fr::make_u256(1, 0, 0, 0);
+  } else if (vsrc & VS_2B) {
+    n = 1;
+    v0 = d.tvals[vsrc & 0x3fffffffu];
+  } else if (vsrc & VS_2A) {
+    n = 2;
+    v0 = d.roots[2 * (vsrc & 0x3fffffffu)];
+    v1 = d.roots[2 * (vsrc & 0x3fffffffu) + 1];
+  }
+  return n;
+}
 __global__ void k_export(Dev d, int buf, fr::u256* lb, fr::u256* ub, uint8_t* nvalues,
                          fr::u256* values) {
   uint32_t w = blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -1511,27 +1532,77 @@ __global__ void k_export(Dev d, int buf, fr::u256* lb, fr::u256* ub, uint8_t* nv
   if (lb) lb[w - 1] = d.table[d.LBR[buf][w]];
   if (ub) ub[w - 1] = d.table[d.UBR[buf][w]];
   if (nvalues || values) {
-    uint32_t vsrc = d.valsrc[w];
-    uint8_t n = 0;
-    fr::u256 v0 = fr::make_u256(0, 0, 0, 0), v1 = v0;
-    if (vsrc == VS_ONE) {
-      n = 1;
-      v0 = fr::make_u256(1, 0, 0, 0);
-    } else if (vsrc == VS_ONEZERO) {
-      n = 2;
-      v0 = fr::make_u256(1, 0, 0, 0);
-    } else if (vsrc & VS_2B) {
-      n = 1;
-      v0 = d.tvals[vsrc & 0x3fffffffu];
-    } else if (vsrc & VS_2A) {
-      n = 2;
-      v0 = d.roots[2 * (vsrc & 0x3fffffffu)];
-      v1 = d.roots[2 * (vsrc & 0x3fffffffu) + 1];
-    }
+    fr::u256 v0, v1;
+    const uint8_t n = wire_values(d, w, v0, v1);
     if (nvalues) nvalues[w - 1] = n;
     if (values) {
       values[2 * (w - 1)] = v0;
       values[2 * (w - 1) + 1] = v1;
+    }
+  }
+}
+
+// ---- report path (:1599-1635) ---------------------------------------------------------------
+// One thread per row: a row is listed when one of its wires (non-zero terms only = getVariables, :36-56)
+// is not unique (:1612-1620); its wires but wire 1 are marked for the state listing (:1627-1633).  A
+// ballot packs 32 rows into a word of the bitmap.
+__global__ void k_bad_rows(Dev d, int buf, unsigned int* row_bits, unsigned int* wire_mark,
+                           unsigned long long* counts) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint8_t* F = d.F[buf];
+  bool bad = false;
+  if (row < d.N) {
+    const uint32_t b = d.seg[3 * row], e = d.seg[3 * row + 3];
+    for (uint32_t j = b; j < e && !bad; ++j) bad = !(F[d.col[j]] & WF_U);
+    if (bad)
+      for (uint32_t j = b; j < e; ++j) {
+        const uint32_t w = d.col[j];
+        if (w != 1) atomicOr(wire_mark + ((w - 1) >> 5), 1u << ((w - 1) & 31u));
+      }
+  }
+  const unsigned int m = __ballot_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31u) == 0 && row < ((d.N + 63) / 64) * 64) {  // both halves of the last 64-bit word
+    row_bits[row >> 5] = m;
+    if (m) atomicAdd(counts, (unsigned long long)__popc(m));
+  }
+}
+// The marked wires in ascending order: ONE block; every thread owns a contiguous run of mask words,
+// the run totals are scanned in shared memory, then each thread emits its wires behind its offset.
+__global__ void __launch_bounds__(1024) k_report_list(const unsigned int* wire_mark, uint32_t n_words,
+                                                      uint32_t* wires, unsigned long long* counts) {
+  __shared__ uint32_t s_off[1024];
+  const uint32_t per = (n_words + blockDim.x - 1) / blockDim.x;
+  const uint32_t lo = min(threadIdx.x * per, n_words), hi = min(lo + per, n_words);
+  uint32_t c = 0;
+  for (uint32_t i = lo; i < hi; ++i) c += (uint32_t)__popc(wire_mark[i]);
+  s_off[threadIdx.x] = c;
+  __syncthreads();
+  for (uint32_t st = 1; st < blockDim.x; st <<= 1) {  // Hillis-Steele inclusive scan
+    const uint32_t v = threadIdx.x >= st ? s_off[threadIdx.x - st] : 0u;
+    __syncthreads();
+    s_off[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t o = s_off[threadIdx.x] - c;
+  for (uint32_t i = lo; i < hi; ++i)
+    for (unsigned int m = wire_mark[i]; m; m &= m - 1) wires[o++] = i * 32u + (uint32_t)(__ffs((int)m) - 1) + 1u;
+  if (threadIdx.x == blockDim.x - 1) counts[1] = s_off[threadIdx.x];
+}
+__global__ void k_report_export(Dev d, int buf, const uint32_t* wires, uint32_t n, uint8_t* flags, fr::u256* lb,
+                                fr::u256* ub, uint8_t* nvalues, fr::u256* values) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t w = wires[i];
+  if (flags) flags[i] = d.F[buf][w] & (WF_U | WF_K);
+  if (lb) lb[i] = d.table[d.LBR[buf][w]];
+  if (ub) ub[i] = d.table[d.UBR[buf][w]];
+  if (nvalues || values) {
+    fr::u256 v0, v1;
+    const uint8_t nv = wire_values(d, w, v0, v1);
+    if (nvalues) nvalues[i] = nv;
+    if (values) {
+      values[2 * i] = v0;
+      values[2 * i + 1] = v1;
     }
   }
 }
@@ -1653,6 +1724,19 @@ void launch_finalize(const Dev& d, int buf, unsigned long long* ubits, unsigned 
 void launch_export(const Dev& d, int buf, fr::u256* lb, fr::u256* ub, uint8_t* nvalues,
                    fr::u256* values, cudaStream_t s) {
   k_export<<<blocks_for(d.V, 256), 256, 0, s>>>(d, buf, lb, ub, nvalues, values);
+}
+
+void launch_bad_rows(const Dev& d, int buf, unsigned int* row_bits, unsigned int* wire_mark, uint32_t* wires,
+                     unsigned long long* counts, cudaStream_t s) {
+  const uint32_t mark_words = (d.V + 31) / 32;
+  cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), s);
+  cudaMemsetAsync(wire_mark, 0, (size_t)mark_words * 4, s);
+  if (d.N) k_bad_rows<<<blocks_for(((uint64_t)d.N + 63) / 64 * 64, 256), 256, 0, s>>>(d, buf, row_bits, wire_mark, counts);
+  k_report_list<<<1, 1024, 0, s>>>(wire_mark, mark_words, wires, counts);
+}
+void launch_report_export(const Dev& d, int buf, const uint32_t* wires, uint32_t n, uint8_t* flags, fr::u256* lb,
+                          fr::u256* ub, uint8_t* nvalues, fr::u256* values, cudaStream_t s) {
+  if (n) k_report_export<<<blocks_for(n, 256), 256, 0, s>>>(d, buf, wires, n, flags, lb, ub, nvalues, values);
 }
 
 }  // namespace ecne

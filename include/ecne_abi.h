@@ -127,6 +127,28 @@ int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out);
 int ecne_solve_resident(ecne_resident_t* r, ecne_result_t* result);
 void ecne_free_resident(ecne_resident_t* r);
 
+/* ---- report path: the "Bad Constraints" listing (R1CSConstraintSolver.jl:1599-1635) ----------
+ * The reference walks every constraint, keeps those that mention (getVariables, :36-56: a stored
+ * non-zero coefficient) a wire that is not unique (:1612-1620), and prints the state of each of their
+ * wires but wire 1 (:1627-1633).  The engine finds those rows and compacts the state of exactly those
+ * wires on the device, so the D2H is the bitmap of rows plus one entry per listed wire instead of the
+ * whole per-wire state (ecdsa: 140 MB).  Refers to the LAST solve of the handle; all buffers are the
+ * caller's.  If cap_wires is too small the call returns ECNE_E_BADARG with bad_row_bits, n_bad_rows and
+ * n_wires filled in, so the caller can size the arrays and call again. */
+typedef struct ecne_report {
+  uint64_t* bad_row_bits; /* [(n_rows+63)/64] required; bit i&63 of word i>>6 <=> 0-based row i is listed */
+  uint64_t cap_wires;     /* entries each of the arrays below can hold                                  */
+  uint32_t* wire;         /* [cap_wires]   1-based wire ids, ascending; may be NULL (then so are the rest) */
+  uint8_t* flags;         /* [cap_wires]   bit 0 .unique, bit 1 .is_known                                */
+  uint64_t* lb;           /* [cap_wires*4] .lb.d                                                        */
+  uint64_t* ub;           /* [cap_wires*4] .ub.d                                                        */
+  uint8_t* nvalues;       /* [cap_wires]   length(.values)                                              */
+  uint64_t* values;       /* [cap_wires*8] .values[1..2].d                                              */
+  uint64_t n_bad_rows;    /* out: popcount(bad_row_bits)                                                */
+  uint64_t n_wires;       /* out: wires (other than wire 1) with a non-zero coefficient in a listed row */
+} ecne_report_t;
+int ecne_report_resident(ecne_resident_t* r, ecne_report_t* report);
+
 /* ---- row-range sharding across the GPUs of one box ------------------------
  * One process per GPU.  Every rank is given the WHOLE problem by its host and sweeps rows [lo, hi)
  * chosen by nnz balance; wire state is replicated.  Rounds with a large frontier are sharded: their

@@ -163,7 +163,7 @@ def test_divide_error_2a():
     st, _, ost, _ = both(m)
     assert st == ost == _abi.ECNE_E_DIVZERO
     with pytest.raises(ZeroDivisionError):
-        api.SolveConstraintsSymbolic(m, [], m.known, False, m.targets, m.n_vars)
+        api.SolveConstraintsSymbolic(m, [], m.known, False, m.targets, m.n_vars, "")
 
 
 def test_bounds_error_2a_no_variable():
