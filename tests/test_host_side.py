@@ -178,3 +178,20 @@ def test_loader_truncated_file_is_a_bounds_error():
     for cut in (len(blob) - 8 * 4 - 20, len(blob) - 8 * 4 - 12 - 36 * 5, 40, 11):
         st, _ = _read_mem(blob[:cut])
         assert st in (_abi.ECNE_E_BOUNDS, _abi.ECNE_E_ASSERT), (cut, st)
+
+
+def test_abstraction_goldens():
+    """Reduced system + special constraints of every trusted-function configuration (ecdsa included) against
+    the committed pins (tests/golden/make_abstraction_goldens.py says what they are and are not)."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_abstraction_goldens",
+                                                  os.path.join(here, "golden", "make_abstraction_goldens.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(here, "golden", "abstraction_goldens.json")))
+    got = mod.mint()
+    assert got == want
+    assert want["ecdsa+secp256k1"]["specials"] == 25 and want["ecdsa+secp256k1"]["rows"] == 694264  # SURVEY.md §8a
