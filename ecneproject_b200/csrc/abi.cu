@@ -284,8 +284,13 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
             S.prof[0], S.dense_rounds, S.prof[1], S.rounds - S.dense_rounds, S.prof[2], S.prof[3], S.prof[4], S.prof[5],
             S.prof[6], S.prof[7], S.outer, S.n_cand_total, S.n_cand_max, S.dense_evals, S.evals);
     if (atoi(getenv("ECNE_DEBUG_PROF")) > 2) {
-      std::vector<unsigned long long> pr(28000 + 24 * 148 * 4);
+      std::vector<unsigned long long> pr(28000 + 40 * 148 * 4 + 64);
       cudaMemcpy(pr.data(), d.prof, pr.size() * 8, cudaMemcpyDeviceToHost);
+      {
+        const unsigned long long* q = pr.data() + 28000 + 40 * 148 * 4;
+        fprintf(stderr, "[long row] slowest evaluation (maxima, cycles from entry): total %llu | gather %llu | cases 1-4 %llu | case 5 %llu | "
+                        "case 6 scan %llu | firing done %llu\n", q[0], q[1], q[2], q[3], q[4], q[5]);
+      }
       for (int r = 12; r < 24; ++r) {
         unsigned long long mx[3] = {0, 0, 0}, sum[3] = {0, 0, 0}, g = 0;
         for (int b = 0; b < 148; ++b)

@@ -1130,8 +1130,8 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(A.alloc(&d.bnd_flag, 8));
   CK(A.alloc(&d.c5sig, N));
   CK(A.alloc(&d.barrier, 128));
-  CK(A.alloc(&d.prof, (size_t)28000 + 40 * 148 * 4));
-  CK(cudaMemsetAsync(d.prof, 0, ((size_t)28000 + 40 * 148 * 4) * sizeof(unsigned long long), s));
+  CK(A.alloc(&d.prof, (size_t)28000 + 40 * 148 * 4 + 64));
+  CK(cudaMemsetAsync(d.prof, 0, ((size_t)28000 + 40 * 148 * 4 + 64) * sizeof(unsigned long long), s));
   CK(A.alloc(&d.st, 1));
   CK(A.alloc(&d.p2_row, N));
   CK(A.alloc(&R->d_ubits, (V + 63) / 64));

@@ -217,6 +217,79 @@ struct RowCtx {
   }
 };
 
+// The firing of Case 5 / Case 6: every non-unique wire among terms [s, e) becomes unique + known — on a long row
+// up to 1024 updates from ONE warp (ecdsa: 52 decoder rows fire in one round).  Through c.out() that is 8 dependent
+// {atomicOr, flag load, slot atomic} chains per lane and pass (130 k cycles for a 1025-term row); here a lane
+// issues its 8 atomics before it looks at any result and the warp takes one record-slot allocation per 256 terms.
+// Same updates, same "first writer logs" records (their order inside the list is not observable).
+template <int G>
+__device__ __noinline__ void emit_unique_all(const RowCtx& c, const uint8_t* F, uint32_t s, uint32_t e, uint32_t lane) {
+  const Dev& d = c_dev;
+  if (G == 1 || d.world > 1) {  // thread-per-row callers and sharded runs (distinct-wire counting) keep the plain path
+    scan_terms<G, SCAN_U(G)>(d, F, s, e, lane, [&](uint32_t w, uint32_t f) {
+      if (!(f & WF_U)) c.out(w, WF_U | WF_K);
+    });
+    return;
+  }
+  constexpr int U = 8;
+  constexpr uint32_t BITS = WF_U | WF_K;
+  for (uint32_t base = s; base < e; base += 32 * U) {
+    uint32_t w[U], f[U], old[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t t = base + (uint32_t)u * 32 + lane;
+      w[u] = t < e ? d.col[t] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) f[u] = w[u] != 0xffffffffu ? ld_flag(F, w[u]) : (uint32_t)WF_U;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      old[u] = 0xffu;
+      if (!(f[u] & WF_U)) {
+        unsigned int* word = (unsigned int*)(d.F[c.wbuf] + (w[u] & ~3u));
+        const unsigned int sh = (w[u] & 3u) * 8;
+        old[u] = (atomicOr(word, BITS << sh) >> sh) & 0xffu;
+      }
+    }
+    uint32_t chg = 0;
+    bool heavy = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (BITS & ~old[u]) {  // this update changed the write buffer: it is logged
+        chg |= 1u << u;
+        heavy |= (old[u] & WF_HEAVY) != 0;
+      }
+    if (heavy && !(__ldcg(d.bnd_flag + c.list) & 2u)) atomicOr(d.bnd_flag + c.list, 2u);
+    const uint32_t n = (uint32_t)__popc(chg);
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(d.rec_count + c.list, total);
+    i = __shfl_sync(0xffffffffu, i, 0) + incl - n;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if ((chg >> u) & 1u) {
+        if (i < d.rec_cap) {
+          Rec rr;
+          rr.wire = w[u];
+          rr.bits = BITS;
+          rr.lbr = ECNE_NO_LB;
+          rr.ubr = ECNE_NO_UB;
+          d.recs[c.list][i] = rr;
+        } else {
+          d.st->rec_overflow = 1;
+        }
+        ++i;
+      }
+  }
+}
+
 // |flip_coeffs(c)| of :1245-1257 on the (possibly flipped) stored coefficient
 __device__ __forceinline__ fr::u256 case5_mag(const fr::u256& c, bool flipped) {
   fr::u256 x = flipped ? fr::neg(c) : c;
@@ -307,6 +380,26 @@ __device__ __noinline__ bool eval_row(const Dev&, int rbuf, int wbuf, int list, 
   if (latch & 1) return true;  // equation_solved (:820-822)
   const uint8_t* F = d.F[rbuf];
   const uint32_t s0 = d.seg[3 * row], s2 = d.seg[3 * row + 2], s3 = d.seg[3 * row + 3];
+#ifdef ECNE_PROFILE
+  // slowest long-row evaluation of the solve, stage by stage (maxima; printed with ECNE_DEBUG_PROF=3)
+  long long pt[6] = {clock64(), 0, 0, 0, 0, 0};
+  auto pstamp = [&](int k) {
+    if (G == 32) pt[k] = clock64();
+  };
+  auto pflush = [&](int last) {
+    if (G == 32 && lane == 0) {
+      unsigned long long* q = d.prof + 28000 + 40 * 148 * 4;
+      for (int k = 1; k <= last; ++k)
+        if (pt[k]) atomicMax(q + k, (unsigned long long)(pt[k] - pt[0]));
+      atomicMax(q, (unsigned long long)(clock64() - pt[0]));
+    }
+  };
+#define ECNE_PSTAMP(k) pstamp(k)
+#define ECNE_PFLUSH(k) pflush(k)
+#else
+#define ECNE_PSTAMP(k)
+#define ECNE_PFLUSH(k)
+#endif
 
   // ---- gather: non-unique counts over A u B and over C --------------------------------------
   uint32_t nuAB = 0, nuC = 0, wC = 0, kmiss = 0, abzmiss = 0;
@@ -327,6 +420,7 @@ __device__ __noinline__ bool eval_row(const Dev&, int rbuf, int wbuf, int list, 
     abzmiss = Grp<G>::sum(abzmiss);
   }
 
+  ECNE_PSTAMP(1);  // gather
   RowCtx c;
   c.rbuf = rbuf;
   c.wbuf = wbuf;
@@ -448,7 +542,11 @@ __device__ __noinline__ bool eval_row(const Dev&, int rbuf, int wbuf, int list, 
     }
   }
 
-  if (nuC == 0) return plain;
+  ECNE_PSTAMP(2);  // cases 1-4
+  if (nuC == 0) {
+    ECNE_PFLUSH(2);
+    return plain;
+  }
   // ---- Case 5 (:1235-1298) ----------------------------------------------------------------
   bool local_k = (c.ov.n > 0 && c.ov.k[0]) || (c.ov.n > 1 && c.ov.k[1]);
   // Case 5 is a pure function of the row's non-unique set (uniqueness is monotone, so its size
@@ -457,13 +555,15 @@ __device__ __noinline__ bool eval_row(const Dev&, int rbuf, int wbuf, int list, 
   const uint32_t sig = (bepoch << 12) | (nuC & 0xfffu);
   if ((kmiss == 0 || local_k) && d.c5sig[row] != sig) {
     if (case5<G>(c)) {
-      scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
-        if (!(f & WF_U)) c.out(w, WF_U | WF_K);
-      });
+      ECNE_PSTAMP(3);
+      emit_unique_all<G>(c, F, s2, s3, lane);
+      ECNE_PSTAMP(5);
+      ECNE_PFLUSH(5);
       return plain;
     }
     if (lane == 0 && kmiss == 0 && !local_k) d.c5sig[row] = sig;
   }
+  ECNE_PSTAMP(3);  // case 5
   // ---- Case 6 (:1304-1348) ----------------------------------------------------------------
   if (abzmiss == 0) {
     uint32_t lo = 0xffffffffu, hi = 0;
@@ -476,13 +576,15 @@ __device__ __noinline__ bool eval_row(const Dev&, int rbuf, int wbuf, int list, 
     });
     lo = Grp<G>::min(lo);
     hi = Grp<G>::max(hi);
+    ECNE_PSTAMP(4);  // case 6 scan
     if (lo == hi) {
-      scan_terms<G, SCAN_U(G)>(d, F, s2, s3, lane, [&](uint32_t w, uint32_t f) {
-        if (!(f & WF_U)) c.out(w, WF_U | WF_K);
-      });
+      emit_unique_all<G>(c, F, s2, s3, lane);
+      ECNE_PSTAMP(5);
+      ECNE_PFLUSH(5);
       return plain;
     }
   }
+  ECNE_PFLUSH(4);
   return false;
 }
 
