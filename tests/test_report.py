@@ -192,3 +192,27 @@ def test_printed_listing_matches_oracle_state(r1cs, sym):
         assert got == want
     assert "------ All Variables ------" in got
     assert api.last_bad_constraints is not None and len(api.last_bad_constraints.rows) == len(rows)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ecdsa+secp256k1", "ecdsa"])
+def test_bad_constraints_full_size(name):
+    """BASELINE.json's full sizes (694 k and 1.09 M rows; 78 and 391 133 listed wires) against the pins minted from the
+    oracle's final state (tests/golden/make_report_goldens.py); the compacted state against the engine's own full
+    export.  The D2H of the compact form is what the report path is for: 138 B per listed wire."""
+    import hashlib
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "report_goldens.json")))[name]
+    (reduced, specials, main), secp = _prepare(name)
+    res, bad = _solve_with_report(reduced, specials, main, secp)
+    assert (bad.n_bad_rows, len(bad.wire)) == (gold["n_bad_rows"], gold["n_wires"])
+    row_bytes = bad.row_bits.view(np.uint8)[: (reduced.n_rows + 7) // 8].tobytes()
+    assert hashlib.sha256(row_bytes).hexdigest() == gold["sha_rows"]
+    assert hashlib.sha256(np.ascontiguousarray(bad.wire).tobytes()).hexdigest() == gold["sha_wires"]
+    w0 = bad.wire.astype(np.int64) - 1
+    ub = np.unpackbits(res.unique_bits.view(np.uint8), bitorder="little")[:main.n_vars]
+    kb = np.unpackbits(res.known_bits.view(np.uint8), bitorder="little")[:main.n_vars]
+    assert np.array_equal(bad.flags & 1, ub[w0]) and np.array_equal((bad.flags >> 1) & 1, kb[w0])
+    assert np.array_equal(bad.lb, res.lb[w0]) and np.array_equal(bad.ub, res.ub[w0])
+    assert np.array_equal(bad.nvalues, res.nvalues[w0]) and np.array_equal(bad.values, res.values[w0])
