@@ -195,3 +195,12 @@ def test_abstraction_goldens():
     got = mod.mint()
     assert got == want
     assert want["ecdsa+secp256k1"]["specials"] == 25 and want["ecdsa+secp256k1"]["rows"] == 694264
+
+
+def test_abstraction_only_prints_the_specials(capsys):
+    """:545-548: abstractionOnly prints the special constraints and returns true before the solver (no GPU needed)."""
+    ped = [fixtures.path("tornadocash_circuits/Pedersen248@pedersen.r1cs"), fixtures.path("tornadocash_circuits/Pedersen496@pedersen.r1cs")]
+    assert api.solveWithTrustedFunctions(fixtures.path("tornadocash_circuits/withdraw.r1cs"), "Withdraw", trusted_r1cs=ped,
+                                         trusted_r1cs_names=["Pedersen248", "Pedersen496"], abstractionOnly=True) is True
+    out = capsys.readouterr().out
+    assert "Pedersen496" in out and "Pedersen248" in out
