@@ -3,9 +3,9 @@
 system, the number of special constraints and a SHA-256 over the reduced arrays + the (name, inputs, outputs)
 list that ecne_abstraction (libecne_host.so) produces.
 
-These are REGRESSION pins of the host fast path (minted by it, when its output was cross-checked against the
-previous, simpler implementation of the same pass: identical on every configuration), not reference outputs —
-Julia cannot run here.  What ties them to the reference: the match counts bench/bench_abstraction.jl:16,24
+These are REGRESSION pins of the host fast path (minted by it; its output is identical to that of
+oracle/abstraction_ref.py, the plain-Python restatement, on every configuration: tests/test_abstraction_parity.py),
+not reference outputs — Julia cannot run here.  What ties them to the reference: the match counts bench/bench_abstraction.jl:16,24
 asserts, the reduced sizes of SURVEY.md §8a, and the verdicts the reference asserts for the abstracted
 configurations (test/runtests.jl:25,30,35, examples/ecdsa_secp_abstraction.jl:4), which the oracle and the
 engine reproduce from exactly these special constraints."""
