@@ -132,3 +132,64 @@ def test_explicit_zero_terms_do_not_count():
     main = mk([([(2, 1), (4, 0)], [(2, 1)], [(3, 1)]), ([(3, 1)], [(2, 1), (0, 0)], [(1, 1)])], n_wires=5)
     got, reduced = check_chain(main, [("cube", sub)])
     assert got == [("cube", [3], [2])] and reduced.n_rows == 0
+
+
+def _random_case(rng):
+    """A random trusted circuit (n rows over a few wires, small coefficient alphabet so that signatures tie and
+    unrelated rows collide in hash) planted 0-3 times under random wire renamings into a main circuit between random
+    filler rows; sometimes two copies overlap by construction of the filler (identical shapes)."""
+    coefs = [1, 1, 1, P - 1, 2, 0]
+    nw_sub = int(rng.integers(3, 7))               # wires 0..nw_sub-1 (0 = constant one)
+    n = int(rng.integers(1, 4))
+
+    def rand_form(nw, maxlen=3):
+        k = int(rng.integers(0, maxlen + 1))
+        ws = rng.choice(nw, size=min(k, nw), replace=False).tolist()
+        return [(int(w), int(coefs[int(rng.integers(0, len(coefs)))])) for w in ws]
+    sub_rows = [(rand_form(nw_sub), rand_form(nw_sub), rand_form(nw_sub)) for _ in range(n)]
+    pub_out = 1
+    pub_in = int(rng.integers(1, nw_sub - 1))
+    main_rows, next_wire = [], 1
+    n_main_wires = 1
+    for _ in range(int(rng.integers(1, 6))):
+        kind = int(rng.integers(0, 3))
+        if kind == 0:                               # filler row over the wires allocated so far (+ a fresh one)
+            n_main_wires += 1
+            main_rows.append((rand_form(n_main_wires), rand_form(n_main_wires), rand_form(n_main_wires)))
+        else:                                       # a planted copy: wire w of the sub -> fresh or reused main wire
+            ren = {0: 0}
+            for w in range(1, nw_sub):
+                if n_main_wires > 1 and rng.random() < 0.3:
+                    cand = int(rng.integers(1, n_main_wires))
+                    if cand in ren.values():
+                        cand = n_main_wires
+                        n_main_wires += 1
+                    ren[w] = cand
+                else:
+                    ren[w] = n_main_wires
+                    n_main_wires += 1
+            for forms in sub_rows:
+                main_rows.append(tuple([(ren[w], c) for w, c in form] for form in forms))
+    return sub_rows, nw_sub, pub_out, pub_in, main_rows, n_main_wires + 1
+
+
+def test_random_planted_circuits():
+    rng = np.random.default_rng(20261017)
+    n_matches = n_keyerr = 0
+    for case in range(300):
+        sub_rows, nw_sub, pub_out, pub_in, main_rows, nw_main = _random_case(rng)
+        sub = mk(sub_rows, n_wires=nw_sub, pub_out=pub_out, pub_in=pub_in, prv_in=0)
+        main = mk(main_rows, n_wires=nw_main)
+        try:
+            want_sp, want_rows = ref.abstraction("f", rows_of(main), sub.known.tolist(), rows_of(sub), sub.targets.tolist())
+        except ref.KeyErrorAt:
+            n_keyerr += 1
+            with pytest.raises(KeyError):
+                api.abstraction("f", main, sub)
+            continue
+        sp, red = api.abstraction("f", main, sub)
+        got = [(n, [int(x) for x in i], [int(x) for x in o]) for n, i, o in sp.as_list()]
+        assert got == [(n, list(i), list(o)) for n, i, o in want_sp], case
+        assert rows_of(red) == want_rows, case
+        n_matches += len(got)
+    assert n_matches > 100 and n_keyerr > 0  # the generator does exercise matches and the KeyError path
