@@ -15,9 +15,13 @@
 
 namespace ecne {
 
+#ifndef P1_THREADS      // -DP1_THREADS=512 -DP1_MAX_KS=12 builds the 128-register variant
 #define P1_THREADS 1024
+#endif
 #define P1_MIN_BLOCKS 1
+#ifndef P1_MAX_KS
 #define P1_MAX_KS 6     // 6 rows x 32 B x 1024 threads = 192 KB of the 227 KB shared memory
+#endif
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x ^= x >> 33;
