@@ -305,6 +305,22 @@ def row_variables(constraints, row):
     return np.unique(constraints.col[b:e][nz])
 
 
+def nontrivial_variables(constraints):
+    """all_nontrivial_vars (:600-618): every wire with a non-zero coefficient somewhere, ascending."""
+    return np.unique(constraints.col[constraints.coef.any(axis=1)])
+
+
+def format_all_states(constraints, result):
+    """The debug dump of :1573-1577: printState of every non-trivial variable (wire 1 included, as in the reference)."""
+    ubits = np.unpackbits(result.unique_bits.view(np.uint8), bitorder="little")
+    out = []
+    for i in nontrivial_variables(constraints):
+        i = int(i)
+        vals = [_int(result.values[i - 1, k]) for k in range(int(result.nvalues[i - 1]))]
+        out.append(format_state(bool(ubits[i - 1]), _int(result.lb[i - 1]), _int(result.ub[i - 1]), vals))
+    return "".join(out)
+
+
 def format_listing(constraints, bad, result, index_to_signal):
     """Everything :1609-1643 prints after the "------ Bad Constraints ------" header."""
     out = []
@@ -319,9 +335,8 @@ def format_listing(constraints, bad, result, index_to_signal):
             out.append(index_to_signal[j - 2] + "\n")
             out.append(format_state(*bad.state(j)))
     out.append("------ All Variables ------\n\n")
-    nz = constraints.coef.any(axis=1)
     ubits = np.unpackbits(result.unique_bits.view(np.uint8), bitorder="little")
-    for i in np.unique(constraints.col[nz]):
+    for i in nontrivial_variables(constraints):
         i = int(i)
         if i == 1:
             continue
@@ -393,7 +408,7 @@ def SolveConstraintsSymbolic(constraints, special_constraints, known_variables, 
     lib = _engine()
     ph = ProblemHandle(constraints, special_constraints, known_variables, target_variables,
                        num_variables, secp_solve, debug)
-    res = SolveResult(int(num_variables), full_state=full_state or listing)
+    res = SolveResult(int(num_variables), full_state=full_state or listing or debug)
     bad = None
     if not listing:
         st = lib.ecne_solve(C.byref(ph.c), C.byref(res.c))
@@ -414,6 +429,8 @@ def SolveConstraintsSymbolic(constraints, special_constraints, known_variables, 
     last_result = res
     last_bad_constraints = bad
     print(f"Solved for {res.c.n_unique_nontrivial} variables out of {res.c.n_nontrivial} total variables")
+    if debug:  # :1573-1577: the state of every variable that occurs in a constraint (ascending; the Julia walks a Set)
+        print(format_all_states(constraints, res), end="")
     print(f"Solved for {res.c.n_targets_unique} target variables out of {len(target_variables)} total target variables")
     print("------ Bad Constraints ------")
     print()

@@ -216,3 +216,18 @@ def test_bad_constraints_full_size(name):
     assert np.array_equal(bad.flags & 1, ub[w0]) and np.array_equal((bad.flags >> 1) & 1, kb[w0])
     assert np.array_equal(bad.lb, res.lb[w0]) and np.array_equal(bad.ub, res.ub[w0])
     assert np.array_equal(bad.nvalues, res.nvalues[w0]) and np.array_equal(bad.values, res.values[w0])
+
+
+def test_debug_dump_formats_every_nontrivial_variable():
+    """debug=true prints printState of every variable in all_nontrivial_vars (:1573-1577); fed here with the
+    oracle's final state of target/division (no GPU): one entry per non-trivial variable, unique flags as solved."""
+    reduced, specials, main = api.prepare(fixtures.path("target/division.r1cs"))
+    o = oracle_lib.solve(reduced, specials, main.known, main.targets, main.n_vars, False)
+    txt = api.format_all_states(reduced, o)
+    entries = txt.split("\n\n")[:-1]
+    nt = api.nontrivial_variables(reduced)
+    assert len(entries) == len(nt) == o.c.n_nontrivial
+    uniq = np.unpackbits(o.unique_bits.view(np.uint8), bitorder="little")
+    for e, w in zip(entries, nt):
+        assert e.splitlines()[0] == "Uniquely Determined: " + ("true" if uniq[int(w) - 1] else "false")
+    assert sum(e.startswith("Uniquely Determined: true") for e in entries) == o.c.n_unique_nontrivial
