@@ -229,3 +229,26 @@ def test_abstraction_only_prints_the_specials(capsys):
                                          trusted_r1cs_names=["Pedersen248", "Pedersen496"], abstractionOnly=True) is True
     out = capsys.readouterr().out
     assert "Pedersen496" in out and "Pedersen248" in out
+
+
+def test_c_example_compiles_as_strict_c99_and_fails_loudly_without_a_gpu(tmp_path):
+    """include/*.h are C headers (extern "C", plain pointers and sizes): examples/solve_r1cs.c builds with
+    `gcc -std=c99 -pedantic -Werror` against the two libraries, runs the host side (reader + abstraction) and — in
+    this container, without a CUDA device — stops at ecne_solve with ECNE_E_CUDA instead of computing on the CPU."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "ecneproject_b200")
+    exe = str(tmp_path / "solve_r1cs")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "solve_r1cs.c"), "-L", pkg, "-lecne_host", "-lecne_b200",
+                    "-Wl,-rpath," + pkg, "-o", exe], check=True, capture_output=True, text=True)
+    p = subprocess.run([exe, "--secp-solve", fixtures.path("secp256k1.r1cs"), fixtures.path("bigmultmodp.r1cs"), "BigMultModP",
+                        fixtures.path("biglessthan.r1cs"), "BigLessThan"], capture_output=True, text=True, timeout=120)
+    assert "BigMultModP: 3 window(s) abstracted, 4298 rows left" in p.stdout
+    assert "BigLessThan: 1 window(s) abstracted, 3985 rows left" in p.stdout
+    import torch
+    if torch.cuda.is_available():
+        assert p.returncode == 0 and "sound constraints" in p.stdout   # test/runtests.jl:35
+    else:
+        assert p.returncode == 2 and "no CPU fallback" in p.stderr
