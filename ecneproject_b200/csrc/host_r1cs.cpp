@@ -170,26 +170,176 @@ extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t*
     // fill the arrays in place.  A form that repeats a wire (Dict assignment overwrites, ParseR1CS.jl:110)
     // changes the lengths: such files take the serial path below.
     const uint64_t nseg = 3 * (uint64_t)n_cons;
+    const bool prof = getenv("ECNE_HOST_PROF") != nullptr;  // stage times on stderr
+    auto tp0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!prof) return;
+      auto t = std::chrono::steady_clock::now();
+      fprintf(stderr, "[ecne host] read_r1cs   %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
+      tp0 = t;
+    };
     uint64_t* segp = (uint64_t*)malloc((nseg + 1) * sizeof(uint64_t));
-    std::vector<uint64_t> raw(nseg);
-    uint64_t pos = s2, total = 0;
-    bool ok = segp != nullptr;
-    for (uint64_t sgi = 0; ok && sgi < nseg; ++sgi) {
-      if (!need(pos, 4)) { ok = false; break; }
-      const uint32_t n = rd32(arr + pos);
-      if (!need(pos + 4, (uint64_t)n * 36)) { ok = false; break; }
-      raw[sgi] = pos;
-      segp[sgi] = total;
-      total += n ? n : 1;
-      pos += 4 + (uint64_t)n * 36;
+    uint64_t* raw = (uint64_t*)malloc(std::max<uint64_t>(1, nseg) * sizeof(uint64_t));
+    struct FreeRaw {
+      uint64_t* p;
+      ~FreeRaw() { free(p); }
+    } free_raw{raw};
+    uint64_t total = 0;
+    bool ok = segp != nullptr && raw != nullptr;
+    // The offsets of the forms are a chain (each header says where the next one is): 3.3 M dependent loads on
+    // ecdsa, the largest serial piece of the host path.  Large files are cut into byte ranges walked concurrently:
+    // a worker that does not start at the section's first byte looks for the first offset in its range from which
+    // the next 64 headers are plausible (term counts and wire ids below nWires, everything inside the section), and
+    // the guess is then PROVED: the chain of the range before must end exactly on it, the last chain exactly on the
+    // section's end, and the forms must add up to 3 * nConstraints.  Anything else falls back to the serial walk,
+    // so the speculation can only cost time, never change a result.
+    bool walked = false;
+    const uint64_t sec_end = s2 + rd64(arr + starts[2] + 4);
+    unsigned hw = std::thread::hardware_concurrency();
+    if (ok && nseg >= (1u << 18) && hw > 1 && sec_end <= len && sec_end > s2) {
+      unsigned T = std::min<unsigned>(hw, 32);
+      if (const char* e = getenv("ECNE_HOST_WALK_RANGES")) T = (unsigned)std::max(2, std::min(256, atoi(e)));  // testing knob
+      struct Part {
+        uint64_t start = 0, end_pos = 0, terms = 0;
+        bool ok = false;
+        std::vector<uint64_t> pos;
+      };
+      std::vector<Part> parts(T);
+      auto plausible_from = [&](uint64_t c, int steps) {  // `steps` headers from c stay inside the section and look sane
+        for (int k = 0; k < steps && c < sec_end; ++k) {
+          if (c + 4 > sec_end) return false;
+          const uint32_t n = rd32(arr + c);
+          if (n > n_wires || c + 4 + (uint64_t)n * 36 > sec_end) return false;
+          if (n && (rd32(arr + c + 4) >= n_wires || rd32(arr + c + 4 + (uint64_t)(n - 1) * 36) >= n_wires)) return false;
+          c += 4 + (uint64_t)n * 36;
+        }
+        return true;
+      };
+      {
+        Part* pp = parts.data();
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t)
+          th.emplace_back([=, &plausible_from]() {
+            Part& P = pp[t];
+            const uint64_t lo = s2 + (sec_end - s2) / T * t, hi = t + 1 == T ? sec_end : s2 + (sec_end - s2) / T * (t + 1);
+            uint64_t c = lo;
+            if (t > 0) {
+              while (c < hi && !plausible_from(c, 64)) ++c;
+              if (c >= hi) return;  // no header found in the range (a form longer than the range): serial walk
+            }
+            P.start = c;
+            P.pos.reserve((hi - lo) / 48);
+            uint64_t terms = 0;
+            while (c < hi) {
+              if (c + 4 > sec_end) return;
+              const uint32_t n = rd32(arr + c);
+              if (c + 4 + (uint64_t)n * 36 > sec_end) return;
+              P.pos.push_back(c);
+              terms += n ? n : 1;
+              c += 4 + (uint64_t)n * 36;
+            }
+            P.end_pos = c;
+            P.terms = terms;
+            P.ok = true;
+          });
+        for (auto& x : th) x.join();
+      }
+      // proof by construction: part 0 starts on the section's first header, so its chain is the true one and ends on
+      // the first true header of part 1.  From there the true chain is followed until it meets part 1's guessed
+      // chain (two chains that share a header are identical from it on): a guess that began a few bytes early —
+      // inside the zero bytes of a coefficient, which read as empty forms — or on a false trail is repaired by that
+      // short serial prefix, its pseudo-forms dropped; and so on for the next part.  Nothing is trusted that was not
+      // reached from a proven header.
+      bool good = parts[0].ok && parts[0].start == s2;
+      std::vector<std::vector<uint64_t>> pre(T);
+      std::vector<uint64_t> skip(T, 0);
+      uint64_t forms = good ? parts[0].pos.size() : 0;
+      for (unsigned t = 1; t < T && good; ++t) {
+        Part& P = parts[t];
+        const uint64_t hi = t + 1 == T ? sec_end : s2 + (sec_end - s2) / T * (t + 1);
+        if (!P.ok) {  // no usable guess: the whole range is walked here
+          P.pos.clear();
+          P.terms = 0;
+        }
+        uint64_t cur = parts[t - 1].end_pos;
+        size_t i = 0;
+        while (true) {
+          while (i < P.pos.size() && P.pos[i] < cur) {
+            const uint32_t n = rd32(arr + P.pos[i]);
+            P.terms -= n ? n : 1;  // a pseudo-form of the guessed chain
+            ++i;
+          }
+          if (i < P.pos.size() && P.pos[i] == cur) break;  // met the guessed chain: true from here on
+          if (cur >= hi) {                                 // never met it inside the range
+            P.end_pos = cur;
+            break;
+          }
+          if (cur + 4 > sec_end) { good = false; break; }
+          const uint32_t n = rd32(arr + cur);
+          if (cur + 4 + (uint64_t)n * 36 > sec_end) { good = false; break; }
+          pre[t].push_back(cur);
+          P.terms += n ? n : 1;
+          cur += 4 + (uint64_t)n * 36;
+        }
+        skip[t] = i;
+        forms += pre[t].size() + (P.pos.size() - i);
+      }
+      good = good && parts[T - 1].end_pos == sec_end;
+      if (prof) {
+        uint64_t dropped = 0, walked_here = 0;
+        for (unsigned t = 0; t < T; ++t) dropped += skip[t], walked_here += pre[t].size();
+        fprintf(stderr, "[ecne host] read_r1cs   %u ranges: %llu pseudo-forms dropped, %llu forms walked serially to repair guesses, proof %s\n",
+                T, (unsigned long long)dropped, (unsigned long long)walked_here, good && forms == nseg ? "ok" : "FAILED (serial walk)");
+      }
+      if (good && forms == nseg) {
+        std::vector<uint64_t> form_base(T + 1, 0), term_base(T + 1, 0);
+        for (unsigned t = 0; t < T; ++t) {
+          form_base[t + 1] = form_base[t] + pre[t].size() + parts[t].pos.size() - skip[t];
+          term_base[t + 1] = term_base[t] + parts[t].terms;
+        }
+        total = term_base[T];
+        const Part* pp = parts.data();
+        const std::vector<uint64_t>* prep = pre.data();
+        const uint64_t *fb = form_base.data(), *tb = term_base.data(), *sk = skip.data();
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t)
+          th.emplace_back([=]() {
+            uint64_t g = fb[t], run = tb[t];
+            auto put = [&](uint64_t c) {
+              const uint32_t n = rd32(arr + c);
+              raw[g] = c;
+              segp[g] = run;
+              run += n ? n : 1;
+              ++g;
+            };
+            for (uint64_t c : prep[t]) put(c);
+            for (size_t k = (size_t)sk[t]; k < pp[t].pos.size(); ++k) put(pp[t].pos[k]);
+          });
+        for (auto& x : th) x.join();
+        walked = true;
+      }
     }
+    if (!walked) {
+      uint64_t pos = s2;
+      total = 0;
+      for (uint64_t sgi = 0; ok && sgi < nseg; ++sgi) {
+        if (!need(pos, 4)) { ok = false; break; }
+        const uint32_t n = rd32(arr + pos);
+        if (!need(pos + 4, (uint64_t)n * 36)) { ok = false; break; }
+        raw[sgi] = pos;
+        segp[sgi] = total;
+        total += n ? n : 1;
+        pos += 4 + (uint64_t)n * 36;
+      }
+    }
+    lap(walked ? "offset walk (parallel)" : "offset walk (serial)");
     if (ok && total < 0x7fffffffULL) {
       segp[nseg] = total;
       uint32_t* colp = (uint32_t*)malloc(std::max<uint64_t>(1, total) * sizeof(uint32_t));
       uint64_t* coefp = (uint64_t*)malloc(std::max<uint64_t>(1, total) * 4 * sizeof(uint64_t));
       std::vector<uint8_t> dup_flag(1, 0);
       uint8_t* dupf = dup_flag.data();
-      const uint64_t* rawp = raw.data();
+      const uint64_t* rawp = raw;
       parallel_chunks(nseg, 1 << 14, [=](uint64_t b, uint64_t e) {
         std::vector<uint32_t> tmp;
         for (uint64_t sgi = b; sgi < e; ++sgi) {
@@ -226,6 +376,7 @@ extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t*
           }
         }
       });
+      lap("fill (parallel)");
       if (!dup_flag[0]) {
         ecne_r1cs_t* r = (ecne_r1cs_t*)calloc(1, sizeof(ecne_r1cs_t));
         r->n_rows = n_cons;

@@ -142,12 +142,13 @@ def test_abstraction_no_match_is_identity():
 def _mk_r1cs(rows, n_wires, pub_out=1, pub_in=1, prv_in=1):
     """Serialise rows = [(A, B, C)] with each form a list of (wire0, int) into the iden3 .r1cs layout
     (ParseR1CS.jl:50-124); wire ids are 0-based on disk."""
-    cons = b""
+    chunks = []
     for forms in rows:
         for form in forms:
-            cons += len(form).to_bytes(4, "little")
+            chunks.append(len(form).to_bytes(4, "little"))
             for w, c in form:
-                cons += w.to_bytes(4, "little") + (c % (1 << 256)).to_bytes(32, "little")
+                chunks.append(w.to_bytes(4, "little") + (c % (1 << 256)).to_bytes(32, "little"))
+    cons = b"".join(chunks)
     prime = (21888242871839275222246405745257275088548364400416034343698204186575808495617).to_bytes(32, "little")
     hdr = (32).to_bytes(4, "little") + prime + n_wires.to_bytes(4, "little") + pub_out.to_bytes(4, "little") + \
         pub_in.to_bytes(4, "little") + prv_in.to_bytes(4, "little") + (n_wires).to_bytes(8, "little") + \
@@ -252,3 +253,58 @@ def test_c_example_compiles_as_strict_c99_and_fails_loudly_without_a_gpu(tmp_pat
         assert p.returncode == 0 and "sound constraints" in p.stdout   # test/runtests.jl:35
     else:
         assert p.returncode == 2 and "no CPU fallback" in p.stderr
+
+
+def test_loader_parallel_offset_walk_on_ecdsa():
+    """Files with >= 2^18 forms take the speculative parallel offset walk (csrc/host_r1cs.cpp); its result on
+    ecdsa.r1cs (3.3 M forms) is pinned to the digest the serial walk produced."""
+    import hashlib
+    r = api.readR1CS(fixtures.path("ecdsa.r1cs"))
+    h = hashlib.sha256()
+    for a in (r.seg_ptr, r.col, r.coef, r.known, r.targets):
+        h.update(np.ascontiguousarray(a).tobytes())
+    assert (r.n_rows, r.n_vars, r.nnz) == (1092639, 1089136, 4797431)
+    assert h.hexdigest() == "b44a391a1612b970f447c78ca6c7e2beacd25651959d600500bce130c7629d07"
+
+
+def test_loader_parallel_offset_walk_on_a_hostile_file(tmp_path):
+    """A synthetic file big enough for the parallel walk and built to mislead its guesses: coefficients that are
+    mostly zero bytes (they read as runs of empty forms), many truly empty forms, wire ids and term counts that look
+    alike, and a few forms longer than everything around them.  Against the independent Python parser; then the same
+    file truncated must still be a bounds error."""
+    rng = np.random.default_rng(7)
+    n_wires = 50
+    coefs = [1, 2, 3, 0, P - 1, 1 << 64, (1 << 200) + 5]
+    rows = []
+    for i in range(90000):
+        forms = []
+        for _ in range(3):
+            k = int(rng.integers(0, 4))
+            ws = rng.choice(n_wires, size=k, replace=False)
+            forms.append([(int(w), coefs[int(rng.integers(0, len(coefs)))]) for w in ws])
+        if i % 20011 == 7:   # a long form (no repeated wire: those take the serial path by design)
+            forms[2] = [(int(w), 1) for w in range(n_wires)]
+        rows.append(tuple(forms))
+    blob = _mk_r1cs(rows, n_wires=n_wires)
+    path = tmp_path / "hostile.r1cs"
+    path.write_bytes(blob)
+    r = api.readR1CS(str(path))
+    want, known, targets, n_vars = py_read_r1cs(str(path))
+    assert r.n_rows == len(want) == 90000 and r.n_vars == n_vars
+    col, seg = r.col.tolist(), r.seg_ptr.tolist()
+    raw = np.ascontiguousarray(r.coef).view(np.uint8).reshape(-1, 32)
+    for i, forms in enumerate(want):
+        for f, d in enumerate(forms):
+            got = {col[k]: int.from_bytes(raw[k].tobytes(), "little") for k in range(seg[3 * i + f], seg[3 * i + f + 1])}
+            assert got == d, (i, f)
+    # any number of byte ranges (= guessed starts) gives the same arrays
+    import os
+    try:
+        for ranges in ("2", "3", "7", "61", "256"):
+            os.environ["ECNE_HOST_WALK_RANGES"] = ranges
+            r2 = api.readR1CS(str(path))
+            assert np.array_equal(r2.seg_ptr, r.seg_ptr) and np.array_equal(r2.col, r.col) and np.array_equal(r2.coef, r.coef)
+    finally:
+        os.environ.pop("ECNE_HOST_WALK_RANGES", None)
+    st, _ = _read_mem(blob[: len(blob) // 2])
+    assert st in (_abi.ECNE_E_BOUNDS, _abi.ECNE_E_ASSERT)
