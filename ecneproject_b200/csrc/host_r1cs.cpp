@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <unordered_map>
 #include <thread>
@@ -130,10 +132,11 @@ extern "C" void ecne_r1cs_free(ecne_r1cs_t* r) {
 }
 
 // ParseR1CS.jl:50-124.  Offsets below are 0-based; the Julia is 1-based.
-extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t** out) {
+static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** out) {
   if (!arr || !out) return fail(ECNE_E_BADARG, "null argument");
   *out = nullptr;
-  auto need = [&](uint64_t off, uint64_t n) { return off + n <= len; };
+  // overflow-safe: `off + n` may wrap for sizes read from a hostile file
+  auto need = [&](uint64_t off, uint64_t n) { return n <= len && off <= len - n; };
   if (!need(0, 12)) return fail(ECNE_E_BOUNDS, "file shorter than the 12-byte header");
   if (rd32(arr + 4) != 1) return fail(ECNE_E_ASSERT, "version != 1 (ParseR1CS.jl:58)");
   uint32_t sections = rd32(arr + 8);
@@ -148,6 +151,7 @@ extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t*
     starts[ty] = cur;
     have[ty] = true;
     uint64_t sz = rd64(arr + cur + 4);
+    if (sz > len - cur - 12) return fail(ECNE_E_BOUNDS, "section size runs past the end of the file");
     cur += 12 + sz;
   }
   if (!have[1] || !have[2]) return fail(ECNE_E_BOUNDS, "header or constraint section missing");
@@ -165,6 +169,10 @@ extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t*
   uint32_t n_cons = rd32(arr + s1 + 24);
 
   uint64_t s2 = starts[2] + 12;
+  // every form stores at least its 4-byte term count: a header that announces more constraints than the
+  // file can hold is rejected before anything is sized from it
+  if (!need(s2, 0) || (uint64_t)n_cons * 12 > len - s2)
+    return fail(ECNE_E_BOUNDS, "nConstraints does not fit the file (truncated constraint section)");
   {
     // Fast path: one serial walk over the per-form term counts fixes every offset, then the host cores
     // fill the arrays in place.  A form that repeats a wire (Dict assignment overwrites, ParseR1CS.jl:110)
@@ -483,6 +491,19 @@ extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t*
   return ECNE_OK;
 }
 
+// No C++ exception crosses the C ABI: an allocation failure is a status code, as the header promises.
+extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t** out) {
+  try {
+    return read_r1cs_mem_impl(arr, len, out);
+  } catch (const std::bad_alloc&) {
+    if (out) *out = nullptr;
+    return fail(ECNE_E_BOUNDS, "out of memory while reading the file (sizes in its header exceed what can be allocated)");
+  } catch (const std::exception& e) {
+    if (out) *out = nullptr;
+    return fail(ECNE_E_INTERNAL, std::string("reader: ") + e.what());
+  }
+}
+
 extern "C" int ecne_read_r1cs(const char* path, ecne_r1cs_t** out) {
   if (!path || !out) return fail(ECNE_E_BADARG, "null argument");
   // map the file instead of copying it: the parser touches every byte exactly once
@@ -665,9 +686,23 @@ void appearance(const ecne_r1cs_t* r, uint64_t row0, uint64_t n, Appearance& out
 }  // namespace
 
 // abstraction (:237-395).
+static int abstraction_impl(int32_t kind, const ecne_r1cs_t* cons, const ecne_r1cs_t* sub,
+                            ecne_r1cs_t** reduced, ecne_specials_t* specials, uint64_t* n_matches);
 extern "C" int ecne_abstraction(int32_t kind, const ecne_r1cs_t* cons, const ecne_r1cs_t* sub,
                                 ecne_r1cs_t** reduced, ecne_specials_t* specials,
                                 uint64_t* n_matches) {
+  try {
+    return abstraction_impl(kind, cons, sub, reduced, specials, n_matches);
+  } catch (const std::bad_alloc&) {
+    if (reduced) *reduced = nullptr;
+    return fail(ECNE_E_INTERNAL, "out of memory in abstraction()");
+  } catch (const std::exception& e) {
+    if (reduced) *reduced = nullptr;
+    return fail(ECNE_E_INTERNAL, std::string("abstraction: ") + e.what());
+  }
+}
+static int abstraction_impl(int32_t kind, const ecne_r1cs_t* cons, const ecne_r1cs_t* sub,
+                            ecne_r1cs_t** reduced, ecne_specials_t* specials, uint64_t* n_matches) {
   if (!cons || !sub || !reduced || !specials) return fail(ECNE_E_BADARG, "null argument");
   *reduced = nullptr;
   const uint64_t N = cons->n_rows, n = sub->n_rows;

@@ -206,6 +206,28 @@ def test_loader_truncated_file_is_a_bounds_error():
         assert st in (_abi.ECNE_E_BOUNDS, _abi.ECNE_E_ASSERT), (cut, st)
 
 
+def test_loader_hostile_sizes_are_bounds_errors_not_crashes():
+    """Sizes read from the file never index or allocate unchecked: a section size that wraps the 64-bit cursor
+    of the section-table walk, and a header announcing 2^32-1 / 2^28 constraints over an empty constraint
+    section, are BoundsErrors (the reference raises a catchable BoundsError) — not a segfault or std::terminate."""
+    good = _mk_r1cs([([(1, 3)], [(2, 5)], [(3, 1)])], n_wires=4)
+    # (1) first section's size brings the cursor to 2^64 - 8: `cur + 12` wraps to 4
+    blob = bytearray(good)
+    blob[16:24] = ((1 << 64) - 8 - 12 - 12).to_bytes(8, "little")
+    st, _ = _read_mem(bytes(blob))
+    assert st == _abi.ECNE_E_BOUNDS, st
+    # (2) nConstraints from the header with nothing behind it
+    for n_cons in (0xFFFFFFFF, 0x10000000, 1 << 20):
+        prime = (21888242871839275222246405745257275088548364400416034343698204186575808495617).to_bytes(32, "little")
+        hdr = (32).to_bytes(4, "little") + prime + (4).to_bytes(4, "little") + (1).to_bytes(4, "little") * 3 + \
+            (4).to_bytes(8, "little") + n_cons.to_bytes(4, "little")
+        out = b"r1cs" + (1).to_bytes(4, "little") + (3).to_bytes(4, "little")
+        for ty, body in ((1, hdr), (2, b""), (3, b"")):
+            out += ty.to_bytes(4, "little") + len(body).to_bytes(8, "little") + body
+        st, _ = _read_mem(out)
+        assert st == _abi.ECNE_E_BOUNDS, (n_cons, st)
+
+
 def test_abstraction_goldens():
     """Reduced system + special constraints of every trusted-function configuration (ecdsa included) against
     the committed pins (tests/golden/make_abstraction_goldens.py says what they are and are not)."""
