@@ -51,7 +51,7 @@ class Result(C.Structure):
         ("ms_d2h", C.c_double), ("ms_exchange", C.c_double), ("ms_total", C.c_double),
         ("ms_sweep", C.c_double), ("rule_evals", C.c_uint64),
         ("dense_rounds", C.c_uint64), ("dense_evals", C.c_uint64), ("dense_cycles", C.c_uint64),
-        ("ms_device", C.c_double),
+        ("ms_device", C.c_double), ("gpus_used", C.c_uint64),
     ]
 
 
@@ -85,7 +85,7 @@ class SpecialsStruct(C.Structure):
 
 # every symbol include/ecne_abi.h declares (tests check the built library exports all of them)
 ENGINE_SYMBOLS = [
-    "ecne_version", "ecne_init", "ecne_shutdown", "ecne_last_error", "ecne_solve",
+    "ecne_version", "ecne_abi_layout", "ecne_init", "ecne_shutdown", "ecne_last_error", "ecne_solve",
     "ecne_upload", "ecne_solve_resident", "ecne_free_resident", "ecne_report_resident",
     "ecne_dist_unique_id", "ecne_dist_init", "ecne_dist_rank", "ecne_dist_world", "ecne_shard_rows",
     "ecne_set_option", "ecne_fr_batch",
@@ -129,6 +129,29 @@ def host_lib():
     return _host
 
 
+ABI_VERSION = 2
+
+
+def layout_table():
+    """{sizeof, n fields, offsets...} of the three ctypes mirrors, in the order ecne_abi_layout() reports them."""
+    t = []
+    for st in (Problem, Result, Report):
+        t += [C.sizeof(st), len(st._fields_)] + [getattr(st, f[0]).offset for f in st._fields_]
+    return t
+
+
+def check_layout(lib):
+    """One field-order slip in a mirror is a silent ABI break: compare with what the library was compiled with."""
+    if lib.ecne_version() != ABI_VERSION:
+        raise RuntimeError(f"libecne_b200.so has ABI version {lib.ecne_version()}, this mirror is for {ABI_VERSION}")
+    n = lib.ecne_abi_layout(None, 0)
+    buf = (C.c_uint32 * n)()
+    lib.ecne_abi_layout(buf, n)
+    if list(buf) != layout_table():
+        raise RuntimeError("ctypes mirror of include/ecne_abi.h does not match the library's struct layout: "
+                           f"library {list(buf)} mirror {layout_table()}")
+
+
 def engine_lib():
     """libecne_b200.so — the CUDA engine.  There is no fallback: missing library is an error."""
     global _engine
@@ -168,5 +191,8 @@ def engine_lib():
         lib.ecne_set_option.restype = C.c_int
         lib.ecne_fr_batch.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u64p]
         lib.ecne_fr_batch.restype = C.c_int
+        lib.ecne_abi_layout.argtypes = [u32p, C.c_uint32]
+        lib.ecne_abi_layout.restype = C.c_int
+        check_layout(lib)
         _engine = lib
     return _engine

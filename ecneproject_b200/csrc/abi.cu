@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,6 +27,7 @@ struct Global {
   long long max_rounds = 1000000;     // per P1 launch
   long long max_outer = 100000;
   long long grid_blocks = 0;          // testing knob: launch the solve kernel with fewer blocks than SMs (0: one per SM)
+  long long p2_hash_bits = 56;         // testing knob: bits of the P2 set hash that are used (fewer => collisions)
   long long sparse_max = -1;          // records per round up to which a round is frontier-driven (-1: rows / 32)
   // pinned staging shared by every call (the API is single-threaded)
   void* h_status = nullptr;
@@ -115,6 +117,43 @@ extern "C" int ecne_version(void) { return ECNE_ABI_VERSION; }
 
 extern "C" const char* ecne_last_error(void) { return G.err.c_str(); }
 
+// Layout self-check for foreign-language mirrors of the three structs (ctypes, Julia `struct`): for each of
+// ecne_problem_t, ecne_result_t, ecne_report_t the words {sizeof, number of fields, offsetof(field) ...} in
+// declaration order.  Returns the number of words the table has; writes at most `cap` of them.
+extern "C" int ecne_abi_layout(uint32_t* out, uint32_t cap) {
+  std::vector<uint32_t> t;
+#define ECNE_F(T, f) t.push_back((uint32_t)offsetof(T, f));
+#define ECNE_S(T, n) t.push_back((uint32_t)sizeof(T)); t.push_back(n);
+  ECNE_S(ecne_problem_t, 17)
+  ECNE_F(ecne_problem_t, n_rows) ECNE_F(ecne_problem_t, n_vars) ECNE_F(ecne_problem_t, seg_ptr)
+  ECNE_F(ecne_problem_t, col) ECNE_F(ecne_problem_t, coef) ECNE_F(ecne_problem_t, known)
+  ECNE_F(ecne_problem_t, n_known) ECNE_F(ecne_problem_t, targets) ECNE_F(ecne_problem_t, n_targets)
+  ECNE_F(ecne_problem_t, n_specials) ECNE_F(ecne_problem_t, sp_kind) ECNE_F(ecne_problem_t, sp_in_ptr)
+  ECNE_F(ecne_problem_t, sp_in) ECNE_F(ecne_problem_t, sp_out_ptr) ECNE_F(ecne_problem_t, sp_out)
+  ECNE_F(ecne_problem_t, secp_solve) ECNE_F(ecne_problem_t, debug)
+  ECNE_S(ecne_result_t, 30)
+  ECNE_F(ecne_result_t, verdict) ECNE_F(ecne_result_t, status) ECNE_F(ecne_result_t, unique_bits)
+  ECNE_F(ecne_result_t, known_bits) ECNE_F(ecne_result_t, lb) ECNE_F(ecne_result_t, ub)
+  ECNE_F(ecne_result_t, nvalues) ECNE_F(ecne_result_t, values) ECNE_F(ecne_result_t, abz)
+  ECNE_F(ecne_result_t, n_unique_nontrivial) ECNE_F(ecne_result_t, n_nontrivial)
+  ECNE_F(ecne_result_t, n_targets_unique) ECNE_F(ecne_result_t, n_unique) ECNE_F(ecne_result_t, outer_rounds)
+  ECNE_F(ecne_result_t, inner_rounds) ECNE_F(ecne_result_t, constraint_evals) ECNE_F(ecne_result_t, sweep_launches)
+  ECNE_F(ecne_result_t, ms_h2d) ECNE_F(ecne_result_t, ms_classify) ECNE_F(ecne_result_t, ms_solve)
+  ECNE_F(ecne_result_t, ms_d2h) ECNE_F(ecne_result_t, ms_exchange) ECNE_F(ecne_result_t, ms_total)
+  ECNE_F(ecne_result_t, ms_sweep) ECNE_F(ecne_result_t, rule_evals) ECNE_F(ecne_result_t, dense_rounds)
+  ECNE_F(ecne_result_t, dense_evals) ECNE_F(ecne_result_t, dense_cycles) ECNE_F(ecne_result_t, ms_device)
+  ECNE_F(ecne_result_t, gpus_used)
+  ECNE_S(ecne_report_t, 10)
+  ECNE_F(ecne_report_t, bad_row_bits) ECNE_F(ecne_report_t, cap_wires) ECNE_F(ecne_report_t, wire)
+  ECNE_F(ecne_report_t, flags) ECNE_F(ecne_report_t, lb) ECNE_F(ecne_report_t, ub) ECNE_F(ecne_report_t, nvalues)
+  ECNE_F(ecne_report_t, values) ECNE_F(ecne_report_t, n_bad_rows) ECNE_F(ecne_report_t, n_wires)
+#undef ECNE_F
+#undef ECNE_S
+  if (out)
+    for (size_t i = 0; i < t.size() && i < cap; ++i) out[i] = t[i];
+  return (int)t.size();
+}
+
 extern "C" int ecne_init(int device) {
   if (G.inited && G.device == device) return ECNE_OK;
   int n = 0;
@@ -177,6 +216,8 @@ extern "C" int ecne_set_option(const char* key, int64_t value) {
     G.sparse_max = value;
   else if (k == "grid_blocks")
     G.grid_blocks = value;
+  else if (k == "p2_hash_bits")
+    G.p2_hash_bits = value < 0 ? 0 : (value > 56 ? 56 : value);
   else
     return fail(ECNE_E_BADARG, "unknown option " + k);
   return ECNE_OK;
@@ -232,10 +273,16 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   Dev& d = R.d;
   R.have_state = false;
   cudaStream_t s = R.stream;
-  cudaEvent_t e0, e1, e2;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  cudaEventCreate(&e2);
+  struct Events {  // destroyed on every return path
+    cudaEvent_t e[5];
+    Events() {
+      for (auto& x : e) cudaEventCreate(&x);
+    }
+    ~Events() {
+      for (auto& x : e) cudaEventDestroy(x);
+    }
+  } evs;
+  cudaEvent_t e0 = evs.e[0], e1 = evs.e[1], e2 = evs.e[2], s0 = evs.e[3], s1 = evs.e[4];
   cudaEventRecord(e0, s);
   int grid = p1_grid_size(G.device);
   if (G.grid_blocks > 0 && G.grid_blocks < grid) grid = (int)G.grid_blocks;
@@ -253,6 +300,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
     R.table_dirty = false;
   }
   d.max_outer = (uint32_t)std::min<long long>(G.max_outer, 0x7fffffffLL);
+  d.p2_hash_mask = G.p2_hash_bits >= 56 ? 0x00ffffffffffffffULL : ((1ULL << G.p2_hash_bits) - 1ULL);
   {
     // from the whole problem, not the shard: every rank must take the same dense / sparse decision
     const long long sm = G.sparse_max >= 0 ? G.sparse_max : std::max<long long>(4096, (long long)d.N / 32);
@@ -261,9 +309,6 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   int status = ECNE_OK;
   std::string err;
   float ms_sweep = 0;
-  cudaEvent_t s0, s1;
-  cudaEventCreate(&s0);
-  cudaEventCreate(&s1);
   cudaEventRecord(s0, s);
   CKA(launch_solve(d, (unsigned int)std::min<long long>(G.max_rounds, 0x7fffffffLL), grid, s));
   cudaEventRecord(s1, s);
@@ -338,11 +383,6 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   if (status != ECNE_OK) {
     R.table_dirty = true;
     cudaStreamSynchronize(s);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaEventDestroy(e2);
-    cudaEventDestroy(s0);
-    cudaEventDestroy(s1);
     return fail(status, err.empty() ? status_text(status) : err);
   }
   // verdict + D2H
@@ -376,11 +416,6 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   cudaEventElapsedTime(&ms_solve, e0, e1);
   cudaEventElapsedTime(&ms_d2h, e1, e2);
   cudaEventElapsedTime(&ms_device, e0, e2);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaEventDestroy(e2);
-  cudaEventDestroy(s0);
-  cudaEventDestroy(s1);
   res->n_unique = R.h_counts[0];
   res->n_nontrivial = R.h_counts[1];
   res->n_unique_nontrivial = R.h_counts[2];
@@ -401,6 +436,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   res->dense_evals = R.h_status->dense_evals;
   res->dense_cycles = R.h_status->dense_cycles;
   res->ms_device = ms_device;
+  res->gpus_used = (uint64_t)d.world;
   res->ms_total = R.ms_h2d + R.ms_classify + ms_solve + ms_d2h;
   R.have_state = true;
   return ECNE_OK;
@@ -571,7 +607,9 @@ int setup_exchange(Resident& R, size_t cap) {
   }
   d.world = G.world;
   d.rank = G.rank;
-  d.rec_cap = (uint32_t)G.xcap;
+  // d.rec_cap stays this problem's own capacity: the phase lists 3 / 4 live in the problem's arena with exactly
+  // that many slots, and the exchange lists (G.xcap >= cap slots each, the stride every rank uses) hold at least
+  // as many
   for (int l = 0; l < 3; ++l) d.recs[l] = (Rec*)(G.xbuf + 4096 + (size_t)l * G.xcap * sizeof(Rec));
   for (int h = 0; h < G.world; ++h) {
     d.xflag[h] = (unsigned long long*)G.xpeer[h];

@@ -167,6 +167,7 @@ struct Dev {
   uint32_t* p2_slot;          // [N] table slot of each candidate
   uint32_t* p2_k;             // [N] size of its unknown set
   uint32_t h_mask;
+  unsigned long long p2_hash_mask;  // testing knob "p2_hash_bits": fewer hash bits force set-hash collisions
   uint32_t sparse_max;        // a round with at most this many frontier records is frontier-driven
   uint32_t max_outer;
   // records: three rotating lists for the Jacobi rounds + lists 3 / 4 for the phase updates of odd /

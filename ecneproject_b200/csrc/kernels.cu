@@ -15,13 +15,76 @@
 
 namespace ecne {
 
-#ifndef P1_THREADS      // -DP1_THREADS=512 -DP1_MAX_KS=12 builds the 128-register variant
-#define P1_THREADS 1024
+// One block per SM.  512 threads x 128 registers: the latency-bound paths (warp_solo, sparse_round, the row
+// evaluators) compile without register spills — at 1024 x 64 they spill, and every reload is an L2 trip after a
+// round boundary's L1 invalidation (-DP1_THREADS=1024 -DP1_MAX_KS=6 -DP1_INFLIGHT=2 builds that variant).
+#ifndef P1_THREADS
+#define P1_THREADS 512
 #endif
 #define P1_MIN_BLOCKS 1
 #ifndef P1_MAX_KS
-#define P1_MAX_KS 6     // 6 rows x 32 B x 1024 threads = 192 KB of the 227 KB shared memory
+#define P1_MAX_KS (6144 / P1_THREADS)  // rows per thread resident in shared memory: 6144 x 32 B = 192 KB of the 227 KB
 #endif
+#ifndef P1_INFLIGHT
+#define P1_INFLIGHT (P1_THREADS >= 1024 ? 2 : 4)  // rows a thread of the dense sweep has in flight
+#endif
+
+// A thread's set of rows that can still fire, one bit per row it owns (row = tid + k * nthreads), in W 64-bit
+// registers.  148 x 1024 threads x 128 bits cover 19.4 M rows, 148 x 512 threads x 192 bits 14.5 M: the synthetic
+// roofline input S16 (11.1 M rows) runs on the masked fast path in either build.
+#ifndef P1_LIVE_WORDS
+#define P1_LIVE_WORDS (P1_THREADS >= 1024 ? 2 : 3)
+#endif
+template <int W>
+struct LiveMaskT {
+  unsigned long long w[W];
+  static constexpr uint32_t BITS = 64u * W;
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int i = 0; i < W; ++i) w[i] = 0;
+  }
+  __device__ __forceinline__ void set(int k) {
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+      if ((k >> 6) == i) w[i] |= 1ULL << (k & 63);
+  }
+  __device__ __forceinline__ void clear(int k) {
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+      if ((k >> 6) == i) w[i] &= ~(1ULL << (k & 63));
+  }
+  __device__ __forceinline__ bool test(int k) const {
+    unsigned long long v = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+      if ((k >> 6) == i) v = w[i];
+    return ((v >> (k & 63)) & 1ULL) != 0;
+  }
+  __device__ __forceinline__ bool any() const {
+    unsigned long long v = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) v |= w[i];
+    return v != 0;
+  }
+  __device__ __forceinline__ unsigned int count() const {
+    unsigned int c = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) c += (unsigned int)__popcll(w[i]);
+    return c;
+  }
+  __device__ __forceinline__ int pop() {  // lowest row of the set, removed; -1 when empty
+    int k = -1;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+      if (k < 0 && w[i]) {
+        k = 64 * i + __ffsll((long long)w[i]) - 1;
+        w[i] &= w[i] - 1;
+      }
+    return k;
+  }
+  __device__ __forceinline__ int pop_nonempty() { return pop(); }
+};
+typedef LiveMaskT<P1_LIVE_WORDS> LiveMask;
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x ^= x >> 33;
@@ -35,7 +98,10 @@ __device__ __forceinline__ void p2_candidate(const Dev& d, uint32_t row, unsigne
                                              unsigned long long hx, uint32_t k) {
   // candidate list entry + membership in the group of its unknown set (open-addressing table keyed by
   // the 64-bit set hash; the member list is a stack linked through p2_next)
-  const unsigned long long key = mix64(hs ^ (hx * 0x9e3779b97f4a7c15ULL) ^ k) | 1ULL;  // 0 = empty slot
+  // bits 1..7 of the key hold min(k, 127): the members of a slot share k, so "fewer than k members" is an exact
+  // reason to skip the slot even when two different unknown sets collide in it (bit 0: 0 = empty slot)
+  const unsigned long long key = ((mix64(hs ^ (hx * 0x9e3779b97f4a7c15ULL) ^ k) & d.p2_hash_mask) << 8) |
+                                 ((unsigned long long)(k < 127u ? k : 127u) << 1) | 1ULL;
   // warp-aggregated slot allocation (every still-open row is a candidate in every outer round)
   const unsigned int am = __activemask();
   const unsigned int ln = threadIdx.x & 31u;
@@ -437,58 +503,11 @@ __device__ inline uint32_t p2_unknowns(const Dev& d, const uint8_t* F, uint32_t 
   return k;
 }
 
-// One group of candidates (all members of table slot `slot`), resolved by the member that was
-// inserted last: the first k rows in index order (the reference triggers when the k-th row of a set
-// arrives and uses exactly those, :1387-1388), slow_det (:1389-1400) = sum over ODD permutations
-// (Combinatorics.parity is 0 for even ones).
-__device__ __noinline__ void p2_resolve_group(const Dev&, int pl, uint32_t c) {
-  const Dev& d = c_dev;
-  const uint32_t slot = d.p2_slot[c];
-  if (__ldcg(d.h_head + slot) != c + 1) return;  // not the group's resolver
-  const uint8_t* F = d.F[0];
-  const uint32_t cnt = __ldcg(d.h_cnt + slot);
-  if (cnt < d.p2_k[c]) return;  // fewer than k rows share this unknown set (almost every group)
-  uint32_t vars[ECNE_P2_KMAX], terms[ECNE_P2_KMAX][ECNE_P2_KMAX], v2[ECNE_P2_KMAX];
-  uint32_t k = p2_unknowns(d, F, d.p2_row[c], vars, terms[0], ECNE_P2_KMAX);
-  if (cnt < k) return;
-  if (k > ECNE_P2_KMAX) {
-    raise(d, ECNE_E_UNSUPPORTED);
-    return;
-  }
-  // the k smallest row ids of the member list
-  uint32_t best[ECNE_P2_KMAX];
-  uint32_t nb = 0;
-  for (uint32_t m = c + 1; m != 0; m = __ldcg(d.p2_next + (m - 1))) {
-    const uint32_t r = d.p2_row[m - 1];
-    if (nb < k) {
-      uint32_t j = nb++;
-      while (j > 0 && best[j - 1] > r) {
-        best[j] = best[j - 1];
-        --j;
-      }
-      best[j] = r;
-    } else if (r < best[k - 1]) {
-      uint32_t j = k - 1;
-      while (j > 0 && best[j - 1] > r) {
-        best[j] = best[j - 1];
-        --j;
-      }
-      best[j] = r;
-    }
-  }
-  if (nb < k) return;
-  for (uint32_t j = 0; j < k; ++j) {
-    uint32_t kj = p2_unknowns(d, F, best[j], j == 0 ? vars : v2, terms[j], ECNE_P2_KMAX);
-    bool same = kj == k;
-    if (j > 0)
-      for (uint32_t x = 0; same && x < k; ++x) same = v2[x] == vars[x];
-    if (!same) {  // 64-bit set-hash collision: refuse to guess
-      raise(d, ECNE_E_INTERNAL);
-      return;
-    }
-  }
-  // odd-permutation sum; Montgomery products of canonical inputs carry a uniform R^-(k-1) factor,
-  // which does not change whether the sum is zero
+// slow_det (:1389-1400) = sum over ODD permutations (Combinatorics.parity is 0 for even ones) of the products
+// m[j][perm[j]], m[j][x] = coefficient of the x-th unknown in the j-th row.  Montgomery products of canonical
+// inputs carry a uniform R^-(k-1) factor, which does not change whether the sum is zero.
+__device__ __noinline__ bool p2_odd_permutation_sum_nonzero(const Dev& d, uint32_t k,
+                                                            const uint32_t (*terms)[ECNE_P2_KMAX]) {
   uint32_t perm[ECNE_P2_KMAX];
   for (uint32_t j = 0; j < k; ++j) perm[j] = j;
   fr::u256 res = fr::make_u256(0, 0, 0, 0);
@@ -516,9 +535,72 @@ __device__ __noinline__ void p2_resolve_group(const Dev&, int pl, uint32_t c) {
       perm[y] = tmp;
     }
   }
-  if (!fr::is_zero(res)) {
-    for (uint32_t j = 0; j < k; ++j) emit(d, 1, pl, vars[j], WF_U | WF_K);
+  return !fr::is_zero(res);
+}
+
+// The members of one table slot whose unknown set is EXACTLY that of member `leader` (1 + candidate index): the
+// first k of them in row order (the reference triggers when the k-th row of a set arrives and uses exactly
+// those, :1387-1388) decide the set.  Returns false when some member of the slot has a different unknown set,
+// i.e. two sets collided on the 64-bit hash.
+__device__ __noinline__ bool p2_resolve_set(const Dev& d, int pl, uint32_t head, uint32_t leader, bool only_if_first) {
+  const uint8_t* F = d.F[0];
+  uint32_t vars[ECNE_P2_KMAX], terms[ECNE_P2_KMAX][ECNE_P2_KMAX], v2[ECNE_P2_KMAX], t2[ECNE_P2_KMAX];
+  const uint32_t k = p2_unknowns(d, F, d.p2_row[leader - 1], vars, terms[0], ECNE_P2_KMAX);
+  if (k > ECNE_P2_KMAX) {
+    raise(d, ECNE_E_UNSUPPORTED);
+    return true;
   }
+  uint32_t best[ECNE_P2_KMAX];
+  uint32_t nb = 0;
+  bool all_same = true, before_leader = true;
+  for (uint32_t m = head; m != 0; m = __ldcg(d.p2_next + (m - 1))) {
+    const uint32_t r = d.p2_row[m - 1];
+    bool same = m == leader;
+    if (!same) {
+      same = p2_unknowns(d, F, r, v2, t2, ECNE_P2_KMAX) == k;
+      for (uint32_t x = 0; same && x < k; ++x) same = v2[x] == vars[x];
+    }
+    if (m == leader) before_leader = false;
+    if (!same) {
+      all_same = false;
+      continue;
+    }
+    if (only_if_first && before_leader) return all_same;  // an earlier member of the list leads this set
+    if (nb < k) {  // keep the k smallest row ids
+      uint32_t j = nb++;
+      while (j > 0 && best[j - 1] > r) {
+        best[j] = best[j - 1];
+        --j;
+      }
+      best[j] = r;
+    } else if (r < best[k - 1]) {
+      uint32_t j = k - 1;
+      while (j > 0 && best[j - 1] > r) {
+        best[j] = best[j - 1];
+        --j;
+      }
+      best[j] = r;
+    }
+  }
+  if (nb < k) return all_same;  // fewer than k rows share this unknown set
+  for (uint32_t j = 0; j < k; ++j) p2_unknowns(d, F, best[j], v2, terms[j], ECNE_P2_KMAX);
+  if (p2_odd_permutation_sum_nonzero(d, k, terms))
+    for (uint32_t j = 0; j < k; ++j) emit(d, 1, pl, vars[j], WF_U | WF_K);
+  return all_same;
+}
+
+// One group of candidates (all members of table slot `slot`), resolved by the member that was inserted last.
+// When two different unknown sets share the slot (a 64-bit hash collision) the resolver decides every distinct
+// set of the slot by exact comparison — it never guesses and never gives up.
+__device__ __noinline__ void p2_resolve_group(const Dev&, int pl, uint32_t c) {
+  const Dev& d = c_dev;
+  const uint32_t slot = d.p2_slot[c];
+  if (__ldcg(d.h_head + slot) != c + 1) return;  // not the group's resolver
+  const uint32_t cnt = __ldcg(d.h_cnt + slot);
+  if (cnt < d.p2_k[c]) return;  // fewer than k rows in the slot (almost every group); k is part of the key
+  if (p2_resolve_set(d, pl, c + 1, c + 1, false)) return;
+  for (uint32_t m = __ldcg(d.p2_next + c); m != 0; m = __ldcg(d.p2_next + (m - 1)))
+    p2_resolve_set(d, pl, c + 1, m, true);
 }
 
 // ---- P3 (:1425-1483): the lowest row tags a wire, exactly the reference's order -------------------
@@ -893,7 +975,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
   const uint32_t nthreads = gridDim.x * blockDim.x;
   const uint32_t rows = d.row_hi - d.row_lo;
   const uint32_t per_thread = (rows + nthreads - 1) / nthreads;
-  const uint32_t kmask = per_thread < 64 ? per_thread : 64;
+  const uint32_t kmask = per_thread < LiveMask::BITS ? per_thread : LiveMask::BITS;
   const uint32_t warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   unsigned int xe = d.world > 1 ? *d.xepoch : 0u;  // cross-GPU epoch (same on every rank)
@@ -904,12 +986,13 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
   uint32_t bepoch = 0;  // rounds so far that tightened a bound (same value in every thread)
 
   // ---- stage: live mask + the smem-resident row records ---------------------------------------
-  unsigned long long live = 0;
+  LiveMask live;
+  live.reset();
   for (uint32_t k = 0; k < kmask; ++k)
-    if (tid + k * nthreads < rows) live |= 1ULL << k;
+    if (tid + k * nthreads < rows) live.set((int)k);
 #pragma unroll
   for (int k = 0; k < P1_MAX_KS; ++k) {
-    if (k < ks && ((live >> k) & 1ULL)) {
+    if (k < ks && live.test(k)) {
       const uint32_t r = tid + (uint32_t)k * nthreads;
       const uint4* rp = reinterpret_cast<const uint4*>(d.rec + d.row_lo + r);
       sm_rec[(2 * k) * blockDim.x + threadIdx.x] = __ldg(rp);
@@ -1122,47 +1205,46 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
 #ifdef ECNE_PROFILE
           long long dz2 = clock64();
 #endif
-          // (c) sweep the rows this thread still owns, two in flight
-          const unsigned int nl = (unsigned int)__popcll(live);
+          // (c) sweep the rows this thread still owns, P1_INFLIGHT of them in flight
+          const unsigned int nl = live.count();
           evals += nl;
           devals += nl;
           ruleevals += nl;
-          unsigned long long slow = 0;
-          for (unsigned long long m = live; m;) {
-            const int k0 = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            const int k1 = m ? __ffsll((long long)m) - 1 : -1;
-            if (k1 >= 0) m &= m - 1;
-            const int kb = k1 >= 0 ? k1 : k0;
-            const uint32_t row0 = d.row_lo + tid + (uint32_t)k0 * nthreads;
-            const uint32_t row1 = d.row_lo + tid + (uint32_t)kb * nthreads;
-            InlineRow r0, r1;
-            if (k0 < ks)
-              unpack_row(sm_rec[(2 * k0) * blockDim.x + threadIdx.x], sm_rec[(2 * k0 + 1) * blockDim.x + threadIdx.x], r0);
-            else
-              load_row(d, row0, r0);
-            if (kb < ks)
-              unpack_row(sm_rec[(2 * kb) * blockDim.x + threadIdx.x], sm_rec[(2 * kb + 1) * blockDim.x + threadIdx.x], r1);
-            else
-              load_row(d, row1, r1);
-            uint32_t f0[ROWREC_INLINE], f1[ROWREC_INLINE];
-            gather_row(F, r0, f0);
-            if (k1 >= 0) gather_row(F, r1, f1);
-            const uint32_t e0 = eval_inline(d, rbuf, wbuf, (int)list, row0, r0, f0, bepoch);
-            if (e0 & EI_DONE) live &= ~(1ULL << k0);
-            if (e0 & EI_GENERIC) slow |= 1ULL << k0;
-            if (k1 >= 0) {
-              const uint32_t e1 = eval_inline(d, rbuf, wbuf, (int)list, row1, r1, f1, bepoch);
-              if (e1 & EI_DONE) live &= ~(1ULL << k1);
-              if (e1 & EI_GENERIC) slow |= 1ULL << k1;
+          LiveMask slow;
+          slow.reset();
+          for (LiveMask m = live; m.any();) {
+            // P1_INFLIGHT rows of this thread in flight: all their records, then all their state gathers, then
+            // the evaluations (an empty slot repeats the first row's loads and is not evaluated)
+            int kk[P1_INFLIGHT];
+            InlineRow rr[P1_INFLIGHT];
+            uint32_t ff[P1_INFLIGHT][ROWREC_INLINE];
+#pragma unroll
+            for (int h = 0; h < P1_INFLIGHT; ++h) kk[h] = m.pop();
+#pragma unroll
+            for (int h = 0; h < P1_INFLIGHT; ++h) {
+              const int k = kk[h] >= 0 ? kk[h] : kk[0];
+              if (k < ks)
+                unpack_row(sm_rec[(2 * k) * blockDim.x + threadIdx.x], sm_rec[(2 * k + 1) * blockDim.x + threadIdx.x], rr[h]);
+              else
+                load_row(d, d.row_lo + tid + (uint32_t)k * nthreads, rr[h]);
             }
+#pragma unroll
+            for (int h = 0; h < P1_INFLIGHT; ++h)
+              if (kk[h] >= 0) gather_row(F, rr[h], ff[h]);
+#pragma unroll
+            for (int h = 0; h < P1_INFLIGHT; ++h)
+              if (kk[h] >= 0) {
+                const uint32_t e = eval_inline(d, rbuf, wbuf, (int)list, d.row_lo + tid + (uint32_t)kk[h] * nthreads, rr[h],
+                                               ff[h], bepoch);
+                if (e & EI_DONE) live.clear(kk[h]);
+                if (e & EI_GENERIC) slow.set(kk[h]);
+              }
           }
           // the rows that need the generic evaluator (bit-decomposition patterns, x + y = 1, Case 5/6
           // candidates), all lanes together: inside the loop above one such lane would stall its warp in
           // almost every iteration
-          for (unsigned long long m = slow; m;) {
-            const int k = __ffsll((long long)m) - 1;
-            m &= m - 1;
+          for (LiveMask m = slow; m.any();) {
+            const int k = m.pop_nonempty();
             const uint32_t row = d.row_lo + tid + (uint32_t)k * nthreads;
             const bool done = eval_row<1>(d, rbuf, wbuf, (int)list, row, bepoch);
             bool fast;
@@ -1170,9 +1252,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               fast = (sm_rec[(2 * k) * blockDim.x + threadIdx.x].x & RF_FAST) != 0;
             else
               fast = (d.rflags[row] & RF_FAST) != 0;
-            if (done && !fast) live &= ~(1ULL << k);  // fast-path rows stay: bounds may still travel through them
+            if (done && !fast) live.clear(k);  // fast-path rows stay: bounds may still travel through them
           }
-          // rows beyond the 64 tracked per thread (only for problems far larger than the machine)
+          // rows beyond the ones tracked per thread (only for problems far larger than the machine)
           for (uint32_t k = kmask; k < per_thread; ++k) {
             uint32_t r = tid + k * nthreads;
             if (r < rows) {
@@ -1299,19 +1381,17 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       pz0 = clock64();
 #endif
       if (d.world == 1) {
-        evals += (unsigned int)__popcll(live);  // one visit of the linear-system sweep per row (:1359)
+        evals += live.count();  // one visit of the linear-system sweep per row (:1359)
         // two rows in flight; all six state bytes of a row are gathered before any is looked at (unused
         // slots hold the constant wire 1, which is unique)
-        for (unsigned long long m = live; m;) {
-          int kk2[2];
-          kk2[0] = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          kk2[1] = m ? __ffsll((long long)m) - 1 : -1;
-          if (kk2[1] >= 0) m &= m - 1;
-          InlineRow rr[2];
-          uint32_t ff[2][ROWREC_INLINE];
+        for (LiveMask m = live; m.any();) {
+          int kk2[P1_INFLIGHT];
+          InlineRow rr[P1_INFLIGHT];
+          uint32_t ff[P1_INFLIGHT][ROWREC_INLINE];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < P1_INFLIGHT; ++h) kk2[h] = m.pop();
+#pragma unroll
+          for (int h = 0; h < P1_INFLIGHT; ++h) {
             const int k = kk2[h] >= 0 ? kk2[h] : kk2[0];
             if (k < ks)
               unpack_row(sm_rec[(2 * k) * blockDim.x + threadIdx.x], sm_rec[(2 * k + 1) * blockDim.x + threadIdx.x], rr[h]);
@@ -1319,12 +1399,12 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               load_row(d, d.row_lo + tid + (uint32_t)k * nthreads, rr[h]);
           }
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < P1_INFLIGHT; ++h)
 #pragma unroll
             for (int j = 0; j < ROWREC_INLINE; ++j)
-              ff[h][j] = (rr[h].meta & 0x10000u) ? ld_flag(F, rr[h].c[j]) : (uint32_t)WF_U;
+              ff[h][j] = (kk2[h] >= 0 && (rr[h].meta & 0x10000u)) ? ld_flag(F, rr[h].c[j]) : (uint32_t)WF_U;
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < P1_INFLIGHT; ++h)
             if (kk2[h] >= 0) p2_scan_short(d, pl, d.row_lo + tid + (uint32_t)kk2[h] * nthreads, rr[h], ff[h]);
         }
         for (uint32_t k = kmask; k < per_thread; ++k) {
@@ -1443,10 +1523,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     const unsigned int p4f = __ldcg(&d.st->p4_fired);
     if (!stop && p4f != p4_seen) {
       p4_seen = p4f;
-      for (unsigned long long m = live; m;) {
-        const int k = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        if (d.solved[d.row_lo + tid + (uint32_t)k * nthreads] & 1) live &= ~(1ULL << k);
+      for (LiveMask m = live; m.any();) {
+        const int k = m.pop_nonempty();
+        if (d.solved[d.row_lo + tid + (uint32_t)k * nthreads] & 1) live.clear(k);
       }
     }
   }

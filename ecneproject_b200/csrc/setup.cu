@@ -802,10 +802,16 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
     Arena& a;
     ~TmpGuard() { a.release(); }
   } guard{tmp};
-  cudaEvent_t ev0, ev1, ev2;
-  cudaEventCreate(&ev0);
-  cudaEventCreate(&ev1);
-  cudaEventCreate(&ev2);
+  struct Events {  // destroyed on every return path
+    cudaEvent_t e[3];
+    Events() {
+      for (auto& x : e) cudaEventCreate(&x);
+    }
+    ~Events() {
+      for (auto& x : e) cudaEventDestroy(x);
+    }
+  } evs;
+  cudaEvent_t ev0 = evs.e[0], ev1 = evs.e[1], ev2 = evs.e[2];
   cudaEventRecord(ev0, s);
 
   // ---- H2D -------------------------------------------------------------------------------
@@ -1177,9 +1183,6 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   R->ms_h2d = ms;
   cudaEventElapsedTime(&ms, ev1, ev2);
   R->ms_classify = ms;
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
-  cudaEventDestroy(ev2);
   CK(cudaGetLastError());
   if (d.r0 != 0) {
     err = "internal: rank of 0 is not 0";

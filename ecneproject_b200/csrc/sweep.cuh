@@ -552,8 +552,11 @@ __device__ __noinline__ bool eval_row(const Dev&, int rbuf, int wbuf, int list, 
   // Case 5 is a pure function of the row's non-unique set (uniqueness is monotone, so its size
   // identifies it), their is_known bits (all set here) and bounds: skip it when it already failed
   // on exactly this state.
+  // (the memo keeps 12 bits of the count and 20 of the epoch: a row with more non-unique keys than that, or a
+  // solve with more bound-tightening rounds, is simply evaluated again — never skipped on an aliased signature)
+  const bool memo = nuC <= 0xfffu && bepoch <= 0xfffffu;
   const uint32_t sig = (bepoch << 12) | (nuC & 0xfffu);
-  if ((kmiss == 0 || local_k) && d.c5sig[row] != sig) {
+  if ((kmiss == 0 || local_k) && (!memo || d.c5sig[row] != sig)) {
     if (case5<G>(c)) {
       ECNE_PSTAMP(3);
       emit_unique_all<G>(c, F, s2, s3, lane);
@@ -561,7 +564,7 @@ __device__ __noinline__ bool eval_row(const Dev&, int rbuf, int wbuf, int list, 
       ECNE_PFLUSH(5);
       return plain;
     }
-    if (lane == 0 && kmiss == 0 && !local_k) d.c5sig[row] = sig;
+    if (lane == 0 && memo && kmiss == 0 && !local_k) d.c5sig[row] = sig;
   }
   ECNE_PSTAMP(3);  // case 5
   // ---- Case 6 (:1304-1348) ----------------------------------------------------------------

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ECNE_ABI_VERSION 1
+#define ECNE_ABI_VERSION 2
 
 /* Status codes.  The negative ones mirror the exception classes the reference can raise on this
  * path (SURVEY.md §5 / §8b "Errors"); the Julia shim rethrows them. */
@@ -109,10 +109,16 @@ typedef struct ecne_result {
   uint64_t dense_cycles;        /* SM cycles (clock64, block 0) spent in them, barrier included    */
   double ms_device;             /* CUDA-event time of the whole call on the engine's stream: reset,
                                    all rounds, verdict kernels and the D2H of the bitmaps           */
+  uint64_t gpus_used;           /* GPUs the solve kernel ran on (1, or the world of a sharded run)  */
 } ecne_result_t;
 
 /* ---- life cycle ------------------------------------------------------------------------- */
 int ecne_version(void);
+/* Layout self-check for foreign-language mirrors of the structs above (Python ctypes, a Julia `struct`): for each
+ * of ecne_problem_t, ecne_result_t, ecne_report_t, in this order, the words {sizeof, number of fields,
+ * offsetof(field) ... in declaration order}.  Returns the length of the table and writes at most `cap` words.
+ * A binding compares it with its own offsets once at load time (ecneproject_b200/_abi.py). */
+int ecne_abi_layout(uint32_t* out, uint32_t cap);
 /* Bind this process to CUDA device `device` (one process per GPU).  Idempotent. */
 int ecne_init(int device);
 void ecne_shutdown(void);
@@ -168,7 +174,9 @@ int ecne_shard_rows(const ecne_problem_t* problem, int rank, int world, uint64_t
 /* ---- engine knobs (testing / benchmarking) ----------------------------------------------
  * "max_rounds" / "max_outer": round guards (ECNE_E_NOCONVERGE when hit); "sparse_max": a Jacobi round
  * whose frontier has at most this many changed wires is frontier-driven instead of a dense sweep (-1: rows/32,
- * 0: always dense); "grid_blocks": launch the solve kernel with fewer blocks than SMs (0: one per SM). */
+ * 0: always dense); "grid_blocks": launch the solve kernel with fewer blocks than SMs (0: one per SM);
+ * "p2_hash_bits": bits of the unknown-set hash the linear-system sweep groups by (56; fewer force collisions,
+ * which the engine resolves by exact comparison — results do not depend on it). */
 int ecne_set_option(const char* key, int64_t value);
 
 /* ---- field-arithmetic known-answer hooks: run the device Montgomery code on n elements ----

@@ -323,3 +323,24 @@ def test_engine_knobs_do_not_change_the_result(name, blocks, sparse_max):
     finally:
         lib.ecne_set_option(b"grid_blocks", 0)
         lib.ecne_set_option(b"sparse_max", -1)
+
+
+@pytest.mark.parametrize("name", ["root/bigmult86_3", "root/bigmultmodp", "root/bigmultshortlong86_3", "root/poseidon"])
+def test_p2_set_hash_collisions_are_resolved_exactly(name):
+    """The linear-system sweep (:1357-1417) groups candidate rows by a 64-bit hash of their unknown set.  With the
+    hash cut to 0 / 1 / 3 bits every slot of the grouping table holds many different sets: the resolver must
+    separate them by exact comparison and decide each one — same bitmaps, counts and rounds as with the full hash,
+    on the four configurations where P2 fires."""
+    lib = api._engine()
+    (reduced, specials, main), secp = prepare(name)
+    outs = []
+    try:
+        for bits in (56, 0, 1, 3):
+            assert lib.ecne_set_option(b"p2_hash_bits", bits) == 0
+            st, res = gpu_solve(reduced, specials, main, secp)
+            assert st == 0, lib.ecne_last_error()
+            check_against_gold(name, res)
+            outs.append((res.unique_bytes(), res.known_bytes(), int(res.c.outer_rounds), int(res.c.inner_rounds)))
+    finally:
+        lib.ecne_set_option(b"p2_hash_bits", 56)
+    assert all(o == outs[0] for o in outs[1:]), [(o[2], o[3]) for o in outs]

@@ -24,7 +24,12 @@ def test_engine_exports_every_declared_symbol():
     assert set(syms) == set(_abi.ENGINE_SYMBOLS)
     for s in syms:
         assert getattr(lib, s) is not None
-    assert lib.ecne_version() == 1
+    assert lib.ecne_version() == _abi.ABI_VERSION == 2
+    # the layout table the library reports is what the ctypes mirror has (checked at load time as well)
+    n = lib.ecne_abi_layout(None, 0)
+    buf = (C.c_uint32 * n)()
+    assert lib.ecne_abi_layout(buf, n) == n and list(buf) == _abi.layout_table()
+    assert n == 3 * 2 + 17 + 30 + 10
 
 
 def test_host_exports_every_declared_symbol():
