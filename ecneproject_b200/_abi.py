@@ -85,7 +85,7 @@ class SpecialsStruct(C.Structure):
 
 # every symbol include/ecne_abi.h declares (tests check the built library exports all of them)
 ENGINE_SYMBOLS = [
-    "ecne_version", "ecne_abi_layout", "ecne_init", "ecne_shutdown", "ecne_last_error", "ecne_solve",
+    "ecne_version", "ecne_abi_layout", "ecne_init", "ecne_init_multi", "ecne_shutdown", "ecne_last_error", "ecne_solve",
     "ecne_upload", "ecne_solve_resident", "ecne_free_resident", "ecne_report_resident",
     "ecne_dist_unique_id", "ecne_dist_init", "ecne_dist_rank", "ecne_dist_world", "ecne_shard_rows",
     "ecne_set_option", "ecne_fr_batch",
@@ -167,6 +167,8 @@ def engine_lib():
         lib.ecne_version.restype = C.c_int
         lib.ecne_init.argtypes = [C.c_int]
         lib.ecne_init.restype = C.c_int
+        lib.ecne_init_multi.argtypes = [C.c_int]
+        lib.ecne_init_multi.restype = C.c_int
         lib.ecne_shutdown.restype = None
         lib.ecne_last_error.restype = C.c_char_p
         lib.ecne_solve.argtypes = [Pp, Rp]

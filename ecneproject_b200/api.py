@@ -376,11 +376,24 @@ def abstraction(function_name, constraints, sub_equation, specials=None):
 _initialised = False
 
 
+def init_multi(n_gpus):
+    """One process, the GPUs 0 .. n_gpus-1 of the box (ecne_init_multi): every later solve shards its rows over them."""
+    global _initialised
+    lib = _abi.engine_lib()
+    st = lib.ecne_init_multi(int(n_gpus))
+    if st != 0:
+        _raise(st, lib.ecne_last_error().decode())
+    _initialised = True
+
+
 def _engine():
     global _initialised
     lib = _abi.engine_lib()
     if not _initialised:
         import os
+        if int(os.environ.get("ECNE_GPUS", "1")) > 1:   # one process, several GPUs
+            init_multi(int(os.environ["ECNE_GPUS"]))
+            return lib
         dev = int(os.environ.get("LOCAL_RANK", os.environ.get("ECNE_DEVICE", "0")))
         st = lib.ecne_init(dev)
         if st != 0:

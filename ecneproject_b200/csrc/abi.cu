@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine_host.h"
@@ -18,29 +19,40 @@ using namespace ecne;
 
 namespace {
 
+// One device this process drives: its streams, its slab pool, its pinned staging and its exchange buffer.
+struct Ctx {
+  int device = -1;
+  cudaStream_t stream = nullptr, side = nullptr;
+  SlabPool pool;
+  void* h_status = nullptr;
+  void* h_counts = nullptr;
+  char* xbuf = nullptr;  // exchange channel of the rank this context plays (see below)
+};
+
 struct Global {
   bool inited = false;
-  int device = -1;
-  cudaStream_t stream = nullptr;
   std::string err;
+  // devices of this process: one after ecne_init(device) (one process per GPU), n after ecne_init_multi(n)
+  // (ONE process, one host thread, n GPUs: context i plays rank i of world n)
+  std::vector<Ctx*> ctx;
+  bool multi = false;
   // options
   long long max_rounds = 1000000;     // per P1 launch
   long long max_outer = 100000;
   long long grid_blocks = 0;          // testing knob: launch the solve kernel with fewer blocks than SMs (0: one per SM)
   long long p2_hash_bits = 56;         // testing knob: bits of the P2 set hash that are used (fewer => collisions)
   long long sparse_max = -1;          // records per round up to which a round is frontier-driven (-1: rows / 32)
-  // pinned staging shared by every call (the API is single-threaded)
-  void* h_status = nullptr;
-  void* h_counts = nullptr;
-  // dist
+  // one process per GPU: rank / world of this process and the communicator that bootstraps the peer mappings
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
-  // exchange channel: one cudaMalloc'ed buffer per rank, mapped into every peer through CUDA IPC
-  //   [0, 4096)            header: mailbox u64[8] @0, xcnt u32[3][8] @256, xepoch u32 @512, scratch int @1024
+  // exchange channel: one cudaMalloc'ed buffer per rank, visible to every peer (CUDA IPC mappings between
+  // processes, plain peer access inside one process)
+  //   [0, 4096)            header (engine.cuh XH_*): mailbox u64[64] @0, xcnt u32[4][8] @1024, epoch u32 @2048
   //   4096 + l*xcap*16     record list l (l = 0..2)
-  char* xbuf = nullptr;
   size_t xcap = 0;  // records per list
   char* xpeer[ECNE_MAX_WORLD] = {nullptr};
+  int n_local() const { return (int)ctx.size(); }
+  int total_world() const { return multi ? n_local() : world; }
 } G;
 
 // NCCL is bound at run time, not link time: a host process that also imports PyTorch must end up
@@ -71,9 +83,13 @@ struct NcclApi {
 
 }  // namespace
 namespace ecne {
-SlabPool& slab_pool() {
-  static SlabPool pool;
-  return pool;
+SlabPool& slab_pool() {  // the pool of the device that is current
+  static SlabPool fallback;
+  int dev = -1;
+  cudaGetDevice(&dev);
+  for (Ctx* c : G.ctx)
+    if (c->device == dev) return c->pool;
+  return fallback;
 }
 }  // namespace ecne
 namespace {
@@ -104,13 +120,16 @@ const char* status_text(int st) {
 
 }  // namespace
 
+// One uploaded problem: a classified copy per device this process drives (rs[0] reports; all copies hold the same
+// wire state after a solve).
 struct ecne_resident {
-  Resident r;
+  std::vector<Resident> rs;
 };
 
 namespace {
-int setup_exchange(Resident& R, size_t cap);
-int dist_barrier(cudaStream_t s);
+int setup_exchange(ecne_resident& H, size_t cap);
+int open_ctx(int device, Ctx** out);
+void close_all();
 }  // namespace
 
 extern "C" int ecne_version(void) { return ECNE_ABI_VERSION; }
@@ -154,8 +173,8 @@ extern "C" int ecne_abi_layout(uint32_t* out, uint32_t cap) {
   return (int)t.size();
 }
 
-extern "C" int ecne_init(int device) {
-  if (G.inited && G.device == device) return ECNE_OK;
+namespace {
+int open_ctx(int device, Ctx** out) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0)
@@ -170,40 +189,105 @@ extern "C" int ecne_init(int device) {
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
   if (!coop) return fail(ECNE_E_CUDA, "device lacks cooperative launch");
-  if (G.stream) cudaStreamDestroy(G.stream);
-  CKA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
-  if (!G.h_status) CKA(cudaMallocHost(&G.h_status, sizeof(Status)));
-  if (!G.h_counts) CKA(cudaMallocHost(&G.h_counts, 4 * sizeof(unsigned long long)));
-  G.device = device;
-  G.inited = true;
+  Ctx* c = new Ctx();
+  c->device = device;
+  G.ctx.push_back(c);  // (registered first: a failure below is cleaned up by close_all)
+  CKA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CKA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CKA(cudaMallocHost(&c->h_status, sizeof(Status)));
+  CKA(cudaMallocHost(&c->h_counts, 4 * sizeof(unsigned long long)));
+  *out = c;
   return ECNE_OK;
 }
-
-extern "C" void ecne_shutdown(void) {
+void close_all() {
   if (G.comm) {
     NCCL.CommDestroy(G.comm);
     G.comm = nullptr;
   }
-  if (G.stream) {
-    cudaStreamDestroy(G.stream);
-    G.stream = nullptr;
+  for (Ctx* c : G.ctx) {
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->side) cudaStreamDestroy(c->side);
   }
-  for (int h = 0; h < ECNE_MAX_WORLD; ++h)
-    if (G.xpeer[h] && G.xpeer[h] != G.xbuf) cudaIpcCloseMemHandle(G.xpeer[h]);
-  if (G.xbuf) cudaFree(G.xbuf);
+  if (!G.multi)
+    for (int h = 0; h < ECNE_MAX_WORLD; ++h)
+      if (G.xpeer[h] && (G.ctx.empty() || G.xpeer[h] != G.ctx[0]->xbuf)) cudaIpcCloseMemHandle(G.xpeer[h]);
   memset(G.xpeer, 0, sizeof(G.xpeer));
-  G.xbuf = nullptr;
+  for (Ctx* c : G.ctx) {
+    cudaSetDevice(c->device);
+    if (c->xbuf) cudaFree(c->xbuf);
+    c->pool.destroy();
+    if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    delete c;
+  }
+  G.ctx.clear();
   G.xcap = 0;
-  slab_pool().destroy();
-  if (G.h_status) cudaFreeHost(G.h_status);
-  if (G.h_counts) cudaFreeHost(G.h_counts);
-  G.h_status = nullptr;
-  G.h_counts = nullptr;
   G.inited = false;
-  G.device = -1;
+  G.multi = false;
   G.rank = 0;
   G.world = 1;
 }
+}  // namespace
+
+extern "C" int ecne_init(int device) {
+  if (G.inited && !G.multi && G.n_local() == 1 && G.ctx[0]->device == device) return ECNE_OK;
+  close_all();
+  Ctx* c = nullptr;
+  int st = open_ctx(device, &c);
+  if (st != ECNE_OK) {
+    close_all();
+    return st;
+  }
+  G.inited = true;
+  return ECNE_OK;
+}
+
+// SURVEY.md §8b "Threading": ONE process, one host thread, the GPUs 0 .. n_gpus-1 of the box.  The devices see each
+// other's exchange buffers through plain peer access (no IPC handles, no NCCL, no torch), context i plays rank i.
+extern "C" int ecne_init_multi(int n_gpus) {
+  if (n_gpus < 1 || n_gpus > ECNE_MAX_WORLD) return fail(ECNE_E_BADARG, "n_gpus outside 1..8");
+  if (G.inited && G.multi && G.n_local() == n_gpus) return ECNE_OK;
+  close_all();
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(ECNE_E_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (n_gpus > n)
+    return fail(ECNE_E_BADARG, "ecne_init_multi(" + std::to_string(n_gpus) + "): the box has " + std::to_string(n) + " GPU(s)");
+  for (int i = 0; i < n_gpus; ++i) {
+    Ctx* c = nullptr;
+    int st = open_ctx(i, &c);
+    if (st != ECNE_OK) {
+      close_all();
+      return st;
+    }
+  }
+  for (int i = 0; i < n_gpus; ++i)
+    for (int j = 0; j < n_gpus; ++j) {
+      if (i == j) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, i, j);
+      if (!can) {
+        close_all();
+        return fail(ECNE_E_CUDA, "GPUs " + std::to_string(i) + " and " + std::to_string(j) + " have no peer access");
+      }
+      cudaSetDevice(i);
+      cudaError_t pe = cudaDeviceEnablePeerAccess(j, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+        close_all();
+        return fail(ECNE_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
+      }
+      cudaGetLastError();
+    }
+  cudaSetDevice(0);
+  G.multi = n_gpus > 1;
+  G.inited = true;
+  return ECNE_OK;
+}
+
+extern "C" void ecne_shutdown(void) { close_all(); }
 
 extern "C" int ecne_set_option(const char* key, int64_t value) {
   if (!key) return fail(ECNE_E_BADARG, "null key");
@@ -230,27 +314,49 @@ extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out)
     int st = ecne_init(0);
     if (st) return st;
   }
+  const int nl = G.n_local(), world = G.total_world();
+  if (world > 1 && !G.multi && !G.comm) return fail(ECNE_E_NCCL, "ecne_dist_init has not been called");
   ecne_resident* h = new ecne_resident();
-  h->r.stream = G.stream;
-  h->r.h_status = (Status*)G.h_status;
-  h->r.h_counts = (unsigned long long*)G.h_counts;
-  std::string err;
-  int st = build_resident(problem, &h->r, err);
-  if (st != ECNE_OK) {
-    h->r.arena.release();
-    delete h;
-    return fail(st, err);
+  h->rs.resize(nl);
+  std::vector<int> sts(nl, ECNE_OK);
+  std::vector<std::string> errs(nl);
+  auto build_one = [&](int i) {
+    Ctx* c = G.ctx[i];
+    cudaSetDevice(c->device);
+    Resident& R = h->rs[i];
+    R.stream = c->stream;
+    R.side = c->side;
+    R.device = c->device;
+    R.h_status = (Status*)c->h_status;
+    R.h_counts = (unsigned long long*)c->h_counts;
+    R.arena.pool = &c->pool;
+    sts[i] = build_resident(problem, &R, errs[i]);
+  };
+  if (nl == 1) {
+    build_one(0);
+  } else {
+    // every device gets and classifies the whole problem (the wire state and the phases are replicated); the
+    // copies run concurrently, one host thread per device for the duration of the upload only
+    std::vector<std::thread> th;
+    for (int i = 0; i < nl; ++i) th.emplace_back(build_one, i);
+    for (auto& t : th) t.join();
+    cudaSetDevice(G.ctx[0]->device);
   }
-  if (G.world > 1) {
-    if (!G.comm) {
+  for (int i = 0; i < nl; ++i)
+    if (sts[i] != ECNE_OK) {
+      const int st = sts[i];
+      const std::string e = errs[i];
       ecne_free_resident(h);
-      return fail(ECNE_E_NCCL, "ecne_dist_init has not been called");
+      return fail(st, e);
     }
-    uint64_t lo = 0, hi = 0;
-    ecne_shard_rows(problem, G.rank, G.world, &lo, &hi);
-    h->r.d.row_lo = (uint32_t)lo;
-    h->r.d.row_hi = (uint32_t)hi;
-    st = setup_exchange(h->r, h->r.d.rec_cap);
+  if (world > 1) {
+    for (int i = 0; i < nl; ++i) {
+      uint64_t lo = 0, hi = 0;
+      ecne_shard_rows(problem, G.multi ? i : G.rank, world, &lo, &hi);
+      h->rs[i].d.row_lo = (uint32_t)lo;
+      h->rs[i].d.row_hi = (uint32_t)hi;
+    }
+    int st = setup_exchange(*h, h->rs[0].d.rec_cap);
     if (st != ECNE_OK) {
       ecne_free_resident(h);
       return st;
@@ -262,63 +368,103 @@ extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out)
 
 extern "C" void ecne_free_resident(ecne_resident_t* h) {
   if (!h) return;
-  cudaStreamSynchronize(h->r.stream);
-  h->r.arena.release();
+  for (auto& R : h->rs) {
+    cudaSetDevice(R.device);
+    if (R.stream) cudaStreamSynchronize(R.stream);
+    if (R.arena.pool) R.arena.release();
+  }
+  if (!G.ctx.empty()) cudaSetDevice(G.ctx[0]->device);
   delete h;
 }
 
 extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   if (!h || !res || !res->unique_bits || !res->known_bits) return fail(ECNE_E_BADARG, "null argument");
-  Resident& R = h->r;
+  const int nl = (int)h->rs.size();
+  Resident& R = h->rs[0];  // the copy that reports (every copy holds the same final state)
   Dev& d = R.d;
   R.have_state = false;
   cudaStream_t s = R.stream;
   struct Events {  // destroyed on every return path
-    cudaEvent_t e[5];
-    Events() {
-      for (auto& x : e) cudaEventCreate(&x);
+    std::vector<cudaEvent_t> e;
+    std::vector<int> dev;
+    cudaEvent_t make(int device) {
+      cudaSetDevice(device);
+      cudaEvent_t x;
+      cudaEventCreate(&x);
+      e.push_back(x);
+      dev.push_back(device);
+      return x;
     }
     ~Events() {
-      for (auto& x : e) cudaEventDestroy(x);
+      for (size_t i = 0; i < e.size(); ++i) {
+        cudaSetDevice(dev[i]);
+        cudaEventDestroy(e[i]);
+      }
+      if (!dev.empty()) cudaSetDevice(dev[0]);
     }
   } evs;
-  cudaEvent_t e0 = evs.e[0], e1 = evs.e[1], e2 = evs.e[2], s0 = evs.e[3], s1 = evs.e[4];
+  cudaEvent_t e0 = evs.make(R.device), e1 = evs.make(R.device), e2 = evs.make(R.device);
+  std::vector<cudaEvent_t> s0(nl), s1(nl);
+  for (int i = 0; i < nl; ++i) {
+    s0[i] = evs.make(h->rs[i].device);
+    s1[i] = evs.make(h->rs[i].device);
+  }
+  cudaSetDevice(R.device);
   cudaEventRecord(e0, s);
-  int grid = p1_grid_size(G.device);
-  if (G.grid_blocks > 0 && G.grid_blocks < grid) grid = (int)G.grid_blocks;
-  CKA(launch_reset(d, grid, s));
-  if (d.world > 1) {
-    // clear mailbox / counts / epoch, then make sure every rank has done so before anyone posts
-    CKA(cudaMemsetAsync(R.xhdr, 0, 1024, s));
-    int bst = dist_barrier(s);
-    if (bst) return bst;
+  // (sharded runs need no start-of-solve rendezvous: the exchange epochs grow monotonically over the life of the
+  // process and the mailboxes are never cleared, engine.cuh "cross-GPU exchange header")
+  // The whole fixpoint (:706-1556) is ONE persistent cooperative launch per device; the host only reads the
+  // status blocks back when they have finished.  With several local devices all launches are issued before any
+  // is waited for: the kernels meet each other at the sharded rounds.
+  for (int i = 0; i < nl; ++i) {
+    Resident& Ri = h->rs[i];
+    Dev& di = Ri.d;
+    CKA(cudaSetDevice(Ri.device));
+    int grid = p1_grid_size(Ri.device);
+    if (G.grid_blocks > 0 && G.grid_blocks < grid) grid = (int)G.grid_blocks;
+    CKA(launch_reset(di, grid, Ri.stream));
+    if (Ri.table_dirty) {
+      CKA(launch_clear_p2_table(di, Ri.stream));
+      Ri.table_dirty = false;
+    }
+    di.max_outer = (uint32_t)std::min<long long>(G.max_outer, 0x7fffffffLL);
+    di.p2_hash_mask = G.p2_hash_bits >= 56 ? 0x00ffffffffffffffULL : ((1ULL << G.p2_hash_bits) - 1ULL);
+    {
+      // from the whole problem, not the shard: every rank must take the same dense / sparse decision
+      const long long sm = G.sparse_max >= 0 ? G.sparse_max : std::max<long long>(4096, (long long)di.N / 32);
+      di.sparse_max = (uint32_t)std::min<long long>(sm, 0x7fffffffLL);
+    }
+    cudaEventRecord(s0[i], Ri.stream);
+    CKA(launch_solve(di, (unsigned int)std::min<long long>(G.max_rounds, 0x7fffffffLL), grid, Ri.stream));
+    cudaEventRecord(s1[i], Ri.stream);
+    CKA(cudaMemcpyAsync(Ri.h_status, di.st, sizeof(Status), cudaMemcpyDeviceToHost, Ri.stream));
   }
-  // the whole fixpoint (:706-1556) is ONE persistent cooperative launch; the host only reads the
-  // status block back when it has finished
-  if (R.table_dirty) {
-    CKA(launch_clear_p2_table(d, s));
-    R.table_dirty = false;
+  for (int i = 0; i < nl; ++i) {
+    CKA(cudaSetDevice(h->rs[i].device));
+    CKA(cudaStreamSynchronize(h->rs[i].stream));
   }
-  d.max_outer = (uint32_t)std::min<long long>(G.max_outer, 0x7fffffffLL);
-  d.p2_hash_mask = G.p2_hash_bits >= 56 ? 0x00ffffffffffffffULL : ((1ULL << G.p2_hash_bits) - 1ULL);
-  {
-    // from the whole problem, not the shard: every rank must take the same dense / sparse decision
-    const long long sm = G.sparse_max >= 0 ? G.sparse_max : std::max<long long>(4096, (long long)d.N / 32);
-    d.sparse_max = (uint32_t)std::min<long long>(sm, 0x7fffffffLL);
-  }
+  CKA(cudaSetDevice(R.device));
   int status = ECNE_OK;
   std::string err;
   float ms_sweep = 0;
-  cudaEventRecord(s0, s);
-  CKA(launch_solve(d, (unsigned int)std::min<long long>(G.max_rounds, 0x7fffffffLL), grid, s));
-  cudaEventRecord(s1, s);
-  CKA(cudaMemcpyAsync(R.h_status, d.st, sizeof(Status), cudaMemcpyDeviceToHost, s));
-  CKA(cudaStreamSynchronize(s));
-  cudaEventElapsedTime(&ms_sweep, s0, s1);
-  if (R.h_status->err)
-    status = -(int)R.h_status->err;
-  else if (R.h_status->rec_overflow)
-    status = ECNE_E_INTERNAL;
+  unsigned long long evals_total = 0, rule_evals_total = 0, dense_evals_total = 0;
+  for (int i = 0; i < nl; ++i) {
+    const Status& S = *h->rs[i].h_status;
+    float ms = 0;
+    cudaSetDevice(h->rs[i].device);
+    cudaEventElapsedTime(&ms, s0[i], s1[i]);
+    ms_sweep = std::max(ms_sweep, ms);  // the kernels run concurrently: the slowest one is the solve
+    if (status == ECNE_OK) {
+      if (S.err)
+        status = -(int)S.err;
+      else if (S.rec_overflow)
+        status = ECNE_E_INTERNAL;
+    }
+    evals_total += S.evals;  // sharded sweeps: every rank its own rows; replicated work is counted by rank 0 only
+    rule_evals_total += S.rule_evals;
+    dense_evals_total += S.dense_evals;
+  }
+  cudaSetDevice(R.device);
   const uint64_t outer = R.h_status->outer;
   if (getenv("ECNE_DEBUG_PROF")) {
     const Status& S = *R.h_status;
@@ -375,13 +521,12 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   const uint64_t launches = 1 + 1 + (d.n_known ? 1 : 0) + 1 + (d.n_targets ? 1 : 0);
   // the three whole-set sweeps of every outer round visit: P2 the rows that can still fire (counted by
   // the kernel), P3 / P4 the rows with the ABZ / IsZero shape
-  const unsigned long long rounds_total = R.h_status->rounds, evals_total = R.h_status->evals,
-                           rule_evals_total = R.h_status->rule_evals;
+  const unsigned long long rounds_total = R.h_status->rounds;
   const uint64_t phase_evals = d.rank == 0 ? outer * ((uint64_t)d.n_p3 + d.n_p4) : 0;  // replicated: counted once
   cudaEventRecord(e1, s);
   res->status = status;
   if (status != ECNE_OK) {
-    R.table_dirty = true;
+    for (auto& Ri : h->rs) Ri.table_dirty = true;
     cudaStreamSynchronize(s);
     return fail(status, err.empty() ? status_text(status) : err);
   }
@@ -433,10 +578,11 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   res->ms_exchange = 0;
   res->ms_sweep = ms_sweep;
   res->dense_rounds = R.h_status->dense_rounds;
-  res->dense_evals = R.h_status->dense_evals;
+  res->dense_evals = dense_evals_total;
   res->dense_cycles = R.h_status->dense_cycles;
   res->ms_device = ms_device;
   res->gpus_used = (uint64_t)d.world;
+  for (auto& Ri : h->rs) Ri.have_state = true;
   res->ms_total = R.ms_h2d + R.ms_classify + ms_solve + ms_d2h;
   R.have_state = true;
   return ECNE_OK;
@@ -445,8 +591,9 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
 // ---- report path (:1599-1635) ----------------------------------------------------------------------
 extern "C" int ecne_report_resident(ecne_resident_t* h, ecne_report_t* rep) {
   if (!h || !rep || !rep->bad_row_bits) return fail(ECNE_E_BADARG, "null argument");
-  Resident& R = h->r;
+  Resident& R = h->rs[0];
   const Dev& d = R.d;
+  cudaSetDevice(R.device);
   if (!R.have_state) return fail(ECNE_E_BADARG, "ecne_report_resident: no successful solve on this handle");
   cudaStream_t s = R.stream;
   Arena t;
@@ -545,6 +692,7 @@ extern "C" int ecne_dist_unique_id(uint8_t out[128]) {
 }
 extern "C" int ecne_dist_init(int rank, int world, const uint8_t unique_id[128]) {
   if (!G.inited) return fail(ECNE_E_CUDA, "call ecne_init first");
+  if (G.multi) return fail(ECNE_E_BADARG, "ecne_dist_init: this process drives several GPUs itself (ecne_init_multi)");
   if (world < 1 || world > ECNE_MAX_WORLD || rank < 0 || rank >= world) return fail(ECNE_E_BADARG, "bad rank/world");
   if (G.comm) {
     NCCL.CommDestroy(G.comm);
@@ -557,75 +705,86 @@ extern "C" int ecne_dist_init(int rank, int world, const uint8_t unique_id[128])
   if (!NCCL.load()) return fail(ECNE_E_NCCL, "cannot load libnccl.so.2");
   ncclUniqueId id;
   memcpy(&id, unique_id, 128);
+  cudaSetDevice(G.ctx[0]->device);
   if (NCCL.CommInitRank(&G.comm, world, id, rank) != ncclSuccess)
     return fail(ECNE_E_NCCL, "ncclCommInitRank failed");
   return ECNE_OK;
 }
 extern "C" int ecne_dist_rank(void) { return G.rank; }
-extern "C" int ecne_dist_world(void) { return G.world; }
+extern "C" int ecne_dist_world(void) { return G.total_world(); }
 
 namespace {
 // (Re)build the exchange channel so that every list holds at least `cap` records, and point the
-// resident's record lists / peer tables at it.  Collective: every rank calls it with the same cap.
-int setup_exchange(Resident& R, size_t cap) {
-  Dev& d = R.d;
-  cudaStream_t s = R.stream;
+// residents' record lists / peer tables at it.  Collective: every rank calls it with the same cap.
+int setup_exchange(ecne_resident& H, size_t cap) {
+  const int nl = G.n_local(), world = G.total_world();
   if (G.xcap < cap) {
-    for (int h = 0; h < G.world; ++h)
-      if (h != G.rank && G.xpeer[h]) cudaIpcCloseMemHandle(G.xpeer[h]);
-    if (G.xbuf) cudaFree(G.xbuf);
+    if (!G.multi)
+      for (int h = 0; h < world; ++h)
+        if (h != G.rank && G.xpeer[h]) cudaIpcCloseMemHandle(G.xpeer[h]);
     memset(G.xpeer, 0, sizeof(G.xpeer));
-    G.xbuf = nullptr;
     G.xcap = 0;
-    const size_t bytes = 4096 + 3 * cap * sizeof(Rec);
-    CKA(cudaMalloc((void**)&G.xbuf, bytes));
-    CKA(cudaMemset(G.xbuf, 0, 4096));
-    cudaIpcMemHandle_t mine;
-    CKA(cudaIpcGetMemHandle(&mine, G.xbuf));
-    // all-gather the handles through NCCL (device staging lives in the header's scratch area)
-    char* d_all = nullptr;
-    CKA(cudaMalloc((void**)&d_all, sizeof(cudaIpcMemHandle_t) * (size_t)(G.world + 1)));
-    CKA(cudaMemcpyAsync(d_all + sizeof(mine) * G.world, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
-    if (NCCL.AllGather(d_all + sizeof(mine) * G.world, d_all, sizeof(mine), ncclChar, G.comm, s) != ncclSuccess)
-      return fail(ECNE_E_NCCL, "ncclAllGather of the IPC handles failed");
-    std::vector<cudaIpcMemHandle_t> all(G.world);
-    CKA(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * G.world, cudaMemcpyDeviceToHost, s));
-    CKA(cudaStreamSynchronize(s));
-    cudaFree(d_all);
-    for (int h = 0; h < G.world; ++h) {
-      if (h == G.rank) {
-        G.xpeer[h] = G.xbuf;
-      } else {
-        void* p = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&p, all[h], cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess)
-          return fail(ECNE_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
-        G.xpeer[h] = (char*)p;
+    const size_t bytes = XH_BYTES + 3 * cap * sizeof(Rec);
+    for (int i = 0; i < nl; ++i) {
+      Ctx* c = G.ctx[i];
+      CKA(cudaSetDevice(c->device));
+      CKA(cudaDeviceSynchronize());
+      if (c->xbuf) cudaFree(c->xbuf);
+      c->xbuf = nullptr;
+      CKA(cudaMalloc((void**)&c->xbuf, bytes));
+      CKA(cudaMemset(c->xbuf, 0, XH_BYTES));
+      CKA(cudaDeviceSynchronize());  // zeroed before any peer can learn the address
+    }
+    CKA(cudaSetDevice(G.ctx[0]->device));
+    if (G.multi) {
+      for (int h = 0; h < nl; ++h) G.xpeer[h] = G.ctx[h]->xbuf;  // plain peer access inside one process
+    } else {
+      Ctx* c = G.ctx[0];
+      cudaStream_t s = c->stream;
+      cudaIpcMemHandle_t mine;
+      CKA(cudaIpcGetMemHandle(&mine, c->xbuf));
+      // all-gather the handles through NCCL
+      char* d_all = nullptr;
+      CKA(cudaMalloc((void**)&d_all, sizeof(cudaIpcMemHandle_t) * (size_t)(world + 1)));
+      CKA(cudaMemcpyAsync(d_all + sizeof(mine) * world, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+      if (NCCL.AllGather(d_all + sizeof(mine) * world, d_all, sizeof(mine), ncclChar, G.comm, s) != ncclSuccess)
+        return fail(ECNE_E_NCCL, "ncclAllGather of the IPC handles failed");
+      std::vector<cudaIpcMemHandle_t> all(world);
+      CKA(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * world, cudaMemcpyDeviceToHost, s));
+      CKA(cudaStreamSynchronize(s));
+      cudaFree(d_all);
+      for (int h = 0; h < world; ++h) {
+        if (h == G.rank) {
+          G.xpeer[h] = c->xbuf;
+        } else {
+          void* p = nullptr;
+          cudaError_t e = cudaIpcOpenMemHandle(&p, all[h], cudaIpcMemLazyEnablePeerAccess);
+          if (e != cudaSuccess)
+            return fail(ECNE_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+          G.xpeer[h] = (char*)p;
+        }
       }
     }
     G.xcap = cap;
   }
-  d.world = G.world;
-  d.rank = G.rank;
-  // d.rec_cap stays this problem's own capacity: the phase lists 3 / 4 live in the problem's arena with exactly
-  // that many slots, and the exchange lists (G.xcap >= cap slots each, the stride every rank uses) hold at least
-  // as many
-  for (int l = 0; l < 3; ++l) d.recs[l] = (Rec*)(G.xbuf + 4096 + (size_t)l * G.xcap * sizeof(Rec));
-  for (int h = 0; h < G.world; ++h) {
-    d.xflag[h] = (unsigned long long*)G.xpeer[h];
-    for (int l = 0; l < 3; ++l) d.xrecs[h][l] = (Rec*)(G.xpeer[h] + 4096 + (size_t)l * G.xcap * sizeof(Rec));
+  for (int i = 0; i < nl; ++i) {
+    Resident& R = H.rs[i];
+    Dev& d = R.d;
+    char* own = G.ctx[i]->xbuf;
+    d.world = world;
+    d.rank = G.multi ? i : G.rank;
+    // d.rec_cap stays this problem's own capacity: the phase lists 3 / 4 live in the problem's arena with exactly
+    // that many slots, and the exchange lists (G.xcap >= cap slots each, the stride every rank uses) hold at least
+    // as many
+    for (int l = 0; l < 3; ++l) d.recs[l] = (Rec*)(own + XH_BYTES + (size_t)l * G.xcap * sizeof(Rec));
+    for (int h = 0; h < world; ++h) {
+      d.xflag[h] = (unsigned long long*)G.xpeer[h];
+      for (int l = 0; l < 3; ++l) d.xrecs[h][l] = (Rec*)(G.xpeer[h] + XH_BYTES + (size_t)l * G.xcap * sizeof(Rec));
+    }
+    d.xcnt = (unsigned int*)(own + XH_XCNT_OFF);
+    d.xepoch = (unsigned int*)(own + XH_EPOCH_OFF);
+    R.xhdr = own;
   }
-  d.xcnt = (unsigned int*)(G.xbuf + 256);
-  d.xepoch = (unsigned int*)(G.xbuf + 512);
-  R.xhdr = G.xbuf;
-  return ECNE_OK;
-}
-
-// device-side rendezvous of all ranks on the stream (used once per solve, before the first kernel)
-int dist_barrier(cudaStream_t s) {
-  int* scratch = (int*)(G.xbuf + 1024);
-  if (NCCL.AllReduce(scratch, scratch, 1, ncclInt, ncclSum, G.comm, s) != ncclSuccess)
-    return fail(ECNE_E_NCCL, "ncclAllReduce (start barrier) failed");
   return ECNE_OK;
 }
 }  // namespace

@@ -166,6 +166,7 @@ struct Dev {
   uint32_t* p2_next;          // [N] member list links
   uint32_t* p2_slot;          // [N] table slot of each candidate
   uint32_t* p2_k;             // [N] size of its unknown set
+  uint32_t* p2_open;          // [(N + 31) / 32] bit per row: the linear-system sweep still has to look at it
   uint32_t h_mask;
   unsigned long long p2_hash_mask;  // testing knob "p2_hash_bits": fewer hash bits force set-hash collisions
   uint32_t sparse_max;        // a round with at most this many frontier records is frontier-driven
@@ -236,6 +237,27 @@ __device__ __forceinline__ uint32_t or_flag(uint8_t* F, uint32_t w, uint32_t bit
 
 __device__ __forceinline__ bool is01(uint32_t f) { return (f & (WF_UB01 | WF_NOT01)) == WF_UB01; }
 
+// ---- cross-GPU exchange header (one per rank, mapped into every peer) ---------------------------------
+// u64 words: [XH_POST + 16 * (epoch & 1) + r]     rank r's post of a sharded round: {epoch, bound bit, record count}
+//            [XH_POST + 16 * (epoch & 1) + 8 + r] ... its second word: {epoch, heavy bit, distinct wires changed}
+//            [XH_ACK + r]                          the last epoch whose records rank r has finished pulling from us
+// Posts alternate between two slots by epoch parity: a rank can only post epoch e + 2 after every peer has posted
+// e + 1, which a peer does after it has read e — so a post is never overwritten before it has been read.  Epochs
+// grow monotonically over the life of the process (nothing is ever cleared, no start-of-solve rendezvous needed).
+#define XH_POST 0
+#define XH_ACK 32
+#define XH_WORDS 64        // u64 words of mailbox
+#define XH_XCNT_OFF 1024   // byte offset of xcnt u32[4][ECNE_MAX_WORLD]
+#define XH_EPOCH_OFF 2048  // byte offset of the persistent epoch counter
+#define XH_BYTES 4096
+
+__device__ __forceinline__ void spin_guard(const Dev& d, unsigned long long& spins) {
+  if (++spins > (1ULL << 24)) {  // (~10 s) a peer died or diverged: fail loudly instead of hanging the box
+    atomicCAS(&d.st->err, 0u, (unsigned int)(-ECNE_E_NCCL));
+    spins = 0;
+  }
+}
+
 // Cross-GPU part of the round barrier, executed by the last local arriver only: post
 // {epoch, bound bit, own record count} into every peer's mailbox (NVLink peer store), then wait until
 // every peer has posted the same epoch into ours.  Returns the total record count (bit 31: a bound
@@ -247,25 +269,24 @@ __device__ __forceinline__ unsigned int cross_gpu_exchange(const Dev& d, unsigne
   unsigned int own_d = *((volatile const unsigned int*)(d.dcnt + list)) & 0x7fffffffu;
   if (*((volatile const unsigned int*)(d.bnd_flag + list)) & 2u) own_d |= 0x80000000u;
   const unsigned long long word2 = ((unsigned long long)xe << 32) | own_d;
+  const unsigned int par = XH_POST + 16u * (xe & 1u);
   asm volatile("fence.acq_rel.sys;" ::: "memory");
   for (int h = 0; h < d.world; ++h) {
-    unsigned long long* slot = d.xflag[h] + d.rank;
-    asm volatile("st.relaxed.sys.u64 [%0], %1;" ::"l"(slot + ECNE_MAX_WORLD), "l"(word2) : "memory");
+    unsigned long long* slot = d.xflag[h] + par + d.rank;
+    asm volatile("st.relaxed.sys.u64 [%0], %1;" ::"l"(slot + 8), "l"(word2) : "memory");
     asm volatile("st.release.sys.u64 [%0], %1;" ::"l"(slot), "l"(word) : "memory");
   }
   unsigned int total = 0, bnd = 0, dtot = 0, heavy = 0;
   for (int h = 0; h < d.world; ++h) {
-    const unsigned long long* slot = d.xflag[d.rank] + h;
+    const unsigned long long* slot = d.xflag[d.rank] + par + h;
     unsigned long long v, v2;
     unsigned long long spins = 0;
     do {
       asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
-      if (++spins > (1ULL << 28)) {  // a peer died or diverged: fail loudly instead of hanging the box
-        atomicCAS(&d.st->err, 0u, (unsigned int)(-ECNE_E_NCCL));
-        break;
-      }
-    } while ((unsigned int)(v >> 32) < xe);
-    asm volatile("ld.relaxed.sys.u64 %0, [%1];" : "=l"(v2) : "l"(slot + ECNE_MAX_WORLD) : "memory");  // stored before v
+      spin_guard(d, spins);
+      if (*((volatile unsigned int*)&d.st->err)) break;
+    } while ((unsigned int)(v >> 32) != xe);
+    asm volatile("ld.relaxed.sys.u64 %0, [%1];" : "=l"(v2) : "l"(slot + 8) : "memory");  // stored before v
     unsigned int nh = (unsigned int)v & 0x7fffffffu;
     bnd |= (unsigned int)v & 0x80000000u;
     d.xcnt[list * ECNE_MAX_WORLD + h] = nh;
@@ -277,6 +298,28 @@ __device__ __forceinline__ unsigned int cross_gpu_exchange(const Dev& d, unsigne
   d.xcnt[3 * ECNE_MAX_WORLD + 1] = heavy ? 1u : 0u;
   if (total > 0x7fffffffu) total = 0x7fffffffu;
   return total | bnd;
+}
+// "I have pulled your records of epoch xe": posted to every peer by one thread after the pull's grid barrier
+__device__ __forceinline__ void cross_gpu_ack(const Dev& d, unsigned int xe) {
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  for (int h = 0; h < d.world; ++h)
+    if (h != d.rank) {
+      unsigned long long* slot = d.xflag[h] + XH_ACK + d.rank;
+      asm volatile("st.release.sys.u64 [%0], %1;" ::"l"(slot), "l"((unsigned long long)xe) : "memory");
+    }
+}
+// Every peer has pulled our records of epoch xe: the lists they live in may be overwritten from now on.
+__device__ __forceinline__ void cross_gpu_wait_acks(const Dev& d, unsigned int xe) {
+  for (int h = 0; h < d.world; ++h) {
+    if (h == d.rank) continue;
+    const unsigned long long* slot = d.xflag[d.rank] + XH_ACK + h;
+    unsigned long long v, spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+      spin_guard(d, spins);
+      if (*((volatile unsigned int*)&d.st->err)) break;
+    } while ((unsigned int)v < xe);  // epochs of one process never wrap in practice (2^32 sharded rounds)
+  }
 }
 
 #ifdef ECNE_PROFILE

@@ -63,9 +63,12 @@ struct SlabPool {
     free_slabs.clear();
   }
 };
+// One pool per device this process drives (ecne_init: one; ecne_init_multi: several); an Arena allocates from the
+// pool of the device that is current when it makes its first allocation.
 SlabPool& slab_pool();
 
 struct Arena {
+  SlabPool* pool = nullptr;
   std::vector<Slab> slabs;
   size_t off = 0;  // bump offset inside slabs.back()
   size_t bytes = 0;
@@ -74,7 +77,8 @@ struct Arena {
     size_t sz = ((n ? n : 1) * sizeof(T) + 255) & ~(size_t)255;
     if (slabs.empty() || off + sz > slabs.back().size) {
       Slab s;
-      cudaError_t e = slab_pool().acquire(sz, &s);
+      if (!pool) pool = &slab_pool();
+      cudaError_t e = pool->acquire(sz, &s);
       if (e != cudaSuccess) return e;
       slabs.push_back(s);
       off = 0;
@@ -85,7 +89,7 @@ struct Arena {
     return cudaSuccess;
   }
   void release() {
-    for (auto& s : slabs) slab_pool().give_back(s);
+    for (auto& s : slabs) pool->give_back(s);
     slabs.clear();
     off = 0;
     bytes = 0;
@@ -97,6 +101,8 @@ struct Resident {
   Dev d;
   Arena arena;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;  // side stream of the set-up (bound-table chain)
+  int device = 0;
   // host mirrors needed by the solve loop
   uint64_t n_rows = 0, n_vars = 0, n_targets = 0;
   // finalisation buffers

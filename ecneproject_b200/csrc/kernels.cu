@@ -658,7 +658,8 @@ __device__ __forceinline__ void sparse_row(const Dev&, int rbuf, int wbuf, int l
                                            uint32_t bepoch, unsigned int gr, uint32_t* s_long,
                                            unsigned int* s_nlong, unsigned long long& evals, bool all_rows) {
   const Dev& d = c_dev;
-  if (row == 0xffffffffu || (!all_rows && (row < d.row_lo || row >= d.row_hi))) return;
+  (void)all_rows;  // frontier-driven rounds evaluate every listed row on every rank
+  if (row == 0xffffffffu) return;
   const uint4* rp = reinterpret_cast<const uint4*>(d.rec + row);
   const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
   const uint32_t latched = __ldcg(d.solved + row);  // in flight together with the record
@@ -691,7 +692,7 @@ __device__ __forceinline__ void sparse_row(const Dev&, int rbuf, int wbuf, int l
 __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, unsigned int list,
                                                         unsigned int prev_list, unsigned int prev_n,
                                                         uint32_t bepoch, unsigned int gr, bool solo,
-                                                        bool prev_sharded) {
+                                                        unsigned int prev_own) {
   const Dev& d = c_dev;
   __shared__ uint32_t s_long[SP_LONG_CAP];
   __shared__ uint32_t s_heavy[SP_HEAVY_CAP];
@@ -708,19 +709,17 @@ __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, un
   }
   __syncthreads();
   unsigned long long ev = 0;
-  // a list written by a sharded round is spread over the ranks' buffers; one written by replicated rounds
-  // (solo, every rank evaluates every row) or by the phases is complete locally
-  const int nsrc = (d.world > 1 && prev_sharded) ? d.world : 1;
-  for (int h = 0; h < nsrc; ++h) {
-    const bool own = nsrc == 1 || h == d.rank;
-    const Rec* pr = nsrc == 1 ? d.recs[prev_list] : d.xrecs[h][prev_list];
-    unsigned int nh = nsrc == 1 ? prev_n : __ldcg(d.xcnt + prev_list * ECNE_MAX_WORLD + h);
-    if (nh > d.rec_cap) nh = d.rec_cap;
+  // the list is complete locally (after a sharded round the peers' records were appended behind this rank's own
+  // `prev_own` ones when they were pulled and applied to both buffers): only the own records still need their replay
+  {
+    const Rec* pr = d.recs[prev_list];
+    const unsigned int nh = prev_n > d.rec_cap ? d.rec_cap : prev_n;
     for (uint32_t i = first; i < nh; i += stride) {
+      const bool own = i < prev_own;
 #ifdef ECNE_PROFILE
       long long q0 = clock64();
 #endif
-      const Rec r = ld_peer_rec(pr + i);
+      const Rec r = ld_peer_rec(pr + i);  // (volatile: written by other SMs during the previous round)
       // {rows listed for the wire, the first three of them}: one 16-byte load covers 97 % of the wires
       const uint4 hd = __ldcg(reinterpret_cast<const uint4*>(d.inv_head) + r.wire);
 #ifdef ECNE_PROFILE
@@ -790,9 +789,10 @@ __device__ __noinline__ unsigned long long sparse_round(const Dev&, int rbuf, un
 }
 
 // The P2 test of one short row from its inline record and the six gathered state bytes (:1364-1385): every
-// non-unique wire appears in C only; k == 1 is decided on the spot, k >= 2 rows become candidates.
-__device__ __forceinline__ void p2_scan_short(const Dev& d, int pl, uint32_t row, const InlineRow& r, const uint32_t* ff) {
-  if (r.rf & RF_LONG) return;
+// non-unique wire appears in C only; k == 1 is decided on the spot, k >= 2 rows become candidates.  Returns true
+// when the sweep never has to look at the row again.
+__device__ __forceinline__ bool p2_scan_short(const Dev& d, int pl, uint32_t row, const InlineRow& r, const uint32_t* ff) {
+  if (r.rf & RF_LONG) return true;  // long rows are scanned by a warp each, from their own list
   const uint32_t nAB = r.meta & 0xffu;
   uint32_t kk = 0, w1 = 0;
   bool bad = false;
@@ -811,12 +811,14 @@ __device__ __forceinline__ void p2_scan_short(const Dev& d, int pl, uint32_t row
       }
     }
   }
-  if (bad || kk == 0) return;
-  if (d.solved[row] & 1) return;  // equation_solved rows take no part (:1360)
+  if (!bad && kk == 0) return true;  // every wire is unique: the row can never qualify again
+  if (bad) return false;             // a non-unique wire in A or B (:1366, :1378): may qualify later
+  if (d.solved[row] & 1) return true;  // equation_solved rows take no part (:1360)
   if (kk == 1)
     emit(d, 1, pl, w1, WF_U | WF_K);
   else
     p2_candidate(d, row, hs, hx, kk);
+  return false;
 }
 
 // Rounds whose frontier is at most 32 records are run by WARP 0 of block 0 alone (most of ecdsa's rounds
@@ -978,7 +980,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
   const uint32_t kmask = per_thread < LiveMask::BITS ? per_thread : LiveMask::BITS;
   const uint32_t warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
-  unsigned int xe = d.world > 1 ? *d.xepoch : 0u;  // cross-GPU epoch (same on every rank)
+  unsigned int xe = d.world > 1 ? *d.xepoch : 0u;  // cross-GPU epoch (same on every rank, persists over solves)
+  unsigned int ack_pending = 0;                    // epoch of a sharded round whose lists peers may still be reading
   unsigned long long evals = 0, ruleevals = 0, devals = 0, dcycles = 0;
   unsigned int rounds_total = 0, dense_rounds = 0;
   unsigned int gr = 0;  // Jacobi round counter of the solve (stamps the long-row queue)
@@ -1030,10 +1033,16 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       // `dn`: the number of distinct wires the previous round changed.  Mode decisions (dense / sparse /
       // solo) use it instead of the record count on sharded runs, because it is the same on every rank
       unsigned int prev_dn = d.world > 1 ? __ldcg(d.dcnt + pl_r) : n_pl;
-      bool prev_sharded = false;  // the phase list is complete on every rank
+      unsigned int prev_own = prev_n;  // leading records of the list that still have to be replayed into the write
+                                       // buffer (all of them, except after a sharded round: the phase list is complete)
       bool dense = outer == 1 || prev_dn > d.sparse_max || (__ldcg(d.bnd_flag + pl_r) & 2u) != 0;
       unsigned int round = 0;
       while (true) {
+        if (ack_pending) {  // the peers may still be reading the record lists of our last sharded round
+          if (threadIdx.x == 0) cross_gpu_wait_acks(d, ack_pending);
+          __syncthreads();
+          ack_pending = 0;
+        }
         if (!dense && prev_dn <= SOLO_MAX) {
           // ---- solo: while the frontier stays small, block 0 runs the Jacobi rounds alone; a round
           // boundary is a block barrier + one release fence + one acquire load (which also drops this
@@ -1041,7 +1050,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           unsigned int n = 0;
           if (blockIdx.x == 0) {
             while (true) {
-              if (prev_n <= WARP_SOLO_MAX && !prev_sharded) {
+              if (prev_n <= WARP_SOLO_MAX && prev_own == prev_n) {
                 // at most 32 records: warp 0 chases them alone, for as many rounds as that stays so
                 if (threadIdx.x == 0) {
                   s_ws.list = list;
@@ -1080,6 +1089,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
                 if (n == 0 || s_solo[2] > SOLO_MAX || (s_solo[1] & 2u) || round >= max_rounds) break;
                 prev_list = list;
                 prev_n = n;
+                prev_own = n;
                 list = (list + 1) % 3;
                 rbuf ^= 1;
                 continue;
@@ -1088,7 +1098,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
 #ifdef ECNE_PROFILE
               long long z0 = clock64(), z1 = 0, z2 = 0, z3 = 0, z4 = 0;
 #endif
-              const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, true, prev_sharded);
+              const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, true, prev_own);
               if (d.rank == 0) {  // replicated work is counted once
                 evals += ev;
                 ruleevals += ev;
@@ -1145,7 +1155,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               if (n == 0 || s_solo[2] > SOLO_MAX || (s_solo[1] & 2u) || round >= max_rounds) break;
               prev_list = list;
               prev_n = n;
-              prev_sharded = false;  // written by this (replicated) round: complete locally
+              prev_own = n;  // written by this (replicated) round: every record is this rank's own
               list = (list + 1) % 3;
               rbuf ^= 1;
             }
@@ -1180,12 +1190,13 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           list = (list + 1) % 3;
           rbuf ^= 1;
           prev_dn = sdn;
-          prev_sharded = false;
+          prev_own = prev_n;
           dense = sdn > d.sparse_max || hv != 0;
           continue;
         }
         const int wbuf = rbuf ^ 1;
         const uint8_t* F = d.F[rbuf];
+        const bool sharded = d.world > 1 && dense;  // only dense sweeps are split over the ranks
         gr += 1;
         long long tc0 = 0;
         if (dense && tid == 0) tc0 = clock64();
@@ -1194,9 +1205,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           long long dz1 = clock64();
 #endif
           // (b) replay the previous round's own records into the buffer written this round
-          if (prev_n) {
+          if (prev_own) {
             const Rec* pr = d.recs[prev_list];
-            for (uint32_t j = threadIdx.x; blockIdx.x + j * gridDim.x < prev_n; j += blockDim.x) {
+            for (uint32_t j = threadIdx.x; blockIdx.x + j * gridDim.x < prev_own; j += blockDim.x) {
               Rec r = pr[blockIdx.x + j * gridDim.x];
               apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
               consume_rec(d, prev_list, r.wire);
@@ -1294,15 +1305,19 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           }
 #endif
         } else {
-          const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, false, prev_sharded);
-          evals += ev;
-          ruleevals += ev;
+          // frontier-driven rounds are never split over the ranks: every rank evaluates every listed row (a cross-GPU
+          // exchange costs more than such a round), so its record list is complete locally afterwards
+          const unsigned long long ev = sparse_round(d, rbuf, list, prev_list, prev_n, bepoch, gr, false, prev_own);
+          if (d.rank == 0) {  // replicated work is counted once
+            evals += ev;
+            ruleevals += ev;
+          }
         }
-        xe += 1;
         unsigned int n;
         bool heavy = false;  // a wire with very many rows changed: sweep densely instead of chasing its list
         unsigned int dn;
-        if (d.world > 1) {
+        if (sharded) {
+          xe += 1;
           n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list, &d, list, xe);
           bepoch += n >> 31;
           n &= 0x7fffffffu;
@@ -1314,13 +1329,16 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           const unsigned int bf = __ldcg(d.bnd_flag + list);
           bepoch += bf & 1u;
           heavy = (bf & 2u) != 0;
-          dn = n;
+          dn = d.world > 1 ? __ldcg(d.dcnt + list) : n;
         }
         unsigned int n_own = n;
-        if (d.world > 1) {
-          // pull the peers' records of this round over NVLink and apply them to BOTH local buffers (the
-          // buffer read next round must already contain them), then a local barrier
+        if (sharded) {
+          // pull the peers' records of this round over NVLink, apply them to BOTH local buffers (the buffer read
+          // next round must already contain them) and append them behind this rank's own records: the local list is
+          // complete afterwards and nobody reads a peer's list again once the round's acknowledgement is out
           n_own = __ldcg(d.xcnt + list * ECNE_MAX_WORLD + d.rank);
+          if (n_own > d.rec_cap) n_own = d.rec_cap;
+          unsigned int base = n_own;
           for (int h = 0; h < d.world; ++h) {
             if (h == d.rank) continue;
             const unsigned int nh = __ldcg(d.xcnt + list * ECNE_MAX_WORLD + h);
@@ -1329,9 +1347,18 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               Rec r = ld_peer_rec(pr + j);
               apply_update(d, 0, r.wire, r.bits, r.lbr, r.ubr);
               apply_update(d, 1, r.wire, r.bits, r.lbr, r.ubr);
+              if (base + j < d.rec_cap)
+                d.recs[list][base + j] = r;
+              else
+                d.st->rec_overflow = 1;
             }
+            base += nh < d.rec_cap ? nh : d.rec_cap;
           }
-          grid_barrier(d.barrier, epoch, nullptr);
+          grid_sync_flip(d.barrier + 64);
+          // tell the peers that their lists of this round have been read here; our own lists of this round must
+          // not be overwritten before every peer has said the same (checked when the next round starts)
+          if (tid == 0) cross_gpu_ack(d, xe);
+          ack_pending = xe;
         }
         if (tid == 0 && d.prof && gr < 4000) {
           d.prof[4 * gr + 0] = (unsigned long long)(clock64() - tp);
@@ -1355,17 +1382,18 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           atomicAdd(&d.st->prog, n);
         }
         if (n_own > d.rec_cap) n_own = d.rec_cap;
+        if (n > d.rec_cap) n = d.rec_cap;
         if (n == 0) break;  // W already holds every earlier record: both buffers are complete
         if (round >= max_rounds) {
           if (tid == 0) raise(d, ECNE_E_NOCONVERGE);
           break;
         }
         prev_list = list;
-        prev_n = n_own;
+        prev_n = n;        // the whole round's records (after a sharded round: own ones first, then the peers')
+        prev_own = n_own;  // ... of which these still have to be replayed into the other buffer
         list = (list + 1) % 3;
         rbuf = wbuf;
         prev_dn = dn;
-        prev_sharded = d.world > 1;  // a grid round on a sharded run leaves its records spread over the ranks
         dense = dn > d.sparse_max || heavy;
       }
       rounds_total += round;
@@ -1380,57 +1408,45 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
 #ifdef ECNE_PROFILE
       pz0 = clock64();
 #endif
-      if (d.world == 1) {
-        evals += live.count();  // one visit of the linear-system sweep per row (:1359)
-        // two rows in flight; all six state bytes of a row are gathered before any is looked at (unused
-        // slots hold the constant wire 1, which is unique)
-        for (LiveMask m = live; m.any();) {
-          int kk2[P1_INFLIGHT];
-          InlineRow rr[P1_INFLIGHT];
-          uint32_t ff[P1_INFLIGHT][ROWREC_INLINE];
-#pragma unroll
-          for (int h = 0; h < P1_INFLIGHT; ++h) kk2[h] = m.pop();
-#pragma unroll
-          for (int h = 0; h < P1_INFLIGHT; ++h) {
-            const int k = kk2[h] >= 0 ? kk2[h] : kk2[0];
-            if (k < ks)
-              unpack_row(sm_rec[(2 * k) * blockDim.x + threadIdx.x], sm_rec[(2 * k + 1) * blockDim.x + threadIdx.x], rr[h]);
-            else
-              load_row(d, d.row_lo + tid + (uint32_t)k * nthreads, rr[h]);
-          }
-#pragma unroll
-          for (int h = 0; h < P1_INFLIGHT; ++h)
-#pragma unroll
-            for (int j = 0; j < ROWREC_INLINE; ++j)
-              ff[h][j] = (kk2[h] >= 0 && (rr[h].meta & 0x10000u)) ? ld_flag(F, rr[h].c[j]) : (uint32_t)WF_U;
-#pragma unroll
-          for (int h = 0; h < P1_INFLIGHT; ++h)
-            if (kk2[h] >= 0) p2_scan_short(d, pl, d.row_lo + tid + (uint32_t)kk2[h] * nthreads, rr[h], ff[h]);
-        }
-        for (uint32_t k = kmask; k < per_thread; ++k) {
-          uint32_t r = tid + k * nthreads;
-          if (r < rows && !(d.rflags[d.row_lo + r] & RF_LONG) && !(d.solved[d.row_lo + r] & 1))
-            p2_scan_row<1>(d, 0, pl, d.row_lo + r);
-        }
-      } else {
-        // sharded: every rank scans every row (same candidates everywhere, no exchange), streaming the
-        // inline row records from HBM/L2, two rows in flight
-        for (uint32_t row0 = tid; row0 < d.N; row0 += 2 * nthreads) {
-          const uint32_t row1 = row0 + nthreads;
-          const bool two = row1 < d.N;
+      // One bit per row says whether the sweep still has to look at it: a row all of whose wires are unique (or
+      // that is latched as solved) can never qualify again — uniqueness is monotone — and is closed by the scan
+      // that finds it so.  A warp takes 32 consecutive rows (one word of the bitmap, two words in flight), its
+      // lanes one row each: one coalesced 1 KB read of the open rows' records and their state-byte gathers.  On a
+      // sharded run every rank scans every open row (same state everywhere => same candidates, no exchange);
+      // the visits are counted once.
+      {
+        const uint32_t n_words = (d.N + 31u) / 32u;
+        const uint32_t gw = blockIdx.x * warps_per_block + warp_in_block, nw = gridDim.x * warps_per_block;
+        for (uint32_t wi = gw; wi < n_words; wi += 2 * nw) {
+          uint32_t open[2];
           InlineRow rr[2];
           uint32_t ff[2][ROWREC_INLINE];
-          load_row(d, row0, rr[0]);
-          load_row(d, two ? row1 : row0, rr[1]);
+          bool mine[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t w = wi + (uint32_t)h * nw;
+            open[h] = w < n_words ? d.p2_open[w] : 0u;
+            mine[h] = ((open[h] >> lane) & 1u) != 0;
+          }
+          if ((open[0] | open[1]) == 0u) continue;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (mine[h]) load_row(d, (wi + (uint32_t)h * nw) * 32u + lane, rr[h]);
 #pragma unroll
           for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int j = 0; j < ROWREC_INLINE; ++j)
-              ff[h][j] = (rr[h].meta & 0x10000u) ? ld_flag(F, rr[h].c[j]) : (uint32_t)WF_U;
-          p2_scan_short(d, pl, row0, rr[0], ff[0]);
-          if (two) p2_scan_short(d, pl, row1, rr[1], ff[1]);
-          // replicated work is counted once, by the rank that owns the row
-          evals += (row0 >= d.row_lo && row0 < d.row_hi) + (two && row1 >= d.row_lo && row1 < d.row_hi);
+              ff[h][j] = (mine[h] && (rr[h].meta & 0x10000u)) ? ld_flag(F, rr[h].c[j]) : (uint32_t)WF_U;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            bool close = false;
+            if (mine[h]) close = p2_scan_short(d, pl, (wi + (uint32_t)h * nw) * 32u + lane, rr[h], ff[h]);
+            const uint32_t cm = __ballot_sync(0xffffffffu, close);
+            if (lane == 0 && open[h]) {
+              if (cm) d.p2_open[wi + (uint32_t)h * nw] = open[h] & ~cm;
+              if (d.rank == 0) evals += (unsigned int)__popc(open[h]);  // one visit of the sweep per open row (:1359)
+            }
+          }
         }
       }
 #ifdef ECNE_PROFILE
@@ -1439,11 +1455,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       for (uint32_t i = blockIdx.x + warp_in_block * gridDim.x; i < d.n_long; i += warps_per_block * gridDim.x) {
         const uint32_t row = d.long_rows[i];
         if (d.solved[row] & 1) continue;
-        if (d.world == 1 && d.long_done[i]) continue;
-        if (d.world == 1)
-          p2_scan_row<32>(d, 0, pl, row, d.long_p2 + i, __ldcg(d.long_stamp + i), last_dense_gr, gr);
-        else
-          p2_scan_row<32>(d, 0, pl, row);
+        if (d.long_done[i]) continue;  // no non-unique wire left in C (known to the ranks that evaluated the row)
+        p2_scan_row<32>(d, 0, pl, row, d.long_p2 + i, __ldcg(d.long_stamp + i), last_dense_gr, gr);
       }
     }
 #ifdef ECNE_PROFILE
@@ -1529,6 +1542,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       }
     }
   }
+  if (ack_pending && threadIdx.x == 0) cross_gpu_wait_acks(d, ack_pending);  // the next solve rewrites the lists
   // ---- statistics: one atomic per warp ---------------------------------------------------------------
   for (int o = 16; o > 0; o >>= 1) {
     evals += __shfl_xor_sync(0xffffffffu, evals, o);
@@ -1715,6 +1729,7 @@ __global__ void k_reset_all(Dev d) {
     }
   }
   if (i <= d.N) d.solved[i] = 0;  // rows
+  if (i < (d.N + 31u) / 32u) d.p2_open[i] = (i + 1u) * 32u <= d.N ? 0xffffffffu : ((1u << (d.N & 31u)) - 1u);
   if (i < d.N) d.c5sig[i] = 0xffffffffu;
   if (i < d.n_long) {
     d.long_done[i] = 0;
@@ -1766,26 +1781,34 @@ cudaError_t launch_clear_p2_table(const Dev& d, cudaStream_t s) {
 
 int p1_threads() { return P1_THREADS; }
 static size_t solve_max_smem() { return (size_t)P1_MAX_KS * 2 * sizeof(uint4) * P1_THREADS; }  // 192 KB of row records
+#define ECNE_MAX_DEVICES 64
 int p1_grid_size(int device) {
-  static int cached = 0;
-  if (cached) return cached;
+  static int cached[ECNE_MAX_DEVICES] = {0};
+  if (device < 0 || device >= ECNE_MAX_DEVICES) return 0;
+  if (cached[device]) return cached[device];
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  // (function attributes are per device: the caller has made `device` current)
   cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_max_smem());
-  cached = sms;  // one 1024-thread block per SM (persistent, cooperative)
-  return cached;
+  cached[device] = sms;  // one block per SM (persistent, cooperative)
+  return cached[device];
 }
 
 // the whole fixpoint: one cooperative launch
 cudaError_t launch_solve(const Dev& d, unsigned int max_rounds, int grid, cudaStream_t s) {
   // the descriptor goes to constant memory (skipped when it is what the last solve used)
-  static Dev last;
-  static bool have_last = false;
-  if (!have_last || memcmp(&last, &d, sizeof(Dev)) != 0) {
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_dev, &d, sizeof(Dev), 0, cudaMemcpyHostToDevice, s);
+  // (per device: every device has its own copy of the __constant__ symbol; the staging copy must outlive the
+  // asynchronous upload, hence one static slot per device)
+  static Dev last[ECNE_MAX_DEVICES];
+  static bool have_last[ECNE_MAX_DEVICES] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= ECNE_MAX_DEVICES) return cudaErrorInvalidDevice;
+  if (!have_last[dev] || memcmp(&last[dev], &d, sizeof(Dev)) != 0) {
+    memcpy(&last[dev], &d, sizeof(Dev));
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_dev, &last[dev], sizeof(Dev), 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
-    memcpy(&last, &d, sizeof(Dev));
-    have_last = true;
+    have_last[dev] = true;
   }
   unsigned int mr = max_rounds;
   const uint32_t rows = d.row_hi - d.row_lo;

@@ -937,14 +937,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   CK(cudaMemsetAsync(d_next, 0, 2 * sizeof(unsigned int), s));
   // The bound-table chain (values -> sort -> ranks) only depends on the classification, and the sweep
   // layout below does not depend on it: it runs on a side stream, concurrently with the layout kernels.
-  static cudaStream_t s2 = nullptr;
-  static int s2_dev = -1;
-  int cur_dev = 0;
-  cudaGetDevice(&cur_dev);
-  if (!s2 || s2_dev != cur_dev) {  // one side stream per process (one process per GPU)
-    CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-    s2_dev = cur_dev;
-  }
+  cudaStream_t s2 = R->side;  // one side stream per device context (abi.cu)
   cudaEvent_t ev_fork, ev_join;
   cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
@@ -1115,6 +1108,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
     CK(A.alloc(&d.p2_next, N));
     CK(A.alloc(&d.p2_slot, N));
     CK(A.alloc(&d.p2_k, N));
+    CK(A.alloc(&d.p2_open, (N + 31) / 32 + 1));
   }
 
   // ---- wire state, records, scratch -----------------------------------------------------------

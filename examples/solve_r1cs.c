@@ -3,7 +3,10 @@
  *
  *   gcc -std=c99 -Iinclude examples/solve_r1cs.c -Lecneproject_b200 -lecne_host -lecne_b200 \
  *       -Wl,-rpath,$PWD/ecneproject_b200 -o solve_r1cs
- *   ./solve_r1cs [--secp-solve] main.r1cs [trusted.r1cs TrustedName]...
+ *   ./solve_r1cs [--gpus N] [--secp-solve] main.r1cs [trusted.r1cs TrustedName]...
+ *
+ * --gpus N: ONE process drives the GPUs 0 .. N-1 of the box (ecne_init_multi): the rows are sharded over them,
+ * the result is identical to the one-GPU run.
  *
  * Mirrors solveWithTrustedFunctions (R1CSConstraintSolver.jl:502-581) for trusted circuits given longest first.
  * Exit code: 0 sound, 1 potentially unsound, 2 error (the message of the failing library is printed; without a
@@ -17,13 +20,19 @@
 
 int main(int argc, char** argv) {
   int secp_solve = 0; /* the secp_solve keyword of solveWithTrustedFunctions (:511) */
+  int gpus = 1;
+  if (argc > 2 && strcmp(argv[1], "--gpus") == 0) {
+    gpus = atoi(argv[2]);
+    argc -= 2;
+    argv += 2;
+  }
   if (argc > 1 && strcmp(argv[1], "--secp-solve") == 0) {
     secp_solve = 1;
     --argc;
     ++argv;
   }
   if (argc < 2 || (argc % 2) != 0) {
-    fprintf(stderr, "usage: %s [--secp-solve] main.r1cs [trusted.r1cs TrustedName]...\n", argv[0]);
+    fprintf(stderr, "usage: %s [--gpus N] [--secp-solve] main.r1cs [trusted.r1cs TrustedName]...\n", argv[0]);
     return 2;
   }
   ecne_r1cs_t* cur = NULL;
@@ -72,7 +81,8 @@ int main(int argc, char** argv) {
   const size_t words = (size_t)((n_vars + 63) / 64);
   r.unique_bits = (uint64_t*)calloc(words ? words : 1, 8);
   r.known_bits = (uint64_t*)calloc(words ? words : 1, 8);
-  const int st = ecne_solve(&p, &r);
+  int st = gpus > 1 ? ecne_init_multi(gpus) : 0; /* one GPU: ecne_solve binds device 0 by itself */
+  if (st == 0) st = ecne_solve(&p, &r);
   if (st != 0) {
     fprintf(stderr, "ecne_solve: status %d: %s\n", st, ecne_last_error());
     return 2;
@@ -81,9 +91,9 @@ int main(int argc, char** argv) {
          (unsigned long long)r.n_nontrivial);
   printf("Solved for %llu target variables out of %llu total target variables\n",
          (unsigned long long)r.n_targets_unique, (unsigned long long)cur->n_targets);
-  printf("%s (%.3f ms on the device, %llu constraint evaluations)\n",
+  printf("%s (%.3f ms on the device, %llu constraint evaluations, %llu GPU(s))\n",
          r.verdict ? "sound constraints" : "potentially unsound constraints", r.ms_device,
-         (unsigned long long)r.constraint_evals);
+         (unsigned long long)r.constraint_evals, (unsigned long long)r.gpus_used);
   ecne_shutdown();
   return r.verdict ? 0 : 1;
 }

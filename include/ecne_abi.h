@@ -119,8 +119,15 @@ int ecne_version(void);
  * offsetof(field) ... in declaration order}.  Returns the length of the table and writes at most `cap` words.
  * A binding compares it with its own offsets once at load time (ecneproject_b200/_abi.py). */
 int ecne_abi_layout(uint32_t* out, uint32_t cap);
-/* Bind this process to CUDA device `device` (one process per GPU).  Idempotent. */
+/* Bind this process to CUDA device `device` (one GPU, or one process per GPU of a sharded run: see
+ * ecne_dist_init below).  Idempotent. */
 int ecne_init(int device);
+/* SURVEY.md §8b "Threading": ONE process, one host thread, the GPUs 0 .. n_gpus-1 of one box — what the
+ * single-threaded Julia caller of :552 needs to reach every GPU.  The library opens the devices, enables peer
+ * access between them (no IPC handles, no NCCL, no second process) and from then on ecne_upload / ecne_solve /
+ * ecne_solve_resident shard the rows over all of them exactly as a one-process-per-GPU run does (same kernels,
+ * same exchange protocol, results bit-identical to one GPU).  n_gpus == 1 is ecne_init(0).  Idempotent. */
+int ecne_init_multi(int n_gpus);
 void ecne_shutdown(void);
 const char* ecne_last_error(void);
 
@@ -156,13 +163,16 @@ typedef struct ecne_report {
 int ecne_report_resident(ecne_resident_t* r, ecne_report_t* report);
 
 /* ---- row-range sharding across the GPUs of one box ------------------------
- * One process per GPU.  Every rank is given the WHOLE problem by its host and sweeps rows [lo, hi)
- * chosen by nnz balance; wire state is replicated.  Rounds with a large frontier are sharded: their
- * update records are exchanged over NVLink peer mappings inside the solve kernel (one exchange per
- * round); rounds with a small frontier are run replicated on every rank without any exchange.
- * NCCL only bootstraps: unique_id is the 128-byte ncclUniqueId made by rank 0 (ecne_dist_unique_id)
- * and broadcast by the host (torch.distributed / MPI / Julia Distributed); the engine all-gathers
- * its CUDA IPC handles through it.  ecne_upload() and ecne_solve*() are collective calls. */
+ * Either ONE process for all GPUs (ecne_init_multi above) or one process per GPU (ecne_init(local_rank) +
+ * ecne_dist_init).  Every rank is given the WHOLE problem by its host and classifies it; wire state and the phases
+ * P0 / P2 / P3 / P4 are replicated.  The dense sweeps of the single-row rules — the only rounds that stream every
+ * row — are split by row ranges [lo, hi) of equal stored-term weight: their update records are exchanged over
+ * NVLink peer mappings inside the solve kernel (one exchange per sharded round: post counts into the peers'
+ * mailboxes, pull the peers' record lists, acknowledge).  Frontier-driven rounds cost less than an exchange and
+ * are run by every rank on all rows, without any communication.
+ * One process per GPU: NCCL only bootstraps — unique_id is the 128-byte ncclUniqueId made by rank 0
+ * (ecne_dist_unique_id) and broadcast by the host (torch.distributed / MPI / Julia Distributed); the engine
+ * all-gathers its CUDA IPC handles through it.  ecne_upload() and ecne_solve*() are collective calls. */
 int ecne_dist_unique_id(uint8_t out[128]);
 int ecne_dist_init(int rank, int world, const uint8_t unique_id[128]);
 int ecne_dist_rank(void);

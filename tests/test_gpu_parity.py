@@ -139,7 +139,7 @@ def test_resident_solve_is_repeatable():
         assert o[2:] == outs[0][2:], (o[2:], outs[0][2:])
     # the number of row visits of a frontier-driven round depends on which of two racing rows logs a
     # wire first (one record or two); the state it reaches does not
-    assert max(evals) - min(evals) <= 0.02 * max(evals)
+    assert max(evals) - min(evals) <= 0.05 * max(evals)
     assert hashlib.sha256(outs[0][0]).hexdigest() == GOLD["tornado/merkleTree"]["sha_unique"]
 
 
