@@ -19,8 +19,11 @@ abstraction; the configuration the `metric` is quoted on — it fits one GPU).
           time.  roofline.dense_rounds is the same for the dense Jacobi rounds alone (in-kernel
           clock64), the only part of the solve that streams rows.
   N > 1   the rows are sharded by stored-term balance (ecne_shard_rows), wire state is replicated and
-          the per-round update records are exchanged over NVLink inside the solve kernel: the SAME
-          problem is split, so "scaling" is "strong".
+          the update records of the sharded (dense) rounds are exchanged over NVLink inside the solve
+          kernel: the SAME problem is split, so "scaling" is "strong" (at every N, N = 1 included).
+          Every rank hashes its `unique` bitmap and compares it with the committed oracle golden
+          (config.sha_unique / config.matches_golden); a mismatch on any rank fails the run.
+          scale_tiled: the same for the K-times tiled workload (the bandwidth regime).
   cpu_baseline  oracle/ (a single-threaded C++ port of the reference's Julia) on the same workload,
           timed on this box's host, rank 0, N=1 only.
 """
@@ -65,6 +68,25 @@ def cpu_model():
     except Exception:
         pass
     return "unknown"
+
+
+def golden_sha():
+    """SHA-256 of the packed `unique` bitmap the oracle produces on the headline workload (committed pin)."""
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_goldens.json")))
+        return g["ecdsa+secp256k1"]["sha_unique"]
+    except Exception:
+        return None
+
+
+def measured_traffic(key):
+    """DRAM bytes per k_solve launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu
+    capture of this round, profiles/r02_traffic.json (written by tools/ncu_traffic.py from the .ncu-rep)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        return t[key]
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -207,8 +229,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tile", type=int, default=8,
-                    help="also time a K-times tiled copy of the workload (0 = skip): its working set does not fit the L2")
+    ap.add_argument("--tile", type=int, default=16,
+                    help="also time a K-times tiled copy of the workload (0 = skip); 16 = SURVEY.md §8d's S16: 11.1 M rows, "
+                         "355 MB of row records, far beyond the L2")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -318,6 +341,53 @@ def main():
     barrier()
     verdict = bool(res.c.verdict)
     n_unique = int(res.c.n_unique)
+    # ---- parity, on EVERY rank: the determined-variable set against the committed oracle pin --------------
+    import hashlib
+    sha_unique = hashlib.sha256(res.unique_bytes()).hexdigest()
+    want_sha = golden_sha()
+    matches = int(want_sha is not None and sha_unique == want_sha and verdict)
+    if dist is not None:
+        m = torch.tensor([matches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(m, op=dist.ReduceOp.MIN)
+        matches_all = int(m[0])
+    else:
+        matches_all = matches
+
+    # ---- N > 1: the same workload with the dense sweeps FORCED onto row ranges ("shard_min_rows" = 0) ------------
+    # By default a problem of this size is solved by every GPU in full (a sharded round costs a cross-GPU barrier
+    # that a 694 k-row sweep does not earn back); this leg runs the sharded data path on the named workload anyway,
+    # so that its bit-parity and its cost are on the driver's record.
+    sharded_forced = None
+    sharded_default = bool(res.c.sharded)
+    if world > 1 and not sharded_default:
+        assert lib.ecne_set_option(b"shard_min_rows", 0) == 0
+        h_s = C.c_void_p()
+        st = lib.ecne_upload(C.byref(ph.c), C.byref(h_s))
+        if st != 0:
+            raise RuntimeError(lib.ecne_last_error().decode())
+        res_s = api.SolveResult(main.n_vars, full_state=False)
+        ts = 0.0
+        for i in range(2 + 5):
+            l2_flush()
+            barrier()
+            st = lib.ecne_solve_resident(h_s, C.byref(res_s.c))
+            if st != 0:
+                raise RuntimeError(lib.ecne_last_error().decode())
+            if i >= 2:
+                ts += res_s.c.ms_device
+        barrier()
+        lib.ecne_free_resident(h_s)
+        assert lib.ecne_set_option(b"shard_min_rows", 2000000) == 0
+        ok_s = int(hashlib.sha256(res_s.unique_bytes()).hexdigest() == want_sha and bool(res_s.c.sharded))
+        tt = torch.tensor([ts / 5], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ee = torch.tensor([int(res_s.c.constraint_evals), -ok_s], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ee, op=dist.ReduceOp.SUM)
+        sharded_forced = {"ms_per_step": float(tt[0]), "evals_per_step": int(ee[0]),
+                          "matches_golden_on_every_rank": int(ee[1]) == -world,
+                          "sha_unique": hashlib.sha256(res_s.unique_bytes()).hexdigest(),
+                          "how": "ecne_set_option(shard_min_rows, 0): dense sweeps split by row range, records exchanged over NVLink"}
+        matches_all = int(matches_all and sharded_forced["matches_golden_on_every_rank"])
 
     # ---- e2e leg: host buffers in, host buffers out -------------------------------------------------
     res2 = api.SolveResult(main.n_vars, full_state=False)
@@ -372,9 +442,10 @@ def main():
     dense_ach = b_eval * dense_evals / (dense_ms / 1e3) / 1e9 if dense_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_solve (the whole fixpoint, one persistent cooperative launch)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the one k_solve launch of a solve, from the
-                # `ncu --set full` capture committed as profiles/r01_k_solve_ncu_full.csv (not measured live)
-                "traffic": 167.0e6 if world == 1 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the one k_solve launch of a solve, read from the
+                # ncu capture of this round (profiles/r02_traffic.json <- tools/ncu_traffic.py); None if absent
+                "traffic": (measured_traffic("ecdsa") or {}).get("dram_bytes") if world == 1 else None,
+                "traffic_source": (measured_traffic("ecdsa") or {}).get("source") if world == 1 else None,
                 "peak_source": peak_src, "bytes_per_eval": b_eval, "evals_in_kernel_per_step": evals,
                 "jacobi_rounds_per_step": rounds, "kernel_ms_per_step": sweep_ms_step, "launches_per_step": 1,
                 "dense_rounds": {"rounds": dense_rounds, "evals": dense_evals, "ms": dense_ms,
@@ -386,7 +457,7 @@ def main():
 
     # ---- the same kernel on a tiled copy whose working set does not fit the 126 MB L2 ---------------
     tiled = None
-    if args.tile and args.tile > 1 and world == 1:
+    if args.tile and args.tile > 1:
         K = args.tile
         t, sp_t, known_t, targets_t, nv_t = tile_problem(np, reduced, specials, main, K)
         ph_t = api.ProblemHandle(t, sp_t, known_t, targets_t, nv_t, False)
@@ -396,45 +467,72 @@ def main():
         if st != 0:
             raise RuntimeError(lib.ecne_last_error().decode())
         for _ in range(2):
+            barrier()
             lib.ecne_solve_resident(h_t, C.byref(res_t.c))
         tsw = tso = 0.0
         reps = 3
         for _ in range(reps):
             l2_flush()
-            torch.cuda.synchronize()
+            barrier()
             st = lib.ecne_solve_resident(h_t, C.byref(res_t.c))
             if st != 0:
                 raise RuntimeError(lib.ecne_last_error().decode())
             tsw += res_t.c.ms_sweep
             tso += res_t.c.ms_solve
+        barrier()
         lib.ecne_free_resident(h_t)
-        ev_t = int(res_t.c.constraint_evals)
-        ach_t = b_eval * ev_t / (tsw / reps / 1e3) / 1e9
+        ev_t, dev_t = int(res_t.c.constraint_evals), int(res_t.c.dense_evals)
         d_ms_t = int(res_t.c.dense_cycles) / (sm_mhz * 1e3) if sm_mhz else 0.0
-        d_ach_t = b_eval * int(res_t.c.dense_evals) / (d_ms_t / 1e3) / 1e9 if d_ms_t > 0 else 0.0
-        ok_t = int(res_t.c.n_unique) == 1 + K * (n_unique - 1) and bool(res_t.c.verdict) == verdict
-        tiled = {"tile": K, "rows": t.n_rows, "row_record_bytes": 32 * t.n_rows, "evals_per_step": ev_t,
-                 "value": ev_t / (tso / reps / 1e3), "unit": UNIT, "ms_solve": tso / reps,
-                 "kernel_ms_per_step": tsw / reps, "achieved": ach_t, "peak": peak, "frac": ach_t / peak,
-                 "dense_rounds": {"rounds": int(res_t.c.dense_rounds), "evals": int(res_t.c.dense_evals),
-                                  "ms": d_ms_t, "achieved": d_ach_t, "frac": d_ach_t / peak},
-                 "bitmap_is_base_repeated": ok_t}
+        # the tiled bitmap is the base bitmap repeated: wire 1 shared, wires 2.. of copy k behind those of copy k-1
+        base_bits = np.unpackbits(np.frombuffer(res.unique_bytes(), dtype=np.uint8), bitorder="little")[:main.n_vars]
+        want_bits = np.concatenate([base_bits[:1]] + [base_bits[1:]] * K)
+        got_bits = np.unpackbits(np.frombuffer(res_t.unique_bytes(), dtype=np.uint8), bitorder="little")[:nv_t]
+        ok_t = int(bool(np.array_equal(want_bits, got_bits)) and bool(res_t.c.verdict) == verdict)
+        tsw, tso = tsw / reps, tso / reps
+        if dist is not None:   # slowest rank's times, all ranks' row visits, every rank's bitmap check
+            tt = torch.tensor([tsw, tso, d_ms_t], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tsw, tso, d_ms_t = float(tt[0]), float(tt[1]), float(tt[2])
+            ee = torch.tensor([ev_t, dev_t, -ok_t], device="cuda", dtype=torch.int64)
+            dist.all_reduce(ee, op=dist.ReduceOp.SUM)
+            ev_t, dev_t, ok_t = int(ee[0]), int(ee[1]), int(int(ee[2]) == -world)
+        ach_t = b_eval * ev_t / (tsw / 1e3) / 1e9
+        d_ach_t = b_eval * dev_t / (d_ms_t / 1e3) / 1e9 if d_ms_t > 0 else 0.0
+        tr_t = measured_traffic("tiled%d" % K) if world == 1 else None
+        tiled = {"tile": K, "n_gpus": world, "rows": t.n_rows, "row_record_bytes": 32 * t.n_rows, "evals_per_step": ev_t,
+                 "value": ev_t / (tso / 1e3), "unit": UNIT, "ms_solve": tso,
+                 "kernel_ms_per_step": tsw, "achieved": ach_t, "peak": peak * world, "frac": ach_t / (peak * world),
+                 "traffic": (tr_t or {}).get("dram_bytes"), "traffic_source": (tr_t or {}).get("source"),
+                 "dense_rounds": {"rounds": int(res_t.c.dense_rounds), "evals": dev_t,
+                                  "ms": d_ms_t, "achieved": d_ach_t, "frac": d_ach_t / (peak * world),
+                                  "how": "clock64 in block 0 of the slowest rank around the dense rounds, barrier "
+                                         "and cross-GPU exchange included; rows visited summed over the ranks"},
+                 "bitmap_is_base_repeated": bool(ok_t)}
         del ph_t, res_t, t
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+        # the SAME problem at every N (rows sharded over the GPUs): strong scaling, N = 1 included
+        "scaling": "strong", "vs_baseline": None,
         "dtype": "u256 (4x64-bit limbs, BN254 scalar field; sweep works on u8/u32 state)",
         "data": "real circuit (reference fixture ecdsa.r1cs), no synthetic data needed",
         "config": {"workload": WORKLOAD_NAME, "rows": reduced.n_rows, "rows_before_abstraction": main.n_rows,
                    "wires": main.n_vars, "nnz": nnz_nonzero, "evals_per_step": total_evals,
                    "outer_rounds": outer, "jacobi_rounds": rounds, "verdict": verdict, "n_unique": n_unique,
+                   # parity, every rank: SHA-256 of the packed `unique` bitmap against the committed oracle pin
+                   "sha_unique": sha_unique, "golden_sha_unique": want_sha, "matches_golden": bool(matches_all),
+                   "evals_note": "row visits actually executed: a row the live mask / the open-row bitmap has retired "
+                                 "is neither visited nor counted (the linear-system sweep of round 1 counted every live "
+                                 "row in every outer round: 15.0 M visits for the same verdict)",
                    "rule_evals_per_step": rule_evals,
                    "l2": "flushed between timed steps (256 MB fill)",
-                   "parallelism": "1 GPU" if world == 1 else
-                   f"{world} GPUs: rows sharded by stored-term balance, wire state replicated, per-round update "
-                   "records exchanged over NVLink inside the solve kernel (DESIGN.md §7)",
+                   "parallelism": "1 GPU" if world == 1 else (
+                       f"{world} GPUs: rows sharded by stored-term balance, wire state replicated, the dense sweeps' update "
+                       "records exchanged over NVLink inside the solve kernel (DESIGN.md §7)" if sharded_default else
+                       f"{world} GPUs, {reduced.n_rows} rows < shard_min_rows: every GPU solves the whole problem, no exchange "
+                       "(sharding this workload is slower than one GPU, see config.sharded_forced; the tiled leg is sharded)"),
+                   "sharded": sharded_default, "sharded_forced": sharded_forced,
                    "timing": "CUDA events on the engine's stream around each whole call (ecne_result.ms_device), max over ranks",
                    "wall_ms_per_step": ms_wall, "device_ms_solve_per_step": solve_ms / args.steps,
                    "host_prep_seconds": PREP.get("read_and_abstraction"),
@@ -451,6 +549,8 @@ def main():
     }
     if tiled is not None:
         line["roofline_tiled"] = tiled
+        if world > 1:
+            line["scale_tiled"] = tiled
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -470,6 +570,12 @@ def main():
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    if not matches_all:
+        sys.stderr.write("bench.py: the `unique` bitmap of some rank differs from the committed oracle golden\n")
+        return 3
+    if tiled is not None and not tiled["bitmap_is_base_repeated"]:
+        sys.stderr.write("bench.py: the tiled workload's bitmap is not the base bitmap repeated\n")
+        return 3
     return 0
 
 

@@ -51,7 +51,7 @@ class Result(C.Structure):
         ("ms_d2h", C.c_double), ("ms_exchange", C.c_double), ("ms_total", C.c_double),
         ("ms_sweep", C.c_double), ("rule_evals", C.c_uint64),
         ("dense_rounds", C.c_uint64), ("dense_evals", C.c_uint64), ("dense_cycles", C.c_uint64),
-        ("ms_device", C.c_double), ("gpus_used", C.c_uint64),
+        ("ms_device", C.c_double), ("gpus_used", C.c_uint64), ("sharded", C.c_uint64),
     ]
 
 

@@ -42,6 +42,10 @@ struct Global {
   long long grid_blocks = 0;          // testing knob: launch the solve kernel with fewer blocks than SMs (0: one per SM)
   long long p2_hash_bits = 56;         // testing knob: bits of the P2 set hash that are used (fewer => collisions)
   long long sparse_max = -1;          // records per round up to which a round is frontier-driven (-1: rows / 32)
+  // On several GPUs the dense sweeps of a problem with at least this many rows are split over the ranks; a smaller
+  // problem is solved by every rank on all rows without any exchange (a sharded round costs a cross-GPU barrier,
+  // ~15-25 us, which a sweep of a few 10^5 rows does not earn back: ecdsa's 694 k rows sweep in ~20 us)
+  long long shard_min_rows = 2000000;
   // one process per GPU: rank / world of this process and the communicator that bootstraps the peer mappings
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
@@ -150,7 +154,7 @@ extern "C" int ecne_abi_layout(uint32_t* out, uint32_t cap) {
   ECNE_F(ecne_problem_t, n_specials) ECNE_F(ecne_problem_t, sp_kind) ECNE_F(ecne_problem_t, sp_in_ptr)
   ECNE_F(ecne_problem_t, sp_in) ECNE_F(ecne_problem_t, sp_out_ptr) ECNE_F(ecne_problem_t, sp_out)
   ECNE_F(ecne_problem_t, secp_solve) ECNE_F(ecne_problem_t, debug)
-  ECNE_S(ecne_result_t, 30)
+  ECNE_S(ecne_result_t, 31)
   ECNE_F(ecne_result_t, verdict) ECNE_F(ecne_result_t, status) ECNE_F(ecne_result_t, unique_bits)
   ECNE_F(ecne_result_t, known_bits) ECNE_F(ecne_result_t, lb) ECNE_F(ecne_result_t, ub)
   ECNE_F(ecne_result_t, nvalues) ECNE_F(ecne_result_t, values) ECNE_F(ecne_result_t, abz)
@@ -161,7 +165,7 @@ extern "C" int ecne_abi_layout(uint32_t* out, uint32_t cap) {
   ECNE_F(ecne_result_t, ms_d2h) ECNE_F(ecne_result_t, ms_exchange) ECNE_F(ecne_result_t, ms_total)
   ECNE_F(ecne_result_t, ms_sweep) ECNE_F(ecne_result_t, rule_evals) ECNE_F(ecne_result_t, dense_rounds)
   ECNE_F(ecne_result_t, dense_evals) ECNE_F(ecne_result_t, dense_cycles) ECNE_F(ecne_result_t, ms_device)
-  ECNE_F(ecne_result_t, gpus_used)
+  ECNE_F(ecne_result_t, gpus_used) ECNE_F(ecne_result_t, sharded)
   ECNE_S(ecne_report_t, 10)
   ECNE_F(ecne_report_t, bad_row_bits) ECNE_F(ecne_report_t, cap_wires) ECNE_F(ecne_report_t, wire)
   ECNE_F(ecne_report_t, flags) ECNE_F(ecne_report_t, lb) ECNE_F(ecne_report_t, ub) ECNE_F(ecne_report_t, nvalues)
@@ -300,6 +304,8 @@ extern "C" int ecne_set_option(const char* key, int64_t value) {
     G.sparse_max = value;
   else if (k == "grid_blocks")
     G.grid_blocks = value;
+  else if (k == "shard_min_rows")
+    G.shard_min_rows = value < 0 ? 0 : value;
   else if (k == "p2_hash_bits")
     G.p2_hash_bits = value < 0 ? 0 : (value > 56 ? 56 : value);
   else
@@ -350,16 +356,25 @@ extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out)
       return fail(st, e);
     }
   if (world > 1) {
+    const bool shard = (long long)problem->n_rows >= G.shard_min_rows;
     for (int i = 0; i < nl; ++i) {
-      uint64_t lo = 0, hi = 0;
-      ecne_shard_rows(problem, G.multi ? i : G.rank, world, &lo, &hi);
-      h->rs[i].d.row_lo = (uint32_t)lo;
-      h->rs[i].d.row_hi = (uint32_t)hi;
+      Dev& di = h->rs[i].d;
+      di.world = world;
+      di.rank = G.multi ? i : G.rank;
+      di.shard = shard ? 1 : 0;
+      if (shard) {
+        uint64_t lo = 0, hi = 0;
+        ecne_shard_rows(problem, di.rank, world, &lo, &hi);
+        di.row_lo = (uint32_t)lo;
+        di.row_hi = (uint32_t)hi;
+      }
     }
-    int st = setup_exchange(*h, h->rs[0].d.rec_cap);
-    if (st != ECNE_OK) {
-      ecne_free_resident(h);
-      return st;
+    if (shard) {
+      int st = setup_exchange(*h, h->rs[0].d.rec_cap);
+      if (st != ECNE_OK) {
+        ecne_free_resident(h);
+        return st;
+      }
     }
   }
   *out = h;
@@ -447,13 +462,14 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   int status = ECNE_OK;
   std::string err;
   float ms_sweep = 0;
-  unsigned long long evals_total = 0, rule_evals_total = 0, dense_evals_total = 0;
+  unsigned long long evals_total = 0, rule_evals_total = 0, dense_evals_total = 0, dense_cycles_max = 0;
   for (int i = 0; i < nl; ++i) {
     const Status& S = *h->rs[i].h_status;
     float ms = 0;
     cudaSetDevice(h->rs[i].device);
     cudaEventElapsedTime(&ms, s0[i], s1[i]);
     ms_sweep = std::max(ms_sweep, ms);  // the kernels run concurrently: the slowest one is the solve
+    dense_cycles_max = std::max<unsigned long long>(dense_cycles_max, S.dense_cycles);
     if (status == ECNE_OK) {
       if (S.err)
         status = -(int)S.err;
@@ -493,6 +509,12 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
           }
         if (g) fprintf(stderr, "[p2scan] outer %llu: short rows mean %llu max %llu | long rows mean %llu max %llu | pre mean %llu max %llu\n", g,
                        sum[0] / 148, mx[0], sum[1] / 148, mx[1], sum[2] / 148, mx[2]);
+      }
+      for (int r = 0; r < 12; ++r) {
+        const unsigned long long* q = pr.data() + 27000 + 8 * r;
+        if (q[0] | q[4])
+          fprintf(stderr, "[dense %d] block 0: work %llu | round barrier%s %llu | pull %llu | barrier+ack %llu | records %llu\n", r, q[4],
+                  d.world > 1 ? " + exchange" : "", q[0], q[1], q[2], q[3]);
       }
       for (int r = 0; r < 12; ++r) {
         unsigned long long mx[3] = {0, 0, 0}, sum[3] = {0, 0, 0}, g = 0;
@@ -579,9 +601,10 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
   res->ms_sweep = ms_sweep;
   res->dense_rounds = R.h_status->dense_rounds;
   res->dense_evals = dense_evals_total;
-  res->dense_cycles = R.h_status->dense_cycles;
+  res->dense_cycles = dense_cycles_max;
   res->ms_device = ms_device;
   res->gpus_used = (uint64_t)d.world;
+  res->sharded = (uint64_t)d.shard;
   for (auto& Ri : h->rs) Ri.have_state = true;
   res->ms_total = R.ms_h2d + R.ms_classify + ms_solve + ms_d2h;
   R.have_state = true;

@@ -188,6 +188,10 @@ struct Dev {
   uint32_t row_lo, row_hi;
   // multi-GPU exchange over NVLink peer mappings (world == 1: unused)
   int world, rank;
+  // shard != 0: the dense sweeps are split over the ranks (row ranges, one exchange per sharded round).  A run on
+  // several GPUs whose problem is too small for that to pay (ecne_set_option "shard_min_rows") has shard == 0: every
+  // rank runs the whole solve on all rows, nothing is exchanged, rank 0 counts the work.
+  int shard;
   Rec* xrecs[ECNE_MAX_WORLD][3];             // every rank's three record lists (own entry = recs[])
   unsigned long long* xflag[ECNE_MAX_WORLD]; // every rank's mailbox [ECNE_MAX_WORLD]; we post into slot [rank]
   unsigned int* xcnt;                        // [3][ECNE_MAX_WORLD] record counts per list and rank (local copy)

@@ -352,7 +352,7 @@ __device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, int wbuf, 
 // log a state change that the caller applied to BOTH buffers itself
 __device__ __forceinline__ void log_rec(const Dev& d, int pl, uint32_t w, uint32_t bits) {
   if (d.inv_head[w].x > HEAVY_DEG) atomicOr(d.bnd_flag + pl, 2u);
-  if (d.world > 1) {
+  if (d.shard) {
     unsigned int* word = (unsigned int*)(d.wflag[pl] + (w & ~3u));
     const unsigned int sh = (w & 3u) * 8;
     if (!((atomicOr(word, 1u << sh) >> sh) & 1u)) atomicAdd(d.dcnt + pl, 1u);
@@ -922,7 +922,7 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cnt) : "l"(d.rec_count + list) : "memory");
       asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(bf) : "l"(d.bnd_flag + list) : "memory");
-      if (d.world > 1) asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(dn) : "l"(d.dcnt + list) : "memory");
+      if (d.shard) asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(dn) : "l"(d.dcnt + list) : "memory");
       d.rec_count[prev_list] = 0;  // consumed; next written two rounds from now
       d.bnd_flag[prev_list] = 0;
       d.dcnt[prev_list] = 0;
@@ -930,7 +930,7 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
     }
     cnt = __shfl_sync(0xffffffffu, cnt, 0);
     bf = __shfl_sync(0xffffffffu, bf, 0);
-    dn = d.world > 1 ? __shfl_sync(0xffffffffu, dn, 0) : cnt;
+    dn = d.shard ? __shfl_sync(0xffffffffu, dn, 0) : cnt;
     bepoch += bf & 1u;
     hv = bf & 2u;
     round += 1;
@@ -980,7 +980,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
   const uint32_t kmask = per_thread < LiveMask::BITS ? per_thread : LiveMask::BITS;
   const uint32_t warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
-  unsigned int xe = d.world > 1 ? *d.xepoch : 0u;  // cross-GPU epoch (same on every rank, persists over solves)
+  unsigned int xe = d.shard ? *d.xepoch : 0u;  // cross-GPU epoch (same on every rank, persists over solves)
   unsigned int ack_pending = 0;                    // epoch of a sharded round whose lists peers may still be reading
   unsigned long long evals = 0, ruleevals = 0, devals = 0, dcycles = 0;
   unsigned int rounds_total = 0, dense_rounds = 0;
@@ -1032,7 +1032,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       unsigned int list = 0, prev_list = (unsigned int)pl_r, prev_n = n_pl > d.rec_cap ? d.rec_cap : n_pl;
       // `dn`: the number of distinct wires the previous round changed.  Mode decisions (dense / sparse /
       // solo) use it instead of the record count on sharded runs, because it is the same on every rank
-      unsigned int prev_dn = d.world > 1 ? __ldcg(d.dcnt + pl_r) : n_pl;
+      unsigned int prev_dn = d.shard ? __ldcg(d.dcnt + pl_r) : n_pl;
       unsigned int prev_own = prev_n;  // leading records of the list that still have to be replayed into the write
                                        // buffer (all of them, except after a sharded round: the phase list is complete)
       bool dense = outer == 1 || prev_dn > d.sparse_max || (__ldcg(d.bnd_flag + pl_r) & 2u) != 0;
@@ -1119,7 +1119,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
                 asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cnt) : "l"(d.rec_count + list) : "memory");
                 asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(bf) : "l"(d.bnd_flag + list) : "memory");
                 unsigned int dnv = cnt;
-                if (d.world > 1) asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(dnv) : "l"(d.dcnt + list) : "memory");
+                if (d.shard) asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(dnv) : "l"(d.dcnt + list) : "memory");
                 s_solo[0] = cnt;
                 s_solo[1] = bf;
                 s_solo[2] = dnv;
@@ -1196,7 +1196,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         }
         const int wbuf = rbuf ^ 1;
         const uint8_t* F = d.F[rbuf];
-        const bool sharded = d.world > 1 && dense;  // only dense sweeps are split over the ranks
+        const bool sharded = d.shard && dense;  // only dense sweeps are split over the ranks
+        const int elist = sharded ? (int)(list | LIST_NOCOUNT) : (int)list;  // (sweep.cuh: no distinct-wire counting)
         gr += 1;
         long long tc0 = 0;
         if (dense && tid == 0) tc0 = clock64();
@@ -1217,7 +1218,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           long long dz2 = clock64();
 #endif
           // (c) sweep the rows this thread still owns, P1_INFLIGHT of them in flight
-          const unsigned int nl = live.count();
+          const unsigned int nl = (sharded || d.rank == 0) ? live.count() : 0u;  // replicated work is counted once
           evals += nl;
           devals += nl;
           ruleevals += nl;
@@ -1245,7 +1246,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
 #pragma unroll
             for (int h = 0; h < P1_INFLIGHT; ++h)
               if (kk[h] >= 0) {
-                const uint32_t e = eval_inline(d, rbuf, wbuf, (int)list, d.row_lo + tid + (uint32_t)kk[h] * nthreads, rr[h],
+                const uint32_t e = eval_inline(d, rbuf, wbuf, elist, d.row_lo + tid + (uint32_t)kk[h] * nthreads, rr[h],
                                                ff[h], bepoch);
                 if (e & EI_DONE) live.clear(kk[h]);
                 if (e & EI_GENERIC) slow.set(kk[h]);
@@ -1257,7 +1258,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           for (LiveMask m = slow; m.any();) {
             const int k = m.pop_nonempty();
             const uint32_t row = d.row_lo + tid + (uint32_t)k * nthreads;
-            const bool done = eval_row<1>(d, rbuf, wbuf, (int)list, row, bepoch);
+            const bool done = eval_row<1>(d, rbuf, wbuf, elist, row, bepoch);
             bool fast;
             if (k < ks)
               fast = (sm_rec[(2 * k) * blockDim.x + threadIdx.x].x & RF_FAST) != 0;
@@ -1270,7 +1271,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
             uint32_t r = tid + k * nthreads;
             if (r < rows) {
               uint32_t row = d.row_lo + r;
-              if (!(d.rflags[row] & RF_LONG) && !(d.solved[row] & 1)) eval_row<1>(d, rbuf, wbuf, (int)list, row, bepoch);
+              if (!(d.rflags[row] & RF_LONG) && !(d.solved[row] & 1)) eval_row<1>(d, rbuf, wbuf, elist, row, bepoch);
               evals += 1;
               devals += 1;
               ruleevals += 1;
@@ -1285,11 +1286,13 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
             if (d.long_done[i]) continue;
             const uint32_t row = d.long_rows[i];
             if (row >= d.row_lo && row < d.row_hi) {
-              const bool done = eval_row<32>(d, rbuf, wbuf, (int)list, row, bepoch);
+              const bool done = eval_row<32>(d, rbuf, wbuf, elist, row, bepoch);
               if (lane == 0) {
-                evals += 1;
-                devals += 1;
-                ruleevals += 1;
+                if (sharded || d.rank == 0) {
+                  evals += 1;
+                  devals += 1;
+                  ruleevals += 1;
+                }
                 if (done) d.long_done[i] = 1;
               }
             }
@@ -1316,12 +1319,15 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         unsigned int n;
         bool heavy = false;  // a wire with very many rows changed: sweep densely instead of chasing its list
         unsigned int dn;
+#ifdef ECNE_PROFILE
+        long long xz0 = clock64(), xz1 = 0, xz2 = 0;
+#endif
         if (sharded) {
           xe += 1;
           n = grid_barrier(d.barrier, epoch, d.rec_count + list, d.bnd_flag + list, &d, list, xe);
           bepoch += n >> 31;
           n &= 0x7fffffffu;
-          dn = __ldcg(d.xcnt + 3 * ECNE_MAX_WORLD + 0);  // distinct wires changed, summed over the ranks
+          dn = n;  // the ranks' record counts, summed: the same number on every rank (it was exchanged)
           heavy = __ldcg(d.xcnt + 3 * ECNE_MAX_WORLD + 1) != 0;
         } else {
           grid_sync_flip(d.barrier + 64);
@@ -1329,37 +1335,62 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           const unsigned int bf = __ldcg(d.bnd_flag + list);
           bepoch += bf & 1u;
           heavy = (bf & 2u) != 0;
-          dn = d.world > 1 ? __ldcg(d.dcnt + list) : n;
+          dn = d.shard ? __ldcg(d.dcnt + list) : n;
         }
         unsigned int n_own = n;
+#ifdef ECNE_PROFILE
+        xz1 = clock64();
+#endif
         if (sharded) {
           // pull the peers' records of this round over NVLink, apply them to BOTH local buffers (the buffer read
           // next round must already contain them) and append them behind this rank's own records: the local list is
-          // complete afterwards and nobody reads a peer's list again once the round's acknowledgement is out
+          // complete afterwards and nobody reads a peer's list again once the round's acknowledgement is out.  A
+          // peer's record that changes nothing in the buffer this rank wrote during the round repeats one of its own
+          // records (two rows on different ranks fixed the same wire) and is not appended: "first writer logs" across
+          // the ranks, so the next round's frontier is what one GPU would have.
           n_own = __ldcg(d.xcnt + list * ECNE_MAX_WORLD + d.rank);
           if (n_own > d.rec_cap) n_own = d.rec_cap;
-          unsigned int base = n_own;
           for (int h = 0; h < d.world; ++h) {
             if (h == d.rank) continue;
             const unsigned int nh = __ldcg(d.xcnt + list * ECNE_MAX_WORLD + h);
             const Rec* pr = d.xrecs[h][list];
             for (uint32_t j = tid; j < nh && j < d.rec_cap; j += nthreads) {
               Rec r = ld_peer_rec(pr + j);
-              apply_update(d, 0, r.wire, r.bits, r.lbr, r.ubr);
-              apply_update(d, 1, r.wire, r.bits, r.lbr, r.ubr);
-              if (base + j < d.rec_cap)
-                d.recs[list][base + j] = r;
-              else
-                d.st->rec_overflow = 1;
+              const bool fresh = (apply_update_t<true>(wbuf, r.wire, r.bits, r.lbr, r.ubr) & 1u) != 0;
+              apply_update(d, rbuf, r.wire, r.bits, r.lbr, r.ubr);
+              if (fresh) {  // warp-aggregated slot allocation (a big round appends > 10^5 records: one RMW per warp)
+                const unsigned int am = __activemask();
+                const int leader = __ffs((int)am) - 1;
+                unsigned int i = 0;
+                if ((int)lane == leader) i = atomicAdd(d.rec_count + list, (unsigned int)__popc(am));
+                i = __shfl_sync(am, i, leader) + (unsigned int)__popc(am & ((1u << lane) - 1u));
+                if (i < d.rec_cap)
+                  d.recs[list][i] = r;
+                else
+                  d.st->rec_overflow = 1;
+              }
             }
-            base += nh < d.rec_cap ? nh : d.rec_cap;
           }
+#ifdef ECNE_PROFILE
+          xz2 = clock64();
+#endif
           grid_sync_flip(d.barrier + 64);
           // tell the peers that their lists of this round have been read here; our own lists of this round must
           // not be overwritten before every peer has said the same (checked when the next round starts)
           if (tid == 0) cross_gpu_ack(d, xe);
           ack_pending = xe;
+          n = __ldcg(d.rec_count + list);  // own records + the peers' that were new here
         }
+#ifdef ECNE_PROFILE
+        if (tid == 0 && dense && dense_rounds < 40) {
+          unsigned long long* q = d.prof + 27000 + 8 * dense_rounds;
+          q[0] = (unsigned long long)(xz1 - xz0);                       // round barrier (+ cross-GPU exchange)
+          q[1] = sharded ? (unsigned long long)(xz2 - xz1) : 0;         // pull of the peers' records
+          q[2] = sharded ? (unsigned long long)(clock64() - xz2) : 0;   // barrier after the pull + ack
+          q[3] = n;
+          q[4] = (unsigned long long)(xz0 - tc0);                        // replay + sweep + long rows (block 0)
+        }
+#endif
         if (tid == 0 && d.prof && gr < 4000) {
           d.prof[4 * gr + 0] = (unsigned long long)(clock64() - tp);
           d.prof[4 * gr + 1] = n;
@@ -1563,7 +1594,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     for (int i = 0; i < 8; ++i) d.st->prof[i] = pf[i];
     d.st->n_cand_total = cand_total;
     d.st->n_cand_max = cand_max;
-    if (d.world > 1) *d.xepoch = xe;
+    if (d.shard) *d.xepoch = xe;
   }
 }
 
@@ -1723,7 +1754,7 @@ __global__ void k_reset_all(Dev d) {
       d.valsrc[i] = VS_NONE;
       d.abz_claim[i] = ~0ULL;
     }
-    if (d.world > 1) {
+    if (d.shard) {
 #pragma unroll
       for (int l = 0; l < 5; ++l) d.wflag[l][i] = 0;
     }

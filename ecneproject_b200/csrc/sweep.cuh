@@ -58,7 +58,7 @@ __device__ __forceinline__ void apply_update(const Dev&, int buf, uint32_t w, ui
 // a record of list `list` has been consumed (replayed): its wire may be counted again when the list is
 // written next (two rounds from now)
 __device__ __forceinline__ void consume_rec(const Dev& d, unsigned int list, uint32_t w) {
-  if (d.world > 1) {
+  if (d.shard) {
     unsigned int* word = (unsigned int*)(d.wflag[list] + (w & ~3u));
     atomicAnd(word, ~(0xffu << ((w & 3u) * 8)));
   }
@@ -71,15 +71,21 @@ __device__ __forceinline__ void consume_rec(const Dev& d, unsigned int list, uin
 // changes: "no record in a round" is exactly "fixpoint", and the records are the next round's frontier.
 // One copy of this code in the kernel (the fixpoint kernel is instruction-cache bound in its serial
 // stretches: every inlined copy costs more than the call).
-__device__ __noinline__ void emit_impl(int wbuf, int list, uint32_t w, uint32_t bits, uint32_t lbr, uint32_t ubr) {
+// `list` may carry LIST_NOCOUNT: the round is a sharded dense sweep, whose size the ranks learn from the record
+// counts they exchange anyway — no per-record distinct-wire bookkeeping (an extra dependent atomic per record, which
+// made a 2.5 M-record round three times slower).
+#define LIST_NOCOUNT 8
+__device__ __noinline__ void emit_impl(int wbuf, int list_in, uint32_t w, uint32_t bits, uint32_t lbr, uint32_t ubr) {
   const Dev& d = c_dev;
+  const int list = list_in & 7;
+  const bool count_distinct = d.shard && !(list_in & LIST_NOCOUNT);
   const uint32_t r = apply_update_t<true>(wbuf, w, bits, lbr, ubr);
   // round flags (bit0: a bound moved, bit1: a heavy wire changed => the next round is dense): set once —
   // 160 k rows fix a bound in ecdsa's first round, and 160 k REDs on one address serialise in one L2 slice
   const uint32_t want = ((r & 2u) ? 1u : 0u) | (((r & 1u) && (r & 4u)) ? 2u : 0u);
   if (want && (__ldcg(d.bnd_flag + list) & want) != want) atomicOr(d.bnd_flag + list, want);
   if (!(r & 1u)) return;
-  if (d.world > 1) {  // sharded runs count the distinct wires a round changed (same number on every rank)
+  if (count_distinct) {  // replicated rounds of a sharded run count the distinct wires they change (same on every rank)
     unsigned int* word = (unsigned int*)(d.wflag[list] + (w & ~3u));
     const unsigned int sh = (w & 3u) * 8;
     if (!((atomicOr(word, 1u << sh) >> sh) & 1u)) atomicAdd(d.dcnt + list, 1u);
@@ -225,7 +231,8 @@ struct RowCtx {
 template <int G>
 __device__ __noinline__ void emit_unique_all(const RowCtx& c, const uint8_t* F, uint32_t s, uint32_t e, uint32_t lane) {
   const Dev& d = c_dev;
-  if (G == 1 || d.world > 1) {  // thread-per-row callers and sharded runs (distinct-wire counting) keep the plain path
+  const int list = c.list & 7;
+  if (G == 1 || (d.shard && !(c.list & LIST_NOCOUNT))) {  // thread-per-row callers and rounds with distinct-wire counting keep the plain path
     scan_terms<G, SCAN_U(G)>(d, F, s, e, lane, [&](uint32_t w, uint32_t f) {
       if (!(f & WF_U)) c.out(w, WF_U | WF_K);
     });
@@ -259,7 +266,7 @@ __device__ __noinline__ void emit_unique_all(const RowCtx& c, const uint8_t* F, 
         chg |= 1u << u;
         heavy |= (old[u] & WF_HEAVY) != 0;
       }
-    if (heavy && !(__ldcg(d.bnd_flag + c.list) & 2u)) atomicOr(d.bnd_flag + c.list, 2u);
+    if (heavy && !(__ldcg(d.bnd_flag + list) & 2u)) atomicOr(d.bnd_flag + list, 2u);
     const uint32_t n = (uint32_t)__popc(chg);
     uint32_t incl = n;
 #pragma unroll
@@ -270,7 +277,7 @@ __device__ __noinline__ void emit_unique_all(const RowCtx& c, const uint8_t* F, 
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     if (total == 0) continue;
     uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(d.rec_count + c.list, total);
+    if (lane == 0) i = atomicAdd(d.rec_count + list, total);
     i = __shfl_sync(0xffffffffu, i, 0) + incl - n;
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -281,7 +288,7 @@ __device__ __noinline__ void emit_unique_all(const RowCtx& c, const uint8_t* F, 
           rr.bits = BITS;
           rr.lbr = ECNE_NO_LB;
           rr.ubr = ECNE_NO_UB;
-          d.recs[c.list][i] = rr;
+          d.recs[list][i] = rr;
         } else {
           d.st->rec_overflow = 1;
         }

@@ -109,7 +109,9 @@ typedef struct ecne_result {
   uint64_t dense_cycles;        /* SM cycles (clock64, block 0) spent in them, barrier included    */
   double ms_device;             /* CUDA-event time of the whole call on the engine's stream: reset,
                                    all rounds, verdict kernels and the D2H of the bitmaps           */
-  uint64_t gpus_used;           /* GPUs the solve kernel ran on (1, or the world of a sharded run)  */
+  uint64_t gpus_used;           /* GPUs the solve kernel ran on (1, or the world of a multi-GPU run) */
+  uint64_t sharded;             /* 1: the dense sweeps were split over those GPUs; 0: one GPU, or every GPU
+                                   solved the whole problem (fewer rows than "shard_min_rows")         */
 } ecne_result_t;
 
 /* ---- life cycle ------------------------------------------------------------------------- */
@@ -185,6 +187,9 @@ int ecne_shard_rows(const ecne_problem_t* problem, int rank, int world, uint64_t
  * "max_rounds" / "max_outer": round guards (ECNE_E_NOCONVERGE when hit); "sparse_max": a Jacobi round
  * whose frontier has at most this many changed wires is frontier-driven instead of a dense sweep (-1: rows/32,
  * 0: always dense); "grid_blocks": launch the solve kernel with fewer blocks than SMs (0: one per SM);
+ * "shard_min_rows": on several GPUs, problems with at least this many rows have their dense sweeps split over the
+ * GPUs, smaller ones are solved by every GPU in full without any exchange (2 000 000; 0: always shard — must be the
+ * same on every rank);
  * "p2_hash_bits": bits of the unknown-set hash the linear-system sweep groups by (56; fewer force collisions,
  * which the engine resolves by exact comparison — results do not depend on it). */
 int ecne_set_option(const char* key, int64_t value);

@@ -29,7 +29,7 @@ def test_engine_exports_every_declared_symbol():
     n = lib.ecne_abi_layout(None, 0)
     buf = (C.c_uint32 * n)()
     assert lib.ecne_abi_layout(buf, n) == n and list(buf) == _abi.layout_table()
-    assert n == 3 * 2 + 17 + 30 + 10
+    assert n == 3 * 2 + 17 + 31 + 10
 
 
 def test_host_exports_every_declared_symbol():
