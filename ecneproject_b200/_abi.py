@@ -89,6 +89,8 @@ ENGINE_SYMBOLS = [
     "ecne_upload", "ecne_solve_resident", "ecne_free_resident", "ecne_report_resident",
     "ecne_dist_unique_id", "ecne_dist_init", "ecne_dist_rank", "ecne_dist_world", "ecne_shard_rows",
     "ecne_set_option", "ecne_fr_batch",
+    "ecne_abstract_begin", "ecne_abstract_apply", "ecne_abstract_sizes", "ecne_abstract_export",
+    "ecne_abstract_upload", "ecne_abstract_free",
 ]
 HOST_SYMBOLS = [
     "ecne_read_r1cs", "ecne_read_r1cs_mem", "ecne_r1cs_free", "ecne_specials_new",
@@ -193,6 +195,18 @@ def engine_lib():
         lib.ecne_set_option.restype = C.c_int
         lib.ecne_fr_batch.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u64p]
         lib.ecne_fr_batch.restype = C.c_int
+        lib.ecne_abstract_begin.argtypes = [Pp, C.POINTER(C.c_void_p)]
+        lib.ecne_abstract_begin.restype = C.c_int
+        lib.ecne_abstract_apply.argtypes = [C.c_void_p, C.c_int32, Pp, u64p]
+        lib.ecne_abstract_apply.restype = C.c_int
+        lib.ecne_abstract_sizes.argtypes = [C.c_void_p, u64p]
+        lib.ecne_abstract_sizes.restype = C.c_int
+        lib.ecne_abstract_export.argtypes = [C.c_void_p, u64p, u32p, u64p, i32p, u64p, u32p, u64p, u32p]
+        lib.ecne_abstract_export.restype = C.c_int
+        lib.ecne_abstract_upload.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        lib.ecne_abstract_upload.restype = C.c_int
+        lib.ecne_abstract_free.argtypes = [C.c_void_p]
+        lib.ecne_abstract_free.restype = None
         lib.ecne_abi_layout.argtypes = [u32p, C.c_uint32]
         lib.ecne_abi_layout.restype = C.c_int
         check_layout(lib)

@@ -373,6 +373,104 @@ def abstraction(function_name, constraints, sub_equation, specials=None):
     return sp, R1CS(red)
 
 
+class DeviceAbstraction:
+    """abstraction() (R1CSConstraintSolver.jl:237-395) on the GPU (include/ecne_abi.h "abstraction() on the device"):
+    the unreduced system is uploaded once, every `apply` replaces the windows isomorphic to one trusted circuit by
+    special constraints with kernels, `upload` classifies the reduced system where it lies and returns the resident
+    handle ecne_solve_resident takes.  `export` brings the reduced system and the specials back (tests)."""
+
+    def __init__(self, main):
+        lib = _engine()
+        self.main = main
+        self.ph = ProblemHandle(main, None, main.known, main.targets, main.n_vars)
+        self.handle = C.c_void_p()
+        self.names = []
+        st = lib.ecne_abstract_begin(C.byref(self.ph.c), C.byref(self.handle))
+        if st != 0:
+            _raise(st, lib.ecne_last_error().decode())
+
+    def apply(self, function_name, sub):
+        lib = _engine()
+        sp = ProblemHandle(sub, None, sub.known, sub.targets, sub.n_vars)
+        n = C.c_uint64(0)
+        st = lib.ecne_abstract_apply(self.handle, _KIND_OF_NAME.get(function_name, _abi.SPECIAL_GENERIC), C.byref(sp.c), C.byref(n))
+        if st != 0:
+            _raise(st, lib.ecne_last_error().decode())
+        self.names += [function_name] * int(n.value)
+        return int(n.value)
+
+    def sizes(self):
+        z = (C.c_uint64 * 5)()
+        st = _engine().ecne_abstract_sizes(self.handle, z)
+        if st != 0:
+            _raise(st, _engine().ecne_last_error().decode())
+        return [int(x) for x in z]
+
+    def export(self):
+        """(seg_ptr, col, coef[nnz, 4]) of the reduced system and the specials as [(name, inputs, outputs)]."""
+        rows, nnz, ns, n_in, n_out = self.sizes()
+        seg = np.zeros(3 * rows + 1, dtype=np.uint64)
+        col = np.zeros(max(nnz, 1), dtype=np.uint32)
+        coef = np.zeros((max(nnz, 1), 4), dtype=np.uint64)
+        kind = np.zeros(max(ns, 1), dtype=np.int32)
+        ip, op = np.zeros(ns + 1, dtype=np.uint64), np.zeros(ns + 1, dtype=np.uint64)
+        iv, ov = np.zeros(max(n_in, 1), dtype=np.uint32), np.zeros(max(n_out, 1), dtype=np.uint32)
+        st = _engine().ecne_abstract_export(self.handle, seg.ctypes.data_as(_abi.u64p), col.ctypes.data_as(_abi.u32p),
+                                            coef.ctypes.data_as(_abi.u64p), kind.ctypes.data_as(_abi.i32p),
+                                            ip.ctypes.data_as(_abi.u64p), iv.ctypes.data_as(_abi.u32p),
+                                            op.ctypes.data_as(_abi.u64p), ov.ctypes.data_as(_abi.u32p))
+        if st != 0:
+            _raise(st, _engine().ecne_last_error().decode())
+        sp = [(self.names[i], iv[int(ip[i]):int(ip[i + 1])].tolist(), ov[int(op[i]):int(op[i + 1])].tolist()) for i in range(ns)]
+        return (seg, col[:nnz], coef[:nnz]), sp
+
+    def upload(self, secp_solve=False):
+        h = C.c_void_p()
+        st = _engine().ecne_abstract_upload(self.handle, int(bool(secp_solve)), C.byref(h))
+        if st != 0:
+            _raise(st, _engine().ecne_last_error().decode())
+        return h
+
+    def free(self):
+        if self.handle:
+            _engine().ecne_abstract_free(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def solve_with_device_abstraction(input_r1cs, trusted_r1cs=(), trusted_r1cs_names=(), secp_solve=False, full_state=False):
+    """solveWithTrustedFunctions (:502-581) with abstraction() on the GPU: parse (host), upload the unreduced system,
+    abstract the trusted circuits longest first (:527-544) on the device, classify in place, solve.
+    Returns (verdict, SolveResult, DeviceAbstraction sizes)."""
+    global last_result
+    main = readR1CS(input_r1cs)
+    function_list = [(trusted_r1cs_names[i], readR1CS(trusted_r1cs[i])) for i in range(len(trusted_r1cs))]
+    function_list.sort(key=lambda x: -len(x[1]))  # stable, longest first (:527)
+    da = DeviceAbstraction(main)
+    try:
+        for name, sub in function_list:
+            da.apply(name, sub)
+        sizes = da.sizes()
+        h = da.upload(secp_solve)
+    finally:
+        da.free()
+    lib = _engine()
+    res = SolveResult(main.n_vars, full_state=full_state)
+    try:
+        st = lib.ecne_solve_resident(h, C.byref(res.c))
+        if st != 0:
+            _raise(st, lib.ecne_last_error().decode())
+    finally:
+        lib.ecne_free_resident(h)
+    last_result = res
+    return bool(res.c.verdict), res, sizes
+
+
 _initialised = False
 
 

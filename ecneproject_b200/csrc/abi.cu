@@ -313,7 +313,32 @@ extern "C" int ecne_set_option(const char* key, int64_t value) {
   return ECNE_OK;
 }
 
-extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out) {
+namespace {
+// first row of each rank's range: ranges of equal stored-term weight (what ecne_shard_rows does on host arrays)
+__global__ void k_shard_cuts(const unsigned long long* seg, unsigned long long N, int world, unsigned long long* cuts) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > world) return;
+  if (r == 0) {
+    cuts[0] = 0;
+    return;
+  }
+  if (r == world) {
+    cuts[r] = N;
+    return;
+  }
+  const unsigned long long total = seg[3 * N];
+  const unsigned long long want = (unsigned long long)(((unsigned __int128)total * (unsigned)r) / (unsigned)world);
+  unsigned long long a = 0, b = N;  // smallest row i with seg[3 i] >= want
+  while (a < b) {
+    const unsigned long long m = (a + b) / 2;
+    if (seg[3 * m] >= want) b = m; else a = m + 1;
+  }
+  cuts[r] = a;
+}
+
+// ecne_upload: `dev0` != nullptr: the rows are already resident on the first device (abstraction on the device);
+// problem->seg_ptr / col / coef are then not read.
+int upload_impl(const ecne_problem_t* problem, const DevSystem* dev0, ecne_resident_t** out) {
   if (!out) return fail(ECNE_E_BADARG, "null out pointer");
   *out = nullptr;
   if (!G.inited) {
@@ -336,7 +361,33 @@ extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out)
     R.h_status = (Status*)c->h_status;
     R.h_counts = (unsigned long long*)c->h_counts;
     R.arena.pool = &c->pool;
-    sts[i] = build_resident(problem, &R, errs[i]);
+    if (!dev0) {
+      sts[i] = build_resident(problem, &R, errs[i]);
+    } else if (i == 0) {
+      sts[i] = build_resident(problem, &R, errs[i], dev0);
+    } else {
+      // the other devices of this process pull the rows from the first one over NVLink (peer copy)
+      DevSystem ci;
+      ci.N = dev0->N;
+      ci.V = dev0->V;
+      ci.nnz = dev0->nnz;
+      ci.arena.pool = &c->pool;
+      cudaError_t e = ci.arena.alloc(&ci.seg, 3 * ci.N + 2);
+      if (e == cudaSuccess) e = ci.arena.alloc(&ci.col, ci.nnz + 1);
+      if (e == cudaSuccess) e = ci.arena.alloc(&ci.coef, ci.nnz + 1);
+      const int d0 = G.ctx[0]->device;
+      if (e == cudaSuccess) e = cudaMemcpyPeerAsync(ci.seg, c->device, dev0->seg, d0, (3 * ci.N + 1) * 8, c->stream);
+      if (e == cudaSuccess && ci.nnz) e = cudaMemcpyPeerAsync(ci.col, c->device, dev0->col, d0, ci.nnz * 4, c->stream);
+      if (e == cudaSuccess && ci.nnz) e = cudaMemcpyPeerAsync(ci.coef, c->device, dev0->coef, d0, ci.nnz * 32, c->stream);
+      if (e != cudaSuccess) {
+        errs[i] = std::string("peer copy of the reduced system: ") + cudaGetErrorString(e);
+        sts[i] = ECNE_E_CUDA;
+      } else {
+        sts[i] = build_resident(problem, &R, errs[i], &ci);
+      }
+      cudaStreamSynchronize(c->stream);
+      if (ci.arena.pool) ci.arena.release();
+    }
   };
   if (nl == 1) {
     build_one(0);
@@ -356,7 +407,20 @@ extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out)
       return fail(st, e);
     }
   if (world > 1) {
-    const bool shard = (long long)problem->n_rows >= G.shard_min_rows;
+    const uint64_t n_rows = dev0 ? dev0->N : problem->n_rows;
+    const bool shard = (long long)n_rows >= G.shard_min_rows;
+    std::vector<unsigned long long> cuts;
+    if (shard && dev0) {  // the row offsets live on the device: the cut points are found there
+      cuts.resize(world + 1);
+      Arena t;
+      unsigned long long* d_cuts = nullptr;
+      cudaSetDevice(G.ctx[0]->device);
+      CKA(t.alloc(&d_cuts, world + 1));
+      k_shard_cuts<<<1, 32, 0, G.ctx[0]->stream>>>(dev0->seg, dev0->N, world, d_cuts);
+      CKA(cudaMemcpyAsync(cuts.data(), d_cuts, (world + 1) * 8, cudaMemcpyDeviceToHost, G.ctx[0]->stream));
+      CKA(cudaStreamSynchronize(G.ctx[0]->stream));
+      t.release();
+    }
     for (int i = 0; i < nl; ++i) {
       Dev& di = h->rs[i].d;
       di.world = world;
@@ -364,7 +428,12 @@ extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out)
       di.shard = shard ? 1 : 0;
       if (shard) {
         uint64_t lo = 0, hi = 0;
-        ecne_shard_rows(problem, di.rank, world, &lo, &hi);
+        if (dev0) {
+          lo = cuts[di.rank];
+          hi = cuts[di.rank + 1];
+        } else {
+          ecne_shard_rows(problem, di.rank, world, &lo, &hi);
+        }
         di.row_lo = (uint32_t)lo;
         di.row_hi = (uint32_t)hi;
       }
@@ -379,6 +448,119 @@ extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out)
   }
   *out = h;
   return ECNE_OK;
+}
+}  // namespace
+
+extern "C" int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out) { return upload_impl(problem, nullptr, out); }
+
+// ---- abstraction() on the device (SURVEY.md §8f-1, R1CSConstraintSolver.jl:237-395) --------------------------------
+struct ecne_abstracted {
+  DevSystem sys;
+  SpecialsHost sp;
+  std::vector<uint32_t> known, targets;
+  uint64_t n_vars = 0;
+  AbstractionStats stats;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double ms_h2d = 0;
+};
+
+extern "C" int ecne_abstract_begin(const ecne_problem_t* main, ecne_abstracted_t** out) {
+  if (!main || !out) return fail(ECNE_E_BADARG, "null argument");
+  *out = nullptr;
+  if (!G.inited) {
+    int st = ecne_init(0);
+    if (st) return st;
+  }
+  Ctx* c = G.ctx[0];
+  CKA(cudaSetDevice(c->device));
+  ecne_abstracted* a = new ecne_abstracted();
+  a->device = c->device;
+  a->stream = c->stream;
+  a->n_vars = main->n_vars;
+  a->known.assign(main->known, main->known + main->n_known);
+  a->targets.assign(main->targets, main->targets + main->n_targets);
+  a->sys.arena.pool = &c->pool;
+  std::string err;
+  auto t0 = std::chrono::steady_clock::now();
+  int st = dev_system_upload(main, &a->sys, c->stream, err);
+  if (st == ECNE_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    st = ECNE_E_CUDA;
+    err = "upload of the unreduced system failed";
+  }
+  a->ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (st != ECNE_OK) {
+    ecne_abstract_free(a);
+    return fail(st, err);
+  }
+  *out = a;
+  return ECNE_OK;
+}
+extern "C" int ecne_abstract_apply(ecne_abstracted_t* a, int32_t kind, const ecne_problem_t* sub, uint64_t* n_matches) {
+  if (!a || !sub) return fail(ECNE_E_BADARG, "null argument");
+  CKA(cudaSetDevice(a->device));
+  std::string err;
+  int st = dev_abstraction(&a->sys, kind, sub, &a->sp, n_matches, a->stream, err, &a->stats);
+  if (st != ECNE_OK) return fail(st, err);
+  if (getenv("ECNE_HOST_PROF"))
+    fprintf(stderr, "[ecne dev] abstraction: hashes %.3f ms | candidates %.3f ms (%llu) | verification %.3f ms (%llu matches) | "
+                    "compaction %.3f ms (cumulative over the calls of this handle)\n", a->stats.ms_hash, a->stats.ms_candidates,
+            (unsigned long long)a->stats.n_candidates, a->stats.ms_verify, (unsigned long long)a->stats.n_matches, a->stats.ms_compact);
+  return ECNE_OK;
+}
+extern "C" int ecne_abstract_sizes(const ecne_abstracted_t* a, uint64_t sizes[5]) {
+  if (!a || !sizes) return fail(ECNE_E_BADARG, "null argument");
+  sizes[0] = a->sys.N;
+  sizes[1] = a->sys.nnz;
+  sizes[2] = a->sp.kind.size();
+  sizes[3] = a->sp.in.size();
+  sizes[4] = a->sp.out.size();
+  return ECNE_OK;
+}
+extern "C" int ecne_abstract_export(ecne_abstracted_t* a, uint64_t* seg_ptr, uint32_t* col, uint64_t* coef, int32_t* sp_kind,
+                                    uint64_t* sp_in_ptr, uint32_t* sp_in, uint64_t* sp_out_ptr, uint32_t* sp_out) {
+  if (!a) return fail(ECNE_E_BADARG, "null argument");
+  CKA(cudaSetDevice(a->device));
+  if (seg_ptr) CKA(cudaMemcpyAsync(seg_ptr, a->sys.seg, (3 * a->sys.N + 1) * 8, cudaMemcpyDeviceToHost, a->stream));
+  if (col && a->sys.nnz) CKA(cudaMemcpyAsync(col, a->sys.col, a->sys.nnz * 4, cudaMemcpyDeviceToHost, a->stream));
+  if (coef && a->sys.nnz) CKA(cudaMemcpyAsync(coef, a->sys.coef, a->sys.nnz * 32, cudaMemcpyDeviceToHost, a->stream));
+  CKA(cudaStreamSynchronize(a->stream));
+  const size_t ns = a->sp.kind.size();
+  if (sp_kind && ns) memcpy(sp_kind, a->sp.kind.data(), ns * sizeof(int32_t));
+  if (sp_in_ptr) memcpy(sp_in_ptr, a->sp.in_ptr.data(), (ns + 1) * 8);
+  if (sp_out_ptr) memcpy(sp_out_ptr, a->sp.out_ptr.data(), (ns + 1) * 8);
+  if (sp_in && !a->sp.in.empty()) memcpy(sp_in, a->sp.in.data(), a->sp.in.size() * 4);
+  if (sp_out && !a->sp.out.empty()) memcpy(sp_out, a->sp.out.data(), a->sp.out.size() * 4);
+  return ECNE_OK;
+}
+extern "C" int ecne_abstract_upload(ecne_abstracted_t* a, int32_t secp_solve, ecne_resident_t** out) {
+  if (!a || !out) return fail(ECNE_E_BADARG, "null argument");
+  ecne_problem_t p;
+  memset(&p, 0, sizeof p);
+  p.n_rows = a->sys.N;
+  p.n_vars = a->n_vars;
+  p.known = a->known.data();
+  p.n_known = a->known.size();
+  p.targets = a->targets.data();
+  p.n_targets = a->targets.size();
+  p.n_specials = a->sp.kind.size();
+  p.sp_kind = a->sp.kind.data();
+  p.sp_in_ptr = a->sp.in_ptr.data();
+  p.sp_in = a->sp.in.data();
+  p.sp_out_ptr = a->sp.out_ptr.data();
+  p.sp_out = a->sp.out.data();
+  p.secp_solve = secp_solve;
+  int st = upload_impl(&p, &a->sys, out);
+  if (st == ECNE_OK)
+    for (auto& R : (*out)->rs) R.ms_h2d = a->ms_h2d;  // what crossed PCIe for this problem: the unreduced system, once
+  return st;
+}
+extern "C" void ecne_abstract_free(ecne_abstracted_t* a) {
+  if (!a) return;
+  cudaSetDevice(a->device);
+  if (a->stream) cudaStreamSynchronize(a->stream);
+  if (a->sys.arena.pool) a->sys.arena.release();
+  delete a;
 }
 
 extern "C" void ecne_free_resident(ecne_resident_t* h) {

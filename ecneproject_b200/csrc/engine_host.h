@@ -120,7 +120,34 @@ struct Resident {
   void* xhdr = nullptr;
 };
 
-// setup.cu: H2D + classification + layout.  Returns an ecne_status.
-int build_resident(const ecne_problem_t* p, Resident* r, std::string& err);
+// A constraint system in its on-disk layout (explicit zeros included) resident on the device: what the
+// classification reads, and what abstraction() on the device (abstraction.cu) consumes and produces.
+struct DevSystem {
+  uint64_t N = 0, V = 0, nnz = 0;
+  unsigned long long* seg = nullptr;  // [3N + 1]
+  uint32_t* col = nullptr;
+  fr::u256* coef = nullptr;
+  Arena arena;
+};
+struct SpecialsHost {  // the special constraints found so far (:357-384), CSR over specials
+  std::vector<int32_t> kind;
+  std::vector<uint64_t> in_ptr{0}, out_ptr{0};
+  std::vector<uint32_t> in, out;
+};
+struct AbstractionStats {
+  double ms_hash = 0, ms_candidates = 0, ms_verify = 0, ms_compact = 0;
+  uint64_t n_candidates = 0, n_matches = 0;
+};
+#ifndef ECNE_E_KEYERROR
+#define ECNE_E_KEYERROR (-10)  // KeyError at R1CSConstraintSolver.jl:381-382 (same code as include/ecne_host.h)
+#endif
+// abstraction.cu
+int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std::string& err);
+int dev_abstraction(DevSystem* S, int32_t kind, const ecne_problem_t* sub, SpecialsHost* sp, uint64_t* n_matches,
+                    cudaStream_t s, std::string& err, AbstractionStats* stats);
+
+// setup.cu: H2D + classification + layout.  Returns an ecne_status.  With `dev` the rows are taken from a system that
+// is already resident on the device (p->seg_ptr / col / coef are not read; sizes come from `dev`).
+int build_resident(const ecne_problem_t* p, Resident* r, std::string& err, const DevSystem* dev = nullptr);
 
 }  // namespace ecne

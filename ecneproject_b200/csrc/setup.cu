@@ -763,12 +763,12 @@ static cudaError_t h2d(T* dst, const T* src, size_t n, cudaStream_t s) {
 }
 static inline unsigned int nb(uint64_t n, unsigned int t) { return (unsigned int)((n + t - 1) / t); }
 
-int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
-  if (!p || !p->seg_ptr || (p->n_rows && (!p->col || !p->coef))) {
+int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const DevSystem* dev) {
+  if (!p || (!dev && (!p->seg_ptr || (p->n_rows && (!p->col || !p->coef))))) {
     err = "null problem arrays";
     return ECNE_E_BADARG;
   }
-  const uint64_t N = p->n_rows, V = p->n_vars, nnz = p->seg_ptr[3 * N];
+  const uint64_t N = dev ? dev->N : p->n_rows, V = p->n_vars, nnz = dev ? dev->nnz : p->seg_ptr[3 * N];
   if (V < 1 || V >= 0x7fffffffULL || N >= 0x3fffffffULL || nnz >= 0x7fffffffULL) {
     err = "problem too large for 32-bit indices (rows < 2^30, wires, terms < 2^31)";
     return ECNE_E_BADARG;
@@ -818,12 +818,18 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err) {
   unsigned long long* d_seg64;
   uint32_t* d_col_raw;
   fr::u256* d_coef_raw;
-  CK(tmp.alloc(&d_seg64, 3 * N + 2));
-  CK(tmp.alloc(&d_col_raw, nnz));
-  CK(tmp.alloc(&d_coef_raw, nnz));
-  CK(h2d(d_seg64, (const unsigned long long*)p->seg_ptr, 3 * N + 1, s));
-  CK(h2d(d_col_raw, p->col, nnz, s));
-  CK(h2d((uint64_t*)d_coef_raw, p->coef, 4 * nnz, s));
+  if (dev) {  // the rows are on the device already (abstraction.cu): nothing crosses PCIe
+    d_seg64 = dev->seg;
+    d_col_raw = dev->col;
+    d_coef_raw = dev->coef;
+  } else {
+    CK(tmp.alloc(&d_seg64, 3 * N + 2));
+    CK(tmp.alloc(&d_col_raw, nnz));
+    CK(tmp.alloc(&d_coef_raw, nnz));
+    CK(h2d(d_seg64, (const unsigned long long*)p->seg_ptr, 3 * N + 1, s));
+    CK(h2d(d_col_raw, p->col, nnz, s));
+    CK(h2d((uint64_t*)d_coef_raw, p->coef, 4 * nnz, s));
+  }
 
   Dev& d = R->d;
   memset(&d, 0, sizeof(d));

@@ -142,6 +142,30 @@ int ecne_upload(const ecne_problem_t* problem, ecne_resident_t** out);
 int ecne_solve_resident(ecne_resident_t* r, ecne_result_t* result);
 void ecne_free_resident(ecne_resident_t* r);
 
+/* ---- abstraction() on the device (R1CSConstraintSolver.jl:237-395, helpers :205-235) ------
+ * The caller of :552, solveWithTrustedFunctions (:502-581), first replaces every window of the main circuit that is
+ * isomorphic to a trusted circuit by a special constraint (:538-544), trusted circuits longest first.  With these
+ * entry points that pass runs on the GPU: the UNREDUCED system is uploaded once (ecne_abstract_begin), every trusted
+ * circuit is matched by kernels and the kept rows are compacted on the device (ecne_abstract_apply, one call per
+ * trusted circuit in the order of :527-537; `sub` = its rows, known = its inputs, targets = its outputs; n_matches =
+ * windows replaced by this call), and ecne_abstract_upload classifies the reduced system where it lies — it never
+ * crosses PCIe and no host core touches a row — giving the same resident handle as ecne_upload.  KeyError of
+ * :381-382 (an input / output of the trusted circuit that never appears in it) is ECNE_E_KEYERROR.
+ * ecne_abstract_sizes: {rows, stored terms, special constraints, their input wires, their output wires} so far;
+ * ecne_abstract_export: D2H of the reduced system and the specials into caller arrays of those sizes (any pointer may
+ * be NULL) — parity tests and hosts that want the reduced system back. */
+#ifndef ECNE_E_KEYERROR
+#define ECNE_E_KEYERROR (-10)
+#endif
+typedef struct ecne_abstracted ecne_abstracted_t;
+int ecne_abstract_begin(const ecne_problem_t* main_circuit, ecne_abstracted_t** out);
+int ecne_abstract_apply(ecne_abstracted_t* a, int32_t kind, const ecne_problem_t* sub, uint64_t* n_matches);
+int ecne_abstract_sizes(const ecne_abstracted_t* a, uint64_t sizes[5]);
+int ecne_abstract_export(ecne_abstracted_t* a, uint64_t* seg_ptr, uint32_t* col, uint64_t* coef, int32_t* sp_kind,
+                         uint64_t* sp_in_ptr, uint32_t* sp_in, uint64_t* sp_out_ptr, uint32_t* sp_out);
+int ecne_abstract_upload(ecne_abstracted_t* a, int32_t secp_solve, ecne_resident_t** out);
+void ecne_abstract_free(ecne_abstracted_t* a);
+
 /* ---- report path: the "Bad Constraints" listing (R1CSConstraintSolver.jl:1599-1635) ----------
  * The reference walks every constraint, keeps those that mention (getVariables, :36-56: a stored
  * non-zero coefficient) a wire that is not unique (:1612-1620), and prints the state of each of their

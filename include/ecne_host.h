@@ -17,7 +17,9 @@
 extern "C" {
 #endif
 
+#ifndef ECNE_E_KEYERROR
 #define ECNE_E_KEYERROR (-10) /* KeyError at R1CSConstraintSolver.jl:381-382 */
+#endif
 #define ECNE_E_IO (-11)       /* SystemError opening the file (ParseR1CS.jl:52-53) */
 #define ECNE_E_ASSERT (-12)   /* AssertionError at ParseR1CS.jl:58,62,69 */
 
