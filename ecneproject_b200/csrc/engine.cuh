@@ -209,14 +209,31 @@ struct Dev {
 // SM's L1 lines) — so ordinary L1-cacheable loads are correct here, exactly as after grid.sync(),
 // and neighbouring rows that touch neighbouring wires share L1 sectors instead of paying one L2
 // sector per state byte.
+//
+// The exception is the stretch of rounds that ONE warp runs alone (kernels.cu warp_solo): it separates its rounds with
+// __syncwarp only — no fence, no acquire, so nothing drops its SM's L1 lines — and therefore reads the state through
+// the L2 (ld.global.cg), where its own atomics of the round before have been performed.  The mode travels as a tag in
+// the top bit of the state pointer (st_F / st_L / st_U below make the pointers from a buffer index whose bit 1 is the
+// tag), so the evaluators need no second copy and the other paths pay one sign test.
+#define ST_TAG_CG 2  // bit of a buffer index: read the state through the L2
 __device__ __forceinline__ uint32_t ld_flag(const uint8_t* F, uint32_t w) {
   uint32_t v;
-  asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(v) : "l"(F + w));
+  if ((long long)(uintptr_t)F < 0) {
+    const uint8_t* p = (const uint8_t*)((uintptr_t)F & 0x7fffffffffffffffULL) + w;
+    asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  } else {
+    asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(v) : "l"(F + w));
+  }
   return v;
 }
 __device__ __forceinline__ uint32_t ld_u32(const uint32_t* p, uint32_t i) {
   uint32_t v;
-  asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p + i));
+  if ((long long)(uintptr_t)p < 0) {
+    const uint32_t* q = (const uint32_t*)((uintptr_t)p & 0x7fffffffffffffffULL) + i;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(q));
+  } else {
+    asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p + i));
+  }
   return v;
 }
 

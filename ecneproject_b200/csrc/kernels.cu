@@ -303,12 +303,12 @@ __device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, int wbuf, 
     bool K1 = f[0] & WF_K, K2 = f[1] & WF_K;
     if ((f[0] | f[1]) & WF_BND) {
       if (f[0] & WF_BND) {
-        l1 = ld_u32(d.LBR[rbuf], k1);
-        u1 = ld_u32(d.UBR[rbuf], k1);
+        l1 = ld_u32(st_L(rbuf), k1);
+        u1 = ld_u32(st_U(rbuf), k1);
       }
       if (f[1] & WF_BND) {
-        l2 = ld_u32(d.LBR[rbuf], k2);
-        u2 = ld_u32(d.UBR[rbuf], k2);
+        l2 = ld_u32(st_L(rbuf), k2);
+        u2 = ld_u32(st_U(rbuf), k2);
       }
       if (u1 != u2 || l1 != l2) {
         const uint32_t mn = u1 < u2 ? u1 : u2, mx = l1 > l2 ? l1 : l2;
@@ -831,6 +831,15 @@ struct SoloState {
   unsigned int n, list, rbuf, round, bepoch, gr, hv, prev_list;
   unsigned int dn;  // distinct wires the last round changed (== n on one GPU)
 };
+// Unsharded runs take the fast path: between two rounds of the stretch there is only a __syncwarp.  The records stay
+// in shared memory (sweep.cuh "records of a stretch"), the state is read through the L2 (ST_TAG_CG) where the warp's
+// own atomics have been performed — every atomic of a round has returned before the round ends: the updates of the
+// write buffer return the old value that decides whether they are logged, the replays into the other buffer are
+// issued at the start of the round as returning atomics whose results are consumed at its end — and nothing touches the global
+// record lists or counters until the stretch ends (frontier empty or too large, a heavy wire, a spilled queue): then
+// the last round's records are written to the global list, one fence makes everything visible, and the state block is
+// left exactly as a round through the global lists would leave it.  Sharded runs (which count distinct wires per
+// round through the global arrays) keep the round-by-round global protocol.
 __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int prev_n, unsigned int max_rounds,
                                        unsigned long long* evals_io) {
   const Dev& d = c_dev;
@@ -839,9 +848,17 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
                gr = st->gr, hv = 0, dn = 0;
   int rbuf = (int)st->rbuf;
   unsigned long long ev = 0;
+  const bool fast = !d.shard;
+  bool from_smem = false;      // the records of the round before are in s_soloq[qr]
+  unsigned int qr = 0;         // queue read this round (fast path); the round writes queue qr ^ 1
+  unsigned int prog_acc = 0;
+  uint32_t replay_sink = 0;    // consumes the results of the replay atomics (see above)
   while (true) {
     gr += 1;
     const int wbuf = rbuf ^ 1;
+    const int rb = fast ? (rbuf | ST_TAG_CG) : rbuf;
+    const unsigned int qw = qr ^ 1u;
+    const int elist = fast ? (int)(list | LIST_SOLO | (qw ? LIST_SOLO_Q : 0)) : (int)list;
     // lane i holds record i and the head of its wire's row list; the (record, listed row) pairs are then
     // dealt out one per lane, so every row of the frontier is evaluated in the same step
     const bool have = lane < n;
@@ -852,9 +869,24 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
     r.ubr = ECNE_NO_UB;
     uint4 hd = make_uint4(0, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     if (have) {
-      r = ld_peer_rec(d.recs[prev_list] + lane);
-      hd = __ldcg(reinterpret_cast<const uint4*>(d.inv_head) + r.wire);
+      if (from_smem) {
+        r = s_soloq[qr][lane].r;
+        hd = s_soloq[qr][lane].head;
+      } else {
+        r = ld_peer_rec(d.recs[prev_list] + lane);
+        hd = __ldcg(reinterpret_cast<const uint4*>(d.inv_head) + r.wire);
+      }
     }
+    if (fast && lane == 0) {
+      s_soloq_n[qw] = 0;
+      s_solo_flags = 0;
+    }
+    // fast path: the replay of the record into the other buffer is issued FIRST, as a returning atomic whose result
+    // is consumed when the round ends — it has long returned by then, so it is performed at the L2 before the next
+    // round (which reads that buffer) starts, and it costs no trip on the round's critical path
+    uint32_t rp0 = 0, rp1 = 0, rp2 = 0;
+    if (fast && have) apply_update_issue(wbuf, r.wire, r.bits, r.lbr, r.ubr, rp0, rp1, rp2);
+    __syncwarp();
     unsigned int incl = hd.x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -893,10 +925,10 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
             is_long = !__ldcg(d.long_done + li) && atomicExch(d.long_stamp + li, gr) != gr;
           } else if (!(latched & 1)) {
             uint32_t f[ROWREC_INLINE];
-            gather_row(d.F[rbuf], ir, f);
+            gather_row(st_F(rb), ir, f);
             ev += 1;
-            if (eval_inline(d, rbuf, wbuf, (int)list, row, ir, f, bepoch) & EI_GENERIC)
-              eval_row<1>(d, rbuf, wbuf, (int)list, row, bepoch);
+            if (eval_inline(d, rb, wbuf, elist, row, ir, f, bepoch) & EI_GENERIC)
+              eval_row<1>(d, rb, wbuf, elist, row, bepoch);
           }
         }
       }
@@ -905,40 +937,90 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
         const int src = __ffs((int)m) - 1;
         m &= m - 1;
         const uint32_t lrow = __shfl_sync(0xffffffffu, row, src);
-        const bool done = eval_row<32>(d, rbuf, wbuf, (int)list, lrow, bepoch);
+        const bool done = eval_row<32>(d, rb, wbuf, elist, lrow, bepoch);
         if (lane == 0) {
           ev += 1;
           if (done) d.long_done[d.rec[lrow].c[0]] = 1;
         }
       }
     }
-    if (have) {  // the replay
+    if (have && !fast) {  // the replay
       apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
       consume_rec(d, prev_list, r.wire);
     }
+    replay_sink |= rp0 ^ rp1 ^ rp2;  // first use of the replay atomics' results: waits until they have been performed
+    if (__all_sync(0xffffffffu, replay_sink == 0xdeadbeefu)) ev += 1;  // (keeps the use alive; practically never true)
     __syncwarp();
     unsigned int cnt = 0, bf = 0;
-    if (lane == 0) {
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cnt) : "l"(d.rec_count + list) : "memory");
-      asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(bf) : "l"(d.bnd_flag + list) : "memory");
-      if (d.shard) asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(dn) : "l"(d.dcnt + list) : "memory");
-      d.rec_count[prev_list] = 0;  // consumed; next written two rounds from now
-      d.bnd_flag[prev_list] = 0;
-      d.dcnt[prev_list] = 0;
-      atomicAdd(&d.st->prog, cnt);
+    bool leave;
+    if (fast) {
+      const unsigned int flags = s_solo_flags, nq = s_soloq_n[qw];
+      const bool spilled = (flags & 4u) != 0;
+      if (lane == 0 && !from_smem) {  // the list the stretch started from is consumed
+        d.rec_count[prev_list] = 0;
+        d.bnd_flag[prev_list] = 0;
+        d.dcnt[prev_list] = 0;
+      }
+      bf = flags & 3u;
+      cnt = nq < SOLO_Q_CAP ? nq : SOLO_Q_CAP;
+      leave = spilled || cnt == 0 || cnt > WARP_SOLO_MAX || (bf & 2u) || round + 1 >= max_rounds;
+      if (leave) {
+        // hand the last round's records over through the global list (behind what spilled there already)
+        unsigned int base = 0;
+        if (spilled) {
+          if (lane == 0) base = atomicAdd(d.rec_count + list, cnt);
+          base = __shfl_sync(0xffffffffu, base, 0);
+        }
+        for (unsigned int i = lane; i < cnt; i += 32) {
+          if (base + i < d.rec_cap)
+            d.recs[list][base + i] = s_soloq[qw][i].r;
+          else
+            d.st->rec_overflow = 1;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if (!spilled) d.rec_count[list] = cnt;
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          unsigned int gbf = 0;
+          asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cnt) : "l"(d.rec_count + list) : "memory");
+          asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(gbf) : "l"(d.bnd_flag + list) : "memory");
+          bf |= gbf & 3u;
+          atomicAdd(&d.st->prog, prog_acc + cnt);
+        }
+        cnt = __shfl_sync(0xffffffffu, cnt, 0);
+        bf = __shfl_sync(0xffffffffu, bf, 0);
+      } else {
+        prog_acc += cnt;
+      }
+      dn = cnt;
+    } else {
+      if (lane == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cnt) : "l"(d.rec_count + list) : "memory");
+        asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(bf) : "l"(d.bnd_flag + list) : "memory");
+        asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(dn) : "l"(d.dcnt + list) : "memory");
+        d.rec_count[prev_list] = 0;  // consumed; next written two rounds from now
+        d.bnd_flag[prev_list] = 0;
+        d.dcnt[prev_list] = 0;
+        atomicAdd(&d.st->prog, cnt);
+      }
+      cnt = __shfl_sync(0xffffffffu, cnt, 0);
+      bf = __shfl_sync(0xffffffffu, bf, 0);
+      dn = __shfl_sync(0xffffffffu, dn, 0);
+      leave = false;
     }
-    cnt = __shfl_sync(0xffffffffu, cnt, 0);
-    bf = __shfl_sync(0xffffffffu, bf, 0);
-    dn = d.shard ? __shfl_sync(0xffffffffu, dn, 0) : cnt;
     bepoch += bf & 1u;
     hv = bf & 2u;
     round += 1;
     n = cnt;
-    if (n == 0 || n > WARP_SOLO_MAX || hv || round >= max_rounds) break;
+    if (leave || n == 0 || n > WARP_SOLO_MAX || hv || round >= max_rounds) break;
     prev_list = list;
     list = (list + 1) % 3;
     rbuf ^= 1;
+    if (fast) {
+      from_smem = true;
+      qr = qw;
+    }
   }
   *evals_io += ev;
   if (lane == 0) {

@@ -16,6 +16,29 @@ namespace ecne {
 // One solve runs at a time per process (the API is single-threaded).
 __constant__ Dev c_dev;
 
+// state pointers of read buffer `rb` (bit 0: the buffer, bit ST_TAG_CG: read through the L2, engine.cuh)
+__device__ __forceinline__ uintptr_t st_tag(int rb) { return (uintptr_t)(rb & ST_TAG_CG) << 62; }
+__device__ __forceinline__ const uint8_t* st_F(int rb) { return (const uint8_t*)((uintptr_t)c_dev.F[rb & 1] | st_tag(rb)); }
+__device__ __forceinline__ const uint32_t* st_L(int rb) { return (const uint32_t*)((uintptr_t)c_dev.LBR[rb & 1] | st_tag(rb)); }
+__device__ __forceinline__ const uint32_t* st_U(int rb) { return (const uint32_t*)((uintptr_t)c_dev.UBR[rb & 1] | st_tag(rb)); }
+
+// ---- records of a stretch of rounds that one warp runs alone (kernels.cu warp_solo) -----------------------------------
+// The warp is producer and consumer of its update records: they stay in shared memory, with the head of the wire's row
+// list fetched by the emitter next to its state atomic — no slot atomic, no record store / load through the L2, no
+// fence and no counter read between two rounds.  `list` carries LIST_SOLO and the queue to write (LIST_SOLO_Q).  A
+// round that emits more than the queue holds (or fires a whole long row, emit_unique_all) spills to the global list
+// and ends the stretch.
+#define LIST_SOLO 16
+#define LIST_SOLO_Q 32
+#define SOLO_Q_CAP 64
+struct __align__(16) SoloRec {
+  Rec r;
+  uint4 head;  // inv_head[r.wire]
+};
+__shared__ SoloRec s_soloq[2][SOLO_Q_CAP];
+__shared__ unsigned int s_soloq_n[2];
+__shared__ unsigned int s_solo_flags;  // bit0: a bound moved, bit1: a heavy wire changed, bit2: records spilled to the global list
+
 // Apply one update {OR bits into F, max lbr into LBR, min ubr into UBR} to buffer `buf`.  The bits of
 // the derived test "bounds == [0,1]" follow from the update's own values, so every part is a
 // commutative, monotone RMW: no ordering between concurrent updates of a wire is needed.
@@ -55,6 +78,25 @@ __device__ __forceinline__ void apply_update(const Dev&, int buf, uint32_t w, ui
                                              uint32_t ubr) {
   apply_update_t<false>(buf, w, bits, lbr, ubr);
 }
+// The same update issued as RETURNING atomics whose raw results are handed back untouched: the caller consumes them
+// (any use) at the point where it needs the update to have been performed at the L2 — until then the atomics are
+// simply in flight (kernels.cu warp_solo: the replay of a round's records).
+__device__ __forceinline__ void apply_update_issue(int buf, uint32_t w, uint32_t bits, uint32_t lbr, uint32_t ubr,
+                                                   uint32_t& o0, uint32_t& o1, uint32_t& o2) {
+  const Dev& d = c_dev;
+  o0 = o1 = o2 = 0;
+  if (lbr != ECNE_NO_LB || ubr != ECNE_NO_UB) {
+    bits |= WF_BND;
+    if (ubr != ECNE_NO_UB && ubr <= d.r1) bits |= WF_UB01;
+    if ((ubr != ECNE_NO_UB && ubr < d.r1) || (lbr != ECNE_NO_LB && lbr > d.r0)) bits |= WF_NOT01;
+    if (lbr != ECNE_NO_LB) o1 = atomicMax(d.LBR[buf] + w, lbr);
+    if (ubr != ECNE_NO_UB) o2 = atomicMin(d.UBR[buf] + w, ubr);
+  }
+  if (bits) {
+    unsigned int* word = (unsigned int*)(d.F[buf] + (w & ~3u));
+    o0 = atomicOr(word, bits << ((w & 3u) * 8));
+  }
+}
 // a record of list `list` has been consumed (replayed): its wire may be counted again when the list is
 // written next (two rounds from now)
 __device__ __forceinline__ void consume_rec(const Dev& d, unsigned int list, uint32_t w) {
@@ -79,6 +121,33 @@ __device__ __noinline__ void emit_impl(int wbuf, int list_in, uint32_t w, uint32
   const Dev& d = c_dev;
   const int list = list_in & 7;
   const bool count_distinct = d.shard && !(list_in & LIST_NOCOUNT);
+  if (list_in & LIST_SOLO) {
+    // one warp alone: the head of the wire's row list is fetched while the state atomic is in flight
+    const uint4 hd = __ldcg(reinterpret_cast<const uint4*>(d.inv_head) + w);
+    const uint32_t r = apply_update_t<true>(wbuf, w, bits, lbr, ubr);
+    const uint32_t want = ((r & 2u) ? 1u : 0u) | (((r & 1u) && (r & 4u)) ? 2u : 0u);
+    if (want) atomicOr(&s_solo_flags, want);
+    if (!(r & 1u)) return;
+    Rec rr;
+    rr.wire = w;
+    rr.bits = (lbr != ECNE_NO_LB || ubr != ECNE_NO_UB) ? (bits | WF_BND) : bits;
+    rr.lbr = lbr;
+    rr.ubr = ubr;
+    const int q = (list_in & LIST_SOLO_Q) ? 1 : 0;
+    const unsigned int i = atomicAdd(&s_soloq_n[q], 1u);
+    if (i < SOLO_Q_CAP) {
+      s_soloq[q][i].r = rr;
+      s_soloq[q][i].head = hd;
+      return;
+    }
+    atomicOr(&s_solo_flags, 4u);  // queue full: this record goes to the global list, the stretch ends with this round
+    const unsigned int gi = atomicAdd(d.rec_count + list, 1u);
+    if (gi < d.rec_cap)
+      d.recs[list][gi] = rr;
+    else
+      d.st->rec_overflow = 1;
+    return;
+  }
   const uint32_t r = apply_update_t<true>(wbuf, w, bits, lbr, ubr);
   // round flags (bit0: a bound moved, bit1: a heavy wire changed => the next round is dense): set once —
   // 160 k rows fix a bound in ecdsa's first round, and 160 k REDs on one address serialise in one L2 slice
@@ -197,25 +266,25 @@ struct RowCtx {
       l = ov.lb[i];
       u = ov.ub[i];
     } else {
-      l = ld_u32(d.LBR[rbuf], w);
-      u = ld_u32(d.UBR[rbuf], w);
+      l = ld_u32(st_L(rbuf), w);
+      u = ld_u32(st_U(rbuf), w);
     }
   }
   __device__ __forceinline__ bool b01(uint32_t w) const {
     const Dev& d = c_dev;
     int i = ov.find(w);
     if (i >= 0) return ov.lb[i] == d.r0 && ov.ub[i] == d.r1;
-    return is01(ld_flag(d.F[rbuf], w));
+    return is01(ld_flag(st_F(rbuf), w));
   }
   __device__ __forceinline__ bool uniq(uint32_t w) const {
     const Dev& d = c_dev;
-    return ov.all_unique || (ld_flag(d.F[rbuf], w) & WF_U);
+    return ov.all_unique || (ld_flag(st_F(rbuf), w) & WF_U);
   }
   __device__ __forceinline__ bool known(uint32_t w) const {
     const Dev& d = c_dev;
     int i = ov.find(w);
     if (i >= 0 && ov.k[i]) return true;
-    return ld_flag(d.F[rbuf], w) & WF_K;
+    return ld_flag(st_F(rbuf), w) & WF_K;
   }
   __device__ __forceinline__ void out(uint32_t w, uint32_t bits, uint32_t l = ECNE_NO_LB,
                                       uint32_t u = ECNE_NO_UB) const {
@@ -277,6 +346,7 @@ __device__ __noinline__ void emit_unique_all(const RowCtx& c, const uint8_t* F, 
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     if (total == 0) continue;
     uint32_t i = 0;
+    if (lane == 0 && (c.list & LIST_SOLO)) atomicOr(&s_solo_flags, 4u);  // records in the global list: the solo stretch ends
     if (lane == 0) i = atomicAdd(d.rec_count + list, total);
     i = __shfl_sync(0xffffffffu, i, 0) + incl - n;
 #pragma unroll
@@ -385,7 +455,7 @@ __device__ __noinline__ bool eval_row(const Dev&, int rbuf, int wbuf, int list, 
   const uint32_t rf = d.rflags[row];
   uint8_t latch = d.solved[row];
   if (latch & 1) return true;  // equation_solved (:820-822)
-  const uint8_t* F = d.F[rbuf];
+  const uint8_t* F = st_F(rbuf);
   const uint32_t s0 = d.seg[3 * row], s2 = d.seg[3 * row + 2], s3 = d.seg[3 * row + 3];
 #ifdef ECNE_PROFILE
   // slowest long-row evaluation of the solve, stage by stage (maxima; printed with ECNE_DEBUG_PROF=3)

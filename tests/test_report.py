@@ -100,7 +100,18 @@ def _solve_with_report(reduced, specials, main, secp):
 REPORT_CONFIGS = ["target/division", "root/bad_bd_check", "circomlib/Decoder@multiplexer", "circomlib/IsZero@comparators",
                   "circomlib/Point2Bits@pointbits", "circomlib/BabyPbk@babyjub", "circomlib/EdDSAPoseidonVerifier@eddsaposeidon",
                   "root/biglessthan", "root/secp256k1", "tornado/withdraw", "secp256k1+bmmp+blt", "root/poseidon",
-                  "tornado/withdraw+pedersen", "benchmarks/bigmod_86_3"]
+                  "tornado/withdraw+pedersen", "benchmarks/bigmod_86_3",
+                  # the two circuits whose listing shows schedule-dependent wires: compared against the
+                  # oracle everywhere except on the pinned wires, which must hold exactly their pinned state
+                  "circomlib/Bits2Point_Strict@pointbits", "circomlib/EdDSAVerifier@eddsa"]
+import json as _json
+import os as _os
+SCHEDULE_DIFFS = _json.load(open(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden",
+                                               "schedule_dependent_diffs.json")))
+
+
+def _toint(a):
+    return sum(int(a[i]) << (64 * i) for i in range(4))
 
 
 @pytest.mark.gpu
@@ -120,11 +131,24 @@ def test_bad_constraints_match_oracle(name):
     assert np.array_equal((bad.flags >> 1) & 1, kbits[w0])
     assert np.array_equal(bad.lb, res.lb[w0]) and np.array_equal(bad.ub, res.ub[w0])
     assert np.array_equal(bad.nvalues, res.nvalues[w0]) and np.array_equal(bad.values, res.values[w0])
-    # ... and on the wires that are NOT unique (what a reader of the listing looks at) it is the oracle's
-    nu = ~uniq[w0]
+    # ... and on the wires that are NOT unique (what a reader of the listing looks at) it is the oracle's — except on
+    # the pinned schedule-dependent wires, which hold exactly their pinned state and print as pinned
+    pinned = {e["wire"]: e for e in SCHEDULE_DIFFS.get(name, []) if not e["unique"]}
+    nu = ~uniq[w0] & ~np.isin(wires, list(pinned))
     assert np.array_equal(bad.lb[nu], o.lb[w0][nu]) and np.array_equal(bad.ub[nu], o.ub[w0][nu])
     assert np.array_equal(bad.nvalues[nu], o.nvalues[w0][nu])
     assert np.array_equal(bad.values[nu], o.values[w0][nu])
+    for w, e in pinned.items():
+        k = int(np.flatnonzero(wires == w)[0])  # a pinned non-unique wire is always listed
+        assert hex(_toint(bad.lb[k])) == e["engine"]["lb"] and hex(_toint(bad.ub[k])) == e["engine"]["ub"]
+        assert bool((bad.flags[k] >> 1) & 1) == e["engine"]["is_known"] and int(bad.nvalues[k]) == e["engine"]["nvalues"]
+        # what the listing prints for the wire (:396-419) on either side
+        got = api.format_state(False, _toint(bad.lb[k]), _toint(bad.ub[k]), [])
+        want_oracle = api.format_state(False, _toint(o.lb[w - 1]), _toint(o.ub[w - 1]), [])
+        assert got == f"Uniquely Determined: false\nBounds: [0, {int(e['engine']['ub'], 16)}]\n\n"
+        assert want_oracle == "Uniquely Determined: false\nBounds: None\n\n"
+    if name in ("circomlib/Bits2Point_Strict@pointbits", "circomlib/EdDSAVerifier@eddsa"):
+        assert len(pinned) == (2 if "Bits2Point" in name else 8)
     if len(rows) == 0:  # a sound system with every wire determined lists nothing
         assert len(wires) == 0 and bad.n_bad_rows == 0
 
