@@ -406,6 +406,36 @@ def main():
         if st != 0:
             raise RuntimeError(lib.ecne_last_error().decode())
     barrier()
+    # ---- file -> verdict with abstraction() on the device (N = 1): parse on the host cores, upload the UNREDUCED
+    # system once, abstract + classify where it lies, solve (include/ecne_abi.h "abstraction() on the device")
+    f2v = None
+    if world == 1:
+        from ecneproject_b200 import fixtures
+        f2v_t, f2v_parts = [], None
+        for _ in range(4):
+            t0 = time.perf_counter()
+            m_ = api.readR1CS(fixtures.path(WORKLOAD["main"]))
+            subs_ = [(WORKLOAD["trusted_names"][i], api.readR1CS(fixtures.path(t))) for i, t in enumerate(WORKLOAD["trusted"])]
+            subs_.sort(key=lambda x: -len(x[1]))
+            t1 = time.perf_counter()
+            da = api.DeviceAbstraction(m_)
+            for nm_, sub_ in subs_:
+                da.apply(nm_, sub_)
+            t2 = time.perf_counter()
+            h_ = da.upload(False)
+            res3 = api.SolveResult(m_.n_vars, full_state=False)
+            st = lib.ecne_solve_resident(h_, C.byref(res3.c))
+            t3 = time.perf_counter()
+            lib.ecne_free_resident(h_)
+            da.free()
+            if st != 0:
+                raise RuntimeError(lib.ecne_last_error().decode())
+            assert res3.unique_bits.tobytes() == res.unique_bits.tobytes()
+            f2v_t.append(t3 - t0)
+            f2v_parts = {"read_s": t1 - t0, "upload_and_abstraction_on_device_s": t2 - t1, "classify_and_solve_s": t3 - t2}
+        f2v = {"seconds": sum(f2v_t[1:]) / len(f2v_t[1:]), "runs": f2v_t, "last_run": f2v_parts,
+               "how": "readR1CS on the host cores, ecne_abstract_begin/apply/upload (abstraction and classification on the "
+                      "GPU, the reduced system never crosses PCIe), ecne_solve_resident; bitmap equal to the resident leg's"}
     clocks = sampler.stop()
     e2e_ms = 1e3 * t_e2e / e2e_steps
     h2d_ms, classify_ms = res2.c.ms_h2d, res2.c.ms_classify
@@ -540,8 +570,11 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "ms_h2d": h2d_ms,
                 "ms_classify": classify_ms, "seconds_to_verdict": e2e_ms / 1e3,
-                # the whole user-visible pipeline: native reader + abstraction on the host cores, then ecne_solve
-                "seconds_file_to_verdict": (PREP.get("read_and_abstraction") or 0.0) + e2e_ms / 1e3,
+                # the whole user-visible pipeline from the .r1cs files: with abstraction() on the device (file_to_verdict),
+                # and with the host library's abstraction followed by ecne_solve (…_host_abstraction)
+                "seconds_file_to_verdict": f2v["seconds"] if f2v else None,
+                "file_to_verdict": f2v,
+                "seconds_file_to_verdict_host_abstraction": (PREP.get("read_and_abstraction") or 0.0) + e2e_ms / 1e3,
                 "timing": "host clock around ecne_solve() (pinned host buffers in, host bitmaps out), max over ranks"},
         "gpu_launches": launches,
         "roofline": roofline,

@@ -463,6 +463,15 @@ struct ecne_abstracted {
   int device = 0;
   cudaStream_t stream = nullptr;
   double ms_h2d = 0;
+  // the upload of the unreduced system runs behind the caller's back until the handle is used for the first time:
+  // the host prepares the first trusted circuit (sorted coefficient lists, signature classes) meanwhile
+  std::thread uploader;
+  int upload_status = ECNE_OK;
+  std::string upload_err;
+  int wait_upload() {
+    if (uploader.joinable()) uploader.join();
+    return upload_status;
+  }
 };
 
 extern "C" int ecne_abstract_begin(const ecne_problem_t* main, ecne_abstracted_t** out) {
@@ -481,18 +490,18 @@ extern "C" int ecne_abstract_begin(const ecne_problem_t* main, ecne_abstracted_t
   a->known.assign(main->known, main->known + main->n_known);
   a->targets.assign(main->targets, main->targets + main->n_targets);
   a->sys.arena.pool = &c->pool;
-  std::string err;
-  auto t0 = std::chrono::steady_clock::now();
-  int st = dev_system_upload(main, &a->sys, c->stream, err);
-  if (st == ECNE_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {
-    st = ECNE_E_CUDA;
-    err = "upload of the unreduced system failed";
-  }
-  a->ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (st != ECNE_OK) {
-    ecne_abstract_free(a);
-    return fail(st, err);
-  }
+  // (the caller's arrays must stay alive until the first ecne_abstract_apply / _sizes / _export / _upload returns)
+  a->uploader = std::thread([a, main, c]() {
+    cudaSetDevice(c->device);
+    auto t0 = std::chrono::steady_clock::now();
+    int st = dev_system_upload(main, &a->sys, c->stream, a->upload_err);
+    if (st == ECNE_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      st = ECNE_E_CUDA;
+      a->upload_err = "upload of the unreduced system failed";
+    }
+    a->ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    a->upload_status = st;
+  });
   *out = a;
   return ECNE_OK;
 }
@@ -500,16 +509,20 @@ extern "C" int ecne_abstract_apply(ecne_abstracted_t* a, int32_t kind, const ecn
   if (!a || !sub) return fail(ECNE_E_BADARG, "null argument");
   CKA(cudaSetDevice(a->device));
   std::string err;
-  int st = dev_abstraction(&a->sys, kind, sub, &a->sp, n_matches, a->stream, err, &a->stats);
+  int st = dev_abstraction(&a->sys, kind, sub, &a->sp, n_matches, a->stream, err, &a->stats,
+                           [a]() { return a->wait_upload(); });
+  if (st != ECNE_OK && a->upload_status != ECNE_OK) return fail(a->upload_status, a->upload_err);
   if (st != ECNE_OK) return fail(st, err);
   if (getenv("ECNE_HOST_PROF"))
-    fprintf(stderr, "[ecne dev] abstraction: hashes %.3f ms | candidates %.3f ms (%llu) | verification %.3f ms (%llu matches) | "
-                    "compaction %.3f ms (cumulative over the calls of this handle)\n", a->stats.ms_hash, a->stats.ms_candidates,
+    fprintf(stderr, "[ecne dev] abstraction: trusted circuit prepared on the host %.3f ms | hashes %.3f ms | candidates %.3f ms (%llu) | "
+                    "verification %.3f ms (%llu matches) | compaction %.3f ms (cumulative over the calls of this handle)\n",
+            a->stats.ms_prepare, a->stats.ms_hash, a->stats.ms_candidates,
             (unsigned long long)a->stats.n_candidates, a->stats.ms_verify, (unsigned long long)a->stats.n_matches, a->stats.ms_compact);
   return ECNE_OK;
 }
 extern "C" int ecne_abstract_sizes(const ecne_abstracted_t* a, uint64_t sizes[5]) {
   if (!a || !sizes) return fail(ECNE_E_BADARG, "null argument");
+  if (const_cast<ecne_abstracted_t*>(a)->wait_upload() != ECNE_OK) return fail(a->upload_status, a->upload_err);
   sizes[0] = a->sys.N;
   sizes[1] = a->sys.nnz;
   sizes[2] = a->sp.kind.size();
@@ -520,6 +533,7 @@ extern "C" int ecne_abstract_sizes(const ecne_abstracted_t* a, uint64_t sizes[5]
 extern "C" int ecne_abstract_export(ecne_abstracted_t* a, uint64_t* seg_ptr, uint32_t* col, uint64_t* coef, int32_t* sp_kind,
                                     uint64_t* sp_in_ptr, uint32_t* sp_in, uint64_t* sp_out_ptr, uint32_t* sp_out) {
   if (!a) return fail(ECNE_E_BADARG, "null argument");
+  if (a->wait_upload() != ECNE_OK) return fail(a->upload_status, a->upload_err);
   CKA(cudaSetDevice(a->device));
   if (seg_ptr) CKA(cudaMemcpyAsync(seg_ptr, a->sys.seg, (3 * a->sys.N + 1) * 8, cudaMemcpyDeviceToHost, a->stream));
   if (col && a->sys.nnz) CKA(cudaMemcpyAsync(col, a->sys.col, a->sys.nnz * 4, cudaMemcpyDeviceToHost, a->stream));
@@ -535,6 +549,7 @@ extern "C" int ecne_abstract_export(ecne_abstracted_t* a, uint64_t* seg_ptr, uin
 }
 extern "C" int ecne_abstract_upload(ecne_abstracted_t* a, int32_t secp_solve, ecne_resident_t** out) {
   if (!a || !out) return fail(ECNE_E_BADARG, "null argument");
+  if (a->wait_upload() != ECNE_OK) return fail(a->upload_status, a->upload_err);
   ecne_problem_t p;
   memset(&p, 0, sizeof p);
   p.n_rows = a->sys.N;
@@ -557,6 +572,7 @@ extern "C" int ecne_abstract_upload(ecne_abstracted_t* a, int32_t secp_solve, ec
 }
 extern "C" void ecne_abstract_free(ecne_abstracted_t* a) {
   if (!a) return;
+  a->wait_upload();
   cudaSetDevice(a->device);
   if (a->stream) cudaStreamSynchronize(a->stream);
   if (a->sys.arena.pool) a->sys.arena.release();

@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine_host.h"
@@ -322,8 +323,11 @@ struct SubHost {  // everything about the trusted circuit that does not depend o
   std::vector<uint8_t> class_needed;
   unsigned long long seed = 0;
   uint32_t snz = 0;
-  // per class: the trusted circuit's wires with that signature, ascending
-  std::vector<std::vector<uint32_t>> members;
+  // every wire of the trusted circuit that appears: {wire, class of its signature, rank among the class's wires by id}
+  struct Where {
+    uint32_t wire, cls, rank;
+  };
+  std::vector<Where> where;  // sorted by wire
   // the trusted circuit's inputs (known, wire 1 left out, :376) and outputs (:382): class and rank inside it
   struct Need {
     uint32_t wire, cls, rank;  // cls == 0xffffffff: the wire never appears with a non-zero coefficient (KeyError)
@@ -409,7 +413,7 @@ bool prepare_sub(const ecne_problem_t* sub, SubHost& H) {
     H.class_slot.clear();
     H.class_coef.clear();
     H.class_size.clear();
-    H.members.clear();
+    H.where.clear();
     for (size_t i = 0; i < order.size() && !collision;) {
       size_t e = i + 1;
       while (e < order.size() && ws[order[e]].h == ws[order[i]].h) {
@@ -424,9 +428,8 @@ bool prepare_sub(const ecne_problem_t* sub, SubHost& H) {
       }
       H.class_off.push_back((uint32_t)H.class_slot.size());
       H.class_size.push_back((uint32_t)(e - i));
-      std::vector<uint32_t> mem;
-      for (size_t k = i; k < e; ++k) mem.push_back(ws[order[k]].wire);  // ascending (sort key)
-      H.members.push_back(std::move(mem));
+      for (size_t k = i; k < e; ++k)  // ascending wire ids (sort key): the rank is the position in the run
+        H.where.push_back(SubHost::Where{ws[order[k]].wire, (uint32_t)(H.class_hash.size() - 1), (uint32_t)(k - i)});
       i = e;
     }
     if (!collision) break;
@@ -434,16 +437,14 @@ bool prepare_sub(const ecne_problem_t* sub, SubHost& H) {
   }
   // (c) where the inputs / outputs sit
   H.class_needed.assign(H.class_hash.size(), 0);
+  std::sort(H.where.begin(), H.where.end(), [](const SubHost::Where& a, const SubHost::Where& b) { return a.wire < b.wire; });
   auto locate = [&](uint32_t x) {
     SubHost::Need nd{x, 0xffffffffu, 0};
-    for (size_t k = 0; k < H.members.size(); ++k) {
-      auto it = std::lower_bound(H.members[k].begin(), H.members[k].end(), x);
-      if (it != H.members[k].end() && *it == x) {
-        nd.cls = (uint32_t)k;
-        nd.rank = (uint32_t)(it - H.members[k].begin());
-        H.class_needed[k] = 1;
-        break;
-      }
+    auto it = std::lower_bound(H.where.begin(), H.where.end(), x, [](const SubHost::Where& a, uint32_t v) { return a.wire < v; });
+    if (it != H.where.end() && it->wire == x) {
+      nd.cls = it->cls;
+      nd.rank = it->rank;
+      H.class_needed[it->cls] = 1;
     }
     return nd;
   };
@@ -465,6 +466,79 @@ cudaError_t up(Arena& a, const std::vector<T>& v, const T** out, cudaStream_t s,
 }
 }  // namespace
 
+// Pageable host arrays reach the device at ~8 GB/s through cudaMemcpyAsync's own bounce buffer.  Large uploads are
+// staged instead: host threads copy slices into a ring of pinned buffers (kept for the life of the process) and every
+// slice is sent with its own asynchronous copy, so the memcpy of one slice overlaps the DMA of the slices before it —
+// 172 MB of ecdsa in ~5 ms instead of 21.
+namespace {
+struct StagingRing {
+  static constexpr int SLOTS = 8;
+  static constexpr size_t SLOT_BYTES = (size_t)4 << 20;
+  char* buf[SLOTS] = {nullptr};
+  cudaEvent_t done[SLOTS];
+  bool ok = false;
+  int device = -1;  // the events belong to a device
+  bool init() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (ok && dev == device) return true;
+    if (ok) {
+      for (int i = 0; i < SLOTS; ++i) {
+        cudaFreeHost(buf[i]);
+        cudaEventDestroy(done[i]);
+      }
+      ok = false;
+    }
+    device = dev;
+    for (int i = 0; i < SLOTS; ++i) {
+      if (cudaMallocHost((void**)&buf[i], SLOT_BYTES) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    }
+    ok = true;
+    return true;
+  }
+};
+StagingRing g_ring;
+
+cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  cudaPointerAttributes at;
+  const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();  // (an unregistered host pointer is reported as an error by older runtimes)
+  if (pinned || bytes < ((size_t)16 << 20) || !g_ring.init())
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+  const size_t SB = StagingRing::SLOT_BYTES;
+  const size_t n_slices = (bytes + SB - 1) / SB;
+  // Worker t takes slices t, t + T, ...: waits until the copy that last read the slot has completed, fills the slot and
+  // sends it itself (the slices are independent, so the order in which the workers reach the stream does not matter).
+  const int T = StagingRing::SLOTS;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::vector<cudaError_t> errs(T, cudaSuccess);
+  std::vector<std::thread> th;
+  for (int t = 0; t < T && (size_t)t < n_slices; ++t)
+    th.emplace_back([&, t]() {
+      cudaSetDevice(dev);
+      for (size_t j = t; j < n_slices; j += T) {
+        cudaError_t e = cudaEventSynchronize(g_ring.done[t]);  // (also a copy of an EARLIER call may still read the slot)
+        const size_t off = j * SB, len = std::min(SB, bytes - off);
+        if (e == cudaSuccess) {
+          memcpy(g_ring.buf[t], (const char*)src + off, len);
+          e = cudaMemcpyAsync((char*)dst + off, g_ring.buf[t], len, cudaMemcpyHostToDevice, s);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(g_ring.done[t], s);
+        if (e != cudaSuccess) {
+          errs[t] = e;
+          return;
+        }
+      }
+    });
+  for (auto& x : th) x.join();
+  for (cudaError_t e : errs)
+    if (e != cudaSuccess) return e;
+  return cudaSuccess;
+}
+}  // namespace
+
 int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std::string& err) {
   if (!p || !p->seg_ptr || (p->n_rows && (!p->col || !p->coef))) {
     err = "null problem arrays";
@@ -477,10 +551,10 @@ int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std
   CKE(S->arena.alloc(&S->seg, 3 * N + 2));
   CKE(S->arena.alloc(&S->col, nnz + 1));
   CKE(S->arena.alloc(&S->coef, nnz + 1));
-  CKE(cudaMemcpyAsync(S->seg, p->seg_ptr, (3 * N + 1) * 8, cudaMemcpyHostToDevice, s));
+  CKE(staged_h2d(S->seg, p->seg_ptr, (3 * N + 1) * 8, s));
   if (nnz) {
-    CKE(cudaMemcpyAsync(S->col, p->col, nnz * 4, cudaMemcpyHostToDevice, s));
-    CKE(cudaMemcpyAsync(S->coef, p->coef, nnz * 32, cudaMemcpyHostToDevice, s));
+    CKE(staged_h2d(S->col, p->col, nnz * 4, s));
+    CKE(staged_h2d(S->coef, p->coef, nnz * 32, s));
   }
   return ECNE_OK;
 }
@@ -488,7 +562,7 @@ int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std
 // One abstraction() call on a device-resident system: `S` is replaced by the reduced system, the special
 // constraints of the consumed windows are appended to `sp`.
 int dev_abstraction(DevSystem* S, int32_t kind, const ecne_problem_t* sub, SpecialsHost* sp, uint64_t* n_matches,
-                    cudaStream_t s, std::string& err, AbstractionStats* stats) {
+                    cudaStream_t s, std::string& err, AbstractionStats* stats, const std::function<int()>& ready) {
   if (!sub || !sub->seg_ptr || sub->n_rows == 0) {
     err = "trusted circuit without rows";
     return ECNE_E_BADARG;
@@ -500,12 +574,22 @@ int dev_abstraction(DevSystem* S, int32_t kind, const ecne_problem_t* sub, Speci
     if (acc) *acc += std::chrono::duration<double, std::milli>(t - tp0).count();
     tp0 = t;
   };
-  const uint64_t N = S->N, n = sub->n_rows;
+  const uint64_t n = sub->n_rows;
   SubHost H;
   if (!prepare_sub(sub, H)) {
     err = "internal: signature hash of the trusted circuit collides under every seed";
     return ECNE_E_INTERNAL;
   }
+  if (stats) stats->ms_prepare += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
+  if (ready) {  // the big system is on the device from here on
+    const int rst = ready();
+    if (rst != ECNE_OK) {
+      err = "upload of the unreduced system failed";
+      return rst;
+    }
+  }
+  tp0 = std::chrono::steady_clock::now();
+  const uint64_t N = S->N;
   Arena tmp;
   struct Guard {
     Arena& a;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -135,7 +136,7 @@ struct SpecialsHost {  // the special constraints found so far (:357-384), CSR o
   std::vector<uint32_t> in, out;
 };
 struct AbstractionStats {
-  double ms_hash = 0, ms_candidates = 0, ms_verify = 0, ms_compact = 0;
+  double ms_prepare = 0, ms_hash = 0, ms_candidates = 0, ms_verify = 0, ms_compact = 0;
   uint64_t n_candidates = 0, n_matches = 0;
 };
 #ifndef ECNE_E_KEYERROR
@@ -143,8 +144,10 @@ struct AbstractionStats {
 #endif
 // abstraction.cu
 int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std::string& err);
+// `ready`: called after the trusted circuit has been prepared on the host and before the first kernel touches `S`
+// (the upload of the big system may still be running until then); returns an ecne_status.
 int dev_abstraction(DevSystem* S, int32_t kind, const ecne_problem_t* sub, SpecialsHost* sp, uint64_t* n_matches,
-                    cudaStream_t s, std::string& err, AbstractionStats* stats);
+                    cudaStream_t s, std::string& err, AbstractionStats* stats, const std::function<int()>& ready);
 
 // setup.cu: H2D + classification + layout.  Returns an ecne_status.  With `dev` the rows are taken from a system that
 // is already resident on the device (p->seg_ptr / col / coef are not read; sizes come from `dev`).
