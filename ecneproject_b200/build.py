@@ -73,18 +73,43 @@ def nvcc_path():
     return None
 
 
-def build_engine(force=False, verbose=False):
+# libecne_b200.so carries the solve kernel twice: kernels.cu as it stands (512 threads x 128 registers per block) and a
+# second build for bandwidth-bound problems (1024 x 64) in its own namespace (csrc/kernels.cu, "the second build")
+SOLVE_VARIANT_1024 = ["-DP1_THREADS=1024", "-DP1_MAX_KS=6", "-DP1_INFLIGHT=2", "-Decne=ecne_v1024",
+                      "-DECNE_VARIANT_SUFFIX=v1024"]
+
+
+def build_engine(force=False, verbose=False, extra_flags=(), out=None, objdir_name="_obj"):
+    """extra_flags / out: side builds (tools/build_prof.sh: -DECNE_PROFILE into libecne_b200_prof.so)."""
+    out_so = out or ENGINE_SO
     src = _sources(CSRC, (".cu",))
     deps = src + _sources(CSRC, (".cuh", ".h")) + _sources(INC, (".h",))
-    if force or _newer(ENGINE_SO, deps):
+    if force or _newer(out_so, deps):
         nvcc = nvcc_path()
         if nvcc is None:
             raise RuntimeError("nvcc not found: libecne_b200.so cannot be built (no CPU fallback exists)")
-        cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-shared", "--cudart", "shared", "-Xcompiler", "-fPIC",
-               "-Xptxas", "-v", "-I", INC, "-I", CSRC] + NVCC_ARCH
-        cmd += ["-o", ENGINE_SO] + src + ["-ldl"]
-        _run(cmd, verbose)
-    return ENGINE_SO
+        objdir = os.path.join(PKG, objdir_name)
+        os.makedirs(objdir, exist_ok=True)
+        base = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INC, "-I", CSRC] + NVCC_ARCH + \
+            list(extra_flags)
+        jobs = [(f, os.path.join(objdir, os.path.basename(f)[:-3] + ".o"), []) for f in src]
+        jobs.append((os.path.join(CSRC, "kernels.cu"), os.path.join(objdir, "kernels_v1024.o"), SOLVE_VARIANT_1024))
+        procs = []
+        for f, o, extra in jobs:   # the translation units compile side by side
+            cmd = base + extra + ["-c", f, "-o", o]
+            if verbose:
+                print("+", " ".join(cmd), flush=True)
+            procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        for cmd, p in procs:
+            out, _ = p.communicate()
+            if p.returncode != 0:
+                sys.stderr.write(out)
+                raise RuntimeError("build failed: " + " ".join(cmd))
+            if verbose and out:
+                print(out)
+        _run([nvcc, "-shared", "--cudart", "shared", "-Xcompiler", "-fPIC"] + NVCC_ARCH + ["-o", out_so] +
+             [o for _, o, _ in jobs] + ["-ldl"], verbose)
+    return out_so
 
 
 def build_all(force=False, verbose=False):
@@ -92,4 +117,9 @@ def build_all(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build_all(force="--force" in sys.argv, verbose=True)
+    if "--side" in sys.argv:   # python -m ecneproject_b200.build --side <out.so> [nvcc flags...]
+        i = sys.argv.index("--side")
+        build_engine(force=True, verbose=False, extra_flags=sys.argv[i + 2:], out=os.path.abspath(sys.argv[i + 1]),
+                     objdir_name="_obj_side")
+    else:
+        build_all(force="--force" in sys.argv, verbose=True)

@@ -17,6 +17,10 @@
 
 using namespace ecne;
 
+// the second build of the solve kernel (1024 threads x 64 registers per block; csrc/kernels.cu "the second build")
+extern "C" cudaError_t ecne_launch_solve_v1024(const void* dev, unsigned int max_rounds, int grid, cudaStream_t s);
+extern "C" int ecne_p1_grid_size_v1024(int device);
+
 namespace {
 
 // One device this process drives: its streams, its slab pool, its pinned staging and its exchange buffer.
@@ -46,6 +50,10 @@ struct Global {
   // problem is solved by every rank on all rows without any exchange (a sharded round costs a cross-GPU barrier,
   // ~15-25 us, which a sweep of a few 10^5 rows does not earn back: ecdsa's 694 k rows sweep in ~20 us)
   long long shard_min_rows = 2000000;
+  // which build of the solve kernel: 0 = by size (a GPU that sweeps at least `wide_min_rows` rows takes the 1024-thread
+  // build), 1 = 512 threads x 128 registers, 2 = 1024 x 64
+  long long solve_variant = 0;
+  long long wide_min_rows = 1500000;
   // one process per GPU: rank / world of this process and the communicator that bootstraps the peer mappings
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
@@ -304,6 +312,10 @@ extern "C" int ecne_set_option(const char* key, int64_t value) {
     G.sparse_max = value;
   else if (k == "grid_blocks")
     G.grid_blocks = value;
+  else if (k == "solve_variant")
+    G.solve_variant = value < 0 || value > 2 ? 0 : value;
+  else if (k == "wide_min_rows")
+    G.wide_min_rows = value < 0 ? 0 : value;
   else if (k == "shard_min_rows")
     G.shard_min_rows = value < 0 ? 0 : value;
   else if (k == "p2_hash_bits")
@@ -633,7 +645,9 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
     Resident& Ri = h->rs[i];
     Dev& di = Ri.d;
     CKA(cudaSetDevice(Ri.device));
-    int grid = p1_grid_size(Ri.device);
+    const bool wide = G.solve_variant == 2 ||
+                      (G.solve_variant == 0 && (long long)(di.row_hi - di.row_lo) >= G.wide_min_rows);
+    int grid = wide ? ecne_p1_grid_size_v1024(Ri.device) : p1_grid_size(Ri.device);
     if (G.grid_blocks > 0 && G.grid_blocks < grid) grid = (int)G.grid_blocks;
     CKA(launch_reset(di, grid, Ri.stream));
     if (Ri.table_dirty) {
@@ -648,7 +662,8 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
       di.sparse_max = (uint32_t)std::min<long long>(sm, 0x7fffffffLL);
     }
     cudaEventRecord(s0[i], Ri.stream);
-    CKA(launch_solve(di, (unsigned int)std::min<long long>(G.max_rounds, 0x7fffffffLL), grid, Ri.stream));
+    const unsigned int mr = (unsigned int)std::min<long long>(G.max_rounds, 0x7fffffffLL);
+    CKA(wide ? ecne_launch_solve_v1024(&di, mr, grid, Ri.stream) : launch_solve(di, mr, grid, Ri.stream));
     cudaEventRecord(s1[i], Ri.stream);
     CKA(cudaMemcpyAsync(Ri.h_status, di.st, sizeof(Status), cudaMemcpyDeviceToHost, Ri.stream));
   }

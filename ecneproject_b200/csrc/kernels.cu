@@ -1959,3 +1959,19 @@ void launch_report_export(const Dev& d, int buf, const uint32_t* wires, uint32_t
 }
 
 }  // namespace ecne
+
+// ---- the second build of this file -----------------------------------------------------------------------------------
+// The library carries the solve kernel twice (ecneproject_b200/build.py): 512 threads x 128 registers per block — the
+// latency-bound dependency chains of small problems run spill-free — and 1024 x 64, whose 32 warps per SM hide more of a
+// bandwidth-bound sweep (S16: dense rounds 1.5x faster).  The second copy is this same file compiled with
+// -Decne=ecne_v1024 (its own namespace, its own __constant__ descriptor) and reaches abi.cu through these two C symbols.
+#ifdef ECNE_VARIANT_SUFFIX
+#define ECNE_CAT2(a, b) a##b
+#define ECNE_CAT(a, b) ECNE_CAT2(a, b)
+extern "C" cudaError_t ECNE_CAT(ecne_launch_solve_, ECNE_VARIANT_SUFFIX)(const void* dev, unsigned int max_rounds, int grid,
+                                                                         cudaStream_t s) {
+  return ecne::launch_solve(*reinterpret_cast<const ecne::Dev*>(dev), max_rounds, grid, s);
+}
+extern "C" int ECNE_CAT(ecne_p1_grid_size_, ECNE_VARIANT_SUFFIX)(int device) { return ecne::p1_grid_size(device); }
+extern "C" int ECNE_CAT(ecne_p1_threads_, ECNE_VARIANT_SUFFIX)(void) { return ecne::p1_threads(); }
+#endif

@@ -214,6 +214,8 @@ int ecne_shard_rows(const ecne_problem_t* problem, int rank, int world, uint64_t
  * "shard_min_rows": on several GPUs, problems with at least this many rows have their dense sweeps split over the
  * GPUs, smaller ones are solved by every GPU in full without any exchange (2 000 000; 0: always shard — must be the
  * same on every rank);
+ * "solve_variant": which build of the solve kernel runs (0: by size — a GPU that sweeps at least "wide_min_rows" = 1 500 000 rows
+ * takes the 1024-thread x 64-register build, smaller problems the 512 x 128 one; 1 / 2 force them);
  * "p2_hash_bits": bits of the unknown-set hash the linear-system sweep groups by (56; fewer force collisions,
  * which the engine resolves by exact comparison — results do not depend on it). */
 int ecne_set_option(const char* key, int64_t value);

@@ -314,12 +314,27 @@ def test_repeated_solves_are_bit_stable(name):
 @pytest.mark.parametrize("name", ["secp256k1+bmmp+blt", "tornado/withdraw+pedersen", "root/bigmult86_3",
                                   "circomlib/EdDSAPoseidonVerifier@eddsaposeidon"])
 def test_engine_knobs_do_not_change_the_result(name, blocks, sparse_max):
+    _knob_run(name, blocks, sparse_max, 0)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("name", ["secp256k1+bmmp+blt", "tornado/withdraw+pedersen", "root/bigmult86_3", "root/poseidon",
+                                  "circomlib/EdDSAPoseidonVerifier@eddsaposeidon", "tornado/merkleTree"])
+def test_both_builds_of_the_solve_kernel(name, variant):
+    """The library carries the solve kernel twice (512 threads x 128 registers, 1024 x 64; picked by problem size):
+    both must give the goldens, at the full grid and squeezed into three blocks."""
+    _knob_run(name, 0, -1, variant)
+    _knob_run(name, 3, -1, variant)
+
+
+def _knob_run(name, blocks, sparse_max, variant):
     """The same circuits with the solve kernel squeezed into 1-3 blocks (so that a thread owns more rows than
     its 64-bit live mask tracks and more than shared memory holds: the paths a >10 M-row problem takes), and
     with every round forced dense (sparse_max = 0) or frontier-driven (sparse_max = huge)."""
     lib = api._engine()
     assert lib.ecne_set_option(b"grid_blocks", blocks) == 0
     assert lib.ecne_set_option(b"sparse_max", sparse_max) == 0
+    assert lib.ecne_set_option(b"solve_variant", variant) == 0
     try:
         (reduced, specials, main), secp = prepare(name)
         st, res = gpu_solve(reduced, specials, main, secp)
@@ -328,6 +343,7 @@ def test_engine_knobs_do_not_change_the_result(name, blocks, sparse_max):
     finally:
         lib.ecne_set_option(b"grid_blocks", 0)
         lib.ecne_set_option(b"sparse_max", -1)
+        lib.ecne_set_option(b"solve_variant", 0)
 
 
 @pytest.mark.parametrize("name", ["root/bigmult86_3", "root/bigmultmodp", "root/bigmultshortlong86_3", "root/poseidon"])

@@ -23,6 +23,8 @@ from ecneproject_b200 import _abi
 lib = _abi.engine_lib()
 # the fixtures are far below "shard_min_rows": force the sharded path, which is what this tool checks
 assert lib.ecne_set_option(b"shard_min_rows", 0) == 0
+if os.environ.get("ECNE_GRID_BLOCKS"):  # sanitizer runs squeeze the solve kernels into a few blocks
+    assert lib.ecne_set_option(b"grid_blocks", int(os.environ["ECNE_GRID_BLOCKS"])) == 0
 
 
 def solve(n, ph, n_vars):
