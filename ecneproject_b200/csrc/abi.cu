@@ -285,6 +285,10 @@ extern "C" int ecne_init_multi(int n_gpus) {
         close_all();
         return fail(ECNE_E_CUDA, "GPUs " + std::to_string(i) + " and " + std::to_string(j) + " have no peer access");
       }
+      // (a process may call ecne_init_multi again after ecne_shutdown: the mapping of a pair is enabled once for the
+      // life of the process, and asking again would only leave an API error for the tools to report)
+      static bool peer_on[ECNE_MAX_WORLD][ECNE_MAX_WORLD];
+      if (peer_on[i][j]) continue;
       cudaSetDevice(i);
       cudaError_t pe = cudaDeviceEnablePeerAccess(j, 0);
       if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
@@ -292,6 +296,7 @@ extern "C" int ecne_init_multi(int n_gpus) {
         return fail(ECNE_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
       }
       cudaGetLastError();
+      peer_on[i][j] = true;
     }
   cudaSetDevice(0);
   G.multi = n_gpus > 1;
@@ -730,16 +735,20 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
                   d.world > 1 ? " + exchange" : "", q[0], q[1], q[2], q[3]);
       }
       for (int r = 0; r < 12; ++r) {
-        unsigned long long mx[3] = {0, 0, 0}, sum[3] = {0, 0, 0}, g = 0;
-        for (int b = 0; b < 148; ++b)
+        unsigned long long mx[3] = {0, 0, 0}, sum[3] = {0, 0, 0}, g = 0, inl = 0;
+        for (int b = 0; b < 148; ++b) {
           for (int k = 0; k < 3; ++k) {
             unsigned long long v = pr[28000 + ((size_t)r * 148 + b) * 4 + k];
             mx[k] = v > mx[k] ? v : mx[k];
             sum[k] += v;
-            g = pr[28000 + ((size_t)r * 148 + b) * 4 + 3];
           }
-        if (g) fprintf(stderr, "[dense] round %llu: long rows mean %llu max %llu | replay mean %llu max %llu | sweep mean %llu max %llu\n", g,
-                       sum[0] / 148, mx[0], sum[1] / 148, mx[1], sum[2] / 148, mx[2]);
+          g = pr[28000 + ((size_t)r * 148 + b) * 4 + 3] & 0xfffffULL;
+          inl += pr[28000 + ((size_t)r * 148 + b) * 4 + 3] >> 20;
+        }
+        if (g) fprintf(stderr, "[dense] round %llu: long rows mean %llu max %llu | replay mean %llu max %llu | sweep mean %llu max %llu "
+                       "(inline loop of warp 0: mean %llu; rows sent to the generic evaluator: %llu)\n", g,
+                       sum[0] / 148, mx[0], sum[1] / 148, mx[1], sum[2] / 148, mx[2], inl / 148,
+                       pr[28000 + 40 * 148 * 4 + 8 + r]);
       }
     }
     if (atoi(getenv("ECNE_DEBUG_PROF")) > 1) {

@@ -955,6 +955,7 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
     bool leave;
     if (fast) {
       const unsigned int flags = s_solo_flags, nq = s_soloq_n[qw];
+      __syncwarp();  // every lane has read the round's flags before lane 0 clears them for the next round (racecheck)
       const bool spilled = (flags & 4u) != 0;
       if (lane == 0 && !from_smem) {  // the list the stretch started from is consumed
         d.rec_count[prev_list] = 0;
@@ -1334,6 +1335,11 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
                 if (e & EI_GENERIC) slow.set(kk[h]);
               }
           }
+#ifdef ECNE_PROFILE
+          long long dzf = clock64();
+          if (dense_rounds < 40 && slow.any())
+            atomicAdd(d.prof + 28000 + 40 * 148 * 4 + 8 + dense_rounds, (unsigned long long)slow.count());
+#endif
           // the rows that need the generic evaluator (bit-decomposition patterns, x + y = 1, Case 5/6
           // candidates), all lanes together: inside the loop above one such lane would stall its warp in
           // almost every iteration
@@ -1386,7 +1392,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
             q[0] = (unsigned long long)(dz3 - dz4);  // long rows
             q[1] = (unsigned long long)(dz2 - dz1);  // replay
             q[2] = (unsigned long long)(dz4 - dz2);  // sweep
-            q[3] = gr;
+            q[3] = gr | ((unsigned long long)(dzf - dz2) << 20);  // ... of which the inline loop
           }
 #endif
         } else {
