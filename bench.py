@@ -290,8 +290,27 @@ def main():
     pr.coef = pr._keep[2].numpy().view(np.uint64).reshape(-1, 4)
     ph = api.ProblemHandle(pr, specials, main.known, main.targets, main.n_vars, False)
     # ProblemHandle copies non-contiguous inputs only; make sure the pinned buffers are what it points at
-    assert ph.keep[0].ctypes.data == pr.seg_ptr.ctypes.data
-    h2d_bytes = pr.seg_ptr.nbytes + pr.col.nbytes + pr.coef.nbytes + 4 * (len(main.known) + len(main.targets))
+    assert ph.keep[0].ctypes.data == pr.col.ctypes.data
+    h2d_bytes_full = pr.seg_ptr.nbytes + pr.col.nbytes + pr.coef.nbytes + 4 * (len(main.known) + len(main.targets))
+    # The e2e leg hands the rows over in the COMPACT form of include/ecne_abi.h (ABI 3): 32-bit offsets, one class byte
+    # per term (0, 1, p - 1, other) and 32-byte limbs only for the other values — what a host that flattens
+    # Dict{Int, GFElem} can emit as cheaply as the full form.  Pinned like the full form; the full form is timed too.
+    t0c = time.perf_counter()
+    cls_, other_, term_ = api.compact_coef(reduced.coef)
+    compact_prep_s = time.perf_counter() - t0c
+    pc = PinnedR1CS()
+    pc._keep = [pinned(np.asarray(reduced.seg_ptr).astype(np.uint32).view(np.int32)), pinned(cls_),
+                pinned(other_.reshape(-1).view(np.int64)), pinned(term_.view(np.int32))]
+    ph_c = api.ProblemHandle(pr, specials, main.known, main.targets, main.n_vars, False)
+    ph_c.c.seg_ptr = None
+    ph_c.c.coef = None
+    ph_c.c.seg_ptr32 = C.cast(pc._keep[0].data_ptr(), _abi.u32p)
+    ph_c.c.coef_class = C.cast(pc._keep[1].data_ptr(), _abi.u8p)
+    ph_c.c.coef_other = C.cast(pc._keep[2].data_ptr(), _abi.u64p)
+    ph_c.c.coef_other_term = C.cast(pc._keep[3].data_ptr(), _abi.u32p)
+    ph_c.c.n_coef_other = len(term_)
+    h2d_bytes = (4 * (3 * reduced.n_rows + 1) + pr.col.nbytes + cls_.nbytes + other_.nbytes + term_.nbytes +
+                 4 * (len(main.known) + len(main.targets)))
     res = api.SolveResult(main.n_vars, full_state=False)
     d2h_bytes = 2 * res.unique_bits.nbytes + 4 * 8
 
@@ -391,21 +410,28 @@ def main():
 
     # ---- e2e leg: host buffers in, host buffers out -------------------------------------------------
     res2 = api.SolveResult(main.n_vars, full_state=False)
-    for _ in range(2):
-        barrier()
-        lib.ecne_solve(C.byref(ph.c), C.byref(res2.c))
-    t_e2e = 0.0
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        l2_flush()
+
+    def e2e_leg(handle_c):
+        for _ in range(2):
+            barrier()
+            lib.ecne_solve(C.byref(handle_c), C.byref(res2.c))
+        tt_ = 0.0
+        for _ in range(e2e_steps):
+            l2_flush()
+            barrier()
+            t0 = time.perf_counter()
+            st = lib.ecne_solve(C.byref(handle_c), C.byref(res2.c))
+            torch.cuda.synchronize()
+            tt_ += time.perf_counter() - t0
+            if st != 0:
+                raise RuntimeError(lib.ecne_last_error().decode())
         barrier()
-        t0 = time.perf_counter()
-        st = lib.ecne_solve(C.byref(ph.c), C.byref(res2.c))
-        torch.cuda.synchronize()
-        t_e2e += time.perf_counter() - t0
-        if st != 0:
-            raise RuntimeError(lib.ecne_last_error().decode())
-    barrier()
+        assert res2.unique_bits.tobytes() == res.unique_bits.tobytes()
+        return tt_, res2.c.ms_h2d, res2.c.ms_classify
+
+    t_e2e_full, h2d_ms_full, classify_ms_full = e2e_leg(ph.c)     # full 32-byte coefficients, 64-bit offsets
+    t_e2e, h2d_ms, classify_ms = e2e_leg(ph_c.c)                  # compact form: the e2e number of the line
     # ---- file -> verdict with abstraction() on the device (N = 1): parse on the host cores, upload the UNREDUCED
     # system once, abstract + classify where it lies, solve (include/ecne_abi.h "abstraction() on the device")
     f2v = None
@@ -438,17 +464,16 @@ def main():
                       "GPU, the reduced system never crosses PCIe), ecne_solve_resident; bitmap equal to the resident leg's"}
     clocks = sampler.stop()
     e2e_ms = 1e3 * t_e2e / e2e_steps
-    h2d_ms, classify_ms = res2.c.ms_h2d, res2.c.ms_classify
-    assert res2.unique_bits.tobytes() == res.unique_bits.tobytes()
+    e2e_ms_full = 1e3 * t_e2e_full / e2e_steps
     lib.ecne_free_resident(handle)
 
     ms_step = t_dev / args.steps
     ms_wall = 1e3 * t_wall / args.steps
     total_evals = evals
     if dist is not None:   # max over ranks of the times, sum over ranks of the rows each rank visited
-        t = torch.tensor([ms_step, e2e_ms, ms_wall], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_step, e2e_ms, ms_wall, e2e_ms_full], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_ms, ms_wall = float(t[0]), float(t[1]), float(t[2])
+        ms_step, e2e_ms, ms_wall, e2e_ms_full = float(t[0]), float(t[1]), float(t[2]), float(t[3])
         e = torch.tensor([evals], device="cuda", dtype=torch.int64)
         dist.all_reduce(e, op=dist.ReduceOp.SUM)
         total_evals = int(e[0])
@@ -570,6 +595,13 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "ms_h2d": h2d_ms,
                 "ms_classify": classify_ms, "seconds_to_verdict": e2e_ms / 1e3,
+                "input_form": "compact (include/ecne_abi.h, ABI 3): 32-bit offsets, wire ids, one class byte per stored term "
+                              "{0, 1, p-1, other} + 32-byte limbs of the other values; expanded on the device into the same "
+                              "arrays the full form is copied into",
+                "compact_prep_seconds_untimed": compact_prep_s,
+                # the same call with the full form (64-bit offsets, 32-byte limbs for every stored term)
+                "full_form": {"ms_per_step": e2e_ms_full, "value": total_evals / (e2e_ms_full / 1e3),
+                              "h2d_bytes_per_step": h2d_bytes_full, "ms_h2d": h2d_ms_full, "ms_classify": classify_ms_full},
                 # the whole user-visible pipeline from the .r1cs files: with abstraction() on the device (file_to_verdict),
                 # and with the host library's abstraction followed by ecne_solve (…_host_abstraction)
                 "seconds_file_to_verdict": f2v["seconds"] if f2v else None,

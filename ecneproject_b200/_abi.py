@@ -35,6 +35,9 @@ class Problem(C.Structure):
         ("n_specials", C.c_uint64), ("sp_kind", i32p),
         ("sp_in_ptr", u64p), ("sp_in", u32p), ("sp_out_ptr", u64p), ("sp_out", u32p),
         ("secp_solve", C.c_int32), ("debug", C.c_int32),
+        # compact form of the coefficients (coef == NULL selects it) and 32-bit offsets (seg_ptr == NULL)
+        ("coef_class", u8p), ("coef_other", u64p), ("coef_other_term", u32p), ("n_coef_other", C.c_uint64),
+        ("seg_ptr32", u32p),
     ]
 
 
@@ -94,7 +97,7 @@ ENGINE_SYMBOLS = [
 ]
 HOST_SYMBOLS = [
     "ecne_read_r1cs", "ecne_read_r1cs_mem", "ecne_r1cs_free", "ecne_specials_new",
-    "ecne_specials_free", "ecne_abstraction", "ecne_host_last_error",
+    "ecne_specials_free", "ecne_abstraction", "ecne_host_last_error", "ecne_compact_coef",
 ]
 
 _host = None
@@ -125,13 +128,15 @@ def host_lib():
         lib.ecne_specials_free.restype = None
         lib.ecne_abstraction.argtypes = [C.c_int32, R1p, R1p, C.POINTER(R1p), Sp, u64p]
         lib.ecne_abstraction.restype = C.c_int
+        lib.ecne_compact_coef.argtypes = [u64p, C.c_uint64, u8p, u64p, u32p, u64p]
+        lib.ecne_compact_coef.restype = C.c_int
         lib.ecne_host_last_error.argtypes = []
         lib.ecne_host_last_error.restype = C.c_char_p
         _host = lib
     return _host
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 def layout_table():

@@ -154,18 +154,52 @@ class SolveResult:
             "ms_solve", "ms_d2h", "ms_exchange", "ms_total", "ms_sweep", "rule_evals")}
 
 
+def compact_coef(coef):
+    """(class bytes, other values [n, 4], their term indices) of a [nnz, 4] limb array: ecne_compact_coef of the host
+    library (include/ecne_host.h), the compact coefficient form of ecne_problem_t."""
+    lib = _abi.host_lib()
+    coef = np.ascontiguousarray(np.asarray(coef, dtype=np.uint64).reshape(-1, 4))
+    nnz = coef.shape[0]
+    cls = np.zeros(max(nnz, 1), dtype=np.uint8)
+    n = C.c_uint64(0)
+    cp = coef.ctypes.data_as(_abi.u64p) if nnz else None
+    st = lib.ecne_compact_coef(cp, nnz, cls.ctypes.data_as(_abi.u8p), None, None, C.byref(n))
+    if st != 0:
+        _raise(st, lib.ecne_host_last_error().decode())
+    other = np.zeros((max(int(n.value), 1), 4), dtype=np.uint64)
+    term = np.zeros(max(int(n.value), 1), dtype=np.uint32)
+    st = lib.ecne_compact_coef(cp, nnz, cls.ctypes.data_as(_abi.u8p), other.ctypes.data_as(_abi.u64p),
+                               term.ctypes.data_as(_abi.u32p), C.byref(n))
+    if st != 0:
+        _raise(st, lib.ecne_host_last_error().decode())
+    return cls[:nnz], other[:int(n.value)], term[:int(n.value)]
+
+
 class ProblemHandle:
     """Keeps the numpy buffers an ecne_problem_t points into alive."""
 
     def __init__(self, constraints, specials, known_variables, target_variables, num_variables,
-                 secp_solve=False, debug=False):
+                 secp_solve=False, debug=False, compact=False):
+        """compact: hand the coefficients over in the compact form of include/ecne_abi.h (class bytes + the values
+        that are not 0, 1, p - 1) with 32-bit offsets — a third of the bytes of the full form cross PCIe."""
         self.keep = []
         p = Problem()
         p.n_rows = constraints.n_rows
         p.n_vars = num_variables
-        p.seg_ptr = self._buf(constraints.seg_ptr, np.uint64, _abi.u64p)
         p.col = self._buf(constraints.col, np.uint32, _abi.u32p)
-        p.coef = self._buf(constraints.coef.reshape(-1), np.uint64, _abi.u64p)
+        if compact:
+            cls, other, term = compact_coef(constraints.coef)
+            p.seg_ptr = None
+            p.seg_ptr32 = self._buf(np.asarray(constraints.seg_ptr).astype(np.uint32), np.uint32, _abi.u32p)
+            p.coef = None
+            p.coef_class = self._buf(cls, np.uint8, _abi.u8p)
+            p.coef_other = self._buf(other.reshape(-1), np.uint64, _abi.u64p)
+            p.coef_other_term = self._buf(term, np.uint32, _abi.u32p)
+            p.n_coef_other = len(term)
+        else:
+            p.seg_ptr = self._buf(constraints.seg_ptr, np.uint64, _abi.u64p)
+            p.coef = self._buf(constraints.coef.reshape(-1), np.uint64, _abi.u64p)
+        self.compact = bool(compact)
         kn = np.asarray(known_variables, dtype=np.uint32)
         tg = np.asarray(target_variables, dtype=np.uint32)
         p.known = self._buf(kn, np.uint32, _abi.u32p)

@@ -155,13 +155,15 @@ extern "C" int ecne_abi_layout(uint32_t* out, uint32_t cap) {
   std::vector<uint32_t> t;
 #define ECNE_F(T, f) t.push_back((uint32_t)offsetof(T, f));
 #define ECNE_S(T, n) t.push_back((uint32_t)sizeof(T)); t.push_back(n);
-  ECNE_S(ecne_problem_t, 17)
+  ECNE_S(ecne_problem_t, 22)
   ECNE_F(ecne_problem_t, n_rows) ECNE_F(ecne_problem_t, n_vars) ECNE_F(ecne_problem_t, seg_ptr)
   ECNE_F(ecne_problem_t, col) ECNE_F(ecne_problem_t, coef) ECNE_F(ecne_problem_t, known)
   ECNE_F(ecne_problem_t, n_known) ECNE_F(ecne_problem_t, targets) ECNE_F(ecne_problem_t, n_targets)
   ECNE_F(ecne_problem_t, n_specials) ECNE_F(ecne_problem_t, sp_kind) ECNE_F(ecne_problem_t, sp_in_ptr)
   ECNE_F(ecne_problem_t, sp_in) ECNE_F(ecne_problem_t, sp_out_ptr) ECNE_F(ecne_problem_t, sp_out)
-  ECNE_F(ecne_problem_t, secp_solve) ECNE_F(ecne_problem_t, debug)
+  ECNE_F(ecne_problem_t, secp_solve) ECNE_F(ecne_problem_t, debug) ECNE_F(ecne_problem_t, coef_class)
+  ECNE_F(ecne_problem_t, coef_other) ECNE_F(ecne_problem_t, coef_other_term) ECNE_F(ecne_problem_t, n_coef_other)
+  ECNE_F(ecne_problem_t, seg_ptr32)
   ECNE_S(ecne_result_t, 31)
   ECNE_F(ecne_result_t, verdict) ECNE_F(ecne_result_t, status) ECNE_F(ecne_result_t, unique_bits)
   ECNE_F(ecne_result_t, known_bits) ECNE_F(ecne_result_t, lb) ECNE_F(ecne_result_t, ub)

@@ -499,6 +499,7 @@ struct StagingRing {
   }
 };
 StagingRing g_ring;
+}  // namespace
 
 cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   cudaPointerAttributes at;
@@ -537,26 +538,25 @@ cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s)
     if (e != cudaSuccess) return e;
   return cudaSuccess;
 }
-}  // namespace
 
 int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std::string& err) {
-  if (!p || !p->seg_ptr || (p->n_rows && (!p->col || !p->coef))) {
-    err = "null problem arrays";
-    return ECNE_E_BADARG;
-  }
-  const uint64_t N = p->n_rows, nnz = p->seg_ptr[3 * N];
+  int st = problem_rows_ok(p, err);
+  if (st != ECNE_OK) return st;
+  const uint64_t N = p->n_rows, nnz = problem_nnz(p);
   S->N = N;
   S->V = p->n_vars;
   S->nnz = nnz;
   CKE(S->arena.alloc(&S->seg, 3 * N + 2));
   CKE(S->arena.alloc(&S->col, nnz + 1));
   CKE(S->arena.alloc(&S->coef, nnz + 1));
-  CKE(staged_h2d(S->seg, p->seg_ptr, (3 * N + 1) * 8, s));
-  if (nnz) {
-    CKE(staged_h2d(S->col, p->col, nnz * 4, s));
-    CKE(staged_h2d(S->coef, p->coef, nnz * 32, s));
+  Arena tmp;
+  tmp.pool = S->arena.pool;
+  st = upload_rows(p, S->seg, S->col, S->coef, tmp, s, err);
+  if (tmp.pool && !tmp.slabs.empty()) {
+    cudaStreamSynchronize(s);  // the expansion kernels read the scratch
+    tmp.release();
   }
-  return ECNE_OK;
+  return st;
 }
 
 // One abstraction() call on a device-resident system: `S` is replaced by the reduced system, the special
@@ -565,6 +565,10 @@ int dev_abstraction(DevSystem* S, int32_t kind, const ecne_problem_t* sub, Speci
                     cudaStream_t s, std::string& err, AbstractionStats* stats, const std::function<int()>& ready) {
   if (!sub || !sub->seg_ptr || sub->n_rows == 0) {
     err = "trusted circuit without rows";
+    return ECNE_E_BADARG;
+  }
+  if (!sub->col || !sub->coef) {  // (a few thousand rows, prepared on the host: the compact form would buy nothing)
+    err = "a trusted circuit is passed with its full 32-byte coefficients";
     return ECNE_E_BADARG;
   }
   auto tp0 = std::chrono::steady_clock::now();

@@ -142,7 +142,16 @@ struct AbstractionStats {
 #ifndef ECNE_E_KEYERROR
 #define ECNE_E_KEYERROR (-10)  // KeyError at R1CSConstraintSolver.jl:381-382 (same code as include/ecne_host.h)
 #endif
-// abstraction.cu
+// abstraction.cu: host -> device copy; pageable sources of 16 MB and more go through a ring of pinned slots filled by
+// worker threads, pinned ones (and small ones) straight into cudaMemcpyAsync
+cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s);
+// setup.cu: the rows of `p` (seg_ptr / col / coef in either form of include/ecne_abi.h: full 32-byte coefficients, or
+// class bytes + the values that are not 0, 1, p-1; 64- or 32-bit offsets) into device arrays of the on-disk layout.
+// `tmp` lends the scratch of the compact form.  Returns an ecne_status.
+uint64_t problem_nnz(const ecne_problem_t* p);
+int problem_rows_ok(const ecne_problem_t* p, std::string& err);
+int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_col, fr::u256* d_coef, Arena& tmp,
+                cudaStream_t s, std::string& err);
 int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std::string& err);
 // `ready`: called after the trusted circuit has been prepared on the host and before the first kernel touches `S`
 // (the upload of the big system may still be running until then); returns an ecne_status.

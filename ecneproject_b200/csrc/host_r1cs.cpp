@@ -898,3 +898,63 @@ static int abstraction_impl(int32_t kind, const ecne_r1cs_t* cons, const ecne_r1
   if (n_matches) *n_matches = added;
   return ECNE_OK;
 }
+
+// ---- compact coefficients (include/ecne_host.h) ---------------------------------------------------------------------
+extern "C" int ecne_compact_coef(const uint64_t* coef, uint64_t nnz, uint8_t* cls, uint64_t* other, uint32_t* other_term,
+                                 uint64_t* n_other) {
+  if ((nnz && (!coef || !cls)) || !n_other || (other == nullptr) != (other_term == nullptr)) {
+    g_err = "ecne_compact_coef: null argument";
+    return ECNE_E_BADARG;
+  }
+  if (nnz >= 0xffffffffULL) {
+    g_err = "ecne_compact_coef: term indices are 32-bit";
+    return ECNE_E_BADARG;
+  }
+  try {
+    // BN254 scalar field modulus minus one, little-endian limbs
+    static const uint64_t PM1[4] = {0x43e1f593f0000000ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+    const uint64_t CH = 1 << 16;
+    const uint64_t n_chunks = (nnz + CH - 1) / CH;
+    std::vector<uint64_t> cnt(n_chunks + 1, 0);
+    parallel_chunks(n_chunks, 4, [&, coef, cls](uint64_t cb, uint64_t ce) {
+      for (uint64_t c = cb; c < ce; ++c) {
+        uint64_t k = 0;
+        const uint64_t te = std::min(nnz, (c + 1) * CH);
+        for (uint64_t t = c * CH; t < te; ++t) {
+          const uint64_t* v = coef + 4 * t;
+          uint8_t cl = 3;
+          if ((v[1] | v[2] | v[3]) == 0 && v[0] <= 1)
+            cl = (uint8_t)v[0];
+          else if (v[0] == PM1[0] && v[1] == PM1[1] && v[2] == PM1[2] && v[3] == PM1[3])
+            cl = 2;
+          cls[t] = cl;
+          k += cl == 3;
+        }
+        cnt[c + 1] = k;
+      }
+    });
+    for (uint64_t c = 0; c < n_chunks; ++c) cnt[c + 1] += cnt[c];
+    if (other) {
+      if (*n_other != cnt[n_chunks]) {
+        g_err = "ecne_compact_coef: *n_other does not match the array (call with other == NULL first)";
+        return ECNE_E_BADARG;
+      }
+      parallel_chunks(n_chunks, 4, [&, coef, cls, other, other_term](uint64_t cb, uint64_t ce) {
+        for (uint64_t c = cb; c < ce; ++c) {
+          uint64_t k = cnt[c];
+          const uint64_t te = std::min(nnz, (c + 1) * CH);
+          for (uint64_t t = c * CH; t < te; ++t)
+            if (cls[t] == 3) {
+              memcpy(other + 4 * k, coef + 4 * t, 32);
+              other_term[k++] = (uint32_t)t;
+            }
+        }
+      });
+    }
+    *n_other = cnt[n_chunks];
+    return ECNE_OK;
+  } catch (const std::bad_alloc&) {
+    g_err = "ecne_compact_coef: out of memory";
+    return ECNE_E_BOUNDS;
+  }
+}

@@ -1291,8 +1291,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           // (b) replay the previous round's own records into the buffer written this round
           if (prev_own) {
             const Rec* pr = d.recs[prev_list];
-            for (uint32_t j = threadIdx.x; blockIdx.x + j * gridDim.x < prev_own; j += blockDim.x) {
-              Rec r = pr[blockIdx.x + j * gridDim.x];
+            // (consecutive threads take consecutive 16-byte records: a round of S16 replays 5 M of them)
+            for (uint32_t j = tid; j < prev_own; j += nthreads) {
+              Rec r = pr[j];
               apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
               consume_rec(d, prev_list, r.wire);
             }

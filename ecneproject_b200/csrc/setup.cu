@@ -763,12 +763,123 @@ static cudaError_t h2d(T* dst, const T* src, size_t n, cudaStream_t s) {
 }
 static inline unsigned int nb(uint64_t n, unsigned int t) { return (unsigned int)((n + t - 1) / t); }
 
-int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const DevSystem* dev) {
-  if (!p || (!dev && (!p->seg_ptr || (p->n_rows && (!p->col || !p->coef))))) {
+// ---- the rows of a host problem into device arrays of the on-disk layout ------------------------------------------
+// Full form: three copies.  Compact form (include/ecne_abi.h, `coef == NULL`): one class byte per term and the 32-byte
+// values of the terms that are not 0, 1 or p - 1 cross PCIe; two kernels write the same `coef` array the full form
+// would have been copied into, so nothing downstream knows the difference.
+__global__ void k_expand_class(const uint8_t* cls, uint64_t nnz, fr::u256* coef, unsigned int* chk) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int n3 = 0;
+  if (t < nnz) {
+    const uint8_t c = cls[t];
+    if (c == 0) {
+      coef[t] = fr::make_u256(0, 0, 0, 0);
+    } else if (c == 1) {
+      coef[t] = fr::make_u256(1, 0, 0, 0);
+    } else if (c == 2) {
+      fr::u256 m;
+      fr::sub_cc(m, fr::modulus(), fr::make_u256(1, 0, 0, 0));
+      coef[t] = m;
+    } else if (c == 3) {
+      n3 = 1;
+    } else {
+      chk[1] = 1;  // no such class
+    }
+  }
+  n3 = __reduce_add_sync(0xffffffffu, n3);
+  if ((threadIdx.x & 31u) == 0 && n3) atomicAdd(chk, n3);  // number of class-3 terms: must equal n_coef_other
+}
+__global__ void k_expand_other(const fr::u256* other, const uint32_t* term, uint64_t n_other, uint64_t nnz,
+                               const uint8_t* cls, fr::u256* coef, unsigned int* chk) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_other) return;
+  const uint32_t t = term[j];
+  if (t >= nnz || cls[t] != 3 || (j > 0 && term[j - 1] >= t)) {
+    chk[1] = 1;  // not a class-3 term, or the list is not strictly ascending
+    return;
+  }
+  coef[t] = other[j];
+}
+__global__ void k_widen_seg(const uint32_t* seg32, uint64_t n, unsigned long long* seg) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) seg[i] = seg32[i];
+}
+
+uint64_t problem_nnz(const ecne_problem_t* p) {
+  return p->seg_ptr ? p->seg_ptr[3 * p->n_rows] : p->seg_ptr32[3 * p->n_rows];
+}
+int problem_rows_ok(const ecne_problem_t* p, std::string& err) {
+  if (!p || (!p->seg_ptr && !p->seg_ptr32)) {
     err = "null problem arrays";
     return ECNE_E_BADARG;
   }
-  const uint64_t N = dev ? dev->N : p->n_rows, V = p->n_vars, nnz = dev ? dev->nnz : p->seg_ptr[3 * N];
+  if (p->n_rows == 0) return ECNE_OK;
+  if (!p->col || (!p->coef && !p->coef_class)) {
+    err = "null problem arrays";
+    return ECNE_E_BADARG;
+  }
+  if (!p->coef && p->n_coef_other && (!p->coef_other || !p->coef_other_term)) {
+    err = "compact coefficients: coef_other / coef_other_term missing";
+    return ECNE_E_BADARG;
+  }
+  return ECNE_OK;
+}
+
+int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_col, fr::u256* d_coef, Arena& tmp,
+                cudaStream_t s, std::string& err) {
+  const uint64_t N = p->n_rows, nnz = problem_nnz(p);
+  if (p->seg_ptr) {
+    CK(staged_h2d(d_seg, p->seg_ptr, (3 * N + 1) * 8, s));
+  } else {
+    uint32_t* d_seg32;
+    CK(tmp.alloc(&d_seg32, 3 * N + 1));
+    CK(staged_h2d(d_seg32, p->seg_ptr32, (3 * N + 1) * 4, s));
+    k_widen_seg<<<(unsigned int)((3 * N + 1 + 255) / 256), 256, 0, s>>>(d_seg32, 3 * N + 1, d_seg);
+  }
+  if (!nnz) return ECNE_OK;
+  CK(staged_h2d(d_col, p->col, nnz * 4, s));
+  if (p->coef) {
+    CK(staged_h2d(d_coef, p->coef, nnz * 32, s));
+    return ECNE_OK;
+  }
+  const uint64_t n_other = p->n_coef_other;
+  uint8_t* d_cls;
+  fr::u256* d_other;
+  uint32_t* d_term;
+  unsigned int* d_chk;
+  CK(tmp.alloc(&d_cls, nnz));
+  CK(tmp.alloc(&d_other, n_other));
+  CK(tmp.alloc(&d_term, n_other));
+  CK(tmp.alloc(&d_chk, 2));
+  CK(cudaMemsetAsync(d_chk, 0, 2 * sizeof(unsigned int), s));
+  CK(staged_h2d(d_cls, p->coef_class, nnz, s));
+  k_expand_class<<<(unsigned int)((nnz + 255) / 256), 256, 0, s>>>(d_cls, nnz, d_coef, d_chk);  // (while the values cross)
+  if (n_other) {
+    CK(staged_h2d(d_other, p->coef_other, n_other * 32, s));
+    CK(staged_h2d(d_term, p->coef_other_term, n_other * 4, s));
+    k_expand_other<<<(unsigned int)((n_other + 255) / 256), 256, 0, s>>>(d_other, d_term, n_other, nnz, d_cls, d_coef, d_chk);
+  }
+  unsigned int chk[2] = {0, 0};
+  CK(cudaMemcpyAsync(chk, d_chk, sizeof(chk), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (chk[1] || chk[0] != n_other) {
+    err = "compact coefficients are inconsistent: coef_class has " + std::to_string(chk[0]) + " class-3 terms, n_coef_other is " +
+          std::to_string(n_other) + (chk[1] ? " (and a class byte > 3, or coef_other_term is not the ascending list of the class-3 terms)" : "");
+    return ECNE_E_BADARG;
+  }
+  return ECNE_OK;
+}
+
+int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const DevSystem* dev) {
+  if (!p) {
+    err = "null problem";
+    return ECNE_E_BADARG;
+  }
+  if (!dev) {
+    const int st = problem_rows_ok(p, err);
+    if (st != ECNE_OK) return st;
+  }
+  const uint64_t N = dev ? dev->N : p->n_rows, V = p->n_vars, nnz = dev ? dev->nnz : problem_nnz(p);
   if (V < 1 || V >= 0x7fffffffULL || N >= 0x3fffffffULL || nnz >= 0x7fffffffULL) {
     err = "problem too large for 32-bit indices (rows < 2^30, wires, terms < 2^31)";
     return ECNE_E_BADARG;
@@ -826,9 +937,8 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     CK(tmp.alloc(&d_seg64, 3 * N + 2));
     CK(tmp.alloc(&d_col_raw, nnz));
     CK(tmp.alloc(&d_coef_raw, nnz));
-    CK(h2d(d_seg64, (const unsigned long long*)p->seg_ptr, 3 * N + 1, s));
-    CK(h2d(d_col_raw, p->col, nnz, s));
-    CK(h2d((uint64_t*)d_coef_raw, p->coef, 4 * nnz, s));
+    const int st = upload_rows(p, d_seg64, d_col_raw, d_coef_raw, tmp, s, err);
+    if (st != ECNE_OK) return st;
   }
 
   Dev& d = R->d;

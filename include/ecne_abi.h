@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ECNE_ABI_VERSION 2
+#define ECNE_ABI_VERSION 3
 
 /* Status codes.  The negative ones mirror the exception classes the reference can raise on this
  * path (SURVEY.md §5 / §8b "Errors"); the Julia shim rethrows them. */
@@ -76,6 +76,17 @@ typedef struct ecne_problem {
   const uint32_t* sp_out;     /* outputs                                                   */
   int32_t secp_solve;         /* :591                                                      */
   int32_t debug;              /* :587 — accepted, ignored (printing stays in the host)     */
+  /* Optional COMPACT form of the coefficients (ABI version 3; `coef == NULL` selects it).  The coefficients of a
+   * circom circuit are almost all 0, 1 or p-1 (ecdsa.r1cs after abstraction: 2.62 M of 2.83 M stored terms), so the
+   * host that flattens `Dict{Int, GFElem}` (`R1CSEquation`, ParseR1CS.jl:9-13) can hand over one class byte per term
+   * and 32-byte limbs only for the others: 38 MB instead of 118 MB cross PCIe for the headline workload, and the
+   * library expands them into the same device arrays the full form is copied into (csrc/setup.cu upload_rows).
+   * The host library (include/ecne_host.h) has a helper that makes this form from a full `coef` array. */
+  const uint8_t* coef_class;       /* [nnz] 0: stored zero, 1: one, 2: p - 1, 3: the value is in coef_other    */
+  const uint64_t* coef_other;      /* [n_coef_other*4] canonical limbs of the class-3 terms, in term order   */
+  const uint32_t* coef_other_term; /* [n_coef_other] index (into col / coef_class) of each of them, ascending */
+  uint64_t n_coef_other;
+  const uint32_t* seg_ptr32;       /* optional 32-bit copy of seg_ptr (`seg_ptr == NULL` selects it)           */
 } ecne_problem_t;
 
 typedef struct ecne_result {

@@ -64,6 +64,13 @@ void ecne_specials_free(ecne_specials_t* s);
 int ecne_abstraction(int32_t kind, const ecne_r1cs_t* constraints, const ecne_r1cs_t* sub,
                      ecne_r1cs_t** reduced, ecne_specials_t* specials, uint64_t* n_matches);
 
+/* The compact form of a coefficient array (include/ecne_abi.h, ecne_problem_t.coef_class / coef_other /
+ * coef_other_term): one class byte per stored term — 0: zero, 1: one, 2: p - 1, 3: another value — and the values and
+ * term indices of the class-3 terms in term order.  Call with other == other_term == NULL to fill `cls` and learn
+ * *n_other, then again with arrays of that size (multi-threaded; `cls` is rewritten identically). */
+int ecne_compact_coef(const uint64_t* coef, uint64_t nnz, uint8_t* cls, uint64_t* other, uint32_t* other_term,
+                      uint64_t* n_other);
+
 const char* ecne_host_last_error(void);
 
 #ifdef __cplusplus

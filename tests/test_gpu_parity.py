@@ -365,3 +365,53 @@ def test_p2_set_hash_collisions_are_resolved_exactly(name):
     finally:
         lib.ecne_set_option(b"p2_hash_bits", 56)
     assert all(o == outs[0] for o in outs[1:]), [(o[2], o[3]) for o in outs]
+
+
+# ---- the compact form of the coefficients (include/ecne_abi.h, ABI 3) ----------------------------------------------
+@pytest.mark.parametrize("name", SMALL)
+def test_compact_form_gives_the_goldens(name):
+    """coef == NULL: class bytes {0, 1, p-1, other} + the other values + 32-bit offsets, expanded on the device into
+    the arrays the full form is copied into — every configuration must give the same goldens through it."""
+    (reduced, specials, main), secp = prepare(name)
+    lib = api._engine()
+    ph = api.ProblemHandle(reduced, specials, main.known, main.targets, main.n_vars, secp, compact=True)
+    assert not ph.c.coef and not ph.c.seg_ptr
+    res = api.SolveResult(main.n_vars)
+    st = lib.ecne_solve(C.byref(ph.c), C.byref(res.c))
+    assert st == GOLD[name].get("status", 0), lib.ecne_last_error()
+    if st == 0:
+        check_against_gold(name, res)
+
+
+def test_compact_form_full_size():
+    (reduced, specials, main), secp = prepare("ecdsa+secp256k1")
+    lib = api._engine()
+    ph = api.ProblemHandle(reduced, specials, main.known, main.targets, main.n_vars, secp, compact=True)
+    res = api.SolveResult(main.n_vars)
+    assert lib.ecne_solve(C.byref(ph.c), C.byref(res.c)) == 0, lib.ecne_last_error()
+    check_against_gold("ecdsa+secp256k1", res)
+
+
+@pytest.mark.parametrize("damage", ["count", "class", "term_order", "term_not_class3"])
+def test_inconsistent_compact_form_is_refused(damage):
+    (reduced, specials, main), secp = prepare("root/poseidon")
+    lib = api._engine()
+    ph = api.ProblemHandle(reduced, specials, main.known, main.targets, main.n_vars, secp, compact=True)
+    cls = next(a for a in ph.keep if a.dtype == np.uint8 and a.size == reduced.nnz)
+    term = next(a for a in ph.keep if a.dtype == np.uint32 and a.size == ph.c.n_coef_other and a is not cls)
+    assert ph.c.n_coef_other >= 2
+    if damage == "count":
+        ph.c.n_coef_other -= 1
+    elif damage == "class":
+        cls[0] = 7
+    elif damage == "term_order":
+        term[0], term[1] = int(term[1]), int(term[0])
+    else:
+        term[0] = int(np.flatnonzero(cls != 3)[0])
+    res = api.SolveResult(main.n_vars)
+    assert lib.ecne_solve(C.byref(ph.c), C.byref(res.c)) == _abi.ECNE_E_BADARG
+    assert b"compact" in lib.ecne_last_error()
+    # the library is fine afterwards
+    st, res = gpu_solve(reduced, specials, main, secp)
+    assert st == 0
+    check_against_gold("root/poseidon", res)

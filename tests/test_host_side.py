@@ -24,12 +24,12 @@ def test_engine_exports_every_declared_symbol():
     assert set(syms) == set(_abi.ENGINE_SYMBOLS)
     for s in syms:
         assert getattr(lib, s) is not None
-    assert lib.ecne_version() == _abi.ABI_VERSION == 2
+    assert lib.ecne_version() == _abi.ABI_VERSION == 3
     # the layout table the library reports is what the ctypes mirror has (checked at load time as well)
     n = lib.ecne_abi_layout(None, 0)
     buf = (C.c_uint32 * n)()
     assert lib.ecne_abi_layout(buf, n) == n and list(buf) == _abi.layout_table()
-    assert n == 3 * 2 + 17 + 31 + 10
+    assert n == 3 * 2 + 22 + 31 + 10
 
 
 def test_host_exports_every_declared_symbol():
@@ -335,3 +335,24 @@ def test_loader_parallel_offset_walk_on_a_hostile_file(tmp_path):
         os.environ.pop("ECNE_HOST_WALK_RANGES", None)
     st, _ = _read_mem(blob[: len(blob) // 2])
     assert st in (_abi.ECNE_E_BOUNDS, _abi.ECNE_E_ASSERT)
+
+def test_compact_coef_matches_a_numpy_classification():
+    """ecne_compact_coef (include/ecne_host.h): class bytes, other values and their term indices."""
+    rng = np.random.default_rng(7)
+    n = 200_003
+    coef = np.zeros((n, 4), dtype=np.uint64)
+    kind = rng.integers(0, 5, n)
+    pm1 = np.array([((P - 1) >> (64 * i)) & (2**64 - 1) for i in range(4)], dtype=np.uint64)
+    coef[kind == 1, 0] = 1
+    coef[kind == 2] = pm1
+    coef[kind == 3] = rng.integers(0, 2**63, (int((kind == 3).sum()), 4), dtype=np.uint64)
+    coef[kind == 4, 0] = 2          # small but not 0/1
+    coef[0] = pm1; coef[0, 0] -= 1  # p - 2: shares three limbs with p - 1
+    cls, other, term = api.compact_coef(coef)
+    want = np.where(kind == 0, 0, np.where(kind == 1, 1, np.where(kind == 2, 2, 3))).astype(np.uint8)
+    want[0] = 3
+    assert np.array_equal(cls, want)
+    assert np.array_equal(term, np.flatnonzero(want == 3).astype(np.uint32))
+    assert np.array_equal(other, coef[want == 3])
+    cls0, other0, term0 = api.compact_coef(np.zeros((0, 4), dtype=np.uint64))
+    assert len(cls0) == 0 and len(term0) == 0
