@@ -26,7 +26,7 @@ namespace {
 // One device this process drives: its streams, its slab pool, its pinned staging and its exchange buffer.
 struct Ctx {
   int device = -1;
-  cudaStream_t stream = nullptr, side = nullptr;
+  cudaStream_t stream = nullptr, side = nullptr, side2 = nullptr;
   SlabPool pool;
   void* h_status = nullptr;
   void* h_counts = nullptr;
@@ -208,6 +208,7 @@ int open_ctx(int device, Ctx** out) {
   G.ctx.push_back(c);  // (registered first: a failure below is cleaned up by close_all)
   CKA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CKA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CKA(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
   CKA(cudaMallocHost(&c->h_status, sizeof(Status)));
   CKA(cudaMallocHost(&c->h_counts, 4 * sizeof(unsigned long long)));
   *out = c;
@@ -223,6 +224,7 @@ void close_all() {
     cudaDeviceSynchronize();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->side) cudaStreamDestroy(c->side);
+    if (c->side2) cudaStreamDestroy(c->side2);
   }
   if (!G.multi)
     for (int h = 0; h < ECNE_MAX_WORLD; ++h)
@@ -376,6 +378,7 @@ int upload_impl(const ecne_problem_t* problem, const DevSystem* dev0, ecne_resid
     Resident& R = h->rs[i];
     R.stream = c->stream;
     R.side = c->side;
+    R.side2 = c->side2;
     R.device = c->device;
     R.h_status = (Status*)c->h_status;
     R.h_counts = (unsigned long long*)c->h_counts;

@@ -103,6 +103,7 @@ struct Resident {
   Arena arena;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // side stream of the set-up (bound-table chain)
+  cudaStream_t side2 = nullptr; // ... a second one (the long rows' classification and layout)
   int device = 0;
   // host mirrors needed by the solve loop
   uint64_t n_rows = 0, n_vars = 0, n_targets = 0;

@@ -749,11 +749,8 @@ __global__ void k_fill_ranks(uint32_t N, const uint32_t* rflags, RowAux* aux, co
   }
 }
 
-struct ValLess {  // order of the candidate bound values (ties: any order, equal values share a rank)
-  const fr::u256* v;
-  __device__ __forceinline__ bool operator()(const uint32_t& a, const uint32_t& b) const {
-    return fr::cmp(v[a], v[b]) < 0;
-  }
+struct U256Less {  // order of the candidate bound values (ties: any order, equal values share a rank)
+  __device__ __forceinline__ bool operator()(const fr::u256& a, const fr::u256& b) const { return fr::cmp(a, b) < 0; }
 };
 
 template <class T>
@@ -1053,12 +1050,29 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(cudaMemsetAsync(d_next, 0, 2 * sizeof(unsigned int), s));
   // The bound-table chain (values -> sort -> ranks) only depends on the classification, and the sweep
   // layout below does not depend on it: it runs on a side stream, concurrently with the layout kernels.
-  cudaStream_t s2 = R->side;  // one side stream per device context (abi.cu)
-  cudaEvent_t ev_fork, ev_join;
+  cudaStream_t s2 = R->side;  // side streams of the device context (abi.cu)
+  cudaStream_t s3 = R->side2 ? R->side2 : s;  // ... the long rows' chain: Case-3 classification -> list -> layout
+  cudaEvent_t ev_fork, ev_join, ev_long;
   cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ev_long, cudaEventDisableTiming);
+  // (outputs of the layout, allocated and cleared before the fork: the short rows are laid out on the main stream, the
+  // long ones on `s3`, both mark the wires they mention)
+  uint32_t* d_col;
+  fr::u256* d_coef;
+  uint8_t* d_nontriv;
+  uint32_t* d_long;
+  unsigned int* d_nlong;
+  CK(A.alloc(&d_col, (size_t)nnz_nz));
+  CK(A.alloc(&d_coef, (size_t)nnz_nz));
+  CK(A.alloc(&d_nontriv, V + 4));
+  CK(A.alloc(&d_long, (size_t)cnt.n_long));
+  CK(tmp.alloc(&d_nlong, 1));
+  CK(cudaMemsetAsync(d_nontriv, 0, V + 4, s));
+  CK(cudaMemsetAsync(d_nlong, 0, sizeof(unsigned int), s));
   cudaEventRecord(ev_fork, s);
   cudaStreamWaitEvent(s2, ev_fork, 0);
+  if (s3 != s) cudaStreamWaitEvent(s3, ev_fork, 0);
   k_consts<<<1, 256, 0, s2>>>(d_tvals);
   if (N) k_values<<<nb(N, 128), 128, 0, s2>>>(raw, d_rflags, d_aux, d_roots, d_tvals, d_next, d_next + 1);
   const uint32_t nc = N_CONST + cnt.n2b;
@@ -1076,14 +1090,19 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   void* d_ms = nullptr;
   size_t d_ms_bytes = 0;
   k_iota<<<nb(nc, 256), 256, 0, s2>>>(d_idx, nc);
-  {  // one merge sort of the index permutation with a 256-bit comparator (a handful of launches; an LSD
-     // radix sort over four 64-bit limbs costs 40 launch-bound passes for these ~10^5 values)
+  {  // one merge sort of (value, index) pairs under a 256-bit comparator (a handful of launches; an LSD radix sort
+     // over four 64-bit limbs costs 40 launch-bound passes for these ~10^5 values).  The VALUES travel with the
+     // indices — ecdsa's 160 k constants are almost all distinct, and sorting the index permutation alone made every
+     // comparison two random 32-byte gathers (0.45 ms; the critical path of the set-up).
+    fr::u256* d_keys;
+    CK(tmp.alloc(&d_keys, nc));
+    CK(cudaMemcpyAsync(d_keys, d_tvals, (size_t)nc * sizeof(fr::u256), cudaMemcpyDeviceToDevice, s2));
     size_t need = 0;
-    cub::DeviceMergeSort::SortKeys((void*)nullptr, need, d_idx, (int)nc, ValLess{d_tvals}, s2);
+    cub::DeviceMergeSort::SortPairs((void*)nullptr, need, d_keys, d_idx, (int)nc, U256Less{}, s2);
     need = std::max<size_t>(need, (size_t)1 << 20);  // own scratch: d_cub is in use on the main stream
     CK(tmp.alloc((uint8_t**)&d_ms, need));
     d_ms_bytes = need;
-    CK(cub::DeviceMergeSort::SortKeys(d_ms, need, d_idx, (int)nc, ValLess{d_tvals}, s2));
+    CK(cub::DeviceMergeSort::SortPairs(d_ms, need, d_keys, d_idx, (int)nc, U256Less{}, s2));
   }
   k_distinct<<<nb(nc, 256), 256, 0, s2>>>(d_tvals, d_idx, nc, d_flag);
   {
@@ -1112,11 +1131,12 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
         err = "2^i mod p repeats below the longest row length";
         cudaStreamSynchronize(s2);  // the side chain works in `tmp`, which is released on return
         cudaStreamSynchronize(s);
+        cudaStreamSynchronize(s3);
         return ECNE_E_UNSUPPORTED;
       }
     Pow2Entry* d_tab;
     CK(tmp.alloc(&d_tab, tn));
-    CK(cudaMemcpyAsync(d_tab, tab.data(), tn * sizeof(Pow2Entry), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_tab, tab.data(), tn * sizeof(Pow2Entry), cudaMemcpyHostToDevice, s3));
     uint32_t mask_words = (tn + 31) / 32;
     const int warps = 4;
     size_t smem = (size_t)warps * 2 * mask_words * sizeof(unsigned int);
@@ -1124,13 +1144,14 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
       err = "row too long for the bit-decomposition classifier";
       cudaStreamSynchronize(s2);
       cudaStreamSynchronize(s);
+      cudaStreamSynchronize(s3);
       return ECNE_E_UNSUPPORTED;
     }
     if (smem > 48 * 1024)
       CK(cudaFuncSetAttribute(k_classify_c3_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_classify_c3_long<<<nb(cnt.n_c3_long, warps), warps * 32, smem, s>>>(
+    k_classify_c3_long<<<nb(cnt.n_c3_long, warps), warps * 32, smem, s3>>>(
         raw, d_rflags, d_aux, d_c3_long, cnt.n_c3_long, d_tab, tn, mask_words);
-    cudaEventRecord(ev_c3, s);  // (`tab` lives until the function's final synchronisation)
+    cudaEventRecord(ev_c3, s3);  // (`tab` lives until the function's final synchronisation)
   }
 
   if (cnt.n_c3_long) cudaStreamWaitEvent(s2, ev_c3, 0);  // k_fill_ranks reads the C3 flags of those rows
@@ -1139,28 +1160,20 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   cudaEventRecord(ev_join, s2);
 
   // ---- sweep layout ---------------------------------------------------------------------------
-  uint32_t* d_col;
-  fr::u256* d_coef;
-  uint8_t* d_nontriv;
-  uint32_t* d_long;
-  unsigned int* d_nlong;
-  CK(A.alloc(&d_col, (size_t)nnz_nz));
-  CK(A.alloc(&d_coef, (size_t)nnz_nz));
-  CK(A.alloc(&d_nontriv, V + 4));
-  CK(A.alloc(&d_long, (size_t)cnt.n_long));
-  CK(tmp.alloc(&d_nlong, 1));
-  CK(cudaMemsetAsync(d_nontriv, 0, V + 4, s));
-  CK(cudaMemsetAsync(d_nlong, 0, sizeof(unsigned int), s));
-  if (cnt.n_long) k_long_rows<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_rflags, d_long, d_nlong);
-  if (nnz)
-    k_layout<<<nb(nnz, 256), 256, 0, s>>>(raw, d_keep, d_pos, d_segnz, d_rflags, d_col, d_coef, d_nontriv);
+  // long rows on `s3` (behind their Case-3 classification, whose flip flag orders their C terms), short rows on the
+  // main stream: the 208 sorting blocks of ecdsa's long rows (0.14 ms) run beside the 0.16 ms pass over every term
   if (cnt.n_long) {
+    k_long_rows<<<nb(N, 256), 256, 0, s3>>>((uint32_t)N, d_rflags, d_long, d_nlong);
     // shared memory for the longest segment the kernel accepts (both kernels apply the same length test)
     const size_t smem = (size_t)LAYOUT_LONG_MAX * (sizeof(fr::u256) + 2 * sizeof(uint32_t) + 1) + 64;  // 168 KB
     CK(cudaFuncSetAttribute(k_layout_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_layout_long<<<cnt.n_long, 1024, smem, s>>>(raw, d_keep, d_segnz, d_rflags, d_long, cnt.n_long, d_col, d_coef,
-                                                 d_nontriv);
+    k_layout_long<<<cnt.n_long, 1024, smem, s3>>>(raw, d_keep, d_segnz, d_rflags, d_long, cnt.n_long, d_col, d_coef,
+                                                  d_nontriv);
   }
+  cudaEventRecord(ev_long, s3);
+  if (nnz)
+    k_layout<<<nb(nnz, 256), 256, 0, s>>>(raw, d_keep, d_pos, d_segnz, d_rflags, d_col, d_coef, d_nontriv);
+  if (s3 != s) cudaStreamWaitEvent(s, ev_long, 0);  // from here on: final row flags, every row laid out
   if (n_sp_in) k_mark<<<nb(n_sp_in, 256), 256, 0, s>>>(d_sp_in, (uint32_t)n_sp_in, d_nontriv);
   if (n_sp_out) k_mark<<<nb(n_sp_out, 256), 256, 0, s>>>(d_sp_out, (uint32_t)n_sp_out, d_nontriv);
   if (p->n_targets) k_mark<<<nb(p->n_targets, 256), 256, 0, s>>>(d_targets, (uint32_t)p->n_targets, d_nontriv);
@@ -1261,9 +1274,11 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(cudaMemcpyAsync(&h_tn, d_incl + (nc - 1), 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   CK(cudaStreamSynchronize(s2));
+  if (s3 != s) CK(cudaStreamSynchronize(s3));
   cudaEventDestroy(ev_fork);
   cudaEventDestroy(ev_join);
   cudaEventDestroy(ev_c3);
+  cudaEventDestroy(ev_long);
   d.r0 = h_rank[0];
   d.r1 = h_rank[1];
   d.rpm1 = h_rank[2];
