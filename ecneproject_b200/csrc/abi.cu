@@ -46,6 +46,8 @@ struct Global {
   long long grid_blocks = 0;          // testing knob: launch the solve kernel with fewer blocks than SMs (0: one per SM)
   long long p2_hash_bits = 56;         // testing knob: bits of the P2 set hash that are used (fewer => collisions)
   long long sparse_max = -1;          // records per round up to which a round is frontier-driven (-1: rows / 32)
+  // open rows of the linear-system sweep below which block 0 runs whole outer rounds alone (0: never; at most CH_LIST_CAP)
+  long long chain_open_max = 4096;
   // On several GPUs the dense sweeps of a problem with at least this many rows are split over the ranks; a smaller
   // problem is solved by every rank on all rows without any exchange (a sharded round costs a cross-GPU barrier,
   // ~15-25 us, which a sweep of a few 10^5 rows does not earn back: ecdsa's 694 k rows sweep in ~20 us)
@@ -321,6 +323,8 @@ extern "C" int ecne_set_option(const char* key, int64_t value) {
     G.sparse_max = value;
   else if (k == "grid_blocks")
     G.grid_blocks = value;
+  else if (k == "chain_open_max")
+    G.chain_open_max = value < 0 ? 0 : (value > (long long)CH_LIST_CAP ? (long long)CH_LIST_CAP : value);
   else if (k == "solve_variant")
     G.solve_variant = value < 0 || value > 2 ? 0 : value;
   else if (k == "wide_min_rows")
@@ -671,6 +675,7 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
       const long long sm = G.sparse_max >= 0 ? G.sparse_max : std::max<long long>(4096, (long long)di.N / 32);
       di.sparse_max = (uint32_t)std::min<long long>(sm, 0x7fffffffLL);
     }
+    di.chain_open_max = G.chain_open_max;
     cudaEventRecord(s0[i], Ri.stream);
     const unsigned int mr = (unsigned int)std::min<long long>(G.max_rounds, 0x7fffffffLL);
     CKA(wide ? ecne_launch_solve_v1024(&di, mr, grid, Ri.stream) : launch_solve(di, mr, grid, Ri.stream));
@@ -714,13 +719,18 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
             S.prof[0], S.dense_rounds, S.prof[1], S.rounds - S.dense_rounds, S.prof[2], S.prof[3], S.prof[4], S.prof[5],
             S.prof[6], S.prof[7], S.outer, S.n_cand_total, S.n_cand_max, S.dense_evals, S.evals);
     if (atoi(getenv("ECNE_DEBUG_PROF")) > 2) {
-      std::vector<unsigned long long> pr(28000 + 40 * 148 * 4 + 64);
+      std::vector<unsigned long long> pr(28000 + 40 * 148 * 4 + 128);
       cudaMemcpy(pr.data(), d.prof, pr.size() * 8, cudaMemcpyDeviceToHost);
       {
         const unsigned long long* q = pr.data() + 28000 + 40 * 148 * 4;
         fprintf(stderr, "[long row] slowest evaluation (maxima, cycles from entry): total %llu | gather %llu | cases 1-4 %llu | case 5 %llu | "
                         "case 6 scan %llu | firing done %llu\n", q[0], q[1], q[2], q[3], q[4], q[5]);
       }
+      fprintf(stderr, "[phases] n_p3 %u n_p4 %u | open rows seen by the P2 scan / P4 rows with a non-unique vk, per outer round:", d.n_p3, d.n_p4);
+      for (int o = 1; o < 40; ++o)
+        if (pr[28000 + 40 * 148 * 4 + 48 + o] | pr[28000 + 40 * 148 * 4 + 88 + o])
+          fprintf(stderr, " %d:%llu/%llu", o, pr[28000 + 40 * 148 * 4 + 48 + o], pr[28000 + 40 * 148 * 4 + 88 + o]);
+      fprintf(stderr, "\n");
       for (int r = 12; r < 24; ++r) {
         unsigned long long mx[3] = {0, 0, 0}, sum[3] = {0, 0, 0}, g = 0;
         for (int b = 0; b < 148; ++b)

@@ -1037,6 +1037,159 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
   }
 }
 
+// ---- chain stretch: whole outer rounds by block 0 alone ----------------------------------------------------------------
+// Most outer rounds of a long dependency chain do almost nothing: one special constraint fires (6 wires), three Jacobi
+// rounds of <= 6 records settle it, the linear-system sweep looks at the few hundred rows it still has open and resolves
+// nothing, no IsZero pair fires (ecdsa + secp256k1: 24 of 28 outer rounds).  On the whole grid such a round is five grid
+// barriers and five phases of a handful of dependent L2 trips each, 147 SMs waiting for one.  Once the linear-system
+// sweep has few rows left (engine knob "chain_open_max"), block 0 therefore runs WHOLE outer rounds — Jacobi rounds as
+// before (warp_solo / sparse_round), then P2, P4 and the next round's P0 — behind block barriers, and the grid meets
+// again when a round needs it (a frontier beyond SOLO_MAX, a heavy wire) or the fixpoint is reached.  Same operations
+// on the same buffers in the same order as the grid phases of k_solve; only who executes them differs.
+
+// block barrier that also makes the block's atomics (performed at the L2) visible to the block's cached loads: one
+// release fence + one acquire load by the leader (it drops the SM's L1 lines), as between two block-solo rounds.
+// Returns *src as of the barrier.
+__device__ __forceinline__ unsigned int block_sync_load(const unsigned int* src) {
+  __shared__ unsigned int s_bsl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int v;
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    s_bsl = v;
+  }
+  __syncthreads();
+  return s_bsl;
+}
+
+// the open rows of the linear-system sweep as a list (block 0; the bitmap stays authoritative: closing a row clears
+// its bit as well).  Returns the list length, or 0xffffffff when more than `cap` rows are open.
+__device__ __noinline__ unsigned int chain_build_list(const Dev&, unsigned int cap) {
+  const Dev& d = c_dev;
+  __shared__ unsigned int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const uint32_t n_words = (d.N + 31u) / 32u;
+  for (uint32_t base = 0; base < n_words; base += 8u * blockDim.x) {
+    uint32_t w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t i = base + (uint32_t)u * blockDim.x + threadIdx.x;
+      w[u] = i < n_words ? __ldcg(d.p2_open + i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (!w[u]) continue;
+      const uint32_t i = base + (uint32_t)u * blockDim.x + threadIdx.x;
+      unsigned int at = atomicAdd(&s_n, (unsigned int)__popc(w[u]));
+      for (uint32_t m = w[u]; m; m &= m - 1) {
+        if (at < cap) d.p2_list[at] = i * 32u + (uint32_t)(__ffs((int)m) - 1);
+        ++at;
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned int n = s_n;
+  __syncthreads();
+  return n <= cap ? n : 0xffffffffu;
+}
+
+// P2 .. P0 of one outer round by block 0 (the state is at the P1 fixpoint in both buffers; `pl`: the phase list this
+// round writes).  Returns the number of records in `pl` afterwards (the frontier of the next round's first Jacobi round).
+__device__ __noinline__ unsigned int chain_phases(const Dev&, int pl, SpecialsCache& spc, unsigned int list_n,
+                                                  unsigned int gr, unsigned int last_dense_gr, unsigned long long* evals_io,
+                                                  unsigned int* n_cand_io) {
+  const Dev& d = c_dev;
+  const uint32_t t = threadIdx.x, nt = blockDim.x, lane = t & 31u, warp = t >> 5, nwarps = nt >> 5;
+  __shared__ unsigned int s_nlq;
+  uint32_t* lq = d.p2_list + CH_LIST_CAP;  // long rows whose cached scan is stale: one warp each
+  const uint8_t* F = d.F[0];
+  unsigned long long ev = 0;
+  if (t == 0) s_nlq = 0;
+  __syncthreads();
+  // ---- P2 candidate scan (:1357-1385): the open short rows, a thread each
+  for (uint32_t i = t; i < list_n; i += nt) {
+    const uint32_t row = __ldcg(d.p2_list + i);
+    if (row == 0xffffffffu) continue;
+    InlineRow rr;
+    load_row(d, row, rr);
+    uint32_t ff[ROWREC_INLINE];
+#pragma unroll
+    for (int j = 0; j < ROWREC_INLINE; ++j) ff[j] = (rr.meta & 0x10000u) ? ld_flag(F, rr.c[j]) : (uint32_t)WF_U;
+    ev += 1;  // one visit of the sweep per open row (:1359)
+    if (p2_scan_short(d, pl, row, rr, ff)) {
+      d.p2_list[i] = 0xffffffffu;
+      atomicAnd(d.p2_open + (row >> 5), ~(1u << (row & 31u)));
+    }
+  }
+  // ... the long rows: a thread each decides from the cached scan; stale ones are queued for a warp
+  for (uint32_t i = t; i < d.n_long; i += nt) {
+    const uint32_t row = d.long_rows[i];
+    if (d.solved[row] & 1) continue;
+    if (d.long_done[i]) continue;
+    const LongP2 c = d.long_p2[i];
+    const unsigned int stamp = __ldcg(d.long_stamp + i);
+    if (c.gr != 0 && stamp < c.gr && last_dense_gr < c.gr) {
+      if (!c.bad && c.k == 1)
+        emit(d, 1, pl, c.w1, WF_U | WF_K);
+      else if (!c.bad && c.k >= 2)
+        p2_candidate(d, row, c.hs, c.hx, c.k);
+    } else {
+      lq[atomicAdd(&s_nlq, 1u)] = i;  // (n_long <= CH_LONG_MAX: the queue cannot overflow)
+    }
+  }
+  __syncthreads();
+  {
+    const unsigned int nlq = s_nlq;
+    for (unsigned int x = warp; x < nlq; x += nwarps) {
+      const uint32_t i = lq[x];
+      p2_scan_row<32>(d, 0, pl, d.long_rows[i], d.long_p2 + i, __ldcg(d.long_stamp + i), last_dense_gr, gr);
+    }
+  }
+  unsigned int n_cand = block_sync_load(&d.st->p2_cand);
+  if (n_cand > d.N) n_cand = d.N;
+  *n_cand_io = n_cand;
+  // ---- P2 resolve (:1386-1417)
+  for (uint32_t c = t; c < n_cand; c += nt) p2_resolve_group(d, pl, c);
+  const unsigned int n_x = block_sync_load(d.rec_count + pl);
+  {  // replay the P2 updates into buffer 0, clear the table (P3 can only tag in the first outer round: not here)
+    const unsigned int nx = n_x > d.rec_cap ? d.rec_cap : n_x;
+    for (uint32_t i = t; i < nx; i += nt) {
+      const Rec r = d.recs[pl][i];
+      apply_update(d, 0, r.wire, r.bits, r.lbr, r.ubr);
+    }
+    for (uint32_t c = t; c < n_cand; c += nt) {
+      const uint32_t slot = d.p2_slot[c];
+      d.h_key[slot] = 0ULL;
+      d.h_cnt[slot] = 0;
+      d.h_head[slot] = 0;
+    }
+    if (t == 0) d.st->p2_cand = 0;
+  }
+  if (n_x > 0) block_sync_load(d.rec_count + pl);
+  // ---- P4 (:1492-1550): reads buffer 0, U|K to buffer 1
+  {
+    bool fired = false;
+    for (uint32_t i = t; i < d.n_p4; i += nt) fired |= p4_row(d, pl, d.p4_rows[i]);
+    if (fired) atomicAdd(&d.st->p4_fired, 1u);
+  }
+  const unsigned int n_y = block_sync_load(d.rec_count + pl);
+  {  // replay the P4 updates into buffer 0, then the next outer round's P0 (buffer 1 is complete)
+    const unsigned int nx = n_x > d.rec_cap ? d.rec_cap : n_x, ny = n_y > d.rec_cap ? d.rec_cap : n_y;
+    for (uint32_t i = nx + t; i < ny; i += nt) {
+      const Rec r = d.recs[pl][i];
+      apply_update(d, 0, r.wire, r.bits, r.lbr, r.ubr);
+    }
+    if (t == 0) atomicAdd(&d.st->prog, n_y);
+    __syncthreads();  // prog += n_y is ordered before P0's atomics on it
+    phase_p0(d, pl, spc);
+  }
+  (void)lane;
+  *evals_io += ev;
+  return block_sync_load(d.rec_count + pl);
+}
+
 // The whole fixpoint (:706-1556) as ONE persistent cooperative launch (148 blocks x 1024 threads):
 //
 //   P0 -> [Jacobi rounds of the single-row rules until no record] -> P2 -> P3 -> P4 -> repeat while
@@ -1105,10 +1258,22 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     tp = t_;                                  \
   } while (0)
 
+  // rows latched by P4 leave the live masks (equation_solved, :820-822)
+  auto refresh_live = [&]() {
+    const unsigned int p4f = __ldcg(&d.st->p4_fired);
+    if (p4f != p4_seen) {
+      p4_seen = p4f;
+      for (LiveMask m = live; m.any();) {
+        const int k = m.pop_nonempty();
+        if (d.solved[d.row_lo + tid + (uint32_t)k * nthreads] & 1) live.clear(k);
+      }
+    }
+  };
   while (!stop) {
     ++outer;
-    const int pl_r = PL0 + (int)((outer - 1) & 1u);  // phase list read by this round's first Jacobi round
-    const int pl = PL0 + (int)(outer & 1u);          // ... written by this round's phases
+    int pl_r = PL0 + (int)((outer - 1) & 1u);  // phase list read by this round's first Jacobi round
+    int pl = PL0 + (int)(outer & 1u);          // ... written by this round's phases
+    bool chain_done = false;  // block 0 ran this round's phases (and possibly whole rounds before it) alone
     // =============================== P1: Jacobi rounds to a fixpoint ===============================
     if (outer == 1 || n_pl > 0) {
       int rbuf = 0;
@@ -1132,6 +1297,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           // SM's L1 lines, as the grid barrier does) instead of a grid barrier
           unsigned int n = 0;
           if (blockIdx.x == 0) {
+            unsigned int ch_pos = CH_NONE, ch_list_n = 0xffffffffu, ch_n_pl = 0, ch_stop = 0;
+            while (true) {  // chain stretch: rounds, and — while the conditions hold — whole outer rounds
             while (true) {
               if (prev_n <= WARP_SOLO_MAX && prev_own == prev_n) {
                 // at most 32 records: warp 0 chases them alone, for as many rounds as that stays so
@@ -1242,6 +1409,58 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               list = (list + 1) % 3;
               rbuf ^= 1;
             }
+            // ---- the P1 fixpoint of outer round `outer` was reached by this block alone: its phases too? ----
+            if (n != 0 || d.shard || outer < 2 || d.chain_open_max <= 0 || d.n_p4 > CH_P4_MAX || d.n_long > CH_LONG_MAX) break;
+            if (ch_list_n == 0xffffffffu) {
+              // rows the sweep of the round before left open (counted by the grid scan; a stretch keeps its own list)
+              if (__ldcg(&d.st->p2_open_n[(outer - 1u) & 1u]) > (unsigned int)d.chain_open_max) break;
+              ch_list_n = chain_build_list(d, CH_LIST_CAP);
+              if (ch_list_n == 0xffffffffu) break;
+            }
+            rounds_total += round;
+            {
+              unsigned long long ev = 0;
+              unsigned int nc = 0;
+              ch_n_pl = chain_phases(d, pl, s_spc, ch_list_n, gr, last_dense_gr, &ev, &nc);
+              if (d.rank == 0) evals += ev;
+              cand_total += nc;
+              cand_max = nc > cand_max ? nc : cand_max;
+            }
+            ch_pos = CH_DONE;
+            round = 0;
+            {
+              const unsigned int prog = __ldcg(&d.st->prog);
+              const unsigned int err = __ldcg(&d.st->err) | __ldcg(&d.st->rec_overflow);
+              if (err || prog == prog_prev) ch_stop = 1;  // successful_steps did not move (:708-711)
+              prog_prev = prog;
+              if (!ch_stop && outer >= d.max_outer) {
+                if (threadIdx.x == 0) raise(d, ECNE_E_NOCONVERGE);
+                ch_stop = 1;
+              }
+            }
+#ifdef ECNE_PROFILE
+            if (threadIdx.x == 0) {
+              long long t_ = clock64();
+              pf[6] += (unsigned long long)(t_ - tp);  // (chain phases are booked under "p0+replay")
+              tp = t_;
+            }
+#endif
+            // the next outer round starts here when its first Jacobi round can be run by this block as well
+            if (ch_stop || ch_n_pl == 0 || ch_n_pl > SOLO_MAX || ch_n_pl > d.rec_cap || (__ldcg(d.bnd_flag + pl) & 2u)) break;
+            ++outer;
+            pl_r = PL0 + (int)((outer - 1) & 1u);
+            pl = PL0 + (int)(outer & 1u);
+            ch_pos = CH_MIDP1;
+            rbuf = 0;
+            list = 0;
+            prev_list = (unsigned int)pl_r;
+            prev_n = ch_n_pl;
+            prev_own = prev_n;
+            n = prev_n;
+            s_solo[1] = 0;
+            s_solo[2] = prev_n;
+            __syncthreads();
+            }
             if (threadIdx.x == 0) {  // where the other blocks pick the loop up again
               d.st->solo[0] = n;
               d.st->solo[1] = list;
@@ -1251,6 +1470,18 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               d.st->solo[5] = gr;
               d.st->solo[6] = s_solo[1] & 2u;
               d.st->solo[7] = s_solo[2];
+              d.st->chain[0] = ch_pos;
+              d.st->chain[1] = outer;
+              d.st->chain[2] = prog_prev;
+              d.st->chain[3] = ch_n_pl;
+              d.st->chain[4] = ch_stop;
+              if (ch_pos != CH_NONE) {
+                // the grid's next entry test reads the count of the last completed round; its next scan adds into the
+                // other slot (a stretch's own scans do not count)
+                const unsigned int done = ch_pos == CH_DONE ? outer : outer - 1u;
+                d.st->p2_open_n[done & 1u] = ch_list_n;
+                d.st->p2_open_n[(done + 1u) & 1u] = 0;
+              }
             }
           }
           grid_sync_flip(d.barrier + 64);
@@ -1262,6 +1493,22 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           gr = __ldcg(&d.st->solo[5]);
           const unsigned int hv = __ldcg(&d.st->solo[6]);
           const unsigned int sdn = __ldcg(&d.st->solo[7]);
+          const unsigned int ch = __ldcg(&d.st->chain[0]);
+          if (ch != CH_NONE) {  // block 0 went on into later outer rounds
+            outer = __ldcg(&d.st->chain[1]);
+            prog_prev = __ldcg(&d.st->chain[2]);
+            pl_r = PL0 + (int)((outer - 1) & 1u);
+            pl = PL0 + (int)(outer & 1u);
+            if (ch == CH_DONE) {  // ... and finished the phases of round `outer`
+              n_pl = __ldcg(&d.st->chain[3]);
+              stop = __ldcg(&d.st->chain[4]) != 0;
+              chain_done = true;
+              round = 0;
+              PROF(7);
+              break;
+            }
+            refresh_live();  // the phases of the rounds in between may have latched IsZero pairs
+          }
           PROF(7);
           if (n == 0) break;
           if (round >= max_rounds) {
@@ -1518,6 +1765,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       }
       rounds_total += round;
     }
+    if (!chain_done) {
     // =============================== P2: linear systems (:1357-1417) ===============================
     // candidate scan over the rows that can still fire (state is at the P1 fixpoint, in both buffers)
 #ifdef ECNE_PROFILE
@@ -1537,6 +1785,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       {
         const uint32_t n_words = (d.N + 31u) / 32u;
         const uint32_t gw = blockIdx.x * warps_per_block + warp_in_block, nw = gridDim.x * warps_per_block;
+        unsigned int open_left = 0;  // rows this warp leaves open (lane 0)
         for (uint32_t wi = gw; wi < n_words; wi += 2 * nw) {
           uint32_t open[2];
           InlineRow rr[2];
@@ -1563,11 +1812,16 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
             if (mine[h]) close = p2_scan_short(d, pl, (wi + (uint32_t)h * nw) * 32u + lane, rr[h], ff[h]);
             const uint32_t cm = __ballot_sync(0xffffffffu, close);
             if (lane == 0 && open[h]) {
+              open_left += (unsigned int)__popc(open[h] & ~cm);
               if (cm) d.p2_open[wi + (uint32_t)h * nw] = open[h] & ~cm;
               if (d.rank == 0) evals += (unsigned int)__popc(open[h]);  // one visit of the sweep per open row (:1359)
+#ifdef ECNE_PROFILE
+              if (outer < 40) atomicAdd(d.prof + 28000 + 40 * 148 * 4 + 48 + outer, (unsigned long long)__popc(open[h]));
+#endif
             }
           }
         }
+        if (lane == 0 && open_left) atomicAdd(&d.st->p2_open_n[outer & 1u], open_left);
       }
 #ifdef ECNE_PROFILE
       pz1 = clock64();
@@ -1613,7 +1867,10 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         d.h_cnt[slot] = 0;
         d.h_head[slot] = 0;
       }
-      if (tid == 0) d.st->p2_cand = 0;
+      if (tid == 0) {
+        d.st->p2_cand = 0;
+        d.st->p2_open_n[(outer + 1u) & 1u] = 0;  // the next round's scan counts the rows it leaves open here
+      }
       if (p3_round)
         for (uint32_t i = tid; i < d.n_p3; i += nthreads) p3_claim_row(d, d.p3_rows[i]);
     }
@@ -1624,7 +1881,14 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       if (p3_round)
         for (uint32_t i = tid; i < d.n_p3; i += nthreads) p3_commit_row(d, pl, d.p3_rows[i]);
       bool fired = false;
-      for (uint32_t i = tid; i < d.n_p4; i += nthreads) fired |= p4_row(d, pl, d.p4_rows[i]);
+      for (uint32_t i = tid; i < d.n_p4; i += nthreads) {
+#ifdef ECNE_PROFILE
+        const uint32_t r_ = d.p4_rows[i];
+        if (outer < 40 && !(d.solved[r_] & 1) && !(ld_flag(d.F[0], d.aux[r_].w4) & WF_U))
+          atomicAdd(d.prof + 28000 + 40 * 148 * 4 + 88 + outer, 1ULL);
+#endif
+        fired |= p4_row(d, pl, d.p4_rows[i]);
+      }
       if (fired) atomicAdd(&d.st->p4_fired, 1u);
     }
     const unsigned int n_y = sync_and_load(d, d.rec_count + pl);
@@ -1652,15 +1916,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       if (tid == 0) raise(d, ECNE_E_NOCONVERGE);
       stop = true;
     }
-    // rows latched by P4 leave the live masks (equation_solved, :820-822)
-    const unsigned int p4f = __ldcg(&d.st->p4_fired);
-    if (!stop && p4f != p4_seen) {
-      p4_seen = p4f;
-      for (LiveMask m = live; m.any();) {
-        const int k = m.pop_nonempty();
-        if (d.solved[d.row_lo + tid + (uint32_t)k * nthreads] & 1) live.clear(k);
-      }
-    }
+    }  // !chain_done
+    if (!stop) refresh_live();
   }
   if (ack_pending && threadIdx.x == 0) cross_gpu_wait_acks(d, ack_pending);  // the next solve rewrites the lists
   // ---- statistics: one atomic per warp ---------------------------------------------------------------

@@ -1238,6 +1238,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     CK(A.alloc(&d.p2_slot, N));
     CK(A.alloc(&d.p2_k, N));
     CK(A.alloc(&d.p2_open, (N + 31) / 32 + 1));
+    CK(A.alloc(&d.p2_list, (size_t)CH_LIST_CAP + CH_LONG_MAX));
   }
 
   // ---- wire state, records, scratch -----------------------------------------------------------
@@ -1259,8 +1260,8 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(A.alloc(&d.bnd_flag, 8));
   CK(A.alloc(&d.c5sig, N));
   CK(A.alloc(&d.barrier, 128));
-  CK(A.alloc(&d.prof, (size_t)28000 + 40 * 148 * 4 + 64));
-  CK(cudaMemsetAsync(d.prof, 0, ((size_t)28000 + 40 * 148 * 4 + 64) * sizeof(unsigned long long), s));
+  CK(A.alloc(&d.prof, (size_t)28000 + 40 * 148 * 4 + 128));
+  CK(cudaMemsetAsync(d.prof, 0, ((size_t)28000 + 40 * 148 * 4 + 128) * sizeof(unsigned long long), s));
   CK(A.alloc(&d.st, 1));
   CK(A.alloc(&d.p2_row, N));
   CK(A.alloc(&R->d_ubits, (V + 63) / 64));

@@ -415,3 +415,45 @@ def test_inconsistent_compact_form_is_refused(damage):
     st, res = gpu_solve(reduced, specials, main, secp)
     assert st == 0
     check_against_gold("root/poseidon", res)
+
+
+# ---- chain stretches: block 0 runs whole outer rounds alone (kernels.cu, engine knob "chain_open_max") --------------
+CHAIN_CONFIGS = ["secp256k1+bmmp+blt", "tornado/withdraw+pedersen", "tornado/commitHasher+pedersen", "root/bigmult86_3",
+                 "root/bigmultmodp", "root/poseidon", "root/multiplexer_33", "circomlib/EdDSAPoseidonVerifier@eddsaposeidon",
+                 "circomlib/Bits2Point_Strict@pointbits", "tornado/merkleTree", "target/division"]
+
+
+def _solve_with_chain(name, chain_open_max):
+    lib = api._engine()
+    assert lib.ecne_set_option(b"chain_open_max", chain_open_max) == 0
+    try:
+        (reduced, specials, main), secp = prepare(name)
+        st, res = gpu_solve(reduced, specials, main, secp)
+        assert st == GOLD[name].get("status", 0), lib.ecne_last_error()
+        if st == 0:
+            check_against_gold(name, res)
+        return st, res
+    finally:
+        lib.ecne_set_option(b"chain_open_max", 4096)
+
+
+@pytest.mark.parametrize("name", CHAIN_CONFIGS)
+def test_chain_stretch_does_not_change_the_result(name):
+    """Once the linear-system sweep has few rows left, ONE block runs whole outer rounds (P0, Jacobi rounds, P2, P4)
+    behind block barriers.  Never (0) or as early as the engine allows (8192): the goldens, and the same number of
+    outer and Jacobi rounds either way (same operations in the same order; only who executes them differs)."""
+    st0, r0 = _solve_with_chain(name, 0)
+    st1, r1 = _solve_with_chain(name, 8192)
+    assert st0 == st1
+    if st0 == 0:
+        assert (r0.c.outer_rounds, r0.c.inner_rounds) == (r1.c.outer_rounds, r1.c.inner_rounds)
+        assert r0.unique_bytes() == r1.unique_bytes() and r0.known_bytes() == r1.known_bytes()
+
+
+@pytest.mark.parametrize("name", ["ecdsa+secp256k1", "ecdsa"])
+def test_chain_stretch_full_size(name):
+    st0, r0 = _solve_with_chain(name, 0)
+    st1, r1 = _solve_with_chain(name, 4096)
+    assert st0 == st1 == 0
+    assert (r0.c.outer_rounds, r0.c.inner_rounds) == (r1.c.outer_rounds, r1.c.inner_rounds)
+    assert r0.unique_bytes() == r1.unique_bytes() and r0.known_bytes() == r1.known_bytes()
