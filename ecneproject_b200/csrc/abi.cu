@@ -719,12 +719,19 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
             S.prof[0], S.dense_rounds, S.prof[1], S.rounds - S.dense_rounds, S.prof[2], S.prof[3], S.prof[4], S.prof[5],
             S.prof[6], S.prof[7], S.outer, S.n_cand_total, S.n_cand_max, S.dense_evals, S.evals);
     if (atoi(getenv("ECNE_DEBUG_PROF")) > 2) {
-      std::vector<unsigned long long> pr(28000 + 40 * 148 * 4 + 128);
+      std::vector<unsigned long long> pr(28000 + 40 * 148 * 4 + 160);
       cudaMemcpy(pr.data(), d.prof, pr.size() * 8, cudaMemcpyDeviceToHost);
       {
         const unsigned long long* q = pr.data() + 28000 + 40 * 148 * 4;
         fprintf(stderr, "[long row] slowest evaluation (maxima, cycles from entry): total %llu | gather %llu | cases 1-4 %llu | case 5 %llu | "
                         "case 6 scan %llu | firing done %llu\n", q[0], q[1], q[2], q[3], q[4], q[5]);
+      }
+      {
+        const unsigned long long* q = pr.data() + 28000 + 40 * 148 * 4 + 128;
+        fprintf(stderr, "[warp solo stages] slowest lane per batch, summed: row record + latch %llu | state gather %llu | inline evaluation (incl. its emits) %llu | "
+                        "generic evaluator %llu (%llu rows)\n", q[8], q[9], q[10], q[11], q[12]);
+        fprintf(stderr, "[warp solo] %llu stretches, %llu rounds, %llu cycles | %llu pair batches, %llu (record, row) pairs | %llu long rows "
+                        "evaluated in %llu cycles (cumulative over the solves of this handle)\n", q[6], q[5], q[4], q[2], q[3], q[1], q[0]);
       }
       fprintf(stderr, "[phases] n_p3 %u n_p4 %u | open rows seen by the P2 scan / P4 rows with a non-unique vk, per outer round:", d.n_p3, d.n_p4);
       for (int o = 1; o < 40; ++o)

@@ -128,6 +128,9 @@ struct Dev {
   uint32_t N, V, nnz, n_long, n_specials, n_known, n_targets, n2a, n2b, table_n;
   uint32_t r0, r1, rpm1;  // ranks of 0, 1, p-1
   int secp_solve;
+  // secp_solve: some (BigMultModP, BigLessThan) pair lies in the same sets of the equal-wire DSU (:634-678, built at
+  // set-up, csrc/setup.cu k_dsu_*) while the BigLessThan has no output: `constraint_j[3][1]` is a BoundsError (:768)
+  int p0p_bounds;
   // rows
   const uint32_t* seg;
   const uint32_t* col;

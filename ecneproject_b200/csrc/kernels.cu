@@ -460,7 +460,7 @@ __device__ __noinline__ void phase_p0(const Dev&, int pl, SpecialsCache& sc) {
           return;
         }
         uint32_t ni = d.sp_in_ptr[i + 1] - d.sp_in_ptr[i], nj = d.sp_in_ptr[j + 1] - d.sp_in_ptr[j];
-        if (ni < 9 || nj < 6) {
+        if (ni < 9 || nj < 6 || d.p0p_bounds) {  // (both BoundsErrors abort the solve: which pair raises first is not observable)
           raise(d, ECNE_E_BOUNDS);
           return;
         }
@@ -853,8 +853,15 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
   unsigned int qr = 0;         // queue read this round (fast path); the round writes queue qr ^ 1
   unsigned int prog_acc = 0;
   uint32_t replay_sink = 0;    // consumes the results of the replay atomics (see above)
+#ifdef ECNE_PROFILE
+  const long long wz0 = clock64();
+  unsigned int wrounds = 0;
+#endif
   while (true) {
     gr += 1;
+#ifdef ECNE_PROFILE
+    wrounds += 1;
+#endif
     const int wbuf = rbuf ^ 1;
     const int rb = fast ? (rbuf | ST_TAG_CG) : rbuf;
     const unsigned int qw = qr ^ 1u;
@@ -909,6 +916,10 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
       const unsigned int q = p - __shfl_sync(0xffffffffu, excl, j);
       uint32_t row = 0xffffffffu;
       bool is_long = false;
+#ifdef ECNE_PROFILE
+      long long sz0 = clock64(), sz1 = sz0, sz2 = sz0, sz3 = sz0, sz4 = sz0;
+      bool was_generic = false;
+#endif
       if (p < total) {
         if (q == 0) row = hy;
         else if (q == 1) row = hz;
@@ -920,6 +931,9 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
           const uint32_t latched = __ldcg(d.solved + row);
           InlineRow ir;
           unpack_row(q0v, q1v, ir);
+#ifdef ECNE_PROFILE
+          sz1 = clock64() + (ir.rf & 0) + (latched & 0);
+#endif
           if (ir.rf & RF_LONG) {
             const uint32_t li = ir.c[0];
             is_long = !__ldcg(d.long_done + li) && atomicExch(d.long_stamp + li, gr) != gr;
@@ -927,12 +941,41 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
             uint32_t f[ROWREC_INLINE];
             gather_row(st_F(rb), ir, f);
             ev += 1;
-            if (eval_inline(d, rb, wbuf, elist, row, ir, f, bepoch) & EI_GENERIC)
+#ifdef ECNE_PROFILE
+            sz2 = clock64() + (f[0] & 0) + (f[1] & 0) + (f[2] & 0);
+#endif
+            const uint32_t ei = eval_inline(d, rb, wbuf, elist, row, ir, f, bepoch);
+#ifdef ECNE_PROFILE
+            sz3 = clock64() + (ei & 0);
+            was_generic = (ei & EI_GENERIC) != 0;
+#endif
+            if (ei & EI_GENERIC)
               eval_row<1>(d, rb, wbuf, elist, row, bepoch);
           }
         }
+#ifdef ECNE_PROFILE
+        sz4 = clock64();
+#endif
       }
+#ifdef ECNE_PROFILE
+        {
+          unsigned long long* q = d.prof + 28000 + 40 * 148 * 4 + 128;
+          // slowest lane of the batch, stage by stage
+          const unsigned int a = __reduce_max_sync(0xffffffffu, (unsigned int)(sz1 - sz0));
+          const unsigned int b = __reduce_max_sync(0xffffffffu, (unsigned int)(sz2 > sz1 ? sz2 - sz1 : 0));
+          const unsigned int c = __reduce_max_sync(0xffffffffu, (unsigned int)(sz3 > sz2 ? sz3 - sz2 : 0));
+          const unsigned int g = __reduce_max_sync(0xffffffffu, (unsigned int)(was_generic ? sz4 - sz3 : 0));
+          const unsigned int ng = __popc(__ballot_sync(0xffffffffu, was_generic));
+          if (lane == 0) {
+            q[8] += a; q[9] += b; q[10] += c; q[11] += g; q[12] += ng;
+          }
+        }
+#endif
       unsigned int m = __ballot_sync(0xffffffffu, is_long);
+#ifdef ECNE_PROFILE
+      const long long lz0 = clock64();
+      const unsigned int lm0 = m;
+#endif
       while (m) {
         const int src = __ffs((int)m) - 1;
         m &= m - 1;
@@ -943,6 +986,15 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
           if (done) d.long_done[d.rec[lrow].c[0]] = 1;
         }
       }
+#ifdef ECNE_PROFILE
+      if (lane == 0) {
+        unsigned long long* q = d.prof + 28000 + 40 * 148 * 4 + 128;
+        q[0] += (unsigned long long)(clock64() - lz0);  // cycles in long rows
+        q[1] += (unsigned long long)__popc(lm0);        // long rows evaluated
+        q[2] += 1;                                       // pair batches
+        q[3] += total > base + 32 ? 32 : total - base;   // (record, row) pairs
+      }
+#endif
     }
     if (have && !fast) {  // the replay
       apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
@@ -1023,6 +1075,14 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
       qr = qw;
     }
   }
+#ifdef ECNE_PROFILE
+  if (lane == 0) {
+    unsigned long long* q = d.prof + 28000 + 40 * 148 * 4 + 128;
+    q[4] += (unsigned long long)(clock64() - wz0);
+    q[5] += wrounds;
+    q[6] += 1;
+  }
+#endif
   *evals_io += ev;
   if (lane == 0) {
     st->n = n;

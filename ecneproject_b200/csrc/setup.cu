@@ -760,6 +760,69 @@ static cudaError_t h2d(T* dst, const T* src, size_t n, cudaStream_t s) {
 }
 static inline unsigned int nb(uint64_t n, unsigned int t) { return (unsigned int)((n + t - 1) / t); }
 
+// ---- the disjoint sets of equal wires (:634-678), secp_solve only -----------------------------------------------------
+// `DataStructures.IntDisjointSet(num_variables)` + one pushed element per distinct constant: rows `x - y = 0` (stored
+// C values exactly {1, p-1}, A and B without non-zero keys) unite their two keys, rows `a x = b` (two stored C keys,
+// one of them the constant wire) unite x with the element of the value b/a — here node V + 1 + rank(value), equal
+// values share a rank.  Lock-free union-find: the larger root is linked under the smaller with a CAS.  Its only
+// readers are the six in_same_set calls per (BigMultModP, BigLessThan) pair (:761-765), whose only observable effect
+// is the BoundsError of `constraint_j[3][1]` when the sets agree and the BigLessThan has no output (:768); building
+// the sets can raise BoundsErrors of its own on rows with stored zeros (`l[1]` / `l[2]`, :660-662).
+__device__ __forceinline__ uint32_t dsu_find(uint32_t* parent, uint32_t x) {
+  while (true) {
+    const uint32_t p = *((volatile uint32_t*)(parent + x));
+    if (p == x) return x;
+    x = p;
+  }
+}
+__device__ __forceinline__ void dsu_union(uint32_t* parent, uint32_t a, uint32_t b) {
+  while (true) {
+    a = dsu_find(parent, a);
+    b = dsu_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      const uint32_t t = a;
+      a = b;
+      b = t;
+    }
+    if (atomicCAS(parent + a, a, b) == a) return;  // a was still a root: now under the smaller root b
+  }
+}
+__global__ void k_dsu_union(Raw r, const uint32_t* rflags, const RowAux* aux, uint32_t* parent, unsigned int* flags) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r.N) return;
+  const uint32_t rf = rflags[row];
+  if (!(rf & RF_LINEAR)) return;                                        // (:640) nonzeroKeys of a and b are empty
+  if (r.seg[3ull * row + 3] - r.seg[3ull * row + 2] != 2) return;       // length(eq.c): STORED keys (:641)
+  bool bad = false;
+  CScan cs;
+  scan_c(r, row, cs, bad);
+  if (bad) return;
+  if (cs.n_one == 1 && cs.n_mone == 1) {  // sorted values == [1, p - 1] (:642-649)
+    dsu_union(parent, cs.key_one, cs.key_mone);
+    return;
+  }
+  if (cs.nC == 0 || (cs.nC == 1 && cs.n_non1 == 0)) {  // `l[1]` of an empty list / `l[2]` of [1] (:660-662)
+    flags[0] = 1;
+    return;
+  }
+  if (cs.nC == 2 && cs.n_non1 == 1)  // one key is the constant wire (:656-657): x ~ value (rank of -c1/cx, k_fill_ranks)
+    dsu_union(parent, cs.x, r.V + 1u + aux[row].rank_a);
+}
+__global__ void k_dsu_pairs(uint32_t n_sp, const int32_t* kind, const uint32_t* in_ptr, const uint32_t* in,
+                            const uint32_t* out_ptr, uint32_t* parent, unsigned int* flags) {
+  const uint64_t pr = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pr >= (uint64_t)n_sp * n_sp) return;
+  const uint32_t i = (uint32_t)(pr / n_sp), j = (uint32_t)(pr % n_sp);
+  if (kind[i] != ECNE_SPECIAL_BIGMULTMODP || kind[j] != ECNE_SPECIAL_BIGLESSTHAN) return;
+  if (in_ptr[i + 1] - in_ptr[i] < 9 || in_ptr[j + 1] - in_ptr[j] < 6) return;  // BoundsError raised by the solve kernel
+  if (out_ptr[j + 1] != out_ptr[j]) return;                                     // constraint_j[3][1] exists
+  bool same = true;
+  for (uint32_t k = 0; k < 6; ++k)
+    same &= dsu_find(parent, in[in_ptr[i] + 3 + k]) == dsu_find(parent, in[in_ptr[j] + k]);
+  if (same) flags[1] = 1;
+}
+
 // ---- the rows of a host problem into device arrays of the on-disk layout ------------------------------------------
 // Full form: three copies.  Compact form (include/ecne_abi.h, `coef == NULL`): one class byte per term and the 32-byte
 // values of the terms that are not 0, 1 or p - 1 cross PCIe; two kernels write the same `coef` array the full form
@@ -1260,8 +1323,8 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(A.alloc(&d.bnd_flag, 8));
   CK(A.alloc(&d.c5sig, N));
   CK(A.alloc(&d.barrier, 128));
-  CK(A.alloc(&d.prof, (size_t)28000 + 40 * 148 * 4 + 128));
-  CK(cudaMemsetAsync(d.prof, 0, ((size_t)28000 + 40 * 148 * 4 + 128) * sizeof(unsigned long long), s));
+  CK(A.alloc(&d.prof, (size_t)28000 + 40 * 148 * 4 + 160));
+  CK(cudaMemsetAsync(d.prof, 0, ((size_t)28000 + 40 * 148 * 4 + 160) * sizeof(unsigned long long), s));
   CK(A.alloc(&d.st, 1));
   CK(A.alloc(&d.p2_row, N));
   CK(A.alloc(&R->d_ubits, (V + 63) / 64));
@@ -1269,6 +1332,26 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(A.alloc(&R->d_counts, 4));
 
   cudaStreamWaitEvent(s, ev_join, 0);  // the timing event below covers the side chain too
+  // the disjoint sets of equal wires and their one observable use (:634-678, :760-768)
+  unsigned int* d_dsu_flags = nullptr;
+  unsigned int h_dsu_flags[2] = {0, 0};
+  if (p->secp_solve && N) {
+    uint32_t* d_parent;
+    CK(tmp.alloc(&d_parent, V + 1 + (size_t)nc));
+    CK(tmp.alloc(&d_dsu_flags, 2));
+    CK(cudaMemsetAsync(d_dsu_flags, 0, 2 * sizeof(unsigned int), s));
+    k_iota<<<nb(V + 1 + (uint64_t)nc, 256), 256, 0, s>>>(d_parent, (uint32_t)(V + 1 + nc));
+    k_dsu_union<<<nb(N, 128), 128, 0, s>>>(raw, d_rflags, d_aux, d_parent, d_dsu_flags);
+    bool has_m = false, has_l = false;
+    for (uint64_t i = 0; i < n_sp; ++i) {
+      has_m |= p->sp_kind[i] == ECNE_SPECIAL_BIGMULTMODP;
+      has_l |= p->sp_kind[i] == ECNE_SPECIAL_BIGLESSTHAN;
+    }
+    if (has_m && has_l)
+      k_dsu_pairs<<<nb(n_sp * n_sp, 128), 128, 0, s>>>((uint32_t)n_sp, d_sp_kind, d_sp_in_ptr, d_sp_in, d_sp_out_ptr, d_parent,
+                                                       d_dsu_flags);
+    CK(cudaMemcpyAsync(h_dsu_flags, d_dsu_flags, sizeof(h_dsu_flags), cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaMemcpyAsync(&h_rank[0], d_rank_of + 0, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&h_rank[1], d_rank_of + 1, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&h_rank[2], d_rank_of + 254, 4, cudaMemcpyDeviceToHost, s));
@@ -1280,6 +1363,11 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   cudaEventDestroy(ev_join);
   cudaEventDestroy(ev_c3);
   cudaEventDestroy(ev_long);
+  if (h_dsu_flags[0]) {
+    err = "BoundsError: a row with two stored C keys and fewer than two usable ones in the disjoint-set construction (:660-662)";
+    return ECNE_E_BOUNDS;
+  }
+  d.p0p_bounds = h_dsu_flags[1] ? 1 : 0;
   d.r0 = h_rank[0];
   d.r1 = h_rank[1];
   d.rpm1 = h_rank[2];

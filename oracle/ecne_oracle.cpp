@@ -102,6 +102,66 @@ struct Solver {
   uint64_t steps = 0, pops = 0, sweep_visits = 0, outer = 0;
   uint64_t fired[16] = {0};
 
+  // ---- the disjoint sets of equal wires (:634-678), built under secp_solve only -----------------------
+  // DataStructures.IntDisjointSet(num_variables) + one pushed element per distinct constant; its only readers are the
+  // in_same_set calls of the BigMultModP x BigLessThan rule (:761-765).
+  std::vector<uint32_t> dsu_parent;
+  bool have_dsu = false;
+  uint32_t dsu_find(uint32_t x) {
+    while (dsu_parent[x] != x) {
+      dsu_parent[x] = dsu_parent[dsu_parent[x]];
+      x = dsu_parent[x];
+    }
+    return x;
+  }
+  void dsu_union(uint32_t a, uint32_t b) {
+    a = dsu_find(a);
+    b = dsu_find(b);
+    if (a != b) dsu_parent[a > b ? a : b] = a > b ? b : a;
+  }
+  void build_dsu() {
+    const uint64_t V = prob->n_vars;
+    dsu_parent.resize(V + 1);
+    for (uint64_t i = 0; i <= V; ++i) dsu_parent[i] = (uint32_t)i;
+    std::map<std::vector<uint64_t>, uint32_t> const_vals;  // value -> pushed element
+    const U256 PM1 = fsub(ZERO, ONE);
+    for (const Row& r : rows) {
+      if (!r.nza.empty() || !r.nzb.empty()) continue;  // (:640)
+      if (r.c.size() != 2) continue;                    // length(eq.c): stored keys, zeros included (:641)
+      const U256 &v0 = r.c[0].c, &v1 = r.c[1].c;
+      const bool xy = (cmp(v0, ONE) == 0 && cmp(v1, PM1) == 0) || (cmp(v0, PM1) == 0 && cmp(v1, ONE) == 0);  // (:642-644)
+      if (xy) {
+        dsu_union(r.nzc[0], r.nzc[1]);  // both stored values are non-zero (:645-649)
+        continue;
+      }
+      // "ax == b" (:650-675): l = nonzeroKeys(eq.c)
+      const std::vector<uint32_t>& l = r.nzc;
+      if (l.empty()) throw OracleError{ECNE_E_BOUNDS, "BoundsError: l[1] of an empty key list (:660)"};
+      bool constant_val = false;
+      for (uint32_t k : l) constant_val |= k == 1;
+      uint32_t non_one = l[0];
+      if (l[0] == 1) {
+        if (l.size() < 2) throw OracleError{ECNE_E_BOUNDS, "BoundsError: l[2] of a one-key list (:662)"};
+        non_one = l[1];
+      }
+      if (!constant_val) continue;
+      U256 c1 = ZERO, cx = ZERO;
+      for (const Term& t : r.c) {
+        if (t.key == 1) c1 = t.c;
+        if (t.key == non_one) cx = t.c;
+      }
+      const U256 value = divexact(c1, fneg(cx));  // (:668)
+      std::vector<uint64_t> key(value.l, value.l + 4);
+      auto it = const_vals.find(key);
+      if (it == const_vals.end()) {
+        dsu_parent.push_back((uint32_t)dsu_parent.size());  // push!(dsu)
+        it = const_vals.emplace(key, (uint32_t)dsu_parent.size() - 1).first;
+      }
+      dsu_union(non_one, it->second);
+    }
+    have_dsu = true;
+  }
+
   void enqueue(uint32_t w) {  // the pattern at :861-866
     for (uint32_t r : v2rows[w])
       if (!in_queue[r]) {
@@ -163,6 +223,7 @@ struct Solver {
     v2rows.assign(V + 1, {});
     for (uint64_t i = 0; i < N; ++i)
       for (uint32_t w : rows[i].vars) v2rows[w].push_back((uint32_t)i);
+    if (prob->secp_solve) build_dsu();  // (:634-678)
     // initial states (:680-693)
     for (uint64_t k = 0; k < prob->n_known; ++k) {
       uint32_t w = prob->known[k];
@@ -590,6 +651,13 @@ struct Solver {
         uint64_t ni = p->sp_in_ptr[i + 1] - p->sp_in_ptr[i];
         uint64_t nj = p->sp_in_ptr[j + 1] - p->sp_in_ptr[j];
         if (ni < 9 || nj < 6) throw OracleError{ECNE_E_BOUNDS, "BoundsError: special inputs (:762)"};
+        bool same_set = true;  // (:760-766)
+        for (uint64_t k = 0; k < 6; ++k)
+          if (dsu_find(p->sp_in[p->sp_in_ptr[i] + 3 + k]) != dsu_find(p->sp_in[p->sp_in_ptr[j] + k])) same_set = false;
+        // `variable_states[constraint_j[3][1]].values` (:768): a BigLessThan without outputs; what follows in the
+        // branch are loops of `continue` statements without effect (:769-783)
+        if (same_set && p->sp_out_ptr[j + 1] == p->sp_out_ptr[j])
+          throw OracleError{ECNE_E_BOUNDS, "BoundsError: constraint_j[3][1] of a BigLessThan without outputs (:768)"};
         for (uint64_t k = 0; k < 3; ++k) {  // constraint_j[2][1:3] (:785)
           uint32_t w = p->sp_in[p->sp_in_ptr[j] + k];
           if (vs[w].U) continue;

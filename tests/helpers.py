@@ -80,3 +80,25 @@ def py_read_r1cs(path):
     known = [1] + list(range(2 + pub_out, 2 + pub_out + pub_in + prv_in))
     targets = list(range(2, 2 + pub_out))
     return rows, known, targets, n_wires + 1
+
+
+def dsu_system(link, zero_out=True, extra_rows=()):
+    """BigMultModP inputs 5..13, BigLessThan inputs 15..20 (+ no output when zero_out).  `link` makes
+    inputs[4:9] of the first and inputs[1:6] of the second the same sets in three different ways."""
+    rows = [({2: 1}, {3: 1}, {4: 1})]
+    for k in range(6):
+        a, b = 8 + k, 15 + k                         # constraint_i[2][k+3], constraint_j[2][k]  (1-based k = 1..6)
+        if link == "xy":
+            rows.append(({}, {}, {a: 1, b: -1}))         # a - b = 0
+        elif link == "chain":
+            rows.append(({}, {}, {a: -1, 22 + k: 1}))    # a = t, t = b through a third wire
+            rows.append(({}, {}, {22 + k: 1, b: -1}))
+        elif link == "const":
+            rows.append(({}, {}, {1: -(7 + k), a: 1}))   # a = 7 + k and 3 b = 3 (7 + k): both equal the same constant
+            rows.append(({}, {}, {1: -3 * (7 + k), b: 3}))
+        elif link == "none":
+            rows.append(({}, {}, {a: 1, b: -1, 29: 0}))  # three stored keys: not looked at by the construction
+    rows += list(extra_rows)
+    m = MiniR1CS(rows, n_vars=30, known=[1, 2, 3], targets=[4])
+    sp = [("BigMultModP", list(range(5, 14)), [14]), ("BigLessThan", list(range(15, 21)), [] if zero_out else [21])]
+    return m, sp

@@ -15,7 +15,7 @@ import pytest
 
 from configs import CONFIGS
 from ecneproject_b200 import _abi, api, fixtures
-from helpers import MiniR1CS, P
+from helpers import MiniR1CS, P, dsu_system as _dsu_system
 import oracle_lib
 
 pytestmark = pytest.mark.gpu
@@ -457,3 +457,40 @@ def test_chain_stretch_full_size(name):
     assert st0 == st1 == 0
     assert (r0.c.outer_rounds, r0.c.inner_rounds) == (r1.c.outer_rounds, r1.c.inner_rounds)
     assert r0.unique_bytes() == r1.unique_bytes() and r0.known_bytes() == r1.known_bytes()
+
+
+# ---- the disjoint sets of equal wires (:634-678) and their one observable use (:760-768) ---------------------------
+@pytest.mark.parametrize("link", ["xy", "chain", "const"])
+def test_dsu_same_sets_and_a_biglessthan_without_outputs_is_a_bounds_error(link):
+    m, sp = _dsu_system(link, zero_out=True)
+    st, _, ost, _ = both(m, sp, secp=True)
+    assert st == ost == _abi.ECNE_E_BOUNDS
+    m, sp = _dsu_system(link, zero_out=False)        # with an output the branch has no effect (:769-783)
+    st, g, ost, o = both(m, sp, secp=True)
+    assert st == ost == 0 and g.unique_bytes() == o.unique_bytes() and g.known_bytes() == o.known_bytes()
+
+
+def test_dsu_different_sets_raise_nothing():
+    m, sp = _dsu_system("none", zero_out=True)
+    st, g, ost, o = both(m, sp, secp=True)
+    assert st == ost == 0 and g.unique_bytes() == o.unique_bytes()
+    # five of six pairs linked: still not the same sets
+    m, sp = _dsu_system("xy", zero_out=True)
+    m2 = MiniR1CS([({2: 1}, {3: 1}, {4: 1})] + [({}, {}, {8 + k: 1, 15 + k: -1}) for k in range(5)], 30, [1, 2, 3], [4])
+    st, g, ost, o = both(m2, sp, secp=True)
+    assert st == ost == 0 and g.unique_bytes() == o.unique_bytes()
+
+
+@pytest.mark.parametrize("row", [({}, {}, {5: 0, 6: 0}),      # two stored zeros: l = [] -> l[1]
+                                 ({}, {}, {1: 4, 6: 0})])     # l = [1] -> l[2]
+def test_dsu_construction_bounds_errors(row):
+    m = MiniR1CS([({2: 1}, {3: 1}, {4: 1}), row], n_vars=8, known=[1, 2, 3], targets=[4])
+    st, _, ost, _ = both(m, secp=True)
+    assert st == ost == _abi.ECNE_E_BOUNDS
+    st, g, ost, o = both(m, secp=False)               # the sets are only built under secp_solve (:634)
+    assert st == ost                                   # (an all-zero row is a BoundsError of Case 2a either way, :916)
+    if st == 0:
+        assert g.unique_bytes() == o.unique_bytes()
+    ok = MiniR1CS([({2: 1}, {3: 1}, {4: 1}), ({}, {}, {5: 3, 6: 0})], n_vars=8, known=[1, 2, 3], targets=[4])
+    st, g, ost, o = both(ok, secp=True)               # l = [5], no constant: `continue` (:664-666)
+    assert st == ost == 0 and g.unique_bytes() == o.unique_bytes()

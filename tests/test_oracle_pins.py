@@ -71,3 +71,28 @@ def test_secp_without_secp_solve_throws():
     with pytest.raises(oracle_lib.OracleError) as e:
         oracle_lib.solve(reduced, specials, main.known, main.targets, main.n_vars, False)
     assert e.value.status == -4
+
+
+def test_oracle_disjoint_sets_of_equal_wires():
+    """The oracle's restatement of :634-678 and of its one observable use (:760-768): same sets + a BigLessThan without
+    outputs is a BoundsError; building the sets raises BoundsErrors of its own on rows with stored zeros."""
+    from helpers import MiniR1CS, dsu_system
+    import oracle_lib
+
+    def status(m, sp, secp):
+        try:
+            oracle_lib.solve(m, sp, m.known, m.targets, m.n_vars, secp)
+            return 0
+        except oracle_lib.OracleError as e:
+            return e.status
+
+    for link in ("xy", "chain", "const"):
+        assert status(*dsu_system(link, True), True) == -3
+        assert status(*dsu_system(link, False), True) == 0
+    assert status(*dsu_system("none", True), True) == 0
+    assert status(*dsu_system("xy", True), False) == -4      # UndefVarError(:dsu) without secp_solve (:762)
+    base = [({2: 1}, {3: 1}, {4: 1})]
+    for row, want in ((({}, {}, {1: 4, 6: 0}), -3), (({}, {}, {5: 3, 6: 0}), 0), (({}, {}, {1: 4, 6: 2}), 0)):
+        m = MiniR1CS(base + [row], n_vars=8, known=[1, 2, 3], targets=[4])
+        assert status(m, [], True) == want
+        assert status(m, [], False) == 0
