@@ -125,7 +125,7 @@ const char* status_text(int st) {
     case ECNE_E_DIVZERO: return "DivideError: divexact by zero (R1CSConstraintSolver.jl:919-920 / :1467)";
     case ECNE_E_BOUNDS: return "BoundsError (R1CSConstraintSolver.jl:916 variable_states[-1] / :762)";
     case ECNE_E_NODSU: return "UndefVarError: dsu not defined (R1CSConstraintSolver.jl:762; secp_solve=false)";
-    case ECNE_E_UNSUPPORTED: return "a linear-system group with k > ECNE_P2_KMAX unknowns triggered";
+    case ECNE_E_UNSUPPORTED: return "a linear-system group with k > ECNE_P2_KBIG (16) unknowns triggered";
     case ECNE_E_NOCONVERGE: return "round guard hit: the propagation did not reach a fixpoint";
     case ECNE_E_INTERNAL: return "internal error (record overflow or set-hash collision)";
     default: return "error";

@@ -87,6 +87,7 @@ struct __align__(16) Rec {
 #define VS_2B 0x80000000u  // | tvals index: [t]                  (:967)
 
 #define ECNE_MAX_WORLD 8
+#define P2_BIGQ_CAP 1024u   // big linear-system groups one sweep can queue
 #define CH_LIST_CAP 8192u   // open rows a chain stretch can track
 #define CH_P4_MAX 1024u     // IsZero pairs it accepts
 #define CH_LONG_MAX 2048u   // long rows it accepts
@@ -117,6 +118,7 @@ struct Status {            // device-resident, read back once per solve
   unsigned int solo[8];            // where the grid resumes after block 0 ran rounds alone: n, list, rbuf, round, bepoch, gr
   // rows the linear-system sweep left open, by parity of the outer round that counted them (the other slot is cleared
   // for the next round): block 0 takes whole outer rounds over once this is small (kernels.cu "chain stretch")
+  unsigned int p2_big_n;           // linear-system groups with more than ECNE_P2_KMAX unknowns queued by the resolvers
   unsigned int p2_open_n[2];
   // where the grid resumes after a chain stretch: position (CH_*), outer, prog_prev, n_pl, stop
   unsigned int chain[6];
@@ -179,6 +181,7 @@ struct Dev {
   uint32_t* p2_slot;          // [N] table slot of each candidate
   uint32_t* p2_k;             // [N] size of its unknown set
   uint32_t* p2_open;          // [(N + 31) / 32] bit per row: the linear-system sweep still has to look at it
+  uint32_t* p2_bigq;          // [P2_BIGQ_CAP] candidate index of the resolver of each queued big group
   uint32_t* p2_list;          // [CH_LIST_CAP] the open short rows as a list, while block 0 runs the outer rounds alone
   long long chain_open_max;   // engine knob "chain_open_max": block 0 takes outer rounds over below this many open rows
   uint32_t h_mask;

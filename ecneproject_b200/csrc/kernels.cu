@@ -598,9 +598,197 @@ __device__ __noinline__ void p2_resolve_group(const Dev&, int pl, uint32_t c) {
   if (__ldcg(d.h_head + slot) != c + 1) return;  // not the group's resolver
   const uint32_t cnt = __ldcg(d.h_cnt + slot);
   if (cnt < d.p2_k[c]) return;  // fewer than k rows in the slot (almost every group); k is part of the key
+  if (d.p2_k[c] > ECNE_P2_KMAX) {
+    // more unknowns than the enumeration of k! permutations is good for: queued, and decided by a whole block after the
+    // resolve barrier (p2_big_slot).  The members of a slot share k (it is part of the key), so this is a property of the slot.
+    const unsigned int i = atomicAdd(&d.st->p2_big_n, 1u);
+    if (d.p2_k[c] > ECNE_P2_KBIG || i >= P2_BIGQ_CAP)
+      raise(d, ECNE_E_UNSUPPORTED);
+    else
+      d.p2_bigq[i] = c;
+    return;
+  }
   if (p2_resolve_set(d, pl, c + 1, c + 1, false)) return;
   for (uint32_t m = __ldcg(d.p2_next + c); m != 0; m = __ldcg(d.p2_next + (m - 1)))
     p2_resolve_set(d, pl, c + 1, m, true);
+}
+
+// ---- P2 groups with ECNE_P2_KMAX < k <= ECNE_P2_KBIG unknowns: a whole block per table slot -----------------------------
+// slow_det (:1389-1400) sums the products over the ODD permutations.  With perm(A) = even + odd and det(A) = even - odd,
+// odd = (perm - det) / 2, and the rule only asks whether it is zero (char != 2): perm by Ryser's formula, the 2^k - 1
+// column subsets dealt out over the threads of the block (O(2^k k^2 / threads) additions, 2^k k / threads products — the
+// reference's own enumeration costs k! * k products), det by Gaussian elimination in shared memory.  Everything in
+// Montgomery form.  The member bookkeeping (which rows share the leader's unknown set, the k smallest row ids, one
+// leader per distinct set of the slot) is the logic of p2_resolve_set / p2_resolve_group, run by thread 0.
+struct P2Big {
+  fr::u256 m[ECNE_P2_KBIG * ECNE_P2_KBIG];
+  fr::u256 part[32];
+  uint32_t vars[ECNE_P2_KBIG], best[ECNE_P2_KBIG];
+  uint32_t k, skip;
+  int fire;
+};
+__device__ inline uint32_t p2_big_unknowns(const Dev& d, const uint8_t* F, uint32_t row, uint32_t* vars) {
+  const uint32_t s2 = d.seg[3 * row + 2], s3 = d.seg[3 * row + 3];
+  uint32_t k = 0;
+  for (uint32_t t = s2; t < s3; ++t) {
+    const uint32_t w = d.col[t];
+    if (ld_flag(F, w) & WF_U) continue;
+    if (k < ECNE_P2_KBIG) {
+      uint32_t j = k;  // insertion sort by wire id (:1386)
+      while (j > 0 && vars[j - 1] > w) {
+        vars[j] = vars[j - 1];
+        --j;
+      }
+      vars[j] = w;
+    }
+    ++k;
+  }
+  return k;
+}
+__device__ inline bool p2_big_same_set(const Dev& d, const uint8_t* F, uint32_t row, const uint32_t* vars, uint32_t k) {
+  const uint32_t s2 = d.seg[3 * row + 2], s3 = d.seg[3 * row + 3];
+  uint32_t n = 0;
+  for (uint32_t t = s2; t < s3; ++t) {
+    const uint32_t w = d.col[t];
+    if (ld_flag(F, w) & WF_U) continue;
+    bool found = false;
+    for (uint32_t x = 0; x < k; ++x) found |= vars[x] == w;
+    if (!found) return false;
+    ++n;
+  }
+  return n == k;  // (the keys of a form are distinct)
+}
+__device__ __noinline__ void p2_big_slot(const Dev&, int pl, uint32_t c, P2Big& S) {
+  const Dev& d = c_dev;
+  const uint8_t* F = d.F[0];
+  const uint32_t t = threadIdx.x, nt = blockDim.x, lane = t & 31u, warp = t >> 5;
+  const uint32_t head = c + 1;
+  for (uint32_t leader = head; leader != 0; leader = __ldcg(d.p2_next + (leader - 1))) {
+    if (t == 0) {
+      S.skip = 0;
+      S.fire = 0;
+      const uint32_t k = p2_big_unknowns(d, F, d.p2_row[leader - 1], S.vars);
+      S.k = k;
+      if (k > ECNE_P2_KBIG) {
+        raise(d, ECNE_E_UNSUPPORTED);
+        S.skip = 2;
+      } else {
+        uint32_t nb = 0;
+        bool before_leader = true;
+        for (uint32_t mm = head; mm != 0; mm = __ldcg(d.p2_next + (mm - 1))) {
+          const uint32_t r = d.p2_row[mm - 1];
+          const bool same = mm == leader || p2_big_same_set(d, F, r, S.vars, k);
+          if (mm == leader) before_leader = false;
+          if (!same) continue;
+          if (leader != head && before_leader) {  // an earlier member of the list leads this set
+            S.skip = 1;
+            break;
+          }
+          if (nb < k) {  // keep the k smallest row ids (:1387-1388)
+            uint32_t j = nb++;
+            while (j > 0 && S.best[j - 1] > r) {
+              S.best[j] = S.best[j - 1];
+              --j;
+            }
+            S.best[j] = r;
+          } else if (r < S.best[k - 1]) {
+            uint32_t j = k - 1;
+            while (j > 0 && S.best[j - 1] > r) {
+              S.best[j] = S.best[j - 1];
+              --j;
+            }
+            S.best[j] = r;
+          }
+        }
+        if (!S.skip && nb < k) S.skip = 1;  // fewer than k rows share this unknown set
+      }
+    }
+    __syncthreads();
+    const uint32_t skip = S.skip, k = S.k;
+    if (skip == 2) return;
+    if (skip == 0) {
+      // the matrix: m[j][x] = coefficient of the x-th unknown in the j-th row, Montgomery form
+      for (uint32_t e = t; e < k * k; e += nt) {
+        const uint32_t j = e / k, x = e % k, row = S.best[j], w = S.vars[x];
+        const uint32_t s2 = d.seg[3 * row + 2], s3 = d.seg[3 * row + 3];
+        fr::u256 v = fr::make_u256(0, 0, 0, 0);
+        for (uint32_t q = s2; q < s3; ++q)
+          if (d.col[q] == w) v = d.coef[q];
+        S.m[j * k + x] = fr::to_mont(v);
+      }
+      __syncthreads();
+      // permanent (Ryser): (-1)^k * sum over the non-empty column subsets s of (-1)^|s| * prod_i sum_{j in s} m[i][j]
+      fr::u256 acc = fr::make_u256(0, 0, 0, 0);
+      for (uint32_t sub = t + 1; sub < (1u << k); sub += nt) {
+        fr::u256 prod = fr::mont_one();
+        for (uint32_t i = 0; i < k; ++i) {
+          fr::u256 r = fr::make_u256(0, 0, 0, 0);
+          for (uint32_t mk = sub; mk; mk &= mk - 1) r = fr::add(r, S.m[i * k + (uint32_t)(__ffs((int)mk) - 1)]);
+          prod = fr::mul(prod, r);
+        }
+        acc = ((__popc(sub) ^ k) & 1u) ? fr::sub(acc, prod) : fr::add(acc, prod);
+      }
+      // block reduction of acc: shuffles inside a warp, the warps' sums through shared memory
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        fr::u256 other;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          other.v[q] = __shfl_xor_sync(0xffffffffu, acc.v[q], o);
+        acc = fr::add(acc, other);
+      }
+      if (lane == 0) S.part[warp] = acc;
+      __syncthreads();
+      if (t == 0) {
+        fr::u256 perm = S.part[0];
+        for (uint32_t w2 = 1; w2 < (nt >> 5); ++w2) perm = fr::add(perm, S.part[w2]);
+        // determinant: elimination with row swaps, in place (the permanent is done with the matrix)
+        fr::u256 det = fr::mont_one();
+        bool neg = false, zero = false;
+        for (uint32_t col = 0; col < k && !zero; ++col) {
+          uint32_t piv = col;
+          while (piv < k && fr::is_zero(S.m[piv * k + col])) ++piv;
+          if (piv == k) {
+            zero = true;
+            break;
+          }
+          if (piv != col) {
+            for (uint32_t x = 0; x < k; ++x) {
+              const fr::u256 tmp = S.m[col * k + x];
+              S.m[col * k + x] = S.m[piv * k + x];
+              S.m[piv * k + x] = tmp;
+            }
+            neg = !neg;
+          }
+          const fr::u256 pv = S.m[col * k + col];
+          det = fr::mul(det, pv);
+          const fr::u256 ipv = fr::inv_mont(pv);
+          for (uint32_t r = col + 1; r < k; ++r) {
+            if (fr::is_zero(S.m[r * k + col])) continue;
+            const fr::u256 f = fr::mul(S.m[r * k + col], ipv);
+            for (uint32_t x = col; x < k; ++x) S.m[r * k + x] = fr::sub(S.m[r * k + x], fr::mul(f, S.m[col * k + x]));
+          }
+        }
+        if (zero) det = fr::make_u256(0, 0, 0, 0);
+        if (neg) det = fr::neg(det);
+        S.fire = !fr::eq(perm, det);  // 2 * (odd-permutation sum) = perm - det != 0
+      }
+      __syncthreads();
+      if (S.fire && t < k) emit(d, 1, pl, S.vars[t], WF_U | WF_K);
+    }
+    __syncthreads();
+  }
+}
+
+// the queued big groups, group q by block / caller `first + i * stride`; returns false when none was queued
+__device__ __noinline__ bool p2_big_phase(const Dev&, int pl, unsigned int first, unsigned int stride) {
+  const Dev& d = c_dev;
+  __shared__ P2Big s_big;
+  unsigned int n_big = __ldcg(&d.st->p2_big_n);  // (uniform: read behind the resolve barrier)
+  if (!n_big) return false;
+  if (n_big > P2_BIGQ_CAP) n_big = P2_BIGQ_CAP;
+  for (unsigned int q = first; q < n_big; q += stride) p2_big_slot(d, pl, __ldcg(d.p2_bigq + q), s_big);
+  return true;
 }
 
 // ---- P3 (:1425-1483): the lowest row tags a wire, exactly the reference's order -------------------
@@ -1212,7 +1400,8 @@ __device__ __noinline__ unsigned int chain_phases(const Dev&, int pl, SpecialsCa
   *n_cand_io = n_cand;
   // ---- P2 resolve (:1386-1417)
   for (uint32_t c = t; c < n_cand; c += nt) p2_resolve_group(d, pl, c);
-  const unsigned int n_x = block_sync_load(d.rec_count + pl);
+  unsigned int n_x = block_sync_load(d.rec_count + pl);
+  if (p2_big_phase(d, pl, 0, 1)) n_x = block_sync_load(d.rec_count + pl);
   {  // replay the P2 updates into buffer 0, clear the table (P3 can only tag in the first outer round: not here)
     const unsigned int nx = n_x > d.rec_cap ? d.rec_cap : n_x;
     for (uint32_t i = t; i < nx; i += nt) {
@@ -1225,7 +1414,10 @@ __device__ __noinline__ unsigned int chain_phases(const Dev&, int pl, SpecialsCa
       d.h_cnt[slot] = 0;
       d.h_head[slot] = 0;
     }
-    if (t == 0) d.st->p2_cand = 0;
+    if (t == 0) {
+      d.st->p2_cand = 0;
+      d.st->p2_big_n = 0;
+    }
   }
   if (n_x > 0) block_sync_load(d.rec_count + pl);
   // ---- P4 (:1492-1550): reads buffer 0, U|K to buffer 1
@@ -1909,7 +2101,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     cand_max = n_cand > cand_max ? n_cand : cand_max;
     PROF(2);
     for (uint32_t c = tid; c < n_cand; c += nthreads) p2_resolve_group(d, pl, c);
-    const unsigned int n_x = sync_and_load(d, d.rec_count + pl);
+    unsigned int n_x = sync_and_load(d, d.rec_count + pl);
+    // groups with more than ECNE_P2_KMAX unknowns were queued by their resolvers: a block each, one more barrier
+    if (p2_big_phase(d, pl, blockIdx.x, gridDim.x)) n_x = sync_and_load(d, d.rec_count + pl);
     PROF(3);
     // replay the P2 updates into buffer 0, clear the table, P3 claim (reads buffer 1: complete, untouched
     // here).  P3 can only ever tag in the first outer round: a wire it looks at is either unique (for
@@ -1929,6 +2123,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       }
       if (tid == 0) {
         d.st->p2_cand = 0;
+        d.st->p2_big_n = 0;
         d.st->p2_open_n[(outer + 1u) & 1u] = 0;  // the next round's scan counts the rows it leaves open here
       }
       if (p3_round)

@@ -1302,6 +1302,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     CK(A.alloc(&d.p2_k, N));
     CK(A.alloc(&d.p2_open, (N + 31) / 32 + 1));
     CK(A.alloc(&d.p2_list, (size_t)CH_LIST_CAP + CH_LONG_MAX));
+    CK(A.alloc(&d.p2_bigq, (size_t)P2_BIGQ_CAP));
   }
 
   // ---- wire state, records, scratch -----------------------------------------------------------

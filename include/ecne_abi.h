@@ -45,7 +45,7 @@ typedef enum ecne_status {
   ECNE_E_NODSU = -4,       /* UndefVarError(:dsu) at :762 when secp_solve == false            */
   ECNE_E_CUDA = -5,        /* CUDA runtime failure / no device / extension not built          */
   ECNE_E_NCCL = -6,        /* multi-GPU exchange failure                                      */
-  ECNE_E_UNSUPPORTED = -7, /* a linear-system group larger than ECNE_P2_KMAX triggered        */
+  ECNE_E_UNSUPPORTED = -7, /* a linear-system group larger than ECNE_P2_KBIG triggered        */
   ECNE_E_NOCONVERGE = -8,  /* round guard hit (the reference would loop forever)              */
   ECNE_E_INTERNAL = -9
 } ecne_status;
@@ -56,7 +56,8 @@ typedef enum ecne_status {
 #define ECNE_SPECIAL_BIGLESSTHAN 2
 
 /* Largest k for which the k x k "slow_det" of the linear-system sweep (:1389-1400) is evaluated. */
-#define ECNE_P2_KMAX 8
+#define ECNE_P2_KMAX 8   /* up to here: the reference's own enumeration of the k! permutations (:1389-1400)          */
+#define ECNE_P2_KBIG 16  /* up to here: the same odd-permutation sum as (permanent - determinant) / 2, a block per group */
 
 typedef struct ecne_problem {
   uint64_t n_rows;         /* length(constraints)                                   (:584) */

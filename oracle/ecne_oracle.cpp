@@ -87,6 +87,49 @@ bool contains(const std::vector<uint32_t>& v, uint32_t k) {
 }
 bool lessU(const U256& a, const U256& b) { return cmp(a, b) < 0; }
 
+// slow_det (:1389-1400): Combinatorics.parity is 0 for even permutations, so the sum runs over the ODD ones only.
+// by_subsets == false: the reference's own enumeration of all k! permutations (k <= 8 here).  by_subsets == true: the
+// same sum from its definition by dynamic programming over column subsets — rows are assigned in order, the state is
+// (set of columns used, parity of the inversions so far), and giving column c to the next row adds one inversion per
+// used column greater than c — O(2^k k) products instead of k! * k, for the group sizes whose k! nobody can wait for.
+U256 odd_permutation_sum(const std::vector<std::vector<U256>>& m, bool by_subsets) {
+  const size_t k = m.size();
+  if (!by_subsets) {
+    std::vector<int> perm(k);
+    for (size_t j = 0; j < k; ++j) perm[j] = (int)j;
+    U256 res = ZERO;
+    do {
+      int inv = 0;
+      for (size_t x = 0; x < k; ++x)
+        for (size_t y = x + 1; y < k; ++y)
+          if (perm[x] > perm[y]) ++inv;
+      if (inv & 1) {
+        U256 term = ONE;
+        for (size_t j = 0; j < k; ++j) term = fmul(term, m[j][perm[j]]);
+        res = fadd(res, term);
+      }
+    } while (std::next_permutation(perm.begin(), perm.end()));
+    return res;
+  }
+  std::vector<U256> dp[2];
+  dp[0].assign((size_t)1 << k, ZERO);
+  dp[1].assign((size_t)1 << k, ZERO);
+  dp[0][0] = ONE;
+  for (size_t mask = 0; mask + 1 < ((size_t)1 << k); ++mask) {
+    const size_t row = (size_t)__builtin_popcountll(mask);
+    for (int par = 0; par < 2; ++par) {
+      if (is_zero(dp[par][mask])) continue;
+      for (size_t c = 0; c < k; ++c) {
+        if (mask & ((size_t)1 << c)) continue;
+        const int flip = __builtin_popcountll(mask >> (c + 1)) & 1;
+        U256& dst = dp[par ^ flip][mask | ((size_t)1 << c)];
+        dst = fadd(dst, fmul(dp[par][mask], m[row][c]));
+      }
+    }
+  }
+  return dp[1][((size_t)1 << k) - 1];
+}
+
 U256 divexact(const U256& a, const U256& b) {  // AbstractAlgebra.divexact on GFElem
   if (is_zero(b)) throw OracleError{ECNE_E_DIVZERO, "DivideError: divexact by zero"};
   return fmul(a, finv(b));
@@ -699,22 +742,8 @@ struct Solver {
       lst.push_back(coefs);
       size_t k = uk.size();
       if (lst.size() != k) continue;
-      if (k > 10) throw OracleError{ECNE_E_UNSUPPORTED, "linear group with k > 10"};
-      // slow_det (:1389-1400): Combinatorics.parity is 0 for even permutations => odd ones only
-      std::vector<int> perm(k);
-      for (size_t j = 0; j < k; ++j) perm[j] = (int)j;
-      U256 res = ZERO;
-      do {
-        int inv = 0;
-        for (size_t x = 0; x < k; ++x)
-          for (size_t y = x + 1; y < k; ++y)
-            if (perm[x] > perm[y]) ++inv;
-        if (inv & 1) {
-          U256 term = ONE;
-          for (size_t j = 0; j < k; ++j) term = fmul(term, lst[j][perm[j]]);
-          res = fadd(res, term);
-        }
-      } while (std::next_permutation(perm.begin(), perm.end()));
+      if (k > 16) throw OracleError{ECNE_E_UNSUPPORTED, "linear group with k > 16"};
+      const U256 res = odd_permutation_sum(lst, k > 8);
       if (!is_zero(res) || (k == 1 && !is_zero(lst[0][0]))) {
         steps += k;
         fired[12]++;
@@ -956,4 +985,24 @@ extern "C" int ecne_oracle_fr(int op, uint64_t n, const uint64_t* a, const uint6
     memcpy(out + 4 * i, r.l, 32);
   }
   return 0;
+}
+
+// The odd-permutation sum of a k x k matrix of canonical limbs (row-major) both ways: by enumeration of the k!
+// permutations (the reference's slow_det, :1389-1400) into out_enum and by the subset recurrence into out_dp.
+// tests/test_oracle_pins.py checks that they agree for every k the enumeration can reach.
+extern "C" int ecne_oracle_odd_permutation_sum(uint32_t k, const uint64_t* m, uint64_t* out_enum, uint64_t* out_dp) {
+  if (k == 0 || k > 16 || !m) return ECNE_E_BADARG;
+  std::vector<std::vector<U256>> a(k, std::vector<U256>(k));
+  for (uint32_t i = 0; i < k; ++i)
+    for (uint32_t j = 0; j < k; ++j) memcpy(a[i][j].l, m + 4 * ((size_t)i * k + j), 32);
+  if (out_enum) {
+    if (k > 9) return ECNE_E_UNSUPPORTED;
+    const U256 r = odd_permutation_sum(a, false);
+    memcpy(out_enum, r.l, 32);
+  }
+  if (out_dp) {
+    const U256 r = odd_permutation_sum(a, true);
+    memcpy(out_dp, r.l, 32);
+  }
+  return ECNE_OK;
 }

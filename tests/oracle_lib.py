@@ -27,6 +27,8 @@ def lib():
         l.ecne_oracle_set_max_outer.argtypes = [C.c_uint64]
         l.ecne_oracle_fr.argtypes = [C.c_int, C.c_uint64, _abi.u64p, _abi.u64p, _abi.u64p]
         l.ecne_oracle_fr.restype = C.c_int
+        l.ecne_oracle_odd_permutation_sum.argtypes = [C.c_uint32, _abi.u64p, _abi.u64p, _abi.u64p]
+        l.ecne_oracle_odd_permutation_sum.restype = C.c_int
         _lib = l
     return _lib
 
@@ -48,3 +50,16 @@ def solve(constraints, specials, known, targets, n_vars, secp_solve=False, full_
     lib().ecne_oracle_counters(cnt.ctypes.data_as(_abi.u64p), 32)
     res.oracle_counters = cnt
     return res
+
+
+def odd_permutation_sum(matrix, enumerate_too=True):
+    """(by enumeration of the k! permutations or None, by the subset recurrence) of a k x k list of ints mod p."""
+    from helpers import to_limbs, from_limbs
+    k = len(matrix)
+    m = np.ascontiguousarray(to_limbs([v for row in matrix for v in row]))
+    oe, od = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+    st = lib().ecne_oracle_odd_permutation_sum(k, m.ctypes.data_as(_abi.u64p),
+                                               oe.ctypes.data_as(_abi.u64p) if enumerate_too else None,
+                                               od.ctypes.data_as(_abi.u64p))
+    assert st == 0, st
+    return (from_limbs(oe)[0] if enumerate_too else None), from_limbs(od)[0]

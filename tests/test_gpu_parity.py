@@ -494,3 +494,78 @@ def test_dsu_construction_bounds_errors(row):
     ok = MiniR1CS([({2: 1}, {3: 1}, {4: 1}), ({}, {}, {5: 3, 6: 0})], n_vars=8, known=[1, 2, 3], targets=[4])
     st, g, ost, o = both(ok, secp=True)               # l = [5], no constant: `continue` (:664-666)
     assert st == ost == 0 and g.unique_bytes() == o.unique_bytes()
+
+
+# ---- linear-system groups with more than ECNE_P2_KMAX unknowns (:1386-1417 has no limit) ----------------------------
+def _big_group(k, kind="random", extra_rows=0, seed=5, first_wire=2, via_outer2=False):
+    """k + extra_rows linear rows over the same k unknown wires (C only, a constant term each)."""
+    import random
+    rng = random.Random(seed)
+    wires = list(range(first_wire, first_wire + k))
+    if kind == "rank1":
+        u, v = [rng.randrange(1, P) for _ in range(k + extra_rows)], [rng.randrange(1, P) for _ in range(k)]
+        mat = [[u[j] * v[x] % P for x in range(k)] for j in range(k + extra_rows)]
+    else:
+        mat = [[rng.randrange(1, P) for _ in range(k)] for _ in range(k + extra_rows)]
+    rows = []
+    nxt = first_wire + k
+    for j in range(k + extra_rows):
+        c = {1: rng.randrange(1, P)}
+        c.update({wires[x]: mat[j][x] for x in range(k)})
+        if via_outer2:
+            c[nxt] = 3          # one more unknown, fixed by a 2 x 2 group in the first outer round
+        rows.append(({}, {}, c))
+    if via_outer2:
+        rows.append(({}, {}, {1: 5, nxt: 2, nxt + 1: 3}))
+        rows.append(({}, {}, {1: 7, nxt: 4, nxt + 1: 5}))
+        nxt += 2
+    return rows, wires, nxt
+
+
+@pytest.mark.parametrize("k,kind,extra", [(9, "random", 0), (12, "random", 0), (12, "rank1", 0), (10, "random", 2),
+                                          (16, "random", 0)])
+def test_linear_system_groups_beyond_the_enumeration(k, kind, extra):
+    rows, wires, nxt = _big_group(k, kind, extra)
+    m = MiniR1CS(rows, n_vars=nxt, known=[1], targets=wires[:1])
+    st, g, ost, o = both(m)
+    assert st == ost == 0, api._engine().ecne_last_error()
+    assert g.unique_bytes() == o.unique_bytes() and g.known_bytes() == o.known_bytes()
+    assert g.c.n_unique == 1 + k and bool(g.c.verdict) is True   # (a rank-1 system is singular and fires all the same)
+
+
+def test_linear_system_group_of_17_is_unsupported_on_both_sides():
+    rows, wires, nxt = _big_group(17)
+    m = MiniR1CS(rows, n_vars=nxt, known=[1], targets=wires[:1])
+    st, _, ost, _ = both(m)
+    assert st == ost == _abi.ECNE_E_UNSUPPORTED
+
+
+def test_two_big_groups_that_collide_in_one_table_slot():
+    lib = api._engine()
+    r1, w1, n1 = _big_group(9, seed=1)
+    r2, w2, n2 = _big_group(9, seed=2, first_wire=n1)
+    r3, w3, n3 = _big_group(9, "random", 0, seed=3, first_wire=n2)
+    r3 = r3[:-1]                                          # one row short: this set must NOT fire
+    m = MiniR1CS(r1 + r2 + r3, n_vars=n3, known=[1], targets=[w1[0], w2[0], w3[0]])
+    assert lib.ecne_set_option(b"p2_hash_bits", 0) == 0  # every set of a given k lands in the same slot
+    try:
+        st, g, ost, o = both(m)
+    finally:
+        lib.ecne_set_option(b"p2_hash_bits", 56)
+    assert st == ost == 0
+    assert g.unique_bytes() == o.unique_bytes() and g.c.n_unique == 1 + 18 and bool(g.c.verdict) is False
+
+
+@pytest.mark.parametrize("chain_open_max", [0, 8192])
+def test_big_group_that_completes_in_the_second_outer_round(chain_open_max):
+    """... where, with chain stretches on, block 0 runs the phases alone (chain_phases -> p2_big_slot)."""
+    rows, wires, nxt = _big_group(9, via_outer2=True)
+    m = MiniR1CS(rows, n_vars=nxt, known=[1], targets=wires[:1])
+    lib = api._engine()
+    assert lib.ecne_set_option(b"chain_open_max", chain_open_max) == 0
+    try:
+        st, g, ost, o = both(m)
+    finally:
+        lib.ecne_set_option(b"chain_open_max", 4096)
+    assert st == ost == 0
+    assert g.unique_bytes() == o.unique_bytes() and g.c.n_unique == 1 + 9 + 2 and g.c.outer_rounds >= 3

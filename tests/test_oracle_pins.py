@@ -96,3 +96,51 @@ def test_oracle_disjoint_sets_of_equal_wires():
         m = MiniR1CS(base + [row], n_vars=8, known=[1, 2, 3], targets=[4])
         assert status(m, [], True) == want
         assert status(m, [], False) == 0
+
+
+def test_odd_permutation_sum_both_ways():
+    """slow_det (:1389-1400) sums the ODD permutations only.  The oracle enumerates them for k <= 8 (as the reference does)
+    and uses a subset recurrence above; both against a plain-Python evaluation of the definition, and — char != 2 —
+    against (permanent - determinant) / 2."""
+    import itertools
+    import random
+    import oracle_lib
+    from helpers import P
+    rng = random.Random(11)
+
+    def by_definition(m):
+        k, tot = len(m), 0
+        for perm in itertools.permutations(range(k)):
+            inv = sum(1 for x in range(k) for y in range(x + 1, k) if perm[x] > perm[y])
+            if inv & 1:
+                t = 1
+                for j in range(k):
+                    t = t * m[j][perm[j]] % P
+                tot = (tot + t) % P
+        return tot
+
+    for k in (1, 2, 3, 4, 5, 6, 7):
+        for kind in ("random", "small", "rank1"):
+            if kind == "random":
+                m = [[rng.randrange(P) for _ in range(k)] for _ in range(k)]
+            elif kind == "small":
+                m = [[rng.randrange(-3, 4) % P for _ in range(k)] for _ in range(k)]
+            else:
+                u, v = [rng.randrange(1, P) for _ in range(k)], [rng.randrange(1, P) for _ in range(k)]
+                m = [[u[i] * v[j] % P for j in range(k)] for i in range(k)]
+            e, d = oracle_lib.odd_permutation_sum(m)
+            assert e == d == by_definition(m), (k, kind)
+    m = [[rng.randrange(P) for _ in range(9)] for _ in range(9)]
+    e, d = oracle_lib.odd_permutation_sum(m)
+    assert e == d
+    # a rank-1 matrix is singular, yet its odd-permutation sum is (k!/2) * prod(u) * prod(v) != 0: the reference's
+    # rule fires on it
+    k = 12
+    u, v = [rng.randrange(1, P) for _ in range(k)], [rng.randrange(1, P) for _ in range(k)]
+    m = [[u[i] * v[j] % P for j in range(k)] for i in range(k)]
+    _, d = oracle_lib.odd_permutation_sum(m, enumerate_too=False)
+    want = 1
+    for x in u + v:
+        want = want * x % P
+    import math
+    assert d == want * (math.factorial(k) // 2) % P
