@@ -233,11 +233,40 @@ __device__ __forceinline__ void gather_row(const uint8_t* F, const InlineRow& r,
 // Returns EI_DONE when the row can never fire again, EI_GENERIC when the caller still has to run the
 // generic evaluator on it (a dense sweep defers those so that one such lane does not stall its warp in
 // every iteration), 0 otherwise.
+//
+// The updates an evaluation wants are not emitted where the cases find them: they are collected — at most two wires per
+// inline row, the effects of several cases on one wire merged (flags by OR, bounds by intersection: exactly what the
+// state merge would make of them) — and emitted by the CALLER at one place (emit_pending).  The lanes of a warp find
+// their updates in different cases; emitted there, every case would run the emit routine on its own, one dependent
+// atomic round trip after the other.  Emitted together, the atomics of all lanes are in flight at once.
 #define EI_DONE 1u
 #define EI_GENERIC 2u
-__device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, int wbuf, int list, uint32_t row,
-                                            const InlineRow& r, const uint32_t* f, uint32_t bepoch) {
+struct Pending {
+  uint32_t w[2], bits[2], lbr[2], ubr[2];
+  __device__ __forceinline__ void reset() {
+    bits[0] = bits[1] = 0;
+    lbr[0] = lbr[1] = ECNE_NO_LB;
+    ubr[0] = ubr[1] = ECNE_NO_UB;
+    w[0] = w[1] = 0;
+  }
+  __device__ __forceinline__ bool has(int s) const { return (bits[s] | lbr[s] | ~ubr[s]) != 0; }
+  __device__ __forceinline__ void add(uint32_t wire, uint32_t b, uint32_t l = ECNE_NO_LB, uint32_t u = ECNE_NO_UB) {
+    const int s = (has(0) && w[0] != wire) ? 1 : 0;  // (an inline row updates at most two wires)
+    w[s] = wire;
+    bits[s] |= b;
+    lbr[s] = l > lbr[s] ? l : lbr[s];
+    ubr[s] = u < ubr[s] ? u : ubr[s];
+  }
+};
+__device__ __forceinline__ void emit_pending(const Dev&, int wbuf, int list, const Pending& p) {
+  if (p.has(0) || p.has(1))
+    emit2_impl(wbuf, list, p.w[0], p.bits[0], p.lbr[0], p.ubr[0], p.w[1], p.bits[1], p.lbr[1], p.ubr[1]);
+}
+__device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, uint32_t row, const InlineRow& r, const uint32_t* f,
+                                            uint32_t bepoch, Pending& out) {
   const Dev& d = c_dev;
+  (void)bepoch;
+  out.reset();
   const uint32_t rf = r.rf;
   if (!(rf & RF_FAST)) {
     if (rf & RF_LONG) return EI_DONE;  // swept by a whole warp instead
@@ -259,7 +288,7 @@ __device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, int wbuf, 
   }
   // Case 1 (:827-873)
   if (nuAB == 0 && nuC == 1) {
-    emit(d, wbuf, list, wC, WF_U | WF_K);
+    out.add(wC, WF_U | WF_K);
     nuC = 0;
   }
   // Case 2a (:875-942): C is empty and every non-constant wire of A, B is v*
@@ -279,7 +308,7 @@ __device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, int wbuf, 
       if (rf & RF_2A_DIVZ) {
         raise(d, ECNE_E_DIVZERO);
       } else {
-        emit(d, wbuf, list, v, WF_K, ECNE_NO_LB, (rf & RF_2A_BOOL) ? d.r1 : ECNE_NO_UB);
+        out.add(v, WF_K, ECNE_NO_LB, (rf & RF_2A_BOOL) ? d.r1 : ECNE_NO_UB);
         d.valsrc[v] = VS_2A | d.aux[row].val_idx;
         d.solved[row] |= 1;
       }
@@ -290,7 +319,7 @@ __device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, int wbuf, 
   if (rf & RF_2B) {
     if (d.solved[row] & 2) return true;  // already applied (a sparse round may meet the row again)
     const RowAux a = d.aux[row];
-    emit(d, wbuf, list, a.w1, WF_U | WF_K, a.rank_a, a.rank_a);
+    out.add(a.w1, WF_U | WF_K, a.rank_a, a.rank_a);
     d.valsrc[a.w1] = VS_2B | a.val_idx;
     d.solved[row] |= 2;
     return true;  // x is unique now, so Cases 5/6 have no unknown key left either
@@ -313,11 +342,11 @@ __device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, int wbuf, 
       if (u1 != u2 || l1 != l2) {
         const uint32_t mn = u1 < u2 ? u1 : u2, mx = l1 > l2 ? l1 : l2;
         if (u1 > mn || l1 < mx) {
-          emit(d, wbuf, list, k1, WF_K, mx, mn);
+          out.add(k1, WF_K, mx, mn);
           K1 = true;
         }
         if (u2 > mn || l2 < mx) {
-          emit(d, wbuf, list, k2, WF_K, mx, mn);
+          out.add(k2, WF_K, mx, mn);
           K2 = true;
         }
         l1 = l2 = mx;  // what the later cases of this evaluation see
@@ -332,8 +361,8 @@ __device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, int wbuf, 
       // Case 6 (:1304-1348): both keys carry the same ABZ tag
       if (!fire && abzmiss == 0) fire = d.abz[k1] == d.abz[k2];
       if (fire) {
-        emit(d, wbuf, list, k1, WF_U | WF_K);
-        emit(d, wbuf, list, k2, WF_U | WF_K);
+        out.add(k1, WF_U | WF_K);
+        out.add(k2, WF_U | WF_K);
       }
     }
     return false;  // bounds may still have to travel through this row later
@@ -870,7 +899,10 @@ __device__ __forceinline__ void sparse_row(const Dev&, int rbuf, int wbuf, int l
   uint32_t f[ROWREC_INLINE];
   gather_row(d.F[rbuf], ir, f);
   evals += 1;
-  if (eval_inline(d, rbuf, wbuf, list, row, ir, f, bepoch) & EI_GENERIC) eval_row<1>(d, rbuf, wbuf, list, row, bepoch);
+  Pending pend;
+  const uint32_t ei = eval_inline(d, rbuf, row, ir, f, bepoch, pend);
+  emit_pending(d, wbuf, list, pend);
+  if (ei & EI_GENERIC) eval_row<1>(d, rbuf, wbuf, list, row, bepoch);
 }
 
 // A frontier-driven Jacobi round: every record of the previous round (a state change of one wire) is
@@ -1049,6 +1081,8 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
     gr += 1;
 #ifdef ECNE_PROFILE
     wrounds += 1;
+    const long long rz0 = clock64();
+    long long rz1 = rz0;
 #endif
     const int wbuf = rbuf ^ 1;
     const int rb = fast ? (rbuf | ST_TAG_CG) : rbuf;
@@ -1104,6 +1138,8 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
       const unsigned int q = p - __shfl_sync(0xffffffffu, excl, j);
       uint32_t row = 0xffffffffu;
       bool is_long = false;
+      Pending pend;  // the updates this lane's row wants: emitted by all lanes together, below
+      pend.reset();
 #ifdef ECNE_PROFILE
       long long sz0 = clock64(), sz1 = sz0, sz2 = sz0, sz3 = sz0, sz4 = sz0;
       bool was_generic = false;
@@ -1132,7 +1168,7 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
 #ifdef ECNE_PROFILE
             sz2 = clock64() + (f[0] & 0) + (f[1] & 0) + (f[2] & 0);
 #endif
-            const uint32_t ei = eval_inline(d, rb, wbuf, elist, row, ir, f, bepoch);
+            const uint32_t ei = eval_inline(d, rb, row, ir, f, bepoch, pend);
 #ifdef ECNE_PROFILE
             sz3 = clock64() + (ei & 0);
             was_generic = (ei & EI_GENERIC) != 0;
@@ -1158,6 +1194,22 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
             q[8] += a; q[9] += b; q[10] += c; q[11] += g; q[12] += ng;
           }
         }
+#endif
+      __syncwarp();
+#ifdef ECNE_PROFILE
+      const long long ez0 = clock64();
+#endif
+      emit_pending(d, wbuf, elist, pend);
+#ifdef ECNE_PROFILE
+      {
+        __syncwarp();
+        const long long ez1 = clock64();
+        if (lane == 0) {
+          d.prof[28000 + 40 * 148 * 4 + 128 + 13] += (unsigned long long)(ez1 - ez0);  // the emits of the batch, all lanes together
+          d.prof[28000 + 40 * 148 * 4 + 128 + 14] += (unsigned long long)(sz0 - rz0);  // round start -> first batch
+          rz1 = ez1;
+        }
+      }
 #endif
       unsigned int m = __ballot_sync(0xffffffffu, is_long);
 #ifdef ECNE_PROFILE
@@ -1250,6 +1302,9 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
       dn = __shfl_sync(0xffffffffu, dn, 0);
       leave = false;
     }
+#ifdef ECNE_PROFILE
+    if (lane == 0) d.prof[28000 + 40 * 148 * 4 + 128 + 15] += (unsigned long long)(clock64() - rz1);  // last emit -> round end
+#endif
     bepoch += bf & 1u;
     hv = bf & 2u;
     round += 1;
@@ -1829,8 +1884,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
 #pragma unroll
             for (int h = 0; h < P1_INFLIGHT; ++h)
               if (kk[h] >= 0) {
-                const uint32_t e = eval_inline(d, rbuf, wbuf, elist, d.row_lo + tid + (uint32_t)kk[h] * nthreads, rr[h],
-                                               ff[h], bepoch);
+                Pending pend;
+                const uint32_t e = eval_inline(d, rbuf, d.row_lo + tid + (uint32_t)kk[h] * nthreads, rr[h], ff[h], bepoch, pend);
+                emit_pending(d, wbuf, elist, pend);
                 if (e & EI_DONE) live.clear(kk[h]);
                 if (e & EI_GENERIC) slow.set(kk[h]);
               }
