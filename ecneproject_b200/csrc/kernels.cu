@@ -1060,6 +1060,7 @@ struct SoloState {
 // the last round's records are written to the global list, one fence makes everything visible, and the state block is
 // left exactly as a round through the global lists would leave it.  Sharded runs (which count distinct wires per
 // round through the global arrays) keep the round-by-round global protocol.
+template <bool fast>  // fast: unsharded run (the records of a stretch stay in shared memory, see above)
 __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int prev_n, unsigned int max_rounds,
                                        unsigned long long* evals_io) {
   const Dev& d = c_dev;
@@ -1068,7 +1069,6 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
                gr = st->gr, hv = 0, dn = 0;
   int rbuf = (int)st->rbuf;
   unsigned long long ev = 0;
-  const bool fast = !d.shard;
   bool from_smem = false;      // the records of the round before are in s_soloq[qr]
   unsigned int qr = 0;         // queue read this round (fast path); the round writes queue qr ^ 1
   unsigned int prog_acc = 0;
@@ -1126,11 +1126,11 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
     const unsigned int excl = incl - hd.x;
     for (unsigned int base = 0; base < total; base += 32) {
       const unsigned int p = base + lane;
-      int j = 0;  // the record whose range [excl, incl) holds pair p
+      int j = 0;  // the record whose range [excl, incl) holds pair p: the number of records whose range ends at or before p
 #pragma unroll
-      for (int k = 0; k < 31; ++k) {
-        const unsigned int e = __shfl_sync(0xffffffffu, incl, k);
-        if (p >= e) j = k + 1;
+      for (int step = 16; step > 0; step >>= 1) {  // (binary search over the non-decreasing prefix sums: 5 shuffles)
+        const unsigned int e = __shfl_sync(0xffffffffu, incl, j + step - 1);
+        if (p >= e) j += step;
       }
       const uint32_t wj = __shfl_sync(0xffffffffu, r.wire, j);
       const uint32_t hy = __shfl_sync(0xffffffffu, hd.y, j), hz = __shfl_sync(0xffffffffu, hd.z, j),
@@ -1620,7 +1620,10 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
                 __syncthreads();
                 if (warp_in_block == 0) {
                   unsigned long long ev = 0;
-                  warp_solo(d, &s_ws, prev_n, max_rounds, &ev);
+                  if (d.shard)
+                    warp_solo<false>(d, &s_ws, prev_n, max_rounds, &ev);
+                  else
+                    warp_solo<true>(d, &s_ws, prev_n, max_rounds, &ev);
                   if (d.rank == 0) {  // replicated work is counted once
                     evals += ev;
                     ruleevals += ev;
