@@ -599,6 +599,8 @@ def main():
                               "{0, 1, p-1, other} + 32-byte limbs of the other values; expanded on the device into the same "
                               "arrays the full form is copied into",
                 "compact_prep_seconds_untimed": compact_prep_s,
+                "upload": ("every rank copies 1/%d of the rows over its own PCIe link, ncclAllGather of the slices over NVLink "
+                           "(h2d_bytes_per_step is the sum over the ranks: the problem once)" % world) if world > 1 else "one GPU",
                 # the same call with the full form (64-bit offsets, 32-byte limbs for every stored term)
                 "full_form": {"ms_per_step": e2e_ms_full, "value": total_evals / (e2e_ms_full / 1e3),
                               "h2d_bytes_per_step": h2d_bytes_full, "ms_h2d": h2d_ms_full, "ms_classify": classify_ms_full},

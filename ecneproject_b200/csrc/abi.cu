@@ -48,6 +48,9 @@ struct Global {
   long long sparse_max = -1;          // records per round up to which a round is frontier-driven (-1: rows / 32)
   // open rows of the linear-system sweep below which block 0 runs whole outer rounds alone (0: never; at most CH_LIST_CAP)
   long long chain_open_max = 4096;
+  // one process per GPU: 1 = every rank uploads 1/world of the rows and the ranks gather them over NVLink; 0 = every
+  // rank uploads the whole problem itself (set before ecne_dist_init; must be the same on every rank)
+  long long shard_upload = 1;
   // On several GPUs the dense sweeps of a problem with at least this many rows are split over the ranks; a smaller
   // problem is solved by every rank on all rows without any exchange (a sharded round costs a cross-GPU barrier,
   // ~15-25 us, which a sweep of a few 10^5 rows does not earn back: ecdsa's 694 k rows sweep in ~20 us)
@@ -323,6 +326,8 @@ extern "C" int ecne_set_option(const char* key, int64_t value) {
     G.sparse_max = value;
   else if (k == "grid_blocks")
     G.grid_blocks = value;
+  else if (k == "shard_upload")
+    G.shard_upload = value ? 1 : 0;
   else if (k == "chain_open_max")
     G.chain_open_max = value < 0 ? 0 : (value > (long long)CH_LIST_CAP ? (long long)CH_LIST_CAP : value);
   else if (k == "solve_variant")
@@ -372,6 +377,27 @@ int upload_impl(const ecne_problem_t* problem, const DevSystem* dev0, ecne_resid
   }
   const int nl = G.n_local(), world = G.total_world();
   if (world > 1 && !G.multi && !G.comm) return fail(ECNE_E_NCCL, "ecne_dist_init has not been called");
+  // one process, several GPUs: the rows cross PCIe ONCE (to the first device); the others pull them over NVLink
+  DevSystem up0;
+  struct Up0Guard {
+    DevSystem& s;
+    ~Up0Guard() {
+      if (s.arena.pool && !s.arena.slabs.empty()) {
+        cudaSetDevice(G.ctx[0]->device);
+        cudaStreamSynchronize(G.ctx[0]->stream);
+        s.arena.release();
+      }
+    }
+  } up0_guard{up0};
+  if (nl > 1 && !dev0) {
+    cudaSetDevice(G.ctx[0]->device);
+    up0.arena.pool = &G.ctx[0]->pool;
+    std::string e;
+    const int st = dev_system_upload(problem, &up0, G.ctx[0]->stream, e);
+    if (st != ECNE_OK) return fail(st, e);
+    CKA(cudaStreamSynchronize(G.ctx[0]->stream));
+    dev0 = &up0;
+  }
   ecne_resident* h = new ecne_resident();
   h->rs.resize(nl);
   std::vector<int> sts(nl, ECNE_OK);
@@ -929,7 +955,9 @@ extern "C" int ecne_solve(const ecne_problem_t* problem, ecne_result_t* result) 
 extern "C" int ecne_shard_rows(const ecne_problem_t* p, int rank, int world, uint64_t* lo, uint64_t* hi) {
   if (!p || !lo || !hi || world < 1 || rank < 0 || rank >= world) return fail(ECNE_E_BADARG, "bad argument");
   const uint64_t N = p->n_rows;
-  const uint64_t total = N ? p->seg_ptr[3 * N] : 0;
+  if (!p->seg_ptr && !p->seg_ptr32) return fail(ECNE_E_BADARG, "null offsets");
+  auto seg = [&](uint64_t i) -> uint64_t { return p->seg_ptr ? p->seg_ptr[i] : (uint64_t)p->seg_ptr32[i]; };
+  const uint64_t total = N ? seg(3 * N) : 0;
   auto cut = [&](int r) -> uint64_t {  // first row whose prefix term count reaches r/world of the total
     if (r <= 0) return 0;
     if (r >= world) return N;
@@ -937,7 +965,7 @@ extern "C" int ecne_shard_rows(const ecne_problem_t* p, int rank, int world, uin
     uint64_t a = 0, b = N;  // smallest row i with seg_ptr[3*i] >= want
     while (a < b) {
       uint64_t m = (a + b) / 2;
-      if (p->seg_ptr[3 * m] >= want)
+      if (seg(3 * m) >= want)
         b = m;
       else
         a = m + 1;
@@ -967,6 +995,7 @@ extern "C" int ecne_dist_init(int rank, int world, const uint8_t unique_id[128])
   }
   G.rank = rank;
   G.world = world;
+  upload_shard() = UploadShard();
   if (world == 1) return ECNE_OK;
   if (!unique_id) return fail(ECNE_E_BADARG, "null unique id");
   if (!NCCL.load()) return fail(ECNE_E_NCCL, "cannot load libnccl.so.2");
@@ -975,6 +1004,17 @@ extern "C" int ecne_dist_init(int rank, int world, const uint8_t unique_id[128])
   cudaSetDevice(G.ctx[0]->device);
   if (NCCL.CommInitRank(&G.comm, world, id, rank) != ncclSuccess)
     return fail(ECNE_E_NCCL, "ncclCommInitRank failed");
+  // sharded upload (engine_host.h UploadShard): every rank copies its slice, the slices are gathered over NVLink
+  UploadShard& U = upload_shard();
+  U.rank = rank;
+  U.world = world;
+  U.allgather = [](void* buf, size_t slice, cudaStream_t s) -> cudaError_t {
+    if (!G.comm || !G.shard_upload) return cudaErrorNotReady;
+    return NCCL.AllGather((const char*)buf + (size_t)G.rank * slice, buf, slice, ncclChar, G.comm, s) == ncclSuccess
+               ? cudaSuccess
+               : cudaErrorUnknown;
+  };
+  if (!G.shard_upload) U.allgather = nullptr;
   return ECNE_OK;
 }
 extern "C" int ecne_dist_rank(void) { return G.rank; }

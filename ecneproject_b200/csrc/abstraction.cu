@@ -546,9 +546,9 @@ int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std
   S->N = N;
   S->V = p->n_vars;
   S->nnz = nnz;
-  CKE(S->arena.alloc(&S->seg, 3 * N + 2));
-  CKE(S->arena.alloc(&S->col, nnz + 1));
-  CKE(S->arena.alloc(&S->coef, nnz + 1));
+  CKE(S->arena.alloc(&S->seg, upload_padded<unsigned long long>(3 * N + 2)));
+  CKE(S->arena.alloc(&S->col, upload_padded<uint32_t>(nnz + 1)));
+  CKE(S->arena.alloc(&S->coef, upload_padded<fr::u256>(nnz + 1)));
   Arena tmp;
   tmp.pool = S->arena.pool;
   st = upload_rows(p, S->seg, S->col, S->coef, tmp, s, err);

@@ -149,6 +149,20 @@ cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s)
 // setup.cu: the rows of `p` (seg_ptr / col / coef in either form of include/ecne_abi.h: full 32-byte coefficients, or
 // class bytes + the values that are not 0, 1, p-1; 64- or 32-bit offsets) into device arrays of the on-disk layout.
 // `tmp` lends the scratch of the compact form.  Returns an ecne_status.
+// One process per GPU (ecne_dist_init): rank r copies the r-th slice of every big upload over its OWN PCIe link and the
+// ranks all-gather the slices over NVLink — the host -> device traffic of a solve is the problem once, not once per GPU.
+// abi.cu installs the gather (ncclAllGather, in place: slice r lies at buf + r * slice_bytes).  Collective: every rank
+// uploads the same problem at the same time, which ecne_solve / ecne_upload on several ranks already require.
+struct UploadShard {
+  int rank = 0, world = 1;
+  std::function<cudaError_t(void* buf, size_t slice_bytes, cudaStream_t s)> allgather;
+};
+UploadShard& upload_shard();
+// elements to allocate for an upload target of n elements (room for `world` equal 256-byte-aligned slices)
+template <class T>
+inline size_t upload_padded(size_t n) {
+  return n + (ECNE_MAX_WORLD * 256 + 256) / sizeof(T) + 1;
+}
 uint64_t problem_nnz(const ecne_problem_t* p);
 int problem_rows_ok(const ecne_problem_t* p, std::string& err);
 int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_col, fr::u256* d_coef, Arena& tmp,

@@ -865,6 +865,23 @@ __global__ void k_widen_seg(const uint32_t* seg32, uint64_t n, unsigned long lon
   if (i < n) seg[i] = seg32[i];
 }
 
+UploadShard& upload_shard() {
+  static UploadShard u;
+  return u;
+}
+// host -> device copy of one array of the problem: whole, or this rank's slice + the all-gather of the ranks' slices
+static cudaError_t put(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  UploadShard& U = upload_shard();
+  if (U.world <= 1 || !U.allgather || bytes < ((size_t)1 << 20)) return staged_h2d(dst, src, bytes, s);
+  const size_t slice = ((bytes + (size_t)U.world - 1) / (size_t)U.world + 255) & ~(size_t)255;
+  const size_t off = (size_t)U.rank * slice;
+  if (off < bytes) {
+    cudaError_t e = staged_h2d((char*)dst + off, (const char*)src + off, std::min(slice, bytes - off), s);
+    if (e != cudaSuccess) return e;
+  }
+  return U.allgather(dst, slice, s);
+}
+
 uint64_t problem_nnz(const ecne_problem_t* p) {
   return p->seg_ptr ? p->seg_ptr[3 * p->n_rows] : p->seg_ptr32[3 * p->n_rows];
 }
@@ -889,17 +906,17 @@ int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_
                 cudaStream_t s, std::string& err) {
   const uint64_t N = p->n_rows, nnz = problem_nnz(p);
   if (p->seg_ptr) {
-    CK(staged_h2d(d_seg, p->seg_ptr, (3 * N + 1) * 8, s));
+    CK(put(d_seg, p->seg_ptr, (3 * N + 1) * 8, s));
   } else {
     uint32_t* d_seg32;
-    CK(tmp.alloc(&d_seg32, 3 * N + 1));
-    CK(staged_h2d(d_seg32, p->seg_ptr32, (3 * N + 1) * 4, s));
+    CK(tmp.alloc(&d_seg32, upload_padded<uint32_t>(3 * N + 1)));
+    CK(put(d_seg32, p->seg_ptr32, (3 * N + 1) * 4, s));
     k_widen_seg<<<(unsigned int)((3 * N + 1 + 255) / 256), 256, 0, s>>>(d_seg32, 3 * N + 1, d_seg);
   }
   if (!nnz) return ECNE_OK;
-  CK(staged_h2d(d_col, p->col, nnz * 4, s));
+  CK(put(d_col, p->col, nnz * 4, s));
   if (p->coef) {
-    CK(staged_h2d(d_coef, p->coef, nnz * 32, s));
+    CK(put(d_coef, p->coef, nnz * 32, s));
     return ECNE_OK;
   }
   const uint64_t n_other = p->n_coef_other;
@@ -907,16 +924,16 @@ int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_
   fr::u256* d_other;
   uint32_t* d_term;
   unsigned int* d_chk;
-  CK(tmp.alloc(&d_cls, nnz));
-  CK(tmp.alloc(&d_other, n_other));
-  CK(tmp.alloc(&d_term, n_other));
+  CK(tmp.alloc(&d_cls, upload_padded<uint8_t>(nnz)));
+  CK(tmp.alloc(&d_other, upload_padded<fr::u256>(n_other)));
+  CK(tmp.alloc(&d_term, upload_padded<uint32_t>(n_other)));
   CK(tmp.alloc(&d_chk, 2));
   CK(cudaMemsetAsync(d_chk, 0, 2 * sizeof(unsigned int), s));
-  CK(staged_h2d(d_cls, p->coef_class, nnz, s));
+  CK(put(d_cls, p->coef_class, nnz, s));
   k_expand_class<<<(unsigned int)((nnz + 255) / 256), 256, 0, s>>>(d_cls, nnz, d_coef, d_chk);  // (while the values cross)
   if (n_other) {
-    CK(staged_h2d(d_other, p->coef_other, n_other * 32, s));
-    CK(staged_h2d(d_term, p->coef_other_term, n_other * 4, s));
+    CK(put(d_other, p->coef_other, n_other * 32, s));
+    CK(put(d_term, p->coef_other_term, n_other * 4, s));
     k_expand_other<<<(unsigned int)((n_other + 255) / 256), 256, 0, s>>>(d_other, d_term, n_other, nnz, d_cls, d_coef, d_chk);
   }
   unsigned int chk[2] = {0, 0};
@@ -994,9 +1011,9 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     d_col_raw = dev->col;
     d_coef_raw = dev->coef;
   } else {
-    CK(tmp.alloc(&d_seg64, 3 * N + 2));
-    CK(tmp.alloc(&d_col_raw, nnz));
-    CK(tmp.alloc(&d_coef_raw, nnz));
+    CK(tmp.alloc(&d_seg64, upload_padded<unsigned long long>(3 * N + 2)));
+    CK(tmp.alloc(&d_col_raw, upload_padded<uint32_t>(nnz)));
+    CK(tmp.alloc(&d_coef_raw, upload_padded<fr::u256>(nnz)));
     const int st = upload_rows(p, d_seg64, d_col_raw, d_coef_raw, tmp, s, err);
     if (st != ECNE_OK) return st;
   }

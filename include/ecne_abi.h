@@ -229,6 +229,9 @@ int ecne_shard_rows(const ecne_problem_t* problem, int rank, int world, uint64_t
  * "chain_open_max": once the linear-system sweep has at most this many rows left to look at (and the frontier is small),
  * ONE block runs whole outer rounds — special constraints, Jacobi rounds, linear systems, IsZero — without any grid
  * barrier (4096; 0: never; results do not depend on it);
+ * "shard_upload": one process per GPU (ecne_dist_init): every rank copies 1/world of the rows over its own PCIe link and
+ * the ranks gather the slices over NVLink (1; 0: every rank uploads the whole problem; set before ecne_dist_init, same
+ * on every rank);
  * "solve_variant": which build of the solve kernel runs (0: by size — a GPU that sweeps at least "wide_min_rows" = 1 500 000 rows
  * takes the 1024-thread x 64-register build, smaller problems the 512 x 128 one; 1 / 2 force them);
  * "p2_hash_bits": bits of the unknown-set hash the linear-system sweep groups by (56; fewer force collisions,
