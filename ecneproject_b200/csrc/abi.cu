@@ -756,6 +756,8 @@ extern "C" int ecne_solve_resident(ecne_resident_t* h, ecne_result_t* res) {
         const unsigned long long* q = pr.data() + 28000 + 40 * 148 * 4 + 128;
         fprintf(stderr, "[warp solo stages] slowest lane per batch, summed: row record + latch %llu | state gather %llu | inline evaluation %llu | "
                         "generic evaluator %llu (%llu rows) | emits of the batch %llu | round start -> first batch %llu | last emit -> round end %llu\n", q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15]);
+        fprintf(stderr, "[warp solo prologue] records from shared memory %llu | replay issued %llu | syncwarp %llu || [epilogue] long-row ballot %llu | "
+                        "replay results consumed %llu | syncwarp %llu\n", q[16], q[17], q[18], q[19], q[20], q[21]);
         fprintf(stderr, "[warp solo] %llu stretches, %llu rounds, %llu cycles | %llu pair batches, %llu (record, row) pairs | %llu long rows "
                         "evaluated in %llu cycles (cumulative over the solves of this handle)\n", q[6], q[5], q[4], q[2], q[3], q[1], q[0]);
       }

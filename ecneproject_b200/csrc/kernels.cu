@@ -411,6 +411,7 @@ struct SpecialsCache {
   uint8_t solved[SPC_N];
   int ok;         // the lists fit
   int has_pairs;  // the list holds a BigMultModP and a BigLessThan (P0' has something to do)
+  int p4_dead;    // chain stretches: a P4 pass found every IsZero pair latched or its vk unique — for good (both are monotone)
 };
 __device__ __forceinline__ void specials_cache_fill(const Dev& d, SpecialsCache& c) {
   const bool fits = d.n_specials <= SPC_N && (d.n_specials == 0 || (d.sp_in_ptr[d.n_specials] <= SPC_IN &&
@@ -423,6 +424,7 @@ __device__ __forceinline__ void specials_cache_fill(const Dev& d, SpecialsCache&
       l |= d.sp_kind[i] == ECNE_SPECIAL_BIGLESSTHAN;
     }
     c.has_pairs = (m && l) ? 1 : 0;
+    c.p4_dead = d.n_p4 == 0 ? 1 : 0;
   }
   if (fits) {
     for (uint32_t i = threadIdx.x; i <= d.n_specials; i += blockDim.x) {
@@ -1106,6 +1108,9 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
         hd = __ldcg(reinterpret_cast<const uint4*>(d.inv_head) + r.wire);
       }
     }
+#ifdef ECNE_PROFILE
+    const long long pz1 = clock64() + (r.wire & 0) + (hd.x & 0);
+#endif
     if (fast && lane == 0) {
       s_soloq_n[qw] = 0;
       s_solo_flags = 0;
@@ -1115,7 +1120,19 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
     // round (which reads that buffer) starts, and it costs no trip on the round's critical path
     uint32_t rp0 = 0, rp1 = 0, rp2 = 0;
     if (fast && have) apply_update_issue(wbuf, r.wire, r.bits, r.lbr, r.ubr, rp0, rp1, rp2);
+#ifdef ECNE_PROFILE
+    const long long pz2 = clock64();
+#endif
     __syncwarp();
+#ifdef ECNE_PROFILE
+    const long long pz3 = clock64();
+    if (lane == 0) {
+      unsigned long long* q = d.prof + 28000 + 40 * 148 * 4 + 128;
+      q[16] += (unsigned long long)(pz1 - rz0);  // records from shared memory
+      q[17] += (unsigned long long)(pz2 - pz1);  // replay issued
+      q[18] += (unsigned long long)(pz3 - pz2);  // __syncwarp
+    }
+#endif
     unsigned int incl = hd.x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1240,9 +1257,23 @@ __device__ __noinline__ void warp_solo(const Dev&, SoloState* st, unsigned int p
       apply_update(d, wbuf, r.wire, r.bits, r.lbr, r.ubr);
       consume_rec(d, prev_list, r.wire);
     }
+#ifdef ECNE_PROFILE
+    const long long qz0 = clock64();
+#endif
     replay_sink |= rp0 ^ rp1 ^ rp2;  // first use of the replay atomics' results: waits until they have been performed
     if (__all_sync(0xffffffffu, replay_sink == 0xdeadbeefu)) ev += 1;  // (keeps the use alive; practically never true)
+#ifdef ECNE_PROFILE
+    const long long qz1 = clock64();
+#endif
     __syncwarp();
+#ifdef ECNE_PROFILE
+    if (lane == 0) {
+      unsigned long long* q = d.prof + 28000 + 40 * 148 * 4 + 128;
+      q[19] += (unsigned long long)(qz0 - rz1);      // last emit -> here (long-row ballot)
+      q[20] += (unsigned long long)(qz1 - qz0);      // replay results consumed
+      q[21] += (unsigned long long)(clock64() - qz1);  // __syncwarp
+    }
+#endif
     unsigned int cnt = 0, bf = 0;
     bool leave;
     if (fast) {
@@ -1475,13 +1506,26 @@ __device__ __noinline__ unsigned int chain_phases(const Dev&, int pl, SpecialsCa
     }
   }
   if (n_x > 0) block_sync_load(d.rec_count + pl);
-  // ---- P4 (:1492-1550): reads buffer 0, U|K to buffer 1
-  {
-    bool fired = false;
-    for (uint32_t i = t; i < d.n_p4; i += nt) fired |= p4_row(d, pl, d.p4_rows[i]);
+  // ---- P4 (:1492-1550): reads buffer 0, U|K to buffer 1.  A pair that is latched, or whose vk is unique, never fires
+  // again (both monotone): once a pass has found every pair so, the phase — and its barrier — is skipped for good.
+  unsigned int n_y = n_x;
+  if (!spc.p4_dead) {
+    bool fired = false, open = false;
+    for (uint32_t i = t; i < d.n_p4; i += nt) {
+      const uint32_t row = d.p4_rows[i];
+      if (d.solved[row] & 1) continue;
+      if (ld_flag(F, d.aux[row].w4) & WF_U) continue;
+      open = true;
+      fired |= p4_row(d, pl, row);
+    }
     if (fired) atomicAdd(&d.st->p4_fired, 1u);
+    const int any_open = __syncthreads_or(open ? 1 : 0);
+    if (!any_open) {
+      if (t == 0) spc.p4_dead = 1;
+    } else {
+      n_y = block_sync_load(d.rec_count + pl);
+    }
   }
-  const unsigned int n_y = block_sync_load(d.rec_count + pl);
   {  // replay the P4 updates into buffer 0, then the next outer round's P0 (buffer 1 is complete)
     const unsigned int nx = n_x > d.rec_cap ? d.rec_cap : n_x, ny = n_y > d.rec_cap ? d.rec_cap : n_y;
     for (uint32_t i = nx + t; i < ny; i += nt) {
