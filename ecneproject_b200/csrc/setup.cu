@@ -5,6 +5,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include "engine_host.h"
@@ -985,6 +986,17 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     }
 
   cudaStream_t s = R->stream;
+  // ECNE_SETUP_PROF=1: wall-clock time of every stage of the set-up, each closed by a device synchronisation (the
+  // stages then no longer overlap: this is a profile, not a benchmark)
+  static const bool setup_prof = getenv("ECNE_SETUP_PROF") != nullptr;
+  auto sp_t0 = std::chrono::steady_clock::now();
+  auto sp_lap = [&](const char* what) {
+    if (!setup_prof) return;
+    cudaDeviceSynchronize();
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ecne setup] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - sp_t0).count());
+    sp_t0 = t;
+  };
   Arena tmp;  // freed on return
   struct TmpGuard {
     Arena& a;
@@ -1018,6 +1030,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     if (st != ECNE_OK) return st;
   }
 
+  sp_lap("upload of the rows");
   Dev& d = R->d;
   memset(&d, 0, sizeof(d));
   d.N = (uint32_t)N;
@@ -1052,7 +1065,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(h2d(d_sp_out_ptr, op.data(), n_sp + 1, s));
   CK(h2d(d_sp_in, p->sp_in, n_sp_in, s));
   CK(h2d(d_sp_out, p->sp_out, n_sp_out, s));
-  CK(cudaStreamSynchronize(s));  // ip/op are stack-owned
+  // (ip / op live until the function returns; the counters readback below synchronises the stream)
   cudaEventRecord(ev1, s);
   d.known = d_known;
   d.targets = d_targets;
@@ -1062,6 +1075,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   d.sp_out_ptr = d_sp_out_ptr;
   d.sp_out = d_sp_out;
 
+  sp_lap("small arrays + sync");
   Raw raw;
   raw.N = (uint32_t)N;
   raw.V = (uint32_t)V;
@@ -1096,6 +1110,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   }
   k_seg<<<nb(3 * N + 1, 256), 256, 0, s>>>(raw, d_pos, d_segnz);
 
+  sp_lap("keep / scan / seg");
   // ---- classify -------------------------------------------------------------------------------
   uint32_t* d_rflags;
   RowAux* d_aux;
@@ -1115,6 +1130,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   uint32_t nnz_nz = 0;
   CK(cudaMemcpyAsync(&nnz_nz, d_pos + nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  sp_lap("classify + counters readback");
   if (cnt.bad) {
     err = "wire id outside 1..num_variables in a constraint (BoundsError at :681/:829)";
     return ECNE_E_BOUNDS;
@@ -1190,6 +1206,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     CK(cub::DeviceScan::InclusiveSum(d_ms, b, d_flag, d_incl, (int)nc, s2));
   }
   k_ranks<<<nb(nc, 256), 256, 0, s2>>>(d_tvals, d_idx, d_incl, nc, d_rank_of, d_table);
+  sp_lap("values + sort + ranks (side)");
   // Long bit-decomposition candidates (main stream, while the side stream sorts the bound values)
   std::vector<Pow2Entry> tab;
   cudaEvent_t ev_c3;
@@ -1239,6 +1256,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   uint32_t h_rank[3], h_tn;
   cudaEventRecord(ev_join, s2);
 
+  sp_lap("c3_long + fill_ranks");
   // ---- sweep layout ---------------------------------------------------------------------------
   // long rows on `s3` (behind their Case-3 classification, whose flip flag orders their C terms), short rows on the
   // main stream: the 208 sorting blocks of ecdsa's long rows (0.14 ms) run beside the 0.16 ms pass over every term
@@ -1254,6 +1272,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   if (nnz)
     k_layout<<<nb(nnz, 256), 256, 0, s>>>(raw, d_keep, d_pos, d_segnz, d_rflags, d_col, d_coef, d_nontriv);
   if (s3 != s) cudaStreamWaitEvent(s, ev_long, 0);  // from here on: final row flags, every row laid out
+  sp_lap("layout (short + long rows)");
   if (n_sp_in) k_mark<<<nb(n_sp_in, 256), 256, 0, s>>>(d_sp_in, (uint32_t)n_sp_in, d_nontriv);
   if (n_sp_out) k_mark<<<nb(n_sp_out, 256), 256, 0, s>>>(d_sp_out, (uint32_t)n_sp_out, d_nontriv);
   if (p->n_targets) k_mark<<<nb(p->n_targets, 256), 256, 0, s>>>(d_targets, (uint32_t)p->n_targets, d_nontriv);
@@ -1274,6 +1293,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   if (N) k_phase_rows<<<nb(N, 256), 256, 0, s>>>((uint32_t)N, d_rflags, d_p3, d_p4, d_nphase);
   unsigned int h_nphase[2] = {0, 0};
   CK(cudaMemcpyAsync(h_nphase, d_nphase, sizeof(h_nphase), cudaMemcpyDeviceToHost, s));
+  sp_lap("marks, rowrec, phase rows");
   // wire -> rows index (count, scan, fill)
   uint32_t *d_inv_ptr, *d_inv_row, *d_inv_cur;
   CK(A.alloc(&d_inv_ptr, V + 3));
@@ -1303,6 +1323,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   d.inv_head = d_inv_head;
   d.p3_rows = d_p3;
   d.p4_rows = d_p4;
+  sp_lap("wire -> rows index");
   // P2 grouping table: power of two >= 2 N slots
   {
     uint32_t cap = 1024;
@@ -1311,9 +1332,11 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     CK(A.alloc(&d.h_key, (size_t)cap));
     CK(A.alloc(&d.h_cnt, (size_t)cap));
     CK(A.alloc(&d.h_head, (size_t)cap));
-    CK(cudaMemsetAsync(d.h_key, 0, (size_t)cap * sizeof(unsigned long long), s));
-    CK(cudaMemsetAsync(d.h_cnt, 0, (size_t)cap * sizeof(uint32_t), s));
-    CK(cudaMemsetAsync(d.h_head, 0, (size_t)cap * sizeof(uint32_t), s));
+    // (cleared on the second side stream, behind the long rows' chain: nothing on the main stream waits for 32 MB of
+    // memsets; the final synchronisation of the function covers them)
+    CK(cudaMemsetAsync(d.h_key, 0, (size_t)cap * sizeof(unsigned long long), s3));
+    CK(cudaMemsetAsync(d.h_cnt, 0, (size_t)cap * sizeof(uint32_t), s3));
+    CK(cudaMemsetAsync(d.h_head, 0, (size_t)cap * sizeof(uint32_t), s3));
     CK(A.alloc(&d.p2_next, N));
     CK(A.alloc(&d.p2_slot, N));
     CK(A.alloc(&d.p2_k, N));
@@ -1349,6 +1372,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(A.alloc(&R->d_kbits, (V + 63) / 64));
   CK(A.alloc(&R->d_counts, 4));
 
+  sp_lap("table memsets + allocations");
   cudaStreamWaitEvent(s, ev_join, 0);  // the timing event below covers the side chain too
   // the disjoint sets of equal wires and their one observable use (:634-678, :760-768)
   unsigned int* d_dsu_flags = nullptr;
@@ -1408,6 +1432,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   R->n_rows = N;
   R->n_vars = V;
   R->n_targets = p->n_targets;
+  sp_lap("dsu + final readbacks");
   cudaEventRecord(ev2, s);
   CK(cudaStreamSynchronize(s));
   float ms = 0;
