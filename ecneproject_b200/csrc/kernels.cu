@@ -241,26 +241,32 @@ __device__ __forceinline__ void gather_row(const uint8_t* F, const InlineRow& r,
 // atomic round trip after the other.  Emitted together, the atomics of all lanes are in flight at once.
 #define EI_DONE 1u
 #define EI_GENERIC 2u
-struct Pending {
-  uint32_t w[2], bits[2], lbr[2], ubr[2];
+struct Pending {  // (scalar fields, no indexing: the struct must live in registers)
+  uint32_t w0, b0, l0, u0, w1, b1, l1, u1;
   __device__ __forceinline__ void reset() {
-    bits[0] = bits[1] = 0;
-    lbr[0] = lbr[1] = ECNE_NO_LB;
-    ubr[0] = ubr[1] = ECNE_NO_UB;
-    w[0] = w[1] = 0;
+    w0 = w1 = 0;
+    b0 = b1 = 0;
+    l0 = l1 = ECNE_NO_LB;
+    u0 = u1 = ECNE_NO_UB;
   }
-  __device__ __forceinline__ bool has(int s) const { return (bits[s] | lbr[s] | ~ubr[s]) != 0; }
+  __device__ __forceinline__ bool has0() const { return (b0 | l0 | ~u0) != 0; }
+  __device__ __forceinline__ bool has1() const { return (b1 | l1 | ~u1) != 0; }
   __device__ __forceinline__ void add(uint32_t wire, uint32_t b, uint32_t l = ECNE_NO_LB, uint32_t u = ECNE_NO_UB) {
-    const int s = (has(0) && w[0] != wire) ? 1 : 0;  // (an inline row updates at most two wires)
-    w[s] = wire;
-    bits[s] |= b;
-    lbr[s] = l > lbr[s] ? l : lbr[s];
-    ubr[s] = u < ubr[s] ? u : ubr[s];
+    if (has0() && w0 != wire) {  // (an inline row updates at most two wires)
+      w1 = wire;
+      b1 |= b;
+      l1 = l > l1 ? l : l1;
+      u1 = u < u1 ? u : u1;
+    } else {
+      w0 = wire;
+      b0 |= b;
+      l0 = l > l0 ? l : l0;
+      u0 = u < u0 ? u : u0;
+    }
   }
 };
 __device__ __forceinline__ void emit_pending(const Dev&, int wbuf, int list, const Pending& p) {
-  if (p.has(0) || p.has(1))
-    emit2_impl(wbuf, list, p.w[0], p.bits[0], p.lbr[0], p.ubr[0], p.w[1], p.bits[1], p.lbr[1], p.ubr[1]);
+  if (p.has0() || p.has1()) emit2_impl(wbuf, list, p.w0, p.b0, p.l0, p.u0, p.w1, p.b1, p.l1, p.u1);
 }
 __device__ __forceinline__ uint32_t eval_inline(const Dev&, int rbuf, uint32_t row, const InlineRow& r, const uint32_t* f,
                                             uint32_t bepoch, Pending& out) {
@@ -632,8 +638,12 @@ __device__ __noinline__ void p2_resolve_group(const Dev&, int pl, uint32_t c) {
   if (d.p2_k[c] > ECNE_P2_KMAX) {
     // more unknowns than the enumeration of k! permutations is good for: queued, and decided by a whole block after the
     // resolve barrier (p2_big_slot).  The members of a slot share k (it is part of the key), so this is a property of the slot.
-    const unsigned int i = atomicAdd(&d.st->p2_big_n, 1u);
-    if (d.p2_k[c] > ECNE_P2_KBIG || i >= P2_BIGQ_CAP)
+    if (d.p2_k[c] > ECNE_P2_KBIG) {
+      raise(d, ECNE_E_UNSUPPORTED);
+      return;
+    }
+    const unsigned int i = atomicAdd(&d.st->p2_big_n, 1u);  // (every counted entry below the cap is written)
+    if (i >= P2_BIGQ_CAP)
       raise(d, ECNE_E_UNSUPPORTED);
     else
       d.p2_bigq[i] = c;
@@ -1933,7 +1943,10 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
               if (kk[h] >= 0) {
                 Pending pend;
                 const uint32_t e = eval_inline(d, rbuf, d.row_lo + tid + (uint32_t)kk[h] * nthreads, rr[h], ff[h], bepoch, pend);
-                emit_pending(d, wbuf, elist, pend);
+                // (one emit per update here: measured against the paired emit2_impl — which wins where ONE warp waits for its
+                // atomics, the solo and frontier-driven rounds — the plain routine is 1-2 % faster under a full grid)
+                if (pend.has0()) emit(d, wbuf, elist, pend.w0, pend.b0, pend.l0, pend.u0);
+                if (pend.has1()) emit(d, wbuf, elist, pend.w1, pend.b1, pend.l1, pend.u1);
                 if (e & EI_DONE) live.clear(kk[h]);
                 if (e & EI_GENERIC) slow.set(kk[h]);
               }
