@@ -43,6 +43,9 @@ def main():
     table = json.load(open(jpath)) if os.path.exists(jpath) else {}
     for arg in sys.argv[1:]:
         key, rep = arg.split("=", 1)
+        tag = "r02"
+        if "@" in key:
+            key, tag = key.split("@", 1)
         launches, units = raw_page(rep)
         solve = [l for l in launches if "k_solve" in l.get("Kernel Name", "")]
         if not solve:
@@ -51,7 +54,7 @@ def main():
         l = solve[-1]
         rd = to_bytes(l["dram__bytes_read.sum"], units["dram__bytes_read.sum"])
         wr = to_bytes(l["dram__bytes_write.sum"], units["dram__bytes_write.sum"])
-        summary = os.path.join("profiles", "r02_k_solve_%s_ncu.csv" % key)
+        summary = os.path.join("profiles", "%s_k_solve_%s_ncu.csv" % (tag, key))
         with open(os.path.join(ROOT, summary), "w") as f:
             f.write("# ncu --set full --clock-control none, last k_solve launch of %s (%s)\n" % (os.path.basename(rep), l["Kernel Name"]))
             f.write("metric,unit,value\n")
