@@ -569,3 +569,22 @@ def test_big_group_that_completes_in_the_second_outer_round(chain_open_max):
         lib.ecne_set_option(b"chain_open_max", 4096)
     assert st == ost == 0
     assert g.unique_bytes() == o.unique_bytes() and g.c.n_unique == 1 + 9 + 2 and g.c.outer_rounds >= 3
+
+
+# ---- rows with hundreds / thousands of terms (one warp per constraint) ------------------------------------------------
+@pytest.mark.parametrize("nbits,out_known", [(300, True), (300, False), (700, True), (2100, True)])
+def test_rows_with_hundreds_of_terms(nbits, out_known):
+    """A bit decomposition with hundreds of terms (Case 3 on a long row), its Boolean rows (Case 2a), and a second long
+    row that Case 1 closes.  (A block per such row was built and measured in round 2: no faster than a warp per row —
+    two rows per block one after the other cost what two warps side by side do — and 25 % slower on S16; dropped.)"""
+    bits = list(range(3, 3 + nbits))
+    out, extra = 2, 3 + nbits
+    rows = [({b: 1}, {b: 1, 1: -1}, {}) for b in bits]                       # b * (b - 1) = 0
+    rows.append(({}, {}, {out: 1, **{b: -pow(2, i, P) for i, b in enumerate(bits)}}))   # out = sum 2^i b_i
+    rows.append(({}, {}, {extra: 1, **{b: 3 + i for i, b in enumerate(bits)}}))         # extra + sum (3 + i) b_i = 0
+    m = MiniR1CS(rows, n_vars=extra, known=[1, out] if out_known else [1], targets=[extra])
+    st, g, ost, o = both(m)
+    assert st == ost == 0, api._engine().ecne_last_error()
+    assert g.unique_bytes() == o.unique_bytes() and g.known_bytes() == o.known_bytes()
+    assert np.array_equal(g.lb, o.lb) and np.array_equal(g.ub, o.ub)
+    assert bool(g.c.verdict) == bool(o.c.verdict)
