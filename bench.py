@@ -554,7 +554,8 @@ def main():
         ach_t = b_eval * ev_t / (tsw / 1e3) / 1e9
         d_ach_t = b_eval * dev_t / (d_ms_t / 1e3) / 1e9 if d_ms_t > 0 else 0.0
         tr_t = measured_traffic("tiled%d" % K) if world == 1 else None
-        tiled = {"tile": K, "n_gpus": world, "rows": t.n_rows, "row_record_bytes": 32 * t.n_rows, "evals_per_step": ev_t,
+        tiled = {"tile": K, "n_gpus": world, "sharded": bool(res_t.c.sharded), "rows": t.n_rows, "row_record_bytes": 32 * t.n_rows,
+                 "evals_per_step": ev_t,
                  "value": ev_t / (tso / 1e3), "unit": UNIT, "ms_solve": tso,
                  "kernel_ms_per_step": tsw, "achieved": ach_t, "peak": peak * world, "frac": ach_t / (peak * world),
                  "traffic": (tr_t or {}).get("dram_bytes"), "traffic_source": (tr_t or {}).get("source"),

@@ -55,6 +55,10 @@ struct Global {
   // problem is solved by every rank on all rows without any exchange (a sharded round costs a cross-GPU barrier,
   // ~15-25 us, which a sweep of a few 10^5 rows does not earn back: ecdsa's 694 k rows sweep in ~20 us)
   long long shard_min_rows = 2000000;
+  // ... and at least this many rows PER GPU: every rank applies every record of a sharded round to its replica of the
+  // wire state, so only the sweep itself shrinks with the world size — measured on S16 (11.1 M rows): 12.3 ms on one
+  // GPU, 12.6 sharded over two, 14.2 sharded over eight.  shard_min_rows == 0 forces sharding regardless.
+  long long shard_min_rows_per_gpu = 4000000;
   // which build of the solve kernel: 0 = by size (a GPU that sweeps at least `wide_min_rows` rows takes the 1024-thread
   // build), 1 = 512 threads x 128 registers, 2 = 1024 x 64
   long long solve_variant = 0;
@@ -336,6 +340,8 @@ extern "C" int ecne_set_option(const char* key, int64_t value) {
     G.wide_min_rows = value < 0 ? 0 : value;
   else if (k == "shard_min_rows")
     G.shard_min_rows = value < 0 ? 0 : value;
+  else if (k == "shard_min_rows_per_gpu")
+    G.shard_min_rows_per_gpu = value < 0 ? 0 : value;
   else if (k == "p2_hash_bits")
     G.p2_hash_bits = value < 0 ? 0 : (value > 56 ? 56 : value);
   else
@@ -460,7 +466,8 @@ int upload_impl(const ecne_problem_t* problem, const DevSystem* dev0, ecne_resid
     }
   if (world > 1) {
     const uint64_t n_rows = dev0 ? dev0->N : problem->n_rows;
-    const bool shard = (long long)n_rows >= G.shard_min_rows;
+    const bool shard = G.shard_min_rows == 0 || ((long long)n_rows >= G.shard_min_rows &&
+                                                 (long long)(n_rows / (uint64_t)world) >= G.shard_min_rows_per_gpu);
     std::vector<unsigned long long> cuts;
     if (shard && dev0) {  // the row offsets live on the device: the cut points are found there
       cuts.resize(world + 1);

@@ -225,7 +225,8 @@ int ecne_shard_rows(const ecne_problem_t* problem, int rank, int world, uint64_t
  * 0: always dense); "grid_blocks": launch the solve kernel with fewer blocks than SMs (0: one per SM);
  * "shard_min_rows": on several GPUs, problems with at least this many rows have their dense sweeps split over the
  * GPUs, smaller ones are solved by every GPU in full without any exchange (2 000 000; 0: always shard — must be the
- * same on every rank);
+ * same on every rank); "shard_min_rows_per_gpu": ... and only when every GPU gets at least this many rows (4 000 000:
+ * every rank applies every record of a sharded round, only the sweep shrinks with the number of GPUs);
  * "chain_open_max": once the linear-system sweep has at most this many rows left to look at (and the frontier is small),
  * ONE block runs whole outer rounds — special constraints, Jacobi rounds, linear systems, IsZero — without any grid
  * barrier (4096; 0: never; results do not depend on it);

@@ -57,7 +57,7 @@ for name in names:
             # A sharded round counts a wire that rows of two ranks changed twice when it sizes the next round, so a
             # round near the dense / frontier threshold can be swept densely on N GPUs and not on one: at most one
             # extra sweep of the rows per such round, never a different result.
-            "same evals as 1 GPU": abs(int(res.c.constraint_evals) - int(r1.c.constraint_evals)) <= 0.05 * r1.c.constraint_evals + 2 * reduced.n_rows,
+            "same evals as 1 GPU": abs(int(res.c.constraint_evals) - int(r1.c.constraint_evals)) <= 0.05 * r1.c.constraint_evals + n_gpus * reduced.n_rows,
             "gpus_used": res.c.gpus_used == n_gpus, "sharded": res.c.sharded == (1 if n_gpus > 1 else 0),
         }
         why = ",".join(k for k, v in checks.items() if not v)
