@@ -1551,6 +1551,31 @@ __device__ __noinline__ unsigned int chain_phases(const Dev&, int pl, SpecialsCa
   return block_sync_load(d.rec_count + pl);
 }
 
+// A heavy wire (more than HEAVY_DEG rows) changed: is the next round better off sweeping densely?  Only when the rows
+// listed next to the changed heavy wires are a sizeable part of all rows — ecdsa's rounds 6 and 7 follow ~50 changed
+// selector wires of 1025 rows each, 51 k row evaluations against a sweep of 400 k live rows.  Every block computes the
+// same sum from the same record list (<= HEAVY_SCAN_MAX records; longer lists sweep densely as before).
+#define HEAVY_SCAN_MAX 4096u
+__device__ __noinline__ bool heavy_wants_dense(const Dev&, unsigned int list, unsigned int n) {
+  const Dev& d = c_dev;
+  if (n > HEAVY_SCAN_MAX) return true;
+  __shared__ unsigned int s_hsum;
+  if (threadIdx.x == 0) s_hsum = 0;
+  __syncthreads();
+  unsigned int sum = 0;
+  for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t w = ld_peer_rec(d.recs[list] + i).wire;
+    const uint32_t dg = __ldcg(reinterpret_cast<const uint4*>(d.inv_head) + w).x;
+    if (dg > HEAVY_DEG) sum += dg;
+  }
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  if ((threadIdx.x & 31u) == 0 && sum) atomicAdd(&s_hsum, sum);
+  __syncthreads();
+  const unsigned int total = s_hsum;
+  __syncthreads();
+  return total > d.N / 8u;
+}
+
 // The whole fixpoint (:706-1556) as ONE persistent cooperative launch (148 blocks x 1024 threads):
 //
 //   P0 -> [Jacobi rounds of the single-row rules until no record] -> P2 -> P3 -> P4 -> repeat while
@@ -1644,7 +1669,14 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       unsigned int prev_dn = d.shard ? __ldcg(d.dcnt + pl_r) : n_pl;
       unsigned int prev_own = prev_n;  // leading records of the list that still have to be replayed into the write
                                        // buffer (all of them, except after a sharded round: the phase list is complete)
-      bool dense = outer == 1 || prev_dn > d.sparse_max || (__ldcg(d.bnd_flag + pl_r) & 2u) != 0;
+      bool dense = outer == 1 || prev_dn > d.sparse_max;
+      // a changed heavy wire whose rows are not worth a dense sweep: the round is frontier-driven on the WHOLE grid (one
+      // block, let alone one warp, would stride tens of thousands of listed rows alone)
+      bool heavy_grid = false;
+      if (!dense && (__ldcg(d.bnd_flag + pl_r) & 2u) != 0) {
+        dense = d.shard || heavy_wants_dense(d, prev_list, prev_n);
+        heavy_grid = !dense;
+      }
       unsigned int round = 0;
       while (true) {
         if (ack_pending) {  // the peers may still be reading the record lists of our last sharded round
@@ -1652,7 +1684,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           __syncthreads();
           ack_pending = 0;
         }
-        if (!dense && prev_dn <= SOLO_MAX) {
+        if (!dense && !heavy_grid && prev_dn <= SOLO_MAX) {
           // ---- solo: while the frontier stays small, block 0 runs the Jacobi rounds alone; a round
           // boundary is a block barrier + one release fence + one acquire load (which also drops this
           // SM's L1 lines, as the grid barrier does) instead of a grid barrier
@@ -1885,7 +1917,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
           rbuf ^= 1;
           prev_dn = sdn;
           prev_own = prev_n;
-          dense = sdn > d.sparse_max || hv != 0;
+          dense = sdn > d.sparse_max || (hv != 0 && (d.shard || heavy_wants_dense(d, prev_list, prev_n)));
+          heavy_grid = hv != 0 && !dense;
           continue;
         }
         const int wbuf = rbuf ^ 1;
@@ -2129,7 +2162,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
         list = (list + 1) % 3;
         rbuf = wbuf;
         prev_dn = dn;
-        dense = dn > d.sparse_max || heavy;
+        dense = dn > d.sparse_max || (heavy && (d.shard || heavy_wants_dense(d, prev_list, prev_n)));
+        heavy_grid = heavy && !dense;
       }
       rounds_total += round;
     }

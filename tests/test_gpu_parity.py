@@ -588,3 +588,34 @@ def test_rows_with_hundreds_of_terms(nbits, out_known):
     assert g.unique_bytes() == o.unique_bytes() and g.known_bytes() == o.known_bytes()
     assert np.array_equal(g.lb, o.lb) and np.array_equal(g.ub, o.ub)
     assert bool(g.c.verdict) == bool(o.c.verdict)
+
+
+def test_bound_overwrite_deviation_is_pinned():
+    """DESIGN.md §6 / ADVICE r1: the engine merges bounds by intersection, the reference OVERWRITES them (make_bounds,
+    :190-201).  They only differ when a rule would loosen a bound, i.e. on an inconsistent circuit: x = 20 together with
+    x = sum of four bits.  The reference's answer then depends on its queue order — with the rows in one order it stops at
+    [20, 20], in the other order Case 2b and Case 3 undo each other forever (the oracle's pop guard trips).  The engine
+    terminates on both orders with the same determined set and the empty interval lb = 20 > ub = 15."""
+    bits = [3, 4, 5, 6]
+    rows = [({b: 1}, {b: 1, 1: -1}, {}) for b in bits]
+    rows.append(({}, {}, {2: 1, **{b: -(2 ** i) for i, b in enumerate(bits)}}))
+    rows.append(({}, {}, {1: -20, 2: 1}))
+    results = []
+    for order in (rows, rows[:4] + [rows[5], rows[4]]):
+        m = MiniR1CS(order, n_vars=7, known=[1], targets=[2])
+        st, g = gpu_solve(m, [], m, False, full_state=True)
+        assert st == 0, api._engine().ecne_last_error()
+        results.append(g)
+        assert _toint(g.lb[1]) == 20 and _toint(g.ub[1]) == 15
+    assert results[0].unique_bytes() == results[1].unique_bytes()
+    m = MiniR1CS(rows, n_vars=7, known=[1], targets=[2])
+    o = oracle_lib.solve(m, [], m.known, m.targets, m.n_vars, False)
+    assert results[0].unique_bytes() == o.unique_bytes() and bool(results[0].c.verdict) == bool(o.c.verdict)
+    assert (_toint(o.lb[1]), _toint(o.ub[1])) == (20, 20)
+    oracle_lib.lib().ecne_oracle_set_max_pops(100000)
+    try:
+        m2 = MiniR1CS(rows[:4] + [rows[5], rows[4]], n_vars=7, known=[1], targets=[2])
+        with pytest.raises(oracle_lib.OracleError):
+            oracle_lib.solve(m2, [], m2.known, m2.targets, m2.n_vars, False)
+    finally:
+        oracle_lib.lib().ecne_oracle_set_max_pops(0)
