@@ -118,6 +118,8 @@ struct Status {            // device-resident, read back once per solve
   unsigned int solo[8];            // where the grid resumes after block 0 ran rounds alone: n, list, rbuf, round, bepoch, gr
   // rows the linear-system sweep left open, by parity of the outer round that counted them (the other slot is cleared
   // for the next round): block 0 takes whole outer rounds over once this is small (kernels.cu "chain stretch")
+  unsigned int p2_full;            // some table slot of this sweep has as many members as its sets have unknowns: the
+                                   // resolve pass has something to look at (else it, and its barrier, are skipped)
   unsigned int p2_big_n;           // linear-system groups with more than ECNE_P2_KMAX unknowns queued by the resolvers
   unsigned int p2_open_n[2];
   // where the grid resumes after a chain stretch: position (CH_*), outer, prog_prev, n_pl, stop

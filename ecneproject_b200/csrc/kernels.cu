@@ -118,8 +118,11 @@ __device__ __forceinline__ void p2_candidate(const Dev& d, uint32_t row, unsigne
     slot = (slot + 1) & d.h_mask;
   }
   d.p2_slot[i] = slot;
-  atomicAdd(d.h_cnt + slot, 1u);
+  const uint32_t before = atomicAdd(d.h_cnt + slot, 1u);
   d.p2_next[i] = atomicExch(d.h_head + slot, i + 1);
+  // a set can only be decided once k rows share it: until some slot holds k members nobody has anything to resolve
+  // (two sets colliding in a slot can only make this fire early, never late)
+  if (before + 1u >= k && !__ldcg(&d.st->p2_full)) d.st->p2_full = 1u;
 }
 
 // P2 qualification of one row through the CSR (generic path): every non-unique wire appears in C
@@ -1494,10 +1497,15 @@ __device__ __noinline__ unsigned int chain_phases(const Dev&, int pl, SpecialsCa
   unsigned int n_cand = block_sync_load(&d.st->p2_cand);
   if (n_cand > d.N) n_cand = d.N;
   *n_cand_io = n_cand;
-  // ---- P2 resolve (:1386-1417)
-  for (uint32_t c = t; c < n_cand; c += nt) p2_resolve_group(d, pl, c);
-  unsigned int n_x = block_sync_load(d.rec_count + pl);
-  if (p2_big_phase(d, pl, 0, 1)) n_x = block_sync_load(d.rec_count + pl);
+  // ---- P2 resolve (:1386-1417): only when some slot holds as many members as its sets have unknowns
+  unsigned int n_x;
+  if (__ldcg(&d.st->p2_full)) {  // (uniform: read behind the barrier)
+    for (uint32_t c = t; c < n_cand; c += nt) p2_resolve_group(d, pl, c);
+    n_x = block_sync_load(d.rec_count + pl);
+    if (p2_big_phase(d, pl, 0, 1)) n_x = block_sync_load(d.rec_count + pl);
+  } else {
+    n_x = __ldcg(d.rec_count + pl);  // the k = 1 rows the scan decided on the spot
+  }
   {  // replay the P2 updates into buffer 0, clear the table (P3 can only tag in the first outer round: not here)
     const unsigned int nx = n_x > d.rec_cap ? d.rec_cap : n_x;
     for (uint32_t i = t; i < nx; i += nt) {
@@ -1512,6 +1520,7 @@ __device__ __noinline__ unsigned int chain_phases(const Dev&, int pl, SpecialsCa
     }
     if (t == 0) {
       d.st->p2_cand = 0;
+      d.st->p2_full = 0;
       d.st->p2_big_n = 0;
     }
   }
@@ -2250,10 +2259,15 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
     cand_total += n_cand;
     cand_max = n_cand > cand_max ? n_cand : cand_max;
     PROF(2);
-    for (uint32_t c = tid; c < n_cand; c += nthreads) p2_resolve_group(d, pl, c);
-    unsigned int n_x = sync_and_load(d, d.rec_count + pl);
-    // groups with more than ECNE_P2_KMAX unknowns were queued by their resolvers: a block each, one more barrier
-    if (p2_big_phase(d, pl, blockIdx.x, gridDim.x)) n_x = sync_and_load(d, d.rec_count + pl);
+    unsigned int n_x;
+    if (__ldcg(&d.st->p2_full)) {  // (uniform: read behind the scan's barrier)
+      for (uint32_t c = tid; c < n_cand; c += nthreads) p2_resolve_group(d, pl, c);
+      n_x = sync_and_load(d, d.rec_count + pl);
+      // groups with more than ECNE_P2_KMAX unknowns were queued by their resolvers: a block each, one more barrier
+      if (p2_big_phase(d, pl, blockIdx.x, gridDim.x)) n_x = sync_and_load(d, d.rec_count + pl);
+    } else {
+      n_x = __ldcg(d.rec_count + pl);  // the k = 1 rows the scan decided on the spot
+    }
     PROF(3);
     // replay the P2 updates into buffer 0, clear the table, P3 claim (reads buffer 1: complete, untouched
     // here).  P3 can only ever tag in the first outer round: a wire it looks at is either unique (for
@@ -2273,6 +2287,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MIN_BLOCKS)
       }
       if (tid == 0) {
         d.st->p2_cand = 0;
+        d.st->p2_full = 0;
         d.st->p2_big_n = 0;
         d.st->p2_open_n[(outer + 1u) & 1u] = 0;  // the next round's scan counts the rows it leaves open here
       }
