@@ -580,7 +580,12 @@ def main():
                    "sha_unique": sha_unique, "golden_sha_unique": want_sha, "matches_golden": bool(matches_all),
                    "evals_note": "row visits actually executed: a row the live mask / the open-row bitmap has retired "
                                  "is neither visited nor counted (the linear-system sweep of round 1 counted every live "
-                                 "row in every outer round: 15.0 M visits for the same verdict)",
+                                 "row in every outer round: 15.0 M visits for the same verdict; two rounds that used to be "
+                                 "dense sweeps are frontier-driven now) - evals/s FALLS when the engine avoids work, the time "
+                                 "per verdict is the like-for-like figure",
+                   # the same verdict's work as this engine counted it at the end of round 1 (15 031 701 row visits, FIFO
+                   # reference: 59 920 653) over today's time: what `value` would read had the schedule not changed
+                   "value_at_round1_evals": 15031701 / (ms_step / 1e3),
                    "rule_evals_per_step": rule_evals,
                    "l2": "flushed between timed steps (256 MB fill)",
                    "parallelism": "1 GPU" if world == 1 else (
