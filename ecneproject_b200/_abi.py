@@ -66,6 +66,8 @@ class R1CSStruct(C.Structure):
         ("targets", u32p), ("n_targets", C.c_uint64),
         ("n_pub_out", C.c_uint32), ("n_pub_in", C.c_uint32), ("n_prv_in", C.c_uint32),
         ("field_size", C.c_uint32), ("n_labels", C.c_uint64),
+        ("coef_class", u8p), ("coef_other", u64p), ("coef_other_term", u32p), ("n_coef_other", C.c_uint64),
+        ("seg_ptr32", u32p),
     ]
 
 
@@ -94,6 +96,7 @@ ENGINE_SYMBOLS = [
     "ecne_set_option", "ecne_fr_batch",
     "ecne_abstract_begin", "ecne_abstract_apply", "ecne_abstract_sizes", "ecne_abstract_export",
     "ecne_abstract_upload", "ecne_abstract_free",
+    "ecne_abstract_prepare", "ecne_abstract_apply_prepared", "ecne_abstract_prepared_free",
 ]
 HOST_SYMBOLS = [
     "ecne_read_r1cs", "ecne_read_r1cs_mem", "ecne_r1cs_free", "ecne_specials_new",
@@ -204,6 +207,12 @@ def engine_lib():
         lib.ecne_abstract_begin.restype = C.c_int
         lib.ecne_abstract_apply.argtypes = [C.c_void_p, C.c_int32, Pp, u64p]
         lib.ecne_abstract_apply.restype = C.c_int
+        lib.ecne_abstract_prepare.argtypes = [Pp, C.POINTER(C.c_void_p)]
+        lib.ecne_abstract_prepare.restype = C.c_int
+        lib.ecne_abstract_apply_prepared.argtypes = [C.c_void_p, C.c_int32, Pp, C.c_void_p, u64p]
+        lib.ecne_abstract_apply_prepared.restype = C.c_int
+        lib.ecne_abstract_prepared_free.argtypes = [C.c_void_p]
+        lib.ecne_abstract_prepared_free.restype = None
         lib.ecne_abstract_sizes.argtypes = [C.c_void_p, u64p]
         lib.ecne_abstract_sizes.restype = C.c_int
         lib.ecne_abstract_export.argtypes = [C.c_void_p, u64p, u32p, u64p, i32p, u64p, u32p, u64p, u32p]

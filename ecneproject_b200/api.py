@@ -65,6 +65,12 @@ class R1CS:
         self.coef = _as_np(s.coef, 4 * self.nnz, np.uint64).reshape(-1, 4)
         self.known = _as_np(s.known, int(s.n_known), np.uint32)
         self.targets = _as_np(s.targets, int(s.n_targets), np.uint32)
+        # the compact form of the same rows, when the reader made it (include/ecne_host.h)
+        self.compact = None
+        if s.coef_class and s.seg_ptr32:
+            n_o = int(s.n_coef_other)
+            self.compact = (_as_np(s.coef_class, self.nnz, np.uint8), _as_np(s.coef_other, 4 * max(n_o, 1), np.uint64)[:4 * n_o],
+                            _as_np(s.coef_other_term, max(n_o, 1), np.uint32)[:n_o], _as_np(s.seg_ptr32, 3 * self.n_rows + 1, np.uint32))
         self.n_pub_out = int(s.n_pub_out)
         self.n_pub_in = int(s.n_pub_in)
         self.n_prv_in = int(s.n_prv_in)
@@ -187,7 +193,17 @@ class ProblemHandle:
         p.n_rows = constraints.n_rows
         p.n_vars = num_variables
         p.col = self._buf(constraints.col, np.uint32, _abi.u32p)
-        if compact:
+        ready = getattr(constraints, "compact", None)
+        if compact and ready is not None:  # the reader made the compact form already: no pass over the coefficients
+            cls, other, term, seg32 = ready
+            p.seg_ptr = None
+            p.seg_ptr32 = self._buf(seg32, np.uint32, _abi.u32p)
+            p.coef = None
+            p.coef_class = self._buf(cls, np.uint8, _abi.u8p)
+            p.coef_other = self._buf(other, np.uint64, _abi.u64p)
+            p.coef_other_term = self._buf(term, np.uint32, _abi.u32p)
+            p.n_coef_other = len(term)
+        elif compact:
             cls, other, term = compact_coef(constraints.coef)
             p.seg_ptr = None
             p.seg_ptr32 = self._buf(np.asarray(constraints.seg_ptr).astype(np.uint32), np.uint32, _abi.u32p)
@@ -407,6 +423,35 @@ def abstraction(function_name, constraints, sub_equation, specials=None):
     return sp, R1CS(red)
 
 
+class PreparedTrusted:
+    """A trusted circuit with the part of abstraction() that depends on it alone done ahead (ecne_abstract_prepare:
+    host work that touches neither the GPU nor any library state — run it on another thread while the main circuit is
+    still being read)."""
+
+    def __init__(self, function_name, sub):
+        self.name = function_name
+        self.sub = sub
+        self.ph = ProblemHandle(sub, None, sub.known, sub.targets, sub.n_vars)
+        self.handle = C.c_void_p()
+        st = _engine().ecne_abstract_prepare(C.byref(self.ph.c), C.byref(self.handle))
+        if st != 0:
+            _raise(st, "ecne_abstract_prepare failed")
+
+    def __len__(self):
+        return len(self.sub)
+
+    def free(self):
+        if self.handle:
+            _engine().ecne_abstract_prepared_free(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class DeviceAbstraction:
     """abstraction() (R1CSConstraintSolver.jl:237-395) on the GPU (include/ecne_abi.h "abstraction() on the device"):
     the unreduced system is uploaded once, every `apply` replaces the windows isomorphic to one trusted circuit by
@@ -416,7 +461,9 @@ class DeviceAbstraction:
     def __init__(self, main):
         lib = _engine()
         self.main = main
-        self.ph = ProblemHandle(main, None, main.known, main.targets, main.n_vars)
+        # (the compact form the reader made beside the full one: a quarter of the bytes cross PCIe)
+        self.ph = ProblemHandle(main, None, main.known, main.targets, main.n_vars,
+                                compact=getattr(main, "compact", None) is not None)
         self.handle = C.c_void_p()
         self.names = []
         st = lib.ecne_abstract_begin(C.byref(self.ph.c), C.byref(self.handle))
@@ -425,9 +472,13 @@ class DeviceAbstraction:
 
     def apply(self, function_name, sub):
         lib = _engine()
-        sp = ProblemHandle(sub, None, sub.known, sub.targets, sub.n_vars)
         n = C.c_uint64(0)
-        st = lib.ecne_abstract_apply(self.handle, _KIND_OF_NAME.get(function_name, _abi.SPECIAL_GENERIC), C.byref(sp.c), C.byref(n))
+        if isinstance(sub, PreparedTrusted):
+            st = lib.ecne_abstract_apply_prepared(self.handle, _KIND_OF_NAME.get(function_name, _abi.SPECIAL_GENERIC),
+                                                  C.byref(sub.ph.c), sub.handle, C.byref(n))
+        else:
+            sp = ProblemHandle(sub, None, sub.known, sub.targets, sub.n_vars)
+            st = lib.ecne_abstract_apply(self.handle, _KIND_OF_NAME.get(function_name, _abi.SPECIAL_GENERIC), C.byref(sp.c), C.byref(n))
         if st != 0:
             _raise(st, lib.ecne_last_error().decode())
         self.names += [function_name] * int(n.value)
@@ -477,14 +528,26 @@ class DeviceAbstraction:
             pass
 
 
+def read_and_prepare(input_r1cs, trusted_r1cs=(), trusted_r1cs_names=()):
+    """The host half of solve_with_device_abstraction: the main circuit is parsed on a worker thread (the native parser
+    is multi-threaded itself and releases the GIL) while this thread reads the — small — trusted circuits and prepares
+    them (ecne_abstract_prepare).  Returns (main, [(name, PreparedTrusted)] longest first, :527)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(1) as ex:
+        fut = ex.submit(readR1CS, input_r1cs)
+        function_list = [(trusted_r1cs_names[i], PreparedTrusted(trusted_r1cs_names[i], readR1CS(trusted_r1cs[i])))
+                         for i in range(len(trusted_r1cs))]
+        function_list.sort(key=lambda x: -len(x[1]))  # stable, longest first (:527)
+        main = fut.result()
+    return main, function_list
+
+
 def solve_with_device_abstraction(input_r1cs, trusted_r1cs=(), trusted_r1cs_names=(), secp_solve=False, full_state=False):
     """solveWithTrustedFunctions (:502-581) with abstraction() on the GPU: parse (host), upload the unreduced system,
     abstract the trusted circuits longest first (:527-544) on the device, classify in place, solve.
     Returns (verdict, SolveResult, DeviceAbstraction sizes)."""
     global last_result
-    main = readR1CS(input_r1cs)
-    function_list = [(trusted_r1cs_names[i], readR1CS(trusted_r1cs[i])) for i in range(len(trusted_r1cs))]
-    function_list.sort(key=lambda x: -len(x[1]))  # stable, longest first (:527)
+    main, function_list = read_and_prepare(input_r1cs, trusted_r1cs, trusted_r1cs_names)
     da = DeviceAbstraction(main)
     try:
         for name, sub in function_list:

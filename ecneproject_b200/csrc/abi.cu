@@ -564,14 +564,50 @@ extern "C" int ecne_abstract_begin(const ecne_problem_t* main, ecne_abstracted_t
   *out = a;
   return ECNE_OK;
 }
+struct ecne_prepared {
+  PreparedSub* p = nullptr;
+};
+// (touches neither CUDA nor the library's global state — not even the last-error string: callable from another thread)
+extern "C" int ecne_abstract_prepare(const ecne_problem_t* sub, ecne_prepared_t** out) {
+  if (!out) return ECNE_E_BADARG;
+  *out = nullptr;
+  PreparedSub* p = abstraction_prepare(sub);
+  if (!p) return ECNE_E_BADARG;
+  ecne_prepared_t* h = new (std::nothrow) ecne_prepared_t();
+  if (!h) {
+    abstraction_prepared_free(p);
+    return ECNE_E_BOUNDS;
+  }
+  h->p = p;
+  *out = h;
+  return ECNE_OK;
+}
+extern "C" void ecne_abstract_prepared_free(ecne_prepared_t* p) {
+  if (!p) return;
+  abstraction_prepared_free(p->p);
+  delete p;
+}
+static int abstract_apply_impl(ecne_abstracted_t* a, int32_t kind, const ecne_problem_t* sub, const ecne_prepared_t* prepared,
+                               uint64_t* n_matches);
 extern "C" int ecne_abstract_apply(ecne_abstracted_t* a, int32_t kind, const ecne_problem_t* sub, uint64_t* n_matches) {
+  return abstract_apply_impl(a, kind, sub, nullptr, n_matches);
+}
+extern "C" int ecne_abstract_apply_prepared(ecne_abstracted_t* a, int32_t kind, const ecne_problem_t* sub,
+                                            const ecne_prepared_t* prepared, uint64_t* n_matches) {
+  if (!prepared || !prepared->p) return fail(ECNE_E_BADARG, "null prepared trusted circuit");
+  return abstract_apply_impl(a, kind, sub, prepared, n_matches);
+}
+static int abstract_apply_impl(ecne_abstracted_t* a, int32_t kind, const ecne_problem_t* sub, const ecne_prepared_t* prepared,
+                               uint64_t* n_matches) {
   if (!a || !sub) return fail(ECNE_E_BADARG, "null argument");
   CKA(cudaSetDevice(a->device));
   std::string err;
   int st = dev_abstraction(&a->sys, kind, sub, &a->sp, n_matches, a->stream, err, &a->stats,
-                           [a]() { return a->wait_upload(); });
+                           [a]() { return a->wait_upload(); }, prepared ? prepared->p : nullptr);
   if (st != ECNE_OK && a->upload_status != ECNE_OK) return fail(a->upload_status, a->upload_err);
   if (st != ECNE_OK) return fail(st, err);
+  if (getenv("ECNE_HOST_PROF"))
+    fprintf(stderr, "[ecne dev] upload of the unreduced system (uploader thread) %.3f ms\n", a->ms_h2d);
   if (getenv("ECNE_HOST_PROF"))
     fprintf(stderr, "[ecne dev] abstraction: trusted circuit prepared on the host %.3f ms | hashes %.3f ms | candidates %.3f ms (%llu) | "
                     "verification %.3f ms (%llu matches) | compaction %.3f ms (cumulative over the calls of this handle)\n",

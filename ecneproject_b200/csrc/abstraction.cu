@@ -68,37 +68,90 @@ __host__ __device__ __forceinline__ int cmp256(const T* a, const U* b) {
 }
 
 // ---- row hashes ------------------------------------------------------------------------------------------------
-__global__ void k_abs_row_hash(uint64_t N, const unsigned long long* seg, const fr::u256* coef,
-                               unsigned long long* out) {
-  const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned int lane = threadIdx.x & 31u;
+// rows with at most ABS_HASH_SHORT stored terms (all but a few hundred of ecdsa's 1.09 M): a thread each; the sums are
+// the same commutative sums the warp version reduces with shuffles
+#define ABS_HASH_SHORT 16u
+__global__ void k_abs_row_hash_short(uint64_t N, const unsigned long long* seg, const fr::u256* coef, unsigned long long* out) {
+  const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= N) return;
+  const unsigned long long s0 = seg[3 * row], s3 = seg[3 * row + 3];
+  if (s3 - s0 > ABS_HASH_SHORT) return;
   unsigned long long h = 0x1234567ULL;
+  unsigned long long b = s0;
   for (int f = 0; f < 3; ++f) {
+    const unsigned long long e = seg[3 * row + f + 1];
     unsigned long long s = 0, cnt = 0;
-    for (uint64_t t = seg[3 * row + f] + lane; t < seg[3 * row + f + 1]; t += 32) {
+    for (unsigned long long t = b; t < e; ++t) {
       const fr::u256 c = coef[t];
       if (!fr::is_zero(c)) {
         s += sig_term(0u, c.v, 0x51ed270b1ULL);
         cnt += 1;
       }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    }
     h = abs_mix64(h ^ s) + cnt * 0x9e3779b97f4a7c15ULL + (unsigned long long)f;
+    b = e;
   }
-  if (lane == 0) out[row] = h;
+  out[row] = h;
 }
+// the few long rows: a warp looks at 32 consecutive rows (one coalesced read of their lengths) and hashes the long ones
+// among them with all its lanes, one after the other
+__global__ void k_abs_row_hash(uint64_t N, const unsigned long long* seg, const fr::u256* coef,
+                               unsigned long long* out) {
+  const uint64_t row0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u;
+  const unsigned int lane = threadIdx.x & 31u;
+  if (row0 >= N) return;
+  const uint64_t mine = row0 + lane;
+  const bool is_long = mine < N && seg[3 * mine + 3] - seg[3 * mine] > ABS_HASH_SHORT;
+  for (unsigned int m = __ballot_sync(0xffffffffu, is_long); m; m &= m - 1) {
+    const uint64_t row = row0 + (unsigned int)(__ffs((int)m) - 1);
+    unsigned long long h = 0x1234567ULL;
+    for (int f = 0; f < 3; ++f) {
+      unsigned long long s = 0, cnt = 0;
+      for (uint64_t t = seg[3 * row + f] + lane; t < seg[3 * row + f + 1]; t += 32) {
+        const fr::u256 c = coef[t];
+        if (!fr::is_zero(c)) {
+          s += sig_term(0u, c.v, 0x51ed270b1ULL);
+          cnt += 1;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      }
+      h = abs_mix64(h ^ s) + cnt * 0x9e3779b97f4a7c15ULL + (unsigned long long)f;
+    }
+    if (lane == 0) out[row] = h;
+  }
+}
+#define ABS_CAND_SERIAL 64u
 __global__ void k_abs_candidates(uint64_t N, uint64_t n, const unsigned long long* hc, const unsigned long long* hs,
                                  unsigned long long* cand, unsigned int* n_cand, unsigned int cap) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i + n > N) return;
-  for (uint64_t j = 0; j + 1 < n; ++j)
-    if (hc[i + j] != hs[j]) return;
+  // Windows of at most ABS_CAND_SERIAL rows are compared here, a thread each.  Longer ones (secp256k1 has 15 935 rows)
+  // are only PROBED at a few positions spread over the window: the 25 threads of ecdsa's true candidates walking 16 k
+  // hashes one after the other WERE the kernel (1.9 ms); the survivors are compared in full by a block each
+  // (k_abs_candidates_full).  The conjunction does not care about the order of the comparisons.
+  if (n > ABS_CAND_SERIAL) {
+    for (uint64_t k = 0; k < 16; ++k) {
+      const uint64_t j = (k * (n - 2)) / 15;
+      if (hc[i + j] != hs[j]) return;
+    }
+  } else {
+    for (uint64_t j = 0; j + 1 < n; ++j)
+      if (hc[i + j] != hs[j]) return;
+  }
   const unsigned int k = atomicAdd(n_cand, 1u);
   if (k < cap) cand[k] = i;
+}
+// a block per probed window: the first n - 1 row hashes line up (:259-270); keep[b] = 1 if so
+__global__ void k_abs_candidates_full(uint64_t n, const unsigned long long* hc, const unsigned long long* hs,
+                                      const unsigned long long* cand, unsigned int* keep) {
+  const uint64_t i = cand[blockIdx.x];
+  bool ok = true;
+  for (uint64_t j = threadIdx.x; j + 1 < n; j += blockDim.x) ok &= hc[i + j] == hs[j];
+  const int all = __syncthreads_and(ok ? 1 : 0);
+  if (threadIdx.x == 0) keep[blockIdx.x] = all ? 1u : 0u;
 }
 
 // ---- the trusted circuit, prepared on the host, as the kernels see it -------------------------------------------
@@ -505,7 +558,7 @@ cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s)
   cudaPointerAttributes at;
   const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
   cudaGetLastError();  // (an unregistered host pointer is reported as an error by older runtimes)
-  if (pinned || bytes < ((size_t)16 << 20) || !g_ring.init())
+  if (pinned || bytes < ((size_t)1 << 20) || !g_ring.init())
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
   const size_t SB = StagingRing::SLOT_BYTES;
   const size_t n_slices = (bytes + SB - 1) / SB;
@@ -561,8 +614,33 @@ int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std
 
 // One abstraction() call on a device-resident system: `S` is replaced by the reduced system, the special
 // constraints of the consumed windows are appended to `sp`.
+struct PreparedSub {
+  SubHost H;
+  uint64_t n_rows, nnz;
+};
+PreparedSub* abstraction_prepare(const ecne_problem_t* sub) {
+  if (!sub || !sub->seg_ptr || sub->n_rows == 0 || !sub->col || !sub->coef) return nullptr;
+  PreparedSub* p = new (std::nothrow) PreparedSub();
+  if (!p) return nullptr;
+  p->n_rows = sub->n_rows;
+  p->nnz = sub->seg_ptr[3 * sub->n_rows];
+  bool ok = false;
+  try {
+    ok = prepare_sub(sub, p->H);
+  } catch (...) {
+    ok = false;
+  }
+  if (!ok) {
+    delete p;
+    return nullptr;
+  }
+  return p;
+}
+void abstraction_prepared_free(PreparedSub* p) { delete p; }
+
 int dev_abstraction(DevSystem* S, int32_t kind, const ecne_problem_t* sub, SpecialsHost* sp, uint64_t* n_matches,
-                    cudaStream_t s, std::string& err, AbstractionStats* stats, const std::function<int()>& ready) {
+                    cudaStream_t s, std::string& err, AbstractionStats* stats, const std::function<int()>& ready,
+                    const PreparedSub* prepared) {
   if (!sub || !sub->seg_ptr || sub->n_rows == 0) {
     err = "trusted circuit without rows";
     return ECNE_E_BADARG;
@@ -579,11 +657,17 @@ int dev_abstraction(DevSystem* S, int32_t kind, const ecne_problem_t* sub, Speci
     tp0 = t;
   };
   const uint64_t n = sub->n_rows;
-  SubHost H;
-  if (!prepare_sub(sub, H)) {
+  SubHost H_local;
+  if (prepared) {
+    if (prepared->n_rows != sub->n_rows || prepared->nnz != sub->seg_ptr[3 * sub->n_rows]) {
+      err = "the prepared trusted circuit is not the one passed with it";
+      return ECNE_E_BADARG;
+    }
+  } else if (!prepare_sub(sub, H_local)) {
     err = "internal: signature hash of the trusted circuit collides under every seed";
     return ECNE_E_INTERNAL;
   }
+  const SubHost& H = prepared ? prepared->H : H_local;
   if (stats) stats->ms_prepare += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
   if (ready) {  // the big system is on the device from here on
     const int rst = ready();
@@ -638,8 +722,12 @@ int dev_abstraction(DevSystem* S, int32_t kind, const ecne_problem_t* sub, Speci
   CKE(tmp.alloc(&d_hs, n + 1));
   CKE(tmp.alloc(&d_ncand, 4));
   CKE(cudaMemsetAsync(d_ncand, 0, 16, s));
-  if (N) k_abs_row_hash<<<(unsigned int)((N * 32 + 255) / 256), 256, 0, s>>>(N, S->seg, S->coef, d_hc);
-  k_abs_row_hash<<<(unsigned int)((n * 32 + 255) / 256), 256, 0, s>>>(n, sd.seg, sd.coef, d_hs);
+  if (N) {
+    k_abs_row_hash_short<<<(unsigned int)((N + 255) / 256), 256, 0, s>>>(N, S->seg, S->coef, d_hc);
+    k_abs_row_hash<<<(unsigned int)((N + 255) / 256), 256, 0, s>>>(N, S->seg, S->coef, d_hc);
+  }
+  k_abs_row_hash_short<<<(unsigned int)((n + 255) / 256), 256, 0, s>>>(n, sd.seg, sd.coef, d_hs);
+  k_abs_row_hash<<<(unsigned int)((n + 255) / 256), 256, 0, s>>>(n, sd.seg, sd.coef, d_hs);
   lap(stats ? &stats->ms_hash : nullptr);
   std::vector<unsigned long long> cand;
   if (N >= n) {
@@ -655,6 +743,21 @@ int dev_abstraction(DevSystem* S, int32_t kind, const ecne_problem_t* sub, Speci
     }
     cand.resize(nc);
     if (nc) CKE(cudaMemcpy(cand.data(), d_cand, (size_t)nc * 8, cudaMemcpyDeviceToHost));
+    if (nc && n > ABS_CAND_SERIAL) {  // the probed windows in full, a block each
+      unsigned int* d_keep = nullptr;
+      CKE(tmp.alloc(&d_keep, nc));
+      std::vector<unsigned int> keep(nc);
+      for (unsigned int b0 = 0; b0 < nc; b0 += 65535u) {
+        const unsigned int nb_ = std::min(65535u, nc - b0);
+        k_abs_candidates_full<<<nb_, 256, 0, s>>>(n, d_hc, d_hs, d_cand + b0, d_keep + b0);
+      }
+      CKE(cudaMemcpyAsync(keep.data(), d_keep, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
+      CKE(cudaStreamSynchronize(s));
+      size_t w = 0;
+      for (unsigned int k = 0; k < nc; ++k)
+        if (keep[k]) cand[w++] = cand[k];
+      cand.resize(w);
+    }
     std::sort(cand.begin(), cand.end());  // ascending window starts, as the reference's loop finds them (:259)
   }
   lap(stats ? &stats->ms_candidates : nullptr);

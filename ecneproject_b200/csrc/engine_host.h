@@ -143,7 +143,7 @@ struct AbstractionStats {
 #ifndef ECNE_E_KEYERROR
 #define ECNE_E_KEYERROR (-10)  // KeyError at R1CSConstraintSolver.jl:381-382 (same code as include/ecne_host.h)
 #endif
-// abstraction.cu: host -> device copy; pageable sources of 16 MB and more go through a ring of pinned slots filled by
+// abstraction.cu: host -> device copy; pageable sources of 1 MB and more go through a ring of pinned slots filled by
 // worker threads, pinned ones (and small ones) straight into cudaMemcpyAsync
 cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s);
 // setup.cu: the rows of `p` (seg_ptr / col / coef in either form of include/ecne_abi.h: full 32-byte coefficients, or
@@ -170,8 +170,16 @@ int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_
 int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std::string& err);
 // `ready`: called after the trusted circuit has been prepared on the host and before the first kernel touches `S`
 // (the upload of the big system may still be running until then); returns an ecne_status.
+// Everything about a trusted circuit that does not depend on the big system (coefficient multisets per form, wire
+// signatures and their classes): host work of a few milliseconds that touches neither CUDA nor any global state, so a
+// host may prepare the trusted circuits on another thread while it still reads the main circuit.
+struct PreparedSub;
+PreparedSub* abstraction_prepare(const ecne_problem_t* sub);  // nullptr: bad argument or no usable signature seed
+void abstraction_prepared_free(PreparedSub* p);
+// `prepared`: what abstraction_prepare made of the same `sub` (nullptr: prepared here)
 int dev_abstraction(DevSystem* S, int32_t kind, const ecne_problem_t* sub, SpecialsHost* sp, uint64_t* n_matches,
-                    cudaStream_t s, std::string& err, AbstractionStats* stats, const std::function<int()>& ready);
+                    cudaStream_t s, std::string& err, AbstractionStats* stats, const std::function<int()>& ready,
+                    const PreparedSub* prepared = nullptr);
 
 // setup.cu: H2D + classification + layout.  Returns an ecne_status.  With `dev` the rows are taken from a system that
 // is already resident on the device (p->seg_ptr / col / coef are not read; sizes come from `dev`).

@@ -93,6 +93,20 @@ void parallel_chunks(uint64_t n, uint64_t min_chunk, Fn fn) {
   for (auto& x : th) x.join();
 }
 
+// The arrays of a parsed circuit are hundreds of megabytes that are written once, right after they were allocated: with
+// 4 KB pages the first-touch page faults are a sizeable part of the read (ecdsa: 49 k faults).  Large arrays are
+// aligned to 2 MB and offered to the kernel as huge pages (transparent huge pages in `madvise` mode); free() releases
+// them like any other allocation.
+static void* big_alloc(size_t bytes) {
+  if (bytes < ((size_t)4 << 20)) return malloc(bytes ? bytes : 1);
+  void* p = nullptr;
+  if (posix_memalign(&p, (size_t)2 << 20, bytes) != 0) return nullptr;
+#ifdef MADV_HUGEPAGE
+  madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+  return p;
+}
+
 template <class T>
 T* dup_vec(const std::vector<T>& v) {
   T* p = (T*)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
@@ -128,7 +142,68 @@ extern "C" void ecne_r1cs_free(ecne_r1cs_t* r) {
   free(r->coef);
   free(r->known);
   free(r->targets);
+  free(r->coef_class);
+  free(r->coef_other);
+  free(r->coef_other_term);
+  free(r->seg_ptr32);
   free(r);
+}
+
+// ---- the compact form (include/ecne_abi.h) beside the full one -----------------------------------------------------------
+static const uint64_t FR_PM1[4] = {0x43e1f593f0000000ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+static inline uint8_t coef_class_of(const uint64_t* v) {
+  if ((v[1] | v[2] | v[3]) == 0 && v[0] <= 1) return (uint8_t)v[0];
+  if (v[0] == FR_PM1[0] && v[1] == FR_PM1[1] && v[2] == FR_PM1[2] && v[3] == FR_PM1[3]) return 2;
+  return 3;
+}
+// class bytes are in place: gather the class-3 values with their term indices, narrow the offsets
+static void compact_tail(ecne_r1cs_t* r) {
+  const uint64_t nnz = r->nnz, nseg = 3 * r->n_rows + 1;
+  const uint64_t CH = 1 << 16, n_chunks = (nnz + CH - 1) / CH;
+  std::vector<uint64_t> cnt(n_chunks + 1, 0);
+  const uint8_t* cls = r->coef_class;
+  uint64_t* cntp = cnt.data();
+  parallel_chunks(n_chunks, 4, [=](uint64_t cb, uint64_t ce) {
+    for (uint64_t c = cb; c < ce; ++c) {
+      uint64_t k = 0;
+      const uint64_t te = std::min(nnz, (c + 1) * CH);
+      for (uint64_t t = c * CH; t < te; ++t) k += cls[t] == 3;
+      cntp[c + 1] = k;
+    }
+  });
+  for (uint64_t c = 0; c < n_chunks; ++c) cnt[c + 1] += cnt[c];
+  const uint64_t n_other = cnt[n_chunks];
+  uint64_t* other = (uint64_t*)big_alloc(std::max<uint64_t>(1, n_other) * 32);
+  uint32_t* term = (uint32_t*)malloc(std::max<uint64_t>(1, n_other) * sizeof(uint32_t));
+  uint32_t* seg32 = (uint32_t*)big_alloc(nseg * sizeof(uint32_t));
+  if (!other || !term || !seg32 || nnz >= 0xffffffffULL) {
+    free(other);
+    free(term);
+    free(seg32);
+    free(r->coef_class);
+    r->coef_class = nullptr;
+    return;
+  }
+  const uint64_t* coef = r->coef;
+  parallel_chunks(n_chunks, 4, [=](uint64_t cb, uint64_t ce) {
+    for (uint64_t c = cb; c < ce; ++c) {
+      uint64_t k = cntp[c];
+      const uint64_t te = std::min(nnz, (c + 1) * CH);
+      for (uint64_t t = c * CH; t < te; ++t)
+        if (cls[t] == 3) {
+          memcpy(other + 4 * k, coef + 4 * t, 32);
+          term[k++] = (uint32_t)t;
+        }
+    }
+  });
+  const uint64_t* seg = r->seg_ptr;
+  parallel_chunks(nseg, 1 << 16, [=](uint64_t b, uint64_t e) {
+    for (uint64_t i = b; i < e; ++i) seg32[i] = (uint32_t)seg[i];
+  });
+  r->coef_other = other;
+  r->coef_other_term = term;
+  r->n_coef_other = n_other;
+  r->seg_ptr32 = seg32;
 }
 
 // ParseR1CS.jl:50-124.  Offsets below are 0-based; the Julia is 1-based.
@@ -186,8 +261,8 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
       fprintf(stderr, "[ecne host] read_r1cs   %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
       tp0 = t;
     };
-    uint64_t* segp = (uint64_t*)malloc((nseg + 1) * sizeof(uint64_t));
-    uint64_t* raw = (uint64_t*)malloc(std::max<uint64_t>(1, nseg) * sizeof(uint64_t));
+    uint64_t* segp = (uint64_t*)big_alloc((nseg + 1) * sizeof(uint64_t));
+    uint64_t* raw = (uint64_t*)big_alloc(std::max<uint64_t>(1, nseg) * sizeof(uint64_t));
     struct FreeRaw {
       uint64_t* p;
       ~FreeRaw() { free(p); }
@@ -343,8 +418,9 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
     lap(walked ? "offset walk (parallel)" : "offset walk (serial)");
     if (ok && total < 0x7fffffffULL) {
       segp[nseg] = total;
-      uint32_t* colp = (uint32_t*)malloc(std::max<uint64_t>(1, total) * sizeof(uint32_t));
-      uint64_t* coefp = (uint64_t*)malloc(std::max<uint64_t>(1, total) * 4 * sizeof(uint64_t));
+      uint32_t* colp = (uint32_t*)big_alloc(std::max<uint64_t>(1, total) * sizeof(uint32_t));
+      uint64_t* coefp = (uint64_t*)big_alloc(std::max<uint64_t>(1, total) * 4 * sizeof(uint64_t));
+      uint8_t* clsp = (uint8_t*)big_alloc(std::max<uint64_t>(1, total));  // compact form: class byte per term
       std::vector<uint8_t> dup_flag(1, 0);
       uint8_t* dupf = dup_flag.data();
       const uint64_t* rawp = raw;
@@ -358,6 +434,7 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
           if (n == 0) {  // explicit zero on key 1 (ParseR1CS.jl:113-115)
             colp[o] = 1;
             coefp[4 * o] = coefp[4 * o + 1] = coefp[4 * o + 2] = coefp[4 * o + 3] = 0;
+            clsp[o] = 0;
             continue;
           }
           for (uint32_t t = 0; t < n; ++t, q += 36, ++o) {
@@ -366,6 +443,7 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
             while (geq_p(c)) sub_p(c);  // F(coeff) reduces (ParseR1CS.jl:111)
             colp[o] = rd32(q) + 1;
             memcpy(coefp + 4 * o, c, 32);
+            clsp[o] = coef_class_of(c);
           }
           if (n > 1) {  // a repeated wire?
             const uint32_t* cc = colp + segp[sgi];
@@ -393,6 +471,9 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
         r->seg_ptr = segp;
         r->col = colp;
         r->coef = coefp;
+        r->coef_class = clsp;
+        compact_tail(r);
+        lap("compact form");
         std::vector<uint32_t> known, targets;
         known.push_back(1);
         for (uint64_t i = 2 + (uint64_t)pub_out; i <= 1 + (uint64_t)pub_out + pub_in + prv_in; ++i)
@@ -412,6 +493,7 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
       }
       free(colp);
       free(coefp);
+      free(clsp);
     }
     free(segp);  // truncated file or repeated wires: the serial walk below reports / handles it
   }
@@ -840,9 +922,9 @@ static int abstraction_impl(int32_t kind, const ecne_r1cs_t* cons, const ecne_r1
   r->n_rows = rows_out;
   r->n_vars = cons->n_vars;
   r->nnz = terms_out;
-  r->seg_ptr = (uint64_t*)malloc((3 * rows_out + 1) * sizeof(uint64_t));
-  r->col = (uint32_t*)malloc(std::max<uint64_t>(1, terms_out) * sizeof(uint32_t));
-  r->coef = (uint64_t*)malloc(std::max<uint64_t>(1, terms_out) * 4 * sizeof(uint64_t));
+  r->seg_ptr = (uint64_t*)big_alloc((3 * rows_out + 1) * sizeof(uint64_t));
+  r->col = (uint32_t*)big_alloc(std::max<uint64_t>(1, terms_out) * sizeof(uint32_t));
+  r->coef = (uint64_t*)big_alloc(std::max<uint64_t>(1, terms_out) * 4 * sizeof(uint64_t));
   struct Run {
     uint64_t r0, r1, row_dst, term_dst;  // rows [r0, r1) of cons land at row_dst / term_dst
   };

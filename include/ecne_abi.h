@@ -172,6 +172,15 @@ void ecne_free_resident(ecne_resident_t* r);
 typedef struct ecne_abstracted ecne_abstracted_t;
 int ecne_abstract_begin(const ecne_problem_t* main_circuit, ecne_abstracted_t** out);
 int ecne_abstract_apply(ecne_abstracted_t* a, int32_t kind, const ecne_problem_t* sub, uint64_t* n_matches);
+/* The part of an apply that depends on the trusted circuit alone (coefficient multisets, wire signatures and their
+ * classes: milliseconds of host work) can be done ahead — it touches neither the GPU nor any state of the library, so a
+ * host prepares the trusted circuits on another thread while it still reads the main circuit — and handed to the
+ * apply together with the same `sub`. */
+typedef struct ecne_prepared ecne_prepared_t;
+int ecne_abstract_prepare(const ecne_problem_t* sub, ecne_prepared_t** out);
+int ecne_abstract_apply_prepared(ecne_abstracted_t* a, int32_t kind, const ecne_problem_t* sub, const ecne_prepared_t* prepared,
+                                 uint64_t* n_matches);
+void ecne_abstract_prepared_free(ecne_prepared_t* p);
 int ecne_abstract_sizes(const ecne_abstracted_t* a, uint64_t sizes[5]);
 int ecne_abstract_export(ecne_abstracted_t* a, uint64_t* seg_ptr, uint32_t* col, uint64_t* coef, int32_t* sp_kind,
                          uint64_t* sp_in_ptr, uint32_t* sp_in, uint64_t* sp_out_ptr, uint32_t* sp_out);

@@ -37,6 +37,13 @@ typedef struct ecne_r1cs {
   uint64_t n_targets;
   uint32_t n_pub_out, n_pub_in, n_prv_in, field_size;
   uint64_t n_labels;
+  /* The same rows in the compact form of include/ecne_abi.h (ecne_problem_t.coef_class ...), filled by the reader's
+   * fast path while it copies the coefficients anyway; NULL when absent (outputs of ecne_abstraction, repaired files). */
+  uint8_t* coef_class;       /* [nnz]                                                   */
+  uint64_t* coef_other;      /* [n_coef_other*4]                                        */
+  uint32_t* coef_other_term; /* [n_coef_other]                                          */
+  uint64_t n_coef_other;
+  uint32_t* seg_ptr32;       /* [3*n_rows+1]                                            */
 } ecne_r1cs_t;
 
 int ecne_read_r1cs(const char* path, ecne_r1cs_t** out);

@@ -16,7 +16,7 @@ import pytest
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import abstraction_ref as ref  # noqa: E402
 from configs import CONFIGS  # noqa: E402
-from ecneproject_b200 import api, fixtures  # noqa: E402
+from ecneproject_b200 import _abi, api, fixtures  # noqa: E402
 from test_abstraction_parity import _random_case, mk, mul, rows_of  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -148,3 +148,37 @@ def test_solve_on_the_device_abstracted_system_matches_the_goldens(name):
     assert (res.c.n_unique_nontrivial, res.c.n_nontrivial, res.c.n_targets_unique, res.c.n_unique) == \
         (g["uniq"], g["nontriv"], g["tgt"], g["n_unique"])
     assert sizes[0] == g["reduced_rows"] and sizes[2] == g["n_specials"]
+
+
+def test_prepared_trusted_circuit_gives_the_same_abstraction():
+    """ecne_abstract_prepare + ecne_abstract_apply_prepared (the trusted circuit prepared ahead, on another thread while the
+    main circuit is read: api.read_and_prepare) against the plain apply."""
+    from configs import CONFIGS
+    from ecneproject_b200 import fixtures
+    for name in ("secp256k1+bmmp+blt", "tornado/withdraw+pedersen"):
+        cfg = CONFIGS[name]
+        paths = [fixtures.path(t) for t in cfg["trusted"]]
+        main, prepared = api.read_and_prepare(fixtures.path(cfg["main"]), paths, cfg["trusted_names"])
+        plain = sorted([(cfg["trusted_names"][i], api.readR1CS(p)) for i, p in enumerate(paths)], key=lambda x: -len(x[1]))
+        out = []
+        for subs in (prepared, plain):
+            da = api.DeviceAbstraction(main)
+            try:
+                for nm, sub in subs:
+                    da.apply(nm, sub)
+                (seg, col, coef), sp = da.export()
+                out.append((seg.tobytes(), col.tobytes(), coef.tobytes(), sp))
+            finally:
+                da.free()
+        assert out[0] == out[1]
+        # a prepared circuit handed over with another circuit's rows is refused
+        other = api.readR1CS(fixtures.path(cfg["main"]))
+        da = api.DeviceAbstraction(main)
+        try:
+            wrong = prepared[0][1]
+            ph = api.ProblemHandle(other, None, other.known, other.targets, other.n_vars)
+            n = C.c_uint64(0)
+            st = api._engine().ecne_abstract_apply_prepared(da.handle, 0, C.byref(ph.c), wrong.handle, C.byref(n))
+            assert st == _abi.ECNE_E_BADARG
+        finally:
+            da.free()

@@ -9,11 +9,14 @@ name = sys.argv[1] if len(sys.argv) > 1 else "ecdsa+secp256k1"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 cfg = CONFIGS[name]
 api._engine()
+main = subs = da = res = None
 for rep in range(reps):
+    main = subs = da = res = None   # the circuits of the run before (hundreds of megabytes) are released outside the timed region
+    import gc; gc.collect()
     t0 = time.perf_counter()
-    main = api.readR1CS(fixtures.path(cfg["main"]))
-    subs = [(cfg["trusted_names"][i], api.readR1CS(fixtures.path(t))) for i, t in enumerate(cfg.get("trusted", []))]
-    subs.sort(key=lambda x: -len(x[1]))
+    # the main circuit is parsed on a worker thread while this one reads and prepares the trusted circuits
+    main, subs = api.read_and_prepare(fixtures.path(cfg["main"]), [fixtures.path(t) for t in cfg.get("trusted", [])],
+                                      cfg.get("trusted_names", []))
     t1 = time.perf_counter()
     da = api.DeviceAbstraction(main)
     t2 = time.perf_counter()
