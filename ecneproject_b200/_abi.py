@@ -99,7 +99,7 @@ ENGINE_SYMBOLS = [
     "ecne_abstract_prepare", "ecne_abstract_apply_prepared", "ecne_abstract_prepared_free",
 ]
 HOST_SYMBOLS = [
-    "ecne_read_r1cs", "ecne_read_r1cs_mem", "ecne_r1cs_free", "ecne_specials_new",
+    "ecne_read_r1cs", "ecne_read_r1cs_opts", "ecne_read_r1cs_mem", "ecne_r1cs_free", "ecne_specials_new",
     "ecne_specials_free", "ecne_abstraction", "ecne_host_last_error", "ecne_compact_coef",
 ]
 
@@ -121,6 +121,8 @@ def host_lib():
         Sp = C.POINTER(SpecialsStruct)
         lib.ecne_read_r1cs.argtypes = [C.c_char_p, C.POINTER(R1p)]
         lib.ecne_read_r1cs.restype = C.c_int
+        lib.ecne_read_r1cs_opts.argtypes = [C.c_char_p, C.c_uint, C.POINTER(R1p)]
+        lib.ecne_read_r1cs_opts.restype = C.c_int
         lib.ecne_read_r1cs_mem.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(R1p)]
         lib.ecne_read_r1cs_mem.restype = C.c_int
         lib.ecne_r1cs_free.argtypes = [R1p]

@@ -62,7 +62,8 @@ class R1CS:
         self.nnz = int(s.nnz)
         self.seg_ptr = _as_np(s.seg_ptr, 3 * self.n_rows + 1, np.uint64)
         self.col = _as_np(s.col, self.nnz, np.uint32)
-        self.coef = _as_np(s.coef, 4 * self.nnz, np.uint64).reshape(-1, 4)
+        # (None after readR1CS(..., compact_only=True): the rows exist in the compact form only)
+        self.coef = _as_np(s.coef, 4 * self.nnz, np.uint64).reshape(-1, 4) if s.coef else None
         self.known = _as_np(s.known, int(s.n_known), np.uint32)
         self.targets = _as_np(s.targets, int(s.n_targets), np.uint32)
         # the compact form of the same rows, when the reader made it (include/ecne_host.h)
@@ -396,12 +397,14 @@ def format_listing(constraints, bad, result, index_to_signal):
     return "".join(out)
 
 
-def readR1CS(filename):
+def readR1CS(filename, compact_only=False):
     """ParseR1CS.readR1CS (ParseR1CS.jl:50).  The reference returns (equations, knowns, outs,
-    num_wires+1); here those four live on the returned R1CS (.known, .targets, .n_vars)."""
+    num_wires+1); here those four live on the returned R1CS (.known, .targets, .n_vars).
+    compact_only: leave out the full 32-byte coefficient array (.coef is None) — for rows that go to the device in the
+    compact form (solve_with_device_abstraction); it is 77 % of what the reader writes."""
     lib = _abi.host_lib()
     out = C.POINTER(_abi.R1CSStruct)()
-    st = lib.ecne_read_r1cs(str(filename).encode(), C.byref(out))
+    st = lib.ecne_read_r1cs_opts(str(filename).encode(), 1 if compact_only else 0, C.byref(out))
     if st != 0:
         _raise(st, lib.ecne_host_last_error().decode())
     return R1CS(out)
@@ -534,7 +537,7 @@ def read_and_prepare(input_r1cs, trusted_r1cs=(), trusted_r1cs_names=()):
     them (ecne_abstract_prepare).  Returns (main, [(name, PreparedTrusted)] longest first, :527)."""
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(1) as ex:
-        fut = ex.submit(readR1CS, input_r1cs)
+        fut = ex.submit(readR1CS, input_r1cs, True)  # (the device takes the compact form: no full coefficient array)
         function_list = [(trusted_r1cs_names[i], PreparedTrusted(trusted_r1cs_names[i], readR1CS(trusted_r1cs[i])))
                          for i in range(len(trusted_r1cs))]
         function_list.sort(key=lambda x: -len(x[1]))  # stable, longest first (:527)

@@ -107,6 +107,27 @@ static void* big_alloc(size_t bytes) {
   return p;
 }
 
+// ... the same split with the index of the chunk, and the number of chunks it makes, for per-chunk results
+inline uint64_t chunk_count(uint64_t n, uint64_t min_chunk) {
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 1;
+  return std::max<uint64_t>(1, std::min<uint64_t>(hw, std::max<uint64_t>(1, n / std::max<uint64_t>(1, min_chunk))));
+}
+template <class Fn>
+void parallel_chunks_idx(uint64_t n, uint64_t nt, Fn fn) {
+  if (nt <= 1) {
+    fn((uint64_t)0, (uint64_t)0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const uint64_t per = (n + nt - 1) / nt;
+  for (uint64_t t = 0; t < nt; ++t) {
+    const uint64_t b = std::min(n, t * per), e = std::min(n, b + per);
+    th.emplace_back([=]() { fn(t, b, e); });
+  }
+  for (auto& x : th) x.join();
+}
+
 template <class T>
 T* dup_vec(const std::vector<T>& v) {
   T* p = (T*)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
@@ -149,6 +170,10 @@ extern "C" void ecne_r1cs_free(ecne_r1cs_t* r) {
   free(r);
 }
 
+// ecne_read_r1cs_opts: ECNE_READ_COMPACT_ONLY leaves out the full coefficient array (coef == NULL) — a caller that hands
+// the rows to the device in the compact form never reads it, and it is 77 % of what the reader writes
+thread_local unsigned int g_read_flags = 0;
+
 // ---- the compact form (include/ecne_abi.h) beside the full one -----------------------------------------------------------
 static const uint64_t FR_PM1[4] = {0x43e1f593f0000000ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
 static inline uint8_t coef_class_of(const uint64_t* v) {
@@ -156,56 +181,6 @@ static inline uint8_t coef_class_of(const uint64_t* v) {
   if (v[0] == FR_PM1[0] && v[1] == FR_PM1[1] && v[2] == FR_PM1[2] && v[3] == FR_PM1[3]) return 2;
   return 3;
 }
-// class bytes are in place: gather the class-3 values with their term indices, narrow the offsets
-static void compact_tail(ecne_r1cs_t* r) {
-  const uint64_t nnz = r->nnz, nseg = 3 * r->n_rows + 1;
-  const uint64_t CH = 1 << 16, n_chunks = (nnz + CH - 1) / CH;
-  std::vector<uint64_t> cnt(n_chunks + 1, 0);
-  const uint8_t* cls = r->coef_class;
-  uint64_t* cntp = cnt.data();
-  parallel_chunks(n_chunks, 4, [=](uint64_t cb, uint64_t ce) {
-    for (uint64_t c = cb; c < ce; ++c) {
-      uint64_t k = 0;
-      const uint64_t te = std::min(nnz, (c + 1) * CH);
-      for (uint64_t t = c * CH; t < te; ++t) k += cls[t] == 3;
-      cntp[c + 1] = k;
-    }
-  });
-  for (uint64_t c = 0; c < n_chunks; ++c) cnt[c + 1] += cnt[c];
-  const uint64_t n_other = cnt[n_chunks];
-  uint64_t* other = (uint64_t*)big_alloc(std::max<uint64_t>(1, n_other) * 32);
-  uint32_t* term = (uint32_t*)malloc(std::max<uint64_t>(1, n_other) * sizeof(uint32_t));
-  uint32_t* seg32 = (uint32_t*)big_alloc(nseg * sizeof(uint32_t));
-  if (!other || !term || !seg32 || nnz >= 0xffffffffULL) {
-    free(other);
-    free(term);
-    free(seg32);
-    free(r->coef_class);
-    r->coef_class = nullptr;
-    return;
-  }
-  const uint64_t* coef = r->coef;
-  parallel_chunks(n_chunks, 4, [=](uint64_t cb, uint64_t ce) {
-    for (uint64_t c = cb; c < ce; ++c) {
-      uint64_t k = cntp[c];
-      const uint64_t te = std::min(nnz, (c + 1) * CH);
-      for (uint64_t t = c * CH; t < te; ++t)
-        if (cls[t] == 3) {
-          memcpy(other + 4 * k, coef + 4 * t, 32);
-          term[k++] = (uint32_t)t;
-        }
-    }
-  });
-  const uint64_t* seg = r->seg_ptr;
-  parallel_chunks(nseg, 1 << 16, [=](uint64_t b, uint64_t e) {
-    for (uint64_t i = b; i < e; ++i) seg32[i] = (uint32_t)seg[i];
-  });
-  r->coef_other = other;
-  r->coef_other_term = term;
-  r->n_coef_other = n_other;
-  r->seg_ptr32 = seg32;
-}
-
 // ParseR1CS.jl:50-124.  Offsets below are 0-based; the Julia is 1-based.
 static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** out) {
   if (!arr || !out) return fail(ECNE_E_BADARG, "null argument");
@@ -418,14 +393,21 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
     lap(walked ? "offset walk (parallel)" : "offset walk (serial)");
     if (ok && total < 0x7fffffffULL) {
       segp[nseg] = total;
+      const bool compact_only = (g_read_flags & ECNE_READ_COMPACT_ONLY) != 0 && total < 0xffffffffULL;
       uint32_t* colp = (uint32_t*)big_alloc(std::max<uint64_t>(1, total) * sizeof(uint32_t));
-      uint64_t* coefp = (uint64_t*)big_alloc(std::max<uint64_t>(1, total) * 4 * sizeof(uint64_t));
+      uint64_t* coefp = compact_only ? nullptr : (uint64_t*)big_alloc(std::max<uint64_t>(1, total) * 4 * sizeof(uint64_t));
       uint8_t* clsp = (uint8_t*)big_alloc(std::max<uint64_t>(1, total));  // compact form: class byte per term
       std::vector<uint8_t> dup_flag(1, 0);
       uint8_t* dupf = dup_flag.data();
       const uint64_t* rawp = raw;
-      parallel_chunks(nseg, 1 << 14, [=](uint64_t b, uint64_t e) {
+      // pass 1 over contiguous ranges of segments: wires, (full coefficients,) class bytes; per range the number of
+      // coefficients that are none of 0, 1, p - 1
+      const uint64_t n_ranges = chunk_count(nseg, 1 << 14);
+      std::vector<uint64_t> others(n_ranges + 1, 0);
+      uint64_t* othersp = others.data();
+      parallel_chunks_idx(nseg, n_ranges, [=](uint64_t ri, uint64_t b, uint64_t e) {
         std::vector<uint32_t> tmp;
+        uint64_t n3 = 0;
         for (uint64_t sgi = b; sgi < e; ++sgi) {
           const uint8_t* q = arr + rawp[sgi];
           const uint32_t n = rd32(q);
@@ -433,7 +415,7 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
           uint64_t o = segp[sgi];
           if (n == 0) {  // explicit zero on key 1 (ParseR1CS.jl:113-115)
             colp[o] = 1;
-            coefp[4 * o] = coefp[4 * o + 1] = coefp[4 * o + 2] = coefp[4 * o + 3] = 0;
+            if (coefp) coefp[4 * o] = coefp[4 * o + 1] = coefp[4 * o + 2] = coefp[4 * o + 3] = 0;
             clsp[o] = 0;
             continue;
           }
@@ -442,8 +424,10 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
             memcpy(c, q + 4, 32);       // 32 bytes hard-coded (ParseR1CS.jl:109)
             while (geq_p(c)) sub_p(c);  // F(coeff) reduces (ParseR1CS.jl:111)
             colp[o] = rd32(q) + 1;
-            memcpy(coefp + 4 * o, c, 32);
-            clsp[o] = coef_class_of(c);
+            if (coefp) memcpy(coefp + 4 * o, c, 32);
+            const uint8_t cl = coef_class_of(c);
+            clsp[o] = cl;
+            n3 += cl == 3;
           }
           if (n > 1) {  // a repeated wire?
             const uint32_t* cc = colp + segp[sgi];
@@ -461,8 +445,42 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
             if (dup) *dupf = 1;  // benign race: every writer stores 1
           }
         }
+        othersp[ri + 1] = n3;
       });
       lap("fill (parallel)");
+      // pass 2 over the same ranges: the other values with their term indices (from the file again: a tenth of the
+      // terms), the 32-bit copy of the offsets
+      uint64_t* otherp = nullptr;
+      uint32_t *termp = nullptr, *seg32p = nullptr;
+      if (!dup_flag[0] && total < 0xffffffffULL) {
+        for (uint64_t ri = 0; ri < n_ranges; ++ri) others[ri + 1] += others[ri];
+        const uint64_t n_other = others[n_ranges];
+        otherp = (uint64_t*)big_alloc(std::max<uint64_t>(1, n_other) * 32);
+        termp = (uint32_t*)big_alloc(std::max<uint64_t>(1, n_other) * sizeof(uint32_t));
+        seg32p = (uint32_t*)big_alloc((nseg + 1) * sizeof(uint32_t));
+        if (otherp && termp && seg32p) {
+          parallel_chunks_idx(nseg, n_ranges, [=](uint64_t ri, uint64_t b, uint64_t e) {
+            uint64_t k = othersp[ri];
+            for (uint64_t sgi = b; sgi < e; ++sgi) {
+              seg32p[sgi] = (uint32_t)segp[sgi];
+              const uint8_t* q = arr + rawp[sgi];
+              const uint32_t n = rd32(q);
+              q += 4;
+              uint64_t o = segp[sgi];
+              for (uint32_t t = 0; t < n; ++t, q += 36, ++o)
+                if (clsp[o] == 3) {
+                  uint64_t c[4];
+                  memcpy(c, q + 4, 32);
+                  while (geq_p(c)) sub_p(c);
+                  memcpy(otherp + 4 * k, c, 32);
+                  termp[k++] = (uint32_t)o;
+                }
+            }
+          });
+          seg32p[nseg] = (uint32_t)total;
+        }
+        lap("compact form");
+      }
       if (!dup_flag[0]) {
         ecne_r1cs_t* r = (ecne_r1cs_t*)calloc(1, sizeof(ecne_r1cs_t));
         r->n_rows = n_cons;
@@ -471,9 +489,24 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
         r->seg_ptr = segp;
         r->col = colp;
         r->coef = coefp;
-        r->coef_class = clsp;
-        compact_tail(r);
-        lap("compact form");
+        if (otherp && termp && seg32p) {
+          r->coef_class = clsp;
+          r->coef_other = otherp;
+          r->coef_other_term = termp;
+          r->n_coef_other = others[n_ranges];
+          r->seg_ptr32 = seg32p;
+        } else {
+          free(clsp);
+          free(otherp);
+          free(termp);
+          free(seg32p);
+          if (!coefp) {  // (compact only was asked for and cannot be had: terms beyond 32-bit indices never get here)
+            free(segp);
+            free(colp);
+            free(r);
+            return fail(ECNE_E_BOUNDS, "out of memory for the compact form");
+          }
+        }
         std::vector<uint32_t> known, targets;
         known.push_back(1);
         for (uint64_t i = 2 + (uint64_t)pub_out; i <= 1 + (uint64_t)pub_out + pub_in + prv_in; ++i)
@@ -494,6 +527,9 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
       free(colp);
       free(coefp);
       free(clsp);
+      free(otherp);
+      free(termp);
+      free(seg32p);
     }
     free(segp);  // truncated file or repeated wires: the serial walk below reports / handles it
   }
@@ -586,8 +622,14 @@ extern "C" int ecne_read_r1cs_mem(const uint8_t* arr, uint64_t len, ecne_r1cs_t*
   }
 }
 
-extern "C" int ecne_read_r1cs(const char* path, ecne_r1cs_t** out) {
+extern "C" int ecne_read_r1cs_opts(const char* path, unsigned int flags, ecne_r1cs_t** out);
+extern "C" int ecne_read_r1cs(const char* path, ecne_r1cs_t** out) { return ecne_read_r1cs_opts(path, 0, out); }
+extern "C" int ecne_read_r1cs_opts(const char* path, unsigned int flags, ecne_r1cs_t** out) {
   if (!path || !out) return fail(ECNE_E_BADARG, "null argument");
+  struct FlagGuard {
+    FlagGuard(unsigned int f) { g_read_flags = f; }
+    ~FlagGuard() { g_read_flags = 0; }
+  } flag_guard(flags);
   // map the file instead of copying it: the parser touches every byte exactly once
   int fd = open(path, O_RDONLY);
   if (fd < 0) return fail(ECNE_E_IO, std::string("cannot open ") + path);

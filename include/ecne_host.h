@@ -47,6 +47,10 @@ typedef struct ecne_r1cs {
 } ecne_r1cs_t;
 
 int ecne_read_r1cs(const char* path, ecne_r1cs_t** out);
+/* ... with options.  ECNE_READ_COMPACT_ONLY: the full coefficient array is left out (coef == NULL; the compact arrays are
+ * always there then, or the call fails) — for a caller that hands the rows to the device in the compact form. */
+#define ECNE_READ_COMPACT_ONLY 1u
+int ecne_read_r1cs_opts(const char* path, unsigned int flags, ecne_r1cs_t** out);
 int ecne_read_r1cs_mem(const uint8_t* buf, uint64_t len, ecne_r1cs_t** out);
 void ecne_r1cs_free(ecne_r1cs_t* r);
 

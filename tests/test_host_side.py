@@ -356,3 +356,22 @@ def test_compact_coef_matches_a_numpy_classification():
     assert np.array_equal(other, coef[want == 3])
     cls0, other0, term0 = api.compact_coef(np.zeros((0, 4), dtype=np.uint64))
     assert len(cls0) == 0 and len(term0) == 0
+
+
+def test_compact_only_read_matches_the_full_read():
+    """ecne_read_r1cs_opts(ECNE_READ_COMPACT_ONLY) (include/ecne_host.h): same rows, same compact form, no 32-byte
+    coefficient array; the compact form the reader emits equals ecne_compact_coef of the full coefficients."""
+    for name in ("ecne_circomlib_tests/EdDSAVerifier@eddsa.r1cs", "bigmultmodp86_3.r1cs", "bad_bd_check.r1cs", "secp256k1.r1cs"):
+        path = fixtures.path(name)
+        full = api.readR1CS(path)
+        lean = api.readR1CS(path, compact_only=True)
+        assert lean.coef is None and full.coef is not None
+        assert np.array_equal(full.seg_ptr, lean.seg_ptr) and np.array_equal(full.col, lean.col)
+        assert full.compact is not None and lean.compact is not None
+        for a, b in zip(full.compact, lean.compact):
+            assert np.array_equal(a, b)
+        cls, other, term = api.compact_coef(full.coef)
+        assert np.array_equal(cls, lean.compact[0])
+        assert np.array_equal(other.reshape(-1), lean.compact[1]) and np.array_equal(term, lean.compact[2])
+        assert np.array_equal(lean.compact[3].astype(np.uint64), full.seg_ptr)
+        assert (lean.known == full.known).all() and (lean.targets == full.targets).all() and lean.n_vars == full.n_vars
