@@ -48,6 +48,20 @@ __host__ __device__ __forceinline__ u256 fold_threshold() {
                    0x2e2e53955f6f1dfeULL);
 }
 
+#ifdef __CUDACC__
+// One 256-bit load / store per value (LDG.E.256 / STG.E.256 on sm_100): the arrays of u256 in global memory are
+// 32-byte aligned (arena allocations of 256 bytes, 32-byte elements); the struct itself only promises 8, so plain
+// accesses compile to four 64-bit ones, each a strided warp access.
+__device__ __forceinline__ u256 ldg256(const u256* p) {
+  u256 r;
+  asm("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(u256* p, const u256& x) {
+  asm volatile("st.global.v4.u64 [%4], {%0,%1,%2,%3};" ::"l"(x.v[0]), "l"(x.v[1]), "l"(x.v[2]), "l"(x.v[3]), "l"(p) : "memory");
+}
+#endif
+
 __host__ __device__ __forceinline__ bool is_zero(const u256& a) {
   return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0;
 }

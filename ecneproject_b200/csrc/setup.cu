@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <mutex>
 
 #include "engine_host.h"
 
@@ -14,6 +15,9 @@ namespace ecne {
 
 #define LONG_T 6u           // rows with more non-zero terms than the inline record holds get a whole warp
 #define N_CONST 255u        // 2^k-1 (k = 0..253) and p-1
+#define LAYOUT_LONG_MIN 64u    // C segments longer than this are ranked by a block in shared memory
+#define LAYOUT_LONG_MID 512u   // ... by a small block up to here, by a large one beyond
+#define LAYOUT_LONG_MAX 4096u  // ... as long as they fit there (49 B per term)
 #define C3_INLINE_MAX 255u  // longer bit-decomposition candidates go through the 2^i mod p table
 
 #define CK(x)                                                                      \
@@ -25,12 +29,16 @@ namespace ecne {
     }                                                                              \
   } while (0)
 
+struct CoefView {  // read-only 32-byte coefficients of the uploaded rows, one 256-bit load each
+  const fr::u256* p;
+  __device__ __forceinline__ fr::u256 operator[](uint64_t t) const { return fr::ldg256(p + t); }
+};
 struct Raw {  // the problem as uploaded (explicit zeros included)
   uint32_t N, V;
   uint64_t nnz;
   const unsigned long long* seg;  // [3N+1]
   const uint32_t* col;
-  const fr::u256* coef;
+  CoefView coef;
 };
 
 __global__ void k_keep(Raw r, uint32_t* keep) {
@@ -170,6 +178,7 @@ __device__ inline int c3_pattern_small(const Raw& r, uint32_t row, uint32_t l) {
 struct Counters {
   unsigned int n2a, n2b, n_long, max_c, n_c3_long, bad;
   unsigned int n_longc;  // rows handed to k_classify_long
+  unsigned int max_seg_c;  // longest stored C segment of a long row (sizes the shared memory of k_layout_long)
 };
 
 // one atomic per converged group of lanes instead of one per row (160 k rows count themselves as 2b)
@@ -182,13 +191,15 @@ __device__ __forceinline__ void warp_count(unsigned int* ctr) {
 __device__ __forceinline__ void classify_decide(const Raw& r, uint32_t row, const ABScan& ab, const CScan& cs, bool bad,
                                             uint32_t* rflags, RowAux* aux, Counters* cnt, uint32_t* c3_long);
 
+// rows whose stored C segment gets a warp (k_classify_long): listed ahead, so that both classifiers run side by side
+__global__ void k_longc(Raw r, Counters* cnt, uint32_t* longc) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < r.N && r.seg[3ull * row + 3] - r.seg[3ull * row + 2] > CLASSIFY_LONG_C) longc[atomicAdd(&cnt->n_longc, 1u)] = row;
+}
 __global__ void k_classify(Raw r, uint32_t* rflags, RowAux* aux, Counters* cnt, uint32_t* c3_long, uint32_t* longc) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= r.N) return;
-  if (r.seg[3ull * row + 3] - r.seg[3ull * row + 2] > CLASSIFY_LONG_C) {  // k_classify_long
-    longc[atomicAdd(&cnt->n_longc, 1u)] = row;
-    return;
-  }
+  if (r.seg[3ull * row + 3] - r.seg[3ull * row + 2] > CLASSIFY_LONG_C) return;  // k_classify_long (listed by k_longc)
   bool bad = false;
   ABScan ab;
   CScan cs;
@@ -214,27 +225,43 @@ __device__ __forceinline__ void classify_long_row(const Raw& r, uint32_t row, ui
   uint32_t nC = 0, n_non1 = 0, n_one = 0, n_mone = 0;
   unsigned long long last_x = 0, last_one = 0, last_mone = 0;  // (term index + 1) << 32 | wire
   bool bad = false, key1 = false;
-  for (uint64_t t = b + lane; t < e; t += 32) {
-    const uint32_t w = r.col[t];
-    if (w < 1 || w > r.V) {
-      bad = true;
-      continue;
+  // (four terms per lane in flight: a 1025-term row is 33 dependent trips to DRAM otherwise)
+  for (uint64_t t0 = b + lane; t0 < e; t0 += 128) {
+    uint32_t wq[4];
+    fr::u256 cq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint64_t t = t0 + 32u * q;
+      if (t < e) {
+        wq[q] = r.col[t];
+        cq[q] = r.coef[t];
+      }
     }
-    const fr::u256 c = r.coef[t];
-    if (w == 1) key1 = true;
-    if (fr::is_zero(c)) continue;
-    const unsigned long long tag = ((unsigned long long)(t - b + 1) << 32) | w;
-    nC++;
-    if (w != 1) {
-      n_non1++;
-      last_x = tag;
-    }
-    if (fr::is_one(c)) {
-      n_one++;
-      last_one = tag;
-    } else if (fr::is_minus_one(c)) {
-      n_mone++;
-      last_mone = tag;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint64_t t = t0 + 32u * q;
+      if (t >= e) break;
+      const uint32_t w = wq[q];
+      if (w < 1 || w > r.V) {
+        bad = true;
+        continue;
+      }
+      const fr::u256 c = cq[q];
+      if (w == 1) key1 = true;
+      if (fr::is_zero(c)) continue;
+      const unsigned long long tag = ((unsigned long long)(t - b + 1) << 32) | w;
+      nC++;
+      if (w != 1) {
+        n_non1++;
+        last_x = tag;
+      }
+      if (fr::is_one(c)) {
+        n_one++;
+        last_one = tag;
+      } else if (fr::is_minus_one(c)) {
+        n_mone++;
+        last_mone = tag;
+      }
     }
   }
   nC = __reduce_add_sync(0xffffffffu, nC);
@@ -378,6 +405,8 @@ __device__ __forceinline__ void classify_decide(const Raw& r, uint32_t row, cons
   if (tot > LONG_T) {
     rf |= RF_LONG;
     atomicAdd(&cnt->n_long, 1u);
+    const uint32_t seg_c = (uint32_t)(r.seg[3ull * row + 3] - r.seg[3ull * row + 2]);
+    if (seg_c > LAYOUT_LONG_MIN) atomicMax(&cnt->max_seg_c, seg_c);
   }
   if (cs.nC > C3_INLINE_MAX) atomicMax(&cnt->max_c, cs.nC);  // sizes the 2^i mod p table of the long candidates
   rflags[row] = rf;
@@ -392,6 +421,17 @@ struct Pow2Entry {
   uint32_t pad[7];
 };
 __device__ inline int pow2_lookup(const Pow2Entry* tab, uint32_t n, const fr::u256& v) {
+  // 2^i < p for i <= 253: a canonical value with one bit set is its own table entry, and below 2^254 the table holds
+  // nothing else — the binary search is only for the wrapped powers (rows longer than 254 terms)
+  const int bits = __popcll(v.v[0]) + __popcll(v.v[1]) + __popcll(v.v[2]) + __popcll(v.v[3]);
+  if (bits == 1) {
+    const int ex = v.v[0] ? __ffsll((long long)v.v[0]) - 1
+                 : v.v[1] ? 63 + __ffsll((long long)v.v[1])
+                 : v.v[2] ? 127 + __ffsll((long long)v.v[2])
+                          : 191 + __ffsll((long long)v.v[3]);
+    return (uint32_t)ex < n ? ex : -1;
+  }
+  if (n <= 254) return -1;
   int lo = 0, hi = (int)n - 1;
   while (lo <= hi) {
     int mid = (lo + hi) >> 1;
@@ -407,61 +447,56 @@ __device__ inline int pow2_lookup(const Pow2Entry* tab, uint32_t n, const fr::u2
 __global__ void k_classify_c3_long(Raw r, uint32_t* rflags, RowAux* aux, const uint32_t* list,
                                    uint32_t n_list, const Pow2Entry* tab, uint32_t tab_n,
                                    uint32_t mask_words) {
+  // one block per row: every exponent beyond 253 costs a ten-step search in the table, and a 1025-term row is 33
+  // dependent rounds of those for a single warp
   extern __shared__ unsigned int smem[];
-  const uint32_t warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-  if (wid >= n_list) return;
-  unsigned int* m1 = smem + (size_t)warp_in_block * 2 * mask_words;
+  __shared__ unsigned int s_ones, s_mones, s_k_one, s_k_mone, s_dead1, s_dead2;
+  if (blockIdx.x >= n_list) return;
+  unsigned int* m1 = smem;
   unsigned int* m2 = m1 + mask_words;
-  for (uint32_t i = lane; i < 2 * mask_words; i += 32) m1[i] = 0;
-  __syncwarp();
-  const uint32_t row = list[wid];
+  for (uint32_t i = threadIdx.x; i < 2 * mask_words; i += blockDim.x) m1[i] = 0;
+  if (threadIdx.x == 0) s_ones = s_mones = s_k_one = s_k_mone = s_dead1 = s_dead2 = 0;
+  __syncthreads();
+  const uint32_t row = list[blockIdx.x];
   const uint64_t b = r.seg[3ull * row + 2], e = r.seg[3ull * row + 3];
   const uint32_t l = (uint32_t)(e - b);
-  uint32_t ones = 0, mones = 0, k_one = 0, k_mone = 0;
-  bool ok1 = true, ok2 = true;
-  for (uint64_t t = b + lane; t < e; t += 32) {
-    fr::u256 c = r.coef[t];
+  // (a form that has failed on one term is dead for the row: the others stop looking their exponents up)
+  for (uint64_t t = b + threadIdx.x; t < e; t += blockDim.x) {
+    const bool dead1 = *(volatile unsigned int*)&s_dead1 != 0, dead2 = *(volatile unsigned int*)&s_dead2 != 0;
+    if (dead1 && dead2) break;
+    const fr::u256 c = r.coef[t];
     if (fr::is_one(c)) {
-      ones++;
-      k_one = r.col[t];
-    } else {
-      int ex = pow2_lookup(tab, tab_n, fr::neg(c));
-      if (ex < 0 || (uint32_t)ex + 1 >= l) {
-        ok1 = false;
-      } else if (atomicOr(m1 + (ex >> 5), 1u << (ex & 31)) & (1u << (ex & 31))) {
-        ok1 = false;
-      }
+      atomicAdd(&s_ones, 1u);
+      atomicMax(&s_k_one, r.col[t]);
+    } else if (!dead1) {
+      const int ex = pow2_lookup(tab, tab_n, fr::neg(c));
+      if (ex < 0 || (uint32_t)ex + 1 >= l || (atomicOr(m1 + (ex >> 5), 1u << (ex & 31)) & (1u << (ex & 31)))) s_dead1 = 1;
     }
     if (fr::is_minus_one(c)) {
-      mones++;
-      k_mone = r.col[t];
-    } else {
-      int ex = pow2_lookup(tab, tab_n, c);
-      if (ex < 0 || (uint32_t)ex + 1 >= l) {
-        ok2 = false;
-      } else if (atomicOr(m2 + (ex >> 5), 1u << (ex & 31)) & (1u << (ex & 31))) {
-        ok2 = false;
-      }
+      atomicAdd(&s_mones, 1u);
+      atomicMax(&s_k_mone, r.col[t]);
+    } else if (!dead2) {
+      const int ex = pow2_lookup(tab, tab_n, c);
+      if (ex < 0 || (uint32_t)ex + 1 >= l || (atomicOr(m2 + (ex >> 5), 1u << (ex & 31)) & (1u << (ex & 31)))) s_dead2 = 1;
     }
   }
-  ok1 = __all_sync(0xffffffffu, ok1) && __reduce_add_sync(0xffffffffu, ones) == 1;
-  ok2 = __all_sync(0xffffffffu, ok2) && __reduce_add_sync(0xffffffffu, mones) == 1;
-  k_one = __reduce_max_sync(0xffffffffu, k_one);
-  k_mone = __reduce_max_sync(0xffffffffu, k_mone);
-  if (lane == 0 && (ok1 || ok2)) {
-    uint32_t rf = rflags[row] | RF_C3;
-    RowAux a = aux[row];
-    if (ok2) {
-      rf |= RF_C3_FLIP;
-      a.w2 = k_mone;
-      a.w5 = k_one;
-    } else {
-      a.w2 = k_one;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const bool ok1 = !s_dead1 && s_ones == 1, ok2 = !s_dead2 && s_mones == 1;
+    if (ok1 || ok2) {
+      uint32_t rf = rflags[row] | RF_C3;
+      RowAux a = aux[row];
+      if (ok2) {
+        rf |= RF_C3_FLIP;
+        a.w2 = s_k_mone;
+        a.w5 = s_k_one;
+      } else {
+        a.w2 = s_k_one;
+      }
+      if (l - 1 >= 254) rf |= RF_C3_TOPBIG;
+      rflags[row] = rf;
+      aux[row] = a;
     }
-    if (l - 1 >= 254) rf |= RF_C3_TOPBIG;
-    rflags[row] = rf;
-    aux[row] = a;
   }
 }
 
@@ -489,19 +524,6 @@ __global__ void k_values(Raw r, const uint32_t* rflags, RowAux* aux, fr::u256* r
   }
 }
 
-// row of an original term by binary search over the 3N+1 segment offsets
-__device__ __forceinline__ uint32_t seg_of(const unsigned long long* seg, uint32_t nseg, uint64_t t) {
-  uint32_t lo = 0, hi = nseg;  // find last s with seg[s] <= t
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (seg[mid] <= t)
-      lo = mid;
-    else
-      hi = mid;
-  }
-  return lo;
-}
-
 __device__ __forceinline__ fr::u256 mag_of(const fr::u256& c, bool flipped) {
   fr::u256 x = flipped ? fr::neg(c) : c;
   if (fr::cmp(x, fr::fold_threshold()) > 0) {
@@ -512,54 +534,134 @@ __device__ __forceinline__ fr::u256 mag_of(const fr::u256& c, bool flipped) {
   return x;
 }
 
-#define LAYOUT_LONG_MIN 64u    // C segments longer than this are ranked by a block in shared memory
-#define LAYOUT_LONG_MAX 4096u  // ... as long as they fit there (45 B per term, padded to a power of two)
 // Scatter the non-zero terms into the sweep layout.  C terms of linear rows are placed by their
 // rank in (|fold(coef)|, wire) order so that Case 5 (:1265) walks them sorted.
-__global__ void k_layout(Raw r, const uint32_t* keep, const uint32_t* pos, const uint32_t* seg_nz,
-                         const uint32_t* rflags, uint32_t* col, fr::u256* coef, uint8_t* nontriv) {
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= r.nnz || !keep[t]) return;
-  uint32_t s = seg_of(r.seg, 3 * r.N, t);
-  while (r.seg[s + 1] <= t) ++s;  // skip empty segments that share the offset
-  uint32_t row = s / 3, form = s % 3;
+// Short rows (everything but RF_LONG): one thread per row walks its three segments — no search for the segment of a
+// term, the row's flags read once, and a linear row's C terms ranked among at most LONG_T kept ones.
+__device__ __forceinline__ void layout_term(const Raw& r, const uint32_t* keep, const uint32_t* pos, const uint32_t* seg_nz,
+                                            uint32_t s, uint64_t seg_b, uint64_t seg_e, uint64_t t, bool ranked, bool fl,
+                                            uint32_t* col, fr::u256* coef, uint8_t* nontriv) {
+  if (!keep[t]) return;
+  const fr::u256 c = r.coef[t];
+  const uint32_t w = r.col[t];
   uint32_t dst = pos[t];
-  fr::u256 c = r.coef[t];
-  uint32_t w = r.col[t];
-  uint32_t rf = rflags[row];
-  if (form == 2 && (rf & RF_LINEAR)) {
-    const uint64_t seg_len = r.seg[s + 1] - r.seg[s];
-    if (seg_len > LAYOUT_LONG_MIN && seg_len <= LAYOUT_LONG_MAX) return;  // k_layout_long ranks these in smem
-    bool fl = (rf & RF_C3_FLIP) != 0;
-    fr::u256 m = mag_of(c, fl);
+  if (ranked) {
+    const fr::u256 m = mag_of(c, fl);
     uint32_t rank = 0;
-    for (uint64_t u = r.seg[s]; u < r.seg[s + 1]; ++u) {
+    for (uint64_t u = seg_b; u < seg_e; ++u) {
       if (u == t || !keep[u]) continue;
-      int cm = fr::cmp(mag_of(r.coef[u], fl), m);
+      const int cm = fr::cmp(mag_of(r.coef[u], fl), m);
       if (cm < 0 || (cm == 0 && r.col[u] < w)) ++rank;
     }
     dst = seg_nz[s] + rank;
   }
   col[dst] = w;
-  coef[dst] = c;
-  nontriv[w] = 1;
+  fr::stg256(coef + dst, c);
+  // (a set-once flag: wire 1 — the constant — is in a third of the rows, and a million byte stores to one address
+  // queue up in one L2 slice; a stale zero from the L1 only repeats the store)
+  if (!nontriv[w]) nontriv[w] = 1;
 }
-// The C segment of one long linear row: magnitudes and wires go to shared memory once and a bitonic
-// network sorts an index permutation by (dropped?, |fold(coef)|, wire) — the kept terms come out in
-// exactly the order k_layout's rank computation gives, in O(n log^2 n) on-chip compares.
-__device__ __forceinline__ bool layout_less(const fr::u256* mag, const uint32_t* wv, const uint8_t* kp, uint32_t n,
-                                            uint32_t a, uint32_t b) {
-  const bool ka = a < n && kp[a], kb = b < n && kp[b];
-  if (ka != kb) return ka;  // kept terms first; padding and dropped zeros last
-  if (!ka) return a < b;
-  const int cm = fr::cmp(mag[a], mag[b]);
-  if (cm != 0) return cm < 0;
-  if (wv[a] != wv[b]) return wv[a] < wv[b];
-  return a < b;
+__global__ void k_layout(Raw r, const uint32_t* keep, const uint32_t* pos, const uint32_t* seg_nz,
+                         const uint32_t* rflags, uint32_t* col, fr::u256* coef, uint8_t* nontriv) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r.N) return;
+  const uint32_t rf = rflags[row];
+  if (rf & RF_LONG) return;  // k_layout_long_rows / k_layout_long
+  const bool fl = (rf & RF_C3_FLIP) != 0;
+  uint64_t seg_b = r.seg[3ull * row];
+#pragma unroll 1
+  for (uint32_t form = 0; form < 3; ++form) {
+    const uint32_t s = 3 * row + form;
+    const uint64_t seg_e = r.seg[s + 1];
+    const bool ranked = form == 2 && (rf & RF_LINEAR);
+    for (uint64_t t = seg_b; t < seg_e; ++t)
+      layout_term(r, keep, pos, seg_nz, s, seg_b, seg_e, t, ranked, fl, col, coef, nontriv);
+    seg_b = seg_e;
+  }
 }
+// Long rows: one warp per row, lanes striding the terms of a segment.  The C segment of a linear row between
+// LAYOUT_LONG_MIN and LAYOUT_LONG_MAX terms is left to k_layout_long (sorted in shared memory).
+__global__ void k_layout_long_rows(Raw r, const uint32_t* keep, const uint32_t* pos, const uint32_t* seg_nz,
+                                   const uint32_t* rflags, const uint32_t* long_rows, uint32_t n_long, uint32_t* col,
+                                   fr::u256* coef, uint8_t* nontriv) {
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (wid >= n_long) return;
+  const uint32_t row = long_rows[wid];
+  const uint32_t rf = rflags[row];
+  const bool fl = (rf & RF_C3_FLIP) != 0;
+  for (uint32_t form = 0; form < 3; ++form) {
+    const uint32_t s = 3 * row + form;
+    const uint64_t seg_b = r.seg[s], seg_e = r.seg[s + 1];
+    const bool ranked = form == 2 && (rf & RF_LINEAR);
+    if (ranked && seg_e - seg_b > LAYOUT_LONG_MIN && seg_e - seg_b <= LAYOUT_LONG_MAX) continue;
+    for (uint64_t t = seg_b + lane; t < seg_e; t += 32)
+      layout_term(r, keep, pos, seg_nz, s, seg_b, seg_e, t, ranked, fl, col, coef, nontriv);
+  }
+}
+// Ascending-only bitonic network over a permutation of n items (the first step of every merge mirrors, the others are
+// half-cleaners): positions beyond n act as +infinity and are never touched, so n needs no padding.  `less(a, b)`
+// compares two ITEMS; all threads of the block call this.
+template <class Less>
+__device__ __forceinline__ void block_sort_perm(uint32_t* perm, uint32_t n, Less less) {
+  uint32_t np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (uint32_t k = 2; k <= np2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      const bool mirror = j == (k >> 1);
+      for (uint32_t t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // t-th pair of the step: bit j of i is clear
+        const uint32_t q = mirror ? (i ^ (k - 1)) : (i | j);
+        if (q < n) {
+          const uint32_t a = perm[i], b = perm[q];
+          if (less(b, a)) {
+            perm[i] = b;
+            perm[q] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+// 256-bit values of a block in shared memory, one array per limb: a compare reads 8-byte words at random items, which
+// spread over the banks (32-byte structs put every item's limb k in one of four bank groups: an 8-way conflict).
+struct LimbsSoA {
+  unsigned long long* l[4];
+  __device__ __forceinline__ void carve(unsigned long long* base, uint32_t cap) {
+    for (int k = 0; k < 4; ++k) l[k] = base + (size_t)k * cap;
+  }
+  __device__ __forceinline__ void put(uint32_t i, const fr::u256& x) const {
+    for (int k = 0; k < 4; ++k) l[k][i] = x.v[k];
+  }
+  __device__ __forceinline__ int cmp(uint32_t a, uint32_t b) const {
+    for (int k = 3; k >= 0; --k) {
+      const unsigned long long x = l[k][a], y = l[k][b];
+      if (x != y) return x < y ? -1 : 1;
+    }
+    return 0;
+  }
+};
+// 64-bit key that orders 256-bit magnitudes: the value itself below 2^55 (exact: equal keys are equal values), else
+// bit length and the 55 bits behind the leading one (equal keys: the limbs decide).
+__device__ __forceinline__ unsigned long long order_key(const fr::u256& m) {
+  int top = 3;
+  while (top > 0 && m.v[top] == 0) --top;
+  const unsigned long long hi = top == 3 ? m.v[3] : top == 2 ? m.v[2] : top == 1 ? m.v[1] : m.v[0];
+  const unsigned long long below = top == 3 ? m.v[2] : top == 2 ? m.v[1] : top == 1 ? m.v[0] : 0ull;
+  if (hi == 0) return 0;
+  const int lz = __clzll((long long)hi);
+  const int len = 64 * top + 64 - lz;  // bit length
+  if (len <= 55) return hi;            // (top == 0 here)
+  // 56 bits from the leading one: `hi` shifted to the top of a word, filled from the limb below
+  const unsigned long long w = lz ? (hi << lz) | (below >> (64 - lz)) : hi;
+  return ((unsigned long long)len << 55) | ((w >> 8) & ((1ull << 55) - 1));
+}
+// The C segment of one long linear row: magnitudes and wires go to shared memory once and the network sorts an index
+// permutation by (dropped?, |fold(coef)|, wire) — the kept terms come out in exactly the order k_layout's rank
+// computation gives, in O(n log^2 n) on-chip compares.
 __global__ void k_layout_long(Raw r, const uint32_t* keep, const uint32_t* seg_nz, const uint32_t* rflags,
-                              const uint32_t* long_rows, uint32_t n_long, uint32_t* col, fr::u256* coef,
-                              uint8_t* nontriv) {
+                              const uint32_t* long_rows, uint32_t n_long, uint32_t len_lo, uint32_t len_hi, uint32_t* col,
+                              fr::u256* coef, uint8_t* nontriv) {
   extern __shared__ unsigned long long sm_u64[];
   if (blockIdx.x >= n_long) return;
   const uint32_t row = long_rows[blockIdx.x];
@@ -568,47 +670,48 @@ __global__ void k_layout_long(Raw r, const uint32_t* keep, const uint32_t* seg_n
   const uint32_t s = 3 * row + 2;
   const uint64_t b = r.seg[s], e = r.seg[s + 1];
   const uint32_t n = (uint32_t)(e - b);
-  if (n <= LAYOUT_LONG_MIN || n > LAYOUT_LONG_MAX) return;
-  uint32_t np2 = 1;
-  while (np2 < n) np2 <<= 1;
-  fr::u256* mag = reinterpret_cast<fr::u256*>(sm_u64);
-  uint32_t* wv = reinterpret_cast<uint32_t*>(mag + n);
+  if (n <= len_lo || n > len_hi) return;  // (this launch's length class: the shared memory is sized for len_hi)
+  LimbsSoA mag;
+  mag.carve(sm_u64, n);
+  unsigned long long* key = sm_u64 + 4 * (size_t)n;
+  uint32_t* wv = reinterpret_cast<uint32_t*>(key + n);
   uint32_t* idx = wv + n;
-  uint8_t* kp = reinterpret_cast<uint8_t*>(idx + np2);
+  uint8_t* kp = reinterpret_cast<uint8_t*>(idx + n);
   const bool fl = (rf & RF_C3_FLIP) != 0;
-  for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) {
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     idx[i] = i;
-    if (i < n) {
-      mag[i] = mag_of(r.coef[b + i], fl);
-      wv[i] = r.col[b + i];
-      kp[i] = (uint8_t)keep[b + i];
-    }
+    const fr::u256 m = mag_of(r.coef[b + i], fl);
+    mag.put(i, m);
+    const uint32_t kept = keep[b + i];
+    key[i] = kept ? order_key(m) : ~0ull;  // dropped zeros last (no key reaches 2^63)
+    wv[i] = r.col[b + i];
+    kp[i] = (uint8_t)kept;
   }
   __syncthreads();
-  for (uint32_t k = 2; k <= np2; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) {
-        const uint32_t ixj = i ^ j;
-        if (ixj > i) {
-          const uint32_t a = idx[i], c = idx[ixj];
-          const bool up = (i & k) == 0;
-          const bool a_after_c = layout_less(mag, wv, kp, n, c, a);
-          if (a_after_c == up) {
-            idx[i] = c;
-            idx[ixj] = a;
-          }
-        }
-      }
-      __syncthreads();
+  auto less = [&](uint32_t x, uint32_t y) {  // kept terms first (dropped zeros last), then (magnitude, wire, position)
+    const unsigned long long kx = key[x], ky = key[y];
+    if (kx != ky) return kx < ky;
+    if (kx == ~0ull) return x < y;
+    if (kx >> 55) {  // not exact: the limbs
+      const int cm = mag.cmp(x, y);
+      if (cm != 0) return cm < 0;
     }
-  }
+    const uint32_t wx = wv[x], wy = wv[y];
+    if (wx != wy) return wx < wy;
+    return x < y;
+  };
+  // circom writes a sum in wire order, and the weights of a bit decomposition grow with the wires: many segments are in
+  // (|fold(coef)|, wire) order already, with nothing dropped — one pass of neighbour compares instead of the network
+  bool in_order = true;
+  for (uint32_t i = threadIdx.x; i + 1 < n; i += blockDim.x) in_order = in_order && less(i, i + 1);
+  if (!__syncthreads_and(in_order)) block_sort_perm(idx, n, less);
   for (uint32_t p = threadIdx.x; p < n; p += blockDim.x) {
     const uint32_t el = idx[p];
-    if (el >= n || !kp[el]) continue;
+    if (!kp[el]) continue;
     const uint32_t dst = seg_nz[s] + p;  // kept terms occupy the first positions of the sorted order
     col[dst] = wv[el];
-    coef[dst] = r.coef[b + el];
-    nontriv[wv[el]] = 1;
+    fr::stg256(coef + dst, r.coef[b + el]);
+    if (!nontriv[wv[el]]) nontriv[wv[el]] = 1;
   }
 }
 // 32-byte sweep records: flags + up to 6 inline wires (A u B first, then C)
@@ -754,6 +857,171 @@ struct U256Less {  // order of the candidate bound values (ties: any order, equa
   __device__ __forceinline__ bool operator()(const fr::u256& a, const fr::u256& b) const { return fr::cmp(a, b) < 0; }
 };
 
+
+// ---- sample sort of the candidate bound values ------------------------------------------------------------------
+// ecdsa has 160 k candidates, almost all distinct: a merge sort of that many 32-byte keys is ten latency-bound passes
+// (0.32 ms, the longest chain of the set-up).  Here: a hashed sample is sorted by one block and gives B - 1 splitters;
+// every value finds its bucket by a search in shared memory and takes a slot in it; one block per bucket sorts it in
+// shared memory.  Four launches; the order is (value, index), so equal values do not pile up in one bucket.  A bucket
+// that does not fit the shared memory is sorted by the same network in global memory (slow, correct, never seen).
+#define SS_MIN 16384u      // below: the library merge sort (a few passes)
+#define SS_MAX 524288u     // above: the library merge sort (bandwidth-bound there, and the sample would not fit one block)
+#define SS_BUCKET_CAP 2048u
+#define SS_OVERSAMPLE 4u
+struct SsKey {
+  fr::u256 v;
+  uint32_t i;
+};
+__device__ __forceinline__ bool ss_less(const fr::u256& a, uint32_t ia, const fr::u256& b, uint32_t ib) {
+  const int c = fr::cmp(a, b);
+  return c < 0 || (c == 0 && ia < ib);
+}
+__device__ __forceinline__ uint32_t ss_hash(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+// one block: sort a hashed sample of n_s values (one per stratum), keep every SS_OVERSAMPLE-th as a splitter
+__global__ void k_ss_sample(const fr::u256* cand, uint32_t n, uint32_t n_s, SsKey* split) {
+  extern __shared__ unsigned long long ss_smem[];
+  LimbsSoA val;
+  val.carve(ss_smem, n_s);
+  unsigned long long* key = ss_smem + 4 * (size_t)n_s;
+  uint32_t* gi = reinterpret_cast<uint32_t*>(key + n_s);
+  uint32_t* perm = gi + n_s;
+  const uint32_t stride = n / n_s;  // >= 2
+  for (uint32_t j = threadIdx.x; j < n_s; j += blockDim.x) {
+    const uint32_t at = j * stride + ss_hash(j) % stride;
+    const fr::u256 v = fr::ldg256(cand + at);
+    val.put(j, v);
+    key[j] = order_key(v);
+    gi[j] = at;
+    perm[j] = j;
+  }
+  __syncthreads();
+  block_sort_perm(perm, n_s, [&](uint32_t x, uint32_t y) {
+    const unsigned long long kx = key[x], ky = key[y];
+    if (kx != ky) return kx < ky;
+    if (kx >> 55) {
+      const int c = val.cmp(x, y);
+      if (c != 0) return c < 0;
+    }
+    return gi[x] < gi[y];
+  });
+  for (uint32_t b = threadIdx.x + 1; b < n_s / SS_OVERSAMPLE; b += blockDim.x) {
+    const uint32_t e = perm[b * SS_OVERSAMPLE];
+    fr::u256 v;
+    for (int k = 0; k < 4; ++k) v.v[k] = val.l[k][e];
+    split[b - 1].v = v;
+    split[b - 1].i = gi[e];
+  }
+}
+// bucket of every value (number of splitters <= it) and its slot there
+__global__ void k_ss_count(const fr::u256* cand, uint32_t n, const SsKey* split, uint32_t n_b, uint32_t* bkt,
+                           uint32_t* slot, unsigned int* counts) {
+  extern __shared__ unsigned long long ss_smem[];
+  fr::u256* sv = reinterpret_cast<fr::u256*>(ss_smem);
+  uint32_t* si = reinterpret_cast<uint32_t*>(sv + n_b);
+  unsigned int* hist = si + n_b;  // n_b counters, then their global bases
+  unsigned int* base = hist + n_b;
+  for (uint32_t b = threadIdx.x; b < n_b; b += blockDim.x) {
+    if (b + 1 < n_b) {
+      sv[b] = split[b].v;
+      si[b] = split[b].i;
+    }
+    hist[b] = 0;
+  }
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t b = 0, local = 0;
+  if (i < n) {
+    const fr::u256 v = fr::ldg256(cand + i);
+    uint32_t lo = 0, hi = n_b - 1;  // splitters [0, lo) are <= v, [hi, n_b - 1) are > v
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (ss_less(v, i, sv[mid], si[mid]))
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    b = lo;
+    local = atomicAdd(hist + b, 1u);
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < n_b; k += blockDim.x) base[k] = hist[k] ? atomicAdd(counts + k, hist[k]) : 0;
+  __syncthreads();
+  if (i < n) {
+    bkt[i] = b;
+    slot[i] = base[b] + local;
+  }
+}
+// exclusive scan of the bucket sizes (one block; n_b <= 1024)
+__global__ void k_ss_starts(const unsigned int* counts, uint32_t n_b, uint32_t* starts) {
+  __shared__ uint32_t sc[1024];
+  const uint32_t t = threadIdx.x;
+  sc[t] = t < n_b ? counts[t] : 0;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    const uint32_t x = t >= d ? sc[t - d] : 0;
+    __syncthreads();
+    sc[t] += x;
+    __syncthreads();
+  }
+  if (t < n_b) starts[t] = sc[t] - counts[t];
+  if (t == 0) starts[n_b] = sc[1023];
+}
+__global__ void k_ss_scatter(const fr::u256* cand, uint32_t n, const uint32_t* bkt, const uint32_t* slot,
+                             const uint32_t* starts, fr::u256* val2, uint32_t* gi2) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t d = starts[bkt[i]] + slot[i];
+  fr::stg256(val2 + d, fr::ldg256(cand + i));
+  gi2[d] = i;
+}
+// one block per bucket: sorted indices of the bucket's values into idx[starts[b] ...)
+__global__ void k_ss_bucket(const fr::u256* val2, const uint32_t* gi2, const uint32_t* starts, uint32_t* perm_scratch,
+                            uint32_t* idx) {
+  extern __shared__ unsigned long long ss_smem[];
+  const uint32_t lo = starts[blockIdx.x], n = starts[blockIdx.x + 1] - lo;
+  if (n == 0) return;
+  if (n <= SS_BUCKET_CAP) {
+    LimbsSoA val;
+    val.carve(ss_smem, SS_BUCKET_CAP);
+    unsigned long long* key = ss_smem + 4 * (size_t)SS_BUCKET_CAP;
+    uint32_t* gi = reinterpret_cast<uint32_t*>(key + SS_BUCKET_CAP);
+    uint32_t* perm = gi + SS_BUCKET_CAP;
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+      const fr::u256 v = fr::ldg256(val2 + lo + j);
+      val.put(j, v);
+      key[j] = order_key(v);
+      gi[j] = gi2[lo + j];
+      perm[j] = j;
+    }
+    __syncthreads();
+    block_sort_perm(perm, n, [&](uint32_t x, uint32_t y) {
+      const unsigned long long kx = key[x], ky = key[y];
+      if (kx != ky) return kx < ky;
+      if (kx >> 55) {
+        const int c = val.cmp(x, y);
+        if (c != 0) return c < 0;
+      }
+      return gi[x] < gi[y];
+    });
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) idx[lo + j] = gi[perm[j]];
+  } else {  // (global memory: every step goes through the L2)
+    uint32_t* perm = perm_scratch + lo;
+    const fr::u256* v = val2 + lo;
+    const uint32_t* g = gi2 + lo;
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) perm[j] = j;
+    __syncthreads();
+    block_sort_perm(perm, n, [&](uint32_t x, uint32_t y) { return ss_less(v[x], g[x], v[y], g[y]); });
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) idx[lo + j] = g[perm[j]];
+  }
+}
+
 template <class T>
 static cudaError_t h2d(T* dst, const T* src, size_t n, cudaStream_t s) {
   if (!n) return cudaSuccess;
@@ -834,13 +1102,13 @@ __global__ void k_expand_class(const uint8_t* cls, uint64_t nnz, fr::u256* coef,
   if (t < nnz) {
     const uint8_t c = cls[t];
     if (c == 0) {
-      coef[t] = fr::make_u256(0, 0, 0, 0);
+      fr::stg256(coef + t, fr::make_u256(0, 0, 0, 0));
     } else if (c == 1) {
-      coef[t] = fr::make_u256(1, 0, 0, 0);
+      fr::stg256(coef + t, fr::make_u256(1, 0, 0, 0));
     } else if (c == 2) {
       fr::u256 m;
       fr::sub_cc(m, fr::modulus(), fr::make_u256(1, 0, 0, 0));
-      coef[t] = m;
+      fr::stg256(coef + t, m);
     } else if (c == 3) {
       n3 = 1;
     } else {
@@ -859,7 +1127,7 @@ __global__ void k_expand_other(const fr::u256* other, const uint32_t* term, uint
     chk[1] = 1;  // not a class-3 term, or the list is not strictly ascending
     return;
   }
-  coef[t] = other[j];
+  fr::stg256(coef + t, fr::ldg256(other + j));
 }
 __global__ void k_widen_seg(const uint32_t* seg32, uint64_t n, unsigned long long* seg) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1082,14 +1350,29 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   raw.nnz = nnz;
   raw.seg = d_seg64;
   raw.col = d_col_raw;
-  raw.coef = d_coef_raw;
+  raw.coef.p = d_coef_raw;
 
   // ---- non-zero compaction offsets ------------------------------------------------------------
   uint32_t *d_keep, *d_pos, *d_segnz;
   CK(tmp.alloc(&d_keep, nnz + 1));
   CK(tmp.alloc(&d_pos, nnz + 1));
   CK(A.alloc(&d_segnz, 3 * N + 1));
-  k_keep<<<nb(nnz + 1, 256), 256, 0, s>>>(raw, d_keep);
+  // Three independent chains from here to the counters' readback: the compaction offsets (keep / scan / seg) on one side
+  // stream, the long rows' classification (a warp per row, latency-bound) on the other, the short rows' on the main one.
+  cudaStream_t sa = R->side ? R->side : s, sb = R->side2 ? R->side2 : s;
+  struct PreEvents {
+    cudaEvent_t up, a, b;
+    PreEvents() {
+      cudaEventCreateWithFlags(&up, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
+    }
+    ~PreEvents() {
+      cudaEventDestroy(up);
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
+    }
+  } pre_ev;
   size_t cub_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, d_keep, d_pos, (int)(nnz + 1), s);
   void* d_cub;
@@ -1104,14 +1387,6 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(A.alloc((uint8_t**)&d_cub, cub_bytes));
   R->d_cub = d_cub;
   R->cub_bytes = cub_bytes;
-  {
-    size_t b = cub_bytes;
-    CK(cub::DeviceScan::ExclusiveSum(d_cub, b, d_keep, d_pos, (int)(nnz + 1), s));
-  }
-  k_seg<<<nb(3 * N + 1, 256), 256, 0, s>>>(raw, d_pos, d_segnz);
-
-  sp_lap("keep / scan / seg");
-  // ---- classify -------------------------------------------------------------------------------
   uint32_t* d_rflags;
   RowAux* d_aux;
   Counters* d_cnt;
@@ -1120,11 +1395,27 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(A.alloc(&d_aux, N));
   CK(tmp.alloc(&d_cnt, 1));
   CK(tmp.alloc(&d_c3_long, N));
-  CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), s));
   uint32_t* d_longc;
   CK(tmp.alloc(&d_longc, N));
+  CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), s));
+  if (N) k_longc<<<nb(N, 256), 256, 0, s>>>(raw, d_cnt, d_longc);
+  cudaEventRecord(pre_ev.up, s);  // the rows are on the device, the long ones listed
+  if (sa != s) cudaStreamWaitEvent(sa, pre_ev.up, 0);
+  if (sb != s) cudaStreamWaitEvent(sb, pre_ev.up, 0);
+  k_keep<<<nb(nnz + 1, 256), 256, 0, sa>>>(raw, d_keep);
+  {
+    size_t b = cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(d_cub, b, d_keep, d_pos, (int)(nnz + 1), sa));
+  }
+  k_seg<<<nb(3 * N + 1, 256), 256, 0, sa>>>(raw, d_pos, d_segnz);
+  cudaEventRecord(pre_ev.a, sa);
+  sp_lap("keep / scan / seg");
+  // ---- classify -------------------------------------------------------------------------------
+  if (N) k_classify_long<<<592, 256, 0, sb>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long, d_longc);
+  cudaEventRecord(pre_ev.b, sb);
   if (N) k_classify<<<nb(N, 128), 128, 0, s>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long, d_longc);
-  if (N) k_classify_long<<<148, 256, 0, s>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long, d_longc);
+  if (sa != s) cudaStreamWaitEvent(s, pre_ev.a, 0);
+  if (sb != s) cudaStreamWaitEvent(s, pre_ev.b, 0);
   Counters cnt;
   CK(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
   uint32_t nnz_nz = 0;
@@ -1169,6 +1460,85 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   cudaEventRecord(ev_fork, s);
   cudaStreamWaitEvent(s2, ev_fork, 0);
   if (s3 != s) cudaStreamWaitEvent(s3, ev_fork, 0);
+  // Order of the launches: the GPU work after the fork is ~0.2 ms in all, about what the host needs to enqueue it — the
+  // main stream's layout of the short rows goes first, then the long rows' chain, then the bound table's.
+  if (N) k_layout<<<nb(N, 128), 128, 0, s>>>(raw, d_keep, d_pos, d_segnz, d_rflags, d_col, d_coef, d_nontriv);
+  // Long bit-decomposition candidates (main stream, while the side stream sorts the bound values)
+  std::vector<Pow2Entry> tab;
+  cudaEvent_t ev_c3;
+  cudaEventCreateWithFlags(&ev_c3, cudaEventDisableTiming);
+  if (cnt.n_c3_long) {
+    // sorted table of 2^i mod p for i < max_c, built on the host (pure constants: kept between calls)
+    uint32_t tn = cnt.max_c;
+    static std::mutex tab_mu;
+    static std::vector<Pow2Entry> tab_cache;
+    static bool tab_repeats = false;
+    {
+      std::lock_guard<std::mutex> lk(tab_mu);
+      if (tab_cache.size() != tn) {
+        tab_cache.resize(tn);
+        fr::u256 x = fr::make_u256(1, 0, 0, 0);
+        for (uint32_t i = 0; i < tn; ++i) {
+          tab_cache[i].v = x;
+          tab_cache[i].e = i;
+          x = fr::add(x, x);
+        }
+        std::sort(tab_cache.begin(), tab_cache.end(),
+                  [](const Pow2Entry& a, const Pow2Entry& b) { return fr::cmp(a.v, b.v) < 0; });
+        tab_repeats = false;
+        for (uint32_t i = 1; i < tn; ++i) tab_repeats |= fr::eq(tab_cache[i].v, tab_cache[i - 1].v);
+      }
+      tab = tab_cache;
+    }
+    if (tab_repeats) {
+      err = "2^i mod p repeats below the longest row length";
+      cudaStreamSynchronize(s2);  // the side chain works in `tmp`, which is released on return
+      cudaStreamSynchronize(s);
+      cudaStreamSynchronize(s3);
+      return ECNE_E_UNSUPPORTED;
+    }
+    Pow2Entry* d_tab;
+    CK(tmp.alloc(&d_tab, tn));
+    CK(cudaMemcpyAsync(d_tab, tab.data(), tn * sizeof(Pow2Entry), cudaMemcpyHostToDevice, s3));
+    uint32_t mask_words = (tn + 31) / 32;
+    size_t smem = (size_t)2 * mask_words * sizeof(unsigned int);
+    if (smem > 200 * 1024) {
+      err = "row too long for the bit-decomposition classifier";
+      cudaStreamSynchronize(s2);
+      cudaStreamSynchronize(s);
+      cudaStreamSynchronize(s3);
+      return ECNE_E_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
+      CK(cudaFuncSetAttribute(k_classify_c3_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_classify_c3_long<<<cnt.n_c3_long, 256, smem, s3>>>(raw, d_rflags, d_aux, d_c3_long, cnt.n_c3_long, d_tab, tn, mask_words);
+    cudaEventRecord(ev_c3, s3);  // (`tab` lives until the function's final synchronisation)
+  }
+
+  // ---- sweep layout ---------------------------------------------------------------------------
+  // long rows on `s3` (behind their Case-3 classification, whose flip flag orders their C terms), short rows on the
+  // main stream: the 208 sorting blocks of ecdsa's long rows (0.14 ms) run beside the 0.16 ms pass over every term
+  if (cnt.n_long) {
+    k_long_rows<<<nb(N, 256), 256, 0, s3>>>((uint32_t)N, d_rflags, d_long, d_nlong);
+    k_layout_long_rows<<<nb((uint64_t)cnt.n_long * 32, 128), 128, 0, s3>>>(raw, d_keep, d_pos, d_segnz, d_rflags, d_long,
+                                                                         cnt.n_long, d_col, d_coef, d_nontriv);
+    // two length classes (both kernels apply the same length tests): ecdsa's 4128 rows of ~88 terms sort in 20 KB
+    // of shared memory with many blocks per SM, its 208 rows of 1025 terms get the large block
+    auto smem_for = [](uint32_t len) {  // per term: four limbs, order key, wire, permutation entry, kept flag
+      return (size_t)len * (sizeof(fr::u256) + sizeof(unsigned long long) + 2 * sizeof(uint32_t) + 1) + 64;
+    };
+    if (cnt.max_seg_c > LAYOUT_LONG_MIN)
+      k_layout_long<<<cnt.n_long, 256, smem_for(LAYOUT_LONG_MID), s3>>>(raw, d_keep, d_segnz, d_rflags, d_long, cnt.n_long,
+                                                                       LAYOUT_LONG_MIN, LAYOUT_LONG_MID, d_col, d_coef, d_nontriv);
+    if (cnt.max_seg_c > LAYOUT_LONG_MID) {
+      const size_t smem = smem_for(std::min<uint32_t>(cnt.max_seg_c, LAYOUT_LONG_MAX));
+      CK(cudaFuncSetAttribute(k_layout_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(LAYOUT_LONG_MAX)));
+      k_layout_long<<<cnt.n_long, 1024, smem, s3>>>(raw, d_keep, d_segnz, d_rflags, d_long, cnt.n_long, LAYOUT_LONG_MID,
+                                                    LAYOUT_LONG_MAX, d_col, d_coef, d_nontriv);
+    }
+  }
+  cudaEventRecord(ev_long, s3);
+  sp_lap("layout of the short rows | c3_long + layout of the long rows");
   k_consts<<<1, 256, 0, s2>>>(d_tvals);
   if (N) k_values<<<nb(N, 128), 128, 0, s2>>>(raw, d_rflags, d_aux, d_roots, d_tvals, d_next, d_next + 1);
   const uint32_t nc = N_CONST + cnt.n2b;
@@ -1185,11 +1555,47 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(A.alloc(&d_table, nc));
   void* d_ms = nullptr;
   size_t d_ms_bytes = 0;
-  k_iota<<<nb(nc, 256), 256, 0, s2>>>(d_idx, nc);
-  {  // one merge sort of (value, index) pairs under a 256-bit comparator (a handful of launches; an LSD radix sort
-     // over four 64-bit limbs costs 40 launch-bound passes for these ~10^5 values).  The VALUES travel with the
-     // indices — ecdsa's 160 k constants are almost all distinct, and sorting the index permutation alone made every
-     // comparison two random 32-byte gathers (0.45 ms; the critical path of the set-up).
+  const char* ss_env = getenv("ECNE_SAMPLE_SORT");  // testing knob: 0 = always the library sort, 1 = sample sort from 1024 values on
+  const bool ss_off = ss_env && atoi(ss_env) == 0;
+  const uint32_t ss_min = ss_env && atoi(ss_env) == 1 ? 1024u : SS_MIN;
+  if (!ss_off && nc >= ss_min && nc <= SS_MAX) {
+    // sample sort (see k_ss_*): 5 launches, ~40 us for ecdsa's 160 k values
+    uint32_t n_b = 64;
+    while (n_b < 1024 && n_b * 512u < nc) n_b <<= 1;
+    while (n_b > 2 && (nc / (n_b * SS_OVERSAMPLE)) < 2) n_b >>= 1;  // (the knob's small inputs: strata of two values at least)
+    const uint32_t n_s = n_b * SS_OVERSAMPLE;
+    SsKey* d_split;
+    uint32_t *d_bkt, *d_slot, *d_starts, *d_gi2;
+    unsigned int* d_counts;
+    fr::u256* d_val2;
+    CK(tmp.alloc(&d_split, n_b));
+    CK(tmp.alloc(&d_bkt, nc));
+    CK(tmp.alloc(&d_slot, nc));
+    CK(tmp.alloc(&d_starts, n_b + 1));
+    CK(tmp.alloc(&d_gi2, nc));
+    CK(tmp.alloc(&d_counts, n_b));
+    CK(tmp.alloc(&d_val2, nc));
+    CK(cudaMemsetAsync(d_counts, 0, n_b * sizeof(unsigned int), s2));
+    const size_t sm_sample = (size_t)n_s * (sizeof(fr::u256) + 8 + 2 * sizeof(uint32_t));
+    const size_t sm_count = (size_t)n_b * (sizeof(fr::u256) + 3 * sizeof(uint32_t));
+    const size_t sm_bucket = (size_t)SS_BUCKET_CAP * (sizeof(fr::u256) + 8 + 2 * sizeof(uint32_t));
+    CK(cudaFuncSetAttribute(k_ss_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sample));
+    CK(cudaFuncSetAttribute(k_ss_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_bucket));
+    k_ss_sample<<<1, 1024, sm_sample, s2>>>(d_tvals, nc, n_s, d_split);
+    k_ss_count<<<nb(nc, 256), 256, sm_count, s2>>>(d_tvals, nc, d_split, n_b, d_bkt, d_slot, d_counts);
+    k_ss_starts<<<1, 1024, 0, s2>>>(d_counts, n_b, d_starts);
+    k_ss_scatter<<<nb(nc, 256), 256, 0, s2>>>(d_tvals, nc, d_bkt, d_slot, d_starts, d_val2, d_gi2);
+    k_ss_bucket<<<n_b, 512, sm_bucket, s2>>>(d_val2, d_gi2, d_starts, d_slot, d_idx);
+    size_t need = 0;  // scratch of the scan below
+    cub::DeviceScan::InclusiveSum((void*)nullptr, need, d_flag, d_incl, (int)nc, s2);
+    need = std::max<size_t>(need, (size_t)1 << 20);
+    CK(tmp.alloc((uint8_t**)&d_ms, need));
+    d_ms_bytes = need;
+  } else {
+    // one merge sort of (value, index) pairs under a 256-bit comparator (a handful of launches; an LSD radix sort
+    // over four 64-bit limbs costs 40 launch-bound passes).  The VALUES travel with the indices: sorting the index
+    // permutation alone made every comparison two random 32-byte gathers.
+    k_iota<<<nb(nc, 256), 256, 0, s2>>>(d_idx, nc);
     fr::u256* d_keys;
     CK(tmp.alloc(&d_keys, nc));
     CK(cudaMemcpyAsync(d_keys, d_tvals, (size_t)nc * sizeof(fr::u256), cudaMemcpyDeviceToDevice, s2));
@@ -1206,73 +1612,13 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     CK(cub::DeviceScan::InclusiveSum(d_ms, b, d_flag, d_incl, (int)nc, s2));
   }
   k_ranks<<<nb(nc, 256), 256, 0, s2>>>(d_tvals, d_idx, d_incl, nc, d_rank_of, d_table);
-  sp_lap("values + sort + ranks (side)");
-  // Long bit-decomposition candidates (main stream, while the side stream sorts the bound values)
-  std::vector<Pow2Entry> tab;
-  cudaEvent_t ev_c3;
-  cudaEventCreateWithFlags(&ev_c3, cudaEventDisableTiming);
-  if (cnt.n_c3_long) {
-    // sorted table of 2^i mod p for i < max_c, built on the host (pure constants)
-    uint32_t tn = cnt.max_c;
-    tab.resize(tn);
-    fr::u256 x = fr::make_u256(1, 0, 0, 0);
-    for (uint32_t i = 0; i < tn; ++i) {
-      tab[i].v = x;
-      tab[i].e = i;
-      x = fr::add(x, x);
-    }
-    std::sort(tab.begin(), tab.end(),
-              [](const Pow2Entry& a, const Pow2Entry& b) { return fr::cmp(a.v, b.v) < 0; });
-    for (uint32_t i = 1; i < tn; ++i)
-      if (fr::eq(tab[i].v, tab[i - 1].v)) {
-        err = "2^i mod p repeats below the longest row length";
-        cudaStreamSynchronize(s2);  // the side chain works in `tmp`, which is released on return
-        cudaStreamSynchronize(s);
-        cudaStreamSynchronize(s3);
-        return ECNE_E_UNSUPPORTED;
-      }
-    Pow2Entry* d_tab;
-    CK(tmp.alloc(&d_tab, tn));
-    CK(cudaMemcpyAsync(d_tab, tab.data(), tn * sizeof(Pow2Entry), cudaMemcpyHostToDevice, s3));
-    uint32_t mask_words = (tn + 31) / 32;
-    const int warps = 4;
-    size_t smem = (size_t)warps * 2 * mask_words * sizeof(unsigned int);
-    if (smem > 200 * 1024) {
-      err = "row too long for the bit-decomposition classifier";
-      cudaStreamSynchronize(s2);
-      cudaStreamSynchronize(s);
-      cudaStreamSynchronize(s3);
-      return ECNE_E_UNSUPPORTED;
-    }
-    if (smem > 48 * 1024)
-      CK(cudaFuncSetAttribute(k_classify_c3_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_classify_c3_long<<<nb(cnt.n_c3_long, warps), warps * 32, smem, s3>>>(
-        raw, d_rflags, d_aux, d_c3_long, cnt.n_c3_long, d_tab, tn, mask_words);
-    cudaEventRecord(ev_c3, s3);  // (`tab` lives until the function's final synchronisation)
-  }
-
   if (cnt.n_c3_long) cudaStreamWaitEvent(s2, ev_c3, 0);  // k_fill_ranks reads the C3 flags of those rows
   if (N) k_fill_ranks<<<nb(N, 256), 256, 0, s2>>>((uint32_t)N, d_rflags, d_aux, d_rank_of, d_segnz);
   uint32_t h_rank[3], h_tn;
   cudaEventRecord(ev_join, s2);
 
-  sp_lap("c3_long + fill_ranks");
-  // ---- sweep layout ---------------------------------------------------------------------------
-  // long rows on `s3` (behind their Case-3 classification, whose flip flag orders their C terms), short rows on the
-  // main stream: the 208 sorting blocks of ecdsa's long rows (0.14 ms) run beside the 0.16 ms pass over every term
-  if (cnt.n_long) {
-    k_long_rows<<<nb(N, 256), 256, 0, s3>>>((uint32_t)N, d_rflags, d_long, d_nlong);
-    // shared memory for the longest segment the kernel accepts (both kernels apply the same length test)
-    const size_t smem = (size_t)LAYOUT_LONG_MAX * (sizeof(fr::u256) + 2 * sizeof(uint32_t) + 1) + 64;  // 168 KB
-    CK(cudaFuncSetAttribute(k_layout_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_layout_long<<<cnt.n_long, 1024, smem, s3>>>(raw, d_keep, d_segnz, d_rflags, d_long, cnt.n_long, d_col, d_coef,
-                                                  d_nontriv);
-  }
-  cudaEventRecord(ev_long, s3);
-  if (nnz)
-    k_layout<<<nb(nnz, 256), 256, 0, s>>>(raw, d_keep, d_pos, d_segnz, d_rflags, d_col, d_coef, d_nontriv);
+  sp_lap("values + sort + ranks (side)");
   if (s3 != s) cudaStreamWaitEvent(s, ev_long, 0);  // from here on: final row flags, every row laid out
-  sp_lap("layout (short + long rows)");
   if (n_sp_in) k_mark<<<nb(n_sp_in, 256), 256, 0, s>>>(d_sp_in, (uint32_t)n_sp_in, d_nontriv);
   if (n_sp_out) k_mark<<<nb(n_sp_out, 256), 256, 0, s>>>(d_sp_out, (uint32_t)n_sp_out, d_nontriv);
   if (p->n_targets) k_mark<<<nb(p->n_targets, 256), 256, 0, s>>>(d_targets, (uint32_t)p->n_targets, d_nontriv);

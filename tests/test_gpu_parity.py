@@ -590,6 +590,60 @@ def test_rows_with_hundreds_of_terms(nbits, out_known):
     assert bool(g.c.verdict) == bool(o.c.verdict)
 
 
+@pytest.mark.parametrize("nbits", [100, 600])
+@pytest.mark.parametrize("zeros", [False, True])
+def test_long_rows_whose_terms_are_not_in_weight_order(nbits, zeros):
+    """The set-up stores the C terms of a linear row by (|fold(coef)|, wire) (Case 5 walks them sorted, :1265).  Segments
+    that are in that order already take a one-pass shortcut; these are not: the weights 2^i are dealt to the wires by a
+    random permutation, the second row's weights repeat (ties broken by wire), and explicit zero coefficients (dropped
+    terms) sit in between.  Both length classes of the sorting kernel (<= 512 terms, beyond)."""
+    rng = np.random.default_rng(nbits + zeros)
+    bits = list(range(3, 3 + nbits))
+    out, extra, dead = 2, 3 + nbits, 4 + nbits
+    perm = rng.permutation(nbits)
+    rows = [({b: 1}, {b: 1, 1: -1}, {}) for b in bits]
+    c1 = {out: 1, **{b: -pow(2, int(perm[i]), P) for i, b in enumerate(bits)}}
+    c2 = {extra: 1, **{b: int(3 + perm[i] % 7) for i, b in enumerate(bits)}}
+    if zeros:
+        for b in bits[::5]:
+            c2[b] = 0
+        c1[dead] = 0
+    rows.append(({}, {}, c1))
+    rows.append(({}, {}, c2))
+    for known in ([1, out], [1]):
+        m = MiniR1CS(rows, n_vars=dead, known=known, targets=[extra])
+        st, g, ost, o = both(m)
+        assert st == ost == 0, api._engine().ecne_last_error()
+        assert g.unique_bytes() == o.unique_bytes() and g.known_bytes() == o.known_bytes()
+        assert np.array_equal(g.lb, o.lb) and np.array_equal(g.ub, o.ub)
+        assert bool(g.c.verdict) == bool(o.c.verdict)
+
+
+def test_sample_sort_of_the_bound_values_gives_the_library_sorts_ranks(monkeypatch):
+    """The bound-value table (distinct candidate values in field order, ranks stored per row) is built by a sample sort
+    between 16 k and 512 k values and by cub's merge sort outside; ECNE_SAMPLE_SORT=1 lowers the threshold to 1024 values,
+    =0 switches it off.  Same complete state either way, on systems with thousands of distinct constants and with one
+    constant repeated thousands of times (ties ordered by index: no bucket overflows)."""
+    rng = np.random.default_rng(5)
+    for distinct in (True, False):
+        n = 3000
+        rows = []
+        for i in range(n):
+            v = int(rng.integers(1, 2**62)) * int(rng.integers(1, 2**62)) if distinct else 12345
+            rows.append(({}, {}, {3 + i: 1, 1: -v % P}))          # x_i = v   (Case 2b: a candidate bound value)
+        rows.append(({}, {}, {2: 1, 3: -1, 4: -1}))                # out = x_0 + x_1
+        m = MiniR1CS(rows, n_vars=3 + n, known=[1], targets=[2])
+        res = []
+        for knob in ("0", "1"):
+            monkeypatch.setenv("ECNE_SAMPLE_SORT", knob)
+            st, g, ost, o = both(m)
+            assert st == ost == 0, api._engine().ecne_last_error()
+            assert g.unique_bytes() == o.unique_bytes()
+            assert np.array_equal(g.lb, o.lb) and np.array_equal(g.ub, o.ub)
+            res.append((g.lb.copy(), g.ub.copy(), g.unique_bytes()))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]
+
+
 def test_bound_overwrite_deviation_is_pinned():
     """DESIGN.md §6 / ADVICE r1: the engine merges bounds by intersection, the reference OVERWRITES them (make_bounds,
     :190-201).  They only differ when a rule would loosen a bound, i.e. on an inconsistent circuit: x = 20 together with
