@@ -100,7 +100,7 @@ ENGINE_SYMBOLS = [
 ]
 HOST_SYMBOLS = [
     "ecne_read_r1cs", "ecne_read_r1cs_opts", "ecne_read_r1cs_mem", "ecne_r1cs_free", "ecne_specials_new",
-    "ecne_specials_free", "ecne_abstraction", "ecne_host_last_error", "ecne_compact_coef",
+    "ecne_specials_free", "ecne_abstraction", "ecne_host_last_error", "ecne_compact_coef", "ecne_host_trim",
 ]
 
 _host = None

@@ -21,6 +21,9 @@
 // (reference-unpinned, Julia Dict order) tie rule as csrc/host_r1cs.cpp and oracle/abstraction_ref.py.
 #include <algorithm>
 #include <chrono>
+#include <mutex>
+#include <deque>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -520,76 +523,116 @@ cudaError_t up(Arena& a, const std::vector<T>& v, const T** out, cudaStream_t s,
 }  // namespace
 
 // Pageable host arrays reach the device at ~8 GB/s through cudaMemcpyAsync's own bounce buffer.  Large uploads are
-// staged instead: host threads copy slices into a ring of pinned buffers (kept for the life of the process) and every
-// slice is sent with its own asynchronous copy, so the memcpy of one slice overlaps the DMA of the slices before it —
-// 172 MB of ecdsa in ~5 ms instead of 21.
+// staged instead: a pool of host threads (started once, kept for the life of the process) copies 1 MB slices into
+// pinned buffers — one per worker — and sends every slice with its own asynchronous copy, so the memcpy of one slice
+// overlaps the DMA of the slices before it.  staged_h2d_async() only queues the slices; staged_flush() returns when
+// every queued slice has been handed to its stream (kernels that read the data are launched after it).
 namespace {
-struct StagingRing {
-  static constexpr int SLOTS = 8;
-  static constexpr size_t SLOT_BYTES = (size_t)4 << 20;
-  char* buf[SLOTS] = {nullptr};
-  cudaEvent_t done[SLOTS];
-  bool ok = false;
-  int device = -1;  // the events belong to a device
-  bool init() {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (ok && dev == device) return true;
-    if (ok) {
-      for (int i = 0; i < SLOTS; ++i) {
-        cudaFreeHost(buf[i]);
-        cudaEventDestroy(done[i]);
+struct StagePool {
+  static constexpr int WORKERS = 12;
+  static constexpr size_t SLOT_BYTES = (size_t)1 << 20;
+  struct Task {
+    char* dst;
+    const char* src;
+    size_t len;
+    cudaStream_t s;
+    int dev;
+  };
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::deque<Task> q;
+  size_t pending = 0;  // queued or being copied
+  cudaError_t err = cudaSuccess;
+  bool started = false, usable = true;
+  void worker() {
+    char* buf = nullptr;
+    cudaEvent_t done = nullptr;
+    int dev = -1;
+    for (;;) {
+      Task t;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_work.wait(lk, [&] { return !q.empty(); });
+        t = q.front();
+        q.pop_front();
       }
-      ok = false;
+      cudaError_t e = cudaSuccess;
+      if (t.dev != dev) {  // (the buffer is pinned for every context; the event belongs to a device)
+        if (done) {
+          cudaEventSynchronize(done);
+          cudaEventDestroy(done);
+          done = nullptr;
+        }
+        e = cudaSetDevice(t.dev);
+        if (e == cudaSuccess && !buf) e = cudaHostAlloc((void**)&buf, SLOT_BYTES, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+        if (e == cudaSuccess) dev = t.dev;
+      } else {
+        e = cudaEventSynchronize(done);  // the copy that last read the buffer
+      }
+      if (e == cudaSuccess) {
+        memcpy(buf, t.src, t.len);
+        e = cudaMemcpyAsync(t.dst, buf, t.len, cudaMemcpyHostToDevice, t.s);
+      }
+      if (e == cudaSuccess) e = cudaEventRecord(done, t.s);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+        if (--pending == 0) cv_done.notify_all();
+      }
     }
-    device = dev;
-    for (int i = 0; i < SLOTS; ++i) {
-      if (cudaMallocHost((void**)&buf[i], SLOT_BYTES) != cudaSuccess) return false;
-      if (cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+  }
+  bool start() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (started) return usable;
+    started = true;
+    try {
+      for (int i = 0; i < WORKERS; ++i) std::thread([this] { worker(); }).detach();
+    } catch (...) {
+      usable = false;
     }
-    ok = true;
-    return true;
+    return usable;
   }
 };
-StagingRing g_ring;
+StagePool& stage_pool() {
+  static StagePool* p = new StagePool();  // (never destroyed: its threads outlive main)
+  return *p;
+}
 }  // namespace
 
-cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+cudaError_t staged_h2d_async(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (!bytes) return cudaSuccess;
   cudaPointerAttributes at;
   const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
   cudaGetLastError();  // (an unregistered host pointer is reported as an error by older runtimes)
-  if (pinned || bytes < ((size_t)1 << 20) || !g_ring.init())
+  StagePool& P = stage_pool();
+  if (pinned || bytes < ((size_t)1 << 20) || !P.start())
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
-  const size_t SB = StagingRing::SLOT_BYTES;
-  const size_t n_slices = (bytes + SB - 1) / SB;
-  // Worker t takes slices t, t + T, ...: waits until the copy that last read the slot has completed, fills the slot and
-  // sends it itself (the slices are independent, so the order in which the workers reach the stream does not matter).
-  const int T = StagingRing::SLOTS;
   int dev = 0;
   cudaGetDevice(&dev);
-  std::vector<cudaError_t> errs(T, cudaSuccess);
-  std::vector<std::thread> th;
-  for (int t = 0; t < T && (size_t)t < n_slices; ++t)
-    th.emplace_back([&, t]() {
-      cudaSetDevice(dev);
-      for (size_t j = t; j < n_slices; j += T) {
-        cudaError_t e = cudaEventSynchronize(g_ring.done[t]);  // (also a copy of an EARLIER call may still read the slot)
-        const size_t off = j * SB, len = std::min(SB, bytes - off);
-        if (e == cudaSuccess) {
-          memcpy(g_ring.buf[t], (const char*)src + off, len);
-          e = cudaMemcpyAsync((char*)dst + off, g_ring.buf[t], len, cudaMemcpyHostToDevice, s);
-        }
-        if (e == cudaSuccess) e = cudaEventRecord(g_ring.done[t], s);
-        if (e != cudaSuccess) {
-          errs[t] = e;
-          return;
-        }
-      }
-    });
-  for (auto& x : th) x.join();
-  for (cudaError_t e : errs)
-    if (e != cudaSuccess) return e;
+  const size_t SB = StagePool::SLOT_BYTES;
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    for (size_t off = 0; off < bytes; off += SB) {
+      P.q.push_back({(char*)dst + off, (const char*)src + off, std::min(SB, bytes - off), s, dev});
+      ++P.pending;
+    }
+  }
+  P.cv_work.notify_all();
   return cudaSuccess;
+}
+cudaError_t staged_flush() {
+  StagePool& P = stage_pool();
+  std::unique_lock<std::mutex> lk(P.mu);
+  P.cv_done.wait(lk, [&] { return P.pending == 0; });
+  const cudaError_t e = P.err;
+  P.err = cudaSuccess;
+  return e;
+}
+cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  cudaError_t e = staged_h2d_async(dst, src, bytes, s);
+  const cudaError_t f = staged_flush();
+  return e != cudaSuccess ? e : f;
 }
 
 int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std::string& err) {
@@ -599,9 +642,14 @@ int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std
   S->N = N;
   S->V = p->n_vars;
   S->nnz = nnz;
+  const bool prof = getenv("ECNE_HOST_PROF") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
   CKE(S->arena.alloc(&S->seg, upload_padded<unsigned long long>(3 * N + 2)));
   CKE(S->arena.alloc(&S->col, upload_padded<uint32_t>(nnz + 1)));
   CKE(S->arena.alloc(&S->coef, upload_padded<fr::u256>(nnz + 1)));
+  if (prof)
+    fprintf(stderr, "[ecne dev] device arrays of the unreduced system allocated in %.3f ms\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   Arena tmp;
   tmp.pool = S->arena.pool;
   st = upload_rows(p, S->seg, S->col, S->coef, tmp, s, err);

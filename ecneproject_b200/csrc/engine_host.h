@@ -146,6 +146,8 @@ struct AbstractionStats {
 // abstraction.cu: host -> device copy; pageable sources of 1 MB and more go through a ring of pinned slots filled by
 // worker threads, pinned ones (and small ones) straight into cudaMemcpyAsync
 cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s);
+cudaError_t staged_h2d_async(void* dst, const void* src, size_t bytes, cudaStream_t s);  // queue only ...
+cudaError_t staged_flush();  // ... every queued slice is on its stream when this returns
 // setup.cu: the rows of `p` (seg_ptr / col / coef in either form of include/ecne_abi.h: full 32-byte coefficients, or
 // class bytes + the values that are not 0, 1, p-1; 64- or 32-bit offsets) into device arrays of the on-disk layout.
 // `tmp` lends the scratch of the compact form.  Returns an ecne_status.

@@ -24,6 +24,7 @@
 #include <string>
 #include <unordered_map>
 #include <thread>
+#include <mutex>
 #include <vector>
 
 namespace {
@@ -95,16 +96,77 @@ void parallel_chunks(uint64_t n, uint64_t min_chunk, Fn fn) {
 
 // The arrays of a parsed circuit are hundreds of megabytes that are written once, right after they were allocated: with
 // 4 KB pages the first-touch page faults are a sizeable part of the read (ecdsa: 49 k faults).  Large arrays are
-// aligned to 2 MB and offered to the kernel as huge pages (transparent huge pages in `madvise` mode); free() releases
-// them like any other allocation.
+// aligned to 2 MB and offered to the kernel as huge pages (transparent huge pages in `madvise` mode).
+// Freed large arrays are kept (up to ECNE_HOST_CACHE_MB, default 1024) and handed out again: a process that reads one
+// circuit after another writes into pages it already owns instead of faulting ~10^5 fresh ones per file (a quarter of
+// the read of ecdsa.r1cs).  ecne_host_trim() returns them to the system.
+namespace {
+struct BigCache {
+  std::mutex mu;
+  std::unordered_map<void*, size_t> live;       // blocks handed out by big_alloc
+  std::multimap<size_t, void*> idle;            // freed blocks by size
+  size_t idle_bytes = 0;
+  size_t cap() {
+    static const size_t c = []() {
+      const char* e = getenv("ECNE_HOST_CACHE_MB");
+      return (size_t)(e ? std::max(0, atoi(e)) : 1024) << 20;
+    }();
+    return c;
+  }
+};
+BigCache& big_cache() {
+  static BigCache* c = new BigCache();  // (never destroyed: arrays may be freed during interpreter shutdown)
+  return *c;
+}
+}  // namespace
 static void* big_alloc(size_t bytes) {
   if (bytes < ((size_t)4 << 20)) return malloc(bytes ? bytes : 1);
+  const size_t sz = (bytes + (((size_t)2 << 20) - 1)) & ~(((size_t)2 << 20) - 1);
+  BigCache& c = big_cache();
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.idle.lower_bound(sz);
+    if (it != c.idle.end() && it->first <= sz + sz / 2) {
+      void* p = it->second;
+      c.live[p] = it->first;
+      c.idle_bytes -= it->first;
+      c.idle.erase(it);
+      return p;
+    }
+  }
   void* p = nullptr;
-  if (posix_memalign(&p, (size_t)2 << 20, bytes) != 0) return nullptr;
+  if (posix_memalign(&p, (size_t)2 << 20, sz) != 0) return nullptr;
 #ifdef MADV_HUGEPAGE
-  madvise(p, bytes, MADV_HUGEPAGE);
+  madvise(p, sz, MADV_HUGEPAGE);
 #endif
+  std::lock_guard<std::mutex> lk(c.mu);
+  c.live[p] = sz;
   return p;
+}
+static void big_free(void* p) {
+  if (!p) return;
+  BigCache& c = big_cache();
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.live.find(p);
+    if (it != c.live.end()) {
+      const size_t sz = it->second;
+      c.live.erase(it);
+      if (c.idle_bytes + sz <= c.cap()) {
+        c.idle.emplace(sz, p);
+        c.idle_bytes += sz;
+        return;
+      }
+    }
+  }
+  free(p);
+}
+extern "C" void ecne_host_trim(void) {
+  BigCache& c = big_cache();
+  std::lock_guard<std::mutex> lk(c.mu);
+  for (auto& kv : c.idle) free(kv.second);
+  c.idle.clear();
+  c.idle_bytes = 0;
 }
 
 // ... the same split with the index of the chunk, and the number of chunks it makes, for per-chunk results
@@ -158,15 +220,15 @@ extern "C" const char* ecne_host_last_error(void) { return g_err.c_str(); }
 
 extern "C" void ecne_r1cs_free(ecne_r1cs_t* r) {
   if (!r) return;
-  free(r->seg_ptr);
-  free(r->col);
-  free(r->coef);
-  free(r->known);
-  free(r->targets);
-  free(r->coef_class);
-  free(r->coef_other);
-  free(r->coef_other_term);
-  free(r->seg_ptr32);
+  big_free(r->seg_ptr);
+  big_free(r->col);
+  big_free(r->coef);
+  big_free(r->known);
+  big_free(r->targets);
+  big_free(r->coef_class);
+  big_free(r->coef_other);
+  big_free(r->coef_other_term);
+  big_free(r->seg_ptr32);
   free(r);
 }
 
@@ -240,7 +302,7 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
     uint64_t* raw = (uint64_t*)big_alloc(std::max<uint64_t>(1, nseg) * sizeof(uint64_t));
     struct FreeRaw {
       uint64_t* p;
-      ~FreeRaw() { free(p); }
+      ~FreeRaw() { big_free(p); }
     } free_raw{raw};
     uint64_t total = 0;
     bool ok = segp != nullptr && raw != nullptr;
@@ -263,15 +325,30 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
         std::vector<uint64_t> pos;
       };
       std::vector<Part> parts(T);
-      auto plausible_from = [&](uint64_t c, int steps) {  // `steps` headers from c stay inside the section and look sane
-        for (int k = 0; k < steps && c < sec_end; ++k) {
+      // `steps` headers from c stay inside the section and look sane.  One family of false trails survives any number of
+      // steps: in a run of one-term forms with coefficient 1 (a * b = c rows), the chain that starts 8 bytes late reads
+      // the coefficient's low word as "one term" and its next word as "wire 0", and lands 8 bytes late in the next form
+      // again.  Every wire it sees is 0 — no real stretch of 64 forms mentions nothing but the constant, so a trail
+      // without a single signal is not taken (the proof below would catch it anyway, at the price of a serial walk of
+      // the whole range: 220 k forms of ecdsa.r1cs with 16 ranges).
+      // Another: a word that reads as a term count of a few hundred thousand "terms" and lands on a true header
+      // megabytes away — one pseudo-form that swallows the range.  A form longer than half a range is not a guess.
+      const uint64_t max_form = std::max<uint64_t>((sec_end - s2) / T / 2, 1 << 16);
+      auto plausible_from = [&](uint64_t c, int steps) {
+        bool signal = false;
+        int k = 0;
+        for (; k < steps && c < sec_end; ++k) {
           if (c + 4 > sec_end) return false;
           const uint32_t n = rd32(arr + c);
-          if (n > n_wires || c + 4 + (uint64_t)n * 36 > sec_end) return false;
-          if (n && (rd32(arr + c + 4) >= n_wires || rd32(arr + c + 4 + (uint64_t)(n - 1) * 36) >= n_wires)) return false;
+          if (n > n_wires || (uint64_t)n * 36 > max_form || c + 4 + (uint64_t)n * 36 > sec_end) return false;
+          if (n) {
+            const uint32_t last = rd32(arr + c + 4 + (uint64_t)(n - 1) * 36);
+            if (rd32(arr + c + 4) >= n_wires || last >= n_wires) return false;
+            signal |= last != 0;
+          }
           c += 4 + (uint64_t)n * 36;
         }
-        return true;
+        return signal || k < steps;
       };
       {
         Part* pp = parts.data();
@@ -302,6 +379,7 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
           });
         for (auto& x : th) x.join();
       }
+      lap("  walk: ranges in parallel");
       // proof by construction: part 0 starts on the section's first header, so its chain is the true one and ends on
       // the first true header of part 1.  From there the true chain is followed until it meets part 1's guessed
       // chain (two chains that share a header are identical from it on): a guess that began a few bytes early —
@@ -343,6 +421,12 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
         forms += pre[t].size() + (P.pos.size() - i);
       }
       good = good && parts[T - 1].end_pos == sec_end;
+      lap("  walk: proof");
+      if (prof && getenv("ECNE_HOST_PROF_PARTS"))
+        for (unsigned t = 0; t < T; ++t)
+          fprintf(stderr, "[ecne host] part %u ok %d start +%llu forms %zu repaired %zu dropped %llu end +%llu\n", t, (int)parts[t].ok,
+                  (unsigned long long)(parts[t].start - s2), parts[t].pos.size(), pre[t].size(), (unsigned long long)skip[t],
+                  (unsigned long long)(parts[t].end_pos - s2));
       if (prof) {
         uint64_t dropped = 0, walked_here = 0;
         for (unsigned t = 0; t < T; ++t) dropped += skip[t], walked_here += pre[t].size();
@@ -362,16 +446,22 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
         std::vector<std::thread> th;
         for (unsigned t = 0; t < T; ++t)
           th.emplace_back([=]() {
+            // (term counts from the distance to the next header — the file is not touched again: the part's true
+            // forms are contiguous, the repaired prefix runs into the kept tail, the tail into the part's end)
             uint64_t g = fb[t], run = tb[t];
-            auto put = [&](uint64_t c) {
-              const uint32_t n = rd32(arr + c);
+            auto put = [&](uint64_t c, uint64_t next) {
+              const uint64_t n = (next - c - 4) / 36;
               raw[g] = c;
               segp[g] = run;
               run += n ? n : 1;
               ++g;
             };
-            for (uint64_t c : prep[t]) put(c);
-            for (size_t k = (size_t)sk[t]; k < pp[t].pos.size(); ++k) put(pp[t].pos[k]);
+            const std::vector<uint64_t>& pr = prep[t];
+            const std::vector<uint64_t>& ps = pp[t].pos;
+            const size_t k0 = (size_t)sk[t];
+            const uint64_t tail_first = k0 < ps.size() ? ps[k0] : pp[t].end_pos;
+            for (size_t k = 0; k < pr.size(); ++k) put(pr[k], k + 1 < pr.size() ? pr[k + 1] : tail_first);
+            for (size_t k = k0; k < ps.size(); ++k) put(ps[k], k + 1 < ps.size() ? ps[k + 1] : pp[t].end_pos);
           });
         for (auto& x : th) x.join();
         walked = true;
@@ -496,13 +586,13 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
           r->n_coef_other = others[n_ranges];
           r->seg_ptr32 = seg32p;
         } else {
-          free(clsp);
-          free(otherp);
-          free(termp);
-          free(seg32p);
+          big_free(clsp);
+          big_free(otherp);
+          big_free(termp);
+          big_free(seg32p);
           if (!coefp) {  // (compact only was asked for and cannot be had: terms beyond 32-bit indices never get here)
-            free(segp);
-            free(colp);
+            big_free(segp);
+            big_free(colp);
             free(r);
             return fail(ECNE_E_BOUNDS, "out of memory for the compact form");
           }
@@ -524,14 +614,14 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
         *out = r;
         return ECNE_OK;
       }
-      free(colp);
-      free(coefp);
-      free(clsp);
-      free(otherp);
-      free(termp);
-      free(seg32p);
+      big_free(colp);
+      big_free(coefp);
+      big_free(clsp);
+      big_free(otherp);
+      big_free(termp);
+      big_free(seg32p);
     }
-    free(segp);  // truncated file or repeated wires: the serial walk below reports / handles it
+    big_free(segp);  // truncated file or repeated wires: the serial walk below reports / handles it
   }
   std::vector<uint64_t> seg;
   seg.reserve(3 * (size_t)n_cons + 1);

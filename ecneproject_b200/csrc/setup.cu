@@ -1139,9 +1139,11 @@ UploadShard& upload_shard() {
   return u;
 }
 // host -> device copy of one array of the problem: whole, or this rank's slice + the all-gather of the ranks' slices
+// One array of the problem to the device.  Unsharded: the slices are only QUEUED on the staging pool (the arrays of a
+// problem cross back to back, no thread is started or joined per array) — put_done() before anything reads them.
 static cudaError_t put(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   UploadShard& U = upload_shard();
-  if (U.world <= 1 || !U.allgather || bytes < ((size_t)1 << 20)) return staged_h2d(dst, src, bytes, s);
+  if (U.world <= 1 || !U.allgather || bytes < ((size_t)1 << 20)) return staged_h2d_async(dst, src, bytes, s);
   const size_t slice = ((bytes + (size_t)U.world - 1) / (size_t)U.world + 255) & ~(size_t)255;
   const size_t off = (size_t)U.rank * slice;
   if (off < bytes) {
@@ -1150,6 +1152,7 @@ static cudaError_t put(void* dst, const void* src, size_t bytes, cudaStream_t s)
   }
   return U.allgather(dst, slice, s);
 }
+static cudaError_t put_done() { return staged_flush(); }
 
 uint64_t problem_nnz(const ecne_problem_t* p) {
   return p->seg_ptr ? p->seg_ptr[3 * p->n_rows] : p->seg_ptr32[3 * p->n_rows];
@@ -1174,18 +1177,36 @@ int problem_rows_ok(const ecne_problem_t* p, std::string& err) {
 int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_col, fr::u256* d_coef, Arena& tmp,
                 cudaStream_t s, std::string& err) {
   const uint64_t N = p->n_rows, nnz = problem_nnz(p);
+  static const bool prof = getenv("ECNE_HOST_PROF") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto done = [&]() {
+    const cudaError_t e = put_done();
+    if (prof)
+      fprintf(stderr, "[ecne dev] rows queued and handed to the stream in %.3f ms\n",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    return e;
+  };
+  // every array first (queued on the staging pool), then the kernels that expand them
+  struct FlushOnExit {  // (an error return must not leave workers reading the caller's arrays)
+    ~FlushOnExit() { staged_flush(); }
+  } flush_on_exit;
+  uint32_t* d_seg32 = nullptr;
   if (p->seg_ptr) {
     CK(put(d_seg, p->seg_ptr, (3 * N + 1) * 8, s));
   } else {
-    uint32_t* d_seg32;
     CK(tmp.alloc(&d_seg32, upload_padded<uint32_t>(3 * N + 1)));
     CK(put(d_seg32, p->seg_ptr32, (3 * N + 1) * 4, s));
-    k_widen_seg<<<(unsigned int)((3 * N + 1 + 255) / 256), 256, 0, s>>>(d_seg32, 3 * N + 1, d_seg);
   }
-  if (!nnz) return ECNE_OK;
+  if (!nnz) {
+    CK(done());
+    if (d_seg32) k_widen_seg<<<(unsigned int)((3 * N + 1 + 255) / 256), 256, 0, s>>>(d_seg32, 3 * N + 1, d_seg);
+    return ECNE_OK;
+  }
   CK(put(d_col, p->col, nnz * 4, s));
   if (p->coef) {
     CK(put(d_coef, p->coef, nnz * 32, s));
+    CK(done());
+    if (d_seg32) k_widen_seg<<<(unsigned int)((3 * N + 1 + 255) / 256), 256, 0, s>>>(d_seg32, 3 * N + 1, d_seg);
     return ECNE_OK;
   }
   const uint64_t n_other = p->n_coef_other;
@@ -1199,12 +1220,15 @@ int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_
   CK(tmp.alloc(&d_chk, 2));
   CK(cudaMemsetAsync(d_chk, 0, 2 * sizeof(unsigned int), s));
   CK(put(d_cls, p->coef_class, nnz, s));
-  k_expand_class<<<(unsigned int)((nnz + 255) / 256), 256, 0, s>>>(d_cls, nnz, d_coef, d_chk);  // (while the values cross)
   if (n_other) {
     CK(put(d_other, p->coef_other, n_other * 32, s));
     CK(put(d_term, p->coef_other_term, n_other * 4, s));
-    k_expand_other<<<(unsigned int)((n_other + 255) / 256), 256, 0, s>>>(d_other, d_term, n_other, nnz, d_cls, d_coef, d_chk);
   }
+  CK(done());
+  if (d_seg32) k_widen_seg<<<(unsigned int)((3 * N + 1 + 255) / 256), 256, 0, s>>>(d_seg32, 3 * N + 1, d_seg);
+  k_expand_class<<<(unsigned int)((nnz + 255) / 256), 256, 0, s>>>(d_cls, nnz, d_coef, d_chk);
+  if (n_other)
+    k_expand_other<<<(unsigned int)((n_other + 255) / 256), 256, 0, s>>>(d_other, d_term, n_other, nnz, d_cls, d_coef, d_chk);
   unsigned int chk[2] = {0, 0};
   CK(cudaMemcpyAsync(chk, d_chk, sizeof(chk), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));

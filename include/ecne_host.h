@@ -53,6 +53,10 @@ int ecne_read_r1cs(const char* path, ecne_r1cs_t** out);
 int ecne_read_r1cs_opts(const char* path, unsigned int flags, ecne_r1cs_t** out);
 int ecne_read_r1cs_mem(const uint8_t* buf, uint64_t len, ecne_r1cs_t** out);
 void ecne_r1cs_free(ecne_r1cs_t* r);
+/* The large arrays of freed systems are kept for the next read (up to ECNE_HOST_CACHE_MB megabytes, default 1024; 0 =
+ * keep nothing): a process that reads circuit after circuit writes into pages it already owns.  This returns them to
+ * the system. */
+void ecne_host_trim(void);
 
 /* The list of (name, inputs, outputs) "special constraints" (:357-384), CSR over specials. */
 typedef struct ecne_specials {

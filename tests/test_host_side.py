@@ -375,3 +375,26 @@ def test_compact_only_read_matches_the_full_read():
         assert np.array_equal(other.reshape(-1), lean.compact[1]) and np.array_equal(term, lean.compact[2])
         assert np.array_equal(lean.compact[3].astype(np.uint64), full.seg_ptr)
         assert (lean.known == full.known).all() and (lean.targets == full.targets).all() and lean.n_vars == full.n_vars
+
+
+def test_freed_arrays_are_recycled_and_trim_releases_them():
+    """include/ecne_host.h: the large arrays of a freed system are handed to the next read (same results, and the second
+    read of a file gets the first one's blocks back); ecne_host_trim() empties the cache."""
+    path = fixtures.path("secp256k1.r1cs")
+    lib = _abi.host_lib()
+    lib.ecne_host_trim.restype = None
+    a = api.readR1CS(path)
+    col0, seg0, coef0 = a.col.copy(), a.seg_ptr.copy(), a.coef.copy()
+    addr = a.col.ctypes.data
+    del a
+    import gc
+    gc.collect()
+    b = api.readR1CS(path)
+    assert np.array_equal(b.col, col0) and np.array_equal(b.seg_ptr, seg0) and np.array_equal(b.coef, coef0)
+    if b.nnz * 4 >= (4 << 20):          # (arrays below 4 MB are plain malloc)
+        assert b.col.ctypes.data == addr
+    del b
+    gc.collect()
+    lib.ecne_host_trim()
+    c = api.readR1CS(path)
+    assert np.array_equal(c.col, col0) and np.array_equal(c.coef, coef0)
