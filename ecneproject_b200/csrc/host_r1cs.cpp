@@ -368,6 +368,8 @@ static int read_r1cs_mem_impl(const uint8_t* arr, uint64_t len, ecne_r1cs_t** ou
             while (c < hi) {
               if (c + 4 > sec_end) return;
               const uint32_t n = rd32(arr + c);
+              __builtin_prefetch(arr + c + 512);  // (a dependent chain of loads: the next headers are a few lines ahead)
+              __builtin_prefetch(arr + c + 576);
               if (c + 4 + (uint64_t)n * 36 > sec_end) return;
               P.pos.push_back(c);
               terms += n ? n : 1;
@@ -734,11 +736,22 @@ extern "C" int ecne_read_r1cs_opts(const char* path, unsigned int flags, ecne_r1
     uint8_t none = 0;
     return ecne_read_r1cs_mem(&none, 0, out);
   }
+  const bool prof = getenv("ECNE_HOST_PROF") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!prof) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ecne host] read_r1cs   %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t0).count());
+    t0 = t;
+  };
   void* m = mmap(nullptr, sz, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
   close(fd);
   if (m == MAP_FAILED) return fail(ECNE_E_IO, std::string("cannot map ") + path);
+  lap("mmap (populate)");
   const int st_code = ecne_read_r1cs_mem((const uint8_t*)m, sz, out);
+  lap("parse (all stages)");
   munmap(m, sz);
+  lap("munmap");
   return st_code;
 }
 
