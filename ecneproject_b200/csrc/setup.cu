@@ -462,7 +462,9 @@ __global__ void k_classify_c3_long(Raw r, uint32_t* rflags, RowAux* aux, const u
   const uint32_t l = (uint32_t)(e - b);
   // (a form that has failed on one term is dead for the row: the others stop looking their exponents up)
   for (uint64_t t = b + threadIdx.x; t < e; t += blockDim.x) {
-    const bool dead1 = *(volatile unsigned int*)&s_dead1 != 0, dead2 = *(volatile unsigned int*)&s_dead2 != 0;
+    // (atomics on both sides: the flags are read while other threads may set them — only to stop early, the verdict is
+    // taken behind the barrier — and racecheck has nothing to report)
+    const bool dead1 = atomicOr(&s_dead1, 0u) != 0, dead2 = atomicOr(&s_dead2, 0u) != 0;
     if (dead1 && dead2) break;
     const fr::u256 c = r.coef[t];
     if (fr::is_one(c)) {
@@ -470,14 +472,14 @@ __global__ void k_classify_c3_long(Raw r, uint32_t* rflags, RowAux* aux, const u
       atomicMax(&s_k_one, r.col[t]);
     } else if (!dead1) {
       const int ex = pow2_lookup(tab, tab_n, fr::neg(c));
-      if (ex < 0 || (uint32_t)ex + 1 >= l || (atomicOr(m1 + (ex >> 5), 1u << (ex & 31)) & (1u << (ex & 31)))) s_dead1 = 1;
+      if (ex < 0 || (uint32_t)ex + 1 >= l || (atomicOr(m1 + (ex >> 5), 1u << (ex & 31)) & (1u << (ex & 31)))) atomicExch(&s_dead1, 1u);
     }
     if (fr::is_minus_one(c)) {
       atomicAdd(&s_mones, 1u);
       atomicMax(&s_k_mone, r.col[t]);
     } else if (!dead2) {
       const int ex = pow2_lookup(tab, tab_n, c);
-      if (ex < 0 || (uint32_t)ex + 1 >= l || (atomicOr(m2 + (ex >> 5), 1u << (ex & 31)) & (1u << (ex & 31)))) s_dead2 = 1;
+      if (ex < 0 || (uint32_t)ex + 1 >= l || (atomicOr(m2 + (ex >> 5), 1u << (ex & 31)) & (1u << (ex & 31)))) atomicExch(&s_dead2, 1u);
     }
   }
   __syncthreads();
