@@ -167,8 +167,10 @@ inline size_t upload_padded(size_t n) {
 }
 uint64_t problem_nnz(const ecne_problem_t* p);
 int problem_rows_ok(const ecne_problem_t* p, std::string& err);
+// (s_col / ev_col: when given, the wire ids — the largest array, needed last — cross on that stream behind the others and
+// `ev_col` is recorded there, so that the kernels that expand the coefficients run while they are still in flight)
 int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_col, fr::u256* d_coef, Arena& tmp,
-                cudaStream_t s, std::string& err);
+                cudaStream_t s, std::string& err, cudaStream_t s_col = nullptr, cudaEvent_t ev_col = nullptr);
 int dev_system_upload(const ecne_problem_t* p, DevSystem* S, cudaStream_t s, std::string& err);
 // `ready`: called after the trusted circuit has been prepared on the host and before the first kernel touches `S`
 // (the upload of the big system may still be running until then); returns an ecne_status.

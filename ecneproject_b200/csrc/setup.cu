@@ -1177,7 +1177,7 @@ int problem_rows_ok(const ecne_problem_t* p, std::string& err) {
 }
 
 int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_col, fr::u256* d_coef, Arena& tmp,
-                cudaStream_t s, std::string& err) {
+                cudaStream_t s, std::string& err, cudaStream_t s_col, cudaEvent_t ev_col) {
   const uint64_t N = p->n_rows, nnz = problem_nnz(p);
   static const bool prof = getenv("ECNE_HOST_PROF") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
@@ -1188,6 +1188,7 @@ int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return e;
   };
+  if (ev_col) CK(cudaEventRecord(ev_col, s));  // (recorded on every path: a problem without terms returns before the wire ids)
   // every array first (queued on the staging pool), then the kernels that expand them
   struct FlushOnExit {  // (an error return must not leave workers reading the caller's arrays)
     ~FlushOnExit() { staged_flush(); }
@@ -1204,10 +1205,20 @@ int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_
     if (d_seg32) k_widen_seg<<<(unsigned int)((3 * N + 1 + 255) / 256), 256, 0, s>>>(d_seg32, 3 * N + 1, d_seg);
     return ECNE_OK;
   }
-  CK(put(d_col, p->col, nnz * 4, s));
+  if (upload_shard().world > 1 || !ev_col) s_col = nullptr;  // (sharded uploads end in a collective: one stream)
+  // the wire ids go last, on their own stream when the caller has one: nothing needs them before the classification
+  auto put_col = [&]() -> cudaError_t {
+    if (!s_col) return put(d_col, p->col, nnz * 4, s);
+    cudaError_t e = cudaEventRecord(ev_col, s);  // (behind the arrays queued so far: an order, not a dependency)
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_col, ev_col, 0);
+    if (e == cudaSuccess) e = put(d_col, p->col, nnz * 4, s_col);
+    return e;
+  };
   if (p->coef) {
     CK(put(d_coef, p->coef, nnz * 32, s));
+    CK(put_col());
     CK(done());
+    if (s_col) CK(cudaEventRecord(ev_col, s_col));
     if (d_seg32) k_widen_seg<<<(unsigned int)((3 * N + 1 + 255) / 256), 256, 0, s>>>(d_seg32, 3 * N + 1, d_seg);
     return ECNE_OK;
   }
@@ -1226,7 +1237,9 @@ int upload_rows(const ecne_problem_t* p, unsigned long long* d_seg, uint32_t* d_
     CK(put(d_other, p->coef_other, n_other * 32, s));
     CK(put(d_term, p->coef_other_term, n_other * 4, s));
   }
+  CK(put_col());
   CK(done());
+  if (s_col) CK(cudaEventRecord(ev_col, s_col));
   if (d_seg32) k_widen_seg<<<(unsigned int)((3 * N + 1 + 255) / 256), 256, 0, s>>>(d_seg32, 3 * N + 1, d_seg);
   k_expand_class<<<(unsigned int)((nnz + 255) / 256), 256, 0, s>>>(d_cls, nnz, d_coef, d_chk);
   if (n_other)
@@ -1308,6 +1321,12 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   cudaEvent_t ev0 = evs.e[0], ev1 = evs.e[1], ev2 = evs.e[2];
   cudaEventRecord(ev0, s);
 
+  struct ColEvent {
+    cudaEvent_t e;
+    ColEvent() { cudaEventCreate(&e); }
+    ~ColEvent() { cudaEventDestroy(e); }
+  } col_ev;
+  bool col_on_side = false;
   // ---- H2D -------------------------------------------------------------------------------
   unsigned long long* d_seg64;
   uint32_t* d_col_raw;
@@ -1320,8 +1339,12 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     CK(tmp.alloc(&d_seg64, upload_padded<unsigned long long>(3 * N + 2)));
     CK(tmp.alloc(&d_col_raw, upload_padded<uint32_t>(nnz)));
     CK(tmp.alloc(&d_coef_raw, upload_padded<fr::u256>(nnz)));
-    const int st = upload_rows(p, d_seg64, d_col_raw, d_coef_raw, tmp, s, err);
+    // (the wire ids cross last, on the second side stream: the coefficients are expanded and the compaction offsets
+    // computed while they are in flight; the classification waits for `col_ev.e`)
+    col_on_side = R->side2 != nullptr;
+    const int st = upload_rows(p, d_seg64, d_col_raw, d_coef_raw, tmp, s, err, R->side2, col_on_side ? col_ev.e : nullptr);
     if (st != ECNE_OK) return st;
+    col_on_side = col_on_side && upload_shard().world <= 1;
   }
 
   sp_lap("upload of the rows");
@@ -1439,6 +1462,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   // ---- classify -------------------------------------------------------------------------------
   if (N) k_classify_long<<<592, 256, 0, sb>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long, d_longc);
   cudaEventRecord(pre_ev.b, sb);
+  if (col_on_side) cudaStreamWaitEvent(s, col_ev.e, 0);  // the wire ids (k_classify_long runs on the stream that carried them)
   if (N) k_classify<<<nb(N, 128), 128, 0, s>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long, d_longc);
   if (sa != s) cudaStreamWaitEvent(s, pre_ev.a, 0);
   if (sb != s) cudaStreamWaitEvent(s, pre_ev.b, 0);
@@ -1810,8 +1834,15 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   float ms = 0;
   cudaEventElapsedTime(&ms, ev0, ev1);
   R->ms_h2d = ms;
-  cudaEventElapsedTime(&ms, ev1, ev2);
-  R->ms_classify = ms;
+  if (col_on_side) {  // (the last array of the upload finished on the side stream; kernels were running by then)
+    float ms_col = 0;
+    if (cudaEventElapsedTime(&ms_col, ev0, col_ev.e) != cudaSuccess)
+      cudaGetLastError();
+    else if (ms_col > R->ms_h2d)
+      R->ms_h2d = ms_col;
+  }
+  cudaEventElapsedTime(&ms, ev0, ev2);
+  R->ms_classify = ms - R->ms_h2d;
   CK(cudaGetLastError());
   if (d.r0 != 0) {
     err = "internal: rank of 0 is not 0";
