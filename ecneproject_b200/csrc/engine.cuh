@@ -163,6 +163,7 @@ struct Dev {
   const uint32_t* sp_out_ptr;
   const uint32_t* sp_out;
   uint8_t* sp_solved;
+  uint32_t* sp_tag;  // [V + 2] lowest index of the specials that set the wire in the running P0 pass (0xffffffff: none)
   const uint32_t* known;
   const uint32_t* targets;
   // wire -> rows index (every wire but the constant wire 1): the frontier of a sparse round

@@ -448,41 +448,120 @@ __device__ __forceinline__ void specials_cache_fill(const Dev& d, SpecialsCache&
   __syncthreads();
 }
 
+#define SP_TAG_NONE 0xffffffffu
+// Lists too long for block 0's shared-memory copy (SPC_N specials): the fired set of a pass is computed by ROUNDS instead
+// of one firing at a time.  In the reference's walk special k fires iff every input was unique before the pass or was
+// set in it by a special with a LOWER index: the warps judge every open special in parallel — an input set during this
+// pass carries the lowest index that set it (sp_tag) and counts for later specials only —, all that are ready fire
+// together, and the judging repeats until nothing is.  The rounds are as many as the longest chain of specials feeding
+// each other inside one pass (one or two), not as many as fire (16 tiles of ecdsa: 400 specials, 16 ready at a time:
+// 5.9 M of 24.7 M cycles went into re-judging the list after every single firing).  sp_solved: 1 fired in an earlier
+// pass, 2 in this one, 3 ready in this round.
+__device__ __noinline__ void phase_p0_rounds(int pl) {
+  const Dev& d = c_dev;
+  __shared__ unsigned int s_ready;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t n = d.n_specials;
+  bool fired_any = false;
+  for (;;) {
+    if (threadIdx.x == 0) s_ready = 0;
+    __syncthreads();
+    for (uint32_t s = warp; s < n; s += nwarps) {
+      if (__ldcg(d.sp_solved + s)) continue;
+      const uint32_t k0 = d.sp_in_ptr[s], k1 = d.sp_in_ptr[s + 1];
+      bool ok = true;
+      for (uint32_t k = k0 + lane; k < k1; k += 32) {
+        const uint32_t w = d.sp_in[k];
+        if (!(ld_flag_cg(d.F[1], w) & WF_U)) {
+          ok = false;
+        } else if (fired_any) {
+          const uint32_t t = __ldcg(d.sp_tag + w);
+          ok &= t == SP_TAG_NONE || t < s;
+        }
+      }
+      if (__all_sync(0xffffffffu, ok) && lane == 0) {
+        d.sp_solved[s] = 3;
+        atomicAdd(&s_ready, 1u);
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (s_ready == 0) break;
+    fired_any = true;
+    // the outputs that are not unique yet take the lowest index among the specials that set them now ...
+    for (uint32_t s = warp; s < n; s += nwarps) {
+      if (__ldcg(d.sp_solved + s) != 3) continue;
+      for (uint32_t k = d.sp_out_ptr[s] + lane; k < d.sp_out_ptr[s + 1]; k += 32) {
+        const uint32_t w = d.sp_out[k];
+        if (!(ld_flag_cg(d.F[1], w) & WF_U)) atomicMin(d.sp_tag + w, s);
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    // ... and are set
+    for (uint32_t s = warp; s < n; s += nwarps) {
+      if (__ldcg(d.sp_solved + s) != 3) continue;
+      for (uint32_t k = d.sp_out_ptr[s] + lane; k < d.sp_out_ptr[s + 1]; k += 32) {
+        const uint32_t w = d.sp_out[k];
+        const uint32_t nw = or_flag(d.F[1], w, WF_U | WF_K);
+        or_flag(d.F[0], w, WF_U | WF_K);
+        if (nw) log_rec(d, pl, w, WF_U | WF_K);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        d.sp_solved[s] = 2;
+        atomicAdd(&d.st->prog, 1u);  // successful_steps += 1 (:731)
+      }
+    }
+    __threadfence();
+    __syncthreads();
+  }
+  if (fired_any) {  // end of the pass: what fired in it is simply "fired", its marks on the wires are taken back
+    for (uint32_t s = warp; s < n; s += nwarps) {
+      if (__ldcg(d.sp_solved + s) != 2) continue;
+      for (uint32_t k = d.sp_out_ptr[s] + lane; k < d.sp_out_ptr[s + 1]; k += 32) d.sp_tag[d.sp_out[k]] = SP_TAG_NONE;
+      __syncwarp();
+      if (lane == 0) d.sp_solved[s] = 1;
+    }
+    __threadfence();
+    __syncthreads();
+  }
+}
 __device__ __noinline__ void phase_p0(const Dev&, int pl, SpecialsCache& sc) {
   const Dev& d = c_dev;
   // The reference walks the specials in list order, so a special sees the outputs of an earlier one
   // that fired in the same pass (and not those of a later one).  Same here: the warps judge every open
   // special from `start` on against the current state in parallel, the lowest one that can fire fires,
-  // and the search resumes behind it.  The wire lists are read from shared memory when they fit.
+  // and the search resumes behind it — with the wire lists in shared memory; longer lists: phase_p0_rounds.
   __shared__ unsigned int s_first;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const bool cached = sc.ok != 0;
+  if (!cached && d.n_specials) phase_p0_rounds(pl);
   uint32_t start = 0;
-  while (start < d.n_specials) {
+  while (cached && start < d.n_specials) {
     if (threadIdx.x == 0) s_first = 0xffffffffu;
     __syncthreads();
     for (uint32_t s = start + warp; s < d.n_specials; s += nwarps) {
-      if (cached ? sc.solved[s] : __ldcg(d.sp_solved + s)) continue;
-      const uint32_t k0 = cached ? sc.in_ptr[s] : d.sp_in_ptr[s], k1 = cached ? sc.in_ptr[s + 1] : d.sp_in_ptr[s + 1];
+      if (sc.solved[s]) continue;
+      const uint32_t k0 = sc.in_ptr[s], k1 = sc.in_ptr[s + 1];
       bool ok = true;
-      for (uint32_t k = k0 + lane; k < k1; k += 32)
-        ok &= (ld_flag_cg(d.F[1], cached ? sc.in[k] : d.sp_in[k]) & WF_U) != 0;
+      for (uint32_t k = k0 + lane; k < k1; k += 32) ok &= (ld_flag_cg(d.F[1], sc.in[k]) & WF_U) != 0;
       if (__all_sync(0xffffffffu, ok) && lane == 0) atomicMin(&s_first, s);
     }
     __syncthreads();
     const uint32_t f = s_first;
     __syncthreads();
     if (f == 0xffffffffu) break;
-    const uint32_t o0 = cached ? sc.out_ptr[f] : d.sp_out_ptr[f], o1 = cached ? sc.out_ptr[f + 1] : d.sp_out_ptr[f + 1];
+    const uint32_t o0 = sc.out_ptr[f], o1 = sc.out_ptr[f + 1];
     for (uint32_t k = o0 + threadIdx.x; k < o1; k += blockDim.x) {
-      const uint32_t w = cached ? sc.out[k] : d.sp_out[k];
+      const uint32_t w = sc.out[k];
       const uint32_t nw = or_flag(d.F[1], w, WF_U | WF_K);
       or_flag(d.F[0], w, WF_U | WF_K);
       if (nw) log_rec(d, pl, w, WF_U | WF_K);
     }
     if (threadIdx.x == 0) {
       d.sp_solved[f] = 1;
-      if (cached) sc.solved[f] = 1;
+      sc.solved[f] = 1;
       atomicAdd(&d.st->prog, 1u);  // successful_steps += 1 (:731)
     }
     __threadfence();
@@ -2537,6 +2616,7 @@ __global__ void k_reset_all(Dev d) {
     d.long_p2[i] = z;
   }
   if (i < d.n_specials) d.sp_solved[i] = 0;
+  if (d.n_specials && i <= d.V + 1) d.sp_tag[i] = SP_TAG_NONE;  // (a solve that stopped on an error inside a pass leaves marks)
   if (i < 8) {
     d.rec_count[i] = 0;
     d.dcnt[i] = 0;

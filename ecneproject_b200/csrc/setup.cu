@@ -196,7 +196,7 @@ __global__ void k_longc(Raw r, Counters* cnt, uint32_t* longc) {
   const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row < r.N && r.seg[3ull * row + 3] - r.seg[3ull * row + 2] > CLASSIFY_LONG_C) longc[atomicAdd(&cnt->n_longc, 1u)] = row;
 }
-__global__ void k_classify(Raw r, uint32_t* rflags, RowAux* aux, Counters* cnt, uint32_t* c3_long, uint32_t* longc) {
+__global__ void k_classify(Raw r, uint32_t* rflags, RowAux* aux, Counters* cnt, uint32_t* c3_long) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= r.N) return;
   if (r.seg[3ull * row + 3] - r.seg[3ull * row + 2] > CLASSIFY_LONG_C) return;  // k_classify_long (listed by k_longc)
@@ -821,11 +821,6 @@ __global__ void k_consts(fr::u256* cand) {
     cand[k] = fr::pow2m1((int)k);
   else if (k == 254)
     fr::sub_cc(cand[k], fr::modulus(), fr::make_u256(1, 0, 0, 0));
-}
-__global__ void k_limb(const fr::u256* cand, const uint32_t* idx, uint32_t n, int limb,
-                       unsigned long long* keys) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = cand[idx[i]].v[limb];
 }
 __global__ void k_iota(uint32_t* idx, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1463,7 +1458,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   if (N) k_classify_long<<<592, 256, 0, sb>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long, d_longc);
   cudaEventRecord(pre_ev.b, sb);
   if (col_on_side) cudaStreamWaitEvent(s, col_ev.e, 0);  // the wire ids (k_classify_long runs on the stream that carried them)
-  if (N) k_classify<<<nb(N, 128), 128, 0, s>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long, d_longc);
+  if (N) k_classify<<<nb(N, 128), 128, 0, s>>>(raw, d_rflags, d_aux, d_cnt, d_c3_long);
   if (sa != s) cudaStreamWaitEvent(s, pre_ev.a, 0);
   if (sb != s) cudaStreamWaitEvent(s, pre_ev.b, 0);
   Counters cnt;
@@ -1592,16 +1587,12 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   k_consts<<<1, 256, 0, s2>>>(d_tvals);
   if (N) k_values<<<nb(N, 128), 128, 0, s2>>>(raw, d_rflags, d_aux, d_roots, d_tvals, d_next, d_next + 1);
   const uint32_t nc = N_CONST + cnt.n2b;
-  uint32_t *d_idx, *d_idx2, *d_flag, *d_incl, *d_rank_of;
-  unsigned long long *d_k1, *d_k2;
+  uint32_t *d_idx, *d_flag, *d_incl, *d_rank_of;
   fr::u256* d_table;
   CK(tmp.alloc(&d_idx, nc));
-  CK(tmp.alloc(&d_idx2, nc));
   CK(tmp.alloc(&d_flag, nc));
   CK(tmp.alloc(&d_incl, nc));
   CK(tmp.alloc(&d_rank_of, nc));
-  CK(tmp.alloc(&d_k1, nc));
-  CK(tmp.alloc(&d_k2, nc));
   CK(A.alloc(&d_table, nc));
   void* d_ms = nullptr;
   size_t d_ms_bytes = 0;
@@ -1752,6 +1743,8 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(A.alloc(&d.abz_claim, V + 1));
   CK(A.alloc(&d.solved, N + 2));
   CK(A.alloc(&d.sp_solved, n_sp));
+  CK(A.alloc(&d.sp_tag, V + 2));
+  CK(cudaMemsetAsync(d.sp_tag, 0xff, (V + 2) * sizeof(uint32_t), s));
   d.rec_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2 * V, nnz) + 4096, 0x7ffffff0ULL);
   for (int l = 0; l < 5; ++l) CK(A.alloc(&d.recs[l], d.rec_cap));
   CK(A.alloc(&d.rec_count, 8));

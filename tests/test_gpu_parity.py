@@ -200,6 +200,49 @@ def test_nodsu_error():
     assert st == ost == _abi.ECNE_E_BOUNDS
 
 
+@pytest.mark.parametrize("n_chain", [5, 40, 150])
+def test_specials_fire_in_list_order_within_one_pass(n_chain):
+    """P0 (:718-747) walks the special constraints in list order: a special sees the outputs of an EARLIER one that fired
+    in the same pass, not those of a later one.  The engine judges all of them in parallel and fires by rounds (inputs
+    set during the pass count for specials with a higher index only); the outer rounds it needs are the reference's: a
+    chain listed in order closes in one pass, the same chain listed backwards takes a pass per link — and several
+    independent chains, interleaved, advance together.  (150 specials do not fit the shared-memory copy of the lists.)"""
+    base = 10
+    def chain(first_wire, n):   # special j: wires first+2j, first+2j+1 -> first+2j+2, first+2j+3
+        return [("Generic%d" % j, [first_wire + 2 * j, first_wire + 2 * j + 1], [first_wire + 2 * j + 2, first_wire + 2 * j + 3])
+                for j in range(n)]
+    n_vars = base + 2 * n_chain + 4 + 3 * (2 * n_chain + 8)
+    rows = [({2: 1}, {3: 1}, {4: 1})]
+    fwd = chain(base, n_chain)
+    last_out = base + 2 * n_chain + 1
+    for order, name in ((fwd, "forward"), (fwd[::-1], "backward")):
+        m = MiniR1CS(rows, n_vars=n_vars, known=[1, 2, 3, base, base + 1], targets=[last_out])
+        st, g, ost, o = both(m, order)
+        assert st == ost == 0, (name, api._engine().ecne_last_error())
+        assert g.unique_bytes() == o.unique_bytes() and bool(g.c.verdict) == bool(o.c.verdict) == True, name
+        # (the engine runs the next round's P0 at the end of a round and stops a round earlier than the reference
+        # when nothing is left: its count is the reference's or one less)
+        assert o.c.outer_rounds == (2 if name == "forward" else n_chain + 1)
+        assert g.c.outer_rounds in (o.c.outer_rounds - 1, o.c.outer_rounds), (name, g.c.outer_rounds, o.c.outer_rounds)
+    # three chains side by side (three specials ready at once in every round), listed forward / backward / shuffled
+    offs = [base + (2 * n_chain + 8) * (c + 1) for c in range(3)]
+    chains = [chain(o_, n_chain) for o_ in offs]
+    inter = [sp for trio in zip(*chains) for sp in trio]
+    rng = np.random.default_rng(n_chain)
+    shuffled = [inter[i] for i in rng.permutation(len(inter))]
+    known = [1, 2, 3] + [w for o_ in offs for w in (o_, o_ + 1)]
+    targets = [o_ + 2 * n_chain + 1 for o_ in offs]
+    res = []
+    for order in (inter, inter[::-1], shuffled):
+        m = MiniR1CS(rows, n_vars=n_vars, known=known, targets=targets)
+        st, g, ost, o = both(m, order)
+        assert st == ost == 0
+        assert g.unique_bytes() == o.unique_bytes() and bool(g.c.verdict) == bool(o.c.verdict) == True
+        assert g.c.outer_rounds in (o.c.outer_rounds - 1, o.c.outer_rounds), (g.c.outer_rounds, o.c.outer_rounds)
+        res.append(g.c.outer_rounds)
+    assert res[0] <= 2 and res[1] >= n_chain
+
+
 def test_bad_wire_is_bounds_error():
     m = MiniR1CS([({2: 1}, {3: 1}, {9: 1})], n_vars=4, known=[1, 2, 3], targets=[4])
     st, _, ost, _ = both(m)
