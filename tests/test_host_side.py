@@ -398,3 +398,52 @@ def test_freed_arrays_are_recycled_and_trim_releases_them():
     lib.ecne_host_trim()
     c = api.readR1CS(path)
     assert np.array_equal(c.col, col0) and np.array_equal(c.coef, coef0)
+
+
+def test_loader_range_guesses_do_not_fall_for_periodic_or_giant_trails(tmp_path):
+    """The parallel offset walk guesses the first header of every byte range and proves the guess afterwards; a wrong
+    guess is repaired by walking serially (slow, never wrong).  Two families of false trails that pass 64 plausible
+    headers: (1) in a run of one-term forms with coefficient 1 (a * b = c rows) the chain that starts 8 bytes late reads
+    "one term, wire 0" for ever; (2) a coefficient whose low word reads as a term count of tens of thousands and lands
+    on a true header far away.  Both must be rejected up front: with any number of ranges the arrays are the serial
+    ones AND (almost) nothing is walked serially to repair guesses — ecdsa.r1cs lost a sixteenth of its forms to (2)."""
+    import subprocess, sys, textwrap
+    n_wires = 200000
+    rows = []
+    for i in range(100000):
+        a, b, c = 1 + (3 * i) % (n_wires - 1), 1 + (3 * i + 1) % (n_wires - 1), 1 + (3 * i + 2) % (n_wires - 1)
+        if i % 500 == 499:    # family (2): low word 100 000 = "100 000 terms" = 3.6 MB ahead
+            rows.append(([(a, 100000 + (1 << 64))], [(b, 1)], [(c, 1)]))
+        else:                 # family (1)
+            rows.append(([(a, 1)], [(b, 1)], [(c, 1)]))
+    path = tmp_path / "trails.r1cs"
+    path.write_bytes(_mk_r1cs(rows, n_wires=n_wires))
+    ref = None
+    for ranges in ("2", "5", "16", "37", "128"):
+        code = textwrap.dedent(f"""
+            import sys, hashlib
+            sys.path.insert(0, {str(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))!r})
+            from ecneproject_b200 import api
+            r = api.readR1CS({str(path)!r})
+            h = hashlib.sha256(r.seg_ptr.tobytes() + r.col.tobytes() + r.coef.tobytes()).hexdigest()
+            print("SHA", h, r.n_rows, r.nnz)
+        """)
+        env = dict(os.environ, ECNE_HOST_WALK_RANGES=ranges, ECNE_HOST_PROF="1")
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        sha = [l for l in out.stdout.splitlines() if l.startswith("SHA")][0]
+        ref = ref or sha
+        assert sha == ref, ranges
+        line = [l for l in out.stderr.splitlines() if "forms walked serially" in l]
+        assert line and "proof ok" in line[0], out.stderr[-2000:]
+        repaired = int(re.search(r"(\d+) forms walked serially", line[0]).group(1))
+        assert repaired < 2000, (ranges, line[0])      # (a whole range would be 300 000 / ranges)
+    r = api.readR1CS(str(path))
+    assert r.n_rows == 100000 and r.nnz == 300000
+    want, _, _, _ = py_read_r1cs(str(path))
+    col, seg = r.col.tolist(), r.seg_ptr.tolist()
+    raw = np.ascontiguousarray(r.coef).view(np.uint8).reshape(-1, 32)
+    for i in list(range(0, 100000, 997)) + [499, 999, 99999]:
+        for f, d in enumerate(want[i]):
+            got = {col[k]: int.from_bytes(raw[k].tobytes(), "little") for k in range(seg[3 * i + f], seg[3 * i + f + 1])}
+            assert got == d, (i, f)
