@@ -980,11 +980,11 @@ __global__ void k_ss_scatter(const fr::u256* cand, uint32_t n, const uint32_t* b
 }
 // one block per bucket: sorted indices of the bucket's values into idx[starts[b] ...)
 __global__ void k_ss_bucket(const fr::u256* val2, const uint32_t* gi2, const uint32_t* starts, uint32_t* perm_scratch,
-                            uint32_t* idx) {
+                            uint32_t* idx, uint32_t cap) {  // cap <= SS_BUCKET_CAP (smaller only to test the global path)
   extern __shared__ unsigned long long ss_smem[];
   const uint32_t lo = starts[blockIdx.x], n = starts[blockIdx.x + 1] - lo;
   if (n == 0) return;
-  if (n <= SS_BUCKET_CAP) {
+  if (n <= cap) {
     LimbsSoA val;
     val.carve(ss_smem, SS_BUCKET_CAP);
     unsigned long long* key = ss_smem + 4 * (size_t)SS_BUCKET_CAP;
@@ -1596,9 +1596,12 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
   CK(A.alloc(&d_table, nc));
   void* d_ms = nullptr;
   size_t d_ms_bytes = 0;
-  const char* ss_env = getenv("ECNE_SAMPLE_SORT");  // testing knob: 0 = always the library sort, 1 = sample sort from 1024 values on
+  // testing knob: 0 = always the library sort, 1 = sample sort from 1024 values on, 2 = ... and buckets of more than 16
+  // values take the global-memory path of the bucket sort
+  const char* ss_env = getenv("ECNE_SAMPLE_SORT");
   const bool ss_off = ss_env && atoi(ss_env) == 0;
-  const uint32_t ss_min = ss_env && atoi(ss_env) == 1 ? 1024u : SS_MIN;
+  const uint32_t ss_min = ss_env && atoi(ss_env) >= 1 ? 1024u : SS_MIN;
+  const uint32_t ss_cap = ss_env && atoi(ss_env) == 2 ? 16u : SS_BUCKET_CAP;
   if (!ss_off && nc >= ss_min && nc <= SS_MAX) {
     // sample sort (see k_ss_*): 5 launches, ~40 us for ecdsa's 160 k values
     uint32_t n_b = 64;
@@ -1626,7 +1629,7 @@ int build_resident(const ecne_problem_t* p, Resident* R, std::string& err, const
     k_ss_count<<<nb(nc, 256), 256, sm_count, s2>>>(d_tvals, nc, d_split, n_b, d_bkt, d_slot, d_counts);
     k_ss_starts<<<1, 1024, 0, s2>>>(d_counts, n_b, d_starts);
     k_ss_scatter<<<nb(nc, 256), 256, 0, s2>>>(d_tvals, nc, d_bkt, d_slot, d_starts, d_val2, d_gi2);
-    k_ss_bucket<<<n_b, 512, sm_bucket, s2>>>(d_val2, d_gi2, d_starts, d_slot, d_idx);
+    k_ss_bucket<<<n_b, 512, sm_bucket, s2>>>(d_val2, d_gi2, d_starts, d_slot, d_idx, ss_cap);
     size_t need = 0;  // scratch of the scan below
     cub::DeviceScan::InclusiveSum((void*)nullptr, need, d_flag, d_incl, (int)nc, s2);
     need = std::max<size_t>(need, (size_t)1 << 20);

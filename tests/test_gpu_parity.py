@@ -665,7 +665,7 @@ def test_long_rows_whose_terms_are_not_in_weight_order(nbits, zeros):
 def test_sample_sort_of_the_bound_values_gives_the_library_sorts_ranks(monkeypatch):
     """The bound-value table (distinct candidate values in field order, ranks stored per row) is built by a sample sort
     between 16 k and 512 k values and by cub's merge sort outside; ECNE_SAMPLE_SORT=1 lowers the threshold to 1024 values,
-    =0 switches it off.  Same complete state either way, on systems with thousands of distinct constants and with one
+    =2 also sends every bucket of more than 16 values through the bucket sort's global-memory path, =0 switches it off.  Same complete state either way, on systems with thousands of distinct constants and with one
     constant repeated thousands of times (ties ordered by index: no bucket overflows)."""
     rng = np.random.default_rng(5)
     for distinct in (True, False):
@@ -677,14 +677,15 @@ def test_sample_sort_of_the_bound_values_gives_the_library_sorts_ranks(monkeypat
         rows.append(({}, {}, {2: 1, 3: -1, 4: -1}))                # out = x_0 + x_1
         m = MiniR1CS(rows, n_vars=3 + n, known=[1], targets=[2])
         res = []
-        for knob in ("0", "1"):
+        for knob in ("0", "1", "2"):      # (2: buckets beyond 16 values are sorted in global memory — the overflow path)
             monkeypatch.setenv("ECNE_SAMPLE_SORT", knob)
             st, g, ost, o = both(m)
             assert st == ost == 0, api._engine().ecne_last_error()
             assert g.unique_bytes() == o.unique_bytes()
             assert np.array_equal(g.lb, o.lb) and np.array_equal(g.ub, o.ub)
             res.append((g.lb.copy(), g.ub.copy(), g.unique_bytes()))
-        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]
+        for other in res[1:]:
+            assert np.array_equal(res[0][0], other[0]) and np.array_equal(res[0][1], other[1]) and res[0][2] == other[2]
 
 
 def test_bound_overwrite_deviation_is_pinned():
