@@ -149,9 +149,9 @@ def test_resident_solve_is_repeatable():
 
 
 # ---- error behaviour: the exception classes of the reference, as status codes ---------------------
-def both(mini, specials=(), secp=False):
+def both(mini, specials=(), secp=False, compact=False):
     lib = api._engine()
-    ph = api.ProblemHandle(mini, list(specials), mini.known, mini.targets, mini.n_vars, secp)
+    ph = api.ProblemHandle(mini, list(specials), mini.known, mini.targets, mini.n_vars, secp, compact=compact)
     res = api.SolveResult(mini.n_vars, full_state=True)
     st = lib.ecne_solve(C.byref(ph.c), C.byref(res.c))
     try:
@@ -654,8 +654,28 @@ def test_long_rows_whose_terms_are_not_in_weight_order(nbits, zeros):
     rows.append(({}, {}, c1))
     rows.append(({}, {}, c2))
     for known in ([1, out], [1]):
-        m = MiniR1CS(rows, n_vars=dead, known=known, targets=[extra])
-        st, g, ost, o = both(m)
+        for compact in (False, True):
+            m = MiniR1CS(rows, n_vars=dead, known=known, targets=[extra])
+            st, g, ost, o = both(m, compact=compact)
+            assert st == ost == 0, api._engine().ecne_last_error()
+            assert g.unique_bytes() == o.unique_bytes() and g.known_bytes() == o.known_bytes()
+            assert np.array_equal(g.lb, o.lb) and np.array_equal(g.ub, o.ub)
+            assert bool(g.c.verdict) == bool(o.c.verdict)
+
+
+@pytest.mark.parametrize("n_zero", [10, 70, 300])
+def test_short_row_with_a_long_run_of_stored_zero_terms(n_zero):
+    """A row with few kept terms is laid out by one thread (k_layout) however long its STORED segments are: explicit
+    zero coefficients (ParseR1CS.jl:113-115 stores them) do not count towards the row's length class.  A linear row
+    x - y + 0*z_1 + ... + 0*z_n = 0 (Case 4a once x is known) and a bit pattern 4*b2 + 2*b1 + b0 - v = 0 with zeros in
+    between, whose C terms must still come out in weight order."""
+    zs = list(range(20, 20 + n_zero))
+    rows = [({}, {}, {2: 1, 3: -1, **{z: 0 for z in zs}}),
+            ({4: 1}, {4: 1, 1: -1}, {}), ({5: 1}, {5: 1, 1: -1}, {}), ({6: 1}, {6: 1, 1: -1}, {}),
+            ({}, {}, {6: 4, **{z: 0 for z in zs[: n_zero // 2]}, 5: 2, 4: 1, **{z: 0 for z in zs[n_zero // 2:]}, 7: -1})]
+    for known, compact in (([1, 2, 7], False), ([1, 2, 7], True), ([1, 3], False), ([1], True)):
+        m = MiniR1CS(rows, n_vars=20 + n_zero, known=known, targets=[3, 4])
+        st, g, ost, o = both(m, compact=compact)
         assert st == ost == 0, api._engine().ecne_last_error()
         assert g.unique_bytes() == o.unique_bytes() and g.known_bytes() == o.known_bytes()
         assert np.array_equal(g.lb, o.lb) and np.array_equal(g.ub, o.ub)
